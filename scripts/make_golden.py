@@ -1,0 +1,167 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (build container only).
+
+Imports lbasicsr from /root/reference (read-only; needs the version stub of SURVEY.md appendix E),
+loads oracle/state_dict_fixture.make_state_dict(seed) with strict=True (pins the 791-key layout),
+runs the reference forward on seeded inputs with hooks on the stage modules, checks the oracle
+restatement against it, and writes compact golden vectors that travel to the GPU box.
+
+    python scripts/make_golden.py            # rewrites tests/golden/
+"""
+import hashlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+
+from oracle import savsr_oracle as O                      # noqa: E402
+from oracle.state_dict_fixture import make_input, make_state_dict, state_dict_spec  # noqa: E402
+
+NETWORK_G = dict(type="SAVSR", num_in_ch=3, num_feat=64, num_frame=7, slid_win=3, fusion_win=5,
+                 interval=0, w1_num_block=4, w2_num_block=2, n_resgroups=4, n_resblocks=8,
+                 center_frame_idx=None)
+
+CASES = [  # name, b, h, w, scale, sd_seed, in_seed
+    ("x2_16x20", 1, 16, 20, (2, 2), 0, 1234),
+    ("x4_16x16", 1, 16, 16, (4, 4), 0, 1235),
+    ("x1p5x4_13x15", 1, 13, 15, (1.5, 4), 1, 1236),       # odd sizes -> pad_spatial + crop
+    ("x2p7_b2_12x14", 2, 12, 14, (2.7, 2.7), 1, 1237),    # b > 1 -> grouped OSA-Conv
+    ("x3_10x12", 1, 10, 12, (3, 3), 2, 1238),             # odd integer scale (floor ambiguity, A.3)
+]
+
+
+def load_reference():
+    sys.path.insert(0, REF)
+    v = types.ModuleType("lbasicsr.version")
+    v.__version__, v.__gitsha__, v.version_info = "0.1.1", "unknown", (0, 1, 1)
+    sys.modules["lbasicsr.version"] = v
+    import lbasicsr  # noqa: F401
+    from lbasicsr.archs import build_network
+    import lbasicsr.archs.savsr_arch as ref_arch
+    return build_network, ref_arch
+
+
+def probe_summary(t: torch.Tensor) -> dict:
+    t = t.detach().float().contiguous()
+    flat = t.flatten()
+    idx = torch.linspace(0, flat.numel() - 1, steps=min(257, flat.numel())).long()
+    return dict(shape=np.array(t.shape, dtype=np.int64), mean=np.float64(flat.double().mean()),
+                std=np.float64(flat.double().std()), absmax=np.float64(flat.abs().max()),
+                sample=flat[idx].numpy().copy())
+
+
+def main():
+    build_network, ref_arch = load_reference()
+    torch.set_num_threads(os.cpu_count())
+    outdir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(outdir, exist_ok=True)
+
+    # --- survey fingerprint of the default-init reference -------------
+    torch.manual_seed(0)
+    net0 = build_network(dict(NETWORK_G)).eval()
+    psum = sum(float(p.double().sum()) for p in net0.parameters())
+    print(f"default-init fingerprint: sum(params) = {psum:.6f}  (survey: 466.810371)")
+    sd0 = {k: v.detach().clone() for k, v in net0.state_dict().items()}
+    spec = state_dict_spec()
+    assert [k for k, _, _ in spec] == list(sd0.keys()), "fixture key order differs from the reference"
+    for k, shp, _ in spec:
+        assert tuple(sd0[k].shape) == tuple(shp), (k, sd0[k].shape, shp)
+    print(f"state_dict layout pinned: {len(spec)} keys, order and shapes identical to the reference")
+    x0 = make_input(1, 64, 64, 1234)
+    net0.set_scale((2, 2))
+    with torch.no_grad():
+        y_ref0 = net0(x0)
+        y_or0 = O.forward(sd0, x0, (2, 2))
+    print(f"cfg1 default init: ref mean {float(y_ref0.mean()):.8f} (survey 0.45701084)  "
+          f"oracle-vs-ref max-abs {float((y_ref0 - y_or0).abs().max()):.3e}")
+    cfg1 = dict(out_mean=np.float64(y_ref0.double().mean()), out_std=np.float64(y_ref0.double().std()),
+                y0000=np.float32(y_ref0[0, 0, 0, 0]), param_sum=np.float64(psum),
+                oracle_maxabs=np.float64((y_ref0 - y_or0).abs().max()))
+    np.savez_compressed(os.path.join(outdir, "cfg1_default_init_fingerprint.npz"), **cfg1)
+
+    net = build_network(dict(NETWORK_G)).eval()
+    for name, b, h, w, scale, sd_seed, in_seed in CASES:
+        sd = make_state_dict(sd_seed)
+        net.load_state_dict(sd, strict=True)
+        net.set_scale(scale)
+        x = make_input(b, h, w, in_seed)
+        probes = {}
+        hooks = []
+
+        def keep(key, pick=lambda o: o):
+            def fn(_m, _i, o):
+                probes[key] = pick(o).detach().clone()
+            return fn
+        hooks.append(net.f2p_win.register_forward_hook(keep("f2p_last")))
+        hooks.append(net.p2f_win.register_forward_hook(keep("p2f_last")))
+        hooks.append(net.h_win.register_forward_hook(keep("h_win", lambda o: o[0][0])))
+        hooks.append(net.h_win_act.register_forward_hook(keep("align")))
+        for i in range(4):
+            hooks.append(net.RG[i].register_forward_hook(keep(f"rg{i}")))
+            hooks.append(net.adapt[i].register_forward_hook(keep(f"adaptmod{i}")))
+        hooks.append(net.conv_last.register_forward_hook(keep("conv_last")))
+        hooks.append(net.upsample.register_forward_hook(keep("satu_out")))
+        hooks.append(net.tail.register_forward_hook(keep("tail")))
+        hooks.append(net.upsample.body.register_forward_pre_hook(
+            lambda _m, i: probes.__setitem__("satu_mlp_input", i[0].detach().clone())))
+        hooks.append(net.upsample.offset.register_forward_hook(keep("satu_offset")))
+        hooks.append(net.upsample.st_offset.register_forward_hook(keep("satu_st_offset")))
+        hooks.append(net.upsample.routing.register_forward_hook(keep("satu_routing")))
+        grids = []
+        orig_gs = ref_arch.F.grid_sample
+
+        def spy(inp, grid, *a, **k):
+            grids.append(grid.detach().clone())
+            return orig_gs(inp, grid, *a, **k)
+        ref_arch.F.grid_sample = spy
+        try:
+            with torch.no_grad():
+                y_ref = net(x)
+        finally:
+            ref_arch.F.grid_sample = orig_gs
+            for hk in hooks:
+                hk.remove()
+
+        oprobes = {}
+        y_or = O.forward(sd, x, scale, oprobes)
+        err = float((y_ref - y_or).abs().max())
+        # bit-level checks of the index path against the tensors the reference actually built
+        H, W = O.get_hw(h, w, scale)
+        s = O.normalize_scale(scale)
+        inp = probes["satu_mlp_input"]
+        assert tuple(inp.shape) == (1, 4, H, W)
+        assert torch.equal(inp, O.satu_mlp_input(h, w, scale)), "SATU coordinate features not bit-exact"
+        g_or = O.satu_grid(h, w, scale, oprobes["satu_offset"])
+        grid_bits = torch.equal(grids[0][0:1], g_or)
+        gmax = float((grids[0][0:1] - g_or).abs().max())
+        base_x = torch.from_numpy(O.satu_base_norm(W, w, s[1]))
+        base_y = torch.from_numpy(O.satu_base_norm(H, h, s[0]))
+        zero_grid = O.satu_grid(h, w, scale, torch.zeros(1, 2, H, W))
+        assert torch.equal(zero_grid[0, 0, :, 0], base_x) and torch.equal(zero_grid[0, :, 0, 1], base_y)
+        stage_err = {k: float((probes[k] - oprobes[k]).abs().max()) for k in probes if k in oprobes}
+        print(f"[{name}] out {tuple(y_ref.shape)} oracle-vs-ref max-abs {err:.3e}; grid bit-exact={grid_bits} "
+              f"(max diff {gmax:.2e}); worst stage {max(stage_err, key=stage_err.get)}={max(stage_err.values()):.3e}")
+        assert err < 2e-5, err
+        assert max(stage_err.values()) < 2e-4, stage_err
+
+        rec = dict(b=np.int64(b), h=np.int64(h), w=np.int64(w), scale=np.array(s, dtype=np.float64),
+                   sd_seed=np.int64(sd_seed), in_seed=np.int64(in_seed), out=y_ref.numpy(),
+                   satu_mlp_input_sha1=np.array(hashlib.sha1(inp.numpy().tobytes()).hexdigest()),
+                   grid0=grids[0][0].numpy(), grid1=grids[1][0].numpy())
+        for k, t in probes.items():
+            if k == "satu_mlp_input":
+                continue
+            for f, val in probe_summary(t).items():
+                rec[f"probe.{k}.{f}"] = val
+        np.savez_compressed(os.path.join(outdir, f"{name}.npz"), **rec)
+    print("golden vectors written to", outdir)
+
+
+if __name__ == "__main__":
+    main()
