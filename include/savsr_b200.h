@@ -1,0 +1,242 @@
+/*
+ * savsr_b200.h -- C ABI of libsavsr_sm100.so: the B200 (sm_100a) kernels behind the SAVSR forward
+ * hot path (OSA-Conv + bi-directional propagation trunk + SATU upsampler).
+ *
+ * The reference (Weepingchestnut/SAVSR) has no C ABI of its own: its hot path is the Python file
+ * lbasicsr/archs/savsr_arch.py calling ATen ops.  Every entry point below therefore cites the
+ * reference *Python* interface it replaces (file:line relative to the reference root); the
+ * binding a maintainer would add on the reference side is the ctypes stub in INTEGRATION.md
+ * (savsr_b200/_capi.py is that stub, shipped).
+ *
+ * Conventions (mirroring the reference's native-op idiom, ops/fused_act/src/fused_bias_act.cpp:10-26):
+ *   - plain pointers and sizes only; no torch types.  All pointers are DEVICE pointers unless noted.
+ *   - the caller owns and allocates every buffer (inputs, outputs, activation arenas, scratch).
+ *     The library never allocates device memory, never synchronises, and launches only on the
+ *     stream it is given (so every call is CUDA-graph capturable).
+ *   - every function returns 0 on success, non-zero on error; savsr_last_error() returns a
+ *     thread-local message.  A device without sm_100 tensor-core support is an error, never a
+ *     fallback.
+ *   - activations live in an "arena": bf16, NHWC with C = 64, shape [nslots * batch, H, W, 64];
+ *     "slot s, sample n" is image index s * batch + n.  A 64*k-channel tensor is k slots.
+ */
+#ifndef SAVSR_B200_H_
+#define SAVSR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAVSR_ABI_VERSION 1
+#define SAVSR_MAX_SRC 5      /* most 64-channel sources one conv concatenates (OSA 320->64)      */
+#define SAVSR_MAX_GROUPS 25  /* most independent convolutions batched into one launch            */
+#define SAVSR_TILE_W 8       /* output tile = 8 x 16 pixels = 128 GEMM rows (one UMMA M)         */
+#define SAVSR_TILE_H 16
+
+typedef struct savsr_ctx savsr_ctx;     /* per-device context (driver entry points, SM count)   */
+typedef struct savsr_arena savsr_arena; /* activation arena + its TMA descriptors               */
+typedef void* savsr_stream;             /* cudaStream_t                                          */
+
+enum savsr_act { SAVSR_ACT_NONE = 0, SAVSR_ACT_LRELU = 1, SAVSR_ACT_RELU = 2 };
+
+/* how a convolution writes its result */
+enum savsr_dst_mode {
+  SAVSR_DST_ARENA = 0, /* bf16 NHWC-64 arena slot (N = 64)                                       */
+  SAVSR_DST_AUX16 = 1, /* fp32 [batch][H*W][16] side buffer (N = 16; OSAdapt mask conv)          */
+  SAVSR_DST_RGB = 2    /* fp32 NCHW [batch][3][H][W] + bilinear skip of the LR centre frame      */
+};
+
+enum savsr_conv_impl {
+  SAVSR_IMPL_TCGEN05_TAP = 0,  /* tcgen05/TMEM implicit GEMM, one TMA box per filter tap          */
+  SAVSR_IMPL_TCGEN05_HALO = 1, /* same, one halo box per source reused by all nine taps            */
+  SAVSR_IMPL_CHECK = 2         /* slow CUDA-core kernel, same contract: on-device checker only     */
+};
+
+/*
+ * One convolution of a batched launch.  Replaces one nn.Conv2d / F.conv2d call of
+ * savsr_arch.py (388-397 ResidualBlock convs, 429-442 WindowUnit_l1, 480-483 WindowUnit_l2,
+ * 541-543 RCAB, 567 ResidualGroup.conv, 166 OSA-Conv grouped conv, 190/203 OSAdapt mask,
+ * 227 kernel_conv, 260 fusion, 620 h_win_conv_h, 629 conv_last, 633 tail) together with the
+ * torch.cat feeding it (404, 412, 462, 498, 721, 374) and the elementwise ops that follow it.
+ *
+ *   acc = sum_{s < nsrc} sum_{tap} W[s, tap] * src_s(shifted by tap)          (zero padding)
+ *   v   = act(acc + bias) ; v *= mask[pixel] ; v += res1 ; v += res2_scale * res2 ; store v
+ *   pool (optional): per-(sample, tile-warp) partial channel sums of v, consumed by the next
+ *   OSA-Conv / channel-attention global average pool (savsr_arch.py:146, 515).
+ */
+typedef struct savsr_conv_group {
+  int32_t src_slot[SAVSR_MAX_SRC];
+  int32_t nsrc;
+  int32_t dst_slot;             /* SAVSR_DST_ARENA only                                          */
+  int32_t res1_slot;            /* -1 = none                                                     */
+  int32_t res2_slot;            /* -1 = none                                                     */
+  float res2_scale;
+  int32_t act;                  /* enum savsr_act                                                */
+  float slope;                  /* LeakyReLU negative slope                                      */
+  const void* weight;           /* packed bf16, see savsr_pack_conv_weight                       */
+  int64_t weight_sample_stride; /* BYTES between per-sample weights (OSA-Conv); 0 = shared       */
+  const float* bias;            /* [N] fp32 or NULL                                              */
+  const float* mask;            /* [batch][H*W] fp32 per-pixel multiplier or NULL (OSAdapt)      */
+  float* pool;                  /* [batch][tiles*4][64] fp32 partial sums or NULL                */
+  void* aux_dst;                /* SAVSR_DST_AUX16 / SAVSR_DST_RGB destination                   */
+} savsr_conv_group;
+
+/* extra arguments of SAVSR_DST_RGB: out = conv + bias + bilinear(x_center -> H x W), savsr_arch.py:738-739 */
+typedef struct savsr_rgb_skip {
+  const float* x;      /* LR input window [batch][t][3][h][w] fp32 NCHW (the module's input)       */
+  int32_t t, centre;   /* frames per window, centre frame index                                   */
+  int32_t h, w;        /* LR size (unpadded)                                                      */
+} savsr_rgb_skip;
+
+/* ---- library / context ------------------------------------------------------------------- */
+int savsr_abi_version(void);
+const char* savsr_last_error(void);
+/* Fails unless `device` is compute capability 10.x (tcgen05 / TMEM / TMA present). */
+int savsr_ctx_create(int device, savsr_ctx** out);
+void savsr_ctx_destroy(savsr_ctx* ctx);
+int savsr_ctx_sm_count(const savsr_ctx* ctx);
+/* HALO fetch-mode layout knobs (bring-up / tests): halo row pitch in pixels (10 or 16) and whether the
+ * UMMA shared-memory descriptor carries base_offset = (start >> 7) & 7.  Affects arenas created later. */
+int savsr_ctx_set_halo(savsr_ctx* ctx, int pitch, int use_base_offset);
+
+/* ---- activation arenas --------------------------------------------------------------------- */
+/* Bytes the caller must allocate (256-byte aligned) for an arena of that shape. */
+size_t savsr_arena_bytes(int nslots, int batch, int height, int width);
+int savsr_arena_create(savsr_ctx* ctx, void* base, int nslots, int batch, int height, int width,
+                       savsr_arena** out);
+void savsr_arena_destroy(savsr_arena* a);
+int savsr_arena_tiles(const savsr_arena* a);             /* output tiles per image                */
+/* debug / test helpers: fp32 NCHW [batch][64][H][W] <-> arena slot */
+int savsr_arena_import(savsr_arena* a, int slot, const float* nchw, savsr_stream st);
+int savsr_arena_export(savsr_arena* a, int slot, float* nchw, savsr_stream st);
+
+/* ---- weights --------------------------------------------------------------------------------- */
+/* Packed size in bytes of a [co][ci][k][k] filter (co multiple of n_tile, ci multiple of 64). */
+size_t savsr_packed_weight_bytes(int co, int ci, int ksize);
+/*
+ * fp32 OIHW [co][ci][k][k] (k = 1 or 3) -> bf16 blocks [co/n_tile][ci/64 * k*k][n_tile][64] in the
+ * 128-byte-swizzled K-major layout tcgen05.mma reads (block index = source * k*k + ky*k + kx).
+ * co_real <= co rows are read, the rest are zero (tail conv: 3 -> 16).  n_tile is 64 or 16.
+ */
+int savsr_pack_conv_weight(const float* w_oihw, int co_real, int co, int ci, int ksize, int n_tile,
+                           void* packed, savsr_stream st);
+
+/* ---- convolutions (tensor-core hot path) ------------------------------------------------------- */
+/*
+ * Batched implicit-GEMM convolution: `ngroups` independent convs x `batch` samples in one launch.
+ * ksize 3 (pad 1) or 1.  n_tile = 64 (dst ARENA) or 16 (AUX16 / RGB).  src and dst arenas may be the
+ * same object; they must have equal batch/height/width.
+ */
+int savsr_conv(savsr_ctx* ctx, savsr_arena* arena, const savsr_conv_group* groups, int ngroups,
+               int ksize, int n_tile, int dst_mode, const savsr_rgb_skip* skip, int impl,
+               savsr_stream st);
+
+/*
+ * First-layer convs on the fp32 NCHW input window (savsr_arch.py:456-457 conv_sup / conv_c with the
+ * frame gather of 447-454 and the reflect pad of 670-690 fused in):
+ * dst = LeakyReLU_0.2(conv3x3(cat(frames[fidx[0..nf)]) ) + bias), written to arena slot dst_slot.
+ */
+typedef struct savsr_front_group {
+  int32_t frame[2];
+  int32_t nframes;      /* 1 (conv_c) or 2 (conv_sup) */
+  int32_t dst_slot;
+  const float* weight;  /* fp32 OIHW [64][3*nframes][3][3] */
+  const float* bias;    /* [64] */
+} savsr_front_group;
+int savsr_front_conv(savsr_ctx* ctx, savsr_arena* arena, const float* x, int t, int h, int w,
+                     const savsr_front_group* groups, int ngroups, savsr_stream st);
+
+/* ---- OSA-Conv prologue (savsr_arch.py:143-163, 91-96, 123-128) ---------------------------------- */
+typedef struct savsr_osa_params {
+  int32_t ci, co, att;            /* in planes (64*nsrc), out planes (64), attention channels      */
+  const float* bank;              /* [8][co][ci][3][3] fp32 weight bank                            */
+  const float* r0_w; const float* r0_b;   /* scale_routing.0  [2ci][ci+2], [2ci]                  */
+  const float* r2_w; const float* r2_b;   /* scale_routing.2  [ci][2ci],   [ci]                   */
+  const float* fc_w;                      /* attention.fc     [att][ci]                            */
+  const float* bn_scale; const float* bn_shift; /* eval BatchNorm folded to z*scale+shift, [att]  */
+  const float* ch_w; const float* ch_b;   /* channel_fc [ci][att], [ci]                            */
+  const float* fl_w; const float* fl_b;   /* filter_fc  [co][att], [co]                            */
+  const float* sp_w; const float* sp_b;   /* spatial_fc [9][att],  [9]                             */
+  const float* kn_w; const float* kn_b;   /* kernel_fc  [8][att],  [8]                             */
+  const float* pool[SAVSR_MAX_SRC];       /* per source: [batch][npart][64] partial sums           */
+  float* scratch;                         /* [batch][5*ci + 192] fp32 work area                    */
+  void* packed;                           /* out: [batch] packed bf16 weights (n_tile 64)          */
+} savsr_osa_params;
+/*
+ * For each OSA-Conv of the launch and each sample: global-average-pool vector (from the producers'
+ * partial sums) -> scale_routing MLP -> ScaleAttention heads -> per-sample modulated kernel
+ * W'[o,i,u,v] = fa[o] ca[i] sa[u,v] sum_k ka[k] bank[k,o,i,u,v], written packed for savsr_conv.
+ * inv_scale_h/w = 1/s_h, 1/s_w (fp32).  npart = partial sums per image, npix = H*W of the pool.
+ */
+int savsr_osa_prologue(savsr_ctx* ctx, const savsr_osa_params* convs, int nconvs, int batch,
+                       int npart, int npix, float inv_scale_h, float inv_scale_w, savsr_stream st);
+/* test hook: per sample, scratch + 4*ci + 8 holds the attention vectors [ca(ci) | fa(co) | sa(9) | ka(8)] */
+
+/* ---- RCAB channel attention (savsr_arch.py:514-524, 547-549) --------------------------------------
+ * y = sigmoid(W2 relu(W1 mean(t) + b1) + b2) ; dst = x + t * y        (t, x, dst: arena slots)   */
+int savsr_ca_scale_residual(savsr_ctx* ctx, savsr_arena* arena, int t_slot, int x_slot, int dst_slot,
+                            const float* pool, int npart, const float* w1, const float* b1,
+                            const float* w2, const float* b2, savsr_stream st);
+
+/* ---- OSAdapt mask tail (savsr_arch.py:193-205) ------------------------------------------------------
+ * in16: [batch][H*W][16] fp32 = ReLU(BN(conv64->16(x))) from savsr_conv(AUX16).  Runs AvgPool2d(2),
+ * two conv16->16+BN+ReLU at half resolution, bilinear x2 upsample, conv16->1+BN, sigmoid.
+ * Weights: BN already folded by the caller.  wa/wb: [16][16][3][3], wc: [1][16][3][3].
+ * half0/half1: [batch][(H/2)*(W/2)][16] fp32 scratch.  mask out: [batch][H*W] fp32.              */
+int savsr_osadapt_mask(savsr_ctx* ctx, const float* in16, int batch, int height, int width,
+                       const float* wa, const float* ba, const float* wb, const float* bb,
+                       const float* wc, const float* bc, float* half0, float* half1, float* mask,
+                       savsr_stream st);
+
+/* ---- SATU (savsr_arch.py:315-376, 262-313) ---------------------------------------------------------- */
+typedef struct savsr_satu_weights {
+  const float* body0_w; const float* body0_b;  /* [64][4], [64]   */
+  const float* body2_w; const float* body2_b;  /* [64][64], [64]  */
+  const float* routing_w; const float* routing_b; /* [4][64], [4] */
+  const float* offset_w; const float* offset_b;   /* [2][64], [2] */
+  const float* st_offset_w; const float* st_offset_b;
+  const float* compress; /* [4][8][64]  */
+  const float* expand;   /* [4][64][8]  */
+} savsr_satu_weights;
+
+/*
+ * Coordinate / index kernel (savsr_arch.py:326-351 and the grid of 262-288), fp32 with the exact
+ * operation order of the reference (IEEE division, no FMA contraction):
+ *   rel_y[H], rel_x[W]   R(.) = (q - floor(q + 1e-3)) - 0.5, q = (i + 0.5) / s
+ *   cell_y[H], cell_x[W] int32 floor(q + 1e-3)              -- source LR cell
+ *   base_y[H], base_x[W] fp32 normalised base grid coordinate (zero offset)
+ *   corner_y[H], corner_x[W] int32 floor of the un-normalised base coordinate (may be -1)
+ *   table [H*W][8] fp32 = (offset_x, offset_y, st_offset_x, st_offset_y, r0, r1, r2, r3) from the
+ *   4->64->64 MLP and its three heads.  Depends only on (h, w, s_h, s_w): computed once per plan.
+ * Any of the index outputs may be NULL.  H, W are passed in (python round() on the host, :745-751).
+ */
+int savsr_satu_index(savsr_ctx* ctx, const savsr_satu_weights* wts, int h, int w, int H, int W,
+                     float s_h, float s_w, float* rel_y, float* rel_x, int32_t* cell_y,
+                     int32_t* cell_x, float* base_y, float* base_x, int32_t* corner_y,
+                     int32_t* corner_x, float* table, savsr_stream st);
+
+/*
+ * Spatio-temporal filtering (savsr_arch.py:297-313): sta[c] = sum_{u,v} xpad[y+u, x+v, c] * K[tap=u*5+v][c]
+ * with K the LeakyReLU_0.1'd kernel_conv output held tap-major in 25 arena slots kslot0..kslot0+24,
+ * replicate padding on the unpadded h x w region.  x_slot -> dst_slot.
+ */
+int savsr_satu_sta(savsr_ctx* ctx, savsr_arena* arena, int x_slot, int kslot0, int dst_slot, int h,
+                   int w, savsr_stream st);
+
+/*
+ * Fused HR gather (savsr_arch.py:364-373): for every HR pixel, bilinear-gather x and sta at the base
+ * coordinate + learned offset (zeros padding, align_corners=True), apply the routed compress/expand
+ * experts (matrix-free two-stage form) and write  hr slot `sta_dst` = sampled sta,  `fea_dst` = fea
+ * (the two operands of the 128->64 fusion conv).  lr: LR arena, hr: HR arena (H x W).
+ */
+int savsr_satu_gather(savsr_ctx* ctx, savsr_arena* lr, int x_slot, int sta_slot, int h, int w,
+                      savsr_arena* hr, int sta_dst, int fea_dst, const float* table,
+                      const float* base_y, const float* base_x, const savsr_satu_weights* wts,
+                      savsr_stream st);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAVSR_B200_H_ */

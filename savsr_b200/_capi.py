@@ -1,0 +1,175 @@
+"""ctypes binding of libsavsr_sm100.so (include/savsr_b200.h).
+
+This is the reference-side FFI stub a maintainer of the (pure-Python) reference would add: plain
+pointers, sizes and a stream, nothing torch-specific crosses the boundary.  There is NO fallback:
+if the shared library is missing or a call fails, a Python exception is raised, mirroring the
+reference's convention of raising from its native ops (ops/dcn/src/deform_conv_ext.cpp:64-67).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+MAX_SRC = 5
+MAX_GROUPS = 25
+TILE_W, TILE_H = 8, 16
+
+ACT_NONE, ACT_LRELU, ACT_RELU = 0, 1, 2
+DST_ARENA, DST_AUX16, DST_RGB = 0, 1, 2
+IMPL_TAP, IMPL_HALO, IMPL_CHECK = 0, 1, 2
+IMPL_NAMES = {"tap": IMPL_TAP, "halo": IMPL_HALO, "check": IMPL_CHECK}
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libsavsr_sm100.so")
+
+
+class SavsrError(RuntimeError):
+    """A libsavsr_sm100 call returned non-zero."""
+
+
+class ConvGroup(C.Structure):
+    _fields_ = [
+        ("src_slot", C.c_int32 * MAX_SRC),
+        ("nsrc", C.c_int32),
+        ("dst_slot", C.c_int32),
+        ("res1_slot", C.c_int32),
+        ("res2_slot", C.c_int32),
+        ("res2_scale", C.c_float),
+        ("act", C.c_int32),
+        ("slope", C.c_float),
+        ("weight", C.c_void_p),
+        ("weight_sample_stride", C.c_int64),
+        ("bias", C.c_void_p),
+        ("mask", C.c_void_p),
+        ("pool", C.c_void_p),
+        ("aux_dst", C.c_void_p),
+    ]
+
+
+class RgbSkip(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("t", C.c_int32), ("centre", C.c_int32), ("h", C.c_int32), ("w", C.c_int32)]
+
+
+class FrontGroup(C.Structure):
+    _fields_ = [("frame", C.c_int32 * 2), ("nframes", C.c_int32), ("dst_slot", C.c_int32),
+                ("weight", C.c_void_p), ("bias", C.c_void_p)]
+
+
+class OsaParams(C.Structure):
+    _fields_ = [
+        ("ci", C.c_int32), ("co", C.c_int32), ("att", C.c_int32),
+        ("bank", C.c_void_p),
+        ("r0_w", C.c_void_p), ("r0_b", C.c_void_p), ("r2_w", C.c_void_p), ("r2_b", C.c_void_p),
+        ("fc_w", C.c_void_p), ("bn_scale", C.c_void_p), ("bn_shift", C.c_void_p),
+        ("ch_w", C.c_void_p), ("ch_b", C.c_void_p), ("fl_w", C.c_void_p), ("fl_b", C.c_void_p),
+        ("sp_w", C.c_void_p), ("sp_b", C.c_void_p), ("kn_w", C.c_void_p), ("kn_b", C.c_void_p),
+        ("pool", C.c_void_p * MAX_SRC),
+        ("scratch", C.c_void_p),
+        ("packed", C.c_void_p),
+    ]
+
+
+class SatuWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "body0_w", "body0_b", "body2_w", "body2_b", "routing_w", "routing_b", "offset_w", "offset_b",
+        "st_offset_w", "st_offset_b", "compress", "expand")]
+
+
+# name -> (restype, argtypes); every symbol declared in include/savsr_b200.h
+_VP, _I, _F, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+SIGNATURES = {
+    "savsr_abi_version": (_I, []),
+    "savsr_last_error": (C.c_char_p, []),
+    "savsr_ctx_create": (_I, [_I, C.POINTER(_VP)]),
+    "savsr_ctx_destroy": (None, [_VP]),
+    "savsr_ctx_sm_count": (_I, [_VP]),
+    "savsr_ctx_set_halo": (_I, [_VP, _I, _I]),
+    "savsr_arena_bytes": (_SZ, [_I, _I, _I, _I]),
+    "savsr_arena_create": (_I, [_VP, _VP, _I, _I, _I, _I, C.POINTER(_VP)]),
+    "savsr_arena_destroy": (None, [_VP]),
+    "savsr_arena_tiles": (_I, [_VP]),
+    "savsr_arena_import": (_I, [_VP, _I, _VP, _VP]),
+    "savsr_arena_export": (_I, [_VP, _I, _VP, _VP]),
+    "savsr_packed_weight_bytes": (_SZ, [_I, _I, _I]),
+    "savsr_pack_conv_weight": (_I, [_VP, _I, _I, _I, _I, _I, _VP, _VP]),
+    "savsr_conv": (_I, [_VP, _VP, C.POINTER(ConvGroup), _I, _I, _I, _I, C.POINTER(RgbSkip), _I, _VP]),
+    "savsr_front_conv": (_I, [_VP, _VP, _VP, _I, _I, _I, C.POINTER(FrontGroup), _I, _VP]),
+    "savsr_osa_prologue": (_I, [_VP, C.POINTER(OsaParams), _I, _I, _I, _I, _F, _F, _VP]),
+    "savsr_ca_scale_residual": (_I, [_VP, _VP, _I, _I, _I, _VP, _I, _VP, _VP, _VP, _VP, _VP]),
+    "savsr_osadapt_mask": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "savsr_satu_index": (_I, [_VP, C.POINTER(SatuWeights), _I, _I, _I, _I, _F, _F] + [_VP] * 9 + [_VP]),
+    "savsr_satu_sta": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP]),
+    "savsr_satu_gather": (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _I, _I, _VP, _VP, _VP, C.POINTER(SatuWeights), _VP]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library and bind every declared symbol.  Raises if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SavsrError(
+            f"{LIB_PATH} not found: build it with `python -m savsr_b200.build` (needs nvcc, sm_100a). "
+            "savsr_b200 has no CPU or PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.savsr_abi_version() != 1:
+        raise SavsrError(f"ABI version mismatch: library {lib.savsr_abi_version()}, binding 1")
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().savsr_last_error()
+        raise SavsrError(f"libsavsr_sm100 error {rc}: {msg.decode(errors='replace') if msg else '?'}")
+
+
+class Context:
+    """savsr_ctx wrapper (one per device)."""
+
+    def __init__(self, device: int):
+        self.lib = load()
+        h = C.c_void_p()
+        check(self.lib.savsr_ctx_create(int(device), C.byref(h)))
+        self.handle = h
+        self.device = int(device)
+        self.sm_count = self.lib.savsr_ctx_sm_count(h)
+
+    def set_halo(self, pitch: int, use_base_offset: bool) -> None:
+        check(self.lib.savsr_ctx_set_halo(self.handle, int(pitch), int(bool(use_base_offset))))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.savsr_ctx_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class Arena:
+    """savsr_arena wrapper over caller-owned device memory (`base_ptr`)."""
+
+    def __init__(self, ctx: Context, base_ptr: int, nslots: int, batch: int, height: int, width: int):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        h = C.c_void_p()
+        check(self.lib.savsr_arena_create(ctx.handle, C.c_void_p(base_ptr), nslots, batch, height, width, C.byref(h)))
+        self.handle = h
+        self.nslots, self.batch, self.height, self.width = nslots, batch, height, width
+        self.tiles = self.lib.savsr_arena_tiles(h)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.savsr_arena_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass

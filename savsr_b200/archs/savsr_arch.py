@@ -1,0 +1,251 @@
+"""Drop-in ``SAVSR`` arch backed by libsavsr_sm100 (B200 / sm_100a).
+
+Boundary contract (reference: lbasicsr/archs/savsr_arch.py:574-742):
+  * class name ``SAVSR``, registered in ``ARCH_REGISTRY`` (the reference's registry when ``lbasicsr`` is
+    importable -- see ``savsr_b200.overlay`` -- otherwise a local registry of the same shape);
+  * identical constructor keyword arguments;
+  * ``set_scale(scale)`` then ``forward(x)`` with ``x`` float32 ``[b, 7, 3, h, w]`` in [0, 1], returning a
+    fresh float32 ``[b, 3, H, W]`` tensor (not clamped), ``H, W = round(h * s_h), round(w * s_w)``;
+  * identical parameter / buffer names, shapes and order, so ``load_state_dict(strict=True)`` round-trips
+    with reference checkpoints (``{'params': state_dict}``).
+
+The sub-modules below are *parameter containers* that reproduce the reference's state_dict layout; they
+never run.  ``forward`` hands the parameters to ``savsr_b200.engine.Plan`` which launches the CUDA
+kernels through the C ABI.  There is no CPU / eager fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Dict, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from savsr_b200 import engine
+
+try:  # the reference's own registry, when this file is loaded as lbasicsr.archs.savsr_arch
+    from lbasicsr.utils.registry import ARCH_REGISTRY  # type: ignore
+except Exception:  # standalone use
+    from savsr_b200.registry import ARCH_REGISTRY
+
+
+def _no_forward(self, *a, **k):
+    raise RuntimeError(f"{type(self).__name__} is a parameter container of savsr_b200.SAVSR; call the top-level module")
+
+
+class _Holder(nn.Module):
+    forward = _no_forward
+
+
+def _conv(ci: int, co: int, k: int, bias: bool = True) -> nn.Conv2d:
+    return nn.Conv2d(ci, co, k, 1, k // 2, bias=bias)
+
+
+class ScaleAttention(_Holder):
+    """Parameters of savsr_arch.py:16-60 (kernel_size 3, kernel_num 8)."""
+
+    def __init__(self, in_planes: int, out_planes: int, kernel_num: int = 8, reduction: float = 0.0625, min_channel: int = 16):
+        super().__init__()
+        a = max(int(in_planes * reduction), min_channel)
+        self.fc = _conv(in_planes, a, 1, bias=False)
+        self.bn = nn.BatchNorm2d(a)
+        self.channel_fc = _conv(a, in_planes, 1)
+        self.filter_fc = _conv(a, out_planes, 1)
+        self.spatial_fc = _conv(a, 9, 1)
+        self.kernel_fc = _conv(a, kernel_num, 1)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+
+
+class OSConv2d(_Holder):
+    """Parameters of the omni-dimensional scale-attention conv (savsr_arch.py:99-134)."""
+
+    def __init__(self, in_planes: int, out_planes: int, kernel_num: int = 8):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(kernel_num, out_planes, in_planes, 3, 3))
+        self.attention = ScaleAttention(in_planes, out_planes, kernel_num)
+        self.scale_routing = nn.Sequential(nn.Linear(in_planes + 2, in_planes * 2), nn.ReLU(True),
+                                           nn.Linear(in_planes * 2, in_planes), nn.ReLU(True))
+        with torch.no_grad():
+            for i in range(kernel_num):
+                nn.init.kaiming_normal_(self.weight[i], mode="fan_out", nonlinearity="relu")
+
+
+class OSAdapt(_Holder):
+    def __init__(self, channels: int, ratio: int = 4):
+        super().__init__()
+        c = channels // ratio
+        self.mask = nn.Sequential(
+            _conv(channels, c, 3), nn.BatchNorm2d(c), nn.ReLU(True), nn.AvgPool2d(2),
+            _conv(c, c, 3), nn.BatchNorm2d(c), nn.ReLU(True),
+            _conv(c, c, 3), nn.BatchNorm2d(c), nn.ReLU(True),
+            nn.Upsample(scale_factor=2, mode="bilinear", align_corners=False),
+            _conv(c, 1, 3), nn.BatchNorm2d(1), nn.Sigmoid())
+        self.adapt = OSConv2d(channels, channels)
+
+
+class STAUpsample(_Holder):
+    def __init__(self, channels: int, num_experts: int = 4, st_ksize: int = 5):
+        super().__init__()
+        wc = torch.empty(num_experts, channels // 8, channels, 1, 1)
+        we = torch.empty(num_experts, channels, channels // 8, 1, 1)
+        for i in range(num_experts):
+            nn.init.kaiming_uniform_(wc[i], a=math.sqrt(5))
+            nn.init.kaiming_uniform_(we[i], a=math.sqrt(5))
+        self.weight_compress = nn.Parameter(wc)
+        self.weight_expand = nn.Parameter(we)
+        self.kernel_conv = nn.Sequential(_conv(channels, channels * st_ksize ** 2, 1), nn.LeakyReLU(0.1, True))
+        self.body = nn.Sequential(_conv(4, 64, 1), nn.ReLU(True), _conv(64, 64, 1), nn.ReLU(True))
+        self.routing = nn.Sequential(_conv(64, num_experts, 1), nn.Sigmoid())
+        self.offset = _conv(64, 2, 1)
+        self.st_offset = _conv(64, 2, 1)
+        self.fusion = _conv(2 * channels, channels, 1)
+
+
+class ResidualBlock(_Holder):
+    def __init__(self, num_feat: int = 64, num_frame: int = 3, use_osconv: bool = False):
+        super().__init__()
+        self.conv0 = nn.Sequential(*[_conv(num_feat, num_feat, 3) for _ in range(num_frame)])
+        if use_osconv:
+            self.osconv = OSConv2d(num_feat * num_frame, num_feat)
+        else:
+            self.conv1 = _conv(num_feat * num_frame, num_feat, 1)
+        self.conv2 = nn.Sequential(*[_conv(num_feat * 2, num_feat, 3) for _ in range(num_frame)])
+
+
+class WindowUnit_l1(_Holder):
+    def __init__(self, num_in_ch: int = 3, num_feat: int = 64, win_size: int = 3, num_block: int = 4):
+        super().__init__()
+        self.conv_c = _conv(num_in_ch, num_feat, 3)
+        self.conv_sup = _conv(num_in_ch * (win_size - 1), num_feat, 3)
+        self.blocks = nn.Sequential(*[ResidualBlock(num_feat, 3, use_osconv=i >= 1) for i in range(num_block)])
+        self.merge = _conv(3 * num_feat, num_feat, 3)
+
+
+class WindowUnit_l2(_Holder):
+    def __init__(self, num_feat: int = 64, win_size: int = 5, slid_win: int = 3, num_block: int = 2):
+        super().__init__()
+        self.conv_h = nn.Sequential(*[_conv(num_feat * 2, num_feat, 3) for _ in range(win_size)])
+        self.blocks = nn.Sequential(*[ResidualBlock(num_feat, slid_win, use_osconv=True) for _ in range(num_block)])
+        self.merge = _conv(slid_win * num_feat, num_feat * 2, 3)
+
+
+class ChannelAttention(_Holder):
+    def __init__(self, num_feat: int, squeeze_factor: int = 16):
+        super().__init__()
+        self.attention = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Conv2d(num_feat, num_feat // squeeze_factor, 1),
+                                       nn.ReLU(True), nn.Conv2d(num_feat // squeeze_factor, num_feat, 1), nn.Sigmoid())
+
+
+class RCAB(_Holder):
+    def __init__(self, num_feat: int, squeeze_factor: int = 16):
+        super().__init__()
+        self.rcab = nn.Sequential(_conv(num_feat, num_feat, 3), nn.ReLU(True), _conv(num_feat, num_feat, 3),
+                                  ChannelAttention(num_feat, squeeze_factor))
+
+
+class ResidualGroup(_Holder):
+    def __init__(self, num_feat: int, num_block: int, squeeze_factor: int = 16):
+        super().__init__()
+        self.residual_group = nn.Sequential(*[RCAB(num_feat, squeeze_factor) for _ in range(num_block)])
+        self.conv = _conv(num_feat, num_feat, 3)
+
+
+@ARCH_REGISTRY.register()
+class SAVSR(nn.Module):
+    """B200-native SAVSR forward.  Same constructor as the reference (savsr_arch.py:576-589)."""
+
+    def __init__(self, num_in_ch=3, num_feat=64, num_frame=7, slid_win=3, fusion_win=5, interval=0, w1_num_block=4,
+                 w2_num_block=2, n_resgroups=4, n_resblocks=8, downsample_scale=2, center_frame_idx=None):
+        super().__init__()
+        if interval != 0:
+            raise NotImplementedError("savsr_b200 implements the shipped configuration interval=0 only")
+        if (num_in_ch, num_feat, num_frame, slid_win, fusion_win, w1_num_block, w2_num_block, n_resgroups, n_resblocks) != \
+                (3, 64, 7, 3, 5, 4, 2, 4, 8):
+            raise NotImplementedError(
+                "savsr_b200 kernels are specialised for the shipped SAVSR YAML (num_feat=64, num_frame=7, slid_win=3, "
+                "fusion_win=5, w1_num_block=4, w2_num_block=2, n_resgroups=4, n_resblocks=8)")
+        self.scale: Union[tuple, float, int] = (4, 4)
+        self.center_frame_idx = num_frame // 2 if center_frame_idx is None else center_frame_idx
+        if self.center_frame_idx != num_frame // 2:
+            raise NotImplementedError("center_frame_idx must be the middle frame")
+        self.num_frame, self.iter_win, self.slid_win, self.interval = num_frame, num_frame, slid_win, interval
+        self.num_feat, self.downsample_scale = num_feat, downsample_scale
+
+        self.f2p_win = WindowUnit_l1(num_in_ch, num_feat, slid_win, w1_num_block)
+        self.p2f_win = WindowUnit_l1(num_in_ch, num_feat, slid_win, w1_num_block)
+        self.h_win = nn.Sequential(*[WindowUnit_l2(num_feat, (self.iter_win - slid_win + 1) - 2 * i, fusion_win, w2_num_block)
+                                     for i in range((self.iter_win - fusion_win + 1) // 2)])
+        self.h_win_act = nn.LeakyReLU(0.2, True)
+        self.h_win_conv_h = _conv(num_feat * 2, num_feat, 3)
+        self.RG = nn.ModuleList([ResidualGroup(num_feat, n_resblocks) for _ in range(n_resgroups)])
+        self.K = 1
+        self.adapt = nn.ModuleList([OSAdapt(num_feat) for _ in range(n_resgroups // self.K)])
+        self.gamma = nn.Parameter(torch.ones(1))
+        self.conv_last = _conv(num_feat, num_feat, 3)
+        self.upsample = STAUpsample(num_feat)
+        self.tail = _conv(num_feat, num_in_ch, 3)
+
+        self._plans: Dict[tuple, engine.Plan] = {}
+        self.conv_impl = os.environ.get("SAVSR_CONV_IMPL", "tap")
+        self.use_graph = os.environ.get("SAVSR_GRAPH", "1") != "0"
+        self.debug_taps: Tuple[str, ...] = ()
+
+    # ---- reference API ---------------------------------------------------------------------------
+    def set_scale(self, scale: Union[tuple, float, int]):
+        self.scale = scale
+
+    def forward(self, x: torch.Tensor, scale=None) -> torch.Tensor:
+        if scale is not None:
+            self.scale = scale
+        plan = self.plan_for(x)
+        plan.x_in.copy_(x)
+        if self.use_graph:
+            plan.run_graph()
+        else:
+            plan.run()
+        return plan.out.clone()
+
+    # ---- plan management ---------------------------------------------------------------------------
+    def _weights_version(self) -> tuple:
+        ver, ptr = 0, 0
+        for t in list(self.parameters()) + list(self.buffers()):
+            ver += t._version
+            ptr ^= t.data_ptr()
+        return ver, ptr
+
+    def plan_for(self, x: torch.Tensor) -> engine.Plan:
+        if x.dim() != 5 or x.shape[1] != self.num_frame or x.shape[2] != 3:
+            raise ValueError(f"expected input [b, {self.num_frame}, 3, h, w], got {tuple(x.shape)}")
+        if not x.is_cuda:
+            raise RuntimeError("savsr_b200.SAVSR runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if self.training:
+            raise NotImplementedError("savsr_b200.SAVSR implements the inference forward; call .eval() first "
+                                      "(train-mode BatchNorm / backward are outside the hot path of this round)")
+        p0 = next(self.parameters())
+        if p0.device != x.device:
+            raise RuntimeError(f"module parameters on {p0.device}, input on {x.device}")
+        b, _, _, h, w = x.shape
+        s = engine.normalize_scale(self.scale)
+        key = (b, h, w, float(s[0]), float(s[1]), self.conv_impl, tuple(self.debug_taps), x.device.index) + self._weights_version()
+        plan = self._plans.get(key)
+        if plan is None:
+            if len(self._plans) >= 8:               # bound the memory held by stale plans
+                self._plans.pop(next(iter(self._plans)))
+            params = {k: v for k, v in self.state_dict(keep_vars=True).items()}
+            plan = engine.Plan(params, b, h, w, s, x.device, conv_impl=self.conv_impl, num_frame=self.num_frame,
+                               taps=self.debug_taps)
+            self._plans[key] = plan
+        return plan
+
+    def release_plans(self) -> None:
+        self._plans.clear()
+
+
+def get_HW(h, w, scale):
+    """savsr_arch.py:745-751."""
+    return engine.get_hw(h, w, scale)

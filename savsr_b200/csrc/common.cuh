@@ -1,0 +1,215 @@
+// Shared device helpers for libsavsr_sm100: PTX wrappers for mbarrier / TMA / tcgen05 (sm_100a only),
+// bf16 packing, error plumbing.  Hand-written; no CUTLASS dependency.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/savsr_b200.h"
+
+namespace savsr {
+
+// ------------------------------------------------------------------------------------------------ host side
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define SAVSR_CUDA(expr)                                   \
+  do {                                                     \
+    cudaError_t _e = (expr);                               \
+    if (_e != cudaSuccess) return ::savsr::cuda_fail(_e, #expr); \
+  } while (0)
+
+#define SAVSR_REQUIRE(cond, ...)          \
+  do {                                    \
+    if (!(cond)) {                        \
+      ::savsr::set_error(__VA_ARGS__);    \
+      return 1;                           \
+    }                                     \
+  } while (0)
+
+constexpr int kTileW = SAVSR_TILE_W;
+constexpr int kTileH = SAVSR_TILE_H;
+constexpr int kTileM = kTileW * kTileH;  // 128
+constexpr int kC = 64;                   // channels per arena slot
+
+}  // namespace savsr
+
+struct savsr_ctx {
+  int device;
+  int sm_count;
+  int cc_major, cc_minor;
+  void* encode_tiled;  // PFN_cuTensorMapEncodeTiled
+  int halo_pitch;      // halo box width in pixels (10 = tight, 16 = 1024-byte aligned rows)
+  int halo_base_offset;  // 1: put (addr >> 7) & 7 into the UMMA descriptor base_offset field
+};
+
+struct savsr_arena {
+  savsr_ctx* ctx;
+  __nv_bfloat16* base;
+  int nslots, batch, height, width;
+  int tiles_x, tiles_y;
+  CUtensorMap tm_tile;  // box [64, 8, 16, 1]
+  CUtensorMap tm_halo;  // box [64, halo_pitch, 18, 1]
+};
+
+#ifdef __CUDACC__
+namespace savsr {
+
+// ------------------------------------------------------------------------------------------------ misc
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// ------------------------------------------------------------------------------------------------ mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Spin with a bounded trip count: a protocol bug traps instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) {
+      printf("savsr: mbarrier timeout block %d thread %d bar %p parity %u\n", blockIdx.x, threadIdx.x,
+             (void*)bar, parity);
+      __trap();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ TMA
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+// 4-D tiled load: coordinates (c, x, y, img), out-of-range elements are zero-filled.
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c, int x,
+                                            int y, int img) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c), "r"(x), "r"(y), "r"(img),
+      "r"(smem_u32(bar))
+      : "memory");
+}
+// 1-D bulk copy global -> shared (size multiple of 16 bytes, both 16-byte aligned).
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ tcgen05
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_out) {  // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_out)),
+               "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {  // same warp that allocated
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+
+// Shared-memory matrix descriptor, K-major operand, 128-byte swizzle (layout_type 2), version 1.
+//   start address >> 4 in bits [0,14); LBO unused for a single swizzle atom along K;
+//   SBO (bytes between 8-row groups) >> 4 in bits [32,46); base_offset in bits [49,52).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_offset) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3fffu);
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(base_offset & 7u) << 49;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, both operands K-major, M = 128.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) {
+  return (1u << 4)                              // c_format  = F32
+         | (1u << 7)                            // a_format  = BF16
+         | (1u << 10)                           // b_format  = BF16
+         | (static_cast<uint32_t>(n >> 3) << 17)  // N >> 3
+         | (static_cast<uint32_t>(128 >> 4) << 24);  // M >> 4
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// 32 lanes x 32 bit, 16 consecutive columns: thread i of the warp gets TMEM lane (base_lane + i).
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+}  // namespace savsr
+#endif  // __CUDACC__

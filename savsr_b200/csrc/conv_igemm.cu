@@ -1,0 +1,546 @@
+// Batched implicit-GEMM 3x3 / 1x1 convolution on tcgen05 tensor cores (sm_100a).
+//
+//   D[128 pixels, N] += A[128 pixels, 64 ch] * B[64 ch, N]      per (source, tap) K-block
+//
+//  * A operand: NHWC bf16 arena, fetched by TMA as a 4-D box (64 ch, 8 x, 16 y, 1 image) straight into
+//    the 128-byte-swizzled K-major layout tcgen05.mma reads.  Zero padding of the convolution is the
+//    TMA out-of-bounds fill.  Two fetch modes:
+//      TAP  : one 16 KB box per filter tap (9 per source), box origin shifted by the tap.
+//      HALO : one (8+2) x (16+2) halo box per source; the nine taps are nine UMMA descriptors into the
+//             same tile (start address shifted by whole 128-byte pixel rows, SBO = halo row pitch),
+//             cutting L2->smem traffic for A by ~6x.
+//  * B operand: weights pre-packed per K-block as [N][64] bf16, already swizzled, fetched with a 1-D
+//    bulk copy (per-sample pointer for OSA-Conv: the "groups = batch" conv of savsr_arch.py:166).
+//  * accumulator: fp32 in TMEM, double buffered (2 x N columns) so the epilogue of tile i overlaps the
+//    main loop of tile i+1.  Persistent CTAs, one per SM, static round-robin over (conv, sample, tile).
+//  * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (single thread), warps 2-5 = epilogue
+//    (tcgen05.ld -> bias/activation/mask/residuals -> bf16 NHWC store, optional pooled partial sums).
+//
+// The CUDA-core kernel at the bottom implements the same contract with plain loads and shares the
+// epilogue; it exists only as an on-device checker for the TMA/UMMA main loop (tests, bring-up).
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace savsr {
+
+constexpr int kMaxAStages = 6;
+constexpr int kBStages = 8;
+constexpr int kARegionBytes = 6 * 16384 + 12288;  // 108 KB: 6 tap stages | 4 halo-10 stages | 3 halo-16 stages
+constexpr int kNumThreads = 192;
+
+struct ConvParams {
+  CUtensorMap tm_tile;
+  CUtensorMap tm_halo;
+  savsr_conv_group g[SAVSR_MAX_GROUPS];
+  savsr_rgb_skip skip;
+  __nv_bfloat16* arena;
+  int ngroups, batch, height, width, tiles_x, tiles_y;
+  int ntaps;            // 1 or 9
+  int halo;             // A fetch mode
+  int halo_pitch;       // pixels per halo row in smem (10 or 16)
+  int use_base_offset;  // fill UMMA descriptor base_offset from the start address
+  int a_stage_bytes, a_stages;
+  int dst_mode;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  if (act == SAVSR_ACT_LRELU) return v > 0.f ? v : v * slope;
+  if (act == SAVSR_ACT_RELU) return fmaxf(v, 0.f);
+  return v;
+}
+
+// ATen upsample_bilinear2d, align_corners = False (savsr_arch.py:739): source index and weight.
+__device__ __forceinline__ void bilinear_src(int dst, int in_size, int out_size, int& i0, int& i1, float& l1) {
+  const float scale = static_cast<float>(in_size) / static_cast<float>(out_size);
+  float src = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  i0 = static_cast<int>(src);
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - static_cast<float>(i0);
+}
+
+// Epilogue shared by the tensor-core kernel and the checker.  `v` holds the fp32 accumulator row of
+// pixel m = quad * 32 + lane of the tile; one warp per 32-row quadrant.
+template <int BN>
+__device__ __forceinline__ void conv_epilogue(const ConvParams& p, const savsr_conv_group& g, int n, int tile,
+                                              int quad, int lane, float (&v)[BN]) {
+  const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+  const int m = quad * 32 + lane;
+  const int px = tx * kTileW + (m & (kTileW - 1));
+  const int py = ty * kTileH + (m >> 3);
+  const bool valid = (px < p.width) && (py < p.height);
+  const long npix = static_cast<long>(p.height) * p.width;
+  const long pix = static_cast<long>(py) * p.width + px;
+
+  if (g.bias != nullptr) {
+#pragma unroll
+    for (int c = 0; c < BN; ++c) v[c] += __ldg(g.bias + c);
+  }
+  if (g.act != SAVSR_ACT_NONE) {
+#pragma unroll
+    for (int c = 0; c < BN; ++c) v[c] = apply_act(v[c], g.act, g.slope);
+  }
+
+  if constexpr (BN == 64) {
+    if (g.mask != nullptr) {
+      const float mk = valid ? __ldg(g.mask + n * npix + pix) : 0.f;
+#pragma unroll
+      for (int c = 0; c < BN; ++c) v[c] *= mk;
+    }
+    if (g.res1_slot >= 0 && valid) {
+      const uint4* r = reinterpret_cast<const uint4*>(p.arena + ((static_cast<long>(g.res1_slot) * p.batch + n) * npix + pix) * kC);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 u = r[j];
+        v[8 * j + 0] += bf16_lo(u.x); v[8 * j + 1] += bf16_hi(u.x);
+        v[8 * j + 2] += bf16_lo(u.y); v[8 * j + 3] += bf16_hi(u.y);
+        v[8 * j + 4] += bf16_lo(u.z); v[8 * j + 5] += bf16_hi(u.z);
+        v[8 * j + 6] += bf16_lo(u.w); v[8 * j + 7] += bf16_hi(u.w);
+      }
+    }
+    if (g.res2_slot >= 0 && valid) {
+      const float s = g.res2_scale;
+      const uint4* r = reinterpret_cast<const uint4*>(p.arena + ((static_cast<long>(g.res2_slot) * p.batch + n) * npix + pix) * kC);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 u = r[j];
+        v[8 * j + 0] += s * bf16_lo(u.x); v[8 * j + 1] += s * bf16_hi(u.x);
+        v[8 * j + 2] += s * bf16_lo(u.y); v[8 * j + 3] += s * bf16_hi(u.y);
+        v[8 * j + 4] += s * bf16_lo(u.z); v[8 * j + 5] += s * bf16_hi(u.z);
+        v[8 * j + 6] += s * bf16_lo(u.w); v[8 * j + 7] += s * bf16_hi(u.w);
+      }
+    }
+    if (valid) {
+      uint4* d = reinterpret_cast<uint4*>(p.arena + ((static_cast<long>(g.dst_slot) * p.batch + n) * npix + pix) * kC);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint4 u;
+        u.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+        u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+        u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+        u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+        d[j] = u;
+      }
+    }
+    if (g.pool != nullptr) {
+      // Per-warp channel sums of the (pre-rounding) outputs over valid pixels, by a shuffle
+      // reduce-scatter: 62 shuffles leave channels (2*lane, 2*lane+1) in each lane.  Deterministic.
+      if (!valid) {
+#pragma unroll
+        for (int c = 0; c < BN; ++c) v[c] = 0.f;
+      }
+#pragma unroll
+      for (int off = 16, cnt = 32; off >= 1; off >>= 1, cnt >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < cnt; ++i) {
+          const float send = upper ? v[i] : v[i + cnt];
+          const float keep = upper ? v[i + cnt] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      const int npart = p.tiles_x * p.tiles_y * 4;
+      float2* dstp = reinterpret_cast<float2*>(g.pool + (static_cast<long>(n) * npart + tile * 4 + quad) * kC);
+      dstp[lane] = make_float2(v[0], v[1]);
+    }
+  } else {
+    if (p.dst_mode == SAVSR_DST_AUX16) {
+      if (valid) {
+        float4* d = reinterpret_cast<float4*>(static_cast<float*>(g.aux_dst) + (n * npix + pix) * 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+    } else {  // SAVSR_DST_RGB: + bilinear skip of the LR centre frame, fp32 NCHW output
+      if (valid) {
+        int y0, y1, x0, x1;
+        float ly, lx;
+        bilinear_src(py, p.skip.h, p.height, y0, y1, ly);
+        bilinear_src(px, p.skip.w, p.width, x0, x1, lx);
+        const long plane = static_cast<long>(p.skip.h) * p.skip.w;
+        const float* xc = p.skip.x + (static_cast<long>(n) * p.skip.t + p.skip.centre) * 3 * plane;
+        float* out = static_cast<float*>(g.aux_dst) + static_cast<long>(n) * 3 * npix + pix;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float* pl = xc + c * plane;
+          const float a = __ldg(pl + y0 * p.skip.w + x0), b = __ldg(pl + y0 * p.skip.w + x1);
+          const float cc = __ldg(pl + y1 * p.skip.w + x0), d = __ldg(pl + y1 * p.skip.w + x1);
+          const float sk = (1.f - ly) * ((1.f - lx) * a + lx * b) + ly * ((1.f - lx) * cc + lx * d);
+          out[c * npix] = v[c] + sk;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ tcgen05 kernel
+template <int BN>
+__global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment: the 128-byte swizzle pattern repeats every 1024 bytes of shared address.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kARegionBytes;
+  constexpr int kBBytes = BN * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kBStages * kBBytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + kMaxAStages;
+  uint64_t* b_full = bars + 2 * kMaxAStages;
+  uint64_t* b_empty = b_full + kBStages;
+  uint64_t* t_full = b_empty + kBStages;
+  uint64_t* t_empty = t_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles = p.tiles_x * p.tiles_y;
+  const int total = p.ngroups * p.batch * tiles;
+  constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&p.tm_tile);
+    prefetch_tensormap(&p.tm_halo);
+    for (int i = 0; i < kMaxAStages; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < kBStages; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer (one thread) ================================
+    if (lane == 0) {
+      int sa = 0, pa = 0, sb = 0, pb = 0;
+      const uint32_t halo_bytes = static_cast<uint32_t>(p.halo_pitch) * (kTileH + 2) * 128u;
+      for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        const int tile = item % tiles;
+        const int gn = item / tiles;
+        const int n = gn % p.batch;
+        const savsr_conv_group& g = p.g[gn / p.batch];
+        const int x0 = (tile % p.tiles_x) * kTileW, y0 = (tile / p.tiles_x) * kTileH;
+        const uint8_t* wptr = static_cast<const uint8_t*>(g.weight) + static_cast<long>(n) * g.weight_sample_stride;
+        for (int s = 0; s < g.nsrc; ++s) {
+          const int img = g.src_slot[s] * p.batch + n;
+          if (p.halo) {
+            mbar_wait(a_empty + sa, pa ^ 1);
+            mbar_expect_tx(a_full + sa, halo_bytes);
+            tma_load_4d(smem_a + sa * p.a_stage_bytes, &p.tm_halo, a_full + sa, 0, x0 - 1, y0 - 1, img);
+            if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+          }
+          for (int tap = 0; tap < p.ntaps; ++tap) {
+            if (!p.halo) {
+              const int dx = p.ntaps == 9 ? tap % 3 - 1 : 0;
+              const int dy = p.ntaps == 9 ? tap / 3 - 1 : 0;
+              mbar_wait(a_empty + sa, pa ^ 1);
+              mbar_expect_tx(a_full + sa, kTileM * 128u);
+              tma_load_4d(smem_a + sa * p.a_stage_bytes, &p.tm_tile, a_full + sa, 0, x0 + dx, y0 + dy, img);
+              if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+            }
+            mbar_wait(b_empty + sb, pb ^ 1);
+            mbar_expect_tx(b_full + sb, kBBytes);
+            bulk_load(smem_b + sb * kBBytes, wptr + static_cast<long>(s * p.ntaps + tap) * kBBytes, kBBytes, b_full + sb);
+            if (++sb == kBStages) { sb = 0; pb ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (one thread) ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BN);
+      int sa = 0, pa = 0, sb = 0, pb = 0;
+      int it = 0;
+      const uint32_t a_sbo = p.halo ? static_cast<uint32_t>(p.halo_pitch) * 128u : 1024u;
+      for (int item = blockIdx.x; item < total; item += gridDim.x, ++it) {
+        const int gn = item / tiles;
+        const savsr_conv_group& g = p.g[gn / p.batch];
+        const int acc = it & 1;
+        mbar_wait(t_empty + acc, ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        uint32_t accumulate = 0;
+        for (int s = 0; s < g.nsrc; ++s) {
+          if (p.halo) {
+            mbar_wait(a_full + sa, pa);
+            tc_fence_after();
+          }
+          for (int tap = 0; tap < p.ntaps; ++tap) {
+            if (!p.halo) mbar_wait(a_full + sa, pa);
+            mbar_wait(b_full + sb, pb);
+            tc_fence_after();
+            uint32_t a_addr = smem_u32(smem_a + sa * p.a_stage_bytes);
+            if (p.halo) {
+              const int dy = p.ntaps == 9 ? tap / 3 : 1, dx = p.ntaps == 9 ? tap % 3 : 1;
+              a_addr += static_cast<uint32_t>(dy * p.halo_pitch + dx) * 128u;
+            }
+            const uint32_t b_addr = smem_u32(smem_b + sb * kBBytes);
+            const uint32_t bo = p.use_base_offset ? ((a_addr >> 7) & 7u) : 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzle atom
+              umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32, a_sbo, bo), umma_desc_sw128(b_addr + k * 32, 1024u, 0u),
+                        idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(b_empty + sb);
+            if (++sb == kBStages) { sb = 0; pb ^= 1; }
+            if (!p.halo) {
+              umma_commit(a_empty + sa);
+              if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+            }
+          }
+          if (p.halo) {
+            umma_commit(a_empty + sa);
+            if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+          }
+        }
+        umma_commit(t_full + acc);
+      }
+    }
+  } else {
+    // ================================ epilogue warps ================================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int it = 0;
+    for (int item = blockIdx.x; item < total; item += gridDim.x, ++it) {
+      const int tile = item % tiles;
+      const int gn = item / tiles;
+      const int n = gn % p.batch;
+      const savsr_conv_group& g = p.g[gn / p.batch];
+      const int acc = it & 1;
+      mbar_wait(t_full + acc, (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      float v[BN];
+#pragma unroll
+      for (int j = 0; j < BN / 16; ++j) {
+        uint32_t r[16];
+        tmem_ld16(taddr + j * 16, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[j * 16 + c] = __uint_as_float(r[c]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty + acc);
+      conv_epilogue<BN>(p, g, n, tile, quad, lane, v);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ checker kernel
+// One block of 128 threads per (conv, sample, tile); thread m accumulates all N outputs of its pixel with
+// plain loads, reading the same packed (swizzled) weights.  Same epilogue.  Slow by design.
+template <int BN>
+__global__ void __launch_bounds__(128) conv_check_kernel(const __grid_constant__ ConvParams p) {
+  const int tiles = p.tiles_x * p.tiles_y;
+  const int item = blockIdx.x;
+  const int tile = item % tiles;
+  const int gn = item / tiles;
+  const int n = gn % p.batch;
+  const savsr_conv_group& g = p.g[gn / p.batch];
+  const int m = threadIdx.x;
+  const int px = (tile % p.tiles_x) * kTileW + (m & 7);
+  const int py = (tile / p.tiles_x) * kTileH + (m >> 3);
+  const long npix = static_cast<long>(p.height) * p.width;
+  const uint8_t* wptr = static_cast<const uint8_t*>(g.weight) + static_cast<long>(n) * g.weight_sample_stride;
+  float v[BN];
+#pragma unroll
+  for (int c = 0; c < BN; ++c) v[c] = 0.f;
+  for (int s = 0; s < g.nsrc; ++s) {
+    const __nv_bfloat16* src = p.arena + (static_cast<long>(g.src_slot[s]) * p.batch + n) * npix * kC;
+    for (int tap = 0; tap < p.ntaps; ++tap) {
+      const int dx = p.ntaps == 9 ? tap % 3 - 1 : 0, dy = p.ntaps == 9 ? tap / 3 - 1 : 0;
+      const int sx = px + dx, sy = py + dy;
+      const bool in = sx >= 0 && sx < p.width && sy >= 0 && sy < p.height;
+      const uint8_t* wb = wptr + static_cast<long>(s * p.ntaps + tap) * (BN * 128);
+      for (int k = 0; k < 64; ++k) {
+        const float a = in ? __bfloat162float(src[(static_cast<long>(sy) * p.width + sx) * kC + k]) : 0.f;
+#pragma unroll
+        for (int c = 0; c < BN; ++c) {
+          const int off = c * 128 + (((k >> 3) ^ (c & 7)) << 4) + (k & 7) * 2;
+          v[c] += a * __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(wb + off));
+        }
+      }
+    }
+  }
+  conv_epilogue<BN>(p, g, n, tile, m >> 5, m & 31, v);
+}
+
+// ------------------------------------------------------------------------------------------------ weight packing
+// fp32 OIHW -> packed bf16 blocks [co/n_tile][ci/64 * k*k][n_tile][64], 128-byte swizzled rows.
+__global__ void pack_weight_kernel(const float* __restrict__ w, int co_real, int co, int ci, int ks, int n_tile,
+                                   __nv_bfloat16* __restrict__ out) {
+  const long total = static_cast<long>(co) * ci * ks * ks;
+  const int taps = ks * ks;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    // idx enumerates the OUTPUT position: (ng, kb, n, k)
+    const int k = idx & 63;
+    long r = idx >> 6;
+    const int n = r % n_tile; r /= n_tile;
+    const int kb = r % ((ci / 64) * taps);
+    const int ng = r / ((ci / 64) * taps);
+    const int s = kb / taps, tap = kb % taps;
+    const int o = ng * n_tile + n, i = s * 64 + k;
+    const float val = o < co_real ? w[(static_cast<long>(o) * ci + i) * taps + tap] : 0.f;
+    const long block = static_cast<long>(ng) * ((ci / 64) * taps) + kb;
+    const long off = block * (n_tile * 64) + n * 64 + ((((k >> 3) ^ (n & 7)) << 3) | (k & 7));
+    out[off] = __float2bfloat16(val);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ arena import / export
+__global__ void arena_import_kernel(const float* __restrict__ nchw, __nv_bfloat16* __restrict__ dst, int batch, long npix) {
+  const long total = static_cast<long>(batch) * npix * kC;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int c = idx & 63;
+    const long pn = idx >> 6;
+    const long pix = pn % npix, n = pn / npix;
+    dst[idx] = __float2bfloat16(nchw[(n * kC + c) * npix + pix]);
+  }
+}
+__global__ void arena_export_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ nchw, int batch, long npix) {
+  const long total = static_cast<long>(batch) * npix * kC;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long pix = idx % npix;
+    const long nc = idx / npix;
+    const int c = nc % kC;
+    const long n = nc / kC;
+    nchw[idx] = __bfloat162float(src[(n * npix + pix) * kC + c]);
+  }
+}
+
+template <int BN>
+static int launch_conv(savsr_ctx* ctx, const ConvParams& p, int impl, cudaStream_t st) {
+  const int total = p.ngroups * p.batch * p.tiles_x * p.tiles_y;
+  if (total == 0) return 0;
+  if (impl == SAVSR_IMPL_CHECK) {
+    conv_check_kernel<BN><<<total, 128, 0, st>>>(p);
+    SAVSR_CUDA(cudaGetLastError());
+    return 0;
+  }
+  const size_t smem = 1024 + kARegionBytes + kBStages * BN * 128 + 512;
+  static bool attr_done[2] = {false, false};
+  const int ai = BN == 64 ? 0 : 1;
+  if (!attr_done[ai]) {
+    SAVSR_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_done[ai] = true;
+  }
+  const int grid = total < ctx->sm_count ? total : ctx->sm_count;
+  conv_igemm_kernel<BN><<<grid, kNumThreads, smem, st>>>(p);
+  SAVSR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace savsr
+
+using namespace savsr;
+
+extern "C" size_t savsr_packed_weight_bytes(int co, int ci, int ksize) {
+  return static_cast<size_t>(co) * ci * ksize * ksize * sizeof(__nv_bfloat16);
+}
+
+extern "C" int savsr_pack_conv_weight(const float* w_oihw, int co_real, int co, int ci, int ksize, int n_tile,
+                                      void* packed, savsr_stream st) {
+  SAVSR_REQUIRE(w_oihw && packed, "savsr_pack_conv_weight: null pointer");
+  SAVSR_REQUIRE(ksize == 1 || ksize == 3, "savsr_pack_conv_weight: ksize must be 1 or 3, got %d", ksize);
+  SAVSR_REQUIRE(n_tile == 64 || n_tile == 16, "savsr_pack_conv_weight: n_tile must be 64 or 16, got %d", n_tile);
+  SAVSR_REQUIRE(ci > 0 && ci % 64 == 0, "savsr_pack_conv_weight: ci (%d) must be a positive multiple of 64", ci);
+  SAVSR_REQUIRE(co > 0 && co % n_tile == 0 && co_real <= co && co_real > 0,
+                "savsr_pack_conv_weight: co (%d) must be a multiple of n_tile (%d) and >= co_real (%d)", co, n_tile, co_real);
+  const long total = static_cast<long>(co) * ci * ksize * ksize;
+  const int blocks = static_cast<int>((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
+  pack_weight_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(st)>>>(w_oihw, co_real, co, ci, ksize, n_tile,
+                                                                       static_cast<__nv_bfloat16*>(packed));
+  SAVSR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int savsr_arena_import(savsr_arena* a, int slot, const float* nchw, savsr_stream st) {
+  SAVSR_REQUIRE(a && nchw, "savsr_arena_import: null pointer");
+  SAVSR_REQUIRE(slot >= 0 && slot < a->nslots, "savsr_arena_import: slot %d out of range [0,%d)", slot, a->nslots);
+  const long npix = static_cast<long>(a->height) * a->width;
+  arena_import_kernel<<<1024, 256, 0, static_cast<cudaStream_t>(st)>>>(
+      nchw, a->base + static_cast<long>(slot) * a->batch * npix * kC, a->batch, npix);
+  SAVSR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int savsr_arena_export(savsr_arena* a, int slot, float* nchw, savsr_stream st) {
+  SAVSR_REQUIRE(a && nchw, "savsr_arena_export: null pointer");
+  SAVSR_REQUIRE(slot >= 0 && slot < a->nslots, "savsr_arena_export: slot %d out of range [0,%d)", slot, a->nslots);
+  const long npix = static_cast<long>(a->height) * a->width;
+  arena_export_kernel<<<1024, 256, 0, static_cast<cudaStream_t>(st)>>>(
+      a->base + static_cast<long>(slot) * a->batch * npix * kC, nchw, a->batch, npix);
+  SAVSR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int savsr_conv(savsr_ctx* ctx, savsr_arena* arena, const savsr_conv_group* groups, int ngroups, int ksize,
+                          int n_tile, int dst_mode, const savsr_rgb_skip* skip, int impl, savsr_stream st) {
+  SAVSR_REQUIRE(ctx && arena && groups, "savsr_conv: null pointer");
+  SAVSR_REQUIRE(ngroups >= 0 && ngroups <= SAVSR_MAX_GROUPS, "savsr_conv: ngroups %d out of range [0,%d]", ngroups, SAVSR_MAX_GROUPS);
+  SAVSR_REQUIRE(ksize == 1 || ksize == 3, "savsr_conv: ksize must be 1 or 3, got %d", ksize);
+  SAVSR_REQUIRE(impl >= SAVSR_IMPL_TCGEN05_TAP && impl <= SAVSR_IMPL_CHECK, "savsr_conv: unknown impl %d", impl);
+  SAVSR_REQUIRE((n_tile == 64 && dst_mode == SAVSR_DST_ARENA) || (n_tile == 16 && (dst_mode == SAVSR_DST_AUX16 || dst_mode == SAVSR_DST_RGB)),
+                "savsr_conv: n_tile %d does not match dst_mode %d", n_tile, dst_mode);
+  SAVSR_REQUIRE(dst_mode != SAVSR_DST_RGB || (skip && skip->x), "savsr_conv: SAVSR_DST_RGB needs the skip arguments");
+  if (ngroups == 0) return 0;
+
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.tm_tile = arena->tm_tile;
+  p.tm_halo = arena->tm_halo;
+  for (int i = 0; i < ngroups; ++i) {
+    const savsr_conv_group& g = groups[i];
+    SAVSR_REQUIRE(g.nsrc >= 1 && g.nsrc <= SAVSR_MAX_SRC, "savsr_conv: group %d nsrc %d out of range", i, g.nsrc);
+    SAVSR_REQUIRE(g.weight != nullptr, "savsr_conv: group %d has no weights", i);
+    for (int s = 0; s < g.nsrc; ++s) {
+      SAVSR_REQUIRE(g.src_slot[s] >= 0 && g.src_slot[s] < arena->nslots, "savsr_conv: group %d source slot %d out of range", i, g.src_slot[s]);
+      SAVSR_REQUIRE(dst_mode != SAVSR_DST_ARENA || g.src_slot[s] != g.dst_slot, "savsr_conv: group %d writes slot %d that it also convolves", i, g.dst_slot);
+    }
+    if (dst_mode == SAVSR_DST_ARENA) {
+      SAVSR_REQUIRE(g.dst_slot >= 0 && g.dst_slot < arena->nslots, "savsr_conv: group %d dst slot %d out of range", i, g.dst_slot);
+      SAVSR_REQUIRE(g.res1_slot < arena->nslots && g.res2_slot < arena->nslots, "savsr_conv: group %d residual slot out of range", i);
+    } else {
+      SAVSR_REQUIRE(g.aux_dst != nullptr, "savsr_conv: group %d needs aux_dst for dst_mode %d", i, dst_mode);
+    }
+    p.g[i] = g;
+  }
+  if (skip) p.skip = *skip;
+  p.arena = arena->base;
+  p.ngroups = ngroups;
+  p.batch = arena->batch;
+  p.height = arena->height;
+  p.width = arena->width;
+  p.tiles_x = arena->tiles_x;
+  p.tiles_y = arena->tiles_y;
+  p.ntaps = ksize * ksize;
+  p.halo = (impl == SAVSR_IMPL_TCGEN05_HALO && ksize == 3) ? 1 : 0;
+  p.halo_pitch = ctx->halo_pitch;
+  p.use_base_offset = ctx->halo_base_offset;
+  if (p.halo) {
+    const int bytes = p.halo_pitch * (kTileH + 2) * 128;
+    p.a_stage_bytes = (bytes + 1023) / 1024 * 1024;
+    p.a_stages = kARegionBytes / p.a_stage_bytes;
+    if (p.a_stages > kMaxAStages) p.a_stages = kMaxAStages;
+  } else {
+    p.a_stage_bytes = kTileM * 128;
+    p.a_stages = kMaxAStages;
+  }
+  p.dst_mode = dst_mode;
+  if (n_tile == 64) return launch_conv<64>(ctx, p, impl, static_cast<cudaStream_t>(st));
+  return launch_conv<16>(ctx, p, impl, static_cast<cudaStream_t>(st));
+}

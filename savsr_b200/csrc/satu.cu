@@ -1,0 +1,382 @@
+// SATU kernels (savsr_arch.py:217-376): bit-exact coordinate / index kernel + per-scale MLP table,
+// spatio-temporal filtering, and the fused HR gather with the routed compress/expand experts.
+//
+// Coordinate arithmetic follows the reference's fp32 operation order exactly (CPU semantics: IEEE
+// division by the scale, no FMA contraction), hence the explicit __fadd_rn/__fmul_rn/__fdiv_rn.
+#include "common.cuh"
+
+namespace savsr {
+
+__device__ __forceinline__ float rel_q(int i, float s) { return __fdiv_rn(__fadd_rn(static_cast<float>(i), 0.5f), s); }
+// R(i) = (q - floor(q + 1e-3)) - 0.5   (savsr_arch.py:331, 333)
+__device__ __forceinline__ float rel_coord(int i, float s, int* cell) {
+  const float q = rel_q(i, s);
+  const float fl = floorf(__fadd_rn(q, 1e-3f));
+  if (cell) *cell = static_cast<int>(fl);
+  return __fsub_rn(__fsub_rn(q, fl), 0.5f);
+}
+// normalised base grid coordinate (savsr_arch.py:275-280), zero offset
+__device__ __forceinline__ float base_norm(int i, float s, int n_lr) {
+  float g = __fsub_rn(__fdiv_rn(__fadd_rn(static_cast<float>(i), 0.5f), s), 0.5f);
+  g = __fsub_rn(__fdiv_rn(__fmul_rn(g, 2.f), static_cast<float>(n_lr - 1)), 1.f);
+  return g;
+}
+// ATen grid_sampler un-normalisation, align_corners = True
+__device__ __forceinline__ float unnormalize(float g, int n_lr) {
+  return __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.f), 2.f), static_cast<float>(n_lr - 1));
+}
+
+__global__ void satu_axis_kernel(int n_out, int n_lr, float s, float* rel, int32_t* cell, float* base, int32_t* corner) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  int c;
+  const float r = rel_coord(i, s, &c);
+  if (rel) rel[i] = r;
+  if (cell) cell[i] = c;
+  const float g = base_norm(i, s, n_lr);
+  if (base) base[i] = g;
+  if (corner) corner[i] = static_cast<int32_t>(floorf(unnormalize(g, n_lr)));
+}
+
+// table[pix] = (offset_x, offset_y, st_offset_x, st_offset_y, r0..r3), the 4 -> 64 -> 64 MLP and its heads
+// (savsr_arch.py:335-351).  One HR pixel per thread, weights in shared memory.
+__global__ void __launch_bounds__(128) satu_table_kernel(const savsr_satu_weights wts, int H, int W, float s_h, float s_w,
+                                                         float* __restrict__ table) {
+  __shared__ __align__(16) float w0[4 * 64];    // [in][out]
+  __shared__ __align__(16) float w2[64 * 64];   // [in][out]
+  __shared__ __align__(16) float wh[8 * 64];    // [head][in]: offset(2), st_offset(2), routing(4)
+  __shared__ float b0[64], b2[64], bh[8];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) w0[i] = wts.body0_w[(i & 63) * 4 + (i >> 6)];
+  for (int i = threadIdx.x; i < 4096; i += blockDim.x) w2[i] = wts.body2_w[(i & 63) * 64 + (i >> 6)];
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+    const int hd = i >> 6, j = i & 63;
+    wh[i] = hd < 2 ? wts.offset_w[hd * 64 + j] : hd < 4 ? wts.st_offset_w[(hd - 2) * 64 + j] : wts.routing_w[(hd - 4) * 64 + j];
+  }
+  if (threadIdx.x < 64) { b0[threadIdx.x] = wts.body0_b[threadIdx.x]; b2[threadIdx.x] = wts.body2_b[threadIdx.x]; }
+  if (threadIdx.x < 8) {
+    const int hd = threadIdx.x;
+    bh[hd] = hd < 2 ? wts.offset_b[hd] : hd < 4 ? wts.st_offset_b[hd - 2] : wts.routing_b[hd - 4];
+  }
+  __syncthreads();
+  const long pix = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (pix >= static_cast<long>(H) * W) return;
+  const int i = pix / W, j = pix % W;
+  float in[4];
+  in[0] = __fdiv_rn(1.f, s_w);  // channel 0 is 1/s_w (savsr_arch.py:336)
+  in[1] = __fdiv_rn(1.f, s_h);
+  in[2] = rel_coord(i, s_h, nullptr);
+  in[3] = rel_coord(j, s_w, nullptr);
+  float e1[64];
+#pragma unroll
+  for (int o = 0; o < 64; ++o) {
+    float a = b0[o];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a += w0[k * 64 + o] * in[k];
+    e1[o] = fmaxf(a, 0.f);
+  }
+  float e2[64];
+#pragma unroll
+  for (int o = 0; o < 64; ++o) e2[o] = b2[o];
+#pragma unroll 4
+  for (int k = 0; k < 64; ++k) {
+    const float a = e1[k];
+    const float4* wr = reinterpret_cast<const float4*>(w2 + k * 64);
+#pragma unroll
+    for (int o4 = 0; o4 < 16; ++o4) {
+      const float4 wv = wr[o4];
+      e2[4 * o4 + 0] += a * wv.x; e2[4 * o4 + 1] += a * wv.y;
+      e2[4 * o4 + 2] += a * wv.z; e2[4 * o4 + 3] += a * wv.w;
+    }
+  }
+  float out[8];
+#pragma unroll
+  for (int hd = 0; hd < 8; ++hd) {
+    float a = bh[hd];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) a += wh[hd * 64 + k] * fmaxf(e2[k], 0.f);
+    out[hd] = hd < 4 ? a : 1.f / (1.f + expf(-a));
+  }
+  float4* d = reinterpret_cast<float4*>(table + pix * 8);
+  d[0] = make_float4(out[0], out[1], out[2], out[3]);
+  d[1] = make_float4(out[4], out[5], out[6], out[7]);
+}
+
+// sta[c] = sum_tap xpad[y+u, x+v, c] * K[tap][c], replicate padding on the h x w region (savsr_arch.py:297-313).
+// One (pixel, 8-channel chunk) per thread; 16-byte loads of bf16.
+__global__ void __launch_bounds__(256) satu_sta_kernel(const __nv_bfloat16* __restrict__ arena, int batch, int hp, int wp,
+                                                       int h, int w, int x_slot, int kslot0, int dst_slot) {
+  const long npix = static_cast<long>(hp) * wp;
+  const long id = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  const int n = blockIdx.y;
+  if (id >= npix * 8) return;
+  const int chunk = id & 7;
+  const long pix = id >> 3;
+  const int py = pix / wp, px = pix % wp;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (py < h && px < w) {
+    const __nv_bfloat16* xs = arena + (static_cast<long>(x_slot) * batch + n) * npix * kC;
+#pragma unroll 5
+    for (int tap = 0; tap < 25; ++tap) {
+      const int sy = min(max(py + tap / 5 - 2, 0), h - 1);
+      const int sx = min(max(px + tap % 5 - 2, 0), w - 1);
+      const uint4 xv = *reinterpret_cast<const uint4*>(xs + (static_cast<long>(sy) * wp + sx) * kC + chunk * 8);
+      const uint4 kv = *reinterpret_cast<const uint4*>(arena + ((static_cast<long>(kslot0 + tap) * batch + n) * npix + pix) * kC + chunk * 8);
+      acc[0] += bf16_lo(xv.x) * bf16_lo(kv.x); acc[1] += bf16_hi(xv.x) * bf16_hi(kv.x);
+      acc[2] += bf16_lo(xv.y) * bf16_lo(kv.y); acc[3] += bf16_hi(xv.y) * bf16_hi(kv.y);
+      acc[4] += bf16_lo(xv.z) * bf16_lo(kv.z); acc[5] += bf16_hi(xv.z) * bf16_hi(kv.z);
+      acc[6] += bf16_lo(xv.w) * bf16_lo(kv.w); acc[7] += bf16_hi(xv.w) * bf16_hi(kv.w);
+    }
+  }
+  uint4 o;
+  o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
+  o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
+  *reinterpret_cast<uint4*>(const_cast<__nv_bfloat16*>(arena) + ((static_cast<long>(dst_slot) * batch + n) * npix + pix) * kC + chunk * 8) = o;
+}
+
+// ------------------------------------------------------------------------------------------------ HR gather
+struct GatherParams {
+  const __nv_bfloat16* lr;
+  __nv_bfloat16* hr;
+  const float* table;
+  const float* base_y;
+  const float* base_x;
+  const float* compress;  // [4][8][64]
+  const float* expand;    // [4][64][8]
+  int batch, hp, wp, h, w, H, W;
+  int x_slot, sta_slot, sta_dst, fea_dst;
+};
+
+struct Corner4 {
+  int off[4];   // element offset of the corner pixel inside the LR image (pixel index * 64), -1 = outside
+  float wt[4];
+};
+
+// bilinear corners, zeros padding, align_corners = True (ATen grid_sampler_2d)
+__device__ __forceinline__ Corner4 make_corners(float gx, float gy, int h, int w, int wp) {
+  const float ix = unnormalize(gx, w), iy = unnormalize(gy, h);
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  const int x0 = static_cast<int>(x0f), y0 = static_cast<int>(y0f);
+  const float tx = ix - x0f, ty = iy - y0f;
+  Corner4 c;
+  const int xs[2] = {x0, x0 + 1}, ys[2] = {y0, y0 + 1};
+  const float wx[2] = {1.f - tx, tx}, wy[2] = {1.f - ty, ty};
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const bool in = xs[b] >= 0 && xs[b] < w && ys[a] >= 0 && ys[a] < h;
+      c.off[a * 2 + b] = in ? (ys[a] * wp + xs[b]) * kC : -1;
+      c.wt[a * 2 + b] = wy[a] * wx[b];
+    }
+  return c;
+}
+
+constexpr int kGatherPix = 128;
+constexpr int kFStride = 65;
+
+// Block = 128 consecutive HR pixels of one sample.
+//  phase A: (pixel, 8-channel chunk) per thread-iteration: bilinear gather of x -> f (smem, fp32) and of
+//           sta -> HR slot sta_dst (bf16, coalesced 16-byte stores).
+//  phase B: one pixel per thread: t = sum_e r_e (Wc_e f), fea = sum_e r_e (We_e t) + f   (matrix-free; the
+//           single-sum shortcut is wrong because r is a per-expert sigmoid -- SURVEY.md A.3 item 5).
+//  phase C: coalesced bf16 store of fea -> HR slot fea_dst.
+__global__ void __launch_bounds__(kGatherPix) satu_gather_kernel(const GatherParams p) {
+  extern __shared__ __align__(16) float sm[];
+  float* f_s = sm;                                // [128][65]
+  float* wc_s = f_s + kGatherPix * kFStride;      // [64 c][32 (e*8+k)]
+  float* we_s = wc_s + 64 * 32;                   // [32 (e*8+k)][64 c]
+  Corner4* cx = reinterpret_cast<Corner4*>(we_s + 32 * 64);  // [128] corners for x
+  Corner4* cs = cx + kGatherPix;                             // [128] corners for sta
+  float* rt = reinterpret_cast<float*>(cs + kGatherPix);     // [128][4] routing
+
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
+    const int c = i >> 5, j = i & 31;              // compress[e][k][c] with j = e*8+k
+    wc_s[i] = p.compress[j * 64 + c];
+    const int jj = i >> 6, cc = i & 63;            // expand[e][c][k] with jj = e*8+k
+    we_s[i] = p.expand[((jj >> 3) * 64 + cc) * 8 + (jj & 7)];
+  }
+  const int n = blockIdx.y;
+  const long NPIX = static_cast<long>(p.H) * p.W;
+  const long pix0 = blockIdx.x * static_cast<long>(kGatherPix);
+  {
+    const long pix = pix0 + threadIdx.x;
+    if (pix < NPIX) {
+      const int i = pix / p.W, j = pix % p.W;
+      const float4 t0 = *reinterpret_cast<const float4*>(p.table + pix * 8);
+      const float4 t1 = *reinterpret_cast<const float4*>(p.table + pix * 8 + 4);
+      const float bx = p.base_x[j], by = p.base_y[i];
+      const float wm1 = static_cast<float>(p.w - 1), hm1 = static_cast<float>(p.h - 1);
+      // grid = base + offset * 2 / (n - 1)   (savsr_arch.py:285-287)
+      cx[threadIdx.x] = make_corners(__fadd_rn(bx, __fdiv_rn(__fmul_rn(t0.x, 2.f), wm1)),
+                                     __fadd_rn(by, __fdiv_rn(__fmul_rn(t0.y, 2.f), hm1)), p.h, p.w, p.wp);
+      cs[threadIdx.x] = make_corners(__fadd_rn(bx, __fdiv_rn(__fmul_rn(t0.z, 2.f), wm1)),
+                                     __fadd_rn(by, __fdiv_rn(__fmul_rn(t0.w, 2.f), hm1)), p.h, p.w, p.wp);
+      rt[threadIdx.x * 4 + 0] = t1.x; rt[threadIdx.x * 4 + 1] = t1.y;
+      rt[threadIdx.x * 4 + 2] = t1.z; rt[threadIdx.x * 4 + 3] = t1.w;
+    }
+  }
+  __syncthreads();
+
+  const long lr_img = static_cast<long>(p.hp) * p.wp * kC;
+  const __nv_bfloat16* xs = p.lr + (static_cast<long>(p.x_slot) * p.batch + n) * lr_img;
+  const __nv_bfloat16* ss = p.lr + (static_cast<long>(p.sta_slot) * p.batch + n) * lr_img;
+  __nv_bfloat16* sta_out = p.hr + (static_cast<long>(p.sta_dst) * p.batch + n) * NPIX * kC;
+  __nv_bfloat16* fea_out = p.hr + (static_cast<long>(p.fea_dst) * p.batch + n) * NPIX * kC;
+
+  // ---- phase A
+  for (int it = 0; it < 8; ++it) {
+    const int id = it * kGatherPix + threadIdx.x;
+    const int lp = id >> 3, chunk = id & 7;
+    if (pix0 + lp >= NPIX) continue;
+    float a[8], b[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { a[e] = 0.f; b[e] = 0.f; }
+    const Corner4 c1 = cx[lp], c2 = cs[lp];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (c1.off[q] >= 0) {
+        const uint4 v = *reinterpret_cast<const uint4*>(xs + c1.off[q] + chunk * 8);
+        const float wgt = c1.wt[q];
+        a[0] += wgt * bf16_lo(v.x); a[1] += wgt * bf16_hi(v.x); a[2] += wgt * bf16_lo(v.y); a[3] += wgt * bf16_hi(v.y);
+        a[4] += wgt * bf16_lo(v.z); a[5] += wgt * bf16_hi(v.z); a[6] += wgt * bf16_lo(v.w); a[7] += wgt * bf16_hi(v.w);
+      }
+      if (c2.off[q] >= 0) {
+        const uint4 v = *reinterpret_cast<const uint4*>(ss + c2.off[q] + chunk * 8);
+        const float wgt = c2.wt[q];
+        b[0] += wgt * bf16_lo(v.x); b[1] += wgt * bf16_hi(v.x); b[2] += wgt * bf16_lo(v.y); b[3] += wgt * bf16_hi(v.y);
+        b[4] += wgt * bf16_lo(v.z); b[5] += wgt * bf16_hi(v.z); b[6] += wgt * bf16_lo(v.w); b[7] += wgt * bf16_hi(v.w);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f_s[lp * kFStride + chunk * 8 + e] = a[e];
+    uint4 o;
+    o.x = pack_bf16(b[0], b[1]); o.y = pack_bf16(b[2], b[3]); o.z = pack_bf16(b[4], b[5]); o.w = pack_bf16(b[6], b[7]);
+    *reinterpret_cast<uint4*>(sta_out + (pix0 + lp) * kC + chunk * 8) = o;
+  }
+  __syncthreads();
+
+  // ---- phase B
+  if (pix0 + threadIdx.x < NPIX) {
+    float* f = f_s + threadIdx.x * kFStride;
+    float u[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) u[j] = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < 64; ++c) {
+      const float fc = f[c];
+      const float4* wr = reinterpret_cast<const float4*>(wc_s + c * 32);
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 wv = wr[j4];
+        u[4 * j4 + 0] += fc * wv.x; u[4 * j4 + 1] += fc * wv.y; u[4 * j4 + 2] += fc * wv.z; u[4 * j4 + 3] += fc * wv.w;
+      }
+    }
+    const float r[4] = {rt[threadIdx.x * 4 + 0], rt[threadIdx.x * 4 + 1], rt[threadIdx.x * 4 + 2], rt[threadIdx.x * 4 + 3]};
+    float t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = r[0] * u[k] + r[1] * u[8 + k] + r[2] * u[16 + k] + r[3] * u[24 + k];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) u[e * 8 + k] = r[e] * t[k];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float acc[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) acc[c] = f[half * 32 + c];
+#pragma unroll 4
+      for (int j = 0; j < 32; ++j) {
+        const float vj = u[j];
+        const float4* wr = reinterpret_cast<const float4*>(we_s + j * 64 + half * 32);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 wv = wr[c4];
+          acc[4 * c4 + 0] += vj * wv.x; acc[4 * c4 + 1] += vj * wv.y; acc[4 * c4 + 2] += vj * wv.z; acc[4 * c4 + 3] += vj * wv.w;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) f[half * 32 + c] = acc[c];
+    }
+  }
+  __syncthreads();
+
+  // ---- phase C
+  for (int it = 0; it < 8; ++it) {
+    const int id = it * kGatherPix + threadIdx.x;
+    const int lp = id >> 3, chunk = id & 7;
+    if (pix0 + lp >= NPIX) continue;
+    const float* f = f_s + lp * kFStride + chunk * 8;
+    uint4 o;
+    o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+    *reinterpret_cast<uint4*>(fea_out + (pix0 + lp) * kC + chunk * 8) = o;
+  }
+}
+
+constexpr size_t kGatherSmem = sizeof(float) * (kGatherPix * kFStride + 64 * 32 + 32 * 64 + kGatherPix * 4) + 2 * kGatherPix * sizeof(Corner4);
+
+}  // namespace savsr
+
+using namespace savsr;
+
+extern "C" int savsr_satu_index(savsr_ctx* ctx, const savsr_satu_weights* wts, int h, int w, int H, int W, float s_h,
+                                float s_w, float* rel_y, float* rel_x, int32_t* cell_y, int32_t* cell_x, float* base_y,
+                                float* base_x, int32_t* corner_y, int32_t* corner_x, float* table, savsr_stream st_) {
+  SAVSR_REQUIRE(ctx, "savsr_satu_index: null context");
+  SAVSR_REQUIRE(h >= 2 && w >= 2 && H >= 1 && W >= 1, "savsr_satu_index: bad sizes lr %dx%d hr %dx%d", h, w, H, W);
+  SAVSR_REQUIRE(s_h > 0.f && s_w > 0.f, "savsr_satu_index: scale must be positive, got (%g, %g)", s_h, s_w);
+  cudaStream_t st = static_cast<cudaStream_t>(st_);
+  satu_axis_kernel<<<(H + 127) / 128, 128, 0, st>>>(H, h, s_h, rel_y, cell_y, base_y, corner_y);
+  satu_axis_kernel<<<(W + 127) / 128, 128, 0, st>>>(W, w, s_w, rel_x, cell_x, base_x, corner_x);
+  if (table) {
+    SAVSR_REQUIRE(wts && wts->body0_w && wts->body0_b && wts->body2_w && wts->body2_b && wts->routing_w && wts->routing_b &&
+                  wts->offset_w && wts->offset_b && wts->st_offset_w && wts->st_offset_b,
+                  "savsr_satu_index: table requested but MLP weights missing");
+    const long npix = static_cast<long>(H) * W;
+    satu_table_kernel<<<static_cast<unsigned>((npix + 127) / 128), 128, 0, st>>>(*wts, H, W, s_h, s_w, table);
+  }
+  SAVSR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int savsr_satu_sta(savsr_ctx* ctx, savsr_arena* arena, int x_slot, int kslot0, int dst_slot, int h, int w,
+                              savsr_stream st) {
+  SAVSR_REQUIRE(ctx && arena, "savsr_satu_sta: null pointer");
+  SAVSR_REQUIRE(x_slot >= 0 && x_slot < arena->nslots && dst_slot >= 0 && dst_slot < arena->nslots && kslot0 >= 0 &&
+                kslot0 + 25 <= arena->nslots, "savsr_satu_sta: slot out of range");
+  SAVSR_REQUIRE(h >= 1 && w >= 1 && h <= arena->height && w <= arena->width, "savsr_satu_sta: region %dx%d exceeds arena", h, w);
+  if (arena->batch == 0) return 0;
+  const long ids = static_cast<long>(arena->height) * arena->width * 8;
+  satu_sta_kernel<<<dim3(static_cast<unsigned>((ids + 255) / 256), arena->batch), 256, 0, static_cast<cudaStream_t>(st)>>>(
+      arena->base, arena->batch, arena->height, arena->width, h, w, x_slot, kslot0, dst_slot);
+  SAVSR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int savsr_satu_gather(savsr_ctx* ctx, savsr_arena* lr, int x_slot, int sta_slot, int h, int w, savsr_arena* hr,
+                                 int sta_dst, int fea_dst, const float* table, const float* base_y, const float* base_x,
+                                 const savsr_satu_weights* wts, savsr_stream st) {
+  SAVSR_REQUIRE(ctx && lr && hr && table && base_y && base_x && wts && wts->compress && wts->expand, "savsr_satu_gather: null pointer");
+  SAVSR_REQUIRE(lr->batch == hr->batch, "savsr_satu_gather: LR batch %d != HR batch %d", lr->batch, hr->batch);
+  SAVSR_REQUIRE(x_slot >= 0 && x_slot < lr->nslots && sta_slot >= 0 && sta_slot < lr->nslots, "savsr_satu_gather: LR slot out of range");
+  SAVSR_REQUIRE(sta_dst >= 0 && sta_dst < hr->nslots && fea_dst >= 0 && fea_dst < hr->nslots && sta_dst != fea_dst,
+                "savsr_satu_gather: HR slot out of range");
+  SAVSR_REQUIRE(h >= 2 && w >= 2 && h <= lr->height && w <= lr->width, "savsr_satu_gather: region %dx%d exceeds LR arena", h, w);
+  if (lr->batch == 0) return 0;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SAVSR_CUDA(cudaFuncSetAttribute(satu_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGatherSmem)));
+    attr_done = true;
+  }
+  GatherParams p;
+  p.lr = lr->base; p.hr = hr->base; p.table = table; p.base_y = base_y; p.base_x = base_x;
+  p.compress = wts->compress; p.expand = wts->expand;
+  p.batch = lr->batch; p.hp = lr->height; p.wp = lr->width; p.h = h; p.w = w; p.H = hr->height; p.W = hr->width;
+  p.x_slot = x_slot; p.sta_slot = sta_slot; p.sta_dst = sta_dst; p.fea_dst = fea_dst;
+  const long npix = static_cast<long>(p.H) * p.W;
+  satu_gather_kernel<<<dim3(static_cast<unsigned>((npix + kGatherPix - 1) / kGatherPix), lr->batch), kGatherPix, kGatherSmem,
+                       static_cast<cudaStream_t>(st)>>>(p);
+  SAVSR_CUDA(cudaGetLastError());
+  return 0;
+}

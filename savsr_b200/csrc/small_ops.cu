@@ -1,0 +1,482 @@
+// CUDA-core kernels around the tensor-core convolutions: first-layer convs on the fp32 input window,
+// the OSA-Conv prologue (pool -> scale_routing MLP -> ScaleAttention -> per-sample kernel assembly),
+// RCAB channel attention, and the OSAdapt mask tail.  All HBM/L2-bound or latency-bound by nature;
+// they use coalesced 128-bit accesses and keep weights in shared memory.
+#include "common.cuh"
+
+namespace savsr {
+
+// ------------------------------------------------------------------------------------------------ first-layer convs
+constexpr int kMaxFront = 8;
+struct FrontParams {
+  savsr_front_group g[kMaxFront];
+  const float* x;
+  __nv_bfloat16* arena;
+  int ngroups, batch, t, h, w, hp, wp;
+};
+
+// dst = LeakyReLU_0.2(conv3x3(cat(frames)) + bias) on the reflect-padded (even-sized) frames.
+// grid (pixel blocks, batch, groups), 128 threads, one pixel x 64 output channels per thread.
+__global__ void __launch_bounds__(128) front_conv_kernel(const __grid_constant__ FrontParams p) {
+  __shared__ __align__(16) float w_s[54 * 64];  // [cin*9][64]
+  __shared__ float b_s[64];
+  const savsr_front_group& g = p.g[blockIdx.z];
+  const int cin = 3 * g.nframes;
+  const int kk = cin * 9;
+  for (int i = threadIdx.x; i < kk * 64; i += blockDim.x) {
+    const int o = i & 63, r = i >> 6;  // r = ci*9 + tap
+    w_s[i] = g.weight[o * kk + r];
+  }
+  if (threadIdx.x < 64) b_s[threadIdx.x] = g.bias[threadIdx.x];
+  __syncthreads();
+  const int n = blockIdx.y;
+  const long npix = static_cast<long>(p.hp) * p.wp;
+  const long pix = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (pix >= npix) return;
+  const int py = pix / p.wp, px = pix % p.wp;
+  float acc[64];
+#pragma unroll
+  for (int o = 0; o < 64; ++o) acc[o] = b_s[o];
+  const long plane = static_cast<long>(p.h) * p.w;
+  for (int f = 0; f < g.nframes; ++f) {
+    const float* fr = p.x + (static_cast<long>(n) * p.t + g.frame[f]) * 3 * plane;
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int sy = py + tap / 3 - 1, sx = px + tap % 3 - 1;
+        float a = 0.f;
+        if (sy >= 0 && sy < p.hp && sx >= 0 && sx < p.wp) {
+          const int ry = sy < p.h ? sy : 2 * p.h - 2 - sy;  // reflect pad of savsr_arch.py:688
+          const int rx = sx < p.w ? sx : 2 * p.w - 2 - sx;
+          a = __ldg(fr + c * plane + static_cast<long>(ry) * p.w + rx);
+        }
+        const float4* wr = reinterpret_cast<const float4*>(w_s + ((f * 3 + c) * 9 + tap) * 64);
+#pragma unroll
+        for (int o4 = 0; o4 < 16; ++o4) {
+          const float4 wv = wr[o4];
+          acc[4 * o4 + 0] += a * wv.x; acc[4 * o4 + 1] += a * wv.y;
+          acc[4 * o4 + 2] += a * wv.z; acc[4 * o4 + 3] += a * wv.w;
+        }
+      }
+    }
+  }
+  uint4* d = reinterpret_cast<uint4*>(p.arena + ((static_cast<long>(g.dst_slot) * p.batch + n) * npix + pix) * kC);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float r[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float v = acc[8 * j + e];
+      r[e] = v > 0.f ? v : 0.2f * v;
+    }
+    uint4 u;
+    u.x = pack_bf16(r[0], r[1]); u.y = pack_bf16(r[2], r[3]);
+    u.z = pack_bf16(r[4], r[5]); u.w = pack_bf16(r[6], r[7]);
+    d[j] = u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ OSA prologue
+constexpr int kMaxOsa = 4;
+struct OsaLaunch {
+  savsr_osa_params c[kMaxOsa];
+  int nconvs, batch, npart, npix;
+  float inv_h, inv_w;
+};
+__host__ __device__ inline int osa_scratch_stride(int ci) { return 5 * ci + 192; }
+__host__ __device__ inline int osa_off_h1(int ci) { return ci + 8; }
+__host__ __device__ inline int osa_off_v2(int ci) { return 3 * ci + 8; }
+__host__ __device__ inline int osa_off_att(int ci) { return 4 * ci + 8; }
+
+// vin = [1/s_h, 1/s_w, mean(x)] (savsr_arch.py:143-146).  grid (nsrc_max, batch, nconvs), 256 threads.
+__global__ void __launch_bounds__(256) osa_pool_kernel(const __grid_constant__ OsaLaunch L) {
+  const savsr_osa_params& c = L.c[blockIdx.z];
+  const int s = blockIdx.x, n = blockIdx.y;
+  if (s * 64 >= c.ci) return;
+  __shared__ float red[4][64];
+  const int ch = threadIdx.x & 63, part = threadIdx.x >> 6;
+  const float* src = c.pool[s] + static_cast<long>(n) * L.npart * kC;
+  float acc = 0.f;
+  for (int q = part; q < L.npart; q += 4) acc += src[q * kC + ch];
+  red[part][ch] = acc;
+  __syncthreads();
+  float* vin = c.scratch + static_cast<long>(n) * osa_scratch_stride(c.ci);
+  if (part == 0) {
+    const float sum = (red[0][ch] + red[1][ch]) + (red[2][ch] + red[3][ch]);
+    vin[2 + s * 64 + ch] = sum / static_cast<float>(L.npix);
+  }
+  if (s == 0 && threadIdx.x == 0) {
+    vin[0] = L.inv_h;
+    vin[1] = L.inv_w;
+  }
+}
+
+// One Linear + ReLU layer of scale_routing (savsr_arch.py:123-128).  layer 0: [2ci][ci+2], layer 1: [ci][2ci].
+// grid (row blocks, nconvs), 256 threads = 8 warps, one output row per warp, all samples per row.
+__global__ void __launch_bounds__(256) osa_linear_kernel(const __grid_constant__ OsaLaunch L, int layer) {
+  const savsr_osa_params& c = L.c[blockIdx.y];
+  const int rows = layer == 0 ? 2 * c.ci : c.ci;
+  const int len = layer == 0 ? c.ci + 2 : 2 * c.ci;
+  const int in_off = layer == 0 ? 0 : osa_off_h1(c.ci);
+  const int out_off = layer == 0 ? osa_off_h1(c.ci) : osa_off_v2(c.ci);
+  const float* W = layer == 0 ? c.r0_w : c.r2_w;
+  const float* B = layer == 0 ? c.r0_b : c.r2_b;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  const float* wr = W + static_cast<long>(row) * len;
+  for (int n = 0; n < L.batch; ++n) {
+    const float* in = c.scratch + static_cast<long>(n) * osa_scratch_stride(c.ci) + in_off;
+    float acc = 0.f;
+    for (int i = lane; i < len; i += 32) acc += __ldg(wr + i) * in[i];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) c.scratch[static_cast<long>(n) * osa_scratch_stride(c.ci) + out_off + row] = fmaxf(acc + B[row], 0.f);
+  }
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ScaleAttention (savsr_arch.py:91-96): z = ReLU(BN(fc v)); ca/fa/sa = sigmoid heads; ka = softmax head (T = 1).
+// grid (batch, nconvs), 256 threads.
+__global__ void __launch_bounds__(256) osa_attention_kernel(const __grid_constant__ OsaLaunch L) {
+  const savsr_osa_params& c = L.c[blockIdx.y];
+  const int n = blockIdx.x;
+  __shared__ float z[32];
+  __shared__ float logit[8];
+  float* sc = c.scratch + static_cast<long>(n) * osa_scratch_stride(c.ci);
+  const float* v2 = sc + osa_off_v2(c.ci);
+  float* att = sc + osa_off_att(c.ci);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int a = warp; a < c.att; a += 8) {
+    float acc = 0.f;
+    for (int i = lane; i < c.ci; i += 32) acc += __ldg(c.fc_w + a * c.ci + i) * v2[i];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) z[a] = fmaxf(acc * c.bn_scale[a] + c.bn_shift[a], 0.f);
+  }
+  __syncthreads();
+  const int nout = c.ci + c.co + 9 + 8;
+  for (int j = threadIdx.x; j < nout; j += blockDim.x) {
+    const float* w;
+    float b;
+    int kind;  // 0 sigmoid, 1 softmax logit
+    int local;
+    if (j < c.ci) { w = c.ch_w + j * c.att; b = c.ch_b[j]; kind = 0; local = j; }
+    else if (j < c.ci + c.co) { local = j - c.ci; w = c.fl_w + local * c.att; b = c.fl_b[local]; kind = 0; }
+    else if (j < c.ci + c.co + 9) { local = j - c.ci - c.co; w = c.sp_w + local * c.att; b = c.sp_b[local]; kind = 0; }
+    else { local = j - c.ci - c.co - 9; w = c.kn_w + local * c.att; b = c.kn_b[local]; kind = 1; }
+    float acc = b;
+    for (int a = 0; a < c.att; ++a) acc += w[a] * z[a];
+    if (kind == 0) att[j] = sigmoidf_(acc);
+    else logit[local] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float mx = logit[0];
+    for (int k = 1; k < 8; ++k) mx = fmaxf(mx, logit[k]);
+    float e[8], sum = 0.f;
+    for (int k = 0; k < 8; ++k) { e[k] = expf(logit[k] - mx); sum += e[k]; }
+    for (int k = 0; k < 8; ++k) att[c.ci + c.co + 9 + k] = e[k] / sum;
+  }
+}
+
+// W'[o,i,u,v] = fa[o] ca[i] sa[u,v] sum_k ka[k] bank[k,o,i,u,v]  -> packed bf16 K-blocks (n_tile 64).
+// grid (ceil(co*ci/256), nconvs), thread = (o, i), bank values kept in registers across samples.
+__global__ void __launch_bounds__(256) osa_assemble_kernel(const __grid_constant__ OsaLaunch L) {
+  const savsr_osa_params& c = L.c[blockIdx.y];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= c.co * c.ci) return;
+  const int i = idx % c.ci, o = idx / c.ci;
+  float bk[8][9];
+  const long per_k = static_cast<long>(c.co) * c.ci * 9;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float* src = c.bank + k * per_k + (static_cast<long>(o) * c.ci + i) * 9;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) bk[k][t] = __ldg(src + t);
+  }
+  const int s = i >> 6, kk = i & 63;
+  const long sample_elems = static_cast<long>(c.co) * c.ci * 9;
+  const int inner = o * 64 + ((((kk >> 3) ^ (o & 7)) << 3) | (kk & 7));
+  for (int n = 0; n < L.batch; ++n) {
+    const float* att = c.scratch + static_cast<long>(n) * osa_scratch_stride(c.ci) + osa_off_att(c.ci);
+    const float ca = att[i], fa = att[c.ci + o];
+    const float* sa = att + c.ci + c.co;
+    const float* ka = sa + 9;
+    __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(c.packed) + n * sample_elems;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc += ka[k] * bk[k][t];
+      dst[static_cast<long>(s * 9 + t) * 4096 + inner] = __float2bfloat16(acc * sa[t] * ca * fa);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ RCAB channel attention
+struct CaParams {
+  const __nv_bfloat16* t;
+  const __nv_bfloat16* x;
+  __nv_bfloat16* dst;
+  const float* pool;
+  const float *w1, *b1, *w2, *b2;
+  int npart;
+  long npix;
+};
+// grid (blocks, batch), 256 threads.  Every block recomputes the 64 -> 4 -> 64 MLP (a few kFLOP) from the
+// producer's partial sums, then streams its share of  dst = x + t * y  as 16-byte chunks.
+__global__ void __launch_bounds__(256) ca_scale_residual_kernel(const CaParams p) {
+  __shared__ float red[4][64];
+  __shared__ float mean[64];
+  __shared__ float hid[4];
+  __shared__ float ys[64];
+  const int n = blockIdx.y;
+  const int ch = threadIdx.x & 63, part = threadIdx.x >> 6;
+  const float* src = p.pool + static_cast<long>(n) * p.npart * kC;
+  float acc = 0.f;
+  for (int q = part; q < p.npart; q += 4) acc += src[q * kC + ch];
+  red[part][ch] = acc;
+  __syncthreads();
+  if (part == 0) mean[ch] = ((red[0][ch] + red[1][ch]) + (red[2][ch] + red[3][ch])) / static_cast<float>(p.npix);
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float a = p.b1[threadIdx.x];
+    for (int i = 0; i < 64; ++i) a += p.w1[threadIdx.x * 64 + i] * mean[i];
+    hid[threadIdx.x] = fmaxf(a, 0.f);
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float a = p.b2[threadIdx.x];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a += p.w2[threadIdx.x * 4 + i] * hid[i];
+    ys[threadIdx.x] = sigmoidf_(a);
+  }
+  __syncthreads();
+  const long chunks = p.npix * 8;
+  const uint4* tt = reinterpret_cast<const uint4*>(p.t + static_cast<long>(n) * p.npix * kC);
+  const uint4* xx = reinterpret_cast<const uint4*>(p.x + static_cast<long>(n) * p.npix * kC);
+  uint4* dd = reinterpret_cast<uint4*>(p.dst + static_cast<long>(n) * p.npix * kC);
+  for (long id = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; id < chunks;
+       id += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int c0 = (id & 7) * 8;
+    const uint4 a = tt[id], b = xx[id];
+    uint4 o;
+    o.x = pack_bf16(bf16_lo(b.x) + bf16_lo(a.x) * ys[c0 + 0], bf16_hi(b.x) + bf16_hi(a.x) * ys[c0 + 1]);
+    o.y = pack_bf16(bf16_lo(b.y) + bf16_lo(a.y) * ys[c0 + 2], bf16_hi(b.y) + bf16_hi(a.y) * ys[c0 + 3]);
+    o.z = pack_bf16(bf16_lo(b.z) + bf16_lo(a.z) * ys[c0 + 4], bf16_hi(b.z) + bf16_hi(a.z) * ys[c0 + 5]);
+    o.w = pack_bf16(bf16_lo(b.w) + bf16_lo(a.w) * ys[c0 + 6], bf16_hi(b.w) + bf16_hi(a.w) * ys[c0 + 7]);
+    dd[id] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ OSAdapt mask tail
+// conv16->16 (3x3, pad 1) + bias + ReLU at half resolution.  kPool: input is full resolution and is
+// 2x2 average pooled on the fly (AvgPool2d(2), savsr_arch.py:193).  One pixel x 16 outputs per thread.
+template <bool kPool>
+__global__ void __launch_bounds__(128) mask_conv16_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                          const float* __restrict__ b, float* __restrict__ out, int h2,
+                                                          int w2) {
+  __shared__ __align__(16) float w_s[9 * 16 * 16];  // [tap][ci][co]
+  for (int i = threadIdx.x; i < 9 * 256; i += blockDim.x) {
+    const int co = i & 15, ci = (i >> 4) & 15, tap = i >> 8;
+    w_s[i] = w[(co * 16 + ci) * 9 + tap];
+  }
+  __syncthreads();
+  const int n = blockIdx.y;
+  const long npix2 = static_cast<long>(h2) * w2;
+  const long pix = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (pix >= npix2) return;
+  const int py = pix / w2, px = pix % w2;
+  float acc[16];
+#pragma unroll
+  for (int o = 0; o < 16; ++o) acc[o] = b[o];
+  const int wf = 2 * w2;
+  const float* base = kPool ? in + static_cast<long>(n) * (4 * npix2) * 16 : in + static_cast<long>(n) * npix2 * 16;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int sy = py + tap / 3 - 1, sx = px + tap % 3 - 1;
+    if (sy < 0 || sy >= h2 || sx < 0 || sx >= w2) continue;
+    float a[16];
+    if (kPool) {
+      const float4* p00 = reinterpret_cast<const float4*>(base + (static_cast<long>(2 * sy) * wf + 2 * sx) * 16);
+      const float4* p10 = reinterpret_cast<const float4*>(base + (static_cast<long>(2 * sy + 1) * wf + 2 * sx) * 16);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 q0 = p00[j], q1 = p00[4 + j], q2 = p10[j], q3 = p10[4 + j];
+        a[4 * j + 0] = 0.25f * ((q0.x + q1.x) + (q2.x + q3.x));
+        a[4 * j + 1] = 0.25f * ((q0.y + q1.y) + (q2.y + q3.y));
+        a[4 * j + 2] = 0.25f * ((q0.z + q1.z) + (q2.z + q3.z));
+        a[4 * j + 3] = 0.25f * ((q0.w + q1.w) + (q2.w + q3.w));
+      }
+    } else {
+      const float4* q = reinterpret_cast<const float4*>(base + (static_cast<long>(sy) * w2 + sx) * 16);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 v = q[j];
+        a[4 * j + 0] = v.x; a[4 * j + 1] = v.y; a[4 * j + 2] = v.z; a[4 * j + 3] = v.w;
+      }
+    }
+#pragma unroll
+    for (int ci = 0; ci < 16; ++ci) {
+      const float4* wr = reinterpret_cast<const float4*>(w_s + (tap * 16 + ci) * 16);
+#pragma unroll
+      for (int o4 = 0; o4 < 4; ++o4) {
+        const float4 wv = wr[o4];
+        acc[4 * o4 + 0] += a[ci] * wv.x; acc[4 * o4 + 1] += a[ci] * wv.y;
+        acc[4 * o4 + 2] += a[ci] * wv.z; acc[4 * o4 + 3] += a[ci] * wv.w;
+      }
+    }
+  }
+  float4* d = reinterpret_cast<float4*>(out + (static_cast<long>(n) * npix2 + pix) * 16);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    d[j] = make_float4(fmaxf(acc[4 * j], 0.f), fmaxf(acc[4 * j + 1], 0.f), fmaxf(acc[4 * j + 2], 0.f), fmaxf(acc[4 * j + 3], 0.f));
+}
+
+// bilinear x2 upsample (align_corners = False) + conv16->1 (3x3, pad 1) + bias (BN folded) + sigmoid.
+__global__ void __launch_bounds__(128) mask_final_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                         const float* __restrict__ b, float* __restrict__ mask, int h2,
+                                                         int w2) {
+  __shared__ float w_s[9 * 16];  // [tap][ci]
+  for (int i = threadIdx.x; i < 144; i += blockDim.x) w_s[i] = w[(i & 15) * 9 + (i >> 4)];
+  __syncthreads();
+  const int n = blockIdx.y;
+  const int H = 2 * h2, W = 2 * w2;
+  const long npix = static_cast<long>(H) * W;
+  const long pix = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (pix >= npix) return;
+  const int py = pix / W, px = pix % W;
+  const float* base = in + static_cast<long>(n) * h2 * w2 * 16;
+  float acc = b[0];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int sy = py + tap / 3 - 1, sx = px + tap % 3 - 1;
+    if (sy < 0 || sy >= H || sx < 0 || sx >= W) continue;
+    float fy = 0.5f * (static_cast<float>(sy) + 0.5f) - 0.5f;
+    float fx = 0.5f * (static_cast<float>(sx) + 0.5f) - 0.5f;
+    fy = fy < 0.f ? 0.f : fy;
+    fx = fx < 0.f ? 0.f : fx;
+    const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+    const int y1 = y0 + (y0 < h2 - 1 ? 1 : 0), x1 = x0 + (x0 < w2 - 1 ? 1 : 0);
+    const float ly = fy - y0, lx = fx - x0;
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    const float4* p00 = reinterpret_cast<const float4*>(base + (static_cast<long>(y0) * w2 + x0) * 16);
+    const float4* p01 = reinterpret_cast<const float4*>(base + (static_cast<long>(y0) * w2 + x1) * 16);
+    const float4* p10 = reinterpret_cast<const float4*>(base + (static_cast<long>(y1) * w2 + x0) * 16);
+    const float4* p11 = reinterpret_cast<const float4*>(base + (static_cast<long>(y1) * w2 + x1) * 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 a = p00[j], bb = p01[j], cc = p10[j], d = p11[j];
+      const float* ws = w_s + tap * 16 + 4 * j;
+      acc += ws[0] * (w00 * a.x + w01 * bb.x + w10 * cc.x + w11 * d.x);
+      acc += ws[1] * (w00 * a.y + w01 * bb.y + w10 * cc.y + w11 * d.y);
+      acc += ws[2] * (w00 * a.z + w01 * bb.z + w10 * cc.z + w11 * d.z);
+      acc += ws[3] * (w00 * a.w + w01 * bb.w + w10 * cc.w + w11 * d.w);
+    }
+  }
+  mask[static_cast<long>(n) * npix + pix] = sigmoidf_(acc);
+}
+
+}  // namespace savsr
+
+using namespace savsr;
+
+extern "C" int savsr_front_conv(savsr_ctx* ctx, savsr_arena* arena, const float* x, int t, int h, int w,
+                                const savsr_front_group* groups, int ngroups, savsr_stream st) {
+  SAVSR_REQUIRE(ctx && arena && x && groups, "savsr_front_conv: null pointer");
+  SAVSR_REQUIRE(ngroups >= 0 && ngroups <= kMaxFront, "savsr_front_conv: ngroups %d out of range [0,%d]", ngroups, kMaxFront);
+  SAVSR_REQUIRE(h >= 2 && w >= 2, "savsr_front_conv: LR frame %dx%d too small for reflect padding", h, w);
+  SAVSR_REQUIRE(arena->height == h + (h & 1) && arena->width == w + (w & 1),
+                "savsr_front_conv: arena %dx%d is not the even-padded size of %dx%d", arena->height, arena->width, h, w);
+  if (ngroups == 0) return 0;
+  FrontParams p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < ngroups; ++i) {
+    const savsr_front_group& g = groups[i];
+    SAVSR_REQUIRE(g.nframes == 1 || g.nframes == 2, "savsr_front_conv: group %d nframes %d", i, g.nframes);
+    for (int f = 0; f < g.nframes; ++f) SAVSR_REQUIRE(g.frame[f] >= 0 && g.frame[f] < t, "savsr_front_conv: frame index %d out of range", g.frame[f]);
+    SAVSR_REQUIRE(g.dst_slot >= 0 && g.dst_slot < arena->nslots && g.weight && g.bias, "savsr_front_conv: bad group %d", i);
+    p.g[i] = g;
+  }
+  p.x = x; p.arena = arena->base; p.ngroups = ngroups; p.batch = arena->batch;
+  p.t = t; p.h = h; p.w = w; p.hp = arena->height; p.wp = arena->width;
+  const long npix = static_cast<long>(p.hp) * p.wp;
+  dim3 grid(static_cast<unsigned>((npix + 127) / 128), arena->batch, ngroups);
+  front_conv_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(st)>>>(p);
+  SAVSR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int savsr_osa_prologue(savsr_ctx* ctx, const savsr_osa_params* convs, int nconvs, int batch, int npart,
+                                  int npix, float inv_scale_h, float inv_scale_w, savsr_stream st_) {
+  SAVSR_REQUIRE(ctx && convs, "savsr_osa_prologue: null pointer");
+  SAVSR_REQUIRE(nconvs >= 0 && nconvs <= kMaxOsa, "savsr_osa_prologue: nconvs %d out of range [0,%d]", nconvs, kMaxOsa);
+  if (nconvs == 0 || batch == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(st_);
+  OsaLaunch L;
+  memset(&L, 0, sizeof(L));
+  int max_ci = 0;
+  for (int i = 0; i < nconvs; ++i) {
+    const savsr_osa_params& c = convs[i];
+    SAVSR_REQUIRE(c.ci > 0 && c.ci % 64 == 0 && c.ci <= 64 * SAVSR_MAX_SRC, "savsr_osa_prologue: conv %d ci %d unsupported", i, c.ci);
+    SAVSR_REQUIRE(c.co == 64, "savsr_osa_prologue: conv %d co %d unsupported (64 only)", i, c.co);
+    SAVSR_REQUIRE(c.att > 0 && c.att <= 32, "savsr_osa_prologue: conv %d attention channels %d out of range", i, c.att);
+    SAVSR_REQUIRE(c.bank && c.r0_w && c.r0_b && c.r2_w && c.r2_b && c.fc_w && c.bn_scale && c.bn_shift && c.ch_w && c.ch_b &&
+                  c.fl_w && c.fl_b && c.sp_w && c.sp_b && c.kn_w && c.kn_b && c.scratch && c.packed,
+                  "savsr_osa_prologue: conv %d has a null parameter pointer", i);
+    for (int s = 0; s < c.ci / 64; ++s) SAVSR_REQUIRE(c.pool[s], "savsr_osa_prologue: conv %d source %d has no pool buffer", i, s);
+    L.c[i] = c;
+    max_ci = c.ci > max_ci ? c.ci : max_ci;
+  }
+  L.nconvs = nconvs; L.batch = batch; L.npart = npart; L.npix = npix;
+  L.inv_h = inv_scale_h; L.inv_w = inv_scale_w;
+  osa_pool_kernel<<<dim3(max_ci / 64, batch, nconvs), 256, 0, st>>>(L);
+  osa_linear_kernel<<<dim3((2 * max_ci + 7) / 8, nconvs), 256, 0, st>>>(L, 0);
+  osa_linear_kernel<<<dim3((max_ci + 7) / 8, nconvs), 256, 0, st>>>(L, 1);
+  osa_attention_kernel<<<dim3(batch, nconvs), 256, 0, st>>>(L);
+  osa_assemble_kernel<<<dim3((64 * max_ci + 255) / 256, nconvs), 256, 0, st>>>(L);
+  SAVSR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int savsr_ca_scale_residual(savsr_ctx* ctx, savsr_arena* arena, int t_slot, int x_slot, int dst_slot,
+                                       const float* pool, int npart, const float* w1, const float* b1, const float* w2,
+                                       const float* b2, savsr_stream st) {
+  SAVSR_REQUIRE(ctx && arena && pool && w1 && b1 && w2 && b2, "savsr_ca_scale_residual: null pointer");
+  SAVSR_REQUIRE(t_slot >= 0 && t_slot < arena->nslots && x_slot >= 0 && x_slot < arena->nslots && dst_slot >= 0 &&
+                dst_slot < arena->nslots, "savsr_ca_scale_residual: slot out of range");
+  CaParams p;
+  p.npix = static_cast<long>(arena->height) * arena->width;
+  const long img = p.npix * kC * arena->batch;
+  p.t = arena->base + t_slot * img;
+  p.x = arena->base + x_slot * img;
+  p.dst = arena->base + dst_slot * img;
+  p.pool = pool; p.npart = npart; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2;
+  long blocks = (p.npix * 8 + 255) / 256;
+  const long cap = 2L * ctx->sm_count / (arena->batch > 0 ? arena->batch : 1) + 1;
+  if (blocks > cap) blocks = cap;
+  if (arena->batch == 0) return 0;
+  ca_scale_residual_kernel<<<dim3(static_cast<unsigned>(blocks), arena->batch), 256, 0, static_cast<cudaStream_t>(st)>>>(p);
+  SAVSR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int savsr_osadapt_mask(savsr_ctx* ctx, const float* in16, int batch, int height, int width, const float* wa,
+                                  const float* ba, const float* wb, const float* bb, const float* wc, const float* bc,
+                                  float* half0, float* half1, float* mask, savsr_stream st_) {
+  SAVSR_REQUIRE(ctx && in16 && wa && ba && wb && bb && wc && bc && half0 && half1 && mask, "savsr_osadapt_mask: null pointer");
+  SAVSR_REQUIRE(height % 2 == 0 && width % 2 == 0, "savsr_osadapt_mask: size %dx%d must be even (pad_spatial)", height, width);
+  if (batch == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(st_);
+  const int h2 = height / 2, w2 = width / 2;
+  const long npix2 = static_cast<long>(h2) * w2;
+  dim3 g2(static_cast<unsigned>((npix2 + 127) / 128), batch);
+  mask_conv16_kernel<true><<<g2, 128, 0, st>>>(in16, wa, ba, half0, h2, w2);
+  mask_conv16_kernel<false><<<g2, 128, 0, st>>>(half0, wb, bb, half1, h2, w2);
+  dim3 g1(static_cast<unsigned>((4 * npix2 + 127) / 128), batch);
+  mask_final_kernel<<<g1, 128, 0, st>>>(half1, wc, bc, mask, h2, w2);
+  SAVSR_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,458 @@
+"""Forward plan of the SAVSR hot path on libsavsr_sm100 (host side, Python like the reference).
+
+A ``Plan`` is built once per (batch, h, w, scale, weights-version).  It packs the weights into the
+tensor-core layouts, lays the activations out in bf16 NHWC arenas, pre-computes the SATU index vectors
+and per-scale MLP table, and records the ordered list of C-ABI kernel launches that make up
+``SAVSR.forward`` (reference: lbasicsr/archs/savsr_arch.py:692-742).  ``run()`` replays that list on the
+current CUDA stream; ``run_graph()`` replays a CUDA graph captured from it.
+
+The two propagation directions (f2p / p2f, savsr_arch.py:708-719) are independent chains, so every
+launch of the propagation phase batches both directions (and the 3 or 5 per-frame streams of a
+ResidualBlock) as "groups" of one grouped implicit-GEMM launch instead of using two streams.
+
+PyTorch is used here only for device memory and streams.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _capi as K
+
+BN_EPS = 1e-5
+
+
+def normalize_scale(scale) -> Tuple[float, float]:
+    if isinstance(scale, (int, float)):
+        return (scale, scale)
+    s = tuple(scale)
+    if len(s) != 2:
+        raise ValueError(f"scale must be a number or a (s_h, s_w) pair, got {scale!r}")
+    return (s[0], s[1])
+
+
+def get_hw(h: int, w: int, scale) -> Tuple[int, int]:
+    """savsr_arch.py:745-751: python round() (half-to-even) on the python float product."""
+    s = normalize_scale(scale)
+    return round(h * s[0]), round(w * s[1])
+
+
+_contexts: Dict[int, K.Context] = {}
+
+
+def context(device_index: int) -> K.Context:
+    if device_index not in _contexts:
+        _contexts[device_index] = K.Context(device_index)
+    return _contexts[device_index]
+
+
+class _Slots:
+    """Arena slot allocator with reuse (program order == stream order, single stream)."""
+
+    def __init__(self):
+        self.free: List[int] = []
+        self.n = 0
+
+    def get(self) -> int:
+        if self.free:
+            return self.free.pop()
+        self.n += 1
+        return self.n - 1
+
+    def get_many(self, k: int) -> List[int]:
+        return [self.get() for _ in range(k)]
+
+    def get_contiguous(self, k: int) -> int:
+        s = self.n
+        self.n += k
+        return s
+
+    def put(self, *slots: int) -> None:
+        self.free.extend(slots)
+
+
+class Plan:
+    def __init__(self, params: Dict[str, torch.Tensor], batch: int, h: int, w: int, scale, device: torch.device,
+                 conv_impl: str = "tap", num_frame: int = 7, taps: Optional[Sequence[str]] = None):
+        if device.type != "cuda":
+            raise K.SavsrError("savsr_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if num_frame != 7:
+            raise NotImplementedError("only the shipped 7-frame configuration is implemented")
+        if h < 2 or w < 2:
+            raise ValueError(f"LR frames must be at least 2x2, got {h}x{w}")
+        self.device = device
+        self.ctx = context(device.index if device.index is not None else torch.cuda.current_device())
+        self.lib = self.ctx.lib
+        self.impl = K.IMPL_NAMES[conv_impl]
+        self.B, self.h, self.w, self.t = batch, h, w, num_frame
+        self.scale = normalize_scale(scale)
+        self.hp, self.wp = h + (h & 1), w + (w & 1)
+        self.H, self.W = get_hw(h, w, self.scale)
+        self.P = params
+        self._keep: List[object] = []   # tensors / ctypes arrays referenced by raw pointers
+        self.ops: List[Callable[[int], int]] = []
+        self.n_launches = 0
+        self.taps = set(taps or ())
+        self.tap_bufs: Dict[str, torch.Tensor] = {}
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self._pack_cache: Dict[str, int] = {}
+        self._pool_cache: Dict[str, int] = {}
+        self._osa_cache: Dict[str, Tuple[K.OsaParams, int, int]] = {}
+        with torch.cuda.device(device), torch.no_grad():
+            self._build()
+
+    # ------------------------------------------------------------------ memory helpers
+    def _buf(self, *shape, dtype=torch.float32) -> torch.Tensor:
+        t = torch.empty(*shape, dtype=dtype, device=self.device)
+        self._keep.append(t)
+        return t
+
+    def _p(self, name: str) -> torch.Tensor:
+        t = self.P[name]
+        if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
+            t = t.detach().to(self.device, torch.float32).contiguous()
+        self._keep.append(t)
+        return t
+
+    def _ptr(self, name: str) -> int:
+        return self._p(name).data_ptr()
+
+    def _dev(self, t: torch.Tensor) -> int:
+        t = t.detach().to(self.device, torch.float32).contiguous()
+        self._keep.append(t)
+        return t.data_ptr()
+
+    def _packp(self, name: str) -> int:
+        """Packed copy of the conv parameter `name` (cached: the five propagation iterations share weights)."""
+        if name not in self._pack_cache:
+            self._pack_cache[name] = self._pack(self._p(name))
+        return self._pack_cache[name]
+
+    def _pack(self, w: torch.Tensor, n_tile: int = 64, co_pad: Optional[int] = None) -> int:
+        """fp32 OIHW -> packed bf16 tensor-core layout; returns the device pointer."""
+        w = w.detach().to(self.device, torch.float32).contiguous()
+        co_real, ci, ks, _ = w.shape
+        co = co_pad or co_real
+        out = self._buf(self.lib.savsr_packed_weight_bytes(co, ci, ks), dtype=torch.uint8)
+        self._keep.append(w)
+        K.check(self.lib.savsr_pack_conv_weight(w.data_ptr(), co_real, co, ci, ks, n_tile, out.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream))
+        return out.data_ptr()
+
+    # ------------------------------------------------------------------ op emitters
+    def _emit(self, fn: Callable[[int], int], launches: int = 1) -> None:
+        self.ops.append(fn)
+        self.n_launches += launches
+
+    def _group(self, src: Sequence[int], dst: int, weight: int, bias: int = 0, act: int = K.ACT_NONE, slope: float = 0.2,
+               res1: int = -1, res2: int = -1, res2_scale: float = 0.0, wstride: int = 0, mask: int = 0, pool: int = 0,
+               aux: int = 0) -> K.ConvGroup:
+        g = K.ConvGroup()
+        for i, s in enumerate(src):
+            g.src_slot[i] = s
+        g.nsrc = len(src)
+        g.dst_slot, g.res1_slot, g.res2_slot, g.res2_scale = dst, res1, res2, res2_scale
+        g.act, g.slope = act, slope
+        g.weight, g.weight_sample_stride = weight, wstride
+        g.bias, g.mask, g.pool, g.aux_dst = bias or None, mask or None, pool or None, aux or None
+        return g
+
+    def _conv(self, arena: K.Arena, groups: Sequence[K.ConvGroup], ksize: int = 3, n_tile: int = 64,
+              dst_mode: int = K.DST_ARENA, skip: Optional[K.RgbSkip] = None) -> None:
+        arr = (K.ConvGroup * len(groups))(*groups)
+        self._keep.append(arr)
+        skip_ref = C.byref(skip) if skip is not None else None
+        lib, ctx, ah, n, impl = self.lib, self.ctx.handle, arena.handle, len(groups), self.impl
+        self._emit(lambda st: lib.savsr_conv(ctx, ah, arr, n, ksize, n_tile, dst_mode, skip_ref, impl, st))
+
+    def _tap(self, name: str, arena: str, slot: int) -> None:
+        """Test/debug hook: if `name` was requested in `taps`, snapshot the slot (fp32 NCHW) right here in the
+        program, before later stages recycle it.  Not emitted in production plans."""
+        if name not in self.taps:
+            return
+        a = self.lr if arena == "lr" else self.hr
+        buf = self._buf(self.B, 64, a.height, a.width)
+        self.tap_bufs[name] = buf
+        lib, ah, ptr = self.lib, a.handle, buf.data_ptr()
+        self._emit(lambda st: lib.savsr_arena_export(ah, slot, ptr, st))
+
+    def _osa_params(self, prefix: str, nsrc: int, pools: Sequence[int]) -> Tuple[K.OsaParams, int, int]:
+        if prefix in self._osa_cache:
+            return self._osa_cache[prefix]
+        ci, co = 64 * nsrc, 64
+        att = max(int(ci * 0.0625), 16)
+        a = prefix + ".attention"
+        bn_s = self._p(a + ".bn.weight") / torch.sqrt(self._p(a + ".bn.running_var") + BN_EPS)
+        bn_b = self._p(a + ".bn.bias") - self._p(a + ".bn.running_mean") * bn_s
+        o = K.OsaParams()
+        o.ci, o.co, o.att = ci, co, att
+        o.bank = self._ptr(prefix + ".weight")
+        o.r0_w, o.r0_b = self._ptr(prefix + ".scale_routing.0.weight"), self._ptr(prefix + ".scale_routing.0.bias")
+        o.r2_w, o.r2_b = self._ptr(prefix + ".scale_routing.2.weight"), self._ptr(prefix + ".scale_routing.2.bias")
+        o.fc_w = self._ptr(a + ".fc.weight")
+        o.bn_scale, o.bn_shift = self._dev(bn_s), self._dev(bn_b)
+        o.ch_w, o.ch_b = self._ptr(a + ".channel_fc.weight"), self._ptr(a + ".channel_fc.bias")
+        o.fl_w, o.fl_b = self._ptr(a + ".filter_fc.weight"), self._ptr(a + ".filter_fc.bias")
+        o.sp_w, o.sp_b = self._ptr(a + ".spatial_fc.weight"), self._ptr(a + ".spatial_fc.bias")
+        o.kn_w, o.kn_b = self._ptr(a + ".kernel_fc.weight"), self._ptr(a + ".kernel_fc.bias")
+        for i, pp in enumerate(pools):
+            o.pool[i] = pp
+        scratch = self._buf(self.B, 5 * ci + 192)
+        packed = self._buf(self.B, co * ci * 9 * 2, dtype=torch.uint8)
+        o.scratch, o.packed = scratch.data_ptr(), packed.data_ptr()
+        self.osa_scratch[prefix] = scratch
+        self._osa_cache[prefix] = (o, packed.data_ptr(), co * ci * 9 * 2)
+        return self._osa_cache[prefix]
+
+    def _osa_prologue(self, convs: Sequence[K.OsaParams]) -> None:
+        arr = (K.OsaParams * len(convs))(*convs)
+        self._keep.append(arr)
+        inv_h = float(np.float32(1.0) / np.float32(self.scale[0]))
+        inv_w = float(np.float32(1.0) / np.float32(self.scale[1]))
+        lib, ctx, n, B = self.lib, self.ctx.handle, len(convs), self.B
+        npart, npix = self.lr.tiles * 4, self.hp * self.wp
+        self._emit(lambda st: lib.savsr_osa_prologue(ctx, arr, n, B, npart, npix, inv_h, inv_w, st), launches=5)
+
+    def _pool(self, key: str) -> int:
+        """Partial-sum buffer [B][tiles*4][64] written by a conv epilogue (cached per producing conv)."""
+        if key not in self._pool_cache:
+            self._pool_cache[key] = self._buf(self.B, self.lr.tiles * 4, 64).data_ptr()
+        return self._pool_cache[key]
+
+    # ------------------------------------------------------------------ program construction
+    def _residual_block(self, prefixes: Sequence[str], xs: Sequence[Sequence[int]], outs: Sequence[Sequence[int]],
+                        tmp: Sequence[Sequence[int]], base: Sequence[int]) -> None:
+        """ResidualBlock.forward (savsr_arch.py:399-415) for len(prefixes) independent blocks at once.
+        xs[d][i] -> outs[d][i]; tmp[d][i] holds x1, base[d] the merged feature."""
+        lr = self.lr
+        nfr = len(xs[0])
+        use_os = (prefixes[0] + ".osconv.weight") in self.P
+        L = K.ACT_LRELU
+        pools = [[self._pool(f"{p}.conv0.{i}") if use_os else 0 for i in range(nfr)] for p in prefixes]
+        self._conv(lr, [self._group([xs[d][i]], tmp[d][i], self._packp(f"{p}.conv0.{i}.weight"),
+                                    self._ptr(f"{p}.conv0.{i}.bias"), act=L, pool=pools[d][i])
+                        for d, p in enumerate(prefixes) for i in range(nfr)])
+        if use_os:
+            osa = [self._osa_params(p + ".osconv", nfr, pools[d]) for d, p in enumerate(prefixes)]
+            self._osa_prologue([o[0] for o in osa])
+            self._conv(lr, [self._group(tmp[d], base[d], osa[d][1], act=L, wstride=osa[d][2]) for d in range(len(prefixes))])
+        else:
+            self._conv(lr, [self._group(tmp[d], base[d], self._packp(p + ".conv1.weight"), self._ptr(p + ".conv1.bias"), act=L)
+                            for d, p in enumerate(prefixes)], ksize=1)
+        self._conv(lr, [self._group([base[d], tmp[d][i]], outs[d][i], self._packp(f"{p}.conv2.{i}.weight"),
+                                    self._ptr(f"{p}.conv2.{i}.bias"), act=L, res1=xs[d][i])
+                        for d, p in enumerate(prefixes) for i in range(nfr)])
+
+    def _build(self) -> None:
+        P, B, t = self.P, self.B, self.t
+        lib, ctx = self.lib, self.ctx.handle
+        L = K.ACT_LRELU
+        self.osa_scratch: Dict[str, torch.Tensor] = {}
+        nf = 64
+        # ---- arenas: slot count is discovered by a dry layout pass (slot ids only), then allocated.
+        sl = _Slots()
+        zero = sl.get()
+        dirs = ("f2p_win", "p2f_win")
+        n_it = t - 3 + 1
+        F = [[sl.get() for _ in range(n_it)] for _ in dirs]        # unit outputs, kept for the l2 fusion
+        S0 = [sl.get_many(2) for _ in dirs]
+        S1 = [sl.get_many(3) for _ in dirs]
+        S2 = [sl.get_many(3) for _ in dirs]
+        T = [sl.get_many(3) for _ in dirs]
+        Bs = [sl.get() for _ in dirs]
+        # l2 / reconstruction reuse the propagation scratch slots
+        pool_free = [s for d in range(2) for s in (S0[d] + S1[d] + S2[d] + T[d])] + Bs
+        extra_needed = 5 + 5 + 5 + 1 + 2 + 1 + 6 + 2
+        while len(pool_free) < extra_needed:
+            pool_free.append(sl.get())
+        kslot0 = sl.get_contiguous(25)
+        self.n_lr_slots = sl.n
+        self.arena_lr_t = self._buf(self.n_lr_slots * B, self.hp, self.wp, 64, dtype=torch.bfloat16)
+        self.arena_lr_t[zero * B:(zero + 1) * B].zero_()
+        self.lr = K.Arena(self.ctx, self.arena_lr_t.data_ptr(), self.n_lr_slots, B, self.hp, self.wp)
+        self.arena_hr_t = self._buf(3 * B, self.H, self.W, 64, dtype=torch.bfloat16)
+        self.hr = K.Arena(self.ctx, self.arena_hr_t.data_ptr(), 3, B, self.H, self.W)
+        lr, hr = self.lr, self.hr
+        self.x_in = self._buf(B, t, 3, self.h, self.w)
+        self.out = self._buf(B, 3, self.H, self.W)
+        xin = self.x_in.data_ptr()
+
+        # ---- 1. bi-directional propagation (savsr_arch.py:703-719), both directions per launch
+        hpast = [zero, zero]
+        for idx in range(n_it):
+            centre = [t - 1 - 1 - idx, idx + 1]                     # f2p walks back, p2f forward
+            fg = []
+            for d, p in enumerate(dirs):
+                c = centre[d]
+                g = K.FrontGroup(); g.frame[0] = c; g.nframes = 1; g.dst_slot = S0[d][0]
+                g.weight, g.bias = self._ptr(p + ".conv_c.weight"), self._ptr(p + ".conv_c.bias")
+                fg.append(g)
+                g = K.FrontGroup(); g.frame[0] = c - 1; g.frame[1] = c + 1; g.nframes = 2; g.dst_slot = S0[d][1]
+                g.weight, g.bias = self._ptr(p + ".conv_sup.weight"), self._ptr(p + ".conv_sup.bias")
+                fg.append(g)
+            farr = (K.FrontGroup * len(fg))(*fg)
+            self._keep.append(farr)
+            lrh, hh, ww, nfg = lr.handle, self.h, self.w, len(fg)
+            self._emit(lambda st, farr=farr, nfg=nfg: lib.savsr_front_conv(ctx, lrh, xin, t, hh, ww, farr, nfg, st))
+            cur = [[S0[d][0], S0[d][1], hpast[d]] for d in range(2)]
+            sets = [S1, S2]
+            for j in range(4):
+                nxt = sets[j % 2]
+                self._residual_block([f"{p}.blocks.{j}" for p in dirs], cur, nxt, T, Bs)
+                cur = [list(nxt[d]) for d in range(2)]
+            self._conv(lr, [self._group(cur[d], F[d][idx], self._packp(p + ".merge.weight"), self._ptr(p + ".merge.bias"))
+                            for d, p in enumerate(dirs)])
+            hpast = [F[0][idx], F[1][idx]]
+        self._tap("f2p_last", "lr", F[0][n_it - 1])
+        self._tap("p2f_last", "lr", F[1][n_it - 1])
+
+        # ---- 2. pyramid fusion, WindowUnit_l2 (savsr_arch.py:485-501, 721-723)
+        free = list(pool_free)
+        take = lambda k: [free.pop() for _ in range(k)]
+        Gx, Gy, T5 = take(5), take(5), take(5)
+        B5, = take(1)
+        M = take(2)
+        A, = take(1)
+        p2 = "h_win.0"
+        # h_f2p_list.insert(0, .) reverses the f2p order: list position i <- unit idx = n_it-1-i
+        self._conv(lr, [self._group([F[0][n_it - 1 - i], F[1][i]], Gx[i], self._packp(f"{p2}.conv_h.{i}.weight"),
+                                    self._ptr(f"{p2}.conv_h.{i}.bias"), act=L) for i in range(5)])
+        cur5, nxt5 = Gx, Gy
+        for j in range(2):
+            self._residual_block([f"{p2}.blocks.{j}"], [cur5], [nxt5], [T5], [B5])
+            cur5, nxt5 = nxt5, cur5
+        wm = self._packp(p2 + ".merge.weight")
+        half = 5 * 9 * 8192
+        bm = self._p(p2 + ".merge.bias")
+        self._conv(lr, [self._group(cur5, M[k], wm + k * half, bm[64 * k:].data_ptr()) for k in range(2)])
+        self._tap("h_win0", "lr", M[0]); self._tap("h_win1", "lr", M[1])
+        self._conv(lr, [self._group(M, A, self._packp("h_win_conv_h.weight"), self._ptr("h_win_conv_h.bias"), act=L)])
+        self._tap("align", "lr", A)
+        free += Gx + Gy + T5 + [B5] + M
+
+        # ---- 3. reconstruction: 4 x (ResidualGroup -> OSAdapt -> + gamma * share) (savsr_arch.py:727-734)
+        gamma = float(self._p("gamma").item())
+        X0, X1, T1, T2, R, Hs = take(6)
+        in16 = self._buf(B, self.hp * self.wp, 16)
+        half0 = self._buf(B, (self.hp // 2) * (self.wp // 2), 16)
+        half1 = self._buf(B, (self.hp // 2) * (self.wp // 2), 16)
+        maskb = self._buf(B, self.hp * self.wp)
+        npart = lr.tiles * 4
+        lrh = lr.handle
+        h_cur = A                                   # share_source / align_feat stay in slot A to the end
+        for gi in range(4):
+            x, xa, xb = h_cur, X0, X1               # RCAB chain ping-pongs X0/X1, h_cur is kept for the group residual
+            for r in range(8):
+                pr = f"RG.{gi}.residual_group.{r}.rcab"
+                self._conv(lr, [self._group([x], T1, self._packp(pr + ".0.weight"), self._ptr(pr + ".0.bias"), act=K.ACT_RELU)])
+                pl = self._pool(pr + ".2")
+                self._conv(lr, [self._group([T1], T2, self._packp(pr + ".2.weight"), self._ptr(pr + ".2.bias"), pool=pl)])
+                w1, b1 = self._ptr(pr + ".3.attention.1.weight"), self._ptr(pr + ".3.attention.1.bias")
+                w2, b2 = self._ptr(pr + ".3.attention.3.weight"), self._ptr(pr + ".3.attention.3.bias")
+                self._emit(lambda st, x=x, xa=xa, pl=pl, w1=w1, b1=b1, w2=w2, b2=b2:
+                           lib.savsr_ca_scale_residual(ctx, lrh, T2, x, xa, pl, npart, w1, b1, w2, b2, st))
+                x, xa, xb = xa, xb, xa
+            plr = self._pool(f"RG.{gi}.conv")
+            self._conv(lr, [self._group([x], R, self._packp(f"RG.{gi}.conv.weight"), self._ptr(f"RG.{gi}.conv.bias"),
+                                        res1=h_cur, pool=plr)])
+            self._tap(f"rg{gi}", "lr", R)
+            # OSAdapt (savsr_arch.py:186-214): mask branch, adapted = OSA-Conv(x); h = x + adapted * mask + gamma * share
+            pa = f"adapt.{gi}"
+            m = pa + ".mask"
+
+            def fold(conv: str, bn: str):
+                sc = self._p(bn + ".weight") / torch.sqrt(self._p(bn + ".running_var") + BN_EPS)
+                wf = self._p(conv + ".weight") * sc.view(-1, 1, 1, 1)
+                bf = (self._p(conv + ".bias") - self._p(bn + ".running_mean")) * sc + self._p(bn + ".bias")
+                return wf, bf
+            w0, b0 = fold(m + ".0", m + ".1")
+            wa, ba = fold(m + ".4", m + ".5")
+            wb, bb = fold(m + ".7", m + ".8")
+            wc, bc = fold(m + ".11", m + ".12")
+            self._conv(lr, [self._group([R], 0, self._pack(w0, n_tile=16), self._dev(b0), act=K.ACT_RELU, aux=in16.data_ptr())],
+                       n_tile=16, dst_mode=K.DST_AUX16)
+            args = (ctx, in16.data_ptr(), B, self.hp, self.wp, self._dev(wa), self._dev(ba), self._dev(wb), self._dev(bb),
+                    self._dev(wc), self._dev(bc), half0.data_ptr(), half1.data_ptr(), maskb.data_ptr())
+            self._emit(lambda st, args=args: lib.savsr_osadapt_mask(*args, st), launches=3)
+            osa = self._osa_params(pa + ".adapt", 1, [plr])
+            self._osa_prologue([osa[0]])
+            self._conv(lr, [self._group([R], Hs, osa[1], wstride=osa[2], mask=maskb.data_ptr(), res1=R, res2=A, res2_scale=gamma)])
+            self._tap(f"adapt{gi}", "lr", Hs)
+            h_cur = Hs
+        TR, = take(1)
+        self._conv(lr, [self._group([h_cur], TR, self._packp("conv_last.weight"), self._ptr("conv_last.bias"), res1=A)])
+        self._tap("trunk", "lr", TR)
+
+        # ---- 4. SATU (savsr_arch.py:315-376) + tail + bilinear skip (738-739)
+        u = "upsample"
+        wk = self._p(u + ".kernel_conv.0.weight").view(64, 25, 64).permute(1, 0, 2).reshape(1600, 64, 1, 1)   # tap-major
+        bk = self._p(u + ".kernel_conv.0.bias").view(64, 25).t().contiguous()
+        wkp = self._pack(wk)
+        bkp = self._dev(bk)
+        self._conv(lr, [self._group([A], kslot0 + tp, wkp + tp * 8192, bkp + tp * 256, act=L, slope=0.1) for tp in range(25)], ksize=1)
+        STA, = take(1)
+        lrh, hrh, hh, ww = lr.handle, hr.handle, self.h, self.w
+        self._emit(lambda st: lib.savsr_satu_sta(ctx, lrh, TR, kslot0, STA, hh, ww, st))
+        self._tap("satu_sta", "lr", STA)
+        sw = K.SatuWeights()
+        sw.body0_w, sw.body0_b = self._ptr(u + ".body.0.weight"), self._ptr(u + ".body.0.bias")
+        sw.body2_w, sw.body2_b = self._ptr(u + ".body.2.weight"), self._ptr(u + ".body.2.bias")
+        sw.routing_w, sw.routing_b = self._ptr(u + ".routing.0.weight"), self._ptr(u + ".routing.0.bias")
+        sw.offset_w, sw.offset_b = self._ptr(u + ".offset.weight"), self._ptr(u + ".offset.bias")
+        sw.st_offset_w, sw.st_offset_b = self._ptr(u + ".st_offset.weight"), self._ptr(u + ".st_offset.bias")
+        sw.compress, sw.expand = self._ptr(u + ".weight_compress"), self._ptr(u + ".weight_expand")
+        self._keep.append(sw)
+        H, W = self.H, self.W
+        self.rel_y, self.rel_x = self._buf(H), self._buf(W)
+        self.base_y, self.base_x = self._buf(H), self._buf(W)
+        self.cell_y, self.cell_x = self._buf(H, dtype=torch.int32), self._buf(W, dtype=torch.int32)
+        self.corner_y, self.corner_x = self._buf(H, dtype=torch.int32), self._buf(W, dtype=torch.int32)
+        self.table = self._buf(H * W, 8)
+        # index vectors + per-scale MLP table: input independent, computed once per plan on the device
+        K.check(lib.savsr_satu_index(ctx, C.byref(sw), self.h, self.w, H, W, float(self.scale[0]), float(self.scale[1]),
+                                     self.rel_y.data_ptr(), self.rel_x.data_ptr(), self.cell_y.data_ptr(), self.cell_x.data_ptr(),
+                                     self.base_y.data_ptr(), self.base_x.data_ptr(), self.corner_y.data_ptr(),
+                                     self.corner_x.data_ptr(), self.table.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        tab, by, bx, swr = self.table.data_ptr(), self.base_y.data_ptr(), self.base_x.data_ptr(), C.byref(sw)
+        self._emit(lambda st: lib.savsr_satu_gather(ctx, lrh, TR, STA, hh, ww, hrh, 0, 1, tab, by, bx, swr, st))
+        self._conv(hr, [self._group([0, 1], 2, self._packp(u + ".fusion.weight"), self._ptr(u + ".fusion.bias"))], ksize=1)
+        self._tap("satu_out", "hr", 2)
+        skip = K.RgbSkip(); skip.x = xin; skip.t = t; skip.centre = t // 2; skip.h = self.h; skip.w = self.w
+        self._keep.append(skip)
+        bt = torch.zeros(16, device=self.device); bt[:3] = self._p("tail.bias")
+        self._conv(hr, [self._group([2], 0, self._pack(self._p("tail.weight"), n_tile=16, co_pad=16), self._dev(bt),
+                                    aux=self.out.data_ptr())], n_tile=16, dst_mode=K.DST_RGB, skip=skip)
+        torch.cuda.current_stream().synchronize()
+
+    # ------------------------------------------------------------------ execution
+    def run(self) -> None:
+        """Launch the whole forward on the current stream (x_in -> out)."""
+        st = torch.cuda.current_stream().cuda_stream
+        for op in self.ops:
+            rc = op(st)
+            if rc:
+                K.check(rc)
+
+    def capture(self) -> None:
+        """Capture run() into a CUDA graph (after one eager warm-up that sets kernel attributes)."""
+        if self.graph is not None:
+            return
+        self.run()
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run()
+        self.graph = g
+
+    def run_graph(self) -> None:
+        if self.graph is None:
+            self.capture()
+        self.graph.replay()
+
+    def read_tap(self, name: str) -> torch.Tensor:
+        """fp32 NCHW snapshot of a named intermediate requested via `taps` (test / debug only)."""
+        return self.tap_bufs[name]

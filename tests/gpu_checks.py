@@ -1,0 +1,501 @@
+"""Parity checks of every libsavsr_sm100 entry point against fp32 PyTorch / the CPU oracle.
+
+Shared by ``tests/test_gpu_*.py`` (pytest, ``-m gpu``) and ``scripts/gpu_bringup.py`` (one subprocess per
+check, so a trapping kernel cannot poison the other checks).  Every check calls through the C ABI.
+Each function returns a dict of error metrics and raises AssertionError when out of tolerance.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from savsr_b200 import _capi as K          # noqa: E402
+from savsr_b200 import engine              # noqa: E402
+
+DEV = torch.device("cuda", 0)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ctx() -> K.Context:
+    return engine.context(0)
+
+
+def bf16_round(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+class ArenaBox:
+    def __init__(self, nslots: int, batch: int, height: int, width: int):
+        self.t = torch.zeros(nslots * batch, height, width, 64, dtype=torch.bfloat16, device=DEV)
+        self.a = K.Arena(ctx(), self.t.data_ptr(), nslots, batch, height, width)
+        self.B, self.H, self.W = batch, height, width
+
+    def put(self, slot: int, nchw: torch.Tensor) -> None:
+        nchw = nchw.to(DEV, torch.float32).contiguous()
+        K.check(K.load().savsr_arena_import(self.a.handle, slot, nchw.data_ptr(), _stream()))
+
+    def get(self, slot: int) -> torch.Tensor:
+        out = torch.empty(self.B, 64, self.H, self.W, device=DEV)
+        K.check(K.load().savsr_arena_export(self.a.handle, slot, out.data_ptr(), _stream()))
+        torch.cuda.synchronize()
+        return out
+
+
+def pack_weight(w: torch.Tensor, n_tile: int = 64, co_pad=None) -> torch.Tensor:
+    lib = K.load()
+    w = w.to(DEV, torch.float32).contiguous()
+    co_real, ci, ks, _ = w.shape
+    co = co_pad or co_real
+    out = torch.empty(lib.savsr_packed_weight_bytes(co, ci, ks), dtype=torch.uint8, device=DEV)
+    K.check(lib.savsr_pack_conv_weight(w.data_ptr(), co_real, co, ci, ks, n_tile, out.data_ptr(), _stream()))
+    return out
+
+
+def unpack_weight(packed: torch.Tensor, co: int, ci: int, ks: int, n_tile: int = 64) -> torch.Tensor:
+    """Inverse of the packed layout (python restatement of the swizzle) -> fp32 [co][ci][ks][ks]."""
+    v = packed.view(torch.bfloat16).float().cpu().numpy()
+    taps = ks * ks
+    nkb = (ci // 64) * taps
+    v = v.reshape(co // n_tile, nkb, n_tile * 64)
+    n = np.arange(n_tile)[:, None]
+    k = np.arange(64)[None, :]
+    pos = n * 64 + ((((k >> 3) ^ (n & 7)) << 3) | (k & 7))
+    blk = v[:, :, pos]                                 # [ng, kb, n, k]
+    blk = blk.reshape(co // n_tile, ci // 64, taps, n_tile, 64)
+    w = blk.transpose(0, 3, 1, 4, 2).reshape(co, ci, ks, ks)
+    return torch.from_numpy(np.ascontiguousarray(w))
+
+
+def group(src, dst, weight, bias=None, act=K.ACT_NONE, slope=0.2, res1=-1, res2=-1, res2_scale=0.0, wstride=0,
+          mask=None, pool=None, aux=None) -> K.ConvGroup:
+    g = K.ConvGroup()
+    for i, s in enumerate(src):
+        g.src_slot[i] = s
+    g.nsrc = len(src)
+    g.dst_slot, g.res1_slot, g.res2_slot, g.res2_scale = dst, res1, res2, res2_scale
+    g.act, g.slope = act, slope
+    g.weight = weight.data_ptr()
+    g.weight_sample_stride = wstride
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.mask = mask.data_ptr() if mask is not None else None
+    g.pool = pool.data_ptr() if pool is not None else None
+    g.aux_dst = aux.data_ptr() if aux is not None else None
+    return g
+
+
+def run_conv(ab: ArenaBox, groups, ksize=3, n_tile=64, dst_mode=K.DST_ARENA, skip=None, impl=K.IMPL_TAP):
+    arr = (K.ConvGroup * len(groups))(*groups)
+    K.check(K.load().savsr_conv(ctx().handle, ab.a.handle, arr, len(groups), ksize, n_tile, dst_mode,
+                                C.byref(skip) if skip is not None else None, impl, _stream()))
+    torch.cuda.synchronize()
+
+
+def _tol(ref: torch.Tensor, rel=2.0 ** -7, abs_=2e-3):
+    return rel * ref.abs() + abs_
+
+
+def assert_close(name, got, ref, rel=2.0 ** -7, abs_=2e-3):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    err = (got - ref).abs()
+    bad = err > _tol(ref, rel, abs_)
+    info = dict(max_abs=float(err.max()), ref_absmax=float(ref.abs().max()), bad=int(bad.sum()), numel=ref.numel())
+    assert not bool(bad.any()), f"{name}: {info}"
+    return info
+
+
+# ------------------------------------------------------------------------------------------------ convolution
+def check_conv(impl=K.IMPL_TAP, ksize=3, nsrc=1, B=1, H=32, W=24, halo=None, full_epilogue=True, seed=0):
+    """savsr_conv (N = 64) vs F.conv2d on the same bf16-rounded operands, with the whole epilogue menu."""
+    torch.manual_seed(seed)
+    if halo is not None:
+        ctx().set_halo(*halo)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ngroups = 2
+    nslots = ngroups * (nsrc + 3) + 1
+    ab = ArenaBox(nslots, B, H, W)
+    tiles = ab.a.tiles
+    results = {}
+    groups, refs, pools = [], [], []
+    slot = 0
+    for gi in range(ngroups):
+        xs = [bf16_round(torch.randn(B, 64, H, W, device=DEV)) for _ in range(nsrc)]
+        src = []
+        for x in xs:
+            ab.put(slot, x); src.append(slot); slot += 1
+        w = bf16_round(torch.randn(64, 64 * nsrc, ksize, ksize, device=DEV) * (1.0 / (8.0 * ksize * nsrc ** 0.5)))
+        bias = torch.randn(64, device=DEV) * 0.1
+        r1 = bf16_round(torch.randn(B, 64, H, W, device=DEV))
+        r2 = bf16_round(torch.randn(B, 64, H, W, device=DEV))
+        mask = torch.rand(B, H * W, device=DEV)
+        ab.put(slot, r1); s_r1 = slot; slot += 1
+        ab.put(slot, r2); s_r2 = slot; slot += 1
+        dst = slot; slot += 1
+        pool = torch.full((B, tiles * 4, 64), float("nan"), device=DEV)
+        wp = pack_weight(w)
+        ref = F.conv2d(torch.cat(xs, 1), w, bias, padding=ksize // 2)
+        if full_epilogue and gi == 0:
+            ref = F.leaky_relu(ref, 0.2) * mask.view(B, 1, H, W) + r1 + 0.75 * r2
+            g = group(src, dst, wp, bias, act=K.ACT_LRELU, slope=0.2, res1=s_r1, res2=s_r2, res2_scale=0.75, mask=mask, pool=pool)
+        elif full_epilogue:
+            ref = F.relu(ref)
+            g = group(src, dst, wp, bias, act=K.ACT_RELU, pool=pool)
+        else:
+            g = group(src, dst, wp, bias)
+        groups.append(g); refs.append((dst, ref, pool if full_epilogue else None)); pools.append((wp, bias, mask, pool))
+    run_conv(ab, groups, ksize=ksize, impl=impl)
+    for gi, (dst, ref, pool) in enumerate(refs):
+        results[f"g{gi}"] = assert_close(f"conv g{gi}", ab.get(dst), ref)
+        if pool is not None:
+            psum = pool.sum(1)                                   # [B, 64]
+            results[f"pool{gi}"] = assert_close(f"pool g{gi}", psum, ref.sum((2, 3)), rel=2e-3, abs_=0.05)
+    return results
+
+
+def check_conv_aux16(impl=K.IMPL_TAP, B=2, H=20, W=28, seed=1):
+    """N = 16 variant writing the fp32 [B][H*W][16] side buffer (OSAdapt mask conv, savsr_arch.py:190-192)."""
+    torch.manual_seed(seed)
+    ab = ArenaBox(2, B, H, W)
+    x = bf16_round(torch.randn(B, 64, H, W, device=DEV))
+    ab.put(0, x)
+    w = bf16_round(torch.randn(16, 64, 3, 3, device=DEV) * 0.05)
+    bias = torch.randn(16, device=DEV) * 0.1
+    aux = torch.full((B, H * W, 16), float("nan"), device=DEV)
+    run_conv(ab, [group([0], 0, pack_weight(w, n_tile=16), bias, act=K.ACT_RELU, aux=aux)], n_tile=16, dst_mode=K.DST_AUX16, impl=impl)
+    ref = F.relu(F.conv2d(x, w, bias, padding=1)).permute(0, 2, 3, 1).reshape(B, H * W, 16)
+    return dict(aux16=assert_close("conv aux16", aux, ref, rel=1e-3, abs_=1e-3))
+
+
+def check_conv_rgb(impl=K.IMPL_TAP, B=2, h=9, w=11, scale=(2.7, 1.5), seed=2):
+    """Tail conv 64 -> 3 + bias + bilinear skip, fp32 NCHW output (savsr_arch.py:738-739)."""
+    torch.manual_seed(seed)
+    H, W = engine.get_hw(h, w, scale)
+    ab = ArenaBox(1, B, H, W)
+    f = bf16_round(torch.randn(B, 64, H, W, device=DEV))
+    ab.put(0, f)
+    wt = bf16_round(torch.randn(3, 64, 3, 3, device=DEV) * 0.05)
+    bias = torch.randn(3, device=DEV) * 0.1
+    b16 = torch.zeros(16, device=DEV); b16[:3] = bias
+    x = torch.rand(B, 7, 3, h, w, device=DEV)
+    out = torch.full((B, 3, H, W), float("nan"), device=DEV)
+    skip = K.RgbSkip(); skip.x = x.data_ptr(); skip.t = 7; skip.centre = 3; skip.h = h; skip.w = w
+    run_conv(ab, [group([0], 0, pack_weight(wt, n_tile=16, co_pad=16), b16, aux=out)], n_tile=16, dst_mode=K.DST_RGB, skip=skip, impl=impl)
+    ref = F.conv2d(f, wt, bias, padding=1) + F.interpolate(x[:, 3], size=(H, W), mode="bilinear", align_corners=False)
+    return dict(rgb=assert_close("conv rgb", out, ref, rel=1e-4, abs_=1e-4))
+
+
+def check_osa_conv_per_sample(impl=K.IMPL_TAP, B=3, H=18, W=26, seed=3):
+    """Per-sample weights (weight_sample_stride): the groups=batch conv of savsr_arch.py:166."""
+    torch.manual_seed(seed)
+    ab = ArenaBox(4, B, H, W)
+    xs = [bf16_round(torch.randn(B, 64, H, W, device=DEV)) for _ in range(3)]
+    for i, x in enumerate(xs):
+        ab.put(i, x)
+    w = bf16_round(torch.randn(B, 64, 192, 3, 3, device=DEV) * 0.03)
+    packs = torch.stack([pack_weight(w[n]) for n in range(B)])
+    run_conv(ab, [group([0, 1, 2], 3, packs, wstride=packs.stride(0))], impl=impl)
+    xin = torch.cat(xs, 1)
+    ref = torch.cat([F.conv2d(xin[n:n + 1], w[n], None, padding=1) for n in range(B)])
+    return dict(per_sample=assert_close("per-sample conv", ab.get(3), ref))
+
+
+def check_pack_roundtrip():
+    torch.manual_seed(4)
+    out = {}
+    for (co, ci, ks, nt) in ((64, 192, 3, 64), (128, 320, 3, 64), (64, 192, 1, 64), (16, 64, 3, 16), (1600, 64, 1, 64)):
+        w = torch.randn(co, ci, ks, ks)
+        back = unpack_weight(pack_weight(w, n_tile=nt), co, ci, ks, nt)
+        assert torch.equal(back, bf16_round(w)), (co, ci, ks, nt)
+        out[f"{co}x{ci}x{ks}"] = "exact"
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ small ops
+def check_front_conv(B=2, h=13, w=15, seed=5):
+    """conv_c / conv_sup on the reflect-padded fp32 window (savsr_arch.py:456-457, 670-690)."""
+    torch.manual_seed(seed)
+    hp, wp = h + (h & 1), w + (w & 1)
+    ab = ArenaBox(2, B, hp, wp)
+    x = torch.rand(B, 7, 3, h, w, device=DEV)
+    wc = torch.randn(64, 3, 3, 3, device=DEV) * 0.2
+    bc = torch.randn(64, device=DEV) * 0.1
+    ws = torch.randn(64, 6, 3, 3, device=DEV) * 0.2
+    bs = torch.randn(64, device=DEV) * 0.1
+    g0 = K.FrontGroup(); g0.frame[0] = 4; g0.nframes = 1; g0.dst_slot = 0; g0.weight = wc.data_ptr(); g0.bias = bc.data_ptr()
+    g1 = K.FrontGroup(); g1.frame[0] = 3; g1.frame[1] = 5; g1.nframes = 2; g1.dst_slot = 1; g1.weight = ws.data_ptr(); g1.bias = bs.data_ptr()
+    arr = (K.FrontGroup * 2)(g0, g1)
+    K.check(K.load().savsr_front_conv(ctx().handle, ab.a.handle, x.data_ptr(), 7, h, w, arr, 2, _stream()))
+    xp = F.pad(x.reshape(-1, 3, h, w), [0, wp - w, 0, hp - h], mode="reflect").view(B, 7, 3, hp, wp) if (hp != h or wp != w) else x
+    ref0 = F.leaky_relu(F.conv2d(xp[:, 4], wc, bc, padding=1), 0.2)
+    ref1 = F.leaky_relu(F.conv2d(torch.cat([xp[:, 3], xp[:, 5]], 1), ws, bs, padding=1), 0.2)
+    return dict(conv_c=assert_close("front conv_c", ab.get(0), ref0), conv_sup=assert_close("front conv_sup", ab.get(1), ref1))
+
+
+def _osa_state(ci, seed):
+    g = torch.Generator().manual_seed(seed)
+    att = max(int(ci * 0.0625), 16)
+    r = lambda *s, k=1.0: torch.randn(*s, generator=g) * k
+    sd = {
+        "o.weight": r(8, 64, ci, 3, 3, k=0.05),
+        "o.scale_routing.0.weight": r(2 * ci, ci + 2, k=(ci + 2) ** -0.5), "o.scale_routing.0.bias": r(2 * ci, k=0.1),
+        "o.scale_routing.2.weight": r(ci, 2 * ci, k=(2 * ci) ** -0.5), "o.scale_routing.2.bias": r(ci, k=0.1),
+        "o.attention.fc.weight": r(att, ci, 1, 1, k=ci ** -0.5),
+        "o.attention.bn.weight": 0.5 + torch.rand(att, generator=g), "o.attention.bn.bias": r(att, k=0.1),
+        "o.attention.bn.running_mean": r(att, k=0.1), "o.attention.bn.running_var": 0.5 + torch.rand(att, generator=g),
+        "o.attention.channel_fc.weight": r(ci, att, 1, 1, k=0.3), "o.attention.channel_fc.bias": r(ci, k=0.1),
+        "o.attention.filter_fc.weight": r(64, att, 1, 1, k=0.3), "o.attention.filter_fc.bias": r(64, k=0.1),
+        "o.attention.spatial_fc.weight": r(9, att, 1, 1, k=0.3), "o.attention.spatial_fc.bias": r(9, k=0.1),
+        "o.attention.kernel_fc.weight": r(8, att, 1, 1, k=0.5), "o.attention.kernel_fc.bias": r(8, k=0.1),
+    }
+    return sd, att
+
+
+def check_osa_prologue(ci=192, B=2, npart=12, npix=300, scale=(1.5, 4), seed=6):
+    """pool -> scale_routing -> ScaleAttention -> assembled per-sample kernel vs the oracle
+    (savsr_arch.py:143-163, 91-96)."""
+    from oracle import savsr_oracle as O
+    sd, att = _osa_state(ci, seed)
+    dsd = {k: v.to(DEV).contiguous() for k, v in sd.items()}
+    nsrc = ci // 64
+    g = torch.Generator().manual_seed(seed + 1)
+    parts = [torch.randn(B, npart, 64, generator=g).to(DEV) for _ in range(nsrc)]
+    pooled = torch.cat([p.sum(1) / npix for p in parts], 1).cpu()          # [B, ci]
+    o = K.OsaParams()
+    o.ci, o.co, o.att = ci, 64, att
+    a = "o.attention"
+    bn_s = dsd[a + ".bn.weight"] / torch.sqrt(dsd[a + ".bn.running_var"] + 1e-5)
+    bn_b = dsd[a + ".bn.bias"] - dsd[a + ".bn.running_mean"] * bn_s
+    o.bank = dsd["o.weight"].data_ptr()
+    o.r0_w, o.r0_b = dsd["o.scale_routing.0.weight"].data_ptr(), dsd["o.scale_routing.0.bias"].data_ptr()
+    o.r2_w, o.r2_b = dsd["o.scale_routing.2.weight"].data_ptr(), dsd["o.scale_routing.2.bias"].data_ptr()
+    o.fc_w = dsd[a + ".fc.weight"].data_ptr()
+    o.bn_scale, o.bn_shift = bn_s.data_ptr(), bn_b.data_ptr()
+    o.ch_w, o.ch_b = dsd[a + ".channel_fc.weight"].data_ptr(), dsd[a + ".channel_fc.bias"].data_ptr()
+    o.fl_w, o.fl_b = dsd[a + ".filter_fc.weight"].data_ptr(), dsd[a + ".filter_fc.bias"].data_ptr()
+    o.sp_w, o.sp_b = dsd[a + ".spatial_fc.weight"].data_ptr(), dsd[a + ".spatial_fc.bias"].data_ptr()
+    o.kn_w, o.kn_b = dsd[a + ".kernel_fc.weight"].data_ptr(), dsd[a + ".kernel_fc.bias"].data_ptr()
+    for i, p in enumerate(parts):
+        o.pool[i] = p.data_ptr()
+    scratch = torch.zeros(B, 5 * ci + 192, device=DEV)
+    packed = torch.zeros(B, 64 * ci * 9 * 2, dtype=torch.uint8, device=DEV)
+    o.scratch, o.packed = scratch.data_ptr(), packed.data_ptr()
+    arr = (K.OsaParams * 1)(o)
+    inv_h = float(np.float32(1.0) / np.float32(scale[0])); inv_w = float(np.float32(1.0) / np.float32(scale[1]))
+    K.check(K.load().savsr_osa_prologue(ctx().handle, arr, 1, B, npart, npix, inv_h, inv_w, _stream()))
+    torch.cuda.synchronize()
+    ca, fa, sa, ka = O.osa_attention(sd, "o", pooled, scale)
+    got = scratch[:, 4 * ci + 8: 4 * ci + 8 + ci + 64 + 17].cpu()
+    ref = torch.cat([ca, fa, sa, ka], 1)
+    res = dict(attention=assert_close("osa attention", got, ref, rel=1e-4, abs_=1e-5))
+    wref = O.osa_fold_weight(sd["o.weight"], ca, fa, sa, ka)                 # [B, 64, ci, 3, 3]
+    for n in range(B):
+        wgot = unpack_weight(packed[n], 64, ci, 3)
+        res[f"weight{n}"] = assert_close(f"osa weight {n}", wgot, wref[n], rel=2.0 ** -8, abs_=1e-6)
+    return res
+
+
+def check_ca(B=2, H=20, W=24, seed=7):
+    """RCAB channel attention: dst = x + t * sigmoid(W2 relu(W1 mean(t) + b1) + b2) (savsr_arch.py:514-549)."""
+    torch.manual_seed(seed)
+    ab = ArenaBox(3, B, H, W)
+    t = bf16_round(torch.randn(B, 64, H, W, device=DEV)); x = bf16_round(torch.randn(B, 64, H, W, device=DEV))
+    ab.put(0, t); ab.put(1, x)
+    npart = 7
+    parts = torch.randn(B, npart, 64, device=DEV)
+    parts = parts - parts.sum(1, keepdim=True) / npart + t.sum((2, 3)).unsqueeze(1) / npart     # partials summing to sum(t)
+    w1 = torch.randn(4, 64, device=DEV) * 0.3; b1 = torch.randn(4, device=DEV) * 0.1
+    w2 = torch.randn(64, 4, device=DEV) * 0.5; b2 = torch.randn(64, device=DEV) * 0.1
+    K.check(K.load().savsr_ca_scale_residual(ctx().handle, ab.a.handle, 0, 1, 2, parts.data_ptr(), npart, w1.data_ptr(),
+                                             b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), _stream()))
+    y = torch.sigmoid(F.relu(t.mean((2, 3)) @ w1.t() + b1) @ w2.t() + b2)
+    ref = x + t * y.view(B, 64, 1, 1)
+    return dict(ca=assert_close("ca_scale_residual", ab.get(2), ref))
+
+
+def check_mask(B=2, H=12, W=18, seed=8):
+    """OSAdapt mask tail: AvgPool2 -> 2 x (conv16+ReLU) -> bilinear x2 -> conv16->1 -> sigmoid (savsr_arch.py:193-205)."""
+    torch.manual_seed(seed)
+    in16 = torch.relu(torch.randn(B, 16, H, W, device=DEV))
+    wa = torch.randn(16, 16, 3, 3, device=DEV) * 0.1; ba = torch.randn(16, device=DEV) * 0.1
+    wb = torch.randn(16, 16, 3, 3, device=DEV) * 0.1; bb = torch.randn(16, device=DEV) * 0.1
+    wc = torch.randn(1, 16, 3, 3, device=DEV) * 0.2; bc = torch.randn(1, device=DEV) * 0.1
+    nhwc = in16.permute(0, 2, 3, 1).reshape(B, H * W, 16).contiguous()
+    h0 = torch.empty(B, (H // 2) * (W // 2), 16, device=DEV); h1 = torch.empty_like(h0)
+    mask = torch.empty(B, H * W, device=DEV)
+    K.check(K.load().savsr_osadapt_mask(ctx().handle, nhwc.data_ptr(), B, H, W, wa.data_ptr(), ba.data_ptr(), wb.data_ptr(),
+                                        bb.data_ptr(), wc.data_ptr(), bc.data_ptr(), h0.data_ptr(), h1.data_ptr(), mask.data_ptr(), _stream()))
+    t = F.avg_pool2d(in16, 2)
+    t = F.relu(F.conv2d(t, wa, ba, padding=1))
+    t = F.relu(F.conv2d(t, wb, bb, padding=1))
+    t = F.interpolate(t, scale_factor=2, mode="bilinear", align_corners=False)
+    ref = torch.sigmoid(F.conv2d(t, wc, bc, padding=1)).view(B, H * W)
+    return dict(mask=assert_close("osadapt mask", mask, ref, rel=1e-4, abs_=1e-5))
+
+
+# ------------------------------------------------------------------------------------------------ SATU
+def _satu_weights(sd):
+    d = {k: v.to(DEV).contiguous() for k, v in sd.items() if k.startswith("upsample.")}
+    sw = K.SatuWeights()
+    sw.body0_w, sw.body0_b = d["upsample.body.0.weight"].data_ptr(), d["upsample.body.0.bias"].data_ptr()
+    sw.body2_w, sw.body2_b = d["upsample.body.2.weight"].data_ptr(), d["upsample.body.2.bias"].data_ptr()
+    sw.routing_w, sw.routing_b = d["upsample.routing.0.weight"].data_ptr(), d["upsample.routing.0.bias"].data_ptr()
+    sw.offset_w, sw.offset_b = d["upsample.offset.weight"].data_ptr(), d["upsample.offset.bias"].data_ptr()
+    sw.st_offset_w, sw.st_offset_b = d["upsample.st_offset.weight"].data_ptr(), d["upsample.st_offset.bias"].data_ptr()
+    sw.compress, sw.expand = d["upsample.weight_compress"].data_ptr(), d["upsample.weight_expand"].data_ptr()
+    return sw, d
+
+
+def satu_index(h, w, scale, sd=None):
+    """Run savsr_satu_index; returns dict of CPU arrays (and the table if weights are given)."""
+    H, W = engine.get_hw(h, w, scale)
+    s = engine.normalize_scale(scale)
+    out = dict(rel_y=torch.empty(H, device=DEV), rel_x=torch.empty(W, device=DEV),
+               cell_y=torch.empty(H, dtype=torch.int32, device=DEV), cell_x=torch.empty(W, dtype=torch.int32, device=DEV),
+               base_y=torch.empty(H, device=DEV), base_x=torch.empty(W, device=DEV),
+               corner_y=torch.empty(H, dtype=torch.int32, device=DEV), corner_x=torch.empty(W, dtype=torch.int32, device=DEV))
+    table = None
+    sw = keep = None
+    if sd is not None:
+        sw, keep = _satu_weights(sd)
+        table = torch.empty(H * W, 8, device=DEV)
+    K.check(K.load().savsr_satu_index(ctx().handle, C.byref(sw) if sw is not None else None, h, w, H, W, float(s[0]), float(s[1]),
+                                      out["rel_y"].data_ptr(), out["rel_x"].data_ptr(), out["cell_y"].data_ptr(), out["cell_x"].data_ptr(),
+                                      out["base_y"].data_ptr(), out["base_x"].data_ptr(), out["corner_y"].data_ptr(),
+                                      out["corner_x"].data_ptr(), table.data_ptr() if table is not None else None, _stream()))
+    torch.cuda.synchronize()
+    res = {k: v.cpu().numpy() for k, v in out.items()}
+    if table is not None:
+        res["table"] = table.cpu()
+    return res, H, W
+
+
+def check_satu_index(h=144, w=180, scale=(1.5, 4)):
+    """Bit-exact index vectors vs the numpy oracle (savsr_arch.py:326-333, 270-280)."""
+    from oracle import savsr_oracle as O
+    res, H, W = satu_index(h, w, scale)
+    s = engine.normalize_scale(scale)
+    for ax, n_out, n_lr, sc in (("y", H, h, s[0]), ("x", W, w, s[1])):
+        assert np.array_equal(res["rel_" + ax].view(np.uint32), O.satu_rel_coord(n_out, sc).view(np.uint32)), f"rel_{ax} not bit-exact"
+        assert np.array_equal(res["cell_" + ax], O.satu_cell(n_out, sc)), f"cell_{ax}"
+        assert np.array_equal(res["base_" + ax].view(np.uint32), O.satu_base_norm(n_out, n_lr, sc).view(np.uint32)), f"base_{ax} not bit-exact"
+        assert np.array_equal(res["corner_" + ax], O.satu_base_corner(n_out, n_lr, sc)), f"corner_{ax}"
+    return dict(H=H, W=W, status="bit-exact")
+
+
+def check_satu_table(h=13, w=15, scale=(2.7, 1.5), seed=1):
+    from oracle import savsr_oracle as O
+    from oracle.state_dict_fixture import make_state_dict
+    sd = make_state_dict(seed)
+    res, H, W = satu_index(h, w, scale, sd)
+    off, st_off, r = O.satu_heads(sd, "upsample", h, w, scale)
+    ref = torch.cat([off, st_off, r], 1)[0].permute(1, 2, 0).reshape(H * W, 8)
+    return dict(table=assert_close("satu table", res["table"], ref, rel=1e-4, abs_=2e-6))
+
+
+def check_satu_sta(B=2, h=13, w=15, seed=9):
+    """sta_conv with replicate padding on the unpadded region (savsr_arch.py:297-313)."""
+    from oracle import savsr_oracle as O
+    torch.manual_seed(seed)
+    hp, wp = h + (h & 1), w + (w & 1)
+    ab = ArenaBox(27, B, hp, wp)
+    x = bf16_round(torch.randn(B, 64, hp, wp, device=DEV))
+    kern = bf16_round(torch.randn(B, 1600, hp, wp, device=DEV) * 0.2)       # reference layout: channel c*25 + tap
+    ab.put(0, x)
+    kt = kern.view(B, 64, 25, hp, wp)
+    for tp in range(25):
+        ab.put(1 + tp, kt[:, :, tp].contiguous())
+    K.check(K.load().savsr_satu_sta(ctx().handle, ab.a.handle, 0, 1, 26, h, w, _stream()))
+    ref = O.satu_sta_conv(x[..., :h, :w].cpu(), kern[..., :h, :w].cpu())
+    got = ab.get(26)[..., :h, :w]
+    return dict(sta=assert_close("satu sta", got, ref))
+
+
+def check_satu_gather(B=2, h=13, w=15, scale=(2.7, 1.5), seed=1):
+    """Fused HR gather + routed experts vs the oracle (savsr_arch.py:262-295, 353-373)."""
+    from oracle import savsr_oracle as O
+    from oracle.state_dict_fixture import make_state_dict
+    sd = make_state_dict(seed)
+    # exaggerate the learned offsets so that corners move and the zero-padding border is exercised
+    sd["upsample.offset.weight"] = sd["upsample.offset.weight"] * 8
+    sd["upsample.st_offset.weight"] = sd["upsample.st_offset.weight"] * 8
+    torch.manual_seed(seed)
+    hp, wp = h + (h & 1), w + (w & 1)
+    res, H, W = satu_index(h, w, scale, sd)
+    lr = ArenaBox(2, B, hp, wp)
+    hr = ArenaBox(2, B, H, W)
+    x = bf16_round(torch.randn(B, 64, hp, wp, device=DEV)); sta = bf16_round(torch.randn(B, 64, hp, wp, device=DEV))
+    lr.put(0, x); lr.put(1, sta)
+    sw, keep = _satu_weights(sd)
+    table = res["table"].to(DEV); by = torch.from_numpy(res["base_y"]).to(DEV); bx = torch.from_numpy(res["base_x"]).to(DEV)
+    K.check(K.load().savsr_satu_gather(ctx().handle, lr.a.handle, 0, 1, h, w, hr.a.handle, 0, 1, table.data_ptr(), by.data_ptr(),
+                                       bx.data_ptr(), C.byref(sw), _stream()))
+    off, st_off, r = O.satu_heads(sd, "upsample", h, w, scale)
+    xc, sc = x[..., :h, :w].cpu(), sta[..., :h, :w].cpu()
+    fea0 = O.satu_gather(xc, scale, off)
+    fea = O.satu_expert_mix(sd, "upsample", fea0, r)
+    sta_s = O.satu_gather(sc, scale, st_off)
+    return dict(sta_sampled=assert_close("gather sta", hr.get(0), sta_s), fea=assert_close("gather fea", hr.get(1), fea))
+
+
+# ------------------------------------------------------------------------------------------------ whole forward
+TAPS = ("f2p_last", "p2f_last", "align", "rg0", "rg3", "trunk", "satu_sta", "satu_out")
+
+
+def run_forward(sd, x, scale, impl="tap", taps=(), graph=False):
+    import savsr_b200
+    net = savsr_b200.SAVSR().to(DEV)
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    net.conv_impl, net.use_graph, net.debug_taps = impl, graph, tuple(taps)
+    net.set_scale(scale)
+    with torch.no_grad():
+        y = net(x.to(DEV))
+    plan = net.plan_for(x.to(DEV))
+    torch.cuda.synchronize()
+    return y.cpu(), {k: plan.read_tap(k).cpu() for k in taps}, plan
+
+
+def stage_report(got: dict, ref: dict, h, w) -> dict:
+    """Relative error (max-abs / ref abs-max) per stage on the unpadded region."""
+    rep = {}
+    for k, g in got.items():
+        if k not in ref:
+            continue
+        r = ref[k]
+        g = g[..., :r.shape[-2], :r.shape[-1]]
+        rep[k] = float((g - r).abs().max() / (r.abs().max() + 1e-12))
+    return rep
+
+
+def check_forward(b=1, h=16, w=20, scale=(2, 2), sd_seed=0, in_seed=1234, impl="tap", graph=False, tol=5e-3, stage_tol=0.05):
+    """End-to-end SAVSR forward vs the CPU oracle (bf16 operand path: tolerance on max-abs and PSNR)."""
+    from oracle import savsr_oracle as O
+    from oracle.state_dict_fixture import make_input, make_state_dict
+    sd = make_state_dict(sd_seed)
+    x = make_input(b, h, w, in_seed)
+    probes = {}
+    y_ref = O.forward(sd, x, scale, probes)
+    y, taps, plan = run_forward(sd, x, scale, impl=impl, taps=TAPS, graph=graph)
+    ref_stage = dict(f2p_last=probes["f2p_last"], p2f_last=probes["p2f_last"], align=probes["align"], rg0=probes["rg0"],
+                     rg3=probes["rg3"], trunk=probes["trunk"], satu_sta=probes["satu_sta"], satu_out=probes["satu_out"])
+    rep = stage_report(taps, ref_stage, h, w)
+    err = float((y - y_ref).abs().max())
+    tail_rel = float(((y - probes["skip"]) - probes["tail"]).abs().max() / (probes["tail"].abs().max() + 1e-12))
+    info = dict(shape=tuple(y.shape), max_abs=err, tail_rel=tail_rel, psnr_vs_oracle=O.psnr_y(y, y_ref), stages=rep,
+                launches=plan.n_launches)
+    assert y.shape == y_ref.shape, info
+    assert err < tol, info
+    assert all(v < stage_tol for v in rep.values()), info
+    return info

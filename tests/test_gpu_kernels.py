@@ -1,0 +1,73 @@
+"""-m gpu: every C-ABI entry point against fp32 PyTorch / the CPU oracle on seeded inputs."""
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gpu_checks
+    return gpu_checks
+
+
+def test_pack_roundtrip(G):
+    G.check_pack_roundtrip()
+
+
+@pytest.mark.parametrize("ksize,nsrc,B,H,W", [(3, 1, 1, 32, 24), (3, 3, 2, 37, 45), (3, 5, 1, 48, 40), (1, 3, 2, 37, 45),
+                                               (3, 2, 1, 5, 3), (3, 2, 2, 144, 180)])
+def test_conv_tcgen05_tap(G, ksize, nsrc, B, H, W):
+    G.check_conv(impl=G.K.IMPL_TAP, ksize=ksize, nsrc=nsrc, B=B, H=H, W=W)
+
+
+def test_conv_checker_kernel(G):
+    G.check_conv(impl=G.K.IMPL_CHECK, ksize=3, nsrc=2, B=2, H=21, W=19)
+
+
+def test_conv_aux16(G):
+    G.check_conv_aux16()
+
+
+def test_conv_rgb_skip(G):
+    G.check_conv_rgb()
+    G.check_conv_rgb(B=1, h=16, w=16, scale=(4, 4), seed=12)
+
+
+def test_conv_per_sample_weights(G):
+    G.check_osa_conv_per_sample()
+
+
+def test_front_conv(G):
+    G.check_front_conv()
+    G.check_front_conv(B=1, h=16, w=20, seed=15)
+
+
+@pytest.mark.parametrize("ci,B", [(192, 2), (320, 1), (64, 3)])
+def test_osa_prologue(G, ci, B):
+    G.check_osa_prologue(ci=ci, B=B)
+
+
+def test_channel_attention(G):
+    G.check_ca()
+
+
+def test_osadapt_mask(G):
+    G.check_mask()
+
+
+@pytest.mark.parametrize("h,w,scale", [(144, 180, (4, 4)), (144, 180, (1.5, 4)), (144, 180, (2.7, 2.7)), (64, 64, (2, 2)),
+                                         (180, 318, (4, 4)), (63, 65, (2.7, 2.7)), (33, 35, (1.5, 1.5)), (31, 31, (3, 3))])
+def test_satu_index_bit_exact(G, h, w, scale):
+    G.check_satu_index(h, w, scale)
+
+
+def test_satu_table(G):
+    G.check_satu_table()
+
+
+def test_satu_sta(G):
+    G.check_satu_sta()
+
+
+def test_satu_gather(G):
+    G.check_satu_gather()

@@ -1,0 +1,122 @@
+"""CPU-only: the host-side forward plan (slot allocation, launch order, grouping) against a recording fake
+of the C library.  Checks the dataflow invariants the kernels rely on; no compute happens here."""
+import ctypes as C
+
+import pytest
+import torch
+
+from fake_lib import CpuPlan, mocked_engine
+from oracle.state_dict_fixture import make_state_dict
+from savsr_b200 import _capi as K
+
+
+def _groups(args):
+    arr, n = args[2], args[3]
+    return [arr[i] for i in range(n)]
+
+
+@pytest.fixture(scope="module")
+def recorded():
+    sd = make_state_dict(0)
+    with mocked_engine() as lib:
+        plan = CpuPlan(sd, 2, 13, 15, (1.5, 4))
+        for op in plan.ops:
+            assert op(0) == 0
+        return plan, list(lib.calls)
+
+
+def test_launch_census(recorded):
+    plan, calls = recorded
+    names = [c[0] for c in calls]
+    build_time = names.count("savsr_pack_conv_weight")
+    # distinct conv weights: l1 2*(4*3 conv0 + 1 conv1 + 4*3 conv2 + merge) + l2 (5 + 2*(5+5) + 1 + 1) + RG 4*(16+1)
+    # + mask.0 x4 + conv_last + kernel_conv + fusion + tail
+    assert build_time == 2 * (12 + 1 + 12 + 1) + (5 + 20 + 1 + 1) + 68 + 4 + 1 + 1 + 1 + 1
+    run = names[names.index("savsr_satu_index") + 1:] if False else names
+    assert names.count("savsr_front_conv") == 5                      # one per propagation iteration, both directions
+    assert names.count("savsr_ca_scale_residual") == 32              # 4 groups x 8 RCAB
+    assert names.count("savsr_osadapt_mask") == 4
+    assert names.count("savsr_osa_prologue") == 5 * 3 + 2 + 4        # l1 blocks 1-3 (both dirs batched), l2 x2, adapt x4
+    assert names.count("savsr_satu_sta") == 1 and names.count("savsr_satu_gather") == 1
+    # conv launches: l1 5*(4*3 + 1) + l2 (1 + 2*3 + 1 + 1) + RG 4*(16 + 1 + mask + adapt) + conv_last + kernel_conv + fusion + tail
+    assert names.count("savsr_conv") == 5 * 13 + 9 + 4 * 19 + 1 + 1 + 1 + 1
+
+
+def test_no_conv_writes_a_slot_it_reads(recorded):
+    _, calls = recorded
+    for name, args in calls:
+        if name != "savsr_conv" or args[6] != K.DST_ARENA:
+            continue
+        for g in _groups(args):
+            srcs = [g.src_slot[i] for i in range(g.nsrc)]
+            assert g.dst_slot not in srcs
+            assert g.res2_slot != g.dst_slot
+
+
+def test_slots_written_before_read_and_hidden_states_persist(recorded):
+    plan, calls = recorded
+    written = {}                                   # (arena id, slot) -> launch index
+    zero_reads = 0
+    F_slots = set()
+    for idx, (name, args) in enumerate(calls):
+        if name == "savsr_front_conv":
+            for i in range(args[7]):
+                written[(id(args[1]), args[6][i].dst_slot)] = idx
+        elif name == "savsr_conv":
+            arena = id(args[1])
+            for g in _groups(args):
+                for i in range(g.nsrc):
+                    s = g.src_slot[i]
+                    if (arena, s) not in written:
+                        zero_reads += 1            # only the all-zero initial hidden state may be read unwritten
+                        assert s == 0, f"launch {idx} reads slot {s} before any write"
+                for r in (g.res1_slot, g.res2_slot):
+                    if r >= 0 and (arena, r) not in written:
+                        assert r == 0
+            if args[6] == K.DST_ARENA:
+                for g in _groups(args):
+                    written[(arena, g.dst_slot)] = idx
+        elif name == "savsr_ca_scale_residual":
+            arena = id(args[1])
+            assert (arena, args[2]) in written and (arena, args[3]) in written
+            written[(arena, args[4])] = idx
+        elif name == "savsr_satu_sta":
+            arena = id(args[1])
+            assert all((arena, args[3] + t) in written for t in range(25)) and (arena, args[2]) in written
+            written[(arena, args[4])] = idx
+        elif name == "savsr_satu_gather":
+            written[(id(args[6]), args[7])] = idx
+            written[(id(args[6]), args[8])] = idx
+    assert zero_reads > 0                          # first iteration of both directions starts from zeros
+
+
+def test_propagation_batches_both_directions(recorded):
+    _, calls = recorded
+    convs = [a for n, a in calls if n == "savsr_conv"]
+    assert convs[0][3] == 6 and convs[0][4] == 3   # conv0 of block 0: 2 directions x 3 streams, 3x3
+    assert convs[1][3] == 2 and convs[1][4] == 1   # conv1 (1x1 192->64) for both directions
+    assert convs[2][3] == 6                         # conv2 x 6 with residual
+    g = convs[2][2][0]
+    assert g.nsrc == 2 and g.res1_slot >= 0 and g.act == K.ACT_LRELU
+    osa = convs[4]                                  # block 1: conv0, [prologue], OSA conv
+    assert osa[3] == 2 and osa[2][0].nsrc == 3 and osa[2][0].weight_sample_stride == 64 * 192 * 9 * 2 and not osa[2][0].bias
+
+
+def test_fusion_order_reverses_f2p(recorded):
+    plan, calls = recorded
+    convs = [a for n, a in calls if n == "savsr_conv"]
+    merges = [c for c in convs if c[3] == 2 and c[4] == 3 and c[2][0].nsrc == 3 and c[2][0].act == K.ACT_NONE and c[2][0].bias]
+    f2p_out = [m[2][0].dst_slot for m in merges[:5]]
+    p2f_out = [m[2][1].dst_slot for m in merges[:5]]
+    conv_h = next(c for c in convs if c[3] == 5 and c[2][0].nsrc == 2)
+    for i in range(5):
+        g = conv_h[2][i]
+        assert g.src_slot[0] == f2p_out[4 - i]      # h_f2p_list.insert(0, .) (savsr_arch.py:713)
+        assert g.src_slot[1] == p2f_out[i]          # h_p2f_list.append(.)   (savsr_arch.py:719)
+
+
+def test_sizes(recorded):
+    plan, _ = recorded
+    assert (plan.hp, plan.wp) == (14, 16)
+    assert (plan.H, plan.W) == (20, 60)            # round(13*1.5)=round(19.5)=20 (half-to-even), 15*4
+    assert tuple(plan.out.shape) == (2, 3, 20, 60)
