@@ -97,9 +97,6 @@ const char* savsr_last_error(void);
 int savsr_ctx_create(int device, savsr_ctx** out);
 void savsr_ctx_destroy(savsr_ctx* ctx);
 int savsr_ctx_sm_count(const savsr_ctx* ctx);
-/* HALO fetch-mode layout knobs (bring-up / tests): halo row pitch in pixels (10 or 16) and whether the
- * UMMA shared-memory descriptor carries base_offset = (start >> 7) & 7.  Affects arenas created later. */
-int savsr_ctx_set_halo(savsr_ctx* ctx, int pitch, int use_base_offset);
 
 /* ---- activation arenas --------------------------------------------------------------------- */
 /* Bytes the caller must allocate (256-byte aligned) for an arena of that shape. */

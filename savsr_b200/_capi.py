@@ -83,7 +83,6 @@ SIGNATURES = {
     "savsr_ctx_create": (_I, [_I, C.POINTER(_VP)]),
     "savsr_ctx_destroy": (None, [_VP]),
     "savsr_ctx_sm_count": (_I, [_VP]),
-    "savsr_ctx_set_halo": (_I, [_VP, _I, _I]),
     "savsr_arena_bytes": (_SZ, [_I, _I, _I, _I]),
     "savsr_arena_create": (_I, [_VP, _VP, _I, _I, _I, _I, C.POINTER(_VP)]),
     "savsr_arena_destroy": (None, [_VP]),
@@ -141,9 +140,6 @@ class Context:
         self.handle = h
         self.device = int(device)
         self.sm_count = self.lib.savsr_ctx_sm_count(h)
-
-    def set_halo(self, pitch: int, use_base_offset: bool) -> None:
-        check(self.lib.savsr_ctx_set_halo(self.handle, int(pitch), int(bool(use_base_offset))))
 
     def __del__(self):
         try:

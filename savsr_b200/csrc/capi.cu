@@ -72,24 +72,12 @@ extern "C" int savsr_ctx_create(int device, savsr_ctx** out) {
   c->cc_major = prop.major;
   c->cc_minor = prop.minor;
   c->encode_tiled = fn;
-  c->halo_pitch = 10;
-  c->halo_base_offset = 1;
-  if (const char* e = getenv("SAVSR_HALO_PITCH")) c->halo_pitch = atoi(e) == 16 ? 16 : 10;
-  if (const char* e = getenv("SAVSR_HALO_BASE_OFFSET")) c->halo_base_offset = atoi(e) ? 1 : 0;
   *out = c;
   return 0;
 }
 
 extern "C" void savsr_ctx_destroy(savsr_ctx* ctx) { free(ctx); }
 extern "C" int savsr_ctx_sm_count(const savsr_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
-
-extern "C" int savsr_ctx_set_halo(savsr_ctx* ctx, int pitch, int use_base_offset) {
-  SAVSR_REQUIRE(ctx, "savsr_ctx_set_halo: null context");
-  SAVSR_REQUIRE(pitch == 10 || pitch == 16, "savsr_ctx_set_halo: pitch must be 10 or 16, got %d", pitch);
-  ctx->halo_pitch = pitch;
-  ctx->halo_base_offset = use_base_offset ? 1 : 0;
-  return 0;
-}
 
 extern "C" size_t savsr_arena_bytes(int nslots, int batch, int height, int width) {
   if (nslots <= 0 || batch <= 0 || height <= 0 || width <= 0) return 0;
@@ -110,7 +98,7 @@ extern "C" int savsr_arena_create(savsr_ctx* ctx, void* base, int nslots, int ba
   a->tiles_x = (width + kTileW - 1) / kTileW;
   a->tiles_y = (height + kTileH - 1) / kTileH;
   int rc = encode_map(ctx, &a->tm_tile, base, nslots * batch, height, width, kTileW, kTileH);
-  if (rc == 0) rc = encode_map(ctx, &a->tm_halo, base, nslots * batch, height, width, ctx->halo_pitch, kTileH + 2);
+  if (rc == 0) rc = encode_map(ctx, &a->tm_halo, base, nslots * batch, height, width, kTileW + 2, kTileH + 2);
   if (rc != 0) { free(a); return rc; }
   *out = a;
   return 0;

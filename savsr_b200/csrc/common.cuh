@@ -43,8 +43,6 @@ struct savsr_ctx {
   int sm_count;
   int cc_major, cc_minor;
   void* encode_tiled;  // PFN_cuTensorMapEncodeTiled
-  int halo_pitch;      // halo box width in pixels (10 = tight, 16 = 1024-byte aligned rows)
-  int halo_base_offset;  // 1: put (addr >> 7) & 7 into the UMMA descriptor base_offset field
 };
 
 struct savsr_arena {
@@ -53,7 +51,7 @@ struct savsr_arena {
   int nslots, batch, height, width;
   int tiles_x, tiles_y;
   CUtensorMap tm_tile;  // box [64, 8, 16, 1]
-  CUtensorMap tm_halo;  // box [64, halo_pitch, 18, 1]
+  CUtensorMap tm_halo;  // box [64, 10, 18, 1]
 };
 
 #ifdef __CUDACC__
@@ -102,11 +100,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware, do not poll
       : "memory");
   return ok != 0;
 }

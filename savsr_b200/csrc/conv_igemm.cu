@@ -2,18 +2,24 @@
 //
 //   D[128 pixels, N] += A[128 pixels, 64 ch] * B[64 ch, N]      per (source, tap) K-block
 //
-//  * A operand: NHWC bf16 arena, fetched by TMA as a 4-D box (64 ch, 8 x, 16 y, 1 image) straight into
-//    the 128-byte-swizzled K-major layout tcgen05.mma reads.  Zero padding of the convolution is the
-//    TMA out-of-bounds fill.  Two fetch modes:
-//      TAP  : one 16 KB box per filter tap (9 per source), box origin shifted by the tap.
+//  * A operand: NHWC bf16 arena, fetched by TMA as a 4-D box (64 ch, x, y, 1 image) straight into the
+//    128-byte-swizzled K-major layout tcgen05.mma reads.  Zero padding of the convolution is the TMA
+//    out-of-bounds fill.  Two fetch modes:
+//      TAP  : one 8x16-pixel box (16 KB) per filter tap, box origin shifted by the tap.
 //      HALO : one (8+2) x (16+2) halo box per source; the nine taps are nine UMMA descriptors into the
-//             same tile (start address shifted by whole 128-byte pixel rows, SBO = halo row pitch),
-//             cutting L2->smem traffic for A by ~6x.
-//  * B operand: weights pre-packed per K-block as [N][64] bf16, already swizzled, fetched with a 1-D
-//    bulk copy (per-sample pointer for OSA-Conv: the "groups = batch" conv of savsr_arch.py:166).
+//             same tile (start address shifted by whole 128-byte pixel rows, SBO = halo row pitch).
+//             Measured on B200: the swizzle XOR is a function of absolute shared-memory address bits,
+//             so shifted starts and an SBO that is not a multiple of 1024 need no base_offset.
+//  * B operand (weights): STATIONARY.  All CTAs of a launch need the same few K-blocks, and streaming
+//    them per tile from L2 makes 148 SMs hammer the same 64 lines (measured: ~1000 cycles per K-block
+//    vs 128 cycles of MMA).  So each persistent CTA works on a contiguous chunk of tiles and keeps up to
+//    18 pre-swizzled K-blocks (144 KB) resident in shared memory, reloading only when the (conv, sample)
+//    weight set changes; K-blocks beyond that are streamed through a small ring.  Loads are issued in a
+//    per-CTA rotated order so that concurrent CTAs pull different L2 lines.
 //  * accumulator: fp32 in TMEM, double buffered (2 x N columns) so the epilogue of tile i overlaps the
-//    main loop of tile i+1.  Persistent CTAs, one per SM, static round-robin over (conv, sample, tile).
-//  * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (single thread), warps 2-5 = epilogue
+//    main loop of tile i+1.
+//  * warp roles: warp 0 = TMA producer (one thread), warp 1 = MMA issuer (one thread, owns TMEM),
+//    warps 2-9 = epilogue: each warp owns a 32-row TMEM lane quadrant x 32 columns
 //    (tcgen05.ld -> bias/activation/mask/residuals -> bf16 NHWC store, optional pooled partial sums).
 //
 // The CUDA-core kernel at the bottom implements the same contract with plain loads and shares the
@@ -24,10 +30,14 @@
 
 namespace savsr {
 
-constexpr int kMaxAStages = 6;
-constexpr int kBStages = 8;
-constexpr int kARegionBytes = 6 * 16384 + 12288;  // 108 KB: 6 tap stages | 4 halo-10 stages | 3 halo-16 stages
-constexpr int kNumThreads = 192;
+constexpr int kMaxAStages = 4;
+constexpr int kHaloPitch = 10;                        // halo row pitch in pixels (tile width 8 + 2)
+constexpr int kHaloStageBytes = 23552;               // 10 x 18 x 128 = 23040, rounded up to 1 KB
+constexpr int kARegionBytes = 3 * kHaloStageBytes;   // 3 halo stages | 4 tap stages (4 x 16 KB)
+constexpr int kBBlocks = 18;                         // resident weight K-blocks per CTA (N=64: 144 KB)
+constexpr int kRing = 3;                             // ring stages carved out of the B region when K is larger
+constexpr int kEpiWarps = 8;
+constexpr int kNumThreads = 64 + 32 * kEpiWarps;
 
 struct ConvParams {
   CUtensorMap tm_tile;
@@ -37,10 +47,10 @@ struct ConvParams {
   __nv_bfloat16* arena;
   int ngroups, batch, height, width, tiles_x, tiles_y;
   int ntaps;            // 1 or 9
+  int nsrc;             // identical for all groups of a launch
   int halo;             // A fetch mode
-  int halo_pitch;       // pixels per halo row in smem (10 or 16)
-  int use_base_offset;  // fill UMMA descriptor base_offset from the start address
-  int a_stage_bytes, a_stages;
+  int n_res;            // K-blocks held resident; the remaining nsrc*ntaps - n_res go through the ring
+  int chunk;            // consecutive work items per CTA
   int dst_mode;
 };
 
@@ -60,11 +70,12 @@ __device__ __forceinline__ void bilinear_src(int dst, int in_size, int out_size,
   l1 = src - static_cast<float>(i0);
 }
 
-// Epilogue shared by the tensor-core kernel and the checker.  `v` holds the fp32 accumulator row of
-// pixel m = quad * 32 + lane of the tile; one warp per 32-row quadrant.
-template <int BN>
+// Epilogue shared by the tensor-core kernel and the checker.  `v` holds NC consecutive accumulator
+// columns (output channels col0 .. col0+NC) of pixel m = quad * 32 + lane of the tile.
+// NC = 32: bf16 arena destination (two warps per quadrant); NC = 16: AUX16 / RGB destinations.
+template <int NC>
 __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const savsr_conv_group& g, int n, int tile,
-                                              int quad, int lane, float (&v)[BN]) {
+                                              int quad, int lane, float (&v)[NC], int col0) {
   const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
   const int m = quad * 32 + lane;
   const int px = tx * kTileW + (m & (kTileW - 1));
@@ -74,24 +85,28 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const savsr_c
   const long pix = static_cast<long>(py) * p.width + px;
 
   if (g.bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(g.bias + col0);
 #pragma unroll
-    for (int c = 0; c < BN; ++c) v[c] += __ldg(g.bias + c);
+    for (int c = 0; c < NC / 4; ++c) {
+      const float4 b = __ldg(b4 + c);
+      v[4 * c + 0] += b.x; v[4 * c + 1] += b.y; v[4 * c + 2] += b.z; v[4 * c + 3] += b.w;
+    }
   }
   if (g.act != SAVSR_ACT_NONE) {
 #pragma unroll
-    for (int c = 0; c < BN; ++c) v[c] = apply_act(v[c], g.act, g.slope);
+    for (int c = 0; c < NC; ++c) v[c] = apply_act(v[c], g.act, g.slope);
   }
 
-  if constexpr (BN == 64) {
+  if constexpr (NC == 32) {
     if (g.mask != nullptr) {
       const float mk = valid ? __ldg(g.mask + n * npix + pix) : 0.f;
 #pragma unroll
-      for (int c = 0; c < BN; ++c) v[c] *= mk;
+      for (int c = 0; c < NC; ++c) v[c] *= mk;
     }
     if (g.res1_slot >= 0 && valid) {
-      const uint4* r = reinterpret_cast<const uint4*>(p.arena + ((static_cast<long>(g.res1_slot) * p.batch + n) * npix + pix) * kC);
+      const uint4* r = reinterpret_cast<const uint4*>(p.arena + ((static_cast<long>(g.res1_slot) * p.batch + n) * npix + pix) * kC + col0);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < NC / 8; ++j) {
         const uint4 u = r[j];
         v[8 * j + 0] += bf16_lo(u.x); v[8 * j + 1] += bf16_hi(u.x);
         v[8 * j + 2] += bf16_lo(u.y); v[8 * j + 3] += bf16_hi(u.y);
@@ -101,9 +116,9 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const savsr_c
     }
     if (g.res2_slot >= 0 && valid) {
       const float s = g.res2_scale;
-      const uint4* r = reinterpret_cast<const uint4*>(p.arena + ((static_cast<long>(g.res2_slot) * p.batch + n) * npix + pix) * kC);
+      const uint4* r = reinterpret_cast<const uint4*>(p.arena + ((static_cast<long>(g.res2_slot) * p.batch + n) * npix + pix) * kC + col0);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < NC / 8; ++j) {
         const uint4 u = r[j];
         v[8 * j + 0] += s * bf16_lo(u.x); v[8 * j + 1] += s * bf16_hi(u.x);
         v[8 * j + 2] += s * bf16_lo(u.y); v[8 * j + 3] += s * bf16_hi(u.y);
@@ -112,9 +127,9 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const savsr_c
       }
     }
     if (valid) {
-      uint4* d = reinterpret_cast<uint4*>(p.arena + ((static_cast<long>(g.dst_slot) * p.batch + n) * npix + pix) * kC);
+      uint4* d = reinterpret_cast<uint4*>(p.arena + ((static_cast<long>(g.dst_slot) * p.batch + n) * npix + pix) * kC + col0);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < NC / 8; ++j) {
         uint4 u;
         u.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
         u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
@@ -125,13 +140,13 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const savsr_c
     }
     if (g.pool != nullptr) {
       // Per-warp channel sums of the (pre-rounding) outputs over valid pixels, by a shuffle
-      // reduce-scatter: 62 shuffles leave channels (2*lane, 2*lane+1) in each lane.  Deterministic.
+      // reduce-scatter: 31 shuffles leave channel col0 + lane in each lane.  Deterministic.
       if (!valid) {
 #pragma unroll
-        for (int c = 0; c < BN; ++c) v[c] = 0.f;
+        for (int c = 0; c < NC; ++c) v[c] = 0.f;
       }
 #pragma unroll
-      for (int off = 16, cnt = 32; off >= 1; off >>= 1, cnt >>= 1) {
+      for (int off = 16, cnt = 16; off >= 1; off >>= 1, cnt >>= 1) {
         const bool upper = (lane & off) != 0;
 #pragma unroll
         for (int i = 0; i < cnt; ++i) {
@@ -141,8 +156,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const savsr_c
         }
       }
       const int npart = p.tiles_x * p.tiles_y * 4;
-      float2* dstp = reinterpret_cast<float2*>(g.pool + (static_cast<long>(n) * npart + tile * 4 + quad) * kC);
-      dstp[lane] = make_float2(v[0], v[1]);
+      g.pool[(static_cast<long>(n) * npart + tile * 4 + quad) * kC + col0 + lane] = v[0];
     }
   } else {
     if (p.dst_mode == SAVSR_DST_AUX16) {
@@ -174,35 +188,51 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const savsr_c
 }
 
 // ------------------------------------------------------------------------------------------------ tcgen05 kernel
-template <int BN>
+// Upper 32 bits of a K-major SWIZZLE_128B shared-memory matrix descriptor (version 1, base_offset 0).
+__device__ __forceinline__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t hi, uint32_t lo) { return (static_cast<uint64_t>(hi) << 32) | lo; }
+
+template <int BN, int KS, bool HALO>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+  constexpr int NT = KS * KS;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: the 128-byte swizzle pattern repeats every 1024 bytes of shared address.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kARegionBytes;
   constexpr int kBBytes = BN * 128;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kBStages * kBBytes);
-  uint64_t* a_full = bars;
-  uint64_t* a_empty = bars + kMaxAStages;
-  uint64_t* b_full = bars + 2 * kMaxAStages;
-  uint64_t* b_empty = b_full + kBStages;
-  uint64_t* t_full = b_empty + kBStages;
-  uint64_t* t_empty = t_full + 2;
+  constexpr int kAStage = HALO ? kHaloStageBytes : kTileM * 128;
+  constexpr int kAStages = HALO ? 3 : 4;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kARegionBytes;                       // kBBlocks resident blocks (last kRing double as ring)
+  uint8_t* smem_ring = smem_b + (kBBlocks - kRing) * kBBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kBBlocks * kBBytes);
+  uint64_t* a_full = bars;                     // [kMaxAStages]
+  uint64_t* a_empty = a_full + kMaxAStages;    // [kMaxAStages]
+  uint64_t* res_full = a_empty + kMaxAStages;  // [kBBlocks]
+  uint64_t* ring_full = res_full + kBBlocks;   // [kRing]
+  uint64_t* ring_empty = ring_full + kRing;    // [kRing]
+  uint64_t* res_free = ring_empty + kRing;     // [1]
+  uint64_t* t_full = res_free + 1;             // [2]
+  uint64_t* t_empty = t_full + 2;              // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles = p.tiles_x * p.tiles_y;
   const int total = p.ngroups * p.batch * tiles;
+  const int item_begin = blockIdx.x * p.chunk;
+  const int item_end = min(item_begin + p.chunk, total);
+  const int nsrc = p.nsrc;
+  const int n_res = p.n_res;
   constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+  constexpr int kEpiArrivals = BN == 64 ? 8 : 4;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tensormap(&p.tm_tile);
-    prefetch_tensormap(&p.tm_halo);
+    prefetch_tensormap(HALO ? &p.tm_halo : &p.tm_tile);
     for (int i = 0; i < kMaxAStages; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
-    for (int i = 0; i < kBStages; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 4); }
+    for (int i = 0; i < kBBlocks; ++i) mbar_init(res_full + i, 1);
+    for (int i = 0; i < kRing; ++i) { mbar_init(ring_full + i, 1); mbar_init(ring_empty + i, 1); }
+    mbar_init(res_free, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, kEpiArrivals); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
@@ -214,118 +244,175 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
   if (warp == 0) {
     // ================================ TMA producer (one thread) ================================
     if (lane == 0) {
-      int sa = 0, pa = 0, sb = 0, pb = 0;
-      const uint32_t halo_bytes = static_cast<uint32_t>(p.halo_pitch) * (kTileH + 2) * 128u;
-      for (int item = blockIdx.x; item < total; item += gridDim.x) {
-        const int tile = item % tiles;
-        const int gn = item / tiles;
+      int sa = 0, pa = 0, sr = 0, pr = 0;
+      int gen = -1, cur_key = -1;
+      const int nkb = nsrc * NT;
+      int tile = item_begin % tiles;
+      int gn = item_begin / tiles;
+      for (int item = item_begin; item < item_end; ++item) {
         const int n = gn % p.batch;
-        const savsr_conv_group& g = p.g[gn / p.batch];
-        const int x0 = (tile % p.tiles_x) * kTileW, y0 = (tile / p.tiles_x) * kTileH;
+        const int gi = gn / p.batch;
+        const savsr_conv_group& g = p.g[gi];
+        const int ty = tile / p.tiles_x;
+        const int x0 = (tile - ty * p.tiles_x) * kTileW, y0 = ty * kTileH;
         const uint8_t* wptr = static_cast<const uint8_t*>(g.weight) + static_cast<long>(n) * g.weight_sample_stride;
-        for (int s = 0; s < g.nsrc; ++s) {
-          const int img = g.src_slot[s] * p.batch + n;
-          if (p.halo) {
-            mbar_wait(a_empty + sa, pa ^ 1);
-            mbar_expect_tx(a_full + sa, halo_bytes);
-            tma_load_4d(smem_a + sa * p.a_stage_bytes, &p.tm_halo, a_full + sa, 0, x0 - 1, y0 - 1, img);
-            if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
-          }
-          for (int tap = 0; tap < p.ntaps; ++tap) {
-            if (!p.halo) {
-              const int dx = p.ntaps == 9 ? tap % 3 - 1 : 0;
-              const int dy = p.ntaps == 9 ? tap / 3 - 1 : 0;
-              mbar_wait(a_empty + sa, pa ^ 1);
-              mbar_expect_tx(a_full + sa, kTileM * 128u);
-              tma_load_4d(smem_a + sa * p.a_stage_bytes, &p.tm_tile, a_full + sa, 0, x0 + dx, y0 + dy, img);
-              if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+        const int key = gi * p.batch + (g.weight_sample_stride != 0 ? n : 0);
+        if (key != cur_key) {
+          // new weight set: wait until every MMA that reads the old resident blocks has retired
+          if (gen >= 0) mbar_wait(res_free, gen & 1);
+          ++gen;
+          cur_key = key;
+          // rotated issue order: concurrent CTAs pull different L2 lines of the shared weights
+          int kb = blockIdx.x % nkb;
+          for (int i = 0; i < nkb; ++i) {
+            if (kb < n_res) {
+              mbar_expect_tx(res_full + kb, kBBytes);
+              bulk_load(smem_b + kb * kBBytes, wptr + static_cast<long>(kb) * kBBytes, kBBytes, res_full + kb);
             }
-            mbar_wait(b_empty + sb, pb ^ 1);
-            mbar_expect_tx(b_full + sb, kBBytes);
-            bulk_load(smem_b + sb * kBBytes, wptr + static_cast<long>(s * p.ntaps + tap) * kBBytes, kBBytes, b_full + sb);
-            if (++sb == kBStages) { sb = 0; pb ^= 1; }
+            if (++kb == nkb) kb = 0;
           }
         }
+        for (int s = 0; s < nsrc; ++s) {
+          const int img = g.src_slot[s] * p.batch + n;
+          if constexpr (HALO) {
+            mbar_wait(a_empty + sa, pa ^ 1);
+            mbar_expect_tx(a_full + sa, kHaloPitch * (kTileH + 2) * 128u);
+            tma_load_4d(smem_a + sa * kAStage, &p.tm_halo, a_full + sa, 0, x0 - 1, y0 - 1, img);
+            if (++sa == kAStages) { sa = 0; pa ^= 1; }
+          }
+#pragma unroll
+          for (int tap = 0; tap < NT; ++tap) {
+            const int kb = s * NT + tap;
+            if constexpr (!HALO) {
+              const int dx = KS == 3 ? tap % 3 - 1 : 0;
+              const int dy = KS == 3 ? tap / 3 - 1 : 0;
+              mbar_wait(a_empty + sa, pa ^ 1);
+              mbar_expect_tx(a_full + sa, kTileM * 128u);
+              tma_load_4d(smem_a + sa * kAStage, &p.tm_tile, a_full + sa, 0, x0 + dx, y0 + dy, img);
+              if (++sa == kAStages) { sa = 0; pa ^= 1; }
+            }
+            if (kb >= n_res) {
+              mbar_wait(ring_empty + sr, pr ^ 1);
+              mbar_expect_tx(ring_full + sr, kBBytes);
+              bulk_load(smem_ring + sr * kBBytes, wptr + static_cast<long>(kb) * kBBytes, kBBytes, ring_full + sr);
+              if (++sr == kRing) { sr = 0; pr ^= 1; }
+            }
+          }
+        }
+        if (++tile == tiles) { tile = 0; ++gn; }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer (one thread) ================================
+    // This loop is the critical path of the kernel (one thread feeds the tensor core): everything that
+    // can be is a compile-time constant, and descriptors are built with 32-bit adds only.
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BN);
-      int sa = 0, pa = 0, sb = 0, pb = 0;
+      constexpr uint32_t a_hi = desc_hi(HALO ? kHaloPitch * 128u : 1024u);
+      constexpr uint32_t b_hi = desc_hi(1024u);
+      const uint32_t a_lo0 = (smem_u32(smem_a) >> 4) & 0x3fffu;
+      const uint32_t b_lo0 = (smem_u32(smem_b) >> 4) & 0x3fffu;
+      const uint32_t ring_lo0 = (smem_u32(smem_ring) >> 4) & 0x3fffu;
+      int sa = 0, pa = 0, sr = 0, pr = 0;
+      int gen = -1, cur_key = -1;
       int it = 0;
-      const uint32_t a_sbo = p.halo ? static_cast<uint32_t>(p.halo_pitch) * 128u : 1024u;
-      for (int item = blockIdx.x; item < total; item += gridDim.x, ++it) {
-        const int gn = item / tiles;
-        const savsr_conv_group& g = p.g[gn / p.batch];
+      int tile = item_begin % tiles;
+      int gn = item_begin / tiles;
+      for (int item = item_begin; item < item_end; ++item, ++it) {
+        const int n = gn % p.batch;
+        const int gi = gn / p.batch;
+        const int key = gi * p.batch + (p.g[gi].weight_sample_stride != 0 ? n : 0);
+        bool fresh = false;
+        if (key != cur_key) {
+          if (gen >= 0) umma_commit(res_free);  // fires when all MMAs of the previous weight set are done
+          ++gen;
+          cur_key = key;
+          fresh = true;
+        }
         const int acc = it & 1;
         mbar_wait(t_empty + acc, ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
         uint32_t accumulate = 0;
-        for (int s = 0; s < g.nsrc; ++s) {
-          if (p.halo) {
+        uint32_t b_lo = b_lo0;
+        int kb = 0;
+        for (int s = 0; s < nsrc; ++s) {
+          if constexpr (HALO) {
             mbar_wait(a_full + sa, pa);
             tc_fence_after();
           }
-          for (int tap = 0; tap < p.ntaps; ++tap) {
-            if (!p.halo) mbar_wait(a_full + sa, pa);
-            mbar_wait(b_full + sb, pb);
-            tc_fence_after();
-            uint32_t a_addr = smem_u32(smem_a + sa * p.a_stage_bytes);
-            if (p.halo) {
-              const int dy = p.ntaps == 9 ? tap / 3 : 1, dx = p.ntaps == 9 ? tap % 3 : 1;
-              a_addr += static_cast<uint32_t>(dy * p.halo_pitch + dx) * 128u;
-            }
-            const uint32_t b_addr = smem_u32(smem_b + sb * kBBytes);
-            const uint32_t bo = p.use_base_offset ? ((a_addr >> 7) & 7u) : 0u;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {  // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzle atom
-              umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32, a_sbo, bo), umma_desc_sw128(b_addr + k * 32, 1024u, 0u),
-                        idesc, accumulate);
+          for (int tap = 0; tap < NT; ++tap, ++kb, b_lo += kBBytes >> 4) {
+            if constexpr (!HALO) {
+              mbar_wait(a_full + sa, pa);
+              tc_fence_after();
+            }
+            uint32_t bl = b_lo;
+            const bool streamed = kb >= n_res;
+            if (streamed) {
+              mbar_wait(ring_full + sr, pr);
+              tc_fence_after();
+              bl = ring_lo0 + sr * (kBBytes >> 4);
+            } else if (fresh) {
+              mbar_wait(res_full + kb, gen & 1);
+              tc_fence_after();
+            }
+            // halo: tap (dy, dx) starts (dy * pitch + dx) pixel rows (128 B = 8 descriptor units) into the tile
+            const uint32_t al = a_lo0 + sa * (kAStage >> 4) + (HALO ? ((tap / 3) * kHaloPitch + tap % 3) * 8 : 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // 4 x (K = 16 bf16 = 32 bytes = 2 units) inside the 128-byte swizzle atom
+              umma_bf16(d_tmem, make_desc(a_hi, al + 2 * k), make_desc(b_hi, bl + 2 * k), idesc, accumulate);
               accumulate = 1;
             }
-            umma_commit(b_empty + sb);
-            if (++sb == kBStages) { sb = 0; pb ^= 1; }
-            if (!p.halo) {
+            if (streamed) {
+              umma_commit(ring_empty + sr);
+              if (++sr == kRing) { sr = 0; pr ^= 1; }
+            }
+            if constexpr (!HALO) {
               umma_commit(a_empty + sa);
-              if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+              if (++sa == kAStages) { sa = 0; pa ^= 1; }
             }
           }
-          if (p.halo) {
+          if constexpr (HALO) {
             umma_commit(a_empty + sa);
-            if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+            if (++sa == kAStages) { sa = 0; pa ^= 1; }
           }
         }
         umma_commit(t_full + acc);
+        if (++tile == tiles) { tile = 0; ++gn; }
       }
     }
   } else {
     // ================================ epilogue warps ================================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-    int it = 0;
-    for (int item = blockIdx.x; item < total; item += gridDim.x, ++it) {
-      const int tile = item % tiles;
-      const int gn = item / tiles;
-      const int n = gn % p.batch;
-      const savsr_conv_group& g = p.g[gn / p.batch];
-      const int acc = it & 1;
-      mbar_wait(t_full + acc, (it >> 1) & 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
-      float v[BN];
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may access (warp id % 4)
+    const int half = (warp - 2) >> 2;   // which 32-column half of the accumulator (N = 64 only)
+    if (BN == 64 || half == 0) {
+      constexpr int NC = BN == 64 ? 32 : 16;
+      int it = 0;
+      int tile = item_begin % tiles;
+      int gn = item_begin / tiles;
+      for (int item = item_begin; item < item_end; ++item, ++it) {
+        const int n = gn % p.batch;
+        const savsr_conv_group& g = p.g[gn / p.batch];
+        const int acc = it & 1;
+        mbar_wait(t_full + acc, (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN + half * 32);
+        float v[NC];
 #pragma unroll
-      for (int j = 0; j < BN / 16; ++j) {
-        uint32_t r[16];
-        tmem_ld16(taddr + j * 16, r);
-        tmem_ld_wait();
+        for (int j = 0; j < NC / 16; ++j) {
+          uint32_t r[16];
+          tmem_ld16(taddr + j * 16, r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 16; ++c) v[j * 16 + c] = __uint_as_float(r[c]);
+          for (int c = 0; c < 16; ++c) v[j * 16 + c] = __uint_as_float(r[c]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t_empty + acc);
+        conv_epilogue<NC>(p, g, n, tile, quad, lane, v, half * 32);
+        if (++tile == tiles) { tile = 0; ++gn; }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(t_empty + acc);
-      conv_epilogue<BN>(p, g, n, tile, quad, lane, v);
     }
   }
 
@@ -353,27 +440,31 @@ __global__ void __launch_bounds__(128) conv_check_kernel(const __grid_constant__
   const int py = (tile / p.tiles_x) * kTileH + (m >> 3);
   const long npix = static_cast<long>(p.height) * p.width;
   const uint8_t* wptr = static_cast<const uint8_t*>(g.weight) + static_cast<long>(n) * g.weight_sample_stride;
-  float v[BN];
+  constexpr int NC = BN == 64 ? 32 : 16;
+  for (int col0 = 0; col0 < BN; col0 += NC) {
+    float v[NC];
 #pragma unroll
-  for (int c = 0; c < BN; ++c) v[c] = 0.f;
-  for (int s = 0; s < g.nsrc; ++s) {
-    const __nv_bfloat16* src = p.arena + (static_cast<long>(g.src_slot[s]) * p.batch + n) * npix * kC;
-    for (int tap = 0; tap < p.ntaps; ++tap) {
-      const int dx = p.ntaps == 9 ? tap % 3 - 1 : 0, dy = p.ntaps == 9 ? tap / 3 - 1 : 0;
-      const int sx = px + dx, sy = py + dy;
-      const bool in = sx >= 0 && sx < p.width && sy >= 0 && sy < p.height;
-      const uint8_t* wb = wptr + static_cast<long>(s * p.ntaps + tap) * (BN * 128);
-      for (int k = 0; k < 64; ++k) {
-        const float a = in ? __bfloat162float(src[(static_cast<long>(sy) * p.width + sx) * kC + k]) : 0.f;
+    for (int c = 0; c < NC; ++c) v[c] = 0.f;
+    for (int s = 0; s < g.nsrc; ++s) {
+      const __nv_bfloat16* src = p.arena + (static_cast<long>(g.src_slot[s]) * p.batch + n) * npix * kC;
+      for (int tap = 0; tap < p.ntaps; ++tap) {
+        const int dx = p.ntaps == 9 ? tap % 3 - 1 : 0, dy = p.ntaps == 9 ? tap / 3 - 1 : 0;
+        const int sx = px + dx, sy = py + dy;
+        const bool in = sx >= 0 && sx < p.width && sy >= 0 && sy < p.height;
+        const uint8_t* wb = wptr + static_cast<long>(s * p.ntaps + tap) * (BN * 128);
+        for (int k = 0; k < 64; ++k) {
+          const float a = in ? __bfloat162float(src[(static_cast<long>(sy) * p.width + sx) * kC + k]) : 0.f;
 #pragma unroll
-        for (int c = 0; c < BN; ++c) {
-          const int off = c * 128 + (((k >> 3) ^ (c & 7)) << 4) + (k & 7) * 2;
-          v[c] += a * __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(wb + off));
+          for (int c = 0; c < NC; ++c) {
+            const int row = col0 + c;
+            const int off = row * 128 + (((k >> 3) ^ (row & 7)) << 4) + (k & 7) * 2;
+            v[c] += a * __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(wb + off));
+          }
         }
       }
     }
+    conv_epilogue<NC>(p, g, n, tile, m >> 5, m & 31, v, col0);
   }
-  conv_epilogue<BN>(p, g, n, tile, m >> 5, m & 31, v);
 }
 
 // ------------------------------------------------------------------------------------------------ weight packing
@@ -422,8 +513,24 @@ __global__ void arena_export_kernel(const __nv_bfloat16* __restrict__ src, float
   }
 }
 
+template <int BN, int KS, bool HALO>
+static int launch_igemm(savsr_ctx* ctx, ConvParams& p, int total, cudaStream_t st) {
+  const size_t smem = 1024 + kARegionBytes + kBBlocks * BN * 128 + 512;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SAVSR_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, KS, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_done = true;
+  }
+  // persistent CTAs over contiguous chunks of work items (weights stay resident within a chunk)
+  p.chunk = (total + ctx->sm_count - 1) / ctx->sm_count;
+  const int grid = (total + p.chunk - 1) / p.chunk;
+  conv_igemm_kernel<BN, KS, HALO><<<grid, kNumThreads, smem, st>>>(p);
+  SAVSR_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <int BN>
-static int launch_conv(savsr_ctx* ctx, const ConvParams& p, int impl, cudaStream_t st) {
+static int launch_conv(savsr_ctx* ctx, ConvParams& p, int impl, cudaStream_t st) {
   const int total = p.ngroups * p.batch * p.tiles_x * p.tiles_y;
   if (total == 0) return 0;
   if (impl == SAVSR_IMPL_CHECK) {
@@ -431,17 +538,9 @@ static int launch_conv(savsr_ctx* ctx, const ConvParams& p, int impl, cudaStream
     SAVSR_CUDA(cudaGetLastError());
     return 0;
   }
-  const size_t smem = 1024 + kARegionBytes + kBStages * BN * 128 + 512;
-  static bool attr_done[2] = {false, false};
-  const int ai = BN == 64 ? 0 : 1;
-  if (!attr_done[ai]) {
-    SAVSR_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_done[ai] = true;
-  }
-  const int grid = total < ctx->sm_count ? total : ctx->sm_count;
-  conv_igemm_kernel<BN><<<grid, kNumThreads, smem, st>>>(p);
-  SAVSR_CUDA(cudaGetLastError());
-  return 0;
+  if (p.ntaps == 1) return launch_igemm<BN, 1, false>(ctx, p, total, st);
+  if (p.halo) return launch_igemm<BN, 3, true>(ctx, p, total, st);
+  return launch_igemm<BN, 3, false>(ctx, p, total, st);
 }
 
 }  // namespace savsr
@@ -507,6 +606,7 @@ extern "C" int savsr_conv(savsr_ctx* ctx, savsr_arena* arena, const savsr_conv_g
     const savsr_conv_group& g = groups[i];
     SAVSR_REQUIRE(g.nsrc >= 1 && g.nsrc <= SAVSR_MAX_SRC, "savsr_conv: group %d nsrc %d out of range", i, g.nsrc);
     SAVSR_REQUIRE(g.weight != nullptr, "savsr_conv: group %d has no weights", i);
+    SAVSR_REQUIRE(g.nsrc == groups[0].nsrc, "savsr_conv: all groups of a launch must have the same nsrc (%d vs %d)", g.nsrc, groups[0].nsrc);
     for (int s = 0; s < g.nsrc; ++s) {
       SAVSR_REQUIRE(g.src_slot[s] >= 0 && g.src_slot[s] < arena->nslots, "savsr_conv: group %d source slot %d out of range", i, g.src_slot[s]);
       SAVSR_REQUIRE(dst_mode != SAVSR_DST_ARENA || g.src_slot[s] != g.dst_slot, "savsr_conv: group %d writes slot %d that it also convolves", i, g.dst_slot);
@@ -529,17 +629,9 @@ extern "C" int savsr_conv(savsr_ctx* ctx, savsr_arena* arena, const savsr_conv_g
   p.tiles_y = arena->tiles_y;
   p.ntaps = ksize * ksize;
   p.halo = (impl == SAVSR_IMPL_TCGEN05_HALO && ksize == 3) ? 1 : 0;
-  p.halo_pitch = ctx->halo_pitch;
-  p.use_base_offset = ctx->halo_base_offset;
-  if (p.halo) {
-    const int bytes = p.halo_pitch * (kTileH + 2) * 128;
-    p.a_stage_bytes = (bytes + 1023) / 1024 * 1024;
-    p.a_stages = kARegionBytes / p.a_stage_bytes;
-    if (p.a_stages > kMaxAStages) p.a_stages = kMaxAStages;
-  } else {
-    p.a_stage_bytes = kTileM * 128;
-    p.a_stages = kMaxAStages;
-  }
+  p.nsrc = groups[0].nsrc;
+  const int nkb = p.nsrc * p.ntaps;
+  p.n_res = nkb <= kBBlocks ? nkb : kBBlocks - kRing;
   p.dst_mode = dst_mode;
   if (n_tile == 64) return launch_conv<64>(ctx, p, impl, static_cast<cudaStream_t>(st));
   return launch_conv<16>(ctx, p, impl, static_cast<cudaStream_t>(st));

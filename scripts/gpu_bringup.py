@@ -23,11 +23,13 @@ CHECKS = {
     "conv_tap_k3_s5": "check_conv(impl=K.IMPL_TAP, ksize=3, nsrc=5, B=1, H=48, W=40)",
     "conv_tap_k1_s3": "check_conv(impl=K.IMPL_TAP, ksize=1, nsrc=3, B=2, H=37, W=45)",
     "conv_tap_big": "check_conv(impl=K.IMPL_TAP, ksize=3, nsrc=2, B=2, H=144, W=180)",
-    "conv_halo_p10_bo1": "check_conv(impl=K.IMPL_HALO, ksize=3, nsrc=2, B=2, H=37, W=45, halo=(10, 1))",
-    "conv_halo_p10_bo0": "check_conv(impl=K.IMPL_HALO, ksize=3, nsrc=2, B=2, H=37, W=45, halo=(10, 0))",
-    "conv_halo_p16_bo1": "check_conv(impl=K.IMPL_HALO, ksize=3, nsrc=2, B=2, H=37, W=45, halo=(16, 1))",
-    "conv_halo_p16_bo0": "check_conv(impl=K.IMPL_HALO, ksize=3, nsrc=2, B=2, H=37, W=45, halo=(16, 0))",
+    "conv_halo_s2_ragged": "check_conv(impl=K.IMPL_HALO, ksize=3, nsrc=2, B=2, H=37, W=45)",
+    "conv_halo_s3_big": "check_conv(impl=K.IMPL_HALO, ksize=3, nsrc=3, B=2, H=144, W=180)",
+    "conv_halo_s5": "check_conv(impl=K.IMPL_HALO, ksize=3, nsrc=5, B=1, H=48, W=40)",
     "conv_aux16": "check_conv_aux16()",
+    "conv_aux16_halo": "check_conv_aux16(impl=K.IMPL_HALO)",
+    "conv_rgb_halo": "check_conv_rgb(impl=K.IMPL_HALO)",
+    "conv_per_sample_halo": "check_osa_conv_per_sample(impl=K.IMPL_HALO)",
     "conv_rgb": "check_conv_rgb()",
     "conv_per_sample": "check_osa_conv_per_sample()",
     "front_conv": "check_front_conv()",

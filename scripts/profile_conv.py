@@ -1,0 +1,47 @@
+#!/usr/bin/env python
+"""One batched conv launch at the Vid4 shape for ncu / timing (bring-up aid).
+usage: profile_conv.py [nsrc] [ngroups] [batch] [impl] [ksize] [reps]"""
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import gpu_checks as G  # noqa: E402
+from gpu_checks import K  # noqa: E402
+
+
+def main():
+    a = sys.argv[1:]
+    nsrc = int(a[0]) if len(a) > 0 else 1
+    ng = int(a[1]) if len(a) > 1 else 6
+    B = int(a[2]) if len(a) > 2 else 4
+    impl = K.IMPL_NAMES[a[3]] if len(a) > 3 else K.IMPL_HALO
+    ks = int(a[4]) if len(a) > 4 else 3
+    reps = int(a[5]) if len(a) > 5 else 5
+    H, W = 144, 180
+    ab = G.ArenaBox(ng * (nsrc + 1), B, H, W)
+    ab.t.normal_()
+    groups, keep = [], []
+    for g in range(ng):
+        w = G.pack_weight(torch.randn(64, 64 * nsrc, ks, ks, device=G.DEV) * 0.05)
+        bias = torch.randn(64, device=G.DEV)
+        keep += [w, bias]
+        groups.append(G.group([g * (nsrc + 1) + i for i in range(nsrc)], g * (nsrc + 1) + nsrc, w, bias, act=K.ACT_LRELU))
+    for _ in range(2):
+        G.run_conv(ab, groups, ksize=ks, impl=impl)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    arr = (K.ConvGroup * len(groups))(*groups)
+    e0.record()
+    for _ in range(reps):
+        K.check(K.load().savsr_conv(G.ctx().handle, ab.a.handle, arr, len(groups), ks, 64, K.DST_ARENA, None, impl, G._stream()))
+    e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / reps
+    flop = 2.0 * ng * B * H * W * 64 * 64 * nsrc * ks * ks
+    print(f"nsrc={nsrc} groups={ng} B={B} impl={a[3] if len(a) > 3 else 'halo'} k={ks}: {us:.1f} us/launch, {flop / us / 1e6:.1f} TFLOP/s")
+
+
+if __name__ == "__main__":
+    main()

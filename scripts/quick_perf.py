@@ -31,11 +31,11 @@ def main():
                     plan.x_in.copy_(x)
                     t0 = time.time(); plan.run(); torch.cuda.synchronize(); eager_ms = (time.time() - t0) * 1e3
                     plan.capture()
-                    for _ in range(3):
+                    n = int(os.environ.get("QP_ITERS", "10"))
+                    for _ in range(int(os.environ.get("QP_WARMUP", "3"))):
                         plan.run_graph()
                     torch.cuda.synchronize()
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    n = 10
                     e0.record()
                     for _ in range(n):
                         plan.run_graph()

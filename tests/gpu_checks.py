@@ -116,11 +116,9 @@ def assert_close(name, got, ref, rel=2.0 ** -7, abs_=2e-3):
 
 
 # ------------------------------------------------------------------------------------------------ convolution
-def check_conv(impl=K.IMPL_TAP, ksize=3, nsrc=1, B=1, H=32, W=24, halo=None, full_epilogue=True, seed=0):
+def check_conv(impl=K.IMPL_TAP, ksize=3, nsrc=1, B=1, H=32, W=24, full_epilogue=True, seed=0):
     """savsr_conv (N = 64) vs F.conv2d on the same bf16-rounded operands, with the whole epilogue menu."""
     torch.manual_seed(seed)
-    if halo is not None:
-        ctx().set_halo(*halo)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     ngroups = 2
