@@ -95,6 +95,7 @@ class Plan:
         self.P = params
         self._keep: List[object] = []   # tensors / ctypes arrays referenced by raw pointers
         self.ops: List[Callable[[int], int]] = []
+        self.op_meta: List[Tuple[str, float, int]] = []   # (kind, algorithmic FLOPs, kernel launches) per op
         self.n_launches = 0
         self.taps = set(taps or ())
         self.tap_bufs: Dict[str, torch.Tensor] = {}
@@ -144,8 +145,9 @@ class Plan:
         return out.data_ptr()
 
     # ------------------------------------------------------------------ op emitters
-    def _emit(self, fn: Callable[[int], int], launches: int = 1) -> None:
+    def _emit(self, fn: Callable[[int], int], launches: int = 1, kind: str = "other", flops: float = 0.0) -> None:
         self.ops.append(fn)
+        self.op_meta.append((kind, flops, launches))
         self.n_launches += launches
 
     def _group(self, src: Sequence[int], dst: int, weight: int, bias: int = 0, act: int = K.ACT_NONE, slope: float = 0.2,
@@ -167,7 +169,10 @@ class Plan:
         self._keep.append(arr)
         skip_ref = C.byref(skip) if skip is not None else None
         lib, ctx, ah, n, impl = self.lib, self.ctx.handle, arena.handle, len(groups), self.impl
-        self._emit(lambda st: lib.savsr_conv(ctx, ah, arr, n, ksize, n_tile, dst_mode, skip_ref, impl, st))
+        co = 64 if n_tile == 64 else (3 if dst_mode == K.DST_RGB else 16)      # real output channels
+        flops = 2.0 * self.B * arena.height * arena.width * co * ksize * ksize * sum(64 * g.nsrc for g in groups)
+        self._emit(lambda st: lib.savsr_conv(ctx, ah, arr, n, ksize, n_tile, dst_mode, skip_ref, impl, st),
+                   kind=f"conv{ksize}x{ksize}_n{n_tile}", flops=flops)
 
     def _tap(self, name: str, arena: str, slot: int) -> None:
         """Test/debug hook: if `name` was requested in `taps`, snapshot the slot (fp32 NCHW) right here in the
@@ -178,7 +183,7 @@ class Plan:
         buf = self._buf(self.B, 64, a.height, a.width)
         self.tap_bufs[name] = buf
         lib, ah, ptr = self.lib, a.handle, buf.data_ptr()
-        self._emit(lambda st: lib.savsr_arena_export(ah, slot, ptr, st))
+        self._emit(lambda st: lib.savsr_arena_export(ah, slot, ptr, st), kind="debug_tap")
 
     def _osa_params(self, prefix: str, nsrc: int, pools: Sequence[int]) -> Tuple[K.OsaParams, int, int]:
         if prefix in self._osa_cache:
@@ -215,7 +220,7 @@ class Plan:
         inv_w = float(np.float32(1.0) / np.float32(self.scale[1]))
         lib, ctx, n, B = self.lib, self.ctx.handle, len(convs), self.B
         npart, npix = self.lr.tiles * 4, self.hp * self.wp
-        self._emit(lambda st: lib.savsr_osa_prologue(ctx, arr, n, B, npart, npix, inv_h, inv_w, st), launches=5)
+        self._emit(lambda st: lib.savsr_osa_prologue(ctx, arr, n, B, npart, npix, inv_h, inv_w, st), launches=5, kind="osa_prologue")
 
     def _pool(self, key: str) -> int:
         """Partial-sum buffer [B][tiles*4][64] written by a conv epilogue (cached per producing conv)."""
@@ -297,7 +302,8 @@ class Plan:
             farr = (K.FrontGroup * len(fg))(*fg)
             self._keep.append(farr)
             lrh, hh, ww, nfg = lr.handle, self.h, self.w, len(fg)
-            self._emit(lambda st, farr=farr, nfg=nfg: lib.savsr_front_conv(ctx, lrh, xin, t, hh, ww, farr, nfg, st))
+            self._emit(lambda st, farr=farr, nfg=nfg: lib.savsr_front_conv(ctx, lrh, xin, t, hh, ww, farr, nfg, st), kind="front_conv",
+                       flops=2.0 * B * self.hp * self.wp * 64 * 9 * 18)
             cur = [[S0[d][0], S0[d][1], hpast[d]] for d in range(2)]
             sets = [S1, S2]
             for j in range(4):
@@ -354,7 +360,7 @@ class Plan:
                 w1, b1 = self._ptr(pr + ".3.attention.1.weight"), self._ptr(pr + ".3.attention.1.bias")
                 w2, b2 = self._ptr(pr + ".3.attention.3.weight"), self._ptr(pr + ".3.attention.3.bias")
                 self._emit(lambda st, x=x, xa=xa, pl=pl, w1=w1, b1=b1, w2=w2, b2=b2:
-                           lib.savsr_ca_scale_residual(ctx, lrh, T2, x, xa, pl, npart, w1, b1, w2, b2, st))
+                           lib.savsr_ca_scale_residual(ctx, lrh, T2, x, xa, pl, npart, w1, b1, w2, b2, st), kind="ca_scale_residual")
                 x, xa, xb = xa, xb, xa
             plr = self._pool(f"RG.{gi}.conv")
             self._conv(lr, [self._group([x], R, self._packp(f"RG.{gi}.conv.weight"), self._ptr(f"RG.{gi}.conv.bias"),
@@ -377,7 +383,7 @@ class Plan:
                        n_tile=16, dst_mode=K.DST_AUX16)
             args = (ctx, in16.data_ptr(), B, self.hp, self.wp, self._dev(wa), self._dev(ba), self._dev(wb), self._dev(bb),
                     self._dev(wc), self._dev(bc), half0.data_ptr(), half1.data_ptr(), maskb.data_ptr())
-            self._emit(lambda st, args=args: lib.savsr_osadapt_mask(*args, st), launches=3)
+            self._emit(lambda st, args=args: lib.savsr_osadapt_mask(*args, st), launches=3, kind="osadapt_mask")
             osa = self._osa_params(pa + ".adapt", 1, [plr])
             self._osa_prologue([osa[0]])
             self._conv(lr, [self._group([R], Hs, osa[1], wstride=osa[2], mask=maskb.data_ptr(), res1=R, res2=A, res2_scale=gamma)])
@@ -396,7 +402,7 @@ class Plan:
         self._conv(lr, [self._group([A], kslot0 + tp, wkp + tp * 8192, bkp + tp * 256, act=L, slope=0.1) for tp in range(25)], ksize=1)
         STA, = take(1)
         lrh, hrh, hh, ww = lr.handle, hr.handle, self.h, self.w
-        self._emit(lambda st: lib.savsr_satu_sta(ctx, lrh, TR, kslot0, STA, hh, ww, st))
+        self._emit(lambda st: lib.savsr_satu_sta(ctx, lrh, TR, kslot0, STA, hh, ww, st), kind="satu_sta")
         self._tap("satu_sta", "lr", STA)
         sw = K.SatuWeights()
         sw.body0_w, sw.body0_b = self._ptr(u + ".body.0.weight"), self._ptr(u + ".body.0.bias")
@@ -418,7 +424,7 @@ class Plan:
                                      self.base_y.data_ptr(), self.base_x.data_ptr(), self.corner_y.data_ptr(),
                                      self.corner_x.data_ptr(), self.table.data_ptr(), torch.cuda.current_stream().cuda_stream))
         tab, by, bx, swr = self.table.data_ptr(), self.base_y.data_ptr(), self.base_x.data_ptr(), C.byref(sw)
-        self._emit(lambda st: lib.savsr_satu_gather(ctx, lrh, TR, STA, hh, ww, hrh, 0, 1, tab, by, bx, swr, st))
+        self._emit(lambda st: lib.savsr_satu_gather(ctx, lrh, TR, STA, hh, ww, hrh, 0, 1, tab, by, bx, swr, st), kind="satu_gather")
         self._conv(hr, [self._group([0, 1], 2, self._packp(u + ".fusion.weight"), self._ptr(u + ".fusion.bias"))], ksize=1)
         self._tap("satu_out", "hr", 2)
         skip = K.RgbSkip(); skip.x = xin; skip.t = t; skip.centre = t // 2; skip.h = self.h; skip.w = self.w
@@ -436,6 +442,27 @@ class Plan:
             rc = op(st)
             if rc:
                 K.check(rc)
+
+    def run_profiled(self) -> Dict[str, Dict[str, float]]:
+        """Eager run with a CUDA-event pair around every op on the launching stream.
+        Returns {kind: {"ms": total device ms, "flops": algorithmic FLOPs, "ops": count, "launches": kernels}}."""
+        stream = torch.cuda.current_stream()
+        st = stream.cuda_stream
+        evs = []
+        for op in self.ops:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            rc = op(st)
+            e1.record(stream)
+            if rc:
+                K.check(rc)
+            evs.append((e0, e1))
+        stream.synchronize()
+        out: Dict[str, Dict[str, float]] = {}
+        for (kind, flops, launches), (e0, e1) in zip(self.op_meta, evs):
+            d = out.setdefault(kind, dict(ms=0.0, flops=0.0, ops=0, launches=0))
+            d["ms"] += e0.elapsed_time(e1); d["flops"] += flops; d["ops"] += 1; d["launches"] += launches
+        return out
 
     def capture(self) -> None:
         """Capture run() into a CUDA graph (after one eager warm-up that sets kernel attributes)."""

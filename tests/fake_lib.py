@@ -72,7 +72,7 @@ class CpuPlan(engine.Plan):
         self.hp, self.wp = h + (h & 1), w + (w & 1)
         self.H, self.W = engine.get_hw(h, w, self.scale)
         self.P = params
-        self._keep, self.ops, self.n_launches = [], [], 0
+        self._keep, self.ops, self.op_meta, self.n_launches = [], [], [], 0
         self.taps, self.tap_bufs, self.graph = set(kw.get("taps", ())), {}, None
         self._pack_cache, self._pool_cache, self._osa_cache = {}, {}, {}
         with torch.no_grad():

@@ -1,0 +1,131 @@
+"""-m gpu: the whole SAVSR forward through the drop-in module (C ABI underneath) against the golden vectors of the
+reference, the CPU oracle, and size-independent properties at the BASELINE shapes."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if "fingerprint" not in p)
+
+# bf16-operand path (fp32 accumulate).  North-star tolerances: <= 0.05 dB PSNR delta on the bf16 path; the fp32 max-abs
+# bound of 1e-3 is reported, and asserted with the margin bf16 rounding of ~150 stacked layers needs.
+MAX_ABS_TOL = 4e-3
+STAGE_REL_TOL = 0.03
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gpu_checks
+    return gpu_checks
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+@pytest.mark.parametrize("impl", ["halo", "tap"])
+def test_forward_matches_reference_golden(G, path, impl):
+    from oracle.state_dict_fixture import make_input, make_state_dict
+    g = np.load(path)
+    b, h, w = int(g["b"]), int(g["h"]), int(g["w"])
+    scale = tuple(float(s) if float(s) != int(s) else int(s) for s in g["scale"])
+    y, taps, plan = G.run_forward(make_state_dict(int(g["sd_seed"])), make_input(b, h, w, int(g["in_seed"])), scale, impl=impl, taps=G.TAPS)
+    ref = torch.from_numpy(g["out"])
+    assert y.shape == ref.shape
+    assert float((y - ref).abs().max()) < MAX_ABS_TOL
+    for key in ("f2p_last", "p2f_last", "align", "rg0", "rg3", "satu_out"):
+        t = taps[key][..., :h, :w] if key != "satu_out" else taps[key]
+        t = t.contiguous().flatten()
+        idx = torch.linspace(0, t.numel() - 1, steps=min(257, t.numel())).long()
+        if tuple(g[f"probe.{key}.shape"]) != tuple((taps[key][..., :h, :w] if key != "satu_out" else taps[key]).shape):
+            continue                          # padded sizes: the golden probe was taken on the padded map
+        samp = torch.from_numpy(g[f"probe.{key}.sample"])
+        assert float((t[idx] - samp).abs().max()) < STAGE_REL_TOL * float(g[f"probe.{key}.absmax"]), key
+
+
+@pytest.mark.parametrize("kw", [dict(b=1, h=16, w=20, scale=(2, 2)), dict(b=2, h=13, w=15, scale=(1.5, 4), sd_seed=1, in_seed=1236),
+                                dict(b=1, h=31, w=31, scale=(3, 3), sd_seed=2), dict(b=3, h=20, w=36, scale=(2.7, 2.7), sd_seed=1),
+                                dict(b=1, h=8, w=8, scale=(4, 4)), dict(b=1, h=2, w=3, scale=(1.1, 1.1))])
+def test_forward_vs_oracle_with_stage_errors(G, kw):
+    info = G.check_forward(impl="halo", tol=MAX_ABS_TOL, stage_tol=STAGE_REL_TOL, **kw)
+    assert info["psnr_vs_oracle"] > 55.0
+
+
+def test_psnr_delta_gate_bf16_path(G):
+    """North-star gate: PSNR_Y(oracle, GT) - PSNR_Y(ours, GT) <= 0.05 dB (reference metric chain)."""
+    import torch.nn.functional as F
+    from oracle import savsr_oracle as O
+    from oracle.state_dict_fixture import make_state_dict
+    torch.manual_seed(3)
+    scale, h, w = (4, 4), 24, 32
+    gt = torch.rand(9, 3, 6, 8)
+    gt = F.interpolate(gt, size=(h * 4, w * 4), mode="bicubic", align_corners=False).clamp(0, 1)       # smooth synthetic HR clip
+    lr = F.interpolate(gt, size=(h, w), mode="bicubic", align_corners=False, antialias=True).clamp(0, 1)
+    from savsr_b200 import sharding
+    sd = make_state_dict(0)
+    frames = [3, 4, 5]
+    win = sharding.gather_windows(lr, frames)
+    y_ref = O.forward(sd, win, scale)
+    y, _, _ = G.run_forward(sd, win, scale, impl="halo")
+    p_ref = O.psnr_y(y_ref, gt[frames]); p_new = O.psnr_y(y, gt[frames])
+    assert abs(p_ref - p_new) <= 0.05, (p_ref, p_new)
+    assert O.psnr_y(y, y_ref) > 55.0
+
+
+def test_determinism_graph_and_batch_invariance(G):
+    """Size-independent properties: run-to-run bit-exact, CUDA graph == eager, batched == per-sample."""
+    from oracle.state_dict_fixture import make_input, make_state_dict
+    sd = make_state_dict(1)
+    x = make_input(3, 22, 26, 77)
+    y1, _, _ = G.run_forward(sd, x, (2.7, 2.7), impl="halo", graph=False)
+    y2, _, _ = G.run_forward(sd, x, (2.7, 2.7), impl="halo", graph=True)
+    y3, _, _ = G.run_forward(sd, x, (2.7, 2.7), impl="halo", graph=True)
+    assert torch.equal(y1, y2) and torch.equal(y2, y3)
+    singles = torch.cat([G.run_forward(sd, x[i:i + 1], (2.7, 2.7), impl="halo")[0] for i in range(3)])
+    assert torch.equal(singles, y1)            # eval-mode windows are independent: batching is numerically free
+    yt, _, _ = G.run_forward(sd, x, (2.7, 2.7), impl="tap")
+    assert float((yt - y1).abs().max()) < 1e-5  # the two A-fetch modes feed identical operands to the tensor core
+
+
+@pytest.mark.parametrize("scale", [(4, 4), (1.5, 4), (2.7, 2.7)])
+def test_vid4_shape_against_cuda_oracle(G, scale):
+    """BASELINE configs 2-3 at full size (144x180): the oracle runs on the GPU here only as the checker (TF32 off)."""
+    from oracle import savsr_oracle as O
+    from oracle.state_dict_fixture import make_input, make_state_dict
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sd = make_state_dict(0)
+    x = make_input(1, 144, 180, 1234)
+    y, _, plan = G.run_forward(sd, x, scale, impl="halo", graph=True)
+    dsd = {k: v.cuda() for k, v in sd.items()}
+    torch.set_default_device("cuda")
+    try:
+        with torch.no_grad():
+            y_ref = O.forward(dsd, x.cuda(), scale).cpu()
+    finally:
+        torch.set_default_device("cpu")
+    assert tuple(y.shape) == (1, 3) + O.get_hw(144, 180, scale)
+    assert float((y - y_ref).abs().max()) < MAX_ABS_TOL
+    assert O.psnr_y(y, y_ref) > 55.0
+    # bit-exact sampling indices at this shape (north star): cell / corner / R vectors vs the numpy oracle
+    H, W = O.get_hw(144, 180, scale)
+    assert np.array_equal(plan.cell_y.cpu().numpy(), O.satu_cell(H, scale[0]))
+    assert np.array_equal(plan.cell_x.cpu().numpy(), O.satu_cell(W, scale[1]))
+    assert np.array_equal(plan.corner_y.cpu().numpy(), O.satu_base_corner(H, 144, scale[0]))
+    assert np.array_equal(plan.corner_x.cpu().numpy(), O.satu_base_corner(W, 180, scale[1]))
+    assert np.array_equal(plan.rel_y.cpu().numpy().view(np.uint32), O.satu_rel_coord(H, scale[0]).view(np.uint32))
+    assert np.array_equal(plan.rel_x.cpu().numpy().view(np.uint32), O.satu_rel_coord(W, scale[1]).view(np.uint32))
+
+
+def test_module_api_errors(G):
+    import savsr_b200
+    net = savsr_b200.SAVSR().cuda()
+    with pytest.raises(NotImplementedError):
+        net(torch.zeros(1, 7, 3, 8, 8, device="cuda"))          # train mode: not part of the inference hot path
+    net.eval()
+    with pytest.raises(ValueError):
+        net(torch.zeros(1, 7, 3, 1, 8, device="cuda"))
+    net.set_scale(2)
+    y = net(torch.rand(1, 7, 3, 8, 10, device="cuda"))
+    assert tuple(y.shape) == (1, 3, 16, 20) and y.dtype == torch.float32

@@ -1,0 +1,66 @@
+"""CPU: frame sharding across ranks (world_size 2, gloo) and the window gather, against single-process results."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from savsr_b200 import sharding
+
+
+def fake_net(x):
+    """Stand-in for the SR network: deterministic function of the 7-frame window -> [b, 3, 2h, 2w]."""
+    b, t, c, h, w = x.shape
+    wts = torch.arange(1, t + 1, dtype=x.dtype).view(1, t, 1, 1, 1)
+    y = (x * wts).sum(1)
+    return torch.nn.functional.interpolate(y, scale_factor=2, mode="nearest")
+
+
+def test_reflection_window_indices():
+    assert sharding.frame_window_indices(0, 34) == [3, 2, 1, 0, 1, 2, 3]          # data_util.py:63-112 'reflection'
+    assert sharding.frame_window_indices(33, 34) == [30, 31, 32, 33, 32, 31, 30]
+    assert sharding.frame_window_indices(10, 34) == [7, 8, 9, 10, 11, 12, 13]
+    assert sharding.frame_window_indices(0, 5, 5) == [2, 1, 0, 1, 2]
+
+
+def test_shard_frames_partition():
+    for n, world in ((34, 1), (34, 2), (34, 8), (5, 2), (3, 8), (0, 2)):
+        for contiguous in (False, True):
+            parts = [sharding.shard_frames(n, r, world, contiguous) for r in range(world)]
+            assert sorted(f for p in parts for f in p) == list(range(n))
+    assert sharding.shard_frames(34, 1, 8) == [1, 9, 17, 25, 33]                 # video_base_model.py:50 rank-strided loop
+    with pytest.raises(ValueError):
+        sharding.shard_frames(10, 2, 2)
+
+
+def test_infer_clip_ragged_batches():
+    clip = torch.rand(11, 3, 6, 8)
+    full = sharding.infer_clip(fake_net, clip, batch=11)
+    for b in (1, 4, 5):
+        assert torch.equal(sharding.infer_clip(fake_net, clip, batch=b), full)
+    assert sharding.infer_clip(fake_net, clip, frames=[], batch=4).numel() == 0
+
+
+def _worker(rank, world, port, n_frames, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        clip = torch.rand(n_frames, 3, 6, 8, generator=torch.Generator().manual_seed(7))
+        mine = sharding.shard_frames(n_frames, rank, world)
+        local = sharding.infer_clip(fake_net, clip, frames=mine, batch=2)
+        full = sharding.gather_outputs(local, mine, n_frames)
+        ref = sharding.infer_clip(fake_net, clip, batch=3)
+        ret[rank] = bool(torch.equal(full, ref)) and len(mine) == len(range(rank, n_frames, world))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_frames", [5, 8])
+def test_two_rank_frame_sharding_and_gather(n_frames):
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + (os.getpid() % 2000) + n_frames
+    mp.spawn(_worker, args=(world, port, n_frames, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
