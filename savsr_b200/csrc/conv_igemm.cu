@@ -51,6 +51,8 @@ struct ConvParams {
   int halo;             // A fetch mode
   int n_res;            // K-blocks held resident; the remaining nsrc*ntaps - n_res go through the ring
   int chunk;            // consecutive work items per CTA
+  uint32_t per_sample_mask;  // bit g set: conv g has per-sample weights (OSA-Conv)
+  long long* dbg;            // optional [grid][8] cycle counters (bring-up aid), nullptr in production
   int dst_mode;
 };
 
@@ -70,64 +72,119 @@ __device__ __forceinline__ void bilinear_src(int dst, int in_size, int out_size,
   l1 = src - static_cast<float>(i0);
 }
 
-// Epilogue shared by the tensor-core kernel and the checker.  `v` holds NC consecutive accumulator
-// columns (output channels col0 .. col0+NC) of pixel m = quad * 32 + lane of the tile.
+// Epilogue shared by the tensor-core kernel and the checker, in two phases so that every global load that does
+// not depend on the accumulator (bias, residuals, mask, bilinear skip) is issued BEFORE waiting for the MMAs of the
+// tile and its latency hides behind them.  `v` holds NC consecutive accumulator columns (output channels
+// col0 .. col0+NC) of pixel m = quad * 32 + lane of the tile.
 // NC = 32: bf16 arena destination (two warps per quadrant); NC = 16: AUX16 / RGB destinations.
 template <int NC>
-__device__ __forceinline__ void conv_epilogue(const ConvParams& p, const savsr_conv_group& g, int n, int tile,
-                                              int quad, int lane, float (&v)[NC], int col0) {
+struct EpiCtx {
+  float bias[NC];      // reloaded only when the conv (group) changes
+  uint4 r1[NC / 8], r2[NC / 8];
+  float mk;
+  float skip[3];
+  long pix;
+  bool valid;
+  int bias_group;
+  // per-conv constants hoisted out of the per-element code (reloaded only when the conv changes)
+  float neg_slope;     // activation as max(v,0) + neg_slope * min(v,0): 1 = none, 0 = ReLU, s = LeakyReLU(s)
+  float res2_scale;
+  int res1_slot, res2_slot, dst_slot;
+  bool has_mask;
+  float* pool;
+};
+
+template <int NC>
+__device__ __forceinline__ void epi_prefetch(const ConvParams& p, const savsr_conv_group& g, int gi, int n, int tile, int quad,
+                                             int lane, int col0, EpiCtx<NC>& c) {
   const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
   const int m = quad * 32 + lane;
   const int px = tx * kTileW + (m & (kTileW - 1));
   const int py = ty * kTileH + (m >> 3);
-  const bool valid = (px < p.width) && (py < p.height);
+  c.valid = (px < p.width) && (py < p.height);
   const long npix = static_cast<long>(p.height) * p.width;
-  const long pix = static_cast<long>(py) * p.width + px;
-
-  if (g.bias != nullptr) {
-    const float4* b4 = reinterpret_cast<const float4*>(g.bias + col0);
+  c.pix = static_cast<long>(py) * p.width + px;
+  if (gi != c.bias_group) {
+    c.bias_group = gi;
+    c.neg_slope = g.act == SAVSR_ACT_NONE ? 1.f : (g.act == SAVSR_ACT_RELU ? 0.f : g.slope);
+    c.res2_scale = g.res2_scale;
+    c.res1_slot = g.res1_slot; c.res2_slot = g.res2_slot; c.dst_slot = g.dst_slot;
+    c.has_mask = g.mask != nullptr;
+    c.pool = g.pool;
+    if (g.bias != nullptr) {
+      const float4* b4 = reinterpret_cast<const float4*>(g.bias + col0);
 #pragma unroll
-    for (int c = 0; c < NC / 4; ++c) {
-      const float4 b = __ldg(b4 + c);
-      v[4 * c + 0] += b.x; v[4 * c + 1] += b.y; v[4 * c + 2] += b.z; v[4 * c + 3] += b.w;
+      for (int j = 0; j < NC / 4; ++j) {
+        const float4 b = __ldg(b4 + j);
+        c.bias[4 * j + 0] = b.x; c.bias[4 * j + 1] = b.y; c.bias[4 * j + 2] = b.z; c.bias[4 * j + 3] = b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) c.bias[j] = 0.f;
     }
   }
-  if (g.act != SAVSR_ACT_NONE) {
-#pragma unroll
-    for (int c = 0; c < NC; ++c) v[c] = apply_act(v[c], g.act, g.slope);
-  }
-
   if constexpr (NC == 32) {
-    if (g.mask != nullptr) {
-      const float mk = valid ? __ldg(g.mask + n * npix + pix) : 0.f;
+    c.mk = (c.has_mask && c.valid) ? __ldg(g.mask + n * npix + c.pix) : 0.f;
+    if (c.res1_slot >= 0 && c.valid) {
+      const uint4* r = reinterpret_cast<const uint4*>(p.arena + ((static_cast<long>(c.res1_slot) * p.batch + n) * npix + c.pix) * kC + col0);
 #pragma unroll
-      for (int c = 0; c < NC; ++c) v[c] *= mk;
+      for (int j = 0; j < NC / 8; ++j) c.r1[j] = r[j];
     }
-    if (g.res1_slot >= 0 && valid) {
-      const uint4* r = reinterpret_cast<const uint4*>(p.arena + ((static_cast<long>(g.res1_slot) * p.batch + n) * npix + pix) * kC + col0);
+    if (c.res2_slot >= 0 && c.valid) {
+      const uint4* r = reinterpret_cast<const uint4*>(p.arena + ((static_cast<long>(c.res2_slot) * p.batch + n) * npix + c.pix) * kC + col0);
 #pragma unroll
-      for (int j = 0; j < NC / 8; ++j) {
-        const uint4 u = r[j];
-        v[8 * j + 0] += bf16_lo(u.x); v[8 * j + 1] += bf16_hi(u.x);
-        v[8 * j + 2] += bf16_lo(u.y); v[8 * j + 3] += bf16_hi(u.y);
-        v[8 * j + 4] += bf16_lo(u.z); v[8 * j + 5] += bf16_hi(u.z);
-        v[8 * j + 6] += bf16_lo(u.w); v[8 * j + 7] += bf16_hi(u.w);
+      for (int j = 0; j < NC / 8; ++j) c.r2[j] = r[j];
+    }
+  } else if (p.dst_mode == SAVSR_DST_RGB) {
+    if (c.valid) {  // bilinear skip of the LR centre frame (savsr_arch.py:739)
+      int y0, y1, x0, x1;
+      float ly, lx;
+      bilinear_src(py, p.skip.h, p.height, y0, y1, ly);
+      bilinear_src(px, p.skip.w, p.width, x0, x1, lx);
+      const long plane = static_cast<long>(p.skip.h) * p.skip.w;
+      const float* xc = p.skip.x + (static_cast<long>(n) * p.skip.t + p.skip.centre) * 3 * plane;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        const float* pl = xc + ch * plane;
+        const float a = __ldg(pl + y0 * p.skip.w + x0), b = __ldg(pl + y0 * p.skip.w + x1);
+        const float cc = __ldg(pl + y1 * p.skip.w + x0), d = __ldg(pl + y1 * p.skip.w + x1);
+        c.skip[ch] = (1.f - ly) * ((1.f - lx) * a + lx * b) + ly * ((1.f - lx) * cc + lx * d);
       }
     }
-    if (g.res2_slot >= 0 && valid) {
-      const float s = g.res2_scale;
-      const uint4* r = reinterpret_cast<const uint4*>(p.arena + ((static_cast<long>(g.res2_slot) * p.batch + n) * npix + pix) * kC + col0);
+  }
+}
+
+__device__ __forceinline__ void add_bf16x8(float* v, const uint4& u, float s) {
+  v[0] += s * bf16_lo(u.x); v[1] += s * bf16_hi(u.x); v[2] += s * bf16_lo(u.y); v[3] += s * bf16_hi(u.y);
+  v[4] += s * bf16_lo(u.z); v[5] += s * bf16_hi(u.z); v[6] += s * bf16_lo(u.w); v[7] += s * bf16_hi(u.w);
+}
+
+template <int NC>
+__device__ __forceinline__ void epi_finish(const ConvParams& p, const savsr_conv_group& g, int n, int tile, int quad, int lane,
+                                           float (&v)[NC], int col0, const EpiCtx<NC>& c) {
+  const long npix = static_cast<long>(p.height) * p.width;
+  const float ns = c.neg_slope;
 #pragma unroll
-      for (int j = 0; j < NC / 8; ++j) {
-        const uint4 u = r[j];
-        v[8 * j + 0] += s * bf16_lo(u.x); v[8 * j + 1] += s * bf16_hi(u.x);
-        v[8 * j + 2] += s * bf16_lo(u.y); v[8 * j + 3] += s * bf16_hi(u.y);
-        v[8 * j + 4] += s * bf16_lo(u.z); v[8 * j + 5] += s * bf16_hi(u.z);
-        v[8 * j + 6] += s * bf16_lo(u.w); v[8 * j + 7] += s * bf16_hi(u.w);
-      }
+  for (int j = 0; j < NC; ++j) {
+    const float t = v[j] + c.bias[j];
+    v[j] = fmaxf(t, 0.f) + ns * fminf(t, 0.f);   // none / ReLU / LeakyReLU without branches
+  }
+  if constexpr (NC == 32) {
+    if (c.has_mask) {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) v[j] *= c.mk;
     }
-    if (valid) {
-      uint4* d = reinterpret_cast<uint4*>(p.arena + ((static_cast<long>(g.dst_slot) * p.batch + n) * npix + pix) * kC + col0);
+    if (c.res1_slot >= 0 && c.valid) {
+#pragma unroll
+      for (int j = 0; j < NC / 8; ++j) add_bf16x8(v + 8 * j, c.r1[j], 1.f);
+    }
+    if (c.res2_slot >= 0 && c.valid) {
+      const float r2s = c.res2_scale;
+#pragma unroll
+      for (int j = 0; j < NC / 8; ++j) add_bf16x8(v + 8 * j, c.r2[j], r2s);
+    }
+    if (c.valid) {
+      uint4* d = reinterpret_cast<uint4*>(p.arena + ((static_cast<long>(c.dst_slot) * p.batch + n) * npix + c.pix) * kC + col0);
 #pragma unroll
       for (int j = 0; j < NC / 8; ++j) {
         uint4 u;
@@ -138,12 +195,12 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const savsr_c
         d[j] = u;
       }
     }
-    if (g.pool != nullptr) {
+    if (c.pool != nullptr) {
       // Per-warp channel sums of the (pre-rounding) outputs over valid pixels, by a shuffle
       // reduce-scatter: 31 shuffles leave channel col0 + lane in each lane.  Deterministic.
-      if (!valid) {
+      if (!c.valid) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) v[c] = 0.f;
+        for (int j = 0; j < NC; ++j) v[j] = 0.f;
       }
 #pragma unroll
       for (int off = 16, cnt = 16; off >= 1; off >>= 1, cnt >>= 1) {
@@ -156,33 +213,19 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const savsr_c
         }
       }
       const int npart = p.tiles_x * p.tiles_y * 4;
-      g.pool[(static_cast<long>(n) * npart + tile * 4 + quad) * kC + col0 + lane] = v[0];
+      c.pool[(static_cast<long>(n) * npart + tile * 4 + quad) * kC + col0 + lane] = v[0];
     }
   } else {
     if (p.dst_mode == SAVSR_DST_AUX16) {
-      if (valid) {
-        float4* d = reinterpret_cast<float4*>(static_cast<float*>(g.aux_dst) + (n * npix + pix) * 16);
+      if (c.valid) {
+        float4* d = reinterpret_cast<float4*>(static_cast<float*>(g.aux_dst) + (n * npix + c.pix) * 16);
 #pragma unroll
         for (int j = 0; j < 4; ++j) d[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
-    } else {  // SAVSR_DST_RGB: + bilinear skip of the LR centre frame, fp32 NCHW output
-      if (valid) {
-        int y0, y1, x0, x1;
-        float ly, lx;
-        bilinear_src(py, p.skip.h, p.height, y0, y1, ly);
-        bilinear_src(px, p.skip.w, p.width, x0, x1, lx);
-        const long plane = static_cast<long>(p.skip.h) * p.skip.w;
-        const float* xc = p.skip.x + (static_cast<long>(n) * p.skip.t + p.skip.centre) * 3 * plane;
-        float* out = static_cast<float*>(g.aux_dst) + static_cast<long>(n) * 3 * npix + pix;
+    } else if (c.valid) {  // SAVSR_DST_RGB: fp32 NCHW output
+      float* out = static_cast<float*>(g.aux_dst) + static_cast<long>(n) * 3 * npix + c.pix;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float* pl = xc + c * plane;
-          const float a = __ldg(pl + y0 * p.skip.w + x0), b = __ldg(pl + y0 * p.skip.w + x1);
-          const float cc = __ldg(pl + y1 * p.skip.w + x0), d = __ldg(pl + y1 * p.skip.w + x1);
-          const float sk = (1.f - ly) * ((1.f - lx) * a + lx * b) + ly * ((1.f - lx) * cc + lx * d);
-          out[c * npix] = v[c] + sk;
-        }
-      }
+      for (int ch = 0; ch < 3; ++ch) out[ch * npix] = v[ch] + c.skip[ch];
     }
   }
 }
@@ -246,6 +289,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
     if (lane == 0) {
       int sa = 0, pa = 0, sr = 0, pr = 0;
       int gen = -1, cur_key = -1;
+      long long dbg_ae = 0;
       const int nkb = nsrc * NT;
       int tile = item_begin % tiles;
       int gn = item_begin / tiles;
@@ -275,7 +319,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
         for (int s = 0; s < nsrc; ++s) {
           const int img = g.src_slot[s] * p.batch + n;
           if constexpr (HALO) {
+            const long long c0 = clock64();
             mbar_wait(a_empty + sa, pa ^ 1);
+            dbg_ae += clock64() - c0;
             mbar_expect_tx(a_full + sa, kHaloPitch * (kTileH + 2) * 128u);
             tma_load_4d(smem_a + sa * kAStage, &p.tm_halo, a_full + sa, 0, x0 - 1, y0 - 1, img);
             if (++sa == kAStages) { sa = 0; pa ^= 1; }
@@ -301,38 +347,72 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
         }
         if (++tile == tiles) { tile = 0; ++gn; }
       }
+      if (p.dbg != nullptr) p.dbg[blockIdx.x * 8 + 6] = dbg_ae;
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer (one thread) ================================
-    // This loop is the critical path of the kernel (one thread feeds the tensor core): everything that
-    // can be is a compile-time constant, and descriptors are built with 32-bit adds only.
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BN);
-      constexpr uint32_t a_hi = desc_hi(HALO ? kHaloPitch * 128u : 1024u);
-      constexpr uint32_t b_hi = desc_hi(1024u);
-      const uint32_t a_lo0 = (smem_u32(smem_a) >> 4) & 0x3fffu;
-      const uint32_t b_lo0 = (smem_u32(smem_b) >> 4) & 0x3fffu;
-      const uint32_t ring_lo0 = (smem_u32(smem_ring) >> 4) & 0x3fffu;
-      int sa = 0, pa = 0, sr = 0, pr = 0;
-      int gen = -1, cur_key = -1;
-      int it = 0;
-      int tile = item_begin % tiles;
-      int gn = item_begin / tiles;
-      for (int item = item_begin; item < item_end; ++item, ++it) {
-        const int n = gn % p.batch;
-        const int gi = gn / p.batch;
-        const int key = gi * p.batch + (p.g[gi].weight_sample_stride != 0 ? n : 0);
-        bool fresh = false;
-        if (key != cur_key) {
-          if (gen >= 0) umma_commit(res_free);  // fires when all MMAs of the previous weight set are done
-          ++gen;
-          cur_key = key;
-          fresh = true;
+    // ================================ MMA issuer ================================
+    // One elected thread feeds the tensor core, so this loop is the critical path of the kernel.  The whole warp
+    // runs it with warp-uniform control flow and values (so descriptors live in uniform registers and ptxas emits
+    // straight UTCHMMA sequences); only the tcgen05 instructions themselves sit under elect.sync.
+    constexpr uint32_t idesc = umma_idesc_bf16(BN);
+    constexpr uint32_t a_hi = desc_hi(HALO ? kHaloPitch * 128u : 1024u);
+    constexpr uint32_t b_hi = desc_hi(1024u);
+    const uint32_t a_lo0 = (smem_u32(smem_a) >> 4) & 0x3fffu;
+    const uint32_t b_lo0 = (smem_u32(smem_b) >> 4) & 0x3fffu;
+    const uint32_t ring_lo0 = (smem_u32(smem_ring) >> 4) & 0x3fffu;
+    const bool all_resident = nsrc * NT <= n_res;
+    int sa = 0, pa = 0, sr = 0, pr = 0;
+    int gen = -1, cur_key = -1;
+    int it = 0;
+    // (tile, n, gi) advance incrementally: no divisions or parameter loads on the per-tile critical path
+    int tile = item_begin % tiles;
+    int n = (item_begin / tiles) % p.batch;
+    int gi = (item_begin / tiles) / p.batch;
+    const uint32_t ps_mask = p.per_sample_mask;
+    const int batch = p.batch;
+    long long dbg_te = 0, dbg_af = 0, dbg_t0 = clock64();
+    for (int item = item_begin; item < item_end; ++item, ++it) {
+      const int key = gi * batch + (((ps_mask >> gi) & 1u) ? n : 0);
+      bool fresh = false;
+      if (key != cur_key) {
+        if (gen >= 0 && elect_one()) umma_commit(res_free);  // fires when all MMAs of the previous weight set are done
+        __syncwarp();
+        ++gen;
+        cur_key = key;
+        fresh = true;
+      }
+      const int acc = it & 1;
+      long long c0 = clock64();
+      mbar_wait(t_empty + acc, ((it >> 1) & 1) ^ 1);
+      dbg_te += clock64() - c0;
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+      if (HALO && all_resident && !fresh) {
+        // ---- fast path: weights resident and already landed; one wait + one elected region per source
+        uint32_t b_lo = b_lo0;
+        for (int s = 0; s < nsrc; ++s) {
+          c0 = clock64();
+          mbar_wait(a_full + sa, pa);
+          dbg_af += clock64() - c0;
+          tc_fence_after();
+          const uint32_t al0 = a_lo0 + sa * (kAStage >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int tap = 0; tap < NT; ++tap) {
+              const uint32_t al = al0 + ((tap / 3) * kHaloPitch + tap % 3) * 8;
+              const uint32_t bl = b_lo + tap * (kBBytes >> 4);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d_tmem, make_desc(a_hi, al + 2 * k), make_desc(b_hi, bl + 2 * k), idesc, (s | tap | k) ? 1u : 0u);
+            }
+            umma_commit(a_empty + sa);
+          }
+          __syncwarp();
+          b_lo += NT * (kBBytes >> 4);
+          if (++sa == kAStages) { sa = 0; pa ^= 1; }
         }
-        const int acc = it & 1;
-        mbar_wait(t_empty + acc, ((it >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+      } else {
+        // ---- general path: per-K-block waits (first tile of a weight set, streamed K-blocks, TAP mode)
         uint32_t accumulate = 0;
         uint32_t b_lo = b_lo0;
         int kb = 0;
@@ -359,28 +439,43 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
             }
             // halo: tap (dy, dx) starts (dy * pitch + dx) pixel rows (128 B = 8 descriptor units) into the tile
             const uint32_t al = a_lo0 + sa * (kAStage >> 4) + (HALO ? ((tap / 3) * kHaloPitch + tap % 3) * 8 : 0);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {  // 4 x (K = 16 bf16 = 32 bytes = 2 units) inside the 128-byte swizzle atom
-              umma_bf16(d_tmem, make_desc(a_hi, al + 2 * k), make_desc(b_hi, bl + 2 * k), idesc, accumulate);
-              accumulate = 1;
+              for (int k = 0; k < 4; ++k) {  // 4 x (K = 16 bf16 = 32 bytes = 2 units) inside the 128-byte swizzle atom
+                umma_bf16(d_tmem, make_desc(a_hi, al + 2 * k), make_desc(b_hi, bl + 2 * k), idesc, accumulate);
+                accumulate = 1;
+              }
+              if (streamed) umma_commit(ring_empty + sr);
+              if (!HALO) umma_commit(a_empty + sa);
             }
+            __syncwarp();
+            accumulate = 1;
             if (streamed) {
-              umma_commit(ring_empty + sr);
               if (++sr == kRing) { sr = 0; pr ^= 1; }
             }
             if constexpr (!HALO) {
-              umma_commit(a_empty + sa);
               if (++sa == kAStages) { sa = 0; pa ^= 1; }
             }
           }
           if constexpr (HALO) {
-            umma_commit(a_empty + sa);
+            if (elect_one()) umma_commit(a_empty + sa);
+            __syncwarp();
             if (++sa == kAStages) { sa = 0; pa ^= 1; }
           }
         }
-        umma_commit(t_full + acc);
-        if (++tile == tiles) { tile = 0; ++gn; }
       }
+      if (elect_one()) umma_commit(t_full + acc);
+      __syncwarp();
+      if (++tile == tiles) {
+        tile = 0;
+        if (++n == batch) { n = 0; ++gi; }
+      }
+    }
+    if (p.dbg != nullptr && lane == 0) {
+      p.dbg[blockIdx.x * 8 + 0] = clock64() - dbg_t0;
+      p.dbg[blockIdx.x * 8 + 1] = dbg_te;
+      p.dbg[blockIdx.x * 8 + 2] = dbg_af;
+      p.dbg[blockIdx.x * 8 + 3] = item_end - item_begin;
     }
   } else {
     // ================================ epilogue warps ================================
@@ -388,14 +483,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
     const int half = (warp - 2) >> 2;   // which 32-column half of the accumulator (N = 64 only)
     if (BN == 64 || half == 0) {
       constexpr int NC = BN == 64 ? 32 : 16;
+      EpiCtx<NC> ec;
+      ec.bias_group = -1;
       int it = 0;
       int tile = item_begin % tiles;
       int gn = item_begin / tiles;
+      long long dbg_tf = 0, dbg_t0 = clock64();
       for (int item = item_begin; item < item_end; ++item, ++it) {
         const int n = gn % p.batch;
-        const savsr_conv_group& g = p.g[gn / p.batch];
+        const int gi = gn / p.batch;
+        const savsr_conv_group& g = p.g[gi];
         const int acc = it & 1;
+        epi_prefetch<NC>(p, g, gi, n, tile, quad, lane, half * 32, ec);   // loads fly while the tile's MMAs run
+        const long long c0 = clock64();
         mbar_wait(t_full + acc, (it >> 1) & 1);
+        dbg_tf += clock64() - c0;
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN + half * 32);
         float v[NC];
@@ -410,8 +512,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(t_empty + acc);
-        conv_epilogue<NC>(p, g, n, tile, quad, lane, v, half * 32);
+        epi_finish<NC>(p, g, n, tile, quad, lane, v, half * 32, ec);
         if (++tile == tiles) { tile = 0; ++gn; }
+      }
+      if (p.dbg != nullptr && warp == 2 && lane == 0) {
+        p.dbg[blockIdx.x * 8 + 4] = clock64() - dbg_t0;
+        p.dbg[blockIdx.x * 8 + 5] = dbg_tf;
       }
     }
   }
@@ -434,7 +540,8 @@ __global__ void __launch_bounds__(128) conv_check_kernel(const __grid_constant__
   const int tile = item % tiles;
   const int gn = item / tiles;
   const int n = gn % p.batch;
-  const savsr_conv_group& g = p.g[gn / p.batch];
+  const int gi = gn / p.batch;
+  const savsr_conv_group& g = p.g[gi];
   const int m = threadIdx.x;
   const int px = (tile % p.tiles_x) * kTileW + (m & 7);
   const int py = (tile / p.tiles_x) * kTileH + (m >> 3);
@@ -463,7 +570,10 @@ __global__ void __launch_bounds__(128) conv_check_kernel(const __grid_constant__
         }
       }
     }
-    conv_epilogue<NC>(p, g, n, tile, m >> 5, m & 31, v, col0);
+    EpiCtx<NC> ec;
+    ec.bias_group = -1;
+    epi_prefetch<NC>(p, g, gi, n, tile, m >> 5, m & 31, col0, ec);
+    epi_finish<NC>(p, g, n, tile, m >> 5, m & 31, v, col0, ec);
   }
 }
 
@@ -546,6 +656,10 @@ static int launch_conv(savsr_ctx* ctx, ConvParams& p, int impl, cudaStream_t st)
 }  // namespace savsr
 
 using namespace savsr;
+
+static long long* g_conv_dbg = nullptr;
+// bring-up aid (not in the public header): device buffer [grid][8] receiving cycle counters of the next conv launches
+extern "C" void savsr_debug_conv_counters(long long* dev_buf) { g_conv_dbg = dev_buf; }
 
 extern "C" size_t savsr_packed_weight_bytes(int co, int ci, int ksize) {
   return static_cast<size_t>(co) * ci * ksize * ksize * sizeof(__nv_bfloat16);
@@ -630,9 +744,11 @@ extern "C" int savsr_conv(savsr_ctx* ctx, savsr_arena* arena, const savsr_conv_g
   p.ntaps = ksize * ksize;
   p.halo = (impl == SAVSR_IMPL_TCGEN05_HALO && ksize == 3) ? 1 : 0;
   p.nsrc = groups[0].nsrc;
+  for (int i = 0; i < ngroups; ++i) if (groups[i].weight_sample_stride != 0) p.per_sample_mask |= 1u << i;
   const int nkb = p.nsrc * p.ntaps;
   p.n_res = nkb <= kBBlocks ? nkb : kBBlocks - kRing;
   p.dst_mode = dst_mode;
+  p.dbg = g_conv_dbg;
   if (n_tile == 64) return launch_conv<64>(ctx, p, impl, static_cast<cudaStream_t>(st));
   return launch_conv<16>(ctx, p, impl, static_cast<cudaStream_t>(st));
 }

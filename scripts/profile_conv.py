@@ -40,6 +40,19 @@ def main():
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / reps
     flop = 2.0 * ng * B * H * W * 64 * 64 * nsrc * ks * ks
+    if os.environ.get("CONV_DBG"):
+        import ctypes
+        dbg = torch.zeros(148, 8, dtype=torch.int64, device=G.DEV)
+        K.load().savsr_debug_conv_counters.argtypes = [ctypes.c_void_p]
+        K.load().savsr_debug_conv_counters(dbg.data_ptr())
+        K.check(K.load().savsr_conv(G.ctx().handle, ab.a.handle, arr, len(groups), ks, 64, K.DST_ARENA, None, impl, G._stream()))
+        torch.cuda.synchronize()
+        K.load().savsr_debug_conv_counters(None)
+        d = dbg.float().cpu()
+        d = d[d[:, 3] > 0]
+        m = d.mean(0)
+        print(f"  per CTA (avg over {len(d)}): tiles {m[3]:.1f} | MMA warp total {m[0]:.0f} cyc ({m[0]/m[3]:.0f}/tile), wait t_empty {m[1]:.0f} ({100*m[1]/m[0]:.0f}%), "
+              f"wait a_full {m[2]:.0f} ({100*m[2]/m[0]:.0f}%) | epilogue total {m[4]:.0f}, wait t_full {m[5]:.0f} ({100*m[5]/max(m[4],1):.0f}%) | producer wait a_empty {m[6]:.0f}")
     print(f"nsrc={nsrc} groups={ng} B={B} impl={a[3] if len(a) > 3 else 'halo'} k={ks}: {us:.1f} us/launch, {flop / us / 1e6:.1f} TFLOP/s")
 
 

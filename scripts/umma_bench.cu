@@ -1,0 +1,146 @@
+// Micro-benchmark: cycles per tcgen05.mma (kind::f16, bf16, SS operands, cta_group::1) for several (M, N).
+// One CTA per SM, one thread issues ITERS x 4 MMAs (K = 16 each) on garbage smem, then commits and waits.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/umma_bench.bin scripts/umma_bench.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../savsr_b200/csrc/common.cuh"
+namespace savsr { void set_error(const char*, ...) {} int cuda_fail(cudaError_t, const char*) { return 1; } }
+using namespace savsr;
+
+__host__ __device__ constexpr uint32_t idesc_mn(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+template <int M, int N>
+__global__ void __launch_bounds__(128, 1) bench(int iters, long long* out, int a_off = 0, int a_sbo = 1024) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < (48 * 1024 + N * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) tmem_alloc<512>(&slot);
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tm = slot;
+  if (warp == 0 && lane == 0) {
+    const uint32_t a_lo = (smem_u32(smem + a_off) >> 4) & 0x3fff, b_lo = (smem_u32(smem + 48 * 1024) >> 4) & 0x3fff;
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t ahi = (uint32_t(a_sbo) >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t idesc = idesc_mn(M, N);
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tm + (it & 1) * N, (uint64_t(ahi) << 32) | (a_lo + 2 * k), (uint64_t(hi) << 32) | (b_lo + 2 * k), idesc, (it | k) ? 1u : 0u);
+    }
+    umma_commit(&bar);
+    mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    if (blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  tc_fence_before(); __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<512>(tm); }
+}
+
+// Emulates the conv main loop: per "tile" 9 taps x 4 MMAs with halo-style A offsets, distinct B blocks, a commit per
+// source (mode bit 0), alternating accumulators (bit 1), accumulate reset per tile (bit 2).
+__global__ void __launch_bounds__(128, 1) bench_conv(int tiles, long long* out, int mode) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  __shared__ uint64_t bar, dummy;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (24 * 1024 + 9 * 8192) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init(&dummy, 1); fence_barrier_init(); }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) tmem_alloc<512>(&slot);
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tm = slot;
+  if (warp == 0) {
+    const uint32_t a_lo0 = (smem_u32(smem) >> 4) & 0x3fff, b_lo0 = (smem_u32(smem + 24 * 1024) >> 4) & 0x3fff;
+    const uint32_t bhi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t ahi = (1280u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t idesc = idesc_mn(128, 64);
+    long long t0 = clock64();
+    for (int t = 0; t < tiles; ++t) {
+      const uint32_t d = tm + ((mode & 2) ? (t & 1) * 64 : 0);
+      if (elect_one()) {
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t al = a_lo0 + ((tap / 3) * 10 + tap % 3) * 8, bl = b_lo0 + tap * 512;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d, (uint64_t(ahi) << 32) | (al + 2 * k), (uint64_t(bhi) << 32) | (bl + 2 * k), idesc,
+                      ((mode & 4) && tap == 0 && k == 0) ? 0u : 1u);
+        }
+        if (mode & 1) umma_commit(&dummy);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(&bar);
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = t1 - t0;
+  }
+  tc_fence_before(); __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<512>(tm); }
+}
+
+template <int M, int N>
+void run(int iters, long long* d_out) {
+  const size_t smem = 1024 + 48 * 1024 + N * 128;
+  cudaFuncSetAttribute(bench<M, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  for (int grid : {1, 148}) {
+    bench<M, N><<<grid, 128, smem>>>(iters, d_out);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long cyc = 0;
+    cudaMemcpy(&cyc, d_out, sizeof(cyc), cudaMemcpyDeviceToHost);
+    const double per = double(cyc) / (iters * 4);
+    printf("M=%3d N=%3d grid=%3d: %8.1f cycles/MMA  -> %6.0f MAC/cycle/SM  (%s)\n", M, N, grid, per, double(M) * N * 16 / per,
+           e == cudaSuccess ? "ok" : cudaGetErrorString(e));
+  }
+}
+
+int main() {
+  long long* d_out;
+  cudaMalloc(&d_out, sizeof(long long));
+  const int iters = 4096;
+  run<128, 64>(iters, d_out);
+  run<128, 128>(iters, d_out);
+  run<128, 256>(iters, d_out);
+  run<128, 32>(iters, d_out);
+  run<128, 16>(iters, d_out);
+  run<64, 64>(iters, d_out);
+  run<64, 128>(iters, d_out);
+  run<64, 256>(iters, d_out);
+  // A-operand alignment study (M=128, N=64): halo-style shifted starts and row-group strides
+  {
+    const size_t smem = 1024 + 48 * 1024 + 64 * 128;
+    cudaFuncSetAttribute(bench<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int cfg[][2] = {{0, 1024}, {128, 1024}, {512, 1024}, {0, 1280}, {1408, 1280}, {2688, 1280}, {0, 2048}, {128, 2048}, {256, 2048}, {0, 1152}};
+    for (auto& c : cfg) {
+      bench<128, 64><<<148, 128, smem>>>(iters, d_out, c[0], c[1]);
+      cudaError_t e = cudaDeviceSynchronize();
+      long long cyc = 0;
+      cudaMemcpy(&cyc, d_out, sizeof(cyc), cudaMemcpyDeviceToHost);
+      printf("A start +%4d B, SBO %4d: %6.1f cycles/MMA (%s)\n", c[0], c[1], double(cyc) / (iters * 4), e == cudaSuccess ? "ok" : cudaGetErrorString(e));
+    }
+  }
+  {
+    const size_t smem = 1024 + 24 * 1024 + 9 * 8192;
+    cudaFuncSetAttribute(bench_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (int mode = 0; mode < 8; ++mode) {
+      bench_conv<<<148, 128, smem>>>(2048, d_out, mode);
+      cudaError_t e = cudaDeviceSynchronize();
+      long long cyc = 0;
+      cudaMemcpy(&cyc, d_out, sizeof(cyc), cudaMemcpyDeviceToHost);
+      printf("conv-like loop mode %d (commit/src=%d alt-acc=%d reset=%d): %6.1f cycles/MMA (%s)\n", mode, mode & 1, (mode >> 1) & 1,
+             (mode >> 2) & 1, double(cyc) / (2048.0 * 36), e == cudaSuccess ? "ok" : cudaGetErrorString(e));
+    }
+  }
+  return 0;
+}
