@@ -145,6 +145,14 @@ typedef struct savsr_front_group {
 int savsr_front_conv(savsr_ctx* ctx, savsr_arena* arena, const float* x, int t, int h, int w,
                      const savsr_front_group* groups, int ngroups, savsr_stream st);
 
+/*
+ * Tensor-core route for the same first layer: pack the fp32 window into ONE arena slot (channel 3f+c = frame f,
+ * colour c; remaining channels zero; reflect pad of savsr_arch.py:670-690 fused), after which conv_c / conv_sup are
+ * ordinary savsr_conv launches with zero-expanded [64][64][3][3] weights.
+ */
+int savsr_pack_frames(savsr_ctx* ctx, savsr_arena* arena, const float* x, int t, int h, int w, int dst_slot,
+                      savsr_stream st);
+
 /* ---- OSA-Conv prologue (savsr_arch.py:143-163, 91-96, 123-128) ---------------------------------- */
 typedef struct savsr_osa_params {
   int32_t ci, co, att;            /* in planes (64*nsrc), out planes (64), attention channels      */

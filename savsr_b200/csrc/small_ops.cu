@@ -76,6 +76,32 @@ __global__ void __launch_bounds__(128) front_conv_kernel(const __grid_constant__
   }
 }
 
+// fp32 NCHW window [B][t][3][h][w] -> one bf16 arena slot whose channels 0..3t-1 are the frames' RGB planes
+// (channel 3f + c), the rest zero, reflect-padded to the even arena size (savsr_arch.py:670-690).  With this slot the
+// first-layer convs (conv_c / conv_sup, savsr_arch.py:456-457) run on the tensor-core kernel with zero-expanded weights.
+__global__ void __launch_bounds__(256) pack_frames_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ dst, int batch,
+                                                          int t, int h, int w, int hp, int wp) {
+  const long npix = static_cast<long>(hp) * wp;
+  const long total = static_cast<long>(batch) * npix * 8;
+  for (long id = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; id < total; id += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int chunk = id & 7;
+    const long pn = id >> 3;
+    const long pix = pn % npix;
+    const int n = pn / npix;
+    const int py = pix / wp, px = pix % wp;
+    const int ry = py < h ? py : 2 * h - 2 - py, rx = px < w ? px : 2 * w - 2 - px;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ch = chunk * 8 + e;
+      v[e] = ch < 3 * t ? __ldg(x + ((static_cast<long>(n) * t * 3 + ch) * h + ry) * w + rx) : 0.f;
+    }
+    uint4 o;
+    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(dst + (static_cast<long>(n) * npix + pix) * kC + chunk * 8) = o;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ OSA prologue
 constexpr int kMaxOsa = 4;
 struct OsaLaunch {
@@ -405,6 +431,23 @@ extern "C" int savsr_front_conv(savsr_ctx* ctx, savsr_arena* arena, const float*
   const long npix = static_cast<long>(p.hp) * p.wp;
   dim3 grid(static_cast<unsigned>((npix + 127) / 128), arena->batch, ngroups);
   front_conv_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(st)>>>(p);
+  SAVSR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int savsr_pack_frames(savsr_ctx* ctx, savsr_arena* arena, const float* x, int t, int h, int w, int dst_slot, savsr_stream st) {
+  SAVSR_REQUIRE(ctx && arena && x, "savsr_pack_frames: null pointer");
+  SAVSR_REQUIRE(t >= 1 && 3 * t <= kC, "savsr_pack_frames: %d frames do not fit 64 channels", t);
+  SAVSR_REQUIRE(h >= 2 && w >= 2, "savsr_pack_frames: LR frame %dx%d too small for reflect padding", h, w);
+  SAVSR_REQUIRE(arena->height == h + (h & 1) && arena->width == w + (w & 1),
+                "savsr_pack_frames: arena %dx%d is not the even-padded size of %dx%d", arena->height, arena->width, h, w);
+  SAVSR_REQUIRE(dst_slot >= 0 && dst_slot < arena->nslots, "savsr_pack_frames: slot %d out of range", dst_slot);
+  if (arena->batch == 0) return 0;
+  const long npix = static_cast<long>(arena->height) * arena->width;
+  const long total = arena->batch * npix * 8;
+  const int blocks = static_cast<int>((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  pack_frames_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(st)>>>(x, arena->base + static_cast<long>(dst_slot) * arena->batch * npix * kC,
+                                                                       arena->batch, t, h, w, arena->height, arena->width);
   SAVSR_CUDA(cudaGetLastError());
   return 0;
 }

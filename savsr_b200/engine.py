@@ -261,6 +261,7 @@ class Plan:
         # ---- arenas: slot count is discovered by a dry layout pass (slot ids only), then allocated.
         sl = _Slots()
         zero = sl.get()
+        FR = sl.get()                                              # the 7 LR frames as one 21(+43 zero)-channel slot
         dirs = ("f2p_win", "p2f_win")
         n_it = t - 3 + 1
         F = [[sl.get() for _ in range(n_it)] for _ in dirs]        # unit outputs, kept for the l2 fusion
@@ -287,23 +288,25 @@ class Plan:
         xin = self.x_in.data_ptr()
 
         # ---- 1. bi-directional propagation (savsr_arch.py:703-719), both directions per launch
+        lrh0, hh0, ww0 = lr.handle, self.h, self.w
+        self._emit(lambda st: lib.savsr_pack_frames(ctx, lrh0, xin, t, hh0, ww0, FR, st), kind="pack_frames")
         hpast = [zero, zero]
         for idx in range(n_it):
             centre = [t - 1 - 1 - idx, idx + 1]                     # f2p walks back, p2f forward
-            fg = []
+            # first-layer convs on the tensor-core kernel: the packed-frames slot is the single source and the
+            # 3/6-channel filters are zero-expanded to the frame channels they read (savsr_arch.py:447-457)
+            fgroups = []
             for d, p in enumerate(dirs):
                 c = centre[d]
-                g = K.FrontGroup(); g.frame[0] = c; g.nframes = 1; g.dst_slot = S0[d][0]
-                g.weight, g.bias = self._ptr(p + ".conv_c.weight"), self._ptr(p + ".conv_c.bias")
-                fg.append(g)
-                g = K.FrontGroup(); g.frame[0] = c - 1; g.frame[1] = c + 1; g.nframes = 2; g.dst_slot = S0[d][1]
-                g.weight, g.bias = self._ptr(p + ".conv_sup.weight"), self._ptr(p + ".conv_sup.bias")
-                fg.append(g)
-            farr = (K.FrontGroup * len(fg))(*fg)
-            self._keep.append(farr)
-            lrh, hh, ww, nfg = lr.handle, self.h, self.w, len(fg)
-            self._emit(lambda st, farr=farr, nfg=nfg: lib.savsr_front_conv(ctx, lrh, xin, t, hh, ww, farr, nfg, st), kind="front_conv",
-                       flops=2.0 * B * self.hp * self.wp * 64 * 9 * 18)
+                wc = torch.zeros(64, 64, 3, 3, device=self.device)
+                wc[:, 3 * c:3 * c + 3] = self._p(p + ".conv_c.weight")
+                ws = torch.zeros(64, 64, 3, 3, device=self.device)
+                wsup = self._p(p + ".conv_sup.weight")
+                ws[:, 3 * (c - 1):3 * (c - 1) + 3] = wsup[:, 0:3]
+                ws[:, 3 * (c + 1):3 * (c + 1) + 3] = wsup[:, 3:6]
+                fgroups.append(self._group([FR], S0[d][0], self._pack(wc), self._ptr(p + ".conv_c.bias"), act=L))
+                fgroups.append(self._group([FR], S0[d][1], self._pack(ws), self._ptr(p + ".conv_sup.bias"), act=L))
+            self._conv(lr, fgroups)
             cur = [[S0[d][0], S0[d][1], hpast[d]] for d in range(2)]
             sets = [S1, S2]
             for j in range(4):

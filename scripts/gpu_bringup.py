@@ -33,6 +33,7 @@ CHECKS = {
     "conv_rgb": "check_conv_rgb()",
     "conv_per_sample": "check_osa_conv_per_sample()",
     "front_conv": "check_front_conv()",
+    "pack_frames": "check_pack_frames()",
     "osa_prologue_192": "check_osa_prologue(ci=192)",
     "osa_prologue_320": "check_osa_prologue(ci=320, B=1)",
     "osa_prologue_64": "check_osa_prologue(ci=64, B=3)",

@@ -241,6 +241,34 @@ def check_front_conv(B=2, h=13, w=15, seed=5):
     return dict(conv_c=assert_close("front conv_c", ab.get(0), ref0), conv_sup=assert_close("front conv_sup", ab.get(1), ref1))
 
 
+def check_pack_frames(B=2, h=13, w=15, seed=11):
+    """savsr_pack_frames + zero-expanded filters on the tensor-core conv == conv_c / conv_sup of the reference."""
+    torch.manual_seed(seed)
+    hp, wp = h + (h & 1), w + (w & 1)
+    ab = ArenaBox(3, B, hp, wp)
+    x = torch.rand(B, 7, 3, h, w, device=DEV)
+    K.check(K.load().savsr_pack_frames(ctx().handle, ab.a.handle, x.data_ptr(), 7, h, w, 0, _stream()))
+    xp = F.pad(x.reshape(-1, 3, h, w), [0, wp - w, 0, hp - h], mode="reflect").view(B, 7, 3, hp, wp) if (hp != h or wp != w) else x
+    got = ab.get(0)
+    ref = torch.zeros(B, 64, hp, wp, device=DEV)
+    ref[:, :21] = xp.reshape(B, 21, hp, wp)
+    res = dict(frames=assert_close("pack_frames", got, bf16_round(ref), rel=0, abs_=0))
+    wc = torch.randn(64, 3, 3, 3, device=DEV) * 0.2
+    ws = torch.randn(64, 6, 3, 3, device=DEV) * 0.2
+    bc = torch.randn(64, device=DEV) * 0.1
+    c = 4
+    w64c = torch.zeros(64, 64, 3, 3, device=DEV); w64c[:, 3 * c:3 * c + 3] = wc
+    w64s = torch.zeros(64, 64, 3, 3, device=DEV); w64s[:, 3 * (c - 1):3 * c] = ws[:, :3]; w64s[:, 3 * (c + 1):3 * (c + 2)] = ws[:, 3:]
+    pc, ps = pack_weight(w64c), pack_weight(w64s)          # keep the packed tensors alive across the launch
+    run_conv(ab, [group([0], 1, pc, bc, act=K.ACT_LRELU), group([0], 2, ps, bc, act=K.ACT_LRELU)], impl=K.IMPL_HALO)
+    xb = bf16_round(xp)
+    ref_c = F.leaky_relu(F.conv2d(xb[:, c], bf16_round(wc), bc, padding=1), 0.2)
+    ref_s = F.leaky_relu(F.conv2d(torch.cat([xb[:, c - 1], xb[:, c + 1]], 1), bf16_round(ws), bc, padding=1), 0.2)
+    res["conv_c"] = assert_close("conv_c via frames slot", ab.get(1), ref_c)
+    res["conv_sup"] = assert_close("conv_sup via frames slot", ab.get(2), ref_s)
+    return res
+
+
 def _osa_state(ci, seed):
     g = torch.Generator().manual_seed(seed)
     att = max(int(ci * 0.0625), 16)

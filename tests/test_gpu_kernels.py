@@ -42,6 +42,11 @@ def test_front_conv(G):
     G.check_front_conv(B=1, h=16, w=20, seed=15)
 
 
+def test_pack_frames_and_first_layer_on_tensor_cores(G):
+    G.check_pack_frames()
+    G.check_pack_frames(B=1, h=16, w=20, seed=16)
+
+
 @pytest.mark.parametrize("ci,B", [(192, 2), (320, 1), (64, 3)])
 def test_osa_prologue(G, ci, B):
     G.check_osa_prologue(ci=ci, B=B)

@@ -30,16 +30,16 @@ def test_launch_census(recorded):
     names = [c[0] for c in calls]
     build_time = names.count("savsr_pack_conv_weight")
     # distinct conv weights: l1 2*(4*3 conv0 + 1 conv1 + 4*3 conv2 + merge) + l2 (5 + 2*(5+5) + 1 + 1) + RG 4*(16+1)
-    # + mask.0 x4 + conv_last + kernel_conv + fusion + tail
-    assert build_time == 2 * (12 + 1 + 12 + 1) + (5 + 20 + 1 + 1) + 68 + 4 + 1 + 1 + 1 + 1
+    # + mask.0 x4 + conv_last + kernel_conv + fusion + tail + zero-expanded first-layer filters (5 iterations x 2 dirs x 2)
+    assert build_time == 2 * (12 + 1 + 12 + 1) + (5 + 20 + 1 + 1) + 68 + 4 + 1 + 1 + 1 + 1 + 20
     run = names[names.index("savsr_satu_index") + 1:] if False else names
-    assert names.count("savsr_front_conv") == 5                      # one per propagation iteration, both directions
+    assert names.count("savsr_pack_frames") == 1 and names.count("savsr_front_conv") == 0
     assert names.count("savsr_ca_scale_residual") == 32              # 4 groups x 8 RCAB
     assert names.count("savsr_osadapt_mask") == 4
     assert names.count("savsr_osa_prologue") == 5 * 3 + 2 + 4        # l1 blocks 1-3 (both dirs batched), l2 x2, adapt x4
     assert names.count("savsr_satu_sta") == 1 and names.count("savsr_satu_gather") == 1
-    # conv launches: l1 5*(4*3 + 1) + l2 (1 + 2*3 + 1 + 1) + RG 4*(16 + 1 + mask + adapt) + conv_last + kernel_conv + fusion + tail
-    assert names.count("savsr_conv") == 5 * 13 + 9 + 4 * 19 + 1 + 1 + 1 + 1
+    # conv launches: l1 5*(first layer + 4*3 + 1) + l2 (1 + 2*3 + 1 + 1) + RG 4*(16 + 1 + mask + adapt) + conv_last + kernel_conv + fusion + tail
+    assert names.count("savsr_conv") == 5 * 14 + 9 + 4 * 19 + 1 + 1 + 1 + 1
 
 
 def test_no_conv_writes_a_slot_it_reads(recorded):
@@ -59,9 +59,8 @@ def test_slots_written_before_read_and_hidden_states_persist(recorded):
     zero_reads = 0
     F_slots = set()
     for idx, (name, args) in enumerate(calls):
-        if name == "savsr_front_conv":
-            for i in range(args[7]):
-                written[(id(args[1]), args[6][i].dst_slot)] = idx
+        if name == "savsr_pack_frames":
+            written[(id(args[1]), args[6])] = idx
         elif name == "savsr_conv":
             arena = id(args[1])
             for g in _groups(args):
@@ -93,12 +92,13 @@ def test_slots_written_before_read_and_hidden_states_persist(recorded):
 def test_propagation_batches_both_directions(recorded):
     _, calls = recorded
     convs = [a for n, a in calls if n == "savsr_conv"]
-    assert convs[0][3] == 6 and convs[0][4] == 3   # conv0 of block 0: 2 directions x 3 streams, 3x3
-    assert convs[1][3] == 2 and convs[1][4] == 1   # conv1 (1x1 192->64) for both directions
-    assert convs[2][3] == 6                         # conv2 x 6 with residual
-    g = convs[2][2][0]
+    assert convs[0][3] == 4 and convs[0][2][0].src_slot[0] == convs[0][2][3].src_slot[0]   # first layer: 4 convs on the frames slot
+    assert convs[1][3] == 6 and convs[1][4] == 3   # conv0 of block 0: 2 directions x 3 streams, 3x3
+    assert convs[2][3] == 2 and convs[2][4] == 1   # conv1 (1x1 192->64) for both directions
+    assert convs[3][3] == 6                         # conv2 x 6 with residual
+    g = convs[3][2][0]
     assert g.nsrc == 2 and g.res1_slot >= 0 and g.act == K.ACT_LRELU
-    osa = convs[4]                                  # block 1: conv0, [prologue], OSA conv
+    osa = convs[5]                                  # block 1: conv0, [prologue], OSA conv
     assert osa[3] == 2 and osa[2][0].nsrc == 3 and osa[2][0].weight_sample_stride == 64 * 192 * 9 * 2 and not osa[2][0].bias
 
 
