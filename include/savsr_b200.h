@@ -241,6 +241,18 @@ int savsr_satu_gather(savsr_ctx* ctx, savsr_arena* lr, int x_slot, int sta_slot,
                       const float* base_y, const float* base_x, const savsr_satu_weights* wts,
                       savsr_stream st);
 
+/*
+ * Tensor-core version of the HR stage: savsr_satu_gather followed by the 128->64 fusion conv (savsr_arch.py:364-374) in
+ * one kernel; the compress / expand / fusion GEMMs run on tcgen05 with the tiles built in shared memory.
+ * w_compress: savsr_pack_conv_weight of [32][64][1][1] (rows e*8+k), n_tile 16; w_expand: of [64][64][1][1] with input
+ * columns e*8+k (32..63 zero), n_tile 64; w_fusion: of the fusion filter [64][128][1][1], n_tile 64.
+ * Writes the fused HR feature (bf16) to hr slot dst_slot.
+ */
+int savsr_satu_fused(savsr_ctx* ctx, savsr_arena* lr, int x_slot, int sta_slot, int h, int w, savsr_arena* hr,
+                     int dst_slot, const float* table, const float* base_y, const float* base_x,
+                     const void* w_compress, const void* w_expand, const void* w_fusion, const float* fusion_bias,
+                     savsr_stream st);
+
 #ifdef __cplusplus
 }
 #endif

@@ -100,6 +100,7 @@ SIGNATURES = {
     "savsr_satu_index": (_I, [_VP, C.POINTER(SatuWeights), _I, _I, _I, _I, _F, _F] + [_VP] * 9 + [_VP]),
     "savsr_satu_sta": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP]),
     "savsr_satu_gather": (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _I, _I, _VP, _VP, _VP, C.POINTER(SatuWeights), _VP]),
+    "savsr_satu_fused": (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -26,6 +26,9 @@ __device__ __forceinline__ float unnormalize(float g, int n_lr) {
   return __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.f), 2.f), static_cast<float>(n_lr - 1));
 }
 
+__host__ __device__ constexpr uint32_t desc_hi_1024() { return (1024u >> 4) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ uint64_t make_desc64(uint32_t hi, uint32_t lo) { return (static_cast<uint64_t>(hi) << 32) | lo; }
+
 __global__ void satu_axis_kernel(int n_out, int n_lr, float s, float* rel, int32_t* cell, float* base, int32_t* corner) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_out) return;
@@ -314,6 +317,248 @@ __global__ void __launch_bounds__(kGatherPix) satu_gather_kernel(const GatherPar
   }
 }
 
+// ------------------------------------------------------------------------------------------------ fused HR kernel
+// gather(x) -> routed experts -> + gather(sta) -> 128->64 fusion conv, one 128-pixel HR tile at a time, with the three
+// small GEMMs on tcgen05 (accumulators in TMEM) and the gathers / routing on CUDA cores:
+//   U[128,32] = F[128,64] Wc^T            (all 4 experts' compress matrices stacked, savsr_arch.py:353-355, 368)
+//   V[e*8+k]  = r_e * sum_e' r_e' U[e'*8+k]                                     (routing, per pixel, in registers)
+//   O[128,64] = V[128,32] We^T ; fea = O + F                                    (expand + residual, 357-370)
+//   Y[128,64] = [S | fea][128,128] Wf^T + b                                     (fusion, 374; S = gathered sta)
+// F, S, V, fea tiles are written by the threads as bf16 in the 128-byte-swizzled K-major layout the UMMA reads.
+// The chain is sequential per tile; two CTAs per SM overlap each other's phases.
+struct FusedParams {
+  const __nv_bfloat16* lr;
+  __nv_bfloat16* hr;
+  const float* table;
+  const float* base_y;
+  const float* base_x;
+  const uint8_t* w_compress;  // packed [32][64]  (4 KB)
+  const uint8_t* w_expand;    // packed [64][64]  (8 KB, K columns 32..63 zero)
+  const uint8_t* w_fusion;    // packed 2 x [64][64] (16 KB): sta block, fea block
+  const float* bias;          // [64]
+  int batch, hp, wp, h, w, H, W;
+  int x_slot, sta_slot, dst_slot;
+  int tiles_per_img;
+};
+
+constexpr int kFusedThreads = 256;   // 8 warps: warp w owns TMEM lane quadrant w & 3 and column half w >> 2
+constexpr int kFusedSmem = 1024 + 3 * 16384 + 4096 + 8192 + 16384 + 2 * 128 * 32 + 128 * 16 + 256 + 64;
+
+__device__ __forceinline__ void gather8(const __nv_bfloat16* img, const Corner4& c, int chunk, float (&a)[8]) {
+  uint4 v[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) v[q] = c.off[q] >= 0 ? *reinterpret_cast<const uint4*>(img + c.off[q] + chunk * 8) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a[e] = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float wgt = c.wt[q];
+    a[0] += wgt * bf16_lo(v[q].x); a[1] += wgt * bf16_hi(v[q].x); a[2] += wgt * bf16_lo(v[q].y); a[3] += wgt * bf16_hi(v[q].y);
+    a[4] += wgt * bf16_lo(v[q].z); a[5] += wgt * bf16_hi(v[q].z); a[6] += wgt * bf16_lo(v[q].w); a[7] += wgt * bf16_hi(v[q].w);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&a)[8]) {
+  uint4 o;
+  o.x = pack_bf16(a[0], a[1]); o.y = pack_bf16(a[2], a[3]); o.z = pack_bf16(a[4], a[5]); o.w = pack_bf16(a[6], a[7]);
+  return o;
+}
+// byte offset of 16-byte chunk `c` of row `r` in a [rows][128 B] SWIZZLE_128B tile
+__device__ __forceinline__ int swz(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
+
+__global__ void __launch_bounds__(kFusedThreads, 2) satu_fused_kernel(const FusedParams p) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sF = smem;                 // F, later fea (in place)      [128][128 B]
+  uint8_t* sS = smem + 16384;         // gathered sta                 [128][128 B]
+  uint8_t* sV = smem + 32768;         // V (K = 32 used)              [128][128 B]
+  uint8_t* sWc = smem + 49152;        // [32][128 B]
+  uint8_t* sWe = sWc + 4096;          // [64][128 B]
+  uint8_t* sWf = sWe + 8192;          // 2 x [64][128 B]
+  Corner4* cx = reinterpret_cast<Corner4*>(sWf + 16384);
+  Corner4* cs = cx + 128;
+  float* rt = reinterpret_cast<float*>(cs + 128);   // [128][4] routing weights
+  float* sbias = rt + 128 * 4;                      // [64]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sbias + 64);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, half = warp >> 2;
+  const int row = quad * 32 + lane;                 // tile row (= TMEM lane) this thread serves in the register phases
+  for (int i = tid; i < (4096 + 8192 + 16384) / 16; i += kFusedThreads) {
+    const uint8_t* src = i < 256 ? p.w_compress + i * 16 : i < 768 ? p.w_expand + (i - 256) * 16 : p.w_fusion + (i - 768) * 16;
+    *reinterpret_cast<uint4*>(sWc + i * 16) = *reinterpret_cast<const uint4*>(src);
+  }
+  // zero the V tile once (chunks 4..7 of every row, the unused K half, are never written again)
+  for (int i = tid; i < 1024; i += kFusedThreads) *reinterpret_cast<uint4*>(sV + i * 16) = make_uint4(0, 0, 0, 0);
+  if (tid < 64) sbias[tid] = __ldg(p.bias + tid);
+  if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc<256>(tmem_slot);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *tmem_slot;
+  const uint32_t tU = tm, tO = tm + 32, tY = tm + 96;
+  const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+  constexpr uint32_t hi = desc_hi_1024();
+  const uint32_t loF = (smem_u32(sF) >> 4) & 0x3fff, loS = (smem_u32(sS) >> 4) & 0x3fff, loV = (smem_u32(sV) >> 4) & 0x3fff;
+  const uint32_t loWc = (smem_u32(sWc) >> 4) & 0x3fff, loWe = (smem_u32(sWe) >> 4) & 0x3fff, loWf = (smem_u32(sWf) >> 4) & 0x3fff;
+  uint32_t phase = 0;
+  const long NPIX = static_cast<long>(p.H) * p.W;
+  const long lr_img = static_cast<long>(p.hp) * p.wp * kC;
+  const int total = p.batch * p.tiles_per_img;
+
+  for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    const int n = t / p.tiles_per_img;
+    const long pix0 = static_cast<long>(t - n * p.tiles_per_img) * 128;
+    // ---- P0: per-pixel sampling corners and routing weights (threads 0..127, one pixel each)
+    if (tid < 128) {
+      const long pix = pix0 + tid;
+      if (pix < NPIX) {
+        const int i = pix / p.W, j = pix - static_cast<long>(i) * p.W;
+        const float4 t0 = *reinterpret_cast<const float4*>(p.table + pix * 8);
+        const float4 t1 = *reinterpret_cast<const float4*>(p.table + pix * 8 + 4);
+        const float bx = p.base_x[j], by = p.base_y[i];
+        const float wm1 = static_cast<float>(p.w - 1), hm1 = static_cast<float>(p.h - 1);
+        cx[tid] = make_corners(__fadd_rn(bx, __fdiv_rn(__fmul_rn(t0.x, 2.f), wm1)), __fadd_rn(by, __fdiv_rn(__fmul_rn(t0.y, 2.f), hm1)), p.h, p.w, p.wp);
+        cs[tid] = make_corners(__fadd_rn(bx, __fdiv_rn(__fmul_rn(t0.z, 2.f), wm1)), __fadd_rn(by, __fdiv_rn(__fmul_rn(t0.w, 2.f), hm1)), p.h, p.w, p.wp);
+        *reinterpret_cast<float4*>(rt + tid * 4) = t1;
+      } else {
+        Corner4 z;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { z.off[q] = -1; z.wt[q] = 0.f; }
+        cx[tid] = z; cs[tid] = z;
+        *reinterpret_cast<float4*>(rt + tid * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    __syncthreads();
+    // ---- P1: bilinear gathers, (pixel, 8-channel chunk) per thread-iteration: 8 lanes read one 128-byte pixel row
+    const __nv_bfloat16* xs = p.lr + (static_cast<long>(p.x_slot) * p.batch + n) * lr_img;
+    const __nv_bfloat16* ss = p.lr + (static_cast<long>(p.sta_slot) * p.batch + n) * lr_img;
+#pragma unroll 2
+    for (int it = 0; it < 4; ++it) {
+      const int id = it * kFusedThreads + tid;
+      const int lp = id >> 3, chunk = id & 7;
+      float a[8], b[8];
+      gather8(xs, cx[lp], chunk, a);
+      gather8(ss, cs[lp], chunk, b);
+      *reinterpret_cast<uint4*>(sF + swz(lp, chunk)) = pack8(a);
+      *reinterpret_cast<uint4*>(sS + swz(lp, chunk)) = pack8(b);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    // ---- P2: U = F Wc^T   (M 128, N 32, K 64)
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tU, make_desc64(hi, loF + 2 * k), make_desc64(hi, loWc + 2 * k), umma_idesc_bf16(32), k ? 1u : 0u);
+        umma_commit(bar);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar, phase); phase ^= 1;
+    tc_fence_after();
+    // ---- P3: routing in registers -> V tile (warps 0-3)
+    if (half == 0) {
+      uint32_t u0[16], u1[16];
+      tmem_ld16(tU + lane_addr, u0);
+      tmem_ld16(tU + lane_addr + 16, u1);
+      tmem_ld_wait();
+      const float4 r = *reinterpret_cast<const float4*>(rt + row * 4);
+      float tk[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        tk[k] = r.x * __uint_as_float(u0[k]) + r.y * __uint_as_float(u0[8 + k]) + r.z * __uint_as_float(u1[k]) + r.w * __uint_as_float(u1[8 + k]);
+      const float re[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = re[e] * tk[k];
+        *reinterpret_cast<uint4*>(sV + swz(row, e)) = pack8(v);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    // ---- P4: O = V We^T   (M 128, N 64, K 32)
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) umma_bf16(tO, make_desc64(hi, loV + 2 * k), make_desc64(hi, loWe + 2 * k), umma_idesc_bf16(64), k ? 1u : 0u);
+        umma_commit(bar);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar, phase); phase ^= 1;
+    tc_fence_after();
+    // ---- P5: fea = O + F, in place over the F tile (each warp: 32 rows x 32 columns)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      uint32_t o[16];
+      tmem_ld16(tO + lane_addr + half * 32 + 16 * j, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
+        uint4* ptr = reinterpret_cast<uint4*>(sF + swz(row, half * 4 + 2 * j + c2));
+        const uint4 f = *ptr;
+        float v[8];
+        v[0] = __uint_as_float(o[8 * c2 + 0]) + bf16_lo(f.x); v[1] = __uint_as_float(o[8 * c2 + 1]) + bf16_hi(f.x);
+        v[2] = __uint_as_float(o[8 * c2 + 2]) + bf16_lo(f.y); v[3] = __uint_as_float(o[8 * c2 + 3]) + bf16_hi(f.y);
+        v[4] = __uint_as_float(o[8 * c2 + 4]) + bf16_lo(f.z); v[5] = __uint_as_float(o[8 * c2 + 5]) + bf16_hi(f.z);
+        v[6] = __uint_as_float(o[8 * c2 + 6]) + bf16_lo(f.w); v[7] = __uint_as_float(o[8 * c2 + 7]) + bf16_hi(f.w);
+        *ptr = pack8(v);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    // ---- P6: Y = [S | fea] Wf^T   (M 128, N 64, K 128)
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tY, make_desc64(hi, loS + 2 * k), make_desc64(hi, loWf + 2 * k), umma_idesc_bf16(64), k ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tY, make_desc64(hi, loF + 2 * k), make_desc64(hi, loWf + 512 + 2 * k), umma_idesc_bf16(64), 1u);
+        umma_commit(bar);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar, phase); phase ^= 1;
+    tc_fence_after();
+    // ---- P7: + bias -> bf16 HR feature (each thread: one pixel, 32 channels = 64 contiguous bytes)
+    {
+      const long pix = pix0 + row;
+      const bool valid = pix < NPIX;
+      uint4* d = reinterpret_cast<uint4*>(p.hr + ((static_cast<long>(p.dst_slot) * p.batch + n) * NPIX + pix) * kC + half * 32);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        uint32_t y[16];
+        tmem_ld16(tY + lane_addr + half * 32 + 16 * j, y);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int c2 = 0; c2 < 2; ++c2) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(y[8 * c2 + e]) + sbias[half * 32 + 16 * j + 8 * c2 + e];
+            d[2 * j + c2] = pack8(v);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();   // the next tile overwrites cx/cs and the F/S/V tiles
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<256>(tm); }
+}
+
 constexpr size_t kGatherSmem = sizeof(float) * (kGatherPix * kFStride + 64 * 32 + 32 * 64 + kGatherPix * 4) + 2 * kGatherPix * sizeof(Corner4);
 
 }  // namespace savsr
@@ -377,6 +622,35 @@ extern "C" int savsr_satu_gather(savsr_ctx* ctx, savsr_arena* lr, int x_slot, in
   const long npix = static_cast<long>(p.H) * p.W;
   satu_gather_kernel<<<dim3(static_cast<unsigned>((npix + kGatherPix - 1) / kGatherPix), lr->batch), kGatherPix, kGatherSmem,
                        static_cast<cudaStream_t>(st)>>>(p);
+  SAVSR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int savsr_satu_fused(savsr_ctx* ctx, savsr_arena* lr, int x_slot, int sta_slot, int h, int w, savsr_arena* hr, int dst_slot,
+                                const float* table, const float* base_y, const float* base_x, const void* w_compress,
+                                const void* w_expand, const void* w_fusion, const float* fusion_bias, savsr_stream st) {
+  SAVSR_REQUIRE(ctx && lr && hr && table && base_y && base_x && w_compress && w_expand && w_fusion && fusion_bias, "savsr_satu_fused: null pointer");
+  SAVSR_REQUIRE(lr->batch == hr->batch, "savsr_satu_fused: LR batch %d != HR batch %d", lr->batch, hr->batch);
+  SAVSR_REQUIRE(x_slot >= 0 && x_slot < lr->nslots && sta_slot >= 0 && sta_slot < lr->nslots, "savsr_satu_fused: LR slot out of range");
+  SAVSR_REQUIRE(dst_slot >= 0 && dst_slot < hr->nslots, "savsr_satu_fused: HR slot out of range");
+  SAVSR_REQUIRE(h >= 2 && w >= 2 && h <= lr->height && w <= lr->width, "savsr_satu_fused: region %dx%d exceeds LR arena", h, w);
+  if (lr->batch == 0) return 0;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SAVSR_CUDA(cudaFuncSetAttribute(satu_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
+    attr_done = true;
+  }
+  FusedParams p;
+  p.lr = lr->base; p.hr = hr->base; p.table = table; p.base_y = base_y; p.base_x = base_x;
+  p.w_compress = static_cast<const uint8_t*>(w_compress); p.w_expand = static_cast<const uint8_t*>(w_expand);
+  p.w_fusion = static_cast<const uint8_t*>(w_fusion); p.bias = fusion_bias;
+  p.batch = lr->batch; p.hp = lr->height; p.wp = lr->width; p.h = h; p.w = w; p.H = hr->height; p.W = hr->width;
+  p.x_slot = x_slot; p.sta_slot = sta_slot; p.dst_slot = dst_slot;
+  const long npix = static_cast<long>(p.H) * p.W;
+  p.tiles_per_img = static_cast<int>((npix + 127) / 128);
+  const int total = p.batch * p.tiles_per_img;
+  const int grid = total < 2 * ctx->sm_count ? total : 2 * ctx->sm_count;
+  satu_fused_kernel<<<grid, kFusedThreads, kFusedSmem, static_cast<cudaStream_t>(st)>>>(p);
   SAVSR_CUDA(cudaGetLastError());
   return 0;
 }

@@ -280,8 +280,8 @@ class Plan:
         self.arena_lr_t = self._buf(self.n_lr_slots * B, self.hp, self.wp, 64, dtype=torch.bfloat16)
         self.arena_lr_t[zero * B:(zero + 1) * B].zero_()
         self.lr = K.Arena(self.ctx, self.arena_lr_t.data_ptr(), self.n_lr_slots, B, self.hp, self.wp)
-        self.arena_hr_t = self._buf(3 * B, self.H, self.W, 64, dtype=torch.bfloat16)
-        self.hr = K.Arena(self.ctx, self.arena_hr_t.data_ptr(), 3, B, self.H, self.W)
+        self.arena_hr_t = self._buf(B, self.H, self.W, 64, dtype=torch.bfloat16)          # fused HR feature only
+        self.hr = K.Arena(self.ctx, self.arena_hr_t.data_ptr(), 1, B, self.H, self.W)
         lr, hr = self.lr, self.hr
         self.x_in = self._buf(B, t, 3, self.h, self.w)
         self.out = self._buf(B, 3, self.H, self.W)
@@ -426,14 +426,20 @@ class Plan:
                                      self.rel_y.data_ptr(), self.rel_x.data_ptr(), self.cell_y.data_ptr(), self.cell_x.data_ptr(),
                                      self.base_y.data_ptr(), self.base_x.data_ptr(), self.corner_y.data_ptr(),
                                      self.corner_x.data_ptr(), self.table.data_ptr(), torch.cuda.current_stream().cuda_stream))
-        tab, by, bx, swr = self.table.data_ptr(), self.base_y.data_ptr(), self.base_x.data_ptr(), C.byref(sw)
-        self._emit(lambda st: lib.savsr_satu_gather(ctx, lrh, TR, STA, hh, ww, hrh, 0, 1, tab, by, bx, swr, st), kind="satu_gather")
-        self._conv(hr, [self._group([0, 1], 2, self._packp(u + ".fusion.weight"), self._ptr(u + ".fusion.bias"))], ksize=1)
-        self._tap("satu_out", "hr", 2)
+        tab, by, bx = self.table.data_ptr(), self.base_y.data_ptr(), self.base_x.data_ptr()
+        # HR stage: gather + routed experts + 128->64 fusion in one tensor-core kernel (savsr_arch.py:364-374)
+        wc_all = self._p(u + ".weight_compress").reshape(32, 64, 1, 1)                               # rows e*8+k
+        we_all = torch.zeros(64, 64, 1, 1, device=self.device)
+        we_all[:, :32, 0, 0] = self._p(u + ".weight_expand").view(4, 64, 8).permute(1, 0, 2).reshape(64, 32)   # cols e*8+k
+        pwc, pwe, pwf = self._pack(wc_all, n_tile=16), self._pack(we_all), self._packp(u + ".fusion.weight")
+        fb = self._ptr(u + ".fusion.bias")
+        self._emit(lambda st: lib.savsr_satu_fused(ctx, lrh, TR, STA, hh, ww, hrh, 0, tab, by, bx, pwc, pwe, pwf, fb, st),
+                   kind="satu_fused", flops=2.0 * B * self.H * self.W * (64 * 32 + 32 * 64 + 128 * 64))
+        self._tap("satu_out", "hr", 0)
         skip = K.RgbSkip(); skip.x = xin; skip.t = t; skip.centre = t // 2; skip.h = self.h; skip.w = self.w
         self._keep.append(skip)
         bt = torch.zeros(16, device=self.device); bt[:3] = self._p("tail.bias")
-        self._conv(hr, [self._group([2], 0, self._pack(self._p("tail.weight"), n_tile=16, co_pad=16), self._dev(bt),
+        self._conv(hr, [self._group([0], 0, self._pack(self._p("tail.weight"), n_tile=16, co_pad=16), self._dev(bt),
                                     aux=self.out.data_ptr())], n_tile=16, dst_mode=K.DST_RGB, skip=skip)
         torch.cuda.current_stream().synchronize()
 

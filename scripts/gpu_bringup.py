@@ -45,6 +45,8 @@ CHECKS = {
     "satu_table": "check_satu_table()",
     "satu_sta": "check_satu_sta()",
     "satu_gather": "check_satu_gather()",
+    "satu_fused": "check_satu_fused()",
+    "satu_fused_x4": "check_satu_fused(B=1, h=16, w=20, scale=(4, 4), seed=2)",
     "forward_check_impl": "check_forward(b=1, h=16, w=20, scale=(2, 2), impl='check')",
     "forward_tap": "check_forward(b=1, h=16, w=20, scale=(2, 2), impl='tap')",
     "forward_tap_odd_b2": "check_forward(b=2, h=13, w=15, scale=(1.5, 4), sd_seed=1, in_seed=1236, impl='tap')",

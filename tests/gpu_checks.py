@@ -475,6 +475,36 @@ def check_satu_gather(B=2, h=13, w=15, scale=(2.7, 1.5), seed=1):
     return dict(sta_sampled=assert_close("gather sta", hr.get(0), sta_s), fea=assert_close("gather fea", hr.get(1), fea))
 
 
+def check_satu_fused(B=2, h=13, w=15, scale=(2.7, 1.5), seed=1):
+    """Tensor-core HR stage (gather + experts + fusion conv) vs the oracle (savsr_arch.py:364-374)."""
+    from oracle import savsr_oracle as O
+    from oracle.state_dict_fixture import make_state_dict
+    sd = make_state_dict(seed)
+    sd["upsample.offset.weight"] = sd["upsample.offset.weight"] * 8
+    sd["upsample.st_offset.weight"] = sd["upsample.st_offset.weight"] * 8
+    torch.manual_seed(seed)
+    hp, wp = h + (h & 1), w + (w & 1)
+    res, H, W = satu_index(h, w, scale, sd)
+    lr = ArenaBox(2, B, hp, wp)
+    hr = ArenaBox(1, B, H, W)
+    x = bf16_round(torch.randn(B, 64, hp, wp, device=DEV)); sta = bf16_round(torch.randn(B, 64, hp, wp, device=DEV))
+    lr.put(0, x); lr.put(1, sta)
+    table = res["table"].to(DEV); by = torch.from_numpy(res["base_y"]).to(DEV); bx = torch.from_numpy(res["base_x"]).to(DEV)
+    wc_all = sd["upsample.weight_compress"].reshape(32, 64, 1, 1)
+    we_all = torch.zeros(64, 64, 1, 1)
+    we_all[:, :32, 0, 0] = sd["upsample.weight_expand"].view(4, 64, 8).permute(1, 0, 2).reshape(64, 32)
+    pwc, pwe, pwf = pack_weight(wc_all, n_tile=16), pack_weight(we_all), pack_weight(sd["upsample.fusion.weight"])
+    fb = sd["upsample.fusion.bias"].to(DEV).contiguous()
+    K.check(K.load().savsr_satu_fused(ctx().handle, lr.a.handle, 0, 1, h, w, hr.a.handle, 0, table.data_ptr(), by.data_ptr(), bx.data_ptr(),
+                                      pwc.data_ptr(), pwe.data_ptr(), pwf.data_ptr(), fb.data_ptr(), _stream()))
+    off, st_off, r = O.satu_heads(sd, "upsample", h, w, scale)
+    xc, sc = x[..., :h, :w].cpu(), sta[..., :h, :w].cpu()
+    fea = O.satu_expert_mix(sd, "upsample", O.satu_gather(xc, scale, off), r)
+    sta_s = O.satu_gather(sc, scale, st_off)
+    ref = F.conv2d(torch.cat([sta_s, fea], 1), sd["upsample.fusion.weight"], sd["upsample.fusion.bias"])
+    return dict(fused=assert_close("satu fused", hr.get(0), ref, rel=2.0 ** -6, abs_=0.02))
+
+
 # ------------------------------------------------------------------------------------------------ whole forward
 TAPS = ("f2p_last", "p2f_last", "align", "rg0", "rg3", "trunk", "satu_sta", "satu_out")
 

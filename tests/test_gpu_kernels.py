@@ -76,3 +76,8 @@ def test_satu_sta(G):
 
 def test_satu_gather(G):
     G.check_satu_gather()
+
+
+def test_satu_fused_tensor_core_hr_stage(G):
+    G.check_satu_fused()
+    G.check_satu_fused(B=1, h=16, w=20, scale=(4, 4), seed=2)

@@ -31,15 +31,16 @@ def test_launch_census(recorded):
     build_time = names.count("savsr_pack_conv_weight")
     # distinct conv weights: l1 2*(4*3 conv0 + 1 conv1 + 4*3 conv2 + merge) + l2 (5 + 2*(5+5) + 1 + 1) + RG 4*(16+1)
     # + mask.0 x4 + conv_last + kernel_conv + fusion + tail + zero-expanded first-layer filters (5 iterations x 2 dirs x 2)
-    assert build_time == 2 * (12 + 1 + 12 + 1) + (5 + 20 + 1 + 1) + 68 + 4 + 1 + 1 + 1 + 1 + 20
+    # + the stacked compress / expand expert matrices
+    assert build_time == 2 * (12 + 1 + 12 + 1) + (5 + 20 + 1 + 1) + 68 + 4 + 1 + 1 + 1 + 1 + 20 + 2
     run = names[names.index("savsr_satu_index") + 1:] if False else names
     assert names.count("savsr_pack_frames") == 1 and names.count("savsr_front_conv") == 0
     assert names.count("savsr_ca_scale_residual") == 32              # 4 groups x 8 RCAB
     assert names.count("savsr_osadapt_mask") == 4
     assert names.count("savsr_osa_prologue") == 5 * 3 + 2 + 4        # l1 blocks 1-3 (both dirs batched), l2 x2, adapt x4
-    assert names.count("savsr_satu_sta") == 1 and names.count("savsr_satu_gather") == 1
+    assert names.count("savsr_satu_sta") == 1 and names.count("savsr_satu_fused") == 1
     # conv launches: l1 5*(first layer + 4*3 + 1) + l2 (1 + 2*3 + 1 + 1) + RG 4*(16 + 1 + mask + adapt) + conv_last + kernel_conv + fusion + tail
-    assert names.count("savsr_conv") == 5 * 14 + 9 + 4 * 19 + 1 + 1 + 1 + 1
+    assert names.count("savsr_conv") == 5 * 14 + 9 + 4 * 19 + 1 + 1 + 1
 
 
 def test_no_conv_writes_a_slot_it_reads(recorded):
@@ -83,9 +84,9 @@ def test_slots_written_before_read_and_hidden_states_persist(recorded):
             arena = id(args[1])
             assert all((arena, args[3] + t) in written for t in range(25)) and (arena, args[2]) in written
             written[(arena, args[4])] = idx
-        elif name == "savsr_satu_gather":
+        elif name == "savsr_satu_fused":
+            assert (id(args[1]), args[2]) in written and (id(args[1]), args[3]) in written
             written[(id(args[6]), args[7])] = idx
-            written[(id(args[6]), args[8])] = idx
     assert zero_reads > 0                          # first iteration of both directions starts from zeros
 
 
