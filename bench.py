@@ -206,8 +206,7 @@ def main():
         # public API, host buffers: H2D of the LR clip, window gather + forward per batch, D2H of the HR frames
         clip = clip_host.to(dev, non_blocking=True)
         with torch.no_grad():
-            y = sharding.infer_clip(net, clip, batch=B)
-        out_host.copy_(y, non_blocking=True)
+            sharding.infer_clip(net, clip, batch=B, out=out_host)      # D2H of batch i overlaps the forward of batch i+1
         torch.cuda.current_stream().synchronize()
 
     def barrier():
@@ -274,7 +273,7 @@ def main():
         "e2e": {"value": round(e2e, 2), "unit": "HR Mpix/s", "ms_per_step": round(ms_e2e / args.steps, 3),
                 "h2d_bytes_per_step": clip_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4,
                 "api": "savsr_b200.sharding.infer_clip(savsr_b200.SAVSR, clip)"},
-        "gpu_launches": launches_per_step * args.steps,
+        "gpu_launches": launches_per_step * args.steps * world,
         "clocks": clocks,
         "roofline": roofline,
     }

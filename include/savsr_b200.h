@@ -180,10 +180,11 @@ int savsr_osa_prologue(savsr_ctx* ctx, const savsr_osa_params* convs, int nconvs
 /* test hook: per sample, scratch + 4*ci + 8 holds the attention vectors [ca(ci) | fa(co) | sa(9) | ka(8)] */
 
 /* ---- RCAB channel attention (savsr_arch.py:514-524, 547-549) --------------------------------------
- * y = sigmoid(W2 relu(W1 mean(t) + b1) + b2) ; dst = x + t * y        (t, x, dst: arena slots)   */
+ * y = sigmoid(W2 relu(W1 mean(t) + b1) + b2) ; dst = x + t * y        (t, x, dst: arena slots)
+ * Two launches: the per-sample channel-scale vector, then the streaming pass.                      */
 int savsr_ca_scale_residual(savsr_ctx* ctx, savsr_arena* arena, int t_slot, int x_slot, int dst_slot,
                             const float* pool, int npart, const float* w1, const float* b1,
-                            const float* w2, const float* b2, savsr_stream st);
+                            const float* w2, const float* b2, float* y_scratch /* [batch][64] */, savsr_stream st);
 
 /* ---- OSAdapt mask tail (savsr_arch.py:193-205) ------------------------------------------------------
  * in16: [batch][H*W][16] fp32 = ReLU(BN(conv64->16(x))) from savsr_conv(AUX16).  Runs AvgPool2d(2),

@@ -25,6 +25,7 @@
 // The CUDA-core kernel at the bottom implements the same contract with plain loads and shares the
 // epilogue; it exists only as an on-device checker for the TMA/UMMA main loop (tests, bring-up).
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -530,6 +531,201 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
   }
 }
 
+// ------------------------------------------------------------------------------------------------ big-K variant
+// Convs whose weights do not fit the resident region (K > 18 blocks: OSA 192->64 / 320->64, merge 192->64, 320->128).
+// Loop order is source-major over a BATCH of up to 4 tiles: the 9 K-blocks of one source are loaded once per batch
+// (two 72 KB sets, double buffered) and used for every tile of the batch, each tile accumulating in its own TMEM
+// buffer (2 x 4 accumulators of 64 columns = all 512 TMEM columns, so the epilogue of batch b overlaps batch b+1).
+// Weight traffic per tile drops 4x versus streaming per tile and no per-tap waits remain on the issue path.
+constexpr int kBatchTiles = 4;
+
+__global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_bigk_kernel(const __grid_constant__ ConvParams p) {
+  constexpr int BN = 64, NT = 9;
+  constexpr int kBBytes = BN * 128;
+  constexpr int kAStage = kHaloStageBytes, kAStages = 3;
+  constexpr int kSetBlocks = 9, kSetBytes = kSetBlocks * kBBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kARegionBytes;   // two sets of 9 K-blocks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + 2 * kSetBytes);
+  uint64_t* a_full = bars;                       // [4]
+  uint64_t* a_empty = a_full + kMaxAStages;      // [4]
+  uint64_t* set_full = a_empty + kMaxAStages;    // [2]
+  uint64_t* set_empty = set_full + 2;            // [2]
+  uint64_t* t_full = set_empty + 2;              // [8]
+  uint64_t* t_empty = t_full + 2 * kBatchTiles;  // [8]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2 * kBatchTiles);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles = p.tiles_x * p.tiles_y;
+  const int total = p.ngroups * p.batch * tiles;
+  const int item_begin = blockIdx.x * p.chunk;
+  const int item_end = min(item_begin + p.chunk, total);
+  const int nsrc = p.nsrc;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&p.tm_halo);
+    for (int i = 0; i < kMaxAStages; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(set_full + i, 1); mbar_init(set_empty + i, 1); }
+    for (int i = 0; i < 2 * kBatchTiles; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // every role walks the same sequence of batches: up to 4 consecutive tiles of one (conv, sample)
+  int item = item_begin;
+  int tile = item_begin % tiles;
+  int gn = item_begin / tiles;
+  int bcount = 0;
+  uint32_t use_bits = 0;  // per accumulator: parity of how many times it has been used
+
+  if (warp == 0) {
+    // ================================ TMA producer (one thread) ================================
+    if (lane == 0) {
+      int sa = 0, pa = 0;
+      uint32_t u = 0;
+      while (item < item_end) {
+        const int cnt = min(kBatchTiles, min(item_end - item, tiles - tile));
+        const int n = gn % p.batch;
+        const savsr_conv_group& g = p.g[gn / p.batch];
+        const uint8_t* wptr = static_cast<const uint8_t*>(g.weight) + static_cast<long>(n) * g.weight_sample_stride;
+        for (int s = 0; s < nsrc; ++s, ++u) {
+          const int set = u & 1;
+          mbar_wait(set_empty + set, ((u >> 1) & 1) ^ 1);
+          mbar_expect_tx(set_full + set, kSetBytes);
+          int kb = blockIdx.x % kSetBlocks;  // rotated issue order across CTAs
+          for (int i = 0; i < kSetBlocks; ++i) {
+            bulk_load(smem_b + set * kSetBytes + kb * kBBytes, wptr + static_cast<long>(s * NT + kb) * kBBytes, kBBytes, set_full + set);
+            if (++kb == kSetBlocks) kb = 0;
+          }
+          const int img = g.src_slot[s] * p.batch + n;
+          for (int j = 0; j < cnt; ++j) {
+            const int tj = tile + j;
+            const int ty = tj / p.tiles_x;
+            mbar_wait(a_empty + sa, pa ^ 1);
+            mbar_expect_tx(a_full + sa, kHaloPitch * (kTileH + 2) * 128u);
+            tma_load_4d(smem_a + sa * kAStage, &p.tm_halo, a_full + sa, 0, (tj - ty * p.tiles_x) * kTileW - 1, ty * kTileH - 1, img);
+            if (++sa == kAStages) { sa = 0; pa ^= 1; }
+          }
+        }
+        item += cnt; tile += cnt;
+        if (tile == tiles) { tile = 0; ++gn; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (warp-uniform, elected issue) ================================
+    constexpr uint32_t idesc = umma_idesc_bf16(BN);
+    constexpr uint32_t a_hi = desc_hi(kHaloPitch * 128u);
+    constexpr uint32_t b_hi = desc_hi(1024u);
+    const uint32_t a_lo0 = (smem_u32(smem_a) >> 4) & 0x3fffu;
+    const uint32_t b_lo0 = (smem_u32(smem_b) >> 4) & 0x3fffu;
+    int sa = 0, pa = 0;
+    uint32_t u = 0;
+    while (item < item_end) {
+      const int cnt = min(kBatchTiles, min(item_end - item, tiles - tile));
+      const int bb = bcount & 1;
+#pragma unroll
+      for (int j = 0; j < kBatchTiles; ++j) {
+        if (j < cnt) mbar_wait(t_empty + bb * kBatchTiles + j, ((use_bits >> (bb * kBatchTiles + j)) & 1u) ^ 1u);
+      }
+      tc_fence_after();
+      for (int s = 0; s < nsrc; ++s, ++u) {
+        const int set = u & 1;
+        mbar_wait(set_full + set, (u >> 1) & 1);
+        tc_fence_after();
+        const uint32_t bl0 = b_lo0 + set * (kSetBytes >> 4);
+#pragma unroll
+        for (int j = 0; j < kBatchTiles; ++j) {
+          if (j < cnt) {
+            mbar_wait(a_full + sa, pa);
+            tc_fence_after();
+            const uint32_t al0 = a_lo0 + sa * (kAStage >> 4);
+            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((bb * kBatchTiles + j) * BN);
+            if (elect_one()) {
+#pragma unroll
+              for (int tap = 0; tap < NT; ++tap) {
+                const uint32_t al = al0 + ((tap / 3) * kHaloPitch + tap % 3) * 8;
+                const uint32_t bl = bl0 + tap * (kBBytes >> 4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(d_tmem, make_desc(a_hi, al + 2 * k), make_desc(b_hi, bl + 2 * k), idesc, (s | tap | k) ? 1u : 0u);
+              }
+              umma_commit(a_empty + sa);
+            }
+            __syncwarp();
+            if (++sa == kAStages) { sa = 0; pa ^= 1; }
+          }
+        }
+        if (elect_one()) umma_commit(set_empty + set);
+        __syncwarp();
+      }
+      if (elect_one()) {
+#pragma unroll
+        for (int j = 0; j < kBatchTiles; ++j)
+          if (j < cnt) umma_commit(t_full + bb * kBatchTiles + j);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < kBatchTiles; ++j)
+        if (j < cnt) use_bits ^= 1u << (bb * kBatchTiles + j);
+      ++bcount;
+      item += cnt; tile += cnt;
+      if (tile == tiles) { tile = 0; ++gn; }
+    }
+  } else {
+    // ================================ epilogue warps ================================
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int NC = 32;
+    EpiCtx<NC> ec;
+    ec.bias_group = -1;
+    while (item < item_end) {
+      const int cnt = min(kBatchTiles, min(item_end - item, tiles - tile));
+      const int bb = bcount & 1;
+      const int n = gn % p.batch;
+      const int gi = gn / p.batch;
+      const savsr_conv_group& g = p.g[gi];
+      for (int j = 0; j < cnt; ++j) {
+        const int acc = bb * kBatchTiles + j;
+        epi_prefetch<NC>(p, g, gi, n, tile + j, quad, lane, half * 32, ec);
+        mbar_wait(t_full + acc, (use_bits >> acc) & 1u);
+        use_bits ^= 1u << acc;
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN + half * 32);
+        float v[NC];
+#pragma unroll
+        for (int q = 0; q < NC / 16; ++q) {
+          uint32_t r[16];
+          tmem_ld16(taddr + q * 16, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) v[q * 16 + c] = __uint_as_float(r[c]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t_empty + acc);
+        epi_finish<NC>(p, g, n, tile + j, quad, lane, v, half * 32, ec);
+      }
+      ++bcount;
+      item += cnt; tile += cnt;
+      if (tile == tiles) { tile = 0; ++gn; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ checker kernel
 // One block of 128 threads per (conv, sample, tile); thread m accumulates all N outputs of its pixel with
 // plain loads, reading the same packed (swizzled) weights.  Same epilogue.  Slow by design.
@@ -649,6 +845,22 @@ static int launch_conv(savsr_ctx* ctx, ConvParams& p, int impl, cudaStream_t st)
     return 0;
   }
   if (p.ntaps == 1) return launch_igemm<BN, 1, false>(ctx, p, total, st);
+  if constexpr (BN == 64) {
+    static const bool bigk_all = getenv("SAVSR_BIGK_ALL") != nullptr && atoi(getenv("SAVSR_BIGK_ALL")) != 0;
+    if (p.halo && (bigk_all || p.nsrc * p.ntaps > kBBlocks)) {
+      const size_t smem = 1024 + kARegionBytes + kBBlocks * BN * 128 + 512;
+      static bool attr_done = false;
+      if (!attr_done) {
+        SAVSR_CUDA(cudaFuncSetAttribute(conv_igemm_bigk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        attr_done = true;
+      }
+      p.chunk = (total + ctx->sm_count - 1) / ctx->sm_count;
+      const int grid = (total + p.chunk - 1) / p.chunk;
+      conv_igemm_bigk_kernel<<<grid, kNumThreads, smem, st>>>(p);
+      SAVSR_CUDA(cudaGetLastError());
+      return 0;
+    }
+  }
   if (p.halo) return launch_igemm<BN, 3, true>(ctx, p, total, st);
   return launch_igemm<BN, 3, false>(ctx, p, total, st);
 }

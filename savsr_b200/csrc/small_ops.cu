@@ -114,27 +114,32 @@ __host__ __device__ inline int osa_off_h1(int ci) { return ci + 8; }
 __host__ __device__ inline int osa_off_v2(int ci) { return 3 * ci + 8; }
 __host__ __device__ inline int osa_off_att(int ci) { return 4 * ci + 8; }
 
-// vin = [1/s_h, 1/s_w, mean(x)] (savsr_arch.py:143-146).  grid (nsrc_max, batch, nconvs), 256 threads.
-__global__ void __launch_bounds__(256) osa_pool_kernel(const __grid_constant__ OsaLaunch L) {
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// vin = [1/s_h, 1/s_w, mean(x)] (savsr_arch.py:143-146), mean from the producers' partial sums.
+// grid (nsrc_max, batch, nconvs), 1024 threads = 16 partial ranges x 64 channels.
+constexpr int kOsaThreads = 1024;
+__global__ void __launch_bounds__(kOsaThreads) osa_pool_kernel(const __grid_constant__ OsaLaunch L) {
   const savsr_osa_params& c = L.c[blockIdx.z];
   const int s = blockIdx.x, n = blockIdx.y;
   if (s * 64 >= c.ci) return;
-  __shared__ float red[4][64];
+  __shared__ float red[16][64];
   const int ch = threadIdx.x & 63, part = threadIdx.x >> 6;
   const float* src = c.pool[s] + static_cast<long>(n) * L.npart * kC;
-  float acc = 0.f;
-  for (int q = part; q < L.npart; q += 4) acc += src[q * kC + ch];
-  red[part][ch] = acc;
+  float a0 = 0.f, a1 = 0.f;
+  int q = part;
+  for (; q + 16 < L.npart; q += 32) { a0 += src[q * kC + ch]; a1 += src[(q + 16) * kC + ch]; }
+  if (q < L.npart) a0 += src[q * kC + ch];
+  red[part][ch] = a0 + a1;
   __syncthreads();
   float* vin = c.scratch + static_cast<long>(n) * osa_scratch_stride(c.ci);
   if (part == 0) {
-    const float sum = (red[0][ch] + red[1][ch]) + (red[2][ch] + red[3][ch]);
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) sum += red[k][ch];
     vin[2 + s * 64 + ch] = sum / static_cast<float>(L.npix);
   }
-  if (s == 0 && threadIdx.x == 0) {
-    vin[0] = L.inv_h;
-    vin[1] = L.inv_w;
-  }
+  if (s == 0 && threadIdx.x == 0) { vin[0] = L.inv_h; vin[1] = L.inv_w; }
 }
 
 // One Linear + ReLU layer of scale_routing (savsr_arch.py:123-128).  layer 0: [2ci][ci+2], layer 1: [ci][2ci].
@@ -160,8 +165,6 @@ __global__ void __launch_bounds__(256) osa_linear_kernel(const __grid_constant__
     if (lane == 0) c.scratch[static_cast<long>(n) * osa_scratch_stride(c.ci) + out_off + row] = fmaxf(acc + B[row], 0.f);
   }
 }
-
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 // ScaleAttention (savsr_arch.py:91-96): z = ReLU(BN(fc v)); ca/fa/sa = sigmoid heads; ka = softmax head (T = 1).
 // grid (batch, nconvs), 256 threads.
@@ -248,24 +251,30 @@ struct CaParams {
   __nv_bfloat16* dst;
   const float* pool;
   const float *w1, *b1, *w2, *b2;
+  float* y;      // [batch][64] channel scales (scratch)
   int npart;
   long npix;
 };
-// grid (blocks, batch), 256 threads.  Every block recomputes the 64 -> 4 -> 64 MLP (a few kFLOP) from the
-// producer's partial sums, then streams its share of  dst = x + t * y  as 16-byte chunks.
-__global__ void __launch_bounds__(256) ca_scale_residual_kernel(const CaParams p) {
-  __shared__ float red[4][64];
+// y = sigmoid(W2 relu(W1 mean(t) + b1) + b2) per sample (savsr_arch.py:514-519).  grid (batch), 1024 threads.
+__global__ void __launch_bounds__(1024) ca_vector_kernel(const CaParams p) {
+  __shared__ float red[16][64];
   __shared__ float mean[64];
   __shared__ float hid[4];
-  __shared__ float ys[64];
-  const int n = blockIdx.y;
+  const int n = blockIdx.x;
   const int ch = threadIdx.x & 63, part = threadIdx.x >> 6;
   const float* src = p.pool + static_cast<long>(n) * p.npart * kC;
-  float acc = 0.f;
-  for (int q = part; q < p.npart; q += 4) acc += src[q * kC + ch];
-  red[part][ch] = acc;
+  float a0 = 0.f, a1 = 0.f;
+  int q = part;
+  for (; q + 16 < p.npart; q += 32) { a0 += src[q * kC + ch]; a1 += src[(q + 16) * kC + ch]; }
+  if (q < p.npart) a0 += src[q * kC + ch];
+  red[part][ch] = a0 + a1;
   __syncthreads();
-  if (part == 0) mean[ch] = ((red[0][ch] + red[1][ch]) + (red[2][ch] + red[3][ch])) / static_cast<float>(p.npix);
+  if (part == 0) {
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) sum += red[k][ch];
+    mean[ch] = sum / static_cast<float>(p.npix);
+  }
   __syncthreads();
   if (threadIdx.x < 4) {
     float a = p.b1[threadIdx.x];
@@ -277,8 +286,14 @@ __global__ void __launch_bounds__(256) ca_scale_residual_kernel(const CaParams p
     float a = p.b2[threadIdx.x];
 #pragma unroll
     for (int i = 0; i < 4; ++i) a += p.w2[threadIdx.x * 4 + i] * hid[i];
-    ys[threadIdx.x] = sigmoidf_(a);
+    p.y[n * 64 + threadIdx.x] = sigmoidf_(a);
   }
+}
+// dst = x + t * y (savsr_arch.py:524, 547-549), streamed as 16-byte chunks.  grid (blocks, batch), 256 threads.
+__global__ void __launch_bounds__(256) ca_scale_residual_kernel(const CaParams p) {
+  __shared__ float ys[64];
+  const int n = blockIdx.y;
+  if (threadIdx.x < 64) ys[threadIdx.x] = p.y[n * 64 + threadIdx.x];
   __syncthreads();
   const long chunks = p.npix * 8;
   const uint4* tt = reinterpret_cast<const uint4*>(p.t + static_cast<long>(n) * p.npix * kC);
@@ -475,7 +490,7 @@ extern "C" int savsr_osa_prologue(savsr_ctx* ctx, const savsr_osa_params* convs,
   }
   L.nconvs = nconvs; L.batch = batch; L.npart = npart; L.npix = npix;
   L.inv_h = inv_scale_h; L.inv_w = inv_scale_w;
-  osa_pool_kernel<<<dim3(max_ci / 64, batch, nconvs), 256, 0, st>>>(L);
+  osa_pool_kernel<<<dim3(max_ci / 64, batch, nconvs), kOsaThreads, 0, st>>>(L);
   osa_linear_kernel<<<dim3((2 * max_ci + 7) / 8, nconvs), 256, 0, st>>>(L, 0);
   osa_linear_kernel<<<dim3((max_ci + 7) / 8, nconvs), 256, 0, st>>>(L, 1);
   osa_attention_kernel<<<dim3(batch, nconvs), 256, 0, st>>>(L);
@@ -486,8 +501,8 @@ extern "C" int savsr_osa_prologue(savsr_ctx* ctx, const savsr_osa_params* convs,
 
 extern "C" int savsr_ca_scale_residual(savsr_ctx* ctx, savsr_arena* arena, int t_slot, int x_slot, int dst_slot,
                                        const float* pool, int npart, const float* w1, const float* b1, const float* w2,
-                                       const float* b2, savsr_stream st) {
-  SAVSR_REQUIRE(ctx && arena && pool && w1 && b1 && w2 && b2, "savsr_ca_scale_residual: null pointer");
+                                       const float* b2, float* y_scratch, savsr_stream st) {
+  SAVSR_REQUIRE(ctx && arena && pool && w1 && b1 && w2 && b2 && y_scratch, "savsr_ca_scale_residual: null pointer");
   SAVSR_REQUIRE(t_slot >= 0 && t_slot < arena->nslots && x_slot >= 0 && x_slot < arena->nslots && dst_slot >= 0 &&
                 dst_slot < arena->nslots, "savsr_ca_scale_residual: slot out of range");
   CaParams p;
@@ -496,11 +511,12 @@ extern "C" int savsr_ca_scale_residual(savsr_ctx* ctx, savsr_arena* arena, int t
   p.t = arena->base + t_slot * img;
   p.x = arena->base + x_slot * img;
   p.dst = arena->base + dst_slot * img;
-  p.pool = pool; p.npart = npart; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2;
+  p.pool = pool; p.npart = npart; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.y = y_scratch;
   long blocks = (p.npix * 8 + 255) / 256;
-  const long cap = 2L * ctx->sm_count / (arena->batch > 0 ? arena->batch : 1) + 1;
+  const long cap = 8L * ctx->sm_count / (arena->batch > 0 ? arena->batch : 1) + 1;
   if (blocks > cap) blocks = cap;
   if (arena->batch == 0) return 0;
+  ca_vector_kernel<<<arena->batch, 1024, 0, static_cast<cudaStream_t>(st)>>>(p);
   ca_scale_residual_kernel<<<dim3(static_cast<unsigned>(blocks), arena->batch), 256, 0, static_cast<cudaStream_t>(st)>>>(p);
   SAVSR_CUDA(cudaGetLastError());
   return 0;

@@ -350,6 +350,7 @@ class Plan:
         half0 = self._buf(B, (self.hp // 2) * (self.wp // 2), 16)
         half1 = self._buf(B, (self.hp // 2) * (self.wp // 2), 16)
         maskb = self._buf(B, self.hp * self.wp)
+        ca_y = self._buf(B, 64).data_ptr()
         npart = lr.tiles * 4
         lrh = lr.handle
         h_cur = A                                   # share_source / align_feat stay in slot A to the end
@@ -363,7 +364,8 @@ class Plan:
                 w1, b1 = self._ptr(pr + ".3.attention.1.weight"), self._ptr(pr + ".3.attention.1.bias")
                 w2, b2 = self._ptr(pr + ".3.attention.3.weight"), self._ptr(pr + ".3.attention.3.bias")
                 self._emit(lambda st, x=x, xa=xa, pl=pl, w1=w1, b1=b1, w2=w2, b2=b2:
-                           lib.savsr_ca_scale_residual(ctx, lrh, T2, x, xa, pl, npart, w1, b1, w2, b2, st), kind="ca_scale_residual")
+                           lib.savsr_ca_scale_residual(ctx, lrh, T2, x, xa, pl, npart, w1, b1, w2, b2, ca_y, st),
+                           launches=2, kind="ca_scale_residual")
                 x, xa, xb = xa, xb, xa
             plr = self._pool(f"RG.{gi}.conv")
             self._conv(lr, [self._group([x], R, self._packp(f"RG.{gi}.conv.weight"), self._ptr(f"RG.{gi}.conv.bias"),

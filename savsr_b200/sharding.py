@@ -47,14 +47,30 @@ def gather_windows(clip: torch.Tensor, frames: Sequence[int], num_frames: int = 
 
 
 def infer_clip(net: Callable[[torch.Tensor], torch.Tensor], clip: torch.Tensor, frames: Optional[Sequence[int]] = None,
-               batch: int = 1, num_frames: int = 7) -> torch.Tensor:
+               batch: int = 1, num_frames: int = 7, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Run `net` on the windows of `frames` (default: all), `batch` windows per forward.
-    Returns [len(frames), 3, H, W].  The last, ragged batch is run at its own size."""
+    Returns [len(frames), 3, H, W].  The last, ragged batch is run at its own size.
+    If `out` (e.g. a pinned host tensor) is given, each batch is copied into it on a side stream while the next
+    batch computes, and `out` is returned once all copies are enqueued behind the current stream."""
     frames = list(range(clip.shape[0])) if frames is None else list(frames)
+    copy_stream = torch.cuda.Stream(clip.device) if (out is not None and clip.is_cuda) else None
     outs = []
     for i in range(0, len(frames), batch):
         chunk = frames[i:i + batch]
-        outs.append(net(gather_windows(clip, chunk, num_frames)))
+        y = net(gather_windows(clip, chunk, num_frames))
+        if out is None:
+            outs.append(y)
+        elif copy_stream is None:
+            out[i:i + len(chunk)].copy_(y)
+        else:
+            copy_stream.wait_stream(torch.cuda.current_stream(clip.device))
+            with torch.cuda.stream(copy_stream):
+                out[i:i + len(chunk)].copy_(y, non_blocking=True)
+            y.record_stream(copy_stream)
+    if out is not None:
+        if copy_stream is not None:
+            torch.cuda.current_stream(clip.device).wait_stream(copy_stream)
+        return out
     if not outs:
         return torch.empty(0)
     return torch.cat(outs, 0)

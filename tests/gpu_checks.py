@@ -343,8 +343,9 @@ def check_ca(B=2, H=20, W=24, seed=7):
     parts = parts - parts.sum(1, keepdim=True) / npart + t.sum((2, 3)).unsqueeze(1) / npart     # partials summing to sum(t)
     w1 = torch.randn(4, 64, device=DEV) * 0.3; b1 = torch.randn(4, device=DEV) * 0.1
     w2 = torch.randn(64, 4, device=DEV) * 0.5; b2 = torch.randn(64, device=DEV) * 0.1
+    ysc = torch.empty(B, 64, device=DEV)
     K.check(K.load().savsr_ca_scale_residual(ctx().handle, ab.a.handle, 0, 1, 2, parts.data_ptr(), npart, w1.data_ptr(),
-                                             b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), _stream()))
+                                             b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), ysc.data_ptr(), _stream()))
     y = torch.sigmoid(F.relu(t.mean((2, 3)) @ w1.t() + b1) @ w2.t() + b2)
     ref = x + t * y.view(B, 64, 1, 1)
     return dict(ca=assert_close("ca_scale_residual", ab.get(2), ref))

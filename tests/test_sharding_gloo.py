@@ -40,6 +40,8 @@ def test_infer_clip_ragged_batches():
     for b in (1, 4, 5):
         assert torch.equal(sharding.infer_clip(fake_net, clip, batch=b), full)
     assert sharding.infer_clip(fake_net, clip, frames=[], batch=4).numel() == 0
+    out = torch.empty(11, 3, 12, 16)
+    assert sharding.infer_clip(fake_net, clip, batch=4, out=out) is out and torch.equal(out, full)
 
 
 def _worker(rank, world, port, n_frames, ret):
