@@ -1,0 +1,95 @@
+#!/usr/bin/env python
+"""Turn the raw artefacts of a gpurun trip (gpurun_out/) into the tracked summaries under profiles/.
+    python scripts/summarize_profiles.py r01
+Needs `ncu` (reads .ncu-rep without a GPU)."""
+import collections
+import csv
+import json
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "gpurun_out")
+P = os.path.join(ROOT, "profiles")
+
+
+def launches(tag):
+    path = os.path.join(G, f"launches_{tag}_bench.csv")
+    lines = [l for l in open(path) if not l.startswith("==")]
+    rows = [r for r in csv.DictReader(lines) if r.get("Metric Name") == "gpu__time_duration.sum"]
+    names = [re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "") for r in rows]
+    vals = [float(r["Metric Value"].replace(",", "")) for r in rows]
+    starts = [i for i, n in enumerate(names) if "pack_frames" in n]            # one per forward
+    # forwards: plan capture warm-up (1) + 3 warm-up steps x 2 + timed step (2) + e2e ...; take the timed step = forwards 7, 8
+    a, b = starts[7], starts[9]
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for n, v in zip(names[a:b], vals[a:b]):
+        agg[n][0] += 1
+        agg[n][1] += v
+    tot = sum(v for _, v in agg.values())
+    out = [f"# {tag}: ncu launch list of `bench.py --steps 1 --warmup 1` (one timed step = 2 forwards of 17 windows, Vid4 x4)", "",
+           "Command: `ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_%s_bench.csv "
+           "python bench.py --steps 1 --warmup 1 --no-cpu-baseline`" % tag,
+           "(per-launch times under ncu are serialised and cold-cache: compare SHARES with `roofline.share_of_step` / `per_kind_ms` of bench.py, not absolutes)", "",
+           f"kernel launches in the step: {b - a}, summed kernel time {tot / 1e6:.2f} ms", "",
+           "| kernel | launches | total ms | share | avg us |", "|---|---|---|---|---|"]
+    for k, (c, v) in sorted(agg.items(), key=lambda x: -x[1][1]):
+        out.append(f"| `{k[:90]}` | {c} | {v / 1e6:.3f} | {100 * v / tot:.1f}% | {v / c / 1e3:.1f} |")
+    open(os.path.join(P, f"{tag}_launches_bench.md"), "w").write("\n".join(out) + "\n")
+    print("\n".join(out[-18:]))
+
+
+KEYS = ["gpu__time_duration.sum", "sm__cycles_active.avg", "gpc__cycles_elapsed.avg.per_second", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+        "launch__shared_mem_per_block_dynamic", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
+        "sm__inst_executed_pipe_uniform.sum", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"]
+
+
+def raw(rep):
+    txt = subprocess.run(["ncu", "-i", os.path.join(G, rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    r = list(csv.reader(txt.splitlines()))
+    return dict(zip(r[0], r[2])), dict(zip(r[0], r[1]))
+
+
+def conv(tag, reps):
+    out = [f"# {tag}: `ncu --set full` captures of the dominant kernel (tcgen05 implicit-GEMM 3x3 conv, N = 64, Vid4 shape 144x180)", "",
+           "Command: `ncu --set full --clock-control none --import-source on -k regex:<kernel> -s 2 -c 1 python scripts/profile_conv.py <nsrc> <convs> <batch> halo 3 1`", ""]
+    cols = []
+    for rep, desc, flops in reps:
+        v, u = raw(rep)
+        cols.append((rep, desc, flops, v, u))
+    out += ["| metric | " + " | ".join(f"{r} ({d})" for r, d, _, _, _ in cols) + " |", "|---|" + "---|" * len(cols)]
+    for k in KEYS:
+        out.append(f"| `{k}` [{cols[0][4].get(k, '')}] | " + " | ".join(c[3].get(k, "-") for c in cols) + " |")
+    out.append("")
+    for rep, desc, flops, v, u in cols:
+        t = float(v["gpu__time_duration.sum"])
+        rd, wr = float(v["dram__bytes_read.sum"]), float(v["dram__bytes_write.sum"])
+        out.append(f"* {rep}: {flops / t / 1e6:.0f} TFLOP/s under the profiler; DRAM {rd:.1f} {u['dram__bytes_read.sum']} read + {wr:.1f} "
+                   f"{u['dram__bytes_write.sum']} written per launch; SM clock {float(v['gpc__cycles_elapsed.avg.per_second']):.2f} GHz.")
+    out += ["", "Reading: the kernel is bound by how fast ONE elected thread can issue `tcgen05.mma` and by the 128 B/clk shared-memory operand",
+            "feed: an M=128, N=64, K=16 SS-mode UMMA costs 48 cycles at best (scripts/umma_bench.cu, 54-58 from one issuing thread), i.e. 67 % of",
+            "the dense peak, and the chip runs at ~1.45 GHz under the 1 kW cap while this kernel is resident (clock64 / kernel time).",
+            "`sm__pipe_tensor_subpipe_hmma_cycles_active` is a nominal count (128 per M=128 UMMA) on this part, not a busy measurement.", ""]
+    open(os.path.join(P, f"{tag}_conv_ncu_summary.md"), "w").write("\n".join(out))
+    last = cols[-1]
+    json.dump({"dram_bytes_per_launch": (float(last[3]["dram__bytes_read.sum"]) + float(last[3]["dram__bytes_write.sum"])) * 1e6,
+               "launch": last[1], "algorithmic_bytes": None, "source": f"profiles/{tag}_conv_ncu_summary.md ({last[0]})"},
+              open(os.path.join(P, "conv_traffic.json"), "w"), indent=1)
+    print("\n".join(out[-12:]))
+
+
+if __name__ == "__main__":
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    os.makedirs(P, exist_ok=True)
+    launches(tag)
+    px = 144 * 180
+    conv(tag, [("conv_r01_a.ncu-rep", "6 convs 64->64, B=4, first version", 2.0 * 6 * 4 * px * 64 * 576),
+               ("conv_r01_e.ncu-rep", "6 convs 128->64, B=4, resident weights", 2.0 * 6 * 4 * px * 64 * 1152),
+               ("conv_r01_f.ncu-rep", "2 convs 192->64, B=17, big-K batched", 2.0 * 2 * 17 * px * 64 * 1728)])
+    src = os.path.join(G, f"bench_{tag}.json")
+    if os.path.exists(src):
+        line = [l for l in open(src) if l.startswith("{")][-1]
+        json.dump(json.loads(line), open(os.path.join(P, f"{tag}_bench.json"), "w"), indent=1)

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(128, 1) bench_conv(int tiles, long long* out, 
       if (elect_one()) {
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
-          const uint32_t al = a_lo0 + ((tap / 3) * 10 + tap % 3) * 8, bl = b_lo0 + tap * 512;
+          const uint32_t al = a_lo0 + ((mode & 8) ? 0 : ((tap / 3) * 10 + tap % 3) * 8), bl = b_lo0 + ((mode & 16) ? 0 : tap * 512);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_bf16(d, (uint64_t(ahi) << 32) | (al + 2 * k), (uint64_t(bhi) << 32) | (bl + 2 * k), idesc,
@@ -85,6 +85,114 @@ __global__ void __launch_bounds__(128, 1) bench_conv(int tiles, long long* out, 
     mbar_wait(&bar, 0);
     long long t1 = clock64();
     if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = t1 - t0;
+  }
+  tc_fence_before(); __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<512>(tm); }
+}
+
+// NW warps issue independent MMA streams (own accumulator each) concurrently: is the per-thread issue rate the limit?
+template <int N>
+__global__ void __launch_bounds__(256, 1) bench_multi(int tiles, long long* out, int nw) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  __shared__ uint64_t bar[8];
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (24 * 1024 + 9 * N * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) mbar_init(&bar[i], 1); fence_barrier_init(); }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) tmem_alloc<512>(&slot);
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tm = slot;
+  long long t0 = clock64();
+  if (warp < nw) {
+    const uint32_t a_lo0 = (smem_u32(smem) >> 4) & 0x3fff, b_lo0 = (smem_u32(smem + 24 * 1024) >> 4) & 0x3fff;
+    const uint32_t bhi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t ahi = (1280u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t idesc = idesc_mn(128, N);
+    const uint32_t d = tm + warp * N;
+    for (int t = 0; t < tiles; ++t) {
+      if (elect_one()) {
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t al = a_lo0 + ((tap / 3) * 10 + tap % 3) * 8, bl = b_lo0 + tap * (N * 8);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d, (uint64_t(ahi) << 32) | (al + 2 * k), (uint64_t(bhi) << 32) | (bl + 2 * k), idesc, (tap | k) ? 1u : 0u);
+        }
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(&bar[warp]);
+    __syncwarp();
+    mbar_wait(&bar[warp], 0);
+  }
+  __syncthreads();
+  long long t1 = clock64();
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = t1 - t0;
+  tc_fence_before(); __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<512>(tm); }
+}
+
+// One issuing warp (conv-like stream, N = 64) plus background activity: bit0 = a warp streaming 23 KB bulk copies into
+// shared memory (what the TMA producer does), bit1 = four warps reading TMEM with tcgen05.ld (what the epilogue does).
+__global__ void __launch_bounds__(320, 1) bench_bg(int tiles, long long* out, int mode, const uint8_t* gsrc) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* scratch = smem + 24 * 1024 + 9 * 8192;   // 2 x 24 KB landing zones
+  __shared__ uint64_t bar, cbar[2];
+  __shared__ uint32_t slot;
+  __shared__ volatile int done;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < (24 * 1024 + 9 * 8192) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init(&cbar[0], 1); mbar_init(&cbar[1], 1); done = 0; fence_barrier_init(); }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) tmem_alloc<512>(&slot);
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tm = slot;
+  if (warp == 0) {
+    const uint32_t a_lo0 = (smem_u32(smem) >> 4) & 0x3fff, b_lo0 = (smem_u32(smem + 24 * 1024) >> 4) & 0x3fff;
+    const uint32_t bhi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t ahi = (1280u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t idesc = idesc_mn(128, 64);
+    long long t0 = clock64();
+    for (int t = 0; t < tiles; ++t) {
+      if (elect_one()) {
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t al = a_lo0 + ((tap / 3) * 10 + tap % 3) * 8, bl = b_lo0 + tap * 512;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tm + (t & 1) * 64, (uint64_t(ahi) << 32) | (al + 2 * k), (uint64_t(bhi) << 32) | (bl + 2 * k), idesc, (tap | k) ? 1u : 0u);
+        }
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(&bar);
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    if (blockIdx.x == 0 && lane == 0) out[0] = t1 - t0;
+    if (lane == 0) done = 1;
+  } else if (warp == 1 && (mode & 1)) {
+    if (lane == 0) {
+      int ph[2] = {0, 0};
+      for (int i = 0; !done; ++i) {
+        const int b = i & 1;
+        mbar_expect_tx(&cbar[b], 23040);
+        bulk_load(scratch + b * 24576, gsrc + (size_t)((blockIdx.x * 64 + (i & 63)) % 4096) * 23040, 23040, &cbar[b]);
+        if (i > 0) { mbar_wait(&cbar[b ^ 1], ph[b ^ 1]); ph[b ^ 1] ^= 1; }
+      }
+    }
+  } else if (warp >= 2 && warp < 6 && (mode & 2)) {
+    uint32_t r[16];
+    uint32_t acc = 0;
+    while (!done) {
+      tmem_ld16(tm + (static_cast<uint32_t>((warp & 3) * 32) << 16) + 256, r);
+      tmem_ld_wait();
+      acc += r[0];
+    }
+    if (acc == 0x12345) out[1] = acc;
   }
   tc_fence_before(); __syncthreads();
   if (warp == 0) { tc_fence_after(); tmem_dealloc<512>(tm); }
@@ -133,13 +241,47 @@ int main() {
   {
     const size_t smem = 1024 + 24 * 1024 + 9 * 8192;
     cudaFuncSetAttribute(bench_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    for (int mode = 0; mode < 8; ++mode) {
+    for (int mode : {0, 8, 16, 24, 7}) {
       bench_conv<<<148, 128, smem>>>(2048, d_out, mode);
       cudaError_t e = cudaDeviceSynchronize();
       long long cyc = 0;
       cudaMemcpy(&cyc, d_out, sizeof(cyc), cudaMemcpyDeviceToHost);
-      printf("conv-like loop mode %d (commit/src=%d alt-acc=%d reset=%d): %6.1f cycles/MMA (%s)\n", mode, mode & 1, (mode >> 1) & 1,
-             (mode >> 2) & 1, double(cyc) / (2048.0 * 36), e == cudaSuccess ? "ok" : cudaGetErrorString(e));
+      printf("conv-like loop mode %2d (commit/src=%d alt-acc=%d reset=%d fixedA=%d fixedB=%d): %6.1f cycles/MMA (%s)\n", mode, mode & 1, (mode >> 1) & 1,
+             (mode >> 2) & 1, (mode >> 3) & 1, (mode >> 4) & 1, double(cyc) / (2048.0 * 36), e == cudaSuccess ? "ok" : cudaGetErrorString(e));
+    }
+  }
+  {
+    const size_t smem = 1024 + 24 * 1024 + 9 * 128 * 128;
+    cudaFuncSetAttribute(bench_multi<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(bench_multi<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (int nw : {1, 2, 3, 4}) {
+      bench_multi<64><<<148, 256, smem>>>(1024, d_out, nw);
+      cudaError_t e = cudaDeviceSynchronize();
+      long long cyc = 0;
+      cudaMemcpy(&cyc, d_out, sizeof(cyc), cudaMemcpyDeviceToHost);
+      printf("N=64, %d issuing warps: %6.1f cycles per MMA aggregate (%s)\n", nw, double(cyc) / (1024.0 * 36 * nw), e == cudaSuccess ? "ok" : cudaGetErrorString(e));
+    }
+    for (int nw : {1, 2}) {
+      bench_multi<128><<<148, 256, smem>>>(1024, d_out, nw);
+      cudaError_t e = cudaDeviceSynchronize();
+      long long cyc = 0;
+      cudaMemcpy(&cyc, d_out, sizeof(cyc), cudaMemcpyDeviceToHost);
+      printf("N=128, %d issuing warps: %6.1f cycles per MMA aggregate (%s)\n", nw, double(cyc) / (1024.0 * 36 * nw), e == cudaSuccess ? "ok" : cudaGetErrorString(e));
+    }
+  }
+  {
+    const size_t smem = 1024 + 24 * 1024 + 9 * 8192 + 2 * 24576;
+    cudaFuncSetAttribute(bench_bg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    uint8_t* gsrc;
+    cudaMalloc(&gsrc, (size_t)4096 * 23040);
+    cudaMemset(gsrc, 0, (size_t)4096 * 23040);
+    for (int mode = 0; mode < 4; ++mode) {
+      bench_bg<<<148, 320, smem>>>(1024, d_out, mode, gsrc);
+      cudaError_t e = cudaDeviceSynchronize();
+      long long cyc = 0;
+      cudaMemcpy(&cyc, d_out, sizeof(cyc), cudaMemcpyDeviceToHost);
+      printf("background mode %d (bulk-copy=%d tmem-ld=%d): %6.1f cycles per MMA (%s)\n", mode, mode & 1, (mode >> 1) & 1, double(cyc) / (1024.0 * 36),
+             e == cudaSuccess ? "ok" : cudaGetErrorString(e));
     }
   }
   return 0;
