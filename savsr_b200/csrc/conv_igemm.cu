@@ -539,7 +539,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
 // Weight traffic per tile drops 4x versus streaming per tile and no per-tap waits remain on the issue path.
 constexpr int kBatchTiles = 4;
 
-__global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_bigk_kernel(const __grid_constant__ ConvParams p) {
+constexpr int kBigkThreads = kNumThreads + 32;   // + a second MMA-issuing warp (warp 10)
+
+__global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const __grid_constant__ ConvParams p) {
   constexpr int BN = 64, NT = 9;
   constexpr int kBBytes = BN * 128;
   constexpr int kAStage = kHaloStageBytes, kAStages = 3;
@@ -564,11 +566,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_bigk_kernel(const _
   const int item_begin = blockIdx.x * p.chunk;
   const int item_end = min(item_begin + p.chunk, total);
   const int nsrc = p.nsrc;
+  // With at most two sources both weight sets stay resident (set s = source s) for as long as consecutive batches
+  // use the same weights; otherwise the two sets double-buffer the sources of one batch.
+  const bool pinned = nsrc <= 2;
+  const uint32_t ps_mask = p.per_sample_mask;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&p.tm_halo);
-    for (int i = 0; i < kMaxAStages; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(set_full + i, 1); mbar_init(set_empty + i, 1); }
+    for (int i = 0; i < kMaxAStages; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 2); }   // owner's commit + the other issuer's pass
+    for (int i = 0; i < 2; ++i) { mbar_init(set_full + i, 1); mbar_init(set_empty + i, 2); }   // both issuers release a set
     for (int i = 0; i < 2 * kBatchTiles; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 8); }
     fence_barrier_init();
   }
@@ -583,7 +589,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_bigk_kernel(const _
   int tile = item_begin % tiles;
   int gn = item_begin / tiles;
   int bcount = 0;
-  uint32_t use_bits = 0;  // per accumulator: parity of how many times it has been used
+  uint32_t use_bits = 0;      // per accumulator: parity of how many times it has been used
+  uint32_t set_loads[2] = {0, 0};  // per weight set: how many times it has been (re)loaded
+  int cur_key = -1;
 
   if (warp == 0) {
     // ================================ TMA producer (one thread) ================================
@@ -593,16 +601,23 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_bigk_kernel(const _
       while (item < item_end) {
         const int cnt = min(kBatchTiles, min(item_end - item, tiles - tile));
         const int n = gn % p.batch;
-        const savsr_conv_group& g = p.g[gn / p.batch];
+        const int gi = gn / p.batch;
+        const savsr_conv_group& g = p.g[gi];
         const uint8_t* wptr = static_cast<const uint8_t*>(g.weight) + static_cast<long>(n) * g.weight_sample_stride;
-        for (int s = 0; s < nsrc; ++s, ++u) {
-          const int set = u & 1;
-          mbar_wait(set_empty + set, ((u >> 1) & 1) ^ 1);
-          mbar_expect_tx(set_full + set, kSetBytes);
-          int kb = blockIdx.x % kSetBlocks;  // rotated issue order across CTAs
-          for (int i = 0; i < kSetBlocks; ++i) {
-            bulk_load(smem_b + set * kSetBytes + kb * kBBytes, wptr + static_cast<long>(s * NT + kb) * kBBytes, kBBytes, set_full + set);
-            if (++kb == kSetBlocks) kb = 0;
+        const int key = gi * p.batch + (((ps_mask >> gi) & 1u) ? n : 0);
+        const bool load = !pinned || key != cur_key;
+        cur_key = key;
+        for (int s = 0; s < nsrc; ++s) {
+          if (load) {
+            const int set = pinned ? s : static_cast<int>(u++ & 1);
+            mbar_wait(set_empty + set, (set_loads[set] & 1u) ^ 1u);
+            ++set_loads[set];
+            mbar_expect_tx(set_full + set, kSetBytes);
+            int kb = blockIdx.x % kSetBlocks;  // rotated issue order across CTAs
+            for (int i = 0; i < kSetBlocks; ++i) {
+              bulk_load(smem_b + set * kSetBytes + kb * kBBytes, wptr + static_cast<long>(s * NT + kb) * kBBytes, kBBytes, set_full + set);
+              if (++kb == kSetBlocks) kb = 0;
+            }
           }
           const int img = g.src_slot[s] * p.batch + n;
           for (int j = 0; j < cnt; ++j) {
@@ -618,8 +633,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_bigk_kernel(const _
         if (tile == tiles) { tile = 0; ++gn; }
       }
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer (warp-uniform, elected issue) ================================
+  } else if (warp == 1 || warp == 10) {
+    // ================================ two MMA issuers (warp-uniform, elected issue) ================================
+    // One thread cannot issue N=64 MMAs as fast as the tensor core retires them (54-58 vs 48 cycles, scripts/umma_bench.cu):
+    // warp 1 takes the even tiles of a batch, warp 10 the odd ones, each into its own TMEM accumulators.
+    const int my = warp == 1 ? 0 : 1;
     constexpr uint32_t idesc = umma_idesc_bf16(BN);
     constexpr uint32_t a_hi = desc_hi(kHaloPitch * 128u);
     constexpr uint32_t b_hi = desc_hi(1024u);
@@ -630,45 +648,71 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_bigk_kernel(const _
     while (item < item_end) {
       const int cnt = min(kBatchTiles, min(item_end - item, tiles - tile));
       const int bb = bcount & 1;
+      const int n = gn % p.batch;
+      const int gi = gn / p.batch;
+      const int key = gi * p.batch + (((ps_mask >> gi) & 1u) ? n : 0);
+      const bool load = !pinned || key != cur_key;
+      if (pinned && load && cur_key >= 0) {
+        // the pinned sets are about to be replaced: release them once every MMA issued so far has retired
+        if (elect_one()) {
+          for (int s = 0; s < nsrc; ++s) umma_commit(set_empty + s);
+        }
+        __syncwarp();
+      }
+      cur_key = key;
 #pragma unroll
       for (int j = 0; j < kBatchTiles; ++j) {
-        if (j < cnt) mbar_wait(t_empty + bb * kBatchTiles + j, ((use_bits >> (bb * kBatchTiles + j)) & 1u) ^ 1u);
+        if (j < cnt && (j & 1) == my) mbar_wait(t_empty + bb * kBatchTiles + j, ((use_bits >> (bb * kBatchTiles + j)) & 1u) ^ 1u);
       }
       tc_fence_after();
-      for (int s = 0; s < nsrc; ++s, ++u) {
-        const int set = u & 1;
-        mbar_wait(set_full + set, (u >> 1) & 1);
-        tc_fence_after();
+      for (int s = 0; s < nsrc; ++s) {
+        const int set = pinned ? s : static_cast<int>(u & 1);
+        if (load) {
+          mbar_wait(set_full + set, set_loads[set] & 1u);
+          ++set_loads[set];
+          tc_fence_after();
+          ++u;
+        }
         const uint32_t bl0 = b_lo0 + set * (kSetBytes >> 4);
 #pragma unroll
         for (int j = 0; j < kBatchTiles; ++j) {
           if (j < cnt) {
+            // BOTH issuers observe every stage fill in order and the stage is refilled only after both have passed it
+            // (a_empty counts 2): mbarrier parity cannot distinguish phases two apart, so neither issuer may run
+            // more than one fill ahead of, or behind, the barrier it waits on.
             mbar_wait(a_full + sa, pa);
-            tc_fence_after();
-            const uint32_t al0 = a_lo0 + sa * (kAStage >> 4);
-            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((bb * kBatchTiles + j) * BN);
-            if (elect_one()) {
+            if ((j & 1) != my) {
+              if (elect_one()) mbar_arrive(a_empty + sa);
+              __syncwarp();
+            } else {
+              tc_fence_after();
+              const uint32_t al0 = a_lo0 + sa * (kAStage >> 4);
+              const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((bb * kBatchTiles + j) * BN);
+              if (elect_one()) {
 #pragma unroll
-              for (int tap = 0; tap < NT; ++tap) {
-                const uint32_t al = al0 + ((tap / 3) * kHaloPitch + tap % 3) * 8;
-                const uint32_t bl = bl0 + tap * (kBBytes >> 4);
+                for (int tap = 0; tap < NT; ++tap) {
+                  const uint32_t al = al0 + ((tap / 3) * kHaloPitch + tap % 3) * 8;
+                  const uint32_t bl = bl0 + tap * (kBBytes >> 4);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16(d_tmem, make_desc(a_hi, al + 2 * k), make_desc(b_hi, bl + 2 * k), idesc, (s | tap | k) ? 1u : 0u);
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16(d_tmem, make_desc(a_hi, al + 2 * k), make_desc(b_hi, bl + 2 * k), idesc, (s | tap | k) ? 1u : 0u);
+                }
+                umma_commit(a_empty + sa);
               }
-              umma_commit(a_empty + sa);
+              __syncwarp();
             }
-            __syncwarp();
             if (++sa == kAStages) { sa = 0; pa ^= 1; }
           }
         }
-        if (elect_one()) umma_commit(set_empty + set);
-        __syncwarp();
+        if (!pinned) {
+          if (elect_one()) umma_commit(set_empty + set);
+          __syncwarp();
+        }
       }
       if (elect_one()) {
 #pragma unroll
         for (int j = 0; j < kBatchTiles; ++j)
-          if (j < cnt) umma_commit(t_full + bb * kBatchTiles + j);
+          if (j < cnt && (j & 1) == my) umma_commit(t_full + bb * kBatchTiles + j);
       }
       __syncwarp();
 #pragma unroll
@@ -846,7 +890,8 @@ static int launch_conv(savsr_ctx* ctx, ConvParams& p, int impl, cudaStream_t st)
   }
   if (p.ntaps == 1) return launch_igemm<BN, 1, false>(ctx, p, total, st);
   if constexpr (BN == 64) {
-    static const bool bigk_all = getenv("SAVSR_BIGK_ALL") != nullptr && atoi(getenv("SAVSR_BIGK_ALL")) != 0;
+    // the batched dual-issuer kernel is the default for every 3x3 HALO conv; SAVSR_BIGK_ALL=0 restricts it to K > 18 blocks
+    static const bool bigk_all = getenv("SAVSR_BIGK_ALL") == nullptr || atoi(getenv("SAVSR_BIGK_ALL")) != 0;
     if (p.halo && (bigk_all || p.nsrc * p.ntaps > kBBlocks)) {
       const size_t smem = 1024 + kARegionBytes + kBBlocks * BN * 128 + 512;
       static bool attr_done = false;
@@ -856,7 +901,7 @@ static int launch_conv(savsr_ctx* ctx, ConvParams& p, int impl, cudaStream_t st)
       }
       p.chunk = (total + ctx->sm_count - 1) / ctx->sm_count;
       const int grid = (total + p.chunk - 1) / p.chunk;
-      conv_igemm_bigk_kernel<<<grid, kNumThreads, smem, st>>>(p);
+      conv_igemm_bigk_kernel<<<grid, kBigkThreads, smem, st>>>(p);
       SAVSR_CUDA(cudaGetLastError());
       return 0;
     }

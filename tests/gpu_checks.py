@@ -162,6 +162,35 @@ def check_conv(impl=K.IMPL_TAP, ksize=3, nsrc=1, B=1, H=32, W=24, full_epilogue=
     return results
 
 
+def check_conv_repeatability(nsrc=2, ngroups=3, B=3, H=144, W=180, reps=25, seed=21):
+    """Back-to-back launches at the benchmark shape must be bit-identical (guards the multi-warp mbarrier protocol
+    of the batched dual-issuer kernel against races: a lapped or aliased barrier phase shows up as a mismatch or a trap)."""
+    torch.manual_seed(seed)
+    ab = ArenaBox(ngroups * (nsrc + 1), B, H, W)
+    ab.t.normal_()
+    groups, keep = [], []
+    for g in range(ngroups):
+        w = pack_weight(torch.randn(64, 64 * nsrc, 3, 3, device=DEV) * 0.05)
+        bias = torch.randn(64, device=DEV)
+        keep += [w, bias]
+        groups.append(group([g * (nsrc + 1) + i for i in range(nsrc)], g * (nsrc + 1) + nsrc, w, bias, act=K.ACT_LRELU))
+    run_conv(ab, groups, impl=K.IMPL_HALO)
+    dst = [g * (nsrc + 1) + nsrc for g in range(ngroups)]
+    first = [ab.t[d * B:(d + 1) * B].clone() for d in dst]
+    for _ in range(reps):
+        for d in dst:
+            ab.t[d * B:(d + 1) * B].zero_()
+        run_conv(ab, groups, impl=K.IMPL_HALO)
+        for d, f in zip(dst, first):
+            assert torch.equal(ab.t[d * B:(d + 1) * B], f), "conv output changed between identical launches"
+    chk = [group(g_.src_slot[:nsrc], dst[i], keep[2 * i], keep[2 * i + 1], act=K.ACT_LRELU) for i, g_ in enumerate(groups)]
+    run_conv(ab, chk, impl=K.IMPL_CHECK)
+    for d, f in zip(dst, first):
+        diff = (ab.t[d * B:(d + 1) * B].float() - f.float()).abs().max().item()
+        assert diff <= 0.04, f"tensor-core kernel differs from the checker kernel by {diff}"
+    return dict(reps=reps, status="bit-identical")
+
+
 def check_conv_aux16(impl=K.IMPL_TAP, B=2, H=20, W=28, seed=1):
     """N = 16 variant writing the fp32 [B][H*W][16] side buffer (OSAdapt mask conv, savsr_arch.py:190-192)."""
     torch.manual_seed(seed)

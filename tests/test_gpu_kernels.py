@@ -20,6 +20,11 @@ def test_conv_tcgen05_tap(G, ksize, nsrc, B, H, W):
     G.check_conv(impl=G.K.IMPL_TAP, ksize=ksize, nsrc=nsrc, B=B, H=H, W=W)
 
 
+@pytest.mark.parametrize("nsrc,ngroups,B", [(1, 6, 3), (2, 3, 3), (3, 2, 4), (5, 1, 2)])
+def test_conv_repeatability_at_bench_shape(G, nsrc, ngroups, B):
+    G.check_conv_repeatability(nsrc=nsrc, ngroups=ngroups, B=B)
+
+
 def test_conv_checker_kernel(G):
     G.check_conv(impl=G.K.IMPL_CHECK, ksize=3, nsrc=2, B=2, H=21, W=19)
 
