@@ -645,6 +645,7 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
     const uint32_t b_lo0 = (smem_u32(smem_b) >> 4) & 0x3fffu;
     int sa = 0, pa = 0;
     uint32_t u = 0;
+    long long dbg_te = 0, dbg_af = 0, dbg_sf = 0, dbg_t0 = clock64(), c0;
     while (item < item_end) {
       const int cnt = min(kBatchTiles, min(item_end - item, tiles - tile));
       const int bb = bcount & 1;
@@ -660,15 +661,19 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
         __syncwarp();
       }
       cur_key = key;
+      c0 = clock64();
 #pragma unroll
       for (int j = 0; j < kBatchTiles; ++j) {
         if (j < cnt && (j & 1) == my) mbar_wait(t_empty + bb * kBatchTiles + j, ((use_bits >> (bb * kBatchTiles + j)) & 1u) ^ 1u);
       }
+      dbg_te += clock64() - c0;
       tc_fence_after();
       for (int s = 0; s < nsrc; ++s) {
         const int set = pinned ? s : static_cast<int>(u & 1);
         if (load) {
+          c0 = clock64();
           mbar_wait(set_full + set, set_loads[set] & 1u);
+          dbg_sf += clock64() - c0;
           ++set_loads[set];
           tc_fence_after();
           ++u;
@@ -680,7 +685,9 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
             // BOTH issuers observe every stage fill in order and the stage is refilled only after both have passed it
             // (a_empty counts 2): mbarrier parity cannot distinguish phases two apart, so neither issuer may run
             // more than one fill ahead of, or behind, the barrier it waits on.
+            c0 = clock64();
             mbar_wait(a_full + sa, pa);
+            dbg_af += clock64() - c0;
             if ((j & 1) != my) {
               if (elect_one()) mbar_arrive(a_empty + sa);
               __syncwarp();
@@ -722,6 +729,13 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
       item += cnt; tile += cnt;
       if (tile == tiles) { tile = 0; ++gn; }
     }
+    if (p.dbg != nullptr && lane == 0 && my == 0) {
+      p.dbg[blockIdx.x * 8 + 0] = clock64() - dbg_t0;
+      p.dbg[blockIdx.x * 8 + 1] = dbg_te;
+      p.dbg[blockIdx.x * 8 + 2] = dbg_af;
+      p.dbg[blockIdx.x * 8 + 3] = item_end - item_begin;
+      p.dbg[blockIdx.x * 8 + 7] = dbg_sf;
+    }
   } else {
     // ================================ epilogue warps ================================
     const int quad = warp & 3;
@@ -729,6 +743,7 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
     constexpr int NC = 32;
     EpiCtx<NC> ec;
     ec.bias_group = -1;
+    long long dbg_tf = 0, dbg_t0 = clock64();
     while (item < item_end) {
       const int cnt = min(kBatchTiles, min(item_end - item, tiles - tile));
       const int bb = bcount & 1;
@@ -738,7 +753,9 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
       for (int j = 0; j < cnt; ++j) {
         const int acc = bb * kBatchTiles + j;
         epi_prefetch<NC>(p, g, gi, n, tile + j, quad, lane, half * 32, ec);
+        const long long c0 = clock64();
         mbar_wait(t_full + acc, (use_bits >> acc) & 1u);
+        dbg_tf += clock64() - c0;
         use_bits ^= 1u << acc;
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN + half * 32);
@@ -759,6 +776,10 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
       ++bcount;
       item += cnt; tile += cnt;
       if (tile == tiles) { tile = 0; ++gn; }
+    }
+    if (p.dbg != nullptr && warp == 2 && lane == 0) {
+      p.dbg[blockIdx.x * 8 + 4] = clock64() - dbg_t0;
+      p.dbg[blockIdx.x * 8 + 5] = dbg_tf;
     }
   }
 

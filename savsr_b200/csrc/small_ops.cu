@@ -143,8 +143,11 @@ __global__ void __launch_bounds__(kOsaThreads) osa_pool_kernel(const __grid_cons
 }
 
 // One Linear + ReLU layer of scale_routing (savsr_arch.py:123-128).  layer 0: [2ci][ci+2], layer 1: [ci][2ci].
-// grid (row blocks, nconvs), 256 threads = 8 warps, one output row per warp, all samples per row.
+// grid (row blocks, nconvs), 256 threads = 8 warps, one output row per warp.  The inputs of ALL samples are staged in
+// shared memory and the row's weights sit in registers, so each weight is fetched once and every sample costs one
+// shared-memory dot product + shuffle reduction.
 __global__ void __launch_bounds__(256) osa_linear_kernel(const __grid_constant__ OsaLaunch L, int layer) {
+  extern __shared__ float s_in[];   // [batch][len]
   const savsr_osa_params& c = L.c[blockIdx.y];
   const int rows = layer == 0 ? 2 * c.ci : c.ci;
   const int len = layer == 0 ? c.ci + 2 : 2 * c.ci;
@@ -153,16 +156,28 @@ __global__ void __launch_bounds__(256) osa_linear_kernel(const __grid_constant__
   const float* W = layer == 0 ? c.r0_w : c.r2_w;
   const float* B = layer == 0 ? c.r0_b : c.r2_b;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x * 8 >= rows) return;
+  const int stride = osa_scratch_stride(c.ci);
+  for (int i = threadIdx.x; i < L.batch * len; i += blockDim.x) {
+    const int n = i / len, k = i - n * len;
+    s_in[i] = c.scratch[static_cast<long>(n) * stride + in_off + k];
+  }
+  __syncthreads();
   const int row = blockIdx.x * 8 + warp;
   if (row >= rows) return;
   const float* wr = W + static_cast<long>(row) * len;
+  float w[20];   // ceil(640 / 32)
+#pragma unroll
+  for (int j = 0; j < 20; ++j) w[j] = lane + 32 * j < len ? __ldg(wr + lane + 32 * j) : 0.f;
+  const float bias = B[row];
   for (int n = 0; n < L.batch; ++n) {
-    const float* in = c.scratch + static_cast<long>(n) * osa_scratch_stride(c.ci) + in_off;
+    const float* in = s_in + n * len;
     float acc = 0.f;
-    for (int i = lane; i < len; i += 32) acc += __ldg(wr + i) * in[i];
+#pragma unroll
+    for (int j = 0; j < 20; ++j) if (lane + 32 * j < len) acc += w[j] * in[lane + 32 * j];
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) c.scratch[static_cast<long>(n) * osa_scratch_stride(c.ci) + out_off + row] = fmaxf(acc + B[row], 0.f);
+    if (lane == 0) c.scratch[static_cast<long>(n) * stride + out_off + row] = fmaxf(acc + bias, 0.f);
   }
 }
 
@@ -491,8 +506,15 @@ extern "C" int savsr_osa_prologue(savsr_ctx* ctx, const savsr_osa_params* convs,
   L.nconvs = nconvs; L.batch = batch; L.npart = npart; L.npix = npix;
   L.inv_h = inv_scale_h; L.inv_w = inv_scale_w;
   osa_pool_kernel<<<dim3(max_ci / 64, batch, nconvs), kOsaThreads, 0, st>>>(L);
-  osa_linear_kernel<<<dim3((2 * max_ci + 7) / 8, nconvs), 256, 0, st>>>(L, 0);
-  osa_linear_kernel<<<dim3((max_ci + 7) / 8, nconvs), 256, 0, st>>>(L, 1);
+  const size_t lin_smem = static_cast<size_t>(batch) * 2 * max_ci * sizeof(float);
+  SAVSR_REQUIRE(lin_smem <= 200 * 1024, "savsr_osa_prologue: batch %d too large for the routing kernel's shared memory", batch);
+  static bool lin_attr = false;
+  if (lin_smem > 48 * 1024 && !lin_attr) {
+    SAVSR_CUDA(cudaFuncSetAttribute(osa_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    lin_attr = true;
+  }
+  osa_linear_kernel<<<dim3((2 * max_ci + 7) / 8, nconvs), 256, lin_smem, st>>>(L, 0);
+  osa_linear_kernel<<<dim3((max_ci + 7) / 8, nconvs), 256, lin_smem, st>>>(L, 1);
   osa_attention_kernel<<<dim3(batch, nconvs), 256, 0, st>>>(L);
   osa_assemble_kernel<<<dim3((64 * max_ci + 255) / 256, nconvs), 256, 0, st>>>(L);
   SAVSR_CUDA(cudaGetLastError());

@@ -52,7 +52,9 @@ def main():
         d = d[d[:, 3] > 0]
         m = d.mean(0)
         print(f"  per CTA (avg over {len(d)}): tiles {m[3]:.1f} | MMA warp total {m[0]:.0f} cyc ({m[0]/m[3]:.0f}/tile), wait t_empty {m[1]:.0f} ({100*m[1]/m[0]:.0f}%), "
-              f"wait a_full {m[2]:.0f} ({100*m[2]/m[0]:.0f}%) | epilogue total {m[4]:.0f}, wait t_full {m[5]:.0f} ({100*m[5]/max(m[4],1):.0f}%) | producer wait a_empty {m[6]:.0f}")
+              f"wait a_full {m[2]:.0f} ({100*m[2]/m[0]:.0f}%), wait set_full {m[7]:.0f} | epilogue total {m[4]:.0f}, wait t_full {m[5]:.0f} ({100*m[5]/max(m[4],1):.0f}%) | producer wait a_empty {m[6]:.0f}")
+    if os.environ.get("CONV_DBG"):
+        print(f"  SM clock from clock64 / event time: {m[0] / us / 1e3:.2f} GHz; cycles per MMA (issuer 0 view): {m[0] / (m[3] * 36 * nsrc):.1f}")
     print(f"nsrc={nsrc} groups={ng} B={B} impl={a[3] if len(a) > 3 else 'halo'} k={ks}: {us:.1f} us/launch, {flop / us / 1e6:.1f} TFLOP/s")
 
 
