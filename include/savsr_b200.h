@@ -254,6 +254,15 @@ int savsr_satu_fused(savsr_ctx* ctx, savsr_arena* lr, int x_slot, int sta_slot, 
                      const void* w_compress, const void* w_expand, const void* w_fusion, const float* fusion_bias,
                      savsr_stream st);
 
+/* ---- post-processing / metrics on the device (next row 8f3) -------------------------------------------------------
+ * tensor2img (lbasicsr/utils/img_util.py:38-94): sr fp32 NCHW [batch][3][H][W] RGB -> uint8 HWC BGR [batch][H][W][3]
+ * (clamp, *255, round half to even), and, when gt is given, the per-frame sum of squared Y-channel differences of the two
+ * uint8 images (metric_util.py:32-45, color_util.py:38-68, psnr_ssim.py:11-48 with crop_border 0) in float64:
+ * PSNR_Y = 10 log10(255^2 * H*W / sse_y).  bgr_u8 and sse_y may each be NULL.
+ */
+int savsr_img_metrics(savsr_ctx* ctx, const float* sr, const float* gt, int batch, int height, int width,
+                      uint8_t* bgr_u8, double* sse_y, savsr_stream st);
+
 #ifdef __cplusplus
 }
 #endif

@@ -411,22 +411,30 @@ def forward(sd: SD, x: Tensor, scale, probes: Optional[dict] = None) -> Tensor:
     return sr + skip
 
 
-# --------------------------------------------------------------------------- metrics used by the parity gates
+# --------------------------------------------------------------------------- post-processing / metrics
+def tensor2img(t: Tensor) -> np.ndarray:
+    """tensor2img (img_util.py:38-94) for one RGB frame [3,H,W] in [0,1]: clamp -> HWC BGR -> (x * 255).round() -> uint8.
+    numpy round = half to even."""
+    x = t.detach().float().cpu().clamp(0, 1).numpy().transpose(1, 2, 0)[..., ::-1]
+    return (x * 255.0).round().astype(np.uint8)
+
+
+def y_channel(img_bgr_u8: np.ndarray) -> np.ndarray:
+    """to_y_channel (metric_util.py:32-45) + bgr2ycbcr(y_only) (color_util.py:38-68): float32 in [16,235], not rounded."""
+    img = img_bgr_u8.astype(np.float32) / 255.
+    out = np.dot(img, [24.966, 128.553, 65.481]) + 16.0          # float64, as numpy promotes against the python list
+    out = (out / 255.).astype(np.float32)                        # _convert_output_type_range for a float32 input
+    return out * 255.
+
+
 def psnr_y(a: Tensor, b: Tensor) -> float:
-    """PSNR on the BT.601 Y channel of uint8-quantised images, the reference's own metric chain:
-    tensor2img (img_util.py:66-90) clamp -> *255 -> round -> uint8 ; to_y_channel
-    (color_util.py:38-68, metric_util.py:32-45) ; calculate_psnr (psnr_ssim.py:11-48), crop_border 0.
-    a, b: [3,H,W] or [n,3,H,W] RGB in [0,1].  Returns mean PSNR over n."""
-    def y_of(t: Tensor) -> np.ndarray:
-        q = (t.detach().float().clamp(0, 1) * 255.0).round().to(torch.uint8).cpu().numpy()
-        q = q.astype(np.float32) / 255.0
-        r, g, bl = q[..., 0, :, :], q[..., 1, :, :], q[..., 2, :, :]
-        return (65.481 * r + 128.553 * g + 24.966 * bl + 16.0).astype(np.float32)
-    ya, yb = y_of(a), y_of(b)
-    if ya.ndim == 2:
-        ya, yb = ya[None], yb[None]
+    """calculate_psnr(test_y_channel=True, crop_border=0) (psnr_ssim.py:11-48) on the reference's uint8 images.
+    a, b: [3,H,W] or [n,3,H,W] RGB in [0,1].  Returns the mean PSNR over n (inf when identical)."""
+    if a.dim() == 3:
+        a, b = a[None], b[None]
     vals = []
-    for p, q in zip(ya, yb):
-        mse = float(np.mean((p.astype(np.float64) - q.astype(np.float64)) ** 2))
-        vals.append(float("inf") if mse == 0 else 10.0 * math.log10(255.0 * 255.0 / mse))
+    for p, q in zip(a, b):
+        y1, y2 = y_channel(tensor2img(p)).astype(np.float64), y_channel(tensor2img(q)).astype(np.float64)
+        mse = np.mean((y1 - y2) ** 2)
+        vals.append(float("inf") if mse == 0 else 10. * np.log10(255. * 255. / mse))
     return float(np.mean(vals))

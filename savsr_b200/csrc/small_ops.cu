@@ -435,6 +435,52 @@ __global__ void __launch_bounds__(128) mask_final_kernel(const float* __restrict
   mask[static_cast<long>(n) * npix + pix] = sigmoidf_(acc);
 }
 
+// ------------------------------------------------------------------------------------------------ post-processing (8f3)
+// tensor2img (img_util.py:38-94): clamp[0,1] -> *255 -> round half-to-even -> uint8, RGB -> BGR, HWC; and the squared
+// Y-channel difference against a ground-truth frame (metric_util.py:32-45, psnr_ssim.py:11-48), accumulated per frame
+// in double.  grid (blocks, batch), 256 threads.
+__device__ __forceinline__ float y_of_u8(int b, int g, int r) {
+  const double d = (static_cast<double>(static_cast<float>(b) / 255.f) * 24.966 + static_cast<double>(static_cast<float>(g) / 255.f) * 128.553) +
+                   static_cast<double>(static_cast<float>(r) / 255.f) * 65.481 + 16.0;
+  return static_cast<float>(d / 255.) * 255.f;
+}
+__global__ void __launch_bounds__(256) img_metrics_kernel(const float* __restrict__ sr, const float* __restrict__ gt, int H, int W,
+                                                          uint8_t* __restrict__ bgr, double* __restrict__ sse) {
+  const int n = blockIdx.y;
+  const long npix = static_cast<long>(H) * W;
+  const float* s = sr + static_cast<long>(n) * 3 * npix;
+  const float* g = gt ? gt + static_cast<long>(n) * 3 * npix : nullptr;
+  double acc = 0.0;
+  for (long pix = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; pix < npix; pix += static_cast<long>(gridDim.x) * blockDim.x) {
+    int q[3], qg[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      q[c] = __float2int_rn(fminf(fmaxf(s[c * npix + pix], 0.f), 1.f) * 255.0f);
+      if (g) qg[c] = __float2int_rn(fminf(fmaxf(g[c * npix + pix], 0.f), 1.f) * 255.0f);
+    }
+    if (bgr) {
+      uint8_t* o = bgr + (static_cast<long>(n) * npix + pix) * 3;
+      o[0] = static_cast<uint8_t>(q[2]); o[1] = static_cast<uint8_t>(q[1]); o[2] = static_cast<uint8_t>(q[0]);
+    }
+    if (g) {
+      const double d = static_cast<double>(y_of_u8(q[2], q[1], q[0])) - static_cast<double>(y_of_u8(qg[2], qg[1], qg[0]));
+      acc += d * d;
+    }
+  }
+  if (sse) {
+    __shared__ double red[8];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int i = 0; i < 8; ++i) t += red[i];
+      atomicAdd(sse + n, t);
+    }
+  }
+}
+
 }  // namespace savsr
 
 using namespace savsr;
@@ -558,6 +604,22 @@ extern "C" int savsr_osadapt_mask(savsr_ctx* ctx, const float* in16, int batch, 
   mask_conv16_kernel<false><<<g2, 128, 0, st>>>(half0, wb, bb, half1, h2, w2);
   dim3 g1(static_cast<unsigned>((4 * npix2 + 127) / 128), batch);
   mask_final_kernel<<<g1, 128, 0, st>>>(half1, wc, bc, mask, h2, w2);
+  SAVSR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int savsr_img_metrics(savsr_ctx* ctx, const float* sr, const float* gt, int batch, int height, int width, uint8_t* bgr_u8,
+                                 double* sse_y, savsr_stream st_) {
+  SAVSR_REQUIRE(ctx && sr, "savsr_img_metrics: null pointer");
+  SAVSR_REQUIRE(batch >= 0 && height > 0 && width > 0, "savsr_img_metrics: bad shape");
+  SAVSR_REQUIRE(!sse_y || gt, "savsr_img_metrics: sse_y requested without a ground-truth frame");
+  if (batch == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(st_);
+  if (sse_y) SAVSR_CUDA(cudaMemsetAsync(sse_y, 0, sizeof(double) * batch, st));
+  const long npix = static_cast<long>(height) * width;
+  long blocks = (npix + 255) / 256;
+  if (blocks > 4L * ctx->sm_count) blocks = 4L * ctx->sm_count;
+  img_metrics_kernel<<<dim3(static_cast<unsigned>(blocks), batch), 256, 0, st>>>(sr, gt, height, width, bgr_u8, sse_y);
   SAVSR_CUDA(cudaGetLastError());
   return 0;
 }

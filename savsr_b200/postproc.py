@@ -1,0 +1,39 @@
+"""Device-side post-processing of SR frames: the reference converts every output frame to a
+uint8 BGR image on the CPU (lbasicsr/utils/img_util.py:38-94) and computes PSNR on the Y channel with numpy
+(lbasicsr/metrics/psnr_ssim.py:11-48); here both run in one CUDA kernel on the frames still resident in HBM."""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _capi as K
+from . import engine
+
+
+def tensor2img_psnr(sr: torch.Tensor, gt: Optional[torch.Tensor] = None, want_image: bool = True
+                    ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """sr, gt: float32 [n,3,H,W] RGB on a CUDA device.  Returns (uint8 [n,H,W,3] BGR images or None,
+    float64 [n] PSNR-Y in dB or None).  Identical frames give inf, like the reference."""
+    if not sr.is_cuda:
+        raise RuntimeError("savsr_b200.postproc runs on CUDA only; there is no CPU fallback")
+    if sr.dim() != 4 or sr.shape[1] != 3:
+        raise ValueError(f"expected [n,3,H,W], got {tuple(sr.shape)}")
+    if gt is not None and gt.shape != sr.shape:
+        raise AssertionError(f"Image shapes are different: {tuple(sr.shape)}, {tuple(gt.shape)}.")   # psnr_ssim.py:26
+    sr = sr.float().contiguous()
+    gt = gt.to(sr.device).float().contiguous() if gt is not None else None
+    n, _, H, W = sr.shape
+    ctx = engine.context(sr.device.index if sr.device.index is not None else torch.cuda.current_device())
+    img = torch.empty(n, H, W, 3, dtype=torch.uint8, device=sr.device) if want_image else None
+    sse = torch.empty(n, dtype=torch.float64, device=sr.device) if gt is not None else None
+    with torch.cuda.device(sr.device):
+        K.check(ctx.lib.savsr_img_metrics(ctx.handle, sr.data_ptr(), gt.data_ptr() if gt is not None else None, n, H, W,
+                                          img.data_ptr() if img is not None else None, sse.data_ptr() if sse is not None else None,
+                                          torch.cuda.current_stream().cuda_stream))
+    psnr = None
+    if sse is not None:
+        mse = sse / float(H * W)
+        psnr = torch.where(mse == 0, torch.full_like(mse, math.inf), 10.0 * torch.log10(255.0 * 255.0 / mse))
+    return img, psnr

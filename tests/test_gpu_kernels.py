@@ -86,3 +86,7 @@ def test_satu_gather(G):
 def test_satu_fused_tensor_core_hr_stage(G):
     G.check_satu_fused()
     G.check_satu_fused(B=1, h=16, w=20, scale=(4, 4), seed=2)
+
+
+def test_device_tensor2img_and_psnr_y(G):
+    G.check_img_metrics()

@@ -12,7 +12,7 @@ from oracle import savsr_oracle as O
 from oracle.state_dict_fixture import make_input, make_state_dict, state_dict_spec
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if "fingerprint" not in p)
+CASES = sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if "fingerprint" not in p and "metrics" not in p)
 
 
 def sha12(a: np.ndarray) -> str:
@@ -106,3 +106,13 @@ def test_state_dict_fixture_is_deterministic():
     assert list(a) == [k for k, _, _ in state_dict_spec()] and len(a) == 791
     assert all(torch.equal(a[k], b[k]) for k in a)
     assert not torch.equal(a["tail.weight"], make_state_dict(6)["tail.weight"])
+
+
+def test_metric_chain_matches_reference_kat():
+    """tensor2img + PSNR-Y of the oracle vs values produced by the reference's own img_util / psnr_ssim (make_golden.py)."""
+    k = np.load(os.path.join(GOLDEN, "metrics_kat.npz"))
+    sr, gt = torch.from_numpy(k["sr"]), torch.from_numpy(k["gt"])
+    for i in range(sr.shape[0]):
+        assert hashlib.sha1(np.ascontiguousarray(O.tensor2img(sr[i])).tobytes()).hexdigest() == str(k["img_sha1"][i])
+        assert abs(O.psnr_y(sr[i], gt[i]) - float(k["psnr_y"][i])) < 1e-9
+    assert O.psnr_y(gt[0], gt[0]) == float("inf")
