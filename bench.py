@@ -149,6 +149,8 @@ def main():
     ap.add_argument("--workload", default="vid4_x4", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=17, help="windows per forward")
     ap.add_argument("--conv-impl", default=os.environ.get("SAVSR_CONV_IMPL", "halo"), choices=["halo", "tap"])
+    ap.add_argument("--precision", default=os.environ.get("SAVSR_PRECISION", "bf16"), choices=["bf16", "fp16"],
+                    help="16-bit operand format (fp32 accumulate): bf16 = throughput path, fp16 = <=1e-3 max-abs path, same speed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -176,6 +178,7 @@ def main():
     torch.manual_seed(0)                                   # random-init weights of the shipped architecture
     net = savsr_b200.SAVSR().to(dev).eval()
     net.conv_impl = args.conv_impl
+    net.precision = args.precision
     net.set_scale(scale)
     B = min(args.batch, frames)
 
@@ -263,7 +266,7 @@ def main():
     line = {
         "metric": "hr_mpix_per_s", "value": round(value, 2), "unit": "HR Mpix/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
         "config": {"workload": args.workload, "frames_per_clip": frames, "clips": world, "lr": [h, w], "hr": [H, W],
                    "scale": list(scale), "windows_per_forward": B, "conv_impl": args.conv_impl, "weights": "random init (seed 0)",
                    "l2": "per-step working set (activation arenas, several GB) exceeds the 126 MB L2; no explicit flush",

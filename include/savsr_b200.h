@@ -39,6 +39,11 @@ typedef struct savsr_ctx savsr_ctx;     /* per-device context (driver entry poin
 typedef struct savsr_arena savsr_arena; /* activation arena + its TMA descriptors               */
 typedef void* savsr_stream;             /* cudaStream_t                                          */
 
+/* 16-bit storage / tensor-core operand format of arenas and packed weights (accumulation is always fp32).
+ * BF16: the throughput path named by the task (<= 0.05 dB PSNR delta).  FP16: same speed, 10-bit mantissa: the
+ * high-precision path that meets the <= 1e-3 max-abs bound; activations must stay below 65504. */
+enum savsr_format { SAVSR_FMT_BF16 = 0, SAVSR_FMT_FP16 = 1 };
+
 enum savsr_act { SAVSR_ACT_NONE = 0, SAVSR_ACT_LRELU = 1, SAVSR_ACT_RELU = 2 };
 
 /* how a convolution writes its result */
@@ -97,6 +102,9 @@ const char* savsr_last_error(void);
 int savsr_ctx_create(int device, savsr_ctx** out);
 void savsr_ctx_destroy(savsr_ctx* ctx);
 int savsr_ctx_sm_count(const savsr_ctx* ctx);
+/* Select the 16-bit format used by every later call on this context (default SAVSR_FMT_BF16). */
+int savsr_ctx_set_format(savsr_ctx* ctx, int format);
+int savsr_ctx_get_format(const savsr_ctx* ctx);
 
 /* ---- activation arenas --------------------------------------------------------------------- */
 /* Bytes the caller must allocate (256-byte aligned) for an arena of that shape. */
@@ -118,7 +126,7 @@ size_t savsr_packed_weight_bytes(int co, int ci, int ksize);
  * co_real <= co rows are read, the rest are zero (tail conv: 3 -> 16).  n_tile is 64 or 16.
  */
 int savsr_pack_conv_weight(const float* w_oihw, int co_real, int co, int ci, int ksize, int n_tile,
-                           void* packed, savsr_stream st);
+                           int format /* enum savsr_format */, void* packed, savsr_stream st);
 
 /* ---- convolutions (tensor-core hot path) ------------------------------------------------------- */
 /*

@@ -19,6 +19,8 @@ ACT_NONE, ACT_LRELU, ACT_RELU = 0, 1, 2
 DST_ARENA, DST_AUX16, DST_RGB = 0, 1, 2
 IMPL_TAP, IMPL_HALO, IMPL_CHECK = 0, 1, 2
 IMPL_NAMES = {"tap": IMPL_TAP, "halo": IMPL_HALO, "check": IMPL_CHECK}
+FMT_BF16, FMT_FP16 = 0, 1
+FMT_NAMES = {"bf16": FMT_BF16, "fp16": FMT_FP16}
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libsavsr_sm100.so")
 
@@ -83,6 +85,8 @@ SIGNATURES = {
     "savsr_ctx_create": (_I, [_I, C.POINTER(_VP)]),
     "savsr_ctx_destroy": (None, [_VP]),
     "savsr_ctx_sm_count": (_I, [_VP]),
+    "savsr_ctx_set_format": (_I, [_VP, _I]),
+    "savsr_ctx_get_format": (_I, [_VP]),
     "savsr_arena_bytes": (_SZ, [_I, _I, _I, _I]),
     "savsr_arena_create": (_I, [_VP, _VP, _I, _I, _I, _I, C.POINTER(_VP)]),
     "savsr_arena_destroy": (None, [_VP]),
@@ -90,7 +94,7 @@ SIGNATURES = {
     "savsr_arena_import": (_I, [_VP, _I, _VP, _VP]),
     "savsr_arena_export": (_I, [_VP, _I, _VP, _VP]),
     "savsr_packed_weight_bytes": (_SZ, [_I, _I, _I]),
-    "savsr_pack_conv_weight": (_I, [_VP, _I, _I, _I, _I, _I, _VP, _VP]),
+    "savsr_pack_conv_weight": (_I, [_VP, _I, _I, _I, _I, _I, _I, _VP, _VP]),
     "savsr_conv": (_I, [_VP, _VP, C.POINTER(ConvGroup), _I, _I, _I, _I, C.POINTER(RgbSkip), _I, _VP]),
     "savsr_front_conv": (_I, [_VP, _VP, _VP, _I, _I, _I, C.POINTER(FrontGroup), _I, _VP]),
     "savsr_pack_frames": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _VP]),
@@ -143,6 +147,10 @@ class Context:
         self.handle = h
         self.device = int(device)
         self.sm_count = self.lib.savsr_ctx_sm_count(h)
+
+    def set_format(self, fmt: int) -> None:
+        """16-bit storage / operand format (FMT_BF16 or FMT_FP16) used by every later call on this context."""
+        check(self.lib.savsr_ctx_set_format(self.handle, int(fmt)))
 
     def __del__(self):
         try:

@@ -193,6 +193,9 @@ class SAVSR(nn.Module):
         self._plans: Dict[tuple, engine.Plan] = {}
         self.conv_impl = os.environ.get("SAVSR_CONV_IMPL", "tap")
         self.use_graph = os.environ.get("SAVSR_GRAPH", "1") != "0"
+        # 16-bit operand format: "bf16" (throughput path, wide range) or "fp16" (same speed, 10-bit mantissa: meets the
+        # <= 1e-3 max-abs bound against the fp32 reference; needs activations below 65504)
+        self.precision = os.environ.get("SAVSR_PRECISION", "bf16")
         self.debug_taps: Tuple[str, ...] = ()
 
     # ---- reference API ---------------------------------------------------------------------------
@@ -231,14 +234,14 @@ class SAVSR(nn.Module):
             raise RuntimeError(f"module parameters on {p0.device}, input on {x.device}")
         b, _, _, h, w = x.shape
         s = engine.normalize_scale(self.scale)
-        key = (b, h, w, float(s[0]), float(s[1]), self.conv_impl, tuple(self.debug_taps), x.device.index) + self._weights_version()
+        key = (b, h, w, float(s[0]), float(s[1]), self.conv_impl, self.precision, tuple(self.debug_taps), x.device.index) + self._weights_version()
         plan = self._plans.get(key)
         if plan is None:
             if len(self._plans) >= 8:               # bound the memory held by stale plans
                 self._plans.pop(next(iter(self._plans)))
             params = {k: v for k, v in self.state_dict(keep_vars=True).items()}
             plan = engine.Plan(params, b, h, w, s, x.device, conv_impl=self.conv_impl, num_frame=self.num_frame,
-                               taps=self.debug_taps)
+                               taps=self.debug_taps, precision=self.precision)
             self._plans[key] = plan
         return plan
 

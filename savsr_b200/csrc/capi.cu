@@ -33,7 +33,7 @@ static int encode_map(savsr_ctx* ctx, CUtensorMap* tm, void* base, int nimg, int
   const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
-      tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (images %d, %dx%d, box %dx%d)", static_cast<int>(r), nimg, height,
@@ -75,6 +75,14 @@ extern "C" int savsr_ctx_create(int device, savsr_ctx** out) {
   *out = c;
   return 0;
 }
+
+extern "C" int savsr_ctx_set_format(savsr_ctx* ctx, int format) {
+  SAVSR_REQUIRE(ctx, "savsr_ctx_set_format: null context");
+  SAVSR_REQUIRE(format == SAVSR_FMT_BF16 || format == SAVSR_FMT_FP16, "savsr_ctx_set_format: unknown format %d", format);
+  ctx->fmt = format;
+  return 0;
+}
+extern "C" int savsr_ctx_get_format(const savsr_ctx* ctx) { return ctx ? ctx->fmt : -1; }
 
 extern "C" void savsr_ctx_destroy(savsr_ctx* ctx) { free(ctx); }
 extern "C" int savsr_ctx_sm_count(const savsr_ctx* ctx) { return ctx ? ctx->sm_count : 0; }

@@ -4,6 +4,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -43,6 +44,7 @@ struct savsr_ctx {
   int sm_count;
   int cc_major, cc_minor;
   void* encode_tiled;  // PFN_cuTensorMapEncodeTiled
+  int fmt;             // 16-bit storage / operand format of arenas and packed weights: SAVSR_FMT_BF16 or SAVSR_FMT_FP16
 };
 
 struct savsr_arena {
@@ -62,12 +64,23 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+// Two 16-bit floats <-> fp32.  fmt = SAVSR_FMT_BF16 (0) or SAVSR_FMT_FP16 (1); warp-uniform, so the select is free.
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi, int fmt) {
+  if (fmt) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ float h_lo(uint32_t v, int fmt) {
+  return fmt ? __half2float(__ushort_as_half(static_cast<unsigned short>(v & 0xffffu))) : __uint_as_float(v << 16);
+}
+__device__ __forceinline__ float h_hi(uint32_t v, int fmt) {
+  return fmt ? __half2float(__ushort_as_half(static_cast<unsigned short>(v >> 16))) : __uint_as_float(v & 0xffff0000u);
+}
+__device__ __forceinline__ float h_to_float(uint16_t raw, int fmt) { return h_lo(raw, fmt); }
+__device__ __forceinline__ uint16_t float_to_h(float x, int fmt) { return static_cast<uint16_t>(pack_h2(x, 0.f, fmt) & 0xffffu); }
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
@@ -171,11 +184,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t sbo
   return d;
 }
 
-// Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, both operands K-major, M = 128.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) {
+// Instruction descriptor for kind::f16: (bf16 | fp16) x same -> fp32, both operands K-major, M = 128.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int n, int fmt) {
   return (1u << 4)                              // c_format  = F32
-         | (1u << 7)                            // a_format  = BF16
-         | (1u << 10)                           // b_format  = BF16
+         | ((fmt ? 0u : 1u) << 7)               // a_format  = BF16 (1) / F16 (0)
+         | ((fmt ? 0u : 1u) << 10)              // b_format
          | (static_cast<uint32_t>(n >> 3) << 17)  // N >> 3
          | (static_cast<uint32_t>(128 >> 4) << 24);  // M >> 4
 }

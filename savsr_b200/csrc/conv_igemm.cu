@@ -55,6 +55,7 @@ struct ConvParams {
   uint32_t per_sample_mask;  // bit g set: conv g has per-sample weights (OSA-Conv)
   long long* dbg;            // optional [grid][8] cycle counters (bring-up aid), nullptr in production
   int dst_mode;
+  int fmt;              // enum savsr_format of the arena and the packed weights
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
@@ -155,9 +156,9 @@ __device__ __forceinline__ void epi_prefetch(const ConvParams& p, const savsr_co
   }
 }
 
-__device__ __forceinline__ void add_bf16x8(float* v, const uint4& u, float s) {
-  v[0] += s * bf16_lo(u.x); v[1] += s * bf16_hi(u.x); v[2] += s * bf16_lo(u.y); v[3] += s * bf16_hi(u.y);
-  v[4] += s * bf16_lo(u.z); v[5] += s * bf16_hi(u.z); v[6] += s * bf16_lo(u.w); v[7] += s * bf16_hi(u.w);
+__device__ __forceinline__ void add_h16x8(float* v, const uint4& u, float s, int fmt) {
+  v[0] += s * h_lo(u.x, fmt); v[1] += s * h_hi(u.x, fmt); v[2] += s * h_lo(u.y, fmt); v[3] += s * h_hi(u.y, fmt);
+  v[4] += s * h_lo(u.z, fmt); v[5] += s * h_hi(u.z, fmt); v[6] += s * h_lo(u.w, fmt); v[7] += s * h_hi(u.w, fmt);
 }
 
 template <int NC>
@@ -177,22 +178,22 @@ __device__ __forceinline__ void epi_finish(const ConvParams& p, const savsr_conv
     }
     if (c.res1_slot >= 0 && c.valid) {
 #pragma unroll
-      for (int j = 0; j < NC / 8; ++j) add_bf16x8(v + 8 * j, c.r1[j], 1.f);
+      for (int j = 0; j < NC / 8; ++j) add_h16x8(v + 8 * j, c.r1[j], 1.f, p.fmt);
     }
     if (c.res2_slot >= 0 && c.valid) {
       const float r2s = c.res2_scale;
 #pragma unroll
-      for (int j = 0; j < NC / 8; ++j) add_bf16x8(v + 8 * j, c.r2[j], r2s);
+      for (int j = 0; j < NC / 8; ++j) add_h16x8(v + 8 * j, c.r2[j], r2s, p.fmt);
     }
     if (c.valid) {
       uint4* d = reinterpret_cast<uint4*>(p.arena + ((static_cast<long>(c.dst_slot) * p.batch + n) * npix + c.pix) * kC + col0);
 #pragma unroll
       for (int j = 0; j < NC / 8; ++j) {
         uint4 u;
-        u.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
-        u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-        u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-        u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+        u.x = pack_h2(v[8 * j + 0], v[8 * j + 1], p.fmt);
+        u.y = pack_h2(v[8 * j + 2], v[8 * j + 3], p.fmt);
+        u.z = pack_h2(v[8 * j + 4], v[8 * j + 5], p.fmt);
+        u.w = pack_h2(v[8 * j + 6], v[8 * j + 7], p.fmt);
         d[j] = u;
       }
     }
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
     // One elected thread feeds the tensor core, so this loop is the critical path of the kernel.  The whole warp
     // runs it with warp-uniform control flow and values (so descriptors live in uniform registers and ptxas emits
     // straight UTCHMMA sequences); only the tcgen05 instructions themselves sit under elect.sync.
-    constexpr uint32_t idesc = umma_idesc_bf16(BN);
+    const uint32_t idesc = umma_idesc_f16(BN, p.fmt);
     constexpr uint32_t a_hi = desc_hi(HALO ? kHaloPitch * 128u : 1024u);
     constexpr uint32_t b_hi = desc_hi(1024u);
     const uint32_t a_lo0 = (smem_u32(smem_a) >> 4) & 0x3fffu;
@@ -638,7 +639,7 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
     // One thread cannot issue N=64 MMAs as fast as the tensor core retires them (54-58 vs 48 cycles, scripts/umma_bench.cu):
     // warp 1 takes the even tiles of a batch, warp 10 the odd ones, each into its own TMEM accumulators.
     const int my = warp == 1 ? 0 : 1;
-    constexpr uint32_t idesc = umma_idesc_bf16(BN);
+    const uint32_t idesc = umma_idesc_f16(BN, p.fmt);
     constexpr uint32_t a_hi = desc_hi(kHaloPitch * 128u);
     constexpr uint32_t b_hi = desc_hi(1024u);
     const uint32_t a_lo0 = (smem_u32(smem_a) >> 4) & 0x3fffu;
@@ -821,12 +822,12 @@ __global__ void __launch_bounds__(128) conv_check_kernel(const __grid_constant__
         const bool in = sx >= 0 && sx < p.width && sy >= 0 && sy < p.height;
         const uint8_t* wb = wptr + static_cast<long>(s * p.ntaps + tap) * (BN * 128);
         for (int k = 0; k < 64; ++k) {
-          const float a = in ? __bfloat162float(src[(static_cast<long>(sy) * p.width + sx) * kC + k]) : 0.f;
+          const float a = in ? h_to_float(reinterpret_cast<const uint16_t*>(src)[(static_cast<long>(sy) * p.width + sx) * kC + k], p.fmt) : 0.f;
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
             const int row = col0 + c;
             const int off = row * 128 + (((k >> 3) ^ (row & 7)) << 4) + (k & 7) * 2;
-            v[c] += a * __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(wb + off));
+            v[c] += a * h_to_float(*reinterpret_cast<const uint16_t*>(wb + off), p.fmt);
           }
         }
       }
@@ -840,8 +841,8 @@ __global__ void __launch_bounds__(128) conv_check_kernel(const __grid_constant__
 
 // ------------------------------------------------------------------------------------------------ weight packing
 // fp32 OIHW -> packed bf16 blocks [co/n_tile][ci/64 * k*k][n_tile][64], 128-byte swizzled rows.
-__global__ void pack_weight_kernel(const float* __restrict__ w, int co_real, int co, int ci, int ks, int n_tile,
-                                   __nv_bfloat16* __restrict__ out) {
+__global__ void pack_weight_kernel(const float* __restrict__ w, int co_real, int co, int ci, int ks, int n_tile, int fmt,
+                                   uint16_t* __restrict__ out) {
   const long total = static_cast<long>(co) * ci * ks * ks;
   const int taps = ks * ks;
   for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
@@ -857,22 +858,22 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int co_real, int
     const float val = o < co_real ? w[(static_cast<long>(o) * ci + i) * taps + tap] : 0.f;
     const long block = static_cast<long>(ng) * ((ci / 64) * taps) + kb;
     const long off = block * (n_tile * 64) + n * 64 + ((((k >> 3) ^ (n & 7)) << 3) | (k & 7));
-    out[off] = __float2bfloat16(val);
+    out[off] = float_to_h(val, fmt);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ arena import / export
-__global__ void arena_import_kernel(const float* __restrict__ nchw, __nv_bfloat16* __restrict__ dst, int batch, long npix) {
+__global__ void arena_import_kernel(const float* __restrict__ nchw, uint16_t* __restrict__ dst, int batch, long npix, int fmt) {
   const long total = static_cast<long>(batch) * npix * kC;
   for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long>(gridDim.x) * blockDim.x) {
     const int c = idx & 63;
     const long pn = idx >> 6;
     const long pix = pn % npix, n = pn / npix;
-    dst[idx] = __float2bfloat16(nchw[(n * kC + c) * npix + pix]);
+    dst[idx] = float_to_h(nchw[(n * kC + c) * npix + pix], fmt);
   }
 }
-__global__ void arena_export_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ nchw, int batch, long npix) {
+__global__ void arena_export_kernel(const uint16_t* __restrict__ src, float* __restrict__ nchw, int batch, long npix, int fmt) {
   const long total = static_cast<long>(batch) * npix * kC;
   for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -880,7 +881,7 @@ __global__ void arena_export_kernel(const __nv_bfloat16* __restrict__ src, float
     const long nc = idx / npix;
     const int c = nc % kC;
     const long n = nc / kC;
-    nchw[idx] = __bfloat162float(src[(n * npix + pix) * kC + c]);
+    nchw[idx] = h_to_float(src[(n * npix + pix) * kC + c], fmt);
   }
 }
 
@@ -943,8 +944,9 @@ extern "C" size_t savsr_packed_weight_bytes(int co, int ci, int ksize) {
   return static_cast<size_t>(co) * ci * ksize * ksize * sizeof(__nv_bfloat16);
 }
 
-extern "C" int savsr_pack_conv_weight(const float* w_oihw, int co_real, int co, int ci, int ksize, int n_tile,
+extern "C" int savsr_pack_conv_weight(const float* w_oihw, int co_real, int co, int ci, int ksize, int n_tile, int format,
                                       void* packed, savsr_stream st) {
+  SAVSR_REQUIRE(format == SAVSR_FMT_BF16 || format == SAVSR_FMT_FP16, "savsr_pack_conv_weight: unknown format %d", format);
   SAVSR_REQUIRE(w_oihw && packed, "savsr_pack_conv_weight: null pointer");
   SAVSR_REQUIRE(ksize == 1 || ksize == 3, "savsr_pack_conv_weight: ksize must be 1 or 3, got %d", ksize);
   SAVSR_REQUIRE(n_tile == 64 || n_tile == 16, "savsr_pack_conv_weight: n_tile must be 64 or 16, got %d", n_tile);
@@ -953,8 +955,8 @@ extern "C" int savsr_pack_conv_weight(const float* w_oihw, int co_real, int co, 
                 "savsr_pack_conv_weight: co (%d) must be a multiple of n_tile (%d) and >= co_real (%d)", co, n_tile, co_real);
   const long total = static_cast<long>(co) * ci * ksize * ksize;
   const int blocks = static_cast<int>((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
-  pack_weight_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(st)>>>(w_oihw, co_real, co, ci, ksize, n_tile,
-                                                                       static_cast<__nv_bfloat16*>(packed));
+  pack_weight_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(st)>>>(w_oihw, co_real, co, ci, ksize, n_tile, format,
+                                                                       static_cast<uint16_t*>(packed));
   SAVSR_CUDA(cudaGetLastError());
   return 0;
 }
@@ -964,7 +966,7 @@ extern "C" int savsr_arena_import(savsr_arena* a, int slot, const float* nchw, s
   SAVSR_REQUIRE(slot >= 0 && slot < a->nslots, "savsr_arena_import: slot %d out of range [0,%d)", slot, a->nslots);
   const long npix = static_cast<long>(a->height) * a->width;
   arena_import_kernel<<<1024, 256, 0, static_cast<cudaStream_t>(st)>>>(
-      nchw, a->base + static_cast<long>(slot) * a->batch * npix * kC, a->batch, npix);
+      nchw, reinterpret_cast<uint16_t*>(a->base + static_cast<long>(slot) * a->batch * npix * kC), a->batch, npix, a->ctx->fmt);
   SAVSR_CUDA(cudaGetLastError());
   return 0;
 }
@@ -974,7 +976,7 @@ extern "C" int savsr_arena_export(savsr_arena* a, int slot, float* nchw, savsr_s
   SAVSR_REQUIRE(slot >= 0 && slot < a->nslots, "savsr_arena_export: slot %d out of range [0,%d)", slot, a->nslots);
   const long npix = static_cast<long>(a->height) * a->width;
   arena_export_kernel<<<1024, 256, 0, static_cast<cudaStream_t>(st)>>>(
-      a->base + static_cast<long>(slot) * a->batch * npix * kC, nchw, a->batch, npix);
+      reinterpret_cast<const uint16_t*>(a->base + static_cast<long>(slot) * a->batch * npix * kC), nchw, a->batch, npix, a->ctx->fmt);
   SAVSR_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1026,6 +1028,7 @@ extern "C" int savsr_conv(savsr_ctx* ctx, savsr_arena* arena, const savsr_conv_g
   const int nkb = p.nsrc * p.ntaps;
   p.n_res = nkb <= kBBlocks ? nkb : kBBlocks - kRing;
   p.dst_mode = dst_mode;
+  p.fmt = ctx->fmt;
   p.dbg = g_conv_dbg;
   if (n_tile == 64) return launch_conv<64>(ctx, p, impl, static_cast<cudaStream_t>(st));
   return launch_conv<16>(ctx, p, impl, static_cast<cudaStream_t>(st));

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(128) satu_table_kernel(const savsr_satu_weight
 // sta[c] = sum_tap xpad[y+u, x+v, c] * K[tap][c], replicate padding on the h x w region (savsr_arch.py:297-313).
 // One (pixel, 8-channel chunk) per thread; 16-byte loads of bf16.
 __global__ void __launch_bounds__(256) satu_sta_kernel(const __nv_bfloat16* __restrict__ arena, int batch, int hp, int wp,
-                                                       int h, int w, int x_slot, int kslot0, int dst_slot) {
+                                                       int h, int w, int x_slot, int kslot0, int dst_slot, int fmt) {
   const long npix = static_cast<long>(hp) * wp;
   const long id = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   const int n = blockIdx.y;
@@ -126,15 +126,15 @@ __global__ void __launch_bounds__(256) satu_sta_kernel(const __nv_bfloat16* __re
       const int sx = min(max(px + tap % 5 - 2, 0), w - 1);
       const uint4 xv = *reinterpret_cast<const uint4*>(xs + (static_cast<long>(sy) * wp + sx) * kC + chunk * 8);
       const uint4 kv = *reinterpret_cast<const uint4*>(arena + ((static_cast<long>(kslot0 + tap) * batch + n) * npix + pix) * kC + chunk * 8);
-      acc[0] += bf16_lo(xv.x) * bf16_lo(kv.x); acc[1] += bf16_hi(xv.x) * bf16_hi(kv.x);
-      acc[2] += bf16_lo(xv.y) * bf16_lo(kv.y); acc[3] += bf16_hi(xv.y) * bf16_hi(kv.y);
-      acc[4] += bf16_lo(xv.z) * bf16_lo(kv.z); acc[5] += bf16_hi(xv.z) * bf16_hi(kv.z);
-      acc[6] += bf16_lo(xv.w) * bf16_lo(kv.w); acc[7] += bf16_hi(xv.w) * bf16_hi(kv.w);
+      acc[0] += h_lo(xv.x, fmt) * h_lo(kv.x, fmt); acc[1] += h_hi(xv.x, fmt) * h_hi(kv.x, fmt);
+      acc[2] += h_lo(xv.y, fmt) * h_lo(kv.y, fmt); acc[3] += h_hi(xv.y, fmt) * h_hi(kv.y, fmt);
+      acc[4] += h_lo(xv.z, fmt) * h_lo(kv.z, fmt); acc[5] += h_hi(xv.z, fmt) * h_hi(kv.z, fmt);
+      acc[6] += h_lo(xv.w, fmt) * h_lo(kv.w, fmt); acc[7] += h_hi(xv.w, fmt) * h_hi(kv.w, fmt);
     }
   }
   uint4 o;
-  o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
-  o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
+  o.x = pack_h2(acc[0], acc[1], fmt); o.y = pack_h2(acc[2], acc[3], fmt);
+  o.z = pack_h2(acc[4], acc[5], fmt); o.w = pack_h2(acc[6], acc[7], fmt);
   *reinterpret_cast<uint4*>(const_cast<__nv_bfloat16*>(arena) + ((static_cast<long>(dst_slot) * batch + n) * npix + pix) * kC + chunk * 8) = o;
 }
 
@@ -149,6 +149,7 @@ struct GatherParams {
   const float* expand;    // [4][64][8]
   int batch, hp, wp, h, w, H, W;
   int x_slot, sta_slot, sta_dst, fea_dst;
+  int fmt;
 };
 
 struct Corner4 {
@@ -242,20 +243,20 @@ __global__ void __launch_bounds__(kGatherPix) satu_gather_kernel(const GatherPar
       if (c1.off[q] >= 0) {
         const uint4 v = *reinterpret_cast<const uint4*>(xs + c1.off[q] + chunk * 8);
         const float wgt = c1.wt[q];
-        a[0] += wgt * bf16_lo(v.x); a[1] += wgt * bf16_hi(v.x); a[2] += wgt * bf16_lo(v.y); a[3] += wgt * bf16_hi(v.y);
-        a[4] += wgt * bf16_lo(v.z); a[5] += wgt * bf16_hi(v.z); a[6] += wgt * bf16_lo(v.w); a[7] += wgt * bf16_hi(v.w);
+        a[0] += wgt * h_lo(v.x, p.fmt); a[1] += wgt * h_hi(v.x, p.fmt); a[2] += wgt * h_lo(v.y, p.fmt); a[3] += wgt * h_hi(v.y, p.fmt);
+        a[4] += wgt * h_lo(v.z, p.fmt); a[5] += wgt * h_hi(v.z, p.fmt); a[6] += wgt * h_lo(v.w, p.fmt); a[7] += wgt * h_hi(v.w, p.fmt);
       }
       if (c2.off[q] >= 0) {
         const uint4 v = *reinterpret_cast<const uint4*>(ss + c2.off[q] + chunk * 8);
         const float wgt = c2.wt[q];
-        b[0] += wgt * bf16_lo(v.x); b[1] += wgt * bf16_hi(v.x); b[2] += wgt * bf16_lo(v.y); b[3] += wgt * bf16_hi(v.y);
-        b[4] += wgt * bf16_lo(v.z); b[5] += wgt * bf16_hi(v.z); b[6] += wgt * bf16_lo(v.w); b[7] += wgt * bf16_hi(v.w);
+        b[0] += wgt * h_lo(v.x, p.fmt); b[1] += wgt * h_hi(v.x, p.fmt); b[2] += wgt * h_lo(v.y, p.fmt); b[3] += wgt * h_hi(v.y, p.fmt);
+        b[4] += wgt * h_lo(v.z, p.fmt); b[5] += wgt * h_hi(v.z, p.fmt); b[6] += wgt * h_lo(v.w, p.fmt); b[7] += wgt * h_hi(v.w, p.fmt);
       }
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) f_s[lp * kFStride + chunk * 8 + e] = a[e];
     uint4 o;
-    o.x = pack_bf16(b[0], b[1]); o.y = pack_bf16(b[2], b[3]); o.z = pack_bf16(b[4], b[5]); o.w = pack_bf16(b[6], b[7]);
+    o.x = pack_h2(b[0], b[1], p.fmt); o.y = pack_h2(b[2], b[3], p.fmt); o.z = pack_h2(b[4], b[5], p.fmt); o.w = pack_h2(b[6], b[7], p.fmt);
     *reinterpret_cast<uint4*>(sta_out + (pix0 + lp) * kC + chunk * 8) = o;
   }
   __syncthreads();
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(kGatherPix) satu_gather_kernel(const GatherPar
     if (pix0 + lp >= NPIX) continue;
     const float* f = f_s + lp * kFStride + chunk * 8;
     uint4 o;
-    o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+    o.x = pack_h2(f[0], f[1], p.fmt); o.y = pack_h2(f[2], f[3], p.fmt); o.z = pack_h2(f[4], f[5], p.fmt); o.w = pack_h2(f[6], f[7], p.fmt);
     *reinterpret_cast<uint4*>(fea_out + (pix0 + lp) * kC + chunk * 8) = o;
   }
 }
@@ -339,12 +340,13 @@ struct FusedParams {
   int batch, hp, wp, h, w, H, W;
   int x_slot, sta_slot, dst_slot;
   int tiles_per_img;
+  int fmt;
 };
 
 constexpr int kFusedThreads = 256;   // 8 warps: warp w owns TMEM lane quadrant w & 3 and column half w >> 2
 constexpr int kFusedSmem = 1024 + 3 * 16384 + 4096 + 8192 + 16384 + 2 * 128 * 32 + 128 * 16 + 256 + 64;
 
-__device__ __forceinline__ void gather8(const __nv_bfloat16* img, const Corner4& c, int chunk, float (&a)[8]) {
+__device__ __forceinline__ void gather8(const __nv_bfloat16* img, const Corner4& c, int chunk, float (&a)[8], int fmt) {
   uint4 v[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) v[q] = c.off[q] >= 0 ? *reinterpret_cast<const uint4*>(img + c.off[q] + chunk * 8) : make_uint4(0, 0, 0, 0);
@@ -353,13 +355,13 @@ __device__ __forceinline__ void gather8(const __nv_bfloat16* img, const Corner4&
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const float wgt = c.wt[q];
-    a[0] += wgt * bf16_lo(v[q].x); a[1] += wgt * bf16_hi(v[q].x); a[2] += wgt * bf16_lo(v[q].y); a[3] += wgt * bf16_hi(v[q].y);
-    a[4] += wgt * bf16_lo(v[q].z); a[5] += wgt * bf16_hi(v[q].z); a[6] += wgt * bf16_lo(v[q].w); a[7] += wgt * bf16_hi(v[q].w);
+    a[0] += wgt * h_lo(v[q].x, fmt); a[1] += wgt * h_hi(v[q].x, fmt); a[2] += wgt * h_lo(v[q].y, fmt); a[3] += wgt * h_hi(v[q].y, fmt);
+    a[4] += wgt * h_lo(v[q].z, fmt); a[5] += wgt * h_hi(v[q].z, fmt); a[6] += wgt * h_lo(v[q].w, fmt); a[7] += wgt * h_hi(v[q].w, fmt);
   }
 }
-__device__ __forceinline__ uint4 pack8(const float (&a)[8]) {
+__device__ __forceinline__ uint4 pack8(const float (&a)[8], int fmt) {
   uint4 o;
-  o.x = pack_bf16(a[0], a[1]); o.y = pack_bf16(a[2], a[3]); o.z = pack_bf16(a[4], a[5]); o.w = pack_bf16(a[6], a[7]);
+  o.x = pack_h2(a[0], a[1], fmt); o.y = pack_h2(a[2], a[3], fmt); o.z = pack_h2(a[4], a[5], fmt); o.w = pack_h2(a[6], a[7], fmt);
   return o;
 }
 // byte offset of 16-byte chunk `c` of row `r` in a [rows][128 B] SWIZZLE_128B tile
@@ -440,10 +442,10 @@ __global__ void __launch_bounds__(kFusedThreads, 2) satu_fused_kernel(const Fuse
       const int id = it * kFusedThreads + tid;
       const int lp = id >> 3, chunk = id & 7;
       float a[8], b[8];
-      gather8(xs, cx[lp], chunk, a);
-      gather8(ss, cs[lp], chunk, b);
-      *reinterpret_cast<uint4*>(sF + swz(lp, chunk)) = pack8(a);
-      *reinterpret_cast<uint4*>(sS + swz(lp, chunk)) = pack8(b);
+      gather8(xs, cx[lp], chunk, a, p.fmt);
+      gather8(ss, cs[lp], chunk, b, p.fmt);
+      *reinterpret_cast<uint4*>(sF + swz(lp, chunk)) = pack8(a, p.fmt);
+      *reinterpret_cast<uint4*>(sS + swz(lp, chunk)) = pack8(b, p.fmt);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
@@ -453,7 +455,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) satu_fused_kernel(const Fuse
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tU, make_desc64(hi, loF + 2 * k), make_desc64(hi, loWc + 2 * k), umma_idesc_bf16(32), k ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_bf16(tU, make_desc64(hi, loF + 2 * k), make_desc64(hi, loWc + 2 * k), umma_idesc_f16(32, p.fmt), k ? 1u : 0u);
         umma_commit(bar);
       }
       __syncwarp();
@@ -477,7 +479,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) satu_fused_kernel(const Fuse
         float v[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] = re[e] * tk[k];
-        *reinterpret_cast<uint4*>(sV + swz(row, e)) = pack8(v);
+        *reinterpret_cast<uint4*>(sV + swz(row, e)) = pack8(v, p.fmt);
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -488,7 +490,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) satu_fused_kernel(const Fuse
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 2; ++k) umma_bf16(tO, make_desc64(hi, loV + 2 * k), make_desc64(hi, loWe + 2 * k), umma_idesc_bf16(64), k ? 1u : 0u);
+        for (int k = 0; k < 2; ++k) umma_bf16(tO, make_desc64(hi, loV + 2 * k), make_desc64(hi, loWe + 2 * k), umma_idesc_f16(64, p.fmt), k ? 1u : 0u);
         umma_commit(bar);
       }
       __syncwarp();
@@ -506,11 +508,11 @@ __global__ void __launch_bounds__(kFusedThreads, 2) satu_fused_kernel(const Fuse
         uint4* ptr = reinterpret_cast<uint4*>(sF + swz(row, half * 4 + 2 * j + c2));
         const uint4 f = *ptr;
         float v[8];
-        v[0] = __uint_as_float(o[8 * c2 + 0]) + bf16_lo(f.x); v[1] = __uint_as_float(o[8 * c2 + 1]) + bf16_hi(f.x);
-        v[2] = __uint_as_float(o[8 * c2 + 2]) + bf16_lo(f.y); v[3] = __uint_as_float(o[8 * c2 + 3]) + bf16_hi(f.y);
-        v[4] = __uint_as_float(o[8 * c2 + 4]) + bf16_lo(f.z); v[5] = __uint_as_float(o[8 * c2 + 5]) + bf16_hi(f.z);
-        v[6] = __uint_as_float(o[8 * c2 + 6]) + bf16_lo(f.w); v[7] = __uint_as_float(o[8 * c2 + 7]) + bf16_hi(f.w);
-        *ptr = pack8(v);
+        v[0] = __uint_as_float(o[8 * c2 + 0]) + h_lo(f.x, p.fmt); v[1] = __uint_as_float(o[8 * c2 + 1]) + h_hi(f.x, p.fmt);
+        v[2] = __uint_as_float(o[8 * c2 + 2]) + h_lo(f.y, p.fmt); v[3] = __uint_as_float(o[8 * c2 + 3]) + h_hi(f.y, p.fmt);
+        v[4] = __uint_as_float(o[8 * c2 + 4]) + h_lo(f.z, p.fmt); v[5] = __uint_as_float(o[8 * c2 + 5]) + h_hi(f.z, p.fmt);
+        v[6] = __uint_as_float(o[8 * c2 + 6]) + h_lo(f.w, p.fmt); v[7] = __uint_as_float(o[8 * c2 + 7]) + h_hi(f.w, p.fmt);
+        *ptr = pack8(v, p.fmt);
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -521,9 +523,9 @@ __global__ void __launch_bounds__(kFusedThreads, 2) satu_fused_kernel(const Fuse
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tY, make_desc64(hi, loS + 2 * k), make_desc64(hi, loWf + 2 * k), umma_idesc_bf16(64), k ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_bf16(tY, make_desc64(hi, loS + 2 * k), make_desc64(hi, loWf + 2 * k), umma_idesc_f16(64, p.fmt), k ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tY, make_desc64(hi, loF + 2 * k), make_desc64(hi, loWf + 512 + 2 * k), umma_idesc_bf16(64), 1u);
+        for (int k = 0; k < 4; ++k) umma_bf16(tY, make_desc64(hi, loF + 2 * k), make_desc64(hi, loWf + 512 + 2 * k), umma_idesc_f16(64, p.fmt), 1u);
         umma_commit(bar);
       }
       __syncwarp();
@@ -546,7 +548,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) satu_fused_kernel(const Fuse
             float v[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(y[8 * c2 + e]) + sbias[half * 32 + 16 * j + 8 * c2 + e];
-            d[2 * j + c2] = pack8(v);
+            d[2 * j + c2] = pack8(v, p.fmt);
           }
         }
       }
@@ -594,7 +596,7 @@ extern "C" int savsr_satu_sta(savsr_ctx* ctx, savsr_arena* arena, int x_slot, in
   if (arena->batch == 0) return 0;
   const long ids = static_cast<long>(arena->height) * arena->width * 8;
   satu_sta_kernel<<<dim3(static_cast<unsigned>((ids + 255) / 256), arena->batch), 256, 0, static_cast<cudaStream_t>(st)>>>(
-      arena->base, arena->batch, arena->height, arena->width, h, w, x_slot, kslot0, dst_slot);
+      arena->base, arena->batch, arena->height, arena->width, h, w, x_slot, kslot0, dst_slot, ctx->fmt);
   SAVSR_CUDA(cudaGetLastError());
   return 0;
 }
@@ -618,7 +620,7 @@ extern "C" int savsr_satu_gather(savsr_ctx* ctx, savsr_arena* lr, int x_slot, in
   p.lr = lr->base; p.hr = hr->base; p.table = table; p.base_y = base_y; p.base_x = base_x;
   p.compress = wts->compress; p.expand = wts->expand;
   p.batch = lr->batch; p.hp = lr->height; p.wp = lr->width; p.h = h; p.w = w; p.H = hr->height; p.W = hr->width;
-  p.x_slot = x_slot; p.sta_slot = sta_slot; p.sta_dst = sta_dst; p.fea_dst = fea_dst;
+  p.x_slot = x_slot; p.sta_slot = sta_slot; p.sta_dst = sta_dst; p.fea_dst = fea_dst; p.fmt = ctx->fmt;
   const long npix = static_cast<long>(p.H) * p.W;
   satu_gather_kernel<<<dim3(static_cast<unsigned>((npix + kGatherPix - 1) / kGatherPix), lr->batch), kGatherPix, kGatherSmem,
                        static_cast<cudaStream_t>(st)>>>(p);
@@ -645,7 +647,7 @@ extern "C" int savsr_satu_fused(savsr_ctx* ctx, savsr_arena* lr, int x_slot, int
   p.w_compress = static_cast<const uint8_t*>(w_compress); p.w_expand = static_cast<const uint8_t*>(w_expand);
   p.w_fusion = static_cast<const uint8_t*>(w_fusion); p.bias = fusion_bias;
   p.batch = lr->batch; p.hp = lr->height; p.wp = lr->width; p.h = h; p.w = w; p.H = hr->height; p.W = hr->width;
-  p.x_slot = x_slot; p.sta_slot = sta_slot; p.dst_slot = dst_slot;
+  p.x_slot = x_slot; p.sta_slot = sta_slot; p.dst_slot = dst_slot; p.fmt = ctx->fmt;
   const long npix = static_cast<long>(p.H) * p.W;
   p.tiles_per_img = static_cast<int>((npix + 127) / 128);
   const int total = p.batch * p.tiles_per_img;

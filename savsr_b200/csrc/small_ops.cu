@@ -13,6 +13,7 @@ struct FrontParams {
   const float* x;
   __nv_bfloat16* arena;
   int ngroups, batch, t, h, w, hp, wp;
+  int fmt;
 };
 
 // dst = LeakyReLU_0.2(conv3x3(cat(frames)) + bias) on the reflect-padded (even-sized) frames.
@@ -70,8 +71,8 @@ __global__ void __launch_bounds__(128) front_conv_kernel(const __grid_constant__
       r[e] = v > 0.f ? v : 0.2f * v;
     }
     uint4 u;
-    u.x = pack_bf16(r[0], r[1]); u.y = pack_bf16(r[2], r[3]);
-    u.z = pack_bf16(r[4], r[5]); u.w = pack_bf16(r[6], r[7]);
+    u.x = pack_h2(r[0], r[1], p.fmt); u.y = pack_h2(r[2], r[3], p.fmt);
+    u.z = pack_h2(r[4], r[5], p.fmt); u.w = pack_h2(r[6], r[7], p.fmt);
     d[j] = u;
   }
 }
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(128) front_conv_kernel(const __grid_constant__
 // (channel 3f + c), the rest zero, reflect-padded to the even arena size (savsr_arch.py:670-690).  With this slot the
 // first-layer convs (conv_c / conv_sup, savsr_arch.py:456-457) run on the tensor-core kernel with zero-expanded weights.
 __global__ void __launch_bounds__(256) pack_frames_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ dst, int batch,
-                                                          int t, int h, int w, int hp, int wp) {
+                                                          int t, int h, int w, int hp, int wp, int fmt) {
   const long npix = static_cast<long>(hp) * wp;
   const long total = static_cast<long>(batch) * npix * 8;
   for (long id = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; id < total; id += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(256) pack_frames_kernel(const float* __restric
       v[e] = ch < 3 * t ? __ldg(x + ((static_cast<long>(n) * t * 3 + ch) * h + ry) * w + rx) : 0.f;
     }
     uint4 o;
-    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+    o.x = pack_h2(v[0], v[1], fmt); o.y = pack_h2(v[2], v[3], fmt); o.z = pack_h2(v[4], v[5], fmt); o.w = pack_h2(v[6], v[7], fmt);
     *reinterpret_cast<uint4*>(dst + (static_cast<long>(n) * npix + pix) * kC + chunk * 8) = o;
   }
 }
@@ -108,6 +109,7 @@ struct OsaLaunch {
   savsr_osa_params c[kMaxOsa];
   int nconvs, batch, npart, npix;
   float inv_h, inv_w;
+  int fmt;
 };
 __host__ __device__ inline int osa_scratch_stride(int ci) { return 5 * ci + 192; }
 __host__ __device__ inline int osa_off_h1(int ci) { return ci + 8; }
@@ -248,13 +250,13 @@ __global__ void __launch_bounds__(256) osa_assemble_kernel(const __grid_constant
     const float ca = att[i], fa = att[c.ci + o];
     const float* sa = att + c.ci + c.co;
     const float* ka = sa + 9;
-    __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(c.packed) + n * sample_elems;
+    uint16_t* dst = static_cast<uint16_t*>(c.packed) + n * sample_elems;
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       float acc = 0.f;
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc += ka[k] * bk[k][t];
-      dst[static_cast<long>(s * 9 + t) * 4096 + inner] = __float2bfloat16(acc * sa[t] * ca * fa);
+      dst[static_cast<long>(s * 9 + t) * 4096 + inner] = float_to_h(acc * sa[t] * ca * fa, L.fmt);
     }
   }
 }
@@ -268,6 +270,7 @@ struct CaParams {
   const float *w1, *b1, *w2, *b2;
   float* y;      // [batch][64] channel scales (scratch)
   int npart;
+  int fmt;
   long npix;
 };
 // y = sigmoid(W2 relu(W1 mean(t) + b1) + b2) per sample (savsr_arch.py:514-519).  grid (batch), 1024 threads.
@@ -319,10 +322,10 @@ __global__ void __launch_bounds__(256) ca_scale_residual_kernel(const CaParams p
     const int c0 = (id & 7) * 8;
     const uint4 a = tt[id], b = xx[id];
     uint4 o;
-    o.x = pack_bf16(bf16_lo(b.x) + bf16_lo(a.x) * ys[c0 + 0], bf16_hi(b.x) + bf16_hi(a.x) * ys[c0 + 1]);
-    o.y = pack_bf16(bf16_lo(b.y) + bf16_lo(a.y) * ys[c0 + 2], bf16_hi(b.y) + bf16_hi(a.y) * ys[c0 + 3]);
-    o.z = pack_bf16(bf16_lo(b.z) + bf16_lo(a.z) * ys[c0 + 4], bf16_hi(b.z) + bf16_hi(a.z) * ys[c0 + 5]);
-    o.w = pack_bf16(bf16_lo(b.w) + bf16_lo(a.w) * ys[c0 + 6], bf16_hi(b.w) + bf16_hi(a.w) * ys[c0 + 7]);
+    o.x = pack_h2(h_lo(b.x, p.fmt) + h_lo(a.x, p.fmt) * ys[c0 + 0], h_hi(b.x, p.fmt) + h_hi(a.x, p.fmt) * ys[c0 + 1], p.fmt);
+    o.y = pack_h2(h_lo(b.y, p.fmt) + h_lo(a.y, p.fmt) * ys[c0 + 2], h_hi(b.y, p.fmt) + h_hi(a.y, p.fmt) * ys[c0 + 3], p.fmt);
+    o.z = pack_h2(h_lo(b.z, p.fmt) + h_lo(a.z, p.fmt) * ys[c0 + 4], h_hi(b.z, p.fmt) + h_hi(a.z, p.fmt) * ys[c0 + 5], p.fmt);
+    o.w = pack_h2(h_lo(b.w, p.fmt) + h_lo(a.w, p.fmt) * ys[c0 + 6], h_hi(b.w, p.fmt) + h_hi(a.w, p.fmt) * ys[c0 + 7], p.fmt);
     dd[id] = o;
   }
 }
@@ -503,7 +506,7 @@ extern "C" int savsr_front_conv(savsr_ctx* ctx, savsr_arena* arena, const float*
     p.g[i] = g;
   }
   p.x = x; p.arena = arena->base; p.ngroups = ngroups; p.batch = arena->batch;
-  p.t = t; p.h = h; p.w = w; p.hp = arena->height; p.wp = arena->width;
+  p.t = t; p.h = h; p.w = w; p.hp = arena->height; p.wp = arena->width; p.fmt = ctx->fmt;
   const long npix = static_cast<long>(p.hp) * p.wp;
   dim3 grid(static_cast<unsigned>((npix + 127) / 128), arena->batch, ngroups);
   front_conv_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(st)>>>(p);
@@ -523,7 +526,7 @@ extern "C" int savsr_pack_frames(savsr_ctx* ctx, savsr_arena* arena, const float
   const long total = arena->batch * npix * 8;
   const int blocks = static_cast<int>((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
   pack_frames_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(st)>>>(x, arena->base + static_cast<long>(dst_slot) * arena->batch * npix * kC,
-                                                                       arena->batch, t, h, w, arena->height, arena->width);
+                                                                       arena->batch, t, h, w, arena->height, arena->width, ctx->fmt);
   SAVSR_CUDA(cudaGetLastError());
   return 0;
 }
@@ -551,6 +554,7 @@ extern "C" int savsr_osa_prologue(savsr_ctx* ctx, const savsr_osa_params* convs,
   }
   L.nconvs = nconvs; L.batch = batch; L.npart = npart; L.npix = npix;
   L.inv_h = inv_scale_h; L.inv_w = inv_scale_w;
+  L.fmt = ctx->fmt;
   osa_pool_kernel<<<dim3(max_ci / 64, batch, nconvs), kOsaThreads, 0, st>>>(L);
   const size_t lin_smem = static_cast<size_t>(batch) * 2 * max_ci * sizeof(float);
   SAVSR_REQUIRE(lin_smem <= 200 * 1024, "savsr_osa_prologue: batch %d too large for the routing kernel's shared memory", batch);
@@ -579,7 +583,7 @@ extern "C" int savsr_ca_scale_residual(savsr_ctx* ctx, savsr_arena* arena, int t
   p.t = arena->base + t_slot * img;
   p.x = arena->base + x_slot * img;
   p.dst = arena->base + dst_slot * img;
-  p.pool = pool; p.npart = npart; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.y = y_scratch;
+  p.fmt = ctx->fmt; p.pool = pool; p.npart = npart; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.y = y_scratch;
   long blocks = (p.npix * 8 + 255) / 256;
   const long cap = 8L * ctx->sm_count / (arena->batch > 0 ? arena->batch : 1) + 1;
   if (blocks > cap) blocks = cap;

@@ -77,7 +77,7 @@ class _Slots:
 
 class Plan:
     def __init__(self, params: Dict[str, torch.Tensor], batch: int, h: int, w: int, scale, device: torch.device,
-                 conv_impl: str = "tap", num_frame: int = 7, taps: Optional[Sequence[str]] = None):
+                 conv_impl: str = "tap", num_frame: int = 7, taps: Optional[Sequence[str]] = None, precision: str = "bf16"):
         if device.type != "cuda":
             raise K.SavsrError("savsr_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
         if num_frame != 7:
@@ -88,6 +88,9 @@ class Plan:
         self.ctx = context(device.index if device.index is not None else torch.cuda.current_device())
         self.lib = self.ctx.lib
         self.impl = K.IMPL_NAMES[conv_impl]
+        if precision not in K.FMT_NAMES:
+            raise ValueError(f"precision must be one of {sorted(K.FMT_NAMES)}, got {precision!r}")
+        self.fmt = K.FMT_NAMES[precision]
         self.B, self.h, self.w, self.t = batch, h, w, num_frame
         self.scale = normalize_scale(scale)
         self.hp, self.wp = h + (h & 1), w + (w & 1)
@@ -104,6 +107,7 @@ class Plan:
         self._pool_cache: Dict[str, int] = {}
         self._osa_cache: Dict[str, Tuple[K.OsaParams, int, int]] = {}
         with torch.cuda.device(device), torch.no_grad():
+            self.ctx.set_format(self.fmt)
             self._build()
 
     # ------------------------------------------------------------------ memory helpers
@@ -140,7 +144,7 @@ class Plan:
         co = co_pad or co_real
         out = self._buf(self.lib.savsr_packed_weight_bytes(co, ci, ks), dtype=torch.uint8)
         self._keep.append(w)
-        K.check(self.lib.savsr_pack_conv_weight(w.data_ptr(), co_real, co, ci, ks, n_tile, out.data_ptr(),
+        K.check(self.lib.savsr_pack_conv_weight(w.data_ptr(), co_real, co, ci, ks, n_tile, self.fmt, out.data_ptr(),
                                                 torch.cuda.current_stream().cuda_stream))
         return out.data_ptr()
 
@@ -448,6 +452,7 @@ class Plan:
     # ------------------------------------------------------------------ execution
     def run(self) -> None:
         """Launch the whole forward on the current stream (x_in -> out)."""
+        self.ctx.set_format(self.fmt)           # the format is context state read at launch (baked into captured graphs)
         st = torch.cuda.current_stream().cuda_stream
         for op in self.ops:
             rc = op(st)
@@ -457,6 +462,7 @@ class Plan:
     def run_profiled(self) -> Dict[str, Dict[str, float]]:
         """Eager run with a CUDA-event pair around every op on the launching stream.
         Returns {kind: {"ms": total device ms, "flops": algorithmic FLOPs, "ops": count, "launches": kernels}}."""
+        self.ctx.set_format(self.fmt)
         stream = torch.cuda.current_stream()
         st = stream.cuda_stream
         evs = []

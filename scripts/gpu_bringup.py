@@ -55,6 +55,9 @@ CHECKS = {
     "forward_tap_odd_b2": "check_forward(b=2, h=13, w=15, scale=(1.5, 4), sd_seed=1, in_seed=1236, impl='tap')",
     "forward_tap_graph": "check_forward(b=1, h=16, w=20, scale=(2.7, 2.7), impl='tap', graph=True)",
     "forward_halo": "check_forward(b=1, h=16, w=20, scale=(2, 2), impl='halo')",
+    "forward_halo_fp16": "check_forward(b=1, h=16, w=20, scale=(2, 2), impl='halo', precision='fp16', tol=1e-3, stage_tol=0.01)",
+    "forward_fp16_odd_b2": "check_forward(b=2, h=13, w=15, scale=(1.5, 4), sd_seed=1, in_seed=1236, impl='halo', precision='fp16', tol=1e-3, stage_tol=0.01)",
+    "forward_fp16_x2p7_graph": "check_forward(b=1, h=16, w=20, scale=(2.7, 2.7), impl='halo', graph=True, precision='fp16', tol=1e-3, stage_tol=0.01)",
 }
 
 

@@ -37,7 +37,7 @@ class FakeArena:
 @contextlib.contextmanager
 def mocked_engine():
     lib = FakeLib()
-    ctx = SimpleNamespace(lib=lib, handle="ctx", sm_count=148)
+    ctx = SimpleNamespace(lib=lib, handle="ctx", sm_count=148, set_format=lambda f: None)
     saved = (engine.context, K.Arena, K.check, torch.cuda.current_stream, torch.cuda.device)
     engine.context = lambda idx: ctx
     K.Arena = FakeArena
@@ -67,6 +67,7 @@ class CpuPlan(engine.Plan):
         self.ctx = engine.context(0)
         self.lib = self.ctx.lib
         self.impl = K.IMPL_NAMES[kw.get("conv_impl", "tap")]
+        self.fmt = K.FMT_NAMES[kw.get("precision", "bf16")]
         self.B, self.h, self.w, self.t = batch, h, w, 7
         self.scale = engine.normalize_scale(scale)
         self.hp, self.wp = h + (h & 1), w + (w & 1)

@@ -32,13 +32,23 @@ def ctx() -> K.Context:
     return engine.context(0)
 
 
+def set_precision(name: str) -> None:
+    """Switch the context's 16-bit operand format ("bf16" / "fp16") for the kernel-level checks."""
+    ctx().set_format(K.FMT_NAMES[name])
+
+
+def _h16() -> torch.dtype:
+    return torch.float16 if K.load().savsr_ctx_get_format(ctx().handle) == K.FMT_FP16 else torch.bfloat16
+
+
 def bf16_round(t: torch.Tensor) -> torch.Tensor:
-    return t.to(torch.bfloat16).to(torch.float32)
+    """Round to the context's 16-bit operand format (bf16 by default) and back to fp32."""
+    return t.to(_h16()).to(torch.float32)
 
 
 class ArenaBox:
     def __init__(self, nslots: int, batch: int, height: int, width: int):
-        self.t = torch.zeros(nslots * batch, height, width, 64, dtype=torch.bfloat16, device=DEV)
+        self.t = torch.zeros(nslots * batch, height, width, 64, dtype=_h16(), device=DEV)
         self.a = K.Arena(ctx(), self.t.data_ptr(), nslots, batch, height, width)
         self.B, self.H, self.W = batch, height, width
 
@@ -59,13 +69,13 @@ def pack_weight(w: torch.Tensor, n_tile: int = 64, co_pad=None) -> torch.Tensor:
     co_real, ci, ks, _ = w.shape
     co = co_pad or co_real
     out = torch.empty(lib.savsr_packed_weight_bytes(co, ci, ks), dtype=torch.uint8, device=DEV)
-    K.check(lib.savsr_pack_conv_weight(w.data_ptr(), co_real, co, ci, ks, n_tile, out.data_ptr(), _stream()))
+    K.check(lib.savsr_pack_conv_weight(w.data_ptr(), co_real, co, ci, ks, n_tile, lib.savsr_ctx_get_format(ctx().handle), out.data_ptr(), _stream()))
     return out
 
 
 def unpack_weight(packed: torch.Tensor, co: int, ci: int, ks: int, n_tile: int = 64) -> torch.Tensor:
     """Inverse of the packed layout (python restatement of the swizzle) -> fp32 [co][ci][ks][ks]."""
-    v = packed.view(torch.bfloat16).float().cpu().numpy()
+    v = packed.view(_h16()).float().cpu().numpy()
     taps = ks * ks
     nkb = (ci // 64) * taps
     v = v.reshape(co // n_tile, nkb, n_tile * 64)
@@ -561,12 +571,12 @@ def check_img_metrics(n=3, H=37, W=53, seed=31):
 TAPS = ("f2p_last", "p2f_last", "align", "rg0", "rg3", "trunk", "satu_sta", "satu_out")
 
 
-def run_forward(sd, x, scale, impl="tap", taps=(), graph=False):
+def run_forward(sd, x, scale, impl="tap", taps=(), graph=False, precision="bf16"):
     import savsr_b200
     net = savsr_b200.SAVSR().to(DEV)
     net.load_state_dict(sd, strict=True)
     net.eval()
-    net.conv_impl, net.use_graph, net.debug_taps = impl, graph, tuple(taps)
+    net.conv_impl, net.use_graph, net.debug_taps, net.precision = impl, graph, tuple(taps), precision
     net.set_scale(scale)
     with torch.no_grad():
         y = net(x.to(DEV))
@@ -587,7 +597,8 @@ def stage_report(got: dict, ref: dict, h, w) -> dict:
     return rep
 
 
-def check_forward(b=1, h=16, w=20, scale=(2, 2), sd_seed=0, in_seed=1234, impl="tap", graph=False, tol=5e-3, stage_tol=0.05):
+def check_forward(b=1, h=16, w=20, scale=(2, 2), sd_seed=0, in_seed=1234, impl="tap", graph=False, tol=5e-3, stage_tol=0.05,
+                  precision="bf16"):
     """End-to-end SAVSR forward vs the CPU oracle (bf16 operand path: tolerance on max-abs and PSNR)."""
     from oracle import savsr_oracle as O
     from oracle.state_dict_fixture import make_input, make_state_dict
@@ -595,7 +606,7 @@ def check_forward(b=1, h=16, w=20, scale=(2, 2), sd_seed=0, in_seed=1234, impl="
     x = make_input(b, h, w, in_seed)
     probes = {}
     y_ref = O.forward(sd, x, scale, probes)
-    y, taps, plan = run_forward(sd, x, scale, impl=impl, taps=TAPS, graph=graph)
+    y, taps, plan = run_forward(sd, x, scale, impl=impl, taps=TAPS, graph=graph, precision=precision)
     ref_stage = dict(f2p_last=probes["f2p_last"], p2f_last=probes["p2f_last"], align=probes["align"], rg0=probes["rg0"],
                      rg3=probes["rg3"], trunk=probes["trunk"], satu_sta=probes["satu_sta"], satu_out=probes["satu_out"])
     rep = stage_report(taps, ref_stage, h, w)

@@ -90,3 +90,22 @@ def test_satu_fused_tensor_core_hr_stage(G):
 
 def test_device_tensor2img_and_psnr_y(G):
     G.check_img_metrics()
+
+
+def test_kernels_in_fp16_operand_format(G):
+    """The same entry points with the context switched to the fp16 storage / operand format."""
+    G.set_precision("fp16")
+    try:
+        G.check_pack_roundtrip()
+        G.check_conv(impl=G.K.IMPL_HALO, ksize=3, nsrc=2, B=2, H=37, W=45)
+        G.check_conv(impl=G.K.IMPL_HALO, ksize=3, nsrc=3, B=1, H=48, W=40)
+        G.check_conv(impl=G.K.IMPL_TAP, ksize=1, nsrc=3, B=2, H=37, W=45)
+        G.check_osa_conv_per_sample(impl=G.K.IMPL_HALO)
+        G.check_pack_frames()
+        G.check_osa_prologue(ci=192, B=2)
+        G.check_ca()
+        G.check_satu_sta()
+        G.check_satu_gather()
+        G.check_satu_fused()
+    finally:
+        G.set_precision("bf16")
