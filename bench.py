@@ -251,14 +251,15 @@ def main():
     conv = prof.get("conv3x3_n64", dict(ms=0.0, flops=0.0, launches=0))
     total_ms = sum(d["ms"] for d in prof.values())
     achieved = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] else 0.0
-    traffic = None
+    traffic, traffic_note = None, None
     tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        tj = json.load(open(tpath))
+        traffic, traffic_note = tj.get("dram_bytes_per_launch"), f"ncu --set full, one launch: {tj.get('launch')} ({tj.get('source')})"
     roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel<64,3,halo> (tcgen05 implicit-GEMM 3x3 conv, all launches of one forward)",
                 "achieved": round(achieved, 1), "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": round(achieved / peaks["bf16_sustained"], 4), "peak_source": peaks["source"] + " bf16 sustained",
-                "traffic": traffic, "share_of_step": round(conv["ms"] / total_ms, 3) if total_ms else None,
+                "traffic": traffic, "traffic_note": traffic_note, "share_of_step": round(conv["ms"] / total_ms, 3) if total_ms else None,
                 "launches": conv["launches"], "avg_launch_us": round(1e3 * conv["ms"] / max(conv["launches"], 1), 1),
                 "per_kind_ms": {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
     whole = flops_per_frame(h, w, H, W) * frames * world * args.steps / (ms_total / 1e3) / 1e12
