@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SAVSR_ABI_VERSION 1
+#define SAVSR_ABI_VERSION 2
 #define SAVSR_MAX_SRC 5      /* most 64-channel sources one conv concatenates (OSA 320->64)      */
 #define SAVSR_MAX_GROUPS 25  /* most independent convolutions batched into one launch            */
 #define SAVSR_TILE_W 8       /* output tile = 8 x 16 pixels = 128 GEMM rows (one UMMA M)         */
@@ -43,6 +43,10 @@ typedef void* savsr_stream;             /* cudaStream_t                         
  * BF16: the throughput path named by the task (<= 0.05 dB PSNR delta).  FP16: same speed, 10-bit mantissa: the
  * high-precision path that meets the <= 1e-3 max-abs bound; activations must stay below 65504. */
 enum savsr_format { SAVSR_FMT_BF16 = 0, SAVSR_FMT_FP16 = 1 };
+/* Row (output channel) order inside a packed n_tile = 64 weight block.  LINEAR: row n = channel n.  QUAD: row n =
+ * channel with the bit fields [2:1] and [4:3] of n swapped -- the order savsr_conv requires for n_tile 64 (its epilogue
+ * reads the accumulator with 16x256b TMEM loads and stores 16 contiguous bytes per thread).  savsr_satu_fused takes LINEAR. */
+enum savsr_row_order { SAVSR_ROWS_LINEAR = 0, SAVSR_ROWS_QUAD = 1 };
 
 enum savsr_act { SAVSR_ACT_NONE = 0, SAVSR_ACT_LRELU = 1, SAVSR_ACT_RELU = 2 };
 
@@ -124,9 +128,11 @@ size_t savsr_packed_weight_bytes(int co, int ci, int ksize);
  * fp32 OIHW [co][ci][k][k] (k = 1 or 3) -> bf16 blocks [co/n_tile][ci/64 * k*k][n_tile][64] in the
  * 128-byte-swizzled K-major layout tcgen05.mma reads (block index = source * k*k + ky*k + kx).
  * co_real <= co rows are read, the rest are zero (tail conv: 3 -> 16).  n_tile is 64 or 16.
+ * row_order (enum savsr_row_order) applies to n_tile 64 only; n_tile 16 blocks are always LINEAR.
  */
 int savsr_pack_conv_weight(const float* w_oihw, int co_real, int co, int ci, int ksize, int n_tile,
-                           int format /* enum savsr_format */, void* packed, savsr_stream st);
+                           int format /* enum savsr_format */, int row_order /* enum savsr_row_order */,
+                           void* packed, savsr_stream st);
 
 /* ---- convolutions (tensor-core hot path) ------------------------------------------------------- */
 /*

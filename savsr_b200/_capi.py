@@ -21,6 +21,7 @@ IMPL_TAP, IMPL_HALO, IMPL_CHECK = 0, 1, 2
 IMPL_NAMES = {"tap": IMPL_TAP, "halo": IMPL_HALO, "check": IMPL_CHECK}
 FMT_BF16, FMT_FP16 = 0, 1
 FMT_NAMES = {"bf16": FMT_BF16, "fp16": FMT_FP16}
+ROWS_LINEAR, ROWS_QUAD = 0, 1     # enum savsr_row_order: QUAD for savsr_conv n_tile 64, LINEAR for savsr_satu_fused
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libsavsr_sm100.so")
 
@@ -94,7 +95,7 @@ SIGNATURES = {
     "savsr_arena_import": (_I, [_VP, _I, _VP, _VP]),
     "savsr_arena_export": (_I, [_VP, _I, _VP, _VP]),
     "savsr_packed_weight_bytes": (_SZ, [_I, _I, _I]),
-    "savsr_pack_conv_weight": (_I, [_VP, _I, _I, _I, _I, _I, _I, _VP, _VP]),
+    "savsr_pack_conv_weight": (_I, [_VP, _I, _I, _I, _I, _I, _I, _I, _VP, _VP]),
     "savsr_conv": (_I, [_VP, _VP, C.POINTER(ConvGroup), _I, _I, _I, _I, C.POINTER(RgbSkip), _I, _VP]),
     "savsr_front_conv": (_I, [_VP, _VP, _VP, _I, _I, _I, C.POINTER(FrontGroup), _I, _VP]),
     "savsr_pack_frames": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _VP]),
@@ -125,8 +126,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.savsr_abi_version() != 1:
-        raise SavsrError(f"ABI version mismatch: library {lib.savsr_abi_version()}, binding 1")
+    if lib.savsr_abi_version() != 2:
+        raise SavsrError(f"ABI version mismatch: library {lib.savsr_abi_version()}, binding 2")
     _lib = lib
     return lib
 

@@ -210,6 +210,12 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// SAVSR_ROWS_QUAD row order of a packed N = 64 weight block: row (= accumulator column) n holds output channel
+// quad_row(n), the bit fields [2:1] and [4:3] of n swapped.  With it the 8 accumulator columns one thread receives from
+// a 16x256b.x4 TMEM load (8 k + 2 q + e) are the 8 CONSECUTIVE channels 8 q + 2 k + e, so conv epilogues read and write
+// 16 contiguous bytes per thread and 64 per thread quad without any transposition.  The map is its own inverse.
+__host__ __device__ __forceinline__ int quad_row(int n) { return (n & 0x21) | (((n >> 1) & 3) << 3) | (((n >> 3) & 3) << 1); }
+
 // 32 lanes x 32 bit, 16 consecutive columns: thread i of the warp gets TMEM lane (base_lane + i).
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
@@ -221,6 +227,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 16 lanes x 256 bit, repeated 4 times along the columns (32 columns): thread t = 4 g + q of the warp receives
+//   v[4 k + e] = TMEM[lane base + g + 8 (e >> 1)][column base + 8 k + 2 q + (e & 1)],  k = 0..3, e = 0..3
+// (the mma.sync accumulator-fragment layout; measured with scripts/tmem_layout.cu).  The address' lane field selects
+// the first of the 16 lanes, so a warp covers its 32-lane quadrant with two loads (lane offsets 0 and 16).
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 
 }  // namespace savsr
 #endif  // __CUDACC__

@@ -232,6 +232,169 @@ __device__ __forceinline__ void epi_finish(const ConvParams& p, const savsr_conv
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ N = 64 epilogue
+// Epilogue of the tensor-core kernels for the 16-bit arena destination.  Each of the 8 epilogue warps owns one TMEM
+// lane quadrant (32 pixels: 4 tile rows of 8) and one 32-column half.  The accumulator is read with 16x256b loads and
+// the weights are packed in SAVSR_ROWS_QUAD order, so thread (g = lane / 4, q = lane % 4) holds, for the four pixels
+// (x = g, y = 4 quad + j), j = 0..3, the eight consecutive channels half * 32 + 8 q .. + 7: residual loads and stores
+// are 16 bytes per thread, 64 contiguous bytes per thread quad, 8 lines per warp instruction.  (The first version
+// read one pixel per lane with 32x32b loads; every 16-byte store then touched 32 different lines and the LSU, not the
+// tensor core, set the pace of single-source convs.)
+struct EpiQuad {
+  float bias[8];
+  uint4 r1[4], r2[4];
+  float mk[4];
+  long pix0;          // pixel index of row j = 0; row j is pix0 + j * width
+  uint32_t valid;     // bit j: pixel j is inside the image
+  int bias_group;
+  float neg_slope, res2_scale;
+  int res1_slot, res2_slot, dst_slot;
+  bool has_mask;
+  float* pool;
+};
+
+__device__ __forceinline__ void epiq_prefetch(const ConvParams& p, const savsr_conv_group& g, int gi, int n, int tile, int quad,
+                                              int lane, int half, EpiQuad& c) {
+  const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+  const int px = tx * kTileW + (lane >> 2);
+  const int py0 = ty * kTileH + quad * 4;
+  const int rows = p.height - py0;   // rows of this quadrant inside the image
+  c.valid = (px < p.width && rows > 0) ? (rows >= 4 ? 0xfu : ((1u << rows) - 1u)) : 0u;
+  const long npix = static_cast<long>(p.height) * p.width;
+  c.pix0 = static_cast<long>(py0) * p.width + px;
+  const int ch0 = half * 32 + (lane & 3) * 8;
+  if (gi != c.bias_group) {
+    c.bias_group = gi;
+    c.neg_slope = g.act == SAVSR_ACT_NONE ? 1.f : (g.act == SAVSR_ACT_RELU ? 0.f : g.slope);
+    c.res2_scale = g.res2_scale;
+    c.res1_slot = g.res1_slot; c.res2_slot = g.res2_slot; c.dst_slot = g.dst_slot;
+    c.has_mask = g.mask != nullptr;
+    c.pool = g.pool;
+    if (g.bias != nullptr) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + ch0));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + ch0) + 1);
+      c.bias[0] = b0.x; c.bias[1] = b0.y; c.bias[2] = b0.z; c.bias[3] = b0.w;
+      c.bias[4] = b1.x; c.bias[5] = b1.y; c.bias[6] = b1.z; c.bias[7] = b1.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) c.bias[j] = 0.f;
+    }
+  }
+  if (c.has_mask) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c.mk[j] = ((c.valid >> j) & 1u) ? __ldg(g.mask + n * npix + c.pix0 + j * p.width) : 0.f;
+  }
+  if (c.res1_slot >= 0) {
+    const __nv_bfloat16* r = p.arena + ((static_cast<long>(c.res1_slot) * p.batch + n) * npix + c.pix0) * kC + ch0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if ((c.valid >> j) & 1u) c.r1[j] = *reinterpret_cast<const uint4*>(r + static_cast<long>(j) * p.width * kC);
+  }
+  if (c.res2_slot >= 0) {
+    const __nv_bfloat16* r = p.arena + ((static_cast<long>(c.res2_slot) * p.batch + n) * npix + c.pix0) * kC + ch0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if ((c.valid >> j) & 1u) c.r2[j] = *reinterpret_cast<const uint4*>(r + static_cast<long>(j) * p.width * kC);
+  }
+}
+
+// `taddr`: TMEM address of (first lane of the quadrant, first column of the half) of the tile's accumulator.
+// Reads the accumulator, calls `release()` (the accumulator may be overwritten from then on), applies bias / activation /
+// mask / residuals, then calls `next()` -- the caller starts the NEXT tile's epiq_prefetch into `c` there, so those loads
+// have the stores, the pooling and the next accumulator wait to land (when the epilogue is the critical path, as in
+// single-source convs, nothing else would hide their latency) -- and finally packs, stores and pools this tile.
+template <class Release, class Next>
+__device__ __forceinline__ void epiq_finish(const ConvParams& p, int n, int tile, int quad, int lane, int half, uint32_t taddr,
+                                            EpiQuad& c, Release release, Next next) {
+  uint32_t ra[16], rb[16];
+  tmem_ld_16x256b_x4(taddr, ra);
+  tmem_ld_16x256b_x4(taddr + (16u << 16), rb);
+  tmem_ld_wait();
+  tc_fence_before();
+  __syncwarp();
+  release();
+  // v[j][2 k + e]: pixel row j, channel ch0 + 2 k + e
+  float v[4][8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[e >> 1][2 * k + (e & 1)] = __uint_as_float(ra[4 * k + e]);
+      v[2 + (e >> 1)][2 * k + (e & 1)] = __uint_as_float(rb[4 * k + e]);
+    }
+  }
+  const long npix = static_cast<long>(p.height) * p.width;
+  const int ch0 = half * 32 + (lane & 3) * 8;
+  const float ns = c.neg_slope;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float t = v[j][i] + c.bias[i];
+      v[j][i] = fmaxf(t, 0.f) + ns * fminf(t, 0.f);   // none / ReLU / LeakyReLU without branches
+    }
+  }
+  if (c.has_mask) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[j][i] *= c.mk[j];
+    }
+  }
+  if (c.res1_slot >= 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if ((c.valid >> j) & 1u) add_h16x8(v[j], c.r1[j], 1.f, p.fmt);
+  }
+  if (c.res2_slot >= 0) {
+    const float r2s = c.res2_scale;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if ((c.valid >> j) & 1u) add_h16x8(v[j], c.r2[j], r2s, p.fmt);
+  }
+  const uint32_t valid = c.valid;
+  float* const pool = c.pool;
+  __nv_bfloat16* d = p.arena + ((static_cast<long>(c.dst_slot) * p.batch + n) * npix + c.pix0) * kC + ch0;
+  next();   // `c` belongs to the next tile from here on
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if ((valid >> j) & 1u) {
+      uint4 u;
+      u.x = pack_h2(v[j][0], v[j][1], p.fmt);
+      u.y = pack_h2(v[j][2], v[j][3], p.fmt);
+      u.z = pack_h2(v[j][4], v[j][5], p.fmt);
+      u.w = pack_h2(v[j][6], v[j][7], p.fmt);
+      *reinterpret_cast<uint4*>(d + static_cast<long>(j) * p.width * kC) = u;
+    }
+  }
+  if (pool != nullptr) {
+    // Channel sums of the (pre-rounding) outputs over the valid pixels of this quadrant: 4 rows in the thread, then a
+    // shuffle reduce-scatter over the 8 thread groups (7 shuffles) leaves channel ch0 + 4 b4 + 2 b3 + b2 (b = lane
+    // bits) in each lane.  Deterministic; one partial per (tile, quadrant) as before.
+    float s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s[i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i] += ((valid >> j) & 1u) ? v[j][i] : 0.f;
+    }
+#pragma unroll
+    for (int off = 16, cnt = 4; off >= 4; off >>= 1, cnt >>= 1) {
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < cnt; ++i) {
+        const float send = upper ? s[i] : s[i + cnt];
+        const float keep = upper ? s[i + cnt] : s[i];
+        s[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    const int npart = p.tiles_x * p.tiles_y * 4;
+    const int ch = ch0 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    pool[(static_cast<long>(n) * npart + tile * 4 + quad) * kC + ch] = s[0];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ tcgen05 kernel
 // Upper 32 bits of a K-major SWIZZLE_128B shared-memory matrix descriptor (version 1, base_offset 0).
 __device__ __forceinline__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
@@ -484,37 +647,49 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
     const int quad = warp & 3;          // TMEM lane quadrant this warp may access (warp id % 4)
     const int half = (warp - 2) >> 2;   // which 32-column half of the accumulator (N = 64 only)
     if (BN == 64 || half == 0) {
-      constexpr int NC = BN == 64 ? 32 : 16;
+      constexpr int NC = 16;             // columns per warp of the N = 16 destinations (AUX16 / RGB)
       EpiCtx<NC> ec;
+      EpiQuad eq;
       ec.bias_group = -1;
+      eq.bias_group = -1;
       int it = 0;
       int tile = item_begin % tiles;
       int gn = item_begin / tiles;
       long long dbg_tf = 0, dbg_t0 = clock64();
+      if constexpr (BN == 64) {
+        if (item_begin < item_end) epiq_prefetch(p, p.g[gn / p.batch], gn / p.batch, gn % p.batch, tile, quad, lane, half, eq);
+      }
       for (int item = item_begin; item < item_end; ++item, ++it) {
         const int n = gn % p.batch;
         const int gi = gn / p.batch;
         const savsr_conv_group& g = p.g[gi];
         const int acc = it & 1;
-        epi_prefetch<NC>(p, g, gi, n, tile, quad, lane, half * 32, ec);   // loads fly while the tile's MMAs run
+        // loads that do not depend on the accumulator fly while the tile's MMAs run
+        if constexpr (BN != 64) epi_prefetch<NC>(p, g, gi, n, tile, quad, lane, 0, ec);
         const long long c0 = clock64();
         mbar_wait(t_full + acc, (it >> 1) & 1);
         dbg_tf += clock64() - c0;
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN + half * 32);
-        float v[NC];
-#pragma unroll
-        for (int j = 0; j < NC / 16; ++j) {
+        if constexpr (BN == 64) {
+          epiq_finish(p, n, tile, quad, lane, half, taddr, eq, [&] { if (lane == 0) mbar_arrive(t_empty + acc); }, [&] {
+            if (item + 1 < item_end) {
+              const int nt = tile + 1 == tiles ? 0 : tile + 1, ngn = tile + 1 == tiles ? gn + 1 : gn;
+              epiq_prefetch(p, p.g[ngn / p.batch], ngn / p.batch, ngn % p.batch, nt, quad, lane, half, eq);
+            }
+          });
+        } else {
+          float v[NC];
           uint32_t r[16];
-          tmem_ld16(taddr + j * 16, r);
+          tmem_ld16(taddr, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 16; ++c) v[j * 16 + c] = __uint_as_float(r[c]);
+          for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(r[c]);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(t_empty + acc);
+          epi_finish<NC>(p, g, n, tile, quad, lane, v, 0, ec);
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(t_empty + acc);
-        epi_finish<NC>(p, g, n, tile, quad, lane, v, half * 32, ec);
         if (++tile == tiles) { tile = 0; ++gn; }
       }
       if (p.dbg != nullptr && warp == 2 && lane == 0) {
@@ -741,38 +916,28 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
     // ================================ epilogue warps ================================
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
-    constexpr int NC = 32;
-    EpiCtx<NC> ec;
-    ec.bias_group = -1;
+    EpiQuad eq;
+    eq.bias_group = -1;
     long long dbg_tf = 0, dbg_t0 = clock64();
+    if (item < item_end) epiq_prefetch(p, p.g[gn / p.batch], gn / p.batch, gn % p.batch, tile, quad, lane, half, eq);
     while (item < item_end) {
       const int cnt = min(kBatchTiles, min(item_end - item, tiles - tile));
       const int bb = bcount & 1;
       const int n = gn % p.batch;
-      const int gi = gn / p.batch;
-      const savsr_conv_group& g = p.g[gi];
       for (int j = 0; j < cnt; ++j) {
         const int acc = bb * kBatchTiles + j;
-        epi_prefetch<NC>(p, g, gi, n, tile + j, quad, lane, half * 32, ec);
         const long long c0 = clock64();
         mbar_wait(t_full + acc, (use_bits >> acc) & 1u);
         dbg_tf += clock64() - c0;
         use_bits ^= 1u << acc;
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN + half * 32);
-        float v[NC];
-#pragma unroll
-        for (int q = 0; q < NC / 16; ++q) {
-          uint32_t r[16];
-          tmem_ld16(taddr + q * 16, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 16; ++c) v[q * 16 + c] = __uint_as_float(r[c]);
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(t_empty + acc);
-        epi_finish<NC>(p, g, n, tile + j, quad, lane, v, half * 32, ec);
+        epiq_finish(p, n, tile + j, quad, lane, half, taddr, eq, [&] { if (lane == 0) mbar_arrive(t_empty + acc); }, [&] {
+          if (item + j + 1 < item_end) {   // a batch never straddles a (conv, sample) boundary
+            const int nt = tile + j + 1 == tiles ? 0 : tile + j + 1, ngn = tile + j + 1 == tiles ? gn + 1 : gn;
+            epiq_prefetch(p, p.g[ngn / p.batch], ngn / p.batch, ngn % p.batch, nt, quad, lane, half, eq);
+          }
+        });
       }
       ++bcount;
       item += cnt; tile += cnt;
@@ -825,7 +990,7 @@ __global__ void __launch_bounds__(128) conv_check_kernel(const __grid_constant__
           const float a = in ? h_to_float(reinterpret_cast<const uint16_t*>(src)[(static_cast<long>(sy) * p.width + sx) * kC + k], p.fmt) : 0.f;
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
-            const int row = col0 + c;
+            const int row = BN == 64 ? quad_row(col0 + c) : col0 + c;   // packed rows of N = 64 blocks are in SAVSR_ROWS_QUAD order
             const int off = row * 128 + (((k >> 3) ^ (row & 7)) << 4) + (k & 7) * 2;
             v[c] += a * h_to_float(*reinterpret_cast<const uint16_t*>(wb + off), p.fmt);
           }
@@ -841,7 +1006,7 @@ __global__ void __launch_bounds__(128) conv_check_kernel(const __grid_constant__
 
 // ------------------------------------------------------------------------------------------------ weight packing
 // fp32 OIHW -> packed bf16 blocks [co/n_tile][ci/64 * k*k][n_tile][64], 128-byte swizzled rows.
-__global__ void pack_weight_kernel(const float* __restrict__ w, int co_real, int co, int ci, int ks, int n_tile, int fmt,
+__global__ void pack_weight_kernel(const float* __restrict__ w, int co_real, int co, int ci, int ks, int n_tile, int fmt, int quad,
                                    uint16_t* __restrict__ out) {
   const long total = static_cast<long>(co) * ci * ks * ks;
   const int taps = ks * ks;
@@ -854,7 +1019,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int co_real, int
     const int kb = r % ((ci / 64) * taps);
     const int ng = r / ((ci / 64) * taps);
     const int s = kb / taps, tap = kb % taps;
-    const int o = ng * n_tile + n, i = s * 64 + k;
+    const int o = ng * n_tile + (quad ? quad_row(n) : n), i = s * 64 + k;   // row n of the block holds channel o
     const float val = o < co_real ? w[(static_cast<long>(o) * ci + i) * taps + tap] : 0.f;
     const long block = static_cast<long>(ng) * ((ci / 64) * taps) + kb;
     const long off = block * (n_tile * 64) + n * 64 + ((((k >> 3) ^ (n & 7)) << 3) | (k & 7));
@@ -945,8 +1110,9 @@ extern "C" size_t savsr_packed_weight_bytes(int co, int ci, int ksize) {
 }
 
 extern "C" int savsr_pack_conv_weight(const float* w_oihw, int co_real, int co, int ci, int ksize, int n_tile, int format,
-                                      void* packed, savsr_stream st) {
+                                      int row_order, void* packed, savsr_stream st) {
   SAVSR_REQUIRE(format == SAVSR_FMT_BF16 || format == SAVSR_FMT_FP16, "savsr_pack_conv_weight: unknown format %d", format);
+  SAVSR_REQUIRE(row_order == SAVSR_ROWS_LINEAR || row_order == SAVSR_ROWS_QUAD, "savsr_pack_conv_weight: unknown row_order %d", row_order);
   SAVSR_REQUIRE(w_oihw && packed, "savsr_pack_conv_weight: null pointer");
   SAVSR_REQUIRE(ksize == 1 || ksize == 3, "savsr_pack_conv_weight: ksize must be 1 or 3, got %d", ksize);
   SAVSR_REQUIRE(n_tile == 64 || n_tile == 16, "savsr_pack_conv_weight: n_tile must be 64 or 16, got %d", n_tile);
@@ -956,6 +1122,7 @@ extern "C" int savsr_pack_conv_weight(const float* w_oihw, int co_real, int co, 
   const long total = static_cast<long>(co) * ci * ksize * ksize;
   const int blocks = static_cast<int>((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
   pack_weight_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(st)>>>(w_oihw, co_real, co, ci, ksize, n_tile, format,
+                                                                       (n_tile == 64 && row_order == SAVSR_ROWS_QUAD) ? 1 : 0,
                                                                        static_cast<uint16_t*>(packed));
   SAVSR_CUDA(cudaGetLastError());
   return 0;

@@ -244,7 +244,8 @@ __global__ void __launch_bounds__(256) osa_assemble_kernel(const __grid_constant
   }
   const int s = i >> 6, kk = i & 63;
   const long sample_elems = static_cast<long>(c.co) * c.ci * 9;
-  const int inner = o * 64 + ((((kk >> 3) ^ (o & 7)) << 3) | (kk & 7));
+  const int row = quad_row(o);   // SAVSR_ROWS_QUAD: the packed row that holds output channel o (the map is an involution)
+  const int inner = row * 64 + ((((kk >> 3) ^ (row & 7)) << 3) | (kk & 7));
   for (int n = 0; n < L.batch; ++n) {
     const float* att = c.scratch + static_cast<long>(n) * osa_scratch_stride(c.ci) + osa_off_att(c.ci);
     const float ca = att[i], fa = att[c.ci + o];

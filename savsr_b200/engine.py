@@ -98,7 +98,7 @@ class Plan:
         self.P = params
         self._keep: List[object] = []   # tensors / ctypes arrays referenced by raw pointers
         self.ops: List[Callable[[int], int]] = []
-        self.op_meta: List[Tuple[str, float, int]] = []   # (kind, algorithmic FLOPs, kernel launches) per op
+        self.op_meta: List[Tuple[str, float, int, str]] = []   # (kind, algorithmic FLOPs, kernel launches, detail) per op
         self.n_launches = 0
         self.taps = set(taps or ())
         self.tap_bufs: Dict[str, torch.Tensor] = {}
@@ -137,21 +137,23 @@ class Plan:
             self._pack_cache[name] = self._pack(self._p(name))
         return self._pack_cache[name]
 
-    def _pack(self, w: torch.Tensor, n_tile: int = 64, co_pad: Optional[int] = None) -> int:
-        """fp32 OIHW -> packed bf16 tensor-core layout; returns the device pointer."""
+    def _pack(self, w: torch.Tensor, n_tile: int = 64, co_pad: Optional[int] = None, rows: int = K.ROWS_QUAD) -> int:
+        """fp32 OIHW -> packed 16-bit tensor-core layout; returns the device pointer.  `rows`: row order of n_tile 64
+        blocks -- QUAD for everything savsr_conv consumes, LINEAR for the SATU expert / fusion GEMMs."""
         w = w.detach().to(self.device, torch.float32).contiguous()
         co_real, ci, ks, _ = w.shape
         co = co_pad or co_real
         out = self._buf(self.lib.savsr_packed_weight_bytes(co, ci, ks), dtype=torch.uint8)
         self._keep.append(w)
-        K.check(self.lib.savsr_pack_conv_weight(w.data_ptr(), co_real, co, ci, ks, n_tile, self.fmt, out.data_ptr(),
+        K.check(self.lib.savsr_pack_conv_weight(w.data_ptr(), co_real, co, ci, ks, n_tile, self.fmt, rows, out.data_ptr(),
                                                 torch.cuda.current_stream().cuda_stream))
         return out.data_ptr()
 
     # ------------------------------------------------------------------ op emitters
-    def _emit(self, fn: Callable[[int], int], launches: int = 1, kind: str = "other", flops: float = 0.0) -> None:
+    def _emit(self, fn: Callable[[int], int], launches: int = 1, kind: str = "other", flops: float = 0.0,
+              detail: str = "") -> None:
         self.ops.append(fn)
-        self.op_meta.append((kind, flops, launches))
+        self.op_meta.append((kind, flops, launches, detail))
         self.n_launches += launches
 
     def _group(self, src: Sequence[int], dst: int, weight: int, bias: int = 0, act: int = K.ACT_NONE, slope: float = 0.2,
@@ -176,7 +178,7 @@ class Plan:
         co = 64 if n_tile == 64 else (3 if dst_mode == K.DST_RGB else 16)      # real output channels
         flops = 2.0 * self.B * arena.height * arena.width * co * ksize * ksize * sum(64 * g.nsrc for g in groups)
         self._emit(lambda st: lib.savsr_conv(ctx, ah, arr, n, ksize, n_tile, dst_mode, skip_ref, impl, st),
-                   kind=f"conv{ksize}x{ksize}_n{n_tile}", flops=flops)
+                   kind=f"conv{ksize}x{ksize}_n{n_tile}", flops=flops, detail=f"g{n}s{groups[0].nsrc}")
 
     def _tap(self, name: str, arena: str, slot: int) -> None:
         """Test/debug hook: if `name` was requested in `taps`, snapshot the slot (fp32 NCHW) right here in the
@@ -437,7 +439,8 @@ class Plan:
         wc_all = self._p(u + ".weight_compress").reshape(32, 64, 1, 1)                               # rows e*8+k
         we_all = torch.zeros(64, 64, 1, 1, device=self.device)
         we_all[:, :32, 0, 0] = self._p(u + ".weight_expand").view(4, 64, 8).permute(1, 0, 2).reshape(64, 32)   # cols e*8+k
-        pwc, pwe, pwf = self._pack(wc_all, n_tile=16), self._pack(we_all), self._packp(u + ".fusion.weight")
+        pwc, pwe = self._pack(wc_all, n_tile=16), self._pack(we_all, rows=K.ROWS_LINEAR)
+        pwf = self._pack(self._p(u + ".fusion.weight"), rows=K.ROWS_LINEAR)
         fb = self._ptr(u + ".fusion.bias")
         self._emit(lambda st: lib.savsr_satu_fused(ctx, lrh, TR, STA, hh, ww, hrh, 0, tab, by, bx, pwc, pwe, pwf, fb, st),
                    kind="satu_fused", flops=2.0 * B * self.H * self.W * (64 * 32 + 32 * 64 + 128 * 64))
@@ -459,9 +462,10 @@ class Plan:
             if rc:
                 K.check(rc)
 
-    def run_profiled(self) -> Dict[str, Dict[str, float]]:
+    def run_profiled(self, detail: bool = False) -> Dict[str, Dict[str, float]]:
         """Eager run with a CUDA-event pair around every op on the launching stream.
-        Returns {kind: {"ms": total device ms, "flops": algorithmic FLOPs, "ops": count, "launches": kernels}}."""
+        Returns {kind: {"ms": total device ms, "flops": algorithmic FLOPs, "ops": count, "launches": kernels}};
+        with `detail` the conv kinds are further split by (groups per launch, sources per group)."""
         self.ctx.set_format(self.fmt)
         stream = torch.cuda.current_stream()
         st = stream.cuda_stream
@@ -476,8 +480,8 @@ class Plan:
             evs.append((e0, e1))
         stream.synchronize()
         out: Dict[str, Dict[str, float]] = {}
-        for (kind, flops, launches), (e0, e1) in zip(self.op_meta, evs):
-            d = out.setdefault(kind, dict(ms=0.0, flops=0.0, ops=0, launches=0))
+        for (kind, flops, launches, tag), (e0, e1) in zip(self.op_meta, evs):
+            d = out.setdefault(f"{kind}:{tag}" if (detail and tag) else kind, dict(ms=0.0, flops=0.0, ops=0, launches=0))
             d["ms"] += e0.elapsed_time(e1); d["flops"] += flops; d["ops"] += 1; d["launches"] += launches
         return out
 

@@ -3,6 +3,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/umma_bench.bin scripts/umma_bench.cu
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "../savsr_b200/csrc/common.cuh"
 namespace savsr { void set_error(const char*, ...) {} int cuda_fail(cudaError_t, const char*) { return 1; } }
@@ -198,6 +199,76 @@ __global__ void __launch_bounds__(320, 1) bench_bg(int tiles, long long* out, in
   if (warp == 0) { tc_fence_after(); tmem_dealloc<512>(tm); }
 }
 
+
+// cta_group::2: a CTA pair issues one M=256 MMA (128 rows per CTA); each CTA supplies its own A rows and HALF of the B rows.
+// The leader's thread issues; the commit is multicast to both CTAs' barriers.
+template <int N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) bench_pair(int iters, long long* out, int a_sbo) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  for (int i = threadIdx.x; i < (48 * 1024 + N * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  tc_fence_after();
+  const uint32_t tm = slot;
+  if (warp == 0 && lane == 0) {
+    long long t0 = clock64();
+    if (rank == 0) {
+      const uint32_t a_lo = (smem_u32(smem) >> 4) & 0x3fff, b_lo = (smem_u32(smem + 48 * 1024) >> 4) & 0x3fff;
+      const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t ahi = (uint32_t(a_sbo) >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t idesc = idesc_mn(256, N);
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = (uint64_t(ahi) << 32) | (a_lo + 2 * k), db = (uint64_t(hi) << 32) | (b_lo + 2 * k);
+          const uint32_t acc = (it | k) ? 1u : 0u;
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                       ::"r"(tm + (it & 1) * N), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                   ::"r"(smem_u32(&bar)), "h"((uint16_t)3) : "memory");
+    }
+    mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    if (blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  tc_fence_before();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tm), "n"(512) : "memory");
+  }
+}
+
+template <int N>
+void run_pair(int iters, long long* d_out) {
+  const size_t smem = 1024 + 48 * 1024 + N * 128;
+  cudaFuncSetAttribute(bench_pair<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  for (int sbo : {1024, 1280}) {
+    bench_pair<N><<<148, 128, smem>>>(iters, d_out, sbo);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long cyc = 0;
+    cudaMemcpy(&cyc, d_out, sizeof(cyc), cudaMemcpyDeviceToHost);
+    const double per = double(cyc) / (iters * 4);
+    printf("cta_group::2 M=256 N=%3d A-SBO %4d: %7.1f cycles/MMA -> %6.0f MAC/cycle/SM (%s)\n", N, sbo, per, 128.0 * N * 16 / per,
+           e == cudaSuccess ? "ok" : cudaGetErrorString(e));
+  }
+}
+
 template <int M, int N>
 void run(int iters, long long* d_out) {
   const size_t smem = 1024 + 48 * 1024 + N * 128;
@@ -217,6 +288,10 @@ int main() {
   long long* d_out;
   cudaMalloc(&d_out, sizeof(long long));
   const int iters = 4096;
+  run_pair<64>(iters, d_out);
+  run_pair<128>(iters, d_out);
+  run_pair<256>(iters, d_out);
+  if (getenv("PAIR_ONLY")) return 0;
   run<128, 64>(iters, d_out);
   run<128, 128>(iters, d_out);
   run<128, 256>(iters, d_out);

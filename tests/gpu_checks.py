@@ -63,18 +63,24 @@ class ArenaBox:
         return out
 
 
-def pack_weight(w: torch.Tensor, n_tile: int = 64, co_pad=None) -> torch.Tensor:
+def quad_row(n):
+    """SAVSR_ROWS_QUAD: packed row n of an N = 64 block holds channel quad_row(n) (bit fields [2:1] and [4:3] swapped)."""
+    return (n & 0x21) | (((n >> 1) & 3) << 3) | (((n >> 3) & 3) << 1)
+
+
+def pack_weight(w: torch.Tensor, n_tile: int = 64, co_pad=None, rows: int = K.ROWS_QUAD) -> torch.Tensor:
     lib = K.load()
     w = w.to(DEV, torch.float32).contiguous()
     co_real, ci, ks, _ = w.shape
     co = co_pad or co_real
     out = torch.empty(lib.savsr_packed_weight_bytes(co, ci, ks), dtype=torch.uint8, device=DEV)
-    K.check(lib.savsr_pack_conv_weight(w.data_ptr(), co_real, co, ci, ks, n_tile, lib.savsr_ctx_get_format(ctx().handle), out.data_ptr(), _stream()))
+    K.check(lib.savsr_pack_conv_weight(w.data_ptr(), co_real, co, ci, ks, n_tile, lib.savsr_ctx_get_format(ctx().handle), rows,
+                                       out.data_ptr(), _stream()))
     return out
 
 
-def unpack_weight(packed: torch.Tensor, co: int, ci: int, ks: int, n_tile: int = 64) -> torch.Tensor:
-    """Inverse of the packed layout (python restatement of the swizzle) -> fp32 [co][ci][ks][ks]."""
+def unpack_weight(packed: torch.Tensor, co: int, ci: int, ks: int, n_tile: int = 64, rows: int = K.ROWS_QUAD) -> torch.Tensor:
+    """Inverse of the packed layout (python restatement of the swizzle and row order) -> fp32 [co][ci][ks][ks]."""
     v = packed.view(_h16()).float().cpu().numpy()
     taps = ks * ks
     nkb = (ci // 64) * taps
@@ -83,6 +89,8 @@ def unpack_weight(packed: torch.Tensor, co: int, ci: int, ks: int, n_tile: int =
     k = np.arange(64)[None, :]
     pos = n * 64 + ((((k >> 3) ^ (n & 7)) << 3) | (k & 7))
     blk = v[:, :, pos]                                 # [ng, kb, n, k]
+    if n_tile == 64 and rows == K.ROWS_QUAD:
+        blk = blk[:, :, quad_row(np.arange(64)), :]    # channel o sits in row quad_row(o) (involution)
     blk = blk.reshape(co // n_tile, ci // 64, taps, n_tile, 64)
     w = blk.transpose(0, 3, 1, 4, 2).reshape(co, ci, ks, ks)
     return torch.from_numpy(np.ascontiguousarray(w))
@@ -254,8 +262,9 @@ def check_pack_roundtrip():
     out = {}
     for (co, ci, ks, nt) in ((64, 192, 3, 64), (128, 320, 3, 64), (64, 192, 1, 64), (16, 64, 3, 16), (1600, 64, 1, 64)):
         w = torch.randn(co, ci, ks, ks)
-        back = unpack_weight(pack_weight(w, n_tile=nt), co, ci, ks, nt)
-        assert torch.equal(back, bf16_round(w)), (co, ci, ks, nt)
+        for rows in (K.ROWS_QUAD, K.ROWS_LINEAR):
+            back = unpack_weight(pack_weight(w, n_tile=nt, rows=rows), co, ci, ks, nt, rows=rows)
+            assert torch.equal(back, bf16_round(w)), (co, ci, ks, nt, rows)
         out[f"{co}x{ci}x{ks}"] = "exact"
     return out
 
@@ -534,7 +543,8 @@ def check_satu_fused(B=2, h=13, w=15, scale=(2.7, 1.5), seed=1):
     wc_all = sd["upsample.weight_compress"].reshape(32, 64, 1, 1)
     we_all = torch.zeros(64, 64, 1, 1)
     we_all[:, :32, 0, 0] = sd["upsample.weight_expand"].view(4, 64, 8).permute(1, 0, 2).reshape(64, 32)
-    pwc, pwe, pwf = pack_weight(wc_all, n_tile=16), pack_weight(we_all), pack_weight(sd["upsample.fusion.weight"])
+    pwc, pwe = pack_weight(wc_all, n_tile=16), pack_weight(we_all, rows=K.ROWS_LINEAR)
+    pwf = pack_weight(sd["upsample.fusion.weight"], rows=K.ROWS_LINEAR)
     fb = sd["upsample.fusion.bias"].to(DEV).contiguous()
     K.check(K.load().savsr_satu_fused(ctx().handle, lr.a.handle, 0, 1, h, w, hr.a.handle, 0, table.data_ptr(), by.data_ptr(), bx.data_ptr(),
                                       pwc.data_ptr(), pwe.data_ptr(), pwf.data_ptr(), fb.data_ptr(), _stream()))

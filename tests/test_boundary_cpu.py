@@ -64,7 +64,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/savsr_b200.h but not exported"
     assert declared == set(_capi.SIGNATURES), declared ^ set(_capi.SIGNATURES)
-    assert lib.savsr_abi_version() == 1
+    assert lib.savsr_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
