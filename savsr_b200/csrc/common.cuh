@@ -147,6 +147,13 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* t
       "r"(smem_u32(bar))
       : "memory");
 }
+// Same box, fetched into L2 only (no shared-memory destination, no completion signal): hides DRAM latency for a later
+// tma_load_4d of the same coordinates without holding a pipeline stage.
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* tm, int c, int x, int y, int img) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c), "r"(x), "r"(y), "r"(img)
+               : "memory");
+}
 // 1-D bulk copy global -> shared (size multiple of 16 bytes, both 16-byte aligned).
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile(

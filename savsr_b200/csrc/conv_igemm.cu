@@ -56,6 +56,7 @@ struct ConvParams {
   long long* dbg;            // optional [grid][8] cycle counters (bring-up aid), nullptr in production
   int dst_mode;
   int fmt;              // enum savsr_format of the arena and the packed weights
+  int issuers;          // batched kernel: MMA-issuing warps, 2 (default) or 1 (bring-up knob SAVSR_BIGK_ISSUERS)
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
@@ -749,8 +750,8 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&p.tm_halo);
-    for (int i = 0; i < kMaxAStages; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 2); }   // owner's commit + the other issuer's pass
-    for (int i = 0; i < 2; ++i) { mbar_init(set_full + i, 1); mbar_init(set_empty + i, 2); }   // both issuers release a set
+    for (int i = 0; i < kMaxAStages; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, p.issuers); }   // owner's commit (+ the other issuer's pass)
+    for (int i = 0; i < 2; ++i) { mbar_init(set_full + i, 1); mbar_init(set_empty + i, p.issuers); }   // every issuer releases a set
     for (int i = 0; i < 2 * kBatchTiles; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 8); }
     fence_barrier_init();
   }
@@ -809,11 +810,13 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
         if (tile == tiles) { tile = 0; ++gn; }
       }
     }
-  } else if (warp == 1 || warp == 10) {
+  } else if (warp == 1 || (warp == 10 && p.issuers == 2)) {
     // ================================ two MMA issuers (warp-uniform, elected issue) ================================
-    // One thread cannot issue N=64 MMAs as fast as the tensor core retires them (54-58 vs 48 cycles, scripts/umma_bench.cu):
-    // warp 1 takes the even tiles of a batch, warp 10 the odd ones, each into its own TMEM accumulators.
+    // In situ one issuing thread also waits on barriers, commits and walks the batch structure between tiles, and the
+    // tensor core idles meanwhile (64 cycles per MMA measured with one issuer, 52 with two): warp 1 takes the even
+    // tiles of a batch, warp 10 the odd ones, each into its own TMEM accumulators, so one fills the other's gaps.
     const int my = warp == 1 ? 0 : 1;
+    const int own_mask = p.issuers == 2 ? 1 : 0;   // tile j of a batch belongs to issuer (j & own_mask)
     const uint32_t idesc = umma_idesc_f16(BN, p.fmt);
     constexpr uint32_t a_hi = desc_hi(kHaloPitch * 128u);
     constexpr uint32_t b_hi = desc_hi(1024u);
@@ -840,7 +843,7 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
       c0 = clock64();
 #pragma unroll
       for (int j = 0; j < kBatchTiles; ++j) {
-        if (j < cnt && (j & 1) == my) mbar_wait(t_empty + bb * kBatchTiles + j, ((use_bits >> (bb * kBatchTiles + j)) & 1u) ^ 1u);
+        if (j < cnt && (j & own_mask) == my) mbar_wait(t_empty + bb * kBatchTiles + j, ((use_bits >> (bb * kBatchTiles + j)) & 1u) ^ 1u);
       }
       dbg_te += clock64() - c0;
       tc_fence_after();
@@ -864,7 +867,7 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
             c0 = clock64();
             mbar_wait(a_full + sa, pa);
             dbg_af += clock64() - c0;
-            if ((j & 1) != my) {
+            if ((j & own_mask) != my) {
               if (elect_one()) mbar_arrive(a_empty + sa);
               __syncwarp();
             } else {
@@ -872,13 +875,23 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
               const uint32_t al0 = a_lo0 + sa * (kAStage >> 4);
               const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((bb * kBatchTiles + j) * BN);
               if (elect_one()) {
+                // The tap-row loop is deliberately NOT unrolled: fully unrolled, ptxas precomputes all 72 descriptors,
+                // spills uniform registers and needs 58 cycles per MMA from one thread; this compact form
+                // (UTCHMMA / UIADD3.64 pairs) issues at 50, the tensor core retiring one N = 64 MMA per 48
+                // (scripts/umma_bench.cu, "rolled tap loop").
+                uint32_t al = al0, bl = bl0, acc = s ? 1u : 0u;
+#pragma unroll 1
+                for (int dy = 0; dy < 3; ++dy) {
 #pragma unroll
-                for (int tap = 0; tap < NT; ++tap) {
-                  const uint32_t al = al0 + ((tap / 3) * kHaloPitch + tap % 3) * 8;
-                  const uint32_t bl = bl0 + tap * (kBBytes >> 4);
+                  for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    umma_bf16(d_tmem, make_desc(a_hi, al + 2 * k), make_desc(b_hi, bl + 2 * k), idesc, (s | tap | k) ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) {
+                      umma_bf16(d_tmem, make_desc(a_hi, al + dx * 8 + 2 * k), make_desc(b_hi, bl + dx * (kBBytes >> 4) + 2 * k), idesc, acc);
+                      acc = 1u;
+                    }
+                  }
+                  al += kHaloPitch * 8;
+                  bl += 3 * (kBBytes >> 4);
                 }
                 umma_commit(a_empty + sa);
               }
@@ -895,7 +908,7 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
       if (elect_one()) {
 #pragma unroll
         for (int j = 0; j < kBatchTiles; ++j)
-          if (j < cnt && (j & 1) == my) umma_commit(t_full + bb * kBatchTiles + j);
+          if (j < cnt && (j & own_mask) == my) umma_commit(t_full + bb * kBatchTiles + j);
       }
       __syncwarp();
 #pragma unroll
@@ -912,7 +925,7 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
       p.dbg[blockIdx.x * 8 + 3] = item_end - item_begin;
       p.dbg[blockIdx.x * 8 + 7] = dbg_sf;
     }
-  } else {
+  } else if (warp < 10) {   // (warp 10 is the optional second issuer; idle when p.issuers == 1)
     // ================================ epilogue warps ================================
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
@@ -1197,6 +1210,8 @@ extern "C" int savsr_conv(savsr_ctx* ctx, savsr_arena* arena, const savsr_conv_g
   p.dst_mode = dst_mode;
   p.fmt = ctx->fmt;
   p.dbg = g_conv_dbg;
+  static const int issuers = (getenv("SAVSR_BIGK_ISSUERS") != nullptr && atoi(getenv("SAVSR_BIGK_ISSUERS")) == 1) ? 1 : 2;
+  p.issuers = issuers;
   if (n_tile == 64) return launch_conv<64>(ctx, p, impl, static_cast<cudaStream_t>(st));
   return launch_conv<16>(ctx, p, impl, static_cast<cudaStream_t>(st));
 }

@@ -91,6 +91,73 @@ __global__ void __launch_bounds__(128, 1) bench_conv(int tiles, long long* out, 
   if (warp == 0) { tc_fence_after(); tmem_dealloc<512>(tm); }
 }
 
+
+// Same MMA stream as bench_conv, but the tap loop is NOT unrolled (dy / dx loops with `#pragma unroll 1`, descriptors
+// advanced incrementally): does a compact loop let one thread issue at the tensor core's rate?
+// variant 0: dy,dx rolled, 4 k-steps unrolled; variant 1: only dy rolled (12 MMAs per iteration).
+__global__ void __launch_bounds__(128, 1) bench_conv_rolled(int tiles, long long* out, int variant) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (24 * 1024 + 9 * 8192) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) tmem_alloc<512>(&slot);
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tm = slot;
+  if (warp == 0) {
+    const uint32_t a_lo0 = (smem_u32(smem) >> 4) & 0x3fff, b_lo0 = (smem_u32(smem + 24 * 1024) >> 4) & 0x3fff;
+    const uint32_t bhi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t ahi = (1280u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t idesc = idesc_mn(128, 64);
+    long long t0 = clock64();
+    for (int t = 0; t < tiles; ++t) {
+      const uint32_t d = tm + (t & 1) * 64;
+      if (elect_one()) {
+        uint32_t al = a_lo0, bl = b_lo0, acc = 0;
+        if (variant == 0) {
+#pragma unroll 1
+          for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll 1
+            for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16(d, (uint64_t(ahi) << 32) | (al + 2 * k), (uint64_t(bhi) << 32) | (bl + 2 * k), idesc, acc);
+                acc = 1;
+              }
+              al += 8; bl += 512;
+            }
+            al += 7 * 8;
+          }
+        } else {
+#pragma unroll 1
+          for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16(d, (uint64_t(ahi) << 32) | (al + dx * 8 + 2 * k), (uint64_t(bhi) << 32) | (bl + dx * 512 + 2 * k), idesc, acc);
+                acc = 1;
+              }
+            }
+            al += 10 * 8; bl += 3 * 512;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(&bar);
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = t1 - t0;
+  }
+  tc_fence_before(); __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<512>(tm); }
+}
+
 // NW warps issue independent MMA streams (own accumulator each) concurrently: is the per-thread issue rate the limit?
 template <int N>
 __global__ void __launch_bounds__(256, 1) bench_multi(int tiles, long long* out, int nw) {
@@ -292,6 +359,18 @@ int main() {
   run_pair<128>(iters, d_out);
   run_pair<256>(iters, d_out);
   if (getenv("PAIR_ONLY")) return 0;
+  {
+    const size_t smem = 1024 + 24 * 1024 + 9 * 8192;
+    cudaFuncSetAttribute(bench_conv_rolled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (int variant : {0, 1}) {
+      bench_conv_rolled<<<148, 128, smem>>>(2048, d_out, variant);
+      cudaError_t e = cudaDeviceSynchronize();
+      long long cyc = 0;
+      cudaMemcpy(&cyc, d_out, sizeof(cyc), cudaMemcpyDeviceToHost);
+      printf("rolled tap loop variant %d: %6.1f cycles/MMA (%s)\n", variant, double(cyc) / (2048.0 * 36), e == cudaSuccess ? "ok" : cudaGetErrorString(e));
+    }
+  }
+  if (getenv("ROLLED_ONLY")) return 0;
   run<128, 64>(iters, d_out);
   run<128, 128>(iters, d_out);
   run<128, 256>(iters, d_out);
