@@ -277,6 +277,16 @@ int savsr_satu_fused(savsr_ctx* ctx, savsr_arena* lr, int x_slot, int sta_slot, 
 int savsr_img_metrics(savsr_ctx* ctx, const float* sr, const float* gt, int batch, int height, int width,
                       uint8_t* bgr_u8, double* sse_y, savsr_stream st);
 
+/*
+ * SSIM on the Y channel of the same uint8 images (lbasicsr/metrics/psnr_ssim.py:85-129 and _ssim 172-200 with
+ * crop_border 0, test_y_channel true; the YAML metric `ssim_y`): 11x11 Gaussian window (sigma 1.5), fully covered
+ * positions only, float64.  Writes one partial sum per 16x16 block of the SSIM map:
+ * partials [batch][savsr_ssim_y_blocks(H, W)], SSIM_n = sum(partials[n]) / ((H - 10) * (W - 10)).  Needs H, W >= 11.
+ */
+int savsr_ssim_y_blocks(int height, int width);
+int savsr_ssim_y(savsr_ctx* ctx, const float* sr, const float* gt, int batch, int height, int width,
+                 double* partials, savsr_stream st);
+
 #ifdef __cplusplus
 }
 #endif

@@ -438,3 +438,37 @@ def psnr_y(a: Tensor, b: Tensor) -> float:
         mse = np.mean((y1 - y2) ** 2)
         vals.append(float("inf") if mse == 0 else 10. * np.log10(255. * 255. / mse))
     return float(np.mean(vals))
+
+
+def _gaussian_window_11() -> np.ndarray:
+    """cv2.getGaussianKernel(11, 1.5) outer itself (psnr_ssim.py:186-187): exp(-(i-5)^2 / (2 sigma^2)), normalised, float64."""
+    x = np.arange(11, dtype=np.float64) - 5.0
+    k = np.exp(-(x * x) / (2.0 * 1.5 * 1.5))
+    k = k / k.sum()
+    return np.outer(k, k)
+
+
+def _filter_valid(img: np.ndarray, window: np.ndarray) -> np.ndarray:
+    """cv2.filter2D(img, -1, window)[5:-5, 5:-5] (psnr_ssim.py:189): correlation, only the fully covered positions."""
+    v = np.lib.stride_tricks.sliding_window_view(img, window.shape)      # [H-10, W-10, 11, 11]
+    return np.einsum("ijkl,kl->ij", v, window)
+
+
+def ssim_y(a: Tensor, b: Tensor) -> float:
+    """calculate_ssim(test_y_channel=True, crop_border=0) (psnr_ssim.py:85-129, _ssim 172-200) on the reference's uint8
+    images.  a, b: [3,H,W] or [n,3,H,W] RGB in [0,1].  Returns the mean SSIM over n."""
+    if a.dim() == 3:
+        a, b = a[None], b[None]
+    c1, c2 = (0.01 * 255) ** 2, (0.03 * 255) ** 2
+    w = _gaussian_window_11()
+    vals = []
+    for p, q in zip(a, b):
+        x, y = y_channel(tensor2img(p)).astype(np.float64), y_channel(tensor2img(q)).astype(np.float64)
+        mu1, mu2 = _filter_valid(x, w), _filter_valid(y, w)
+        mu1_sq, mu2_sq, mu12 = mu1 ** 2, mu2 ** 2, mu1 * mu2
+        s1 = _filter_valid(x ** 2, w) - mu1_sq
+        s2 = _filter_valid(y ** 2, w) - mu2_sq
+        s12 = _filter_valid(x * y, w) - mu12
+        m = ((2 * mu12 + c1) * (2 * s12 + c2)) / ((mu1_sq + mu2_sq + c1) * (s1 + s2 + c2))
+        vals.append(float(m.mean()))
+    return float(np.mean(vals))

@@ -107,6 +107,8 @@ SIGNATURES = {
     "savsr_satu_gather": (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _I, _I, _VP, _VP, _VP, C.POINTER(SatuWeights), _VP]),
     "savsr_satu_fused": (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "savsr_img_metrics": (_I, [_VP, _VP, _VP, _I, _I, _I, _VP, _VP, _VP]),
+    "savsr_ssim_y_blocks": (_I, [_I, _I]),
+    "savsr_ssim_y": (_I, [_VP, _VP, _VP, _I, _I, _I, _VP, _VP]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -489,6 +489,71 @@ __global__ void __launch_bounds__(256) img_metrics_kernel(const float* __restric
 
 using namespace savsr;
 
+// SSIM on the Y channel (psnr_ssim.py:85-129, _ssim 172-200; crop_border 0): both frames are quantised to the uint8 images
+// tensor2img would produce, converted to the unrounded float32 Y of to_y_channel, and filtered in float64 with the 11x11
+// Gaussian window (sigma 1.5) over the fully covered positions only.  Block = 16x16 map positions, the 26x26 Y patches of
+// both frames in shared memory; one partial sum per block (deterministic), summed by the caller.
+struct SsimParams {
+  const float* sr;
+  const float* gt;
+  double* partials;
+  int H, W, bx, by;
+  double k[11];   // cv2.getGaussianKernel(11, 1.5); window = outer(k, k)
+};
+__global__ void __launch_bounds__(256) ssim_y_kernel(const __grid_constant__ SsimParams p) {
+  __shared__ double y1[26][27], y2[26][27];
+  __shared__ double red[8];
+  const int n = blockIdx.z;
+  const long npix = static_cast<long>(p.H) * p.W;
+  const float* s = p.sr + static_cast<long>(n) * 3 * npix;
+  const float* g = p.gt + static_cast<long>(n) * 3 * npix;
+  const int oy0 = blockIdx.y * 16, ox0 = blockIdx.x * 16;
+  for (int i = threadIdx.x; i < 26 * 26; i += 256) {
+    const int r = i / 26, c = i - r * 26;
+    const int y = oy0 + r, x = ox0 + c;
+    double a = 0.0, b = 0.0;
+    if (y < p.H && x < p.W) {
+      const long pix = static_cast<long>(y) * p.W + x;
+      int q[3], qg[3];
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        q[ch] = __float2int_rn(fminf(fmaxf(s[ch * npix + pix], 0.f), 1.f) * 255.0f);
+        qg[ch] = __float2int_rn(fminf(fmaxf(g[ch * npix + pix], 0.f), 1.f) * 255.0f);
+      }
+      a = static_cast<double>(y_of_u8(q[2], q[1], q[0]));
+      b = static_cast<double>(y_of_u8(qg[2], qg[1], qg[0]));
+    }
+    y1[r][c] = a; y2[r][c] = b;
+  }
+  __syncthreads();
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  double val = 0.0;
+  if (oy0 + ty < p.H - 10 && ox0 + tx < p.W - 10) {
+    double mu1 = 0.0, mu2 = 0.0, s11 = 0.0, s22 = 0.0, s12 = 0.0;
+    for (int i = 0; i < 11; ++i) {
+#pragma unroll
+      for (int j = 0; j < 11; ++j) {
+        const double w = p.k[i] * p.k[j];
+        const double a = y1[ty + i][tx + j], b = y2[ty + i][tx + j];
+        mu1 += w * a; mu2 += w * b;
+        s11 += w * (a * a); s22 += w * (b * b); s12 += w * (a * b);
+      }
+    }
+    const double c1 = (0.01 * 255) * (0.01 * 255), c2 = (0.03 * 255) * (0.03 * 255);
+    const double mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+    val = ((2 * mu12 + c1) * (2 * (s12 - mu12) + c2)) / ((mu1_sq + mu2_sq + c1) * ((s11 - mu1_sq) + (s22 - mu2_sq) + c2));
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) val += __shfl_xor_sync(0xffffffffu, val, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = val;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    p.partials[(static_cast<long>(n) * p.by + blockIdx.y) * p.bx + blockIdx.x] = t;
+  }
+}
+
 extern "C" int savsr_front_conv(savsr_ctx* ctx, savsr_arena* arena, const float* x, int t, int h, int w,
                                 const savsr_front_group* groups, int ngroups, savsr_stream st) {
   SAVSR_REQUIRE(ctx && arena && x && groups, "savsr_front_conv: null pointer");
@@ -625,6 +690,27 @@ extern "C" int savsr_img_metrics(savsr_ctx* ctx, const float* sr, const float* g
   long blocks = (npix + 255) / 256;
   if (blocks > 4L * ctx->sm_count) blocks = 4L * ctx->sm_count;
   img_metrics_kernel<<<dim3(static_cast<unsigned>(blocks), batch), 256, 0, st>>>(sr, gt, height, width, bgr_u8, sse_y);
+  SAVSR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int savsr_ssim_y_blocks(int height, int width) {
+  if (height < 11 || width < 11) return 0;
+  return ((height - 10 + 15) / 16) * ((width - 10 + 15) / 16);
+}
+
+extern "C" int savsr_ssim_y(savsr_ctx* ctx, const float* sr, const float* gt, int batch, int height, int width, double* partials,
+                            savsr_stream st) {
+  SAVSR_REQUIRE(ctx && sr && gt && partials, "savsr_ssim_y: null pointer");
+  SAVSR_REQUIRE(batch >= 0 && height >= 11 && width >= 11, "savsr_ssim_y: frames of %dx%d are smaller than the 11x11 window", height, width);
+  if (batch == 0) return 0;
+  SsimParams p;
+  p.sr = sr; p.gt = gt; p.partials = partials; p.H = height; p.W = width;
+  p.bx = (width - 10 + 15) / 16; p.by = (height - 10 + 15) / 16;
+  double sum = 0.0;
+  for (int i = 0; i < 11; ++i) { p.k[i] = exp(-((i - 5.0) * (i - 5.0)) / (2.0 * 1.5 * 1.5)); sum += p.k[i]; }
+  for (int i = 0; i < 11; ++i) p.k[i] /= sum;
+  ssim_y_kernel<<<dim3(p.bx, p.by, batch), 256, 0, static_cast<cudaStream_t>(st)>>>(p);
   SAVSR_CUDA(cudaGetLastError());
   return 0;
 }

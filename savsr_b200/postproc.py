@@ -1,6 +1,6 @@
 """Device-side post-processing of SR frames: the reference converts every output frame to a
-uint8 BGR image on the CPU (lbasicsr/utils/img_util.py:38-94) and computes PSNR on the Y channel with numpy
-(lbasicsr/metrics/psnr_ssim.py:11-48); here both run in one CUDA kernel on the frames still resident in HBM."""
+uint8 BGR image on the CPU (lbasicsr/utils/img_util.py:38-94) and computes PSNR and SSIM on the Y channel with numpy / cv2
+(lbasicsr/metrics/psnr_ssim.py:11-48, 85-129, 172-200); here they run as CUDA kernels on the frames still resident in HBM."""
 from __future__ import annotations
 
 import math
@@ -37,3 +37,26 @@ def tensor2img_psnr(sr: torch.Tensor, gt: Optional[torch.Tensor] = None, want_im
         mse = sse / float(H * W)
         psnr = torch.where(mse == 0, torch.full_like(mse, math.inf), 10.0 * torch.log10(255.0 * 255.0 / mse))
     return img, psnr
+
+
+def ssim_y(sr: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
+    """calculate_ssim(crop_border=0, test_y_channel=True) of the reference (the YAML metric `ssim_y`) per frame:
+    sr, gt float32 [n,3,H,W] RGB on a CUDA device -> float64 [n]."""
+    if not sr.is_cuda:
+        raise RuntimeError("savsr_b200.postproc runs on CUDA only; there is no CPU fallback")
+    if sr.dim() != 4 or sr.shape[1] != 3:
+        raise ValueError(f"expected [n,3,H,W], got {tuple(sr.shape)}")
+    if gt.shape != sr.shape:
+        raise AssertionError(f"Image shapes are different: {tuple(sr.shape)}, {tuple(gt.shape)}.")   # psnr_ssim.py:109
+    sr = sr.float().contiguous()
+    gt = gt.to(sr.device).float().contiguous()
+    n, _, H, W = sr.shape
+    ctx = engine.context(sr.device.index if sr.device.index is not None else torch.cuda.current_device())
+    nb = ctx.lib.savsr_ssim_y_blocks(H, W)
+    if nb == 0:
+        raise ValueError(f"frames of {H}x{W} are smaller than the 11x11 SSIM window")
+    part = torch.empty(n, nb, dtype=torch.float64, device=sr.device)
+    with torch.cuda.device(sr.device):
+        K.check(ctx.lib.savsr_ssim_y(ctx.handle, sr.data_ptr(), gt.data_ptr(), n, H, W, part.data_ptr(),
+                                     torch.cuda.current_stream().cuda_stream))
+    return part.sum(dim=1) / float((H - 10) * (W - 10))

@@ -56,7 +56,36 @@ def probe_summary(t: torch.Tensor) -> dict:
                 sample=flat[idx].numpy().copy())
 
 
+def metric_kat(outdir):
+    import hashlib
+    # --- metric chain (SURVEY.md 8d / 8f3): tensor2img + calculate_psnr(test_y_channel=True) of the reference itself
+    from lbasicsr.metrics.psnr_ssim import calculate_psnr, calculate_ssim
+    from lbasicsr.utils.img_util import tensor2img
+    g = torch.Generator().manual_seed(99)
+    gt = torch.rand(4, 3, 24, 31, generator=g)
+    sr = gt + 0.04 * torch.randn(4, 3, 24, 31, generator=g)
+    sr[0, :, :3] = 1.5; sr[0, :, 3:6] = -0.2
+    sr[1, 0, 0, :31] = (torch.arange(31, dtype=torch.float32) * 2 + 0.5) / 255.0
+    psnr, ssim, shas = [], [], []
+    for i in range(4):
+        a, b = tensor2img(sr[i]), tensor2img(gt[i])
+        psnr.append(calculate_psnr(a, b, crop_border=0, test_y_channel=True))
+        ssim.append(calculate_ssim(a, b, crop_border=0, test_y_channel=True))     # cv2.filter2D path of the reference
+        shas.append(hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest())
+        assert np.array_equal(a, O.tensor2img(sr[i])), "oracle tensor2img differs from the reference"
+        assert abs(psnr[-1] - O.psnr_y(sr[i], gt[i])) < 1e-9, (psnr[-1], O.psnr_y(sr[i], gt[i]))
+        assert abs(ssim[-1] - O.ssim_y(sr[i], gt[i])) < 1e-12, (ssim[-1], O.ssim_y(sr[i], gt[i]))
+    np.savez_compressed(os.path.join(outdir, "metrics_kat.npz"), sr=sr.numpy(), gt=gt.numpy(), psnr_y=np.array(psnr, dtype=np.float64),
+                        ssim_y=np.array(ssim, dtype=np.float64), img_sha1=np.array(shas))
+    print("metric KAT: reference PSNR-Y", [round(p, 4) for p in psnr], "SSIM-Y", [round(p, 6) for p in ssim],
+          "== oracle (1e-9 / 1e-12), uint8 images bit-identical")
+
+
 def main():
+    if "--metrics-only" in sys.argv:
+        load_reference()
+        metric_kat(os.path.join(ROOT, "tests", "golden"))
+        return
     build_network, ref_arch = load_reference()
     torch.set_num_threads(os.cpu_count())
     outdir = os.path.join(ROOT, "tests", "golden")
@@ -160,24 +189,7 @@ def main():
             for f, val in probe_summary(t).items():
                 rec[f"probe.{k}.{f}"] = val
         np.savez_compressed(os.path.join(outdir, f"{name}.npz"), **rec)
-    # --- metric chain (SURVEY.md 8d / 8f3): tensor2img + calculate_psnr(test_y_channel=True) of the reference itself
-    from lbasicsr.metrics.psnr_ssim import calculate_psnr
-    from lbasicsr.utils.img_util import tensor2img
-    g = torch.Generator().manual_seed(99)
-    gt = torch.rand(4, 3, 24, 31, generator=g)
-    sr = gt + 0.04 * torch.randn(4, 3, 24, 31, generator=g)
-    sr[0, :, :3] = 1.5; sr[0, :, 3:6] = -0.2
-    sr[1, 0, 0, :31] = (torch.arange(31, dtype=torch.float32) * 2 + 0.5) / 255.0
-    psnr, shas = [], []
-    for i in range(4):
-        a, b = tensor2img(sr[i]), tensor2img(gt[i])
-        psnr.append(calculate_psnr(a, b, crop_border=0, test_y_channel=True))
-        shas.append(hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest())
-        assert np.array_equal(a, O.tensor2img(sr[i])), "oracle tensor2img differs from the reference"
-        assert abs(psnr[-1] - O.psnr_y(sr[i], gt[i])) < 1e-9, (psnr[-1], O.psnr_y(sr[i], gt[i]))
-    np.savez_compressed(os.path.join(outdir, "metrics_kat.npz"), sr=sr.numpy(), gt=gt.numpy(), psnr_y=np.array(psnr, dtype=np.float64),
-                        img_sha1=np.array(shas))
-    print("metric KAT: reference PSNR-Y", [round(p, 4) for p in psnr], "== oracle (1e-9), uint8 images bit-identical")
+    metric_kat(outdir)
     print("golden vectors written to", outdir)
 
 

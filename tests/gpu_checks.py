@@ -574,7 +574,19 @@ def check_img_metrics(n=3, H=37, W=53, seed=31):
     got = psnr.cpu().tolist()
     assert got[2] == float("inf") and ref[2] == float("inf")
     assert all(abs(a - b) < 1e-6 for a, b in zip(got[:2], ref[:2])), (got, ref)
-    return dict(psnr=got, ref=ref)
+    # SSIM-Y: float64 on both sides, only the summation order differs
+    ssim = postproc.ssim_y(sr.to(DEV), gt.to(DEV)).cpu().tolist()
+    sref = [O.ssim_y(sr[i], gt[i]) for i in range(n)]
+    assert all(abs(a - b) < 1e-9 for a, b in zip(ssim, sref)), (ssim, sref)
+    assert abs(ssim[2] - 1.0) < 1e-12
+    # the reference's own numbers (cv2.filter2D path) for the committed known-answer frames
+    kat = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metrics_kat.npz"))
+    ksr, kgt = torch.from_numpy(kat["sr"]).to(DEV), torch.from_numpy(kat["gt"]).to(DEV)
+    kss = postproc.ssim_y(ksr, kgt).cpu().numpy()
+    assert np.abs(kss - kat["ssim_y"]).max() < 1e-9, (kss, kat["ssim_y"])
+    _, kps = postproc.tensor2img_psnr(ksr, kgt, want_image=False)
+    assert np.abs(kps.cpu().numpy() - kat["psnr_y"]).max() < 1e-6
+    return dict(psnr=got, ref=ref, ssim=ssim, ssim_ref=sref)
 
 
 # ------------------------------------------------------------------------------------------------ whole forward

@@ -115,4 +115,5 @@ def test_metric_chain_matches_reference_kat():
     for i in range(sr.shape[0]):
         assert hashlib.sha1(np.ascontiguousarray(O.tensor2img(sr[i])).tobytes()).hexdigest() == str(k["img_sha1"][i])
         assert abs(O.psnr_y(sr[i], gt[i]) - float(k["psnr_y"][i])) < 1e-9
+        assert abs(O.ssim_y(sr[i], gt[i]) - float(k["ssim_y"][i])) < 1e-12      # reference: cv2.filter2D in float64
     assert O.psnr_y(gt[0], gt[0]) == float("inf")
