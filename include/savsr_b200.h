@@ -287,6 +287,29 @@ int savsr_ssim_y_blocks(int height, int width);
 int savsr_ssim_y(savsr_ctx* ctx, const float* sr, const float* gt, int batch, int height, int width,
                  double* partials, savsr_stream st);
 
+/* ---- LR synthesis on the device (next row 8f2) ------------------------------------------------------------------------
+ * The reference builds every LR window on the CPU from the uint8 ground-truth frames
+ * (lbasicsr/data/video_test_dataset.py:297-328): cv2.imread / 255 (data_util.py:41) -> as_mod_crop (transforms.py:47-69)
+ * -> img2tensor (BGR->RGB, CHW) -> torchvision Resize(size, BICUBIC, antialias=True) (data_util.py:396-412), i.e. ATen's
+ * _upsample_bicubic2d_aa.  These entry points do the same on frames resident in HBM, bit-exactly (width pass first into a
+ * float32 intermediate, a = -0.5 bicubic taps normalised in float32, the accumulation order of the ATen CPU kernel).
+ *
+ * savsr_aa_max_taps: row stride the caller must give the weight table of one axis.
+ * savsr_aa_table:    per output index, first source index, tap count and weights [out_size][max_taps]; *overflow_flag
+ *                    (device int) is set to 1 if a row needed more than max_taps taps (cannot happen with the size above).
+ * savsr_lr_synthesize: frames_bgr uint8 [n][H][W][3] -> lr fp32 [n][3][out_h][out_w] (tmp: [n][3][crop_h][out_w] scratch)
+ *                    and, if gt != NULL, the mod-cropped ground truth fp32 RGB [n][3][crop_h][crop_w].  The crop is the
+ *                    top-left crop_h x crop_w region (as_mod_crop); an axis whose size does not change needs no table.
+ */
+int savsr_aa_max_taps(int in_size, int out_size);
+int savsr_aa_table(savsr_ctx* ctx, int in_size, int out_size, int max_taps, int32_t* xmin, int32_t* xsize,
+                   float* weights, int32_t* overflow_flag, savsr_stream st);
+int savsr_lr_synthesize(savsr_ctx* ctx, const uint8_t* frames_bgr, int nframes, int height, int width,
+                        int crop_h, int crop_w, int out_h, int out_w,
+                        const int32_t* xmin_w, const int32_t* xsize_w, const float* weights_w, int taps_w,
+                        const int32_t* xmin_h, const int32_t* xsize_h, const float* weights_h, int taps_h,
+                        float* tmp, float* lr, float* gt, savsr_stream st);
+
 #ifdef __cplusplus
 }
 #endif

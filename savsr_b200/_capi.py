@@ -109,6 +109,9 @@ SIGNATURES = {
     "savsr_img_metrics": (_I, [_VP, _VP, _VP, _I, _I, _I, _VP, _VP, _VP]),
     "savsr_ssim_y_blocks": (_I, [_I, _I]),
     "savsr_ssim_y": (_I, [_VP, _VP, _VP, _I, _I, _I, _VP, _VP]),
+    "savsr_aa_max_taps": (_I, [_I, _I]),
+    "savsr_aa_table": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP]),
+    "savsr_lr_synthesize": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP, _VP, _VP, _I, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP]),
 }
 
 _lib: Optional[C.CDLL] = None

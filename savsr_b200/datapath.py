@@ -1,0 +1,115 @@
+"""Device-side LR synthesis and clip evaluation.
+
+The reference's test loop (lbasicsr/models/video_base_model.py:50-98 over lbasicsr/data/video_test_dataset.py:297-328) spends
+its time on the CPU around the network: for every output frame it decodes 7 ground-truth PNGs, mod-crops them
+(lbasicsr/data/transforms.py:47-69), converts to float RGB tensors and resizes them with torchvision's antialiased bicubic
+Resize (lbasicsr/data/data_util.py:396-412), then converts the SR frame to uint8 and computes PSNR / SSIM with numpy / cv2.
+Here the decoded uint8 frames of a clip are uploaded once and everything else -- crop, colour conversion, antialiased
+bicubic downsample (bit-exact with the reference's), window gather, the network, tensor2img, PSNR-Y and SSIM-Y -- runs on the
+GPU.  PNG decoding / encoding stays with the caller.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+from math import floor
+from typing import Callable, Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import _capi as K
+from . import engine, postproc, sharding
+
+
+# ------------------------------------------------------------------------------------------------ host integer logic
+def cal_step(scale: float) -> int:
+    """lbasicsr/data/transforms.py:31-44."""
+    for step in (1, 2, 5, 10, 20, 50):
+        if abs(scale * step - round(scale * step)) < 0.001:
+            return step
+    raise ValueError(f"unsupported scale {scale}: no step in (1, 2, 5, 10, 20, 50) makes scale * step an integer")
+
+
+def as_mod_crop_size(h: int, w: int, scale: Sequence[float]) -> Tuple[int, int]:
+    """Size kept by as_mod_crop (lbasicsr/data/transforms.py:47-69); the crop is the top-left region."""
+    sh, sw = (scale, scale) if not isinstance(scale, (tuple, list)) else scale
+    step_h, step_w = cal_step(sh), cal_step(sw)
+    return round(floor(h / step_h / sh) * step_h * sh), round(floor(w / step_w / sw) * step_w * sw)
+
+
+def lr_size(hc: int, wc: int, scale: Sequence[float]) -> Tuple[int, int]:
+    """(round(h / scale_h), round(w / scale_w)), lbasicsr/data/data_util.py:398."""
+    sh, sw = (scale, scale) if not isinstance(scale, (tuple, list)) else scale
+    return round(hc / sh), round(wc / sw)
+
+
+# ------------------------------------------------------------------------------------------------ resampling tables
+_tables: Dict[Tuple[int, int, int], Tuple[torch.Tensor, torch.Tensor, torch.Tensor, int]] = {}
+
+
+def aa_table(in_size: int, out_size: int, device: torch.device):
+    """(xmin int32 [out], xsize int32 [out], weights float32 [out, taps], taps) of the antialiased bicubic resampler for one
+    axis, built on the device once per (in, out) and cached."""
+    key = (in_size, out_size, device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _tables:
+        ctx = engine.context(key[2])
+        taps = ctx.lib.savsr_aa_max_taps(in_size, out_size)
+        xmin = torch.empty(out_size, dtype=torch.int32, device=device)
+        xsize = torch.empty(out_size, dtype=torch.int32, device=device)
+        wts = torch.empty(out_size, taps, dtype=torch.float32, device=device)
+        flag = torch.zeros(1, dtype=torch.int32, device=device)
+        with torch.cuda.device(device):
+            K.check(ctx.lib.savsr_aa_table(ctx.handle, in_size, out_size, taps, xmin.data_ptr(), xsize.data_ptr(), wts.data_ptr(),
+                                           flag.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        if int(flag.item()) != 0:
+            raise RuntimeError(f"antialias table {in_size}->{out_size}: more than {taps} taps needed")
+        _tables[key] = (xmin, xsize, wts, taps)
+    return _tables[key]
+
+
+def synthesize_lr(frames_bgr_u8: torch.Tensor, scale: Sequence[float], want_gt: bool = True
+                  ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """uint8 [T,H,W,3] BGR frames on a CUDA device (what cv2.imread returns, uploaded) ->
+    (LR float32 [T,3,h,w] RGB, mod-cropped GT float32 [T,3,Hc,Wc] RGB or None), as read_img_seq(require_as_mod_crop=True) +
+    arbitrary_scale_downsample(mode='torch') produce them (data_util.py:27-60, 371-420)."""
+    if not frames_bgr_u8.is_cuda:
+        raise RuntimeError("savsr_b200.datapath runs on CUDA only; there is no CPU fallback")
+    if frames_bgr_u8.dtype != torch.uint8 or frames_bgr_u8.dim() != 4 or frames_bgr_u8.shape[-1] != 3:
+        raise ValueError(f"expected uint8 [T,H,W,3], got {frames_bgr_u8.dtype} {tuple(frames_bgr_u8.shape)}")
+    frames = frames_bgr_u8.contiguous()
+    T, H, W, _ = frames.shape
+    hc, wc = as_mod_crop_size(H, W, scale)
+    if hc <= 0 or wc <= 0:
+        raise ValueError(f"as_mod_crop of a {H}x{W} frame at scale {tuple(scale)} is empty")
+    oh, ow = lr_size(hc, wc, scale)
+    dev = frames.device
+    ctx = engine.context(dev.index if dev.index is not None else torch.cuda.current_device())
+    tw = aa_table(wc, ow, dev) if ow != wc else (None, None, None, 0)
+    th = aa_table(hc, oh, dev) if oh != hc else (None, None, None, 0)
+    tmp = torch.empty(T, 3, hc, ow, dtype=torch.float32, device=dev)
+    lr = torch.empty(T, 3, oh, ow, dtype=torch.float32, device=dev)
+    gt = torch.empty(T, 3, hc, wc, dtype=torch.float32, device=dev) if want_gt else None
+    ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+    with torch.cuda.device(dev):
+        K.check(ctx.lib.savsr_lr_synthesize(ctx.handle, frames.data_ptr(), T, H, W, hc, wc, oh, ow,
+                                            ptr(tw[0]), ptr(tw[1]), ptr(tw[2]), tw[3], ptr(th[0]), ptr(th[1]), ptr(th[2]), th[3],
+                                            tmp.data_ptr(), lr.data_ptr(), ptr(gt), torch.cuda.current_stream().cuda_stream))
+    return lr, gt
+
+
+# ------------------------------------------------------------------------------------------------ one clip, end to end
+def evaluate_clip(net: Callable[[torch.Tensor], torch.Tensor], frames_bgr_u8: torch.Tensor, scale: Sequence[float],
+                  frames: Optional[Sequence[int]] = None, batch: int = 17, num_frames: int = 7,
+                  want_images: bool = True) -> Dict[str, torch.Tensor]:
+    """The reference's per-clip test loop (video_base_model.py:50-98 with the YAML metrics psnr_y / ssim_y) on the device:
+    LR synthesis -> 7-frame windows (reflection padding) -> net -> uint8 BGR images + PSNR-Y + SSIM-Y against the
+    mod-cropped ground truth.  `net` must already be set to `scale`.  `frames`: output frames owned by this rank
+    (default all; see sharding.shard_frames).  Returns {"images": uint8 [n,H,W,3] or None, "psnr_y": float64 [n],
+    "ssim_y": float64 [n], "sr": float32 [n,3,H,W]}."""
+    lr, gt = synthesize_lr(frames_bgr_u8, scale, want_gt=True)
+    idx = list(range(lr.shape[0])) if frames is None else list(frames)
+    sr = sharding.infer_clip(net, lr, idx, batch=batch, num_frames=num_frames)
+    gt_sel = gt[torch.tensor(idx, dtype=torch.long, device=gt.device)] if idx else gt[:0]
+    if tuple(sr.shape) != tuple(gt_sel.shape):
+        raise AssertionError(f"Image shapes are different: {tuple(sr.shape)}, {tuple(gt_sel.shape)}.")   # psnr_ssim.py:26
+    images, psnr = postproc.tensor2img_psnr(sr, gt_sel, want_image=want_images)
+    ssim = postproc.ssim_y(sr, gt_sel)
+    return dict(images=images, psnr_y=psnr, ssim_y=ssim, sr=sr)

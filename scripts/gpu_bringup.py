@@ -47,6 +47,8 @@ CHECKS = {
     "satu_gather": "check_satu_gather()",
     "satu_fused": "check_satu_fused()",
     "img_metrics": "check_img_metrics()",
+    "lr_synthesis": "check_lr_synthesis()",
+    "evaluate_clip": "check_evaluate_clip()",
     "conv_repeat_s1": "check_conv_repeatability(nsrc=1, ngroups=6, B=3)",
     "conv_repeat_s3": "check_conv_repeatability(nsrc=3, ngroups=2, B=4)",
     "satu_fused_x4": "check_satu_fused(B=1, h=16, w=20, scale=(4, 4), seed=2)",

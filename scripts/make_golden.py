@@ -81,10 +81,51 @@ def metric_kat(outdir):
           "== oracle (1e-9 / 1e-12), uint8 images bit-identical")
 
 
+def lr_kat(outdir):
+    """Row f2: the reference's own as_mod_crop + img2tensor + arbitrary_scale_downsample (torchvision Resize, bicubic,
+    antialias) on synthetic uint8 frames, stored as known answers for oracle/lr_synthesis.py and the CUDA data path."""
+    from lbasicsr.data.data_util import arbitrary_scale_downsample
+    from lbasicsr.data.transforms import as_mod_crop
+    from lbasicsr.utils import img2tensor
+    from oracle import lr_synthesis as L
+    rng = np.random.default_rng(7)
+    rec = {}
+    cases = [("x4", 3, 50, 66, (4, 4)), ("x2p7", 2, 45, 61, (2.7, 2.7)), ("x1p5x4", 2, 47, 63, (1.5, 4)),
+             ("x3p9", 2, 64, 50, (3.9, 3.9)), ("x1p2x1p7", 1, 37, 53, (1.2, 1.7)), ("x7p3x5p1", 1, 160, 120, (7.3, 5.1))]
+    for name, t, h, w, scale in cases:
+        frames = rng.integers(0, 256, size=(t, h, w, 3), dtype=np.uint8)
+        frames[0, : h // 3] = np.where(rng.random((h // 3, w, 1)) < 0.5, 0, 255)        # hard edges: overshoot outside [0, 1]
+        imgs = [as_mod_crop(f.astype(np.float32) / 255., scale) for f in frames]        # data_util.py:41-46
+        gt = torch.stack(img2tensor(imgs, bgr2rgb=True, float32=True), dim=0)           # [t,3,hc,wc]
+        lr = arbitrary_scale_downsample(gt, scale=scale, mode="torch")                  # video_test_dataset.py:312
+        lr_o, gt_o = L.synthesize_lr(frames, scale)
+        assert gt_o.shape == tuple(gt.shape) and np.array_equal(gt_o, gt.numpy()), name
+        assert lr_o.shape == tuple(lr.shape), (name, lr_o.shape, lr.shape)
+        assert np.array_equal(lr_o, lr.numpy()), (name, float(np.abs(lr_o - lr.numpy()).max()))
+        rec[f"{name}.frames"] = frames
+        rec[f"{name}.scale"] = np.array(scale, dtype=np.float64)
+        rec[f"{name}.lr"] = lr.numpy()
+        rec[f"{name}.crop"] = np.array(gt.shape[-2:], dtype=np.int64)
+        print(f"lr KAT {name}: {h}x{w} -> crop {tuple(gt.shape[-2:])} -> lr {tuple(lr.shape[-2:])}, min {float(lr.min()):.3f} "
+              f"max {float(lr.max()):.3f}; oracle bit-identical")
+    # as_mod_crop sizes over a sweep of the YAML scales (transforms.py:47-69)
+    sweep = []
+    for sc in [(4, 4), (3.9, 3.9), (2.7, 2.7), (1.5, 4), (1.2, 1.2), (3.5, 2.5), (1.05, 1.95), (6.25, 6.25), (2, 3.14)]:
+        for (h, w) in [(576, 720), (480, 704), (101, 67)]:
+            got = as_mod_crop(np.zeros((h, w, 3), np.float32), sc).shape[:2]
+            assert tuple(got) == L.as_mod_crop_size(h, w, sc), (sc, h, w, got, L.as_mod_crop_size(h, w, sc))
+            sweep.append([h, w, sc[0], sc[1], got[0], got[1]])
+    rec["crop_sweep"] = np.array(sweep, dtype=np.float64)
+    np.savez_compressed(os.path.join(outdir, "lr_kat.npz"), **rec)
+
+
 def main():
-    if "--metrics-only" in sys.argv:
+    if "--metrics-only" in sys.argv or "--lr-only" in sys.argv:
         load_reference()
-        metric_kat(os.path.join(ROOT, "tests", "golden"))
+        if "--metrics-only" in sys.argv:
+            metric_kat(os.path.join(ROOT, "tests", "golden"))
+        if "--lr-only" in sys.argv:
+            lr_kat(os.path.join(ROOT, "tests", "golden"))
         return
     build_network, ref_arch = load_reference()
     torch.set_num_threads(os.cpu_count())
@@ -190,6 +231,7 @@ def main():
                 rec[f"probe.{k}.{f}"] = val
         np.savez_compressed(os.path.join(outdir, f"{name}.npz"), **rec)
     metric_kat(outdir)
+    lr_kat(outdir)
     print("golden vectors written to", outdir)
 
 

@@ -589,6 +589,74 @@ def check_img_metrics(n=3, H=37, W=53, seed=31):
     return dict(psnr=got, ref=ref, ssim=ssim, ssim_ref=sref)
 
 
+
+# ------------------------------------------------------------------------------------------------ data path (row f2)
+def check_lr_synthesis():
+    """Device LR synthesis (as_mod_crop + antialiased bicubic downsample from uint8 BGR frames): bit-exact against the
+    reference's own outputs (tests/golden/lr_kat.npz) and against the oracle at larger, odd shapes."""
+    from oracle import lr_synthesis as L
+    from savsr_b200 import datapath
+    kat = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lr_kat.npz"))
+    out = {}
+    for name in ("x4", "x2p7", "x1p5x4", "x3p9", "x1p2x1p7", "x7p3x5p1"):
+        frames, scale = kat[f"{name}.frames"], tuple(float(v) for v in kat[f"{name}.scale"])
+        lr, gt = datapath.synthesize_lr(torch.from_numpy(frames).to(DEV), scale)
+        assert tuple(lr.shape) == kat[f"{name}.lr"].shape, (name, lr.shape)
+        assert np.array_equal(lr.cpu().numpy(), kat[f"{name}.lr"]), f"{name}: LR differs from the reference"
+        hc, wc = (int(v) for v in kat[f"{name}.crop"])
+        assert np.array_equal(gt.cpu().numpy(), L.frames_to_rgb(frames, (hc, wc))), f"{name}: GT tensor differs"
+        out[name] = "bit-exact"
+    rng = np.random.default_rng(11)
+    for (t, h, w, scale) in ((2, 151, 203, (2.7, 2.7)), (1, 144, 180, (4, 4)), (1, 97, 131, (1.5, 4)), (1, 80, 64, (1, 2))):
+        frames = rng.integers(0, 256, size=(t, h, w, 3), dtype=np.uint8)
+        lr_o, gt_o = L.synthesize_lr(frames, scale)
+        lr, gt = datapath.synthesize_lr(torch.from_numpy(frames).to(DEV), scale)
+        assert np.array_equal(lr.cpu().numpy(), lr_o) and np.array_equal(gt.cpu().numpy(), gt_o), (h, w, scale)
+        out[f"{h}x{w}@{scale}"] = "bit-exact"
+    # size-independent property at a full Vid4 frame: a constant image stays constant (weights sum to 1 within rounding)
+    flat = torch.full((1, 576, 720, 3), 137, dtype=torch.uint8, device=DEV)
+    lr, _ = datapath.synthesize_lr(flat, (4, 4), want_gt=False)
+    assert tuple(lr.shape) == (1, 3, 144, 180) and float((lr - 137.0 / 255.0).abs().max()) < 5e-7
+    return out
+
+
+def check_evaluate_clip(seed=5):
+    """The device test loop (LR synthesis -> windows -> net -> tensor2img / PSNR-Y / SSIM-Y) against the oracle chain on a
+    tiny clip: LR bit-exact, SR within the bf16 tolerance, metrics consistent with the oracle's metrics of the same SR."""
+    import savsr_b200
+    from oracle import lr_synthesis as L
+    from oracle import savsr_oracle as O
+    from oracle.state_dict_fixture import make_state_dict
+    from savsr_b200 import datapath, sharding
+    rng = np.random.default_rng(seed)
+    T, H, W, scale = 4, 50, 66, (4, 4)
+    base = rng.integers(0, 256, size=(1, H // 4 + 1, W // 4 + 1, 3), dtype=np.uint8)
+    frames = np.repeat(np.repeat(base, 4, 1), 4, 2)[:, :H, :W]                 # smooth-ish content
+    frames = np.clip(frames.astype(np.int32) + rng.integers(-20, 21, size=(T, H, W, 3)), 0, 255).astype(np.uint8)
+    sd = make_state_dict(0)
+    net = savsr_b200.SAVSR().to(DEV).eval()
+    net.load_state_dict(sd)
+    net.conv_impl = "halo"
+    net.set_scale(scale)
+    with torch.no_grad():
+        res = datapath.evaluate_clip(net, torch.from_numpy(frames).to(DEV), scale, batch=3)
+    lr_o, gt_o = L.synthesize_lr(frames, scale)
+    lr_t = torch.from_numpy(lr_o)
+    sr_o = torch.cat([O.forward(sd, sharding.gather_windows(lr_t, [i]), scale) for i in range(T)])
+    sr = res["sr"].cpu()
+    assert tuple(sr.shape) == tuple(sr_o.shape) == (T, 3, 48, 64)
+    err = float((sr - sr_o).abs().max())
+    assert err < 4e-3, err
+    gt_t = torch.from_numpy(gt_o)
+    for i in range(T):
+        assert np.array_equal(res["images"][i].cpu().numpy(), O.tensor2img(sr[i]))
+        assert abs(float(res["psnr_y"][i]) - O.psnr_y(sr[i], gt_t[i])) < 1e-6
+        assert abs(float(res["ssim_y"][i]) - O.ssim_y(sr[i], gt_t[i])) < 1e-9
+    dpsnr = abs(O.psnr_y(sr_o, gt_t) - float(res["psnr_y"].mean()))
+    assert dpsnr < 0.05, dpsnr                                                  # north-star PSNR gate, bf16 path
+    return dict(sr_max_abs=err, psnr_delta_db=dpsnr, psnr=[round(float(v), 3) for v in res["psnr_y"]])
+
+
 # ------------------------------------------------------------------------------------------------ whole forward
 TAPS = ("f2p_last", "p2f_last", "align", "rg0", "rg3", "trunk", "satu_sta", "satu_out")
 

@@ -92,6 +92,14 @@ def test_device_tensor2img_and_psnr_y(G):
     G.check_img_metrics()
 
 
+def test_device_lr_synthesis_bit_exact(G):
+    G.check_lr_synthesis()
+
+
+def test_device_clip_evaluation_loop(G):
+    G.check_evaluate_clip()
+
+
 def test_kernels_in_fp16_operand_format(G):
     """The same entry points with the context switched to the fp16 storage / operand format."""
     G.set_precision("fp16")

@@ -12,7 +12,7 @@ from oracle import savsr_oracle as O
 from oracle.state_dict_fixture import make_input, make_state_dict, state_dict_spec
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if "fingerprint" not in p and "metrics" not in p)
+CASES = sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if "fingerprint" not in p and "metrics" not in p and "lr_kat" not in p)
 
 
 def sha12(a: np.ndarray) -> str:
