@@ -15,6 +15,8 @@ collective; weak scaling).  Rank 0 prints ONE JSON line:
   roofline   dominant kernel (tcgen05 implicit-GEMM conv, N = 64): algorithmic FLOPs / CUDA-event time of those launches
              measured live in an eager pass, against the measured bf16 peak of MEASURED_PEAKS.json
   cpu_baseline  the oracle (CPU restatement of the reference, kind "port") on the host cores, bounded sample
+  pipeline   (informational) the reference's whole test loop minus the PNG codec through savsr_b200.datapath.evaluate_clip:
+             uint8 ground-truth frames in pinned host memory -> device LR synthesis -> net -> uint8 images + PSNR-Y + SSIM-Y
 
 --impl reference times the reference's own CPU path (the pinned oracle port; the reference itself is a Python
 package that is not present on the GPU box) on this arm's workload/metric, rank 0 only.
@@ -212,6 +214,24 @@ def main():
             sharding.infer_clip(net, clip, batch=B, out=out_host)      # D2H of batch i overlaps the forward of batch i+1
         torch.cuda.current_stream().synchronize()
 
+    # reference test loop on the device (rows f2 + f3): uint8 ground-truth frames in pinned host memory -> LR synthesis ->
+    # windows -> net -> uint8 BGR images + PSNR-Y + SSIM-Y back in host memory (PNG decode / encode stay outside)
+    from savsr_b200 import datapath
+    pipeline_ok = datapath.as_mod_crop_size(H, W, scale) == (H, W) and datapath.lr_size(H, W, scale) == (h, w)
+    if pipeline_ok:
+        gt_u8_host = torch.randint(0, 256, (frames, H, W, 3), dtype=torch.uint8, generator=gen).pin_memory()
+        img_host = torch.empty(frames, H, W, 3, dtype=torch.uint8).pin_memory()
+        met_host = torch.empty(2, frames, dtype=torch.float64).pin_memory()
+
+    def step_pipeline():
+        gt_u8 = gt_u8_host.to(dev, non_blocking=True)
+        with torch.no_grad():
+            res = datapath.evaluate_clip(net, gt_u8, scale, batch=B)
+        img_host.copy_(res["images"], non_blocking=True)
+        met_host[0].copy_(res["psnr_y"], non_blocking=True)
+        met_host[1].copy_(res["ssim_y"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -238,6 +258,11 @@ def main():
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    ms_pipe = None
+    if pipeline_ok:
+        for _ in range(2):
+            step_pipeline()
+        ms_pipe = timed(step_pipeline, args.steps)
 
     mpix_step = frames * H * W / 1e6 * world
     value = mpix_step * args.steps / (ms_total / 1e3)
@@ -277,6 +302,12 @@ def main():
         "e2e": {"value": round(e2e, 2), "unit": "HR Mpix/s", "ms_per_step": round(ms_e2e / args.steps, 3),
                 "h2d_bytes_per_step": clip_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4,
                 "api": "savsr_b200.sharding.infer_clip(savsr_b200.SAVSR, clip)"},
+        "pipeline": None if ms_pipe is None else {
+            "value": round(mpix_step * args.steps / (ms_pipe / 1e3), 2), "unit": "HR Mpix/s", "ms_per_step": round(ms_pipe / args.steps, 3),
+            "h2d_bytes_per_step": frames * H * W * 3, "d2h_bytes_per_step": frames * H * W * 3 + 16 * frames,
+            "api": "savsr_b200.datapath.evaluate_clip(net, uint8 GT frames, scale)",
+            "what": "the reference test loop minus the PNG codec: uint8 GT frames in pinned host memory -> as_mod_crop + antialiased "
+                    "bicubic LR synthesis -> windows -> net -> uint8 BGR images, PSNR-Y and SSIM-Y back in host memory"},
         "gpu_launches": launches_per_step * args.steps * world,
         "clocks": clocks,
         "roofline": roofline,

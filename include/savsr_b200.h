@@ -309,6 +309,15 @@ int savsr_lr_synthesize(savsr_ctx* ctx, const uint8_t* frames_bgr, int nframes, 
                         const int32_t* xmin_w, const int32_t* xsize_w, const float* weights_w, int taps_w,
                         const int32_t* xmin_h, const int32_t* xsize_h, const float* weights_h, int taps_h,
                         float* tmp, float* lr, float* gt, savsr_stream st);
+/*
+ * Row 8f4: the reference resizes an SR result whose size differs from the ground truth with the same antialiased bicubic
+ * Resize before the metrics (lbasicsr/models/sr_model.py:291-304).  src fp32 [n][3][H][W] -> dst fp32 [n][3][out_h][out_w]
+ * (tmp: [n][3][H][out_w] scratch), tables from savsr_aa_table; same separable float32 arithmetic as savsr_lr_synthesize.
+ */
+int savsr_resize_aa(savsr_ctx* ctx, const float* src, int nframes, int height, int width, int out_h, int out_w,
+                    const int32_t* xmin_w, const int32_t* xsize_w, const float* weights_w, int taps_w,
+                    const int32_t* xmin_h, const int32_t* xsize_h, const float* weights_h, int taps_h,
+                    float* tmp, float* dst, savsr_stream st);
 
 #ifdef __cplusplus
 }

@@ -112,6 +112,7 @@ SIGNATURES = {
     "savsr_aa_max_taps": (_I, [_I, _I]),
     "savsr_aa_table": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP]),
     "savsr_lr_synthesize": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP, _VP, _VP, _I, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP]),
+    "savsr_resize_aa": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP, _VP, _VP, _I, _VP, _VP, _VP, _I, _VP, _VP, _VP]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -69,7 +69,8 @@ __device__ __forceinline__ float aa_accumulate(Load load, const float* __restric
 }
 
 struct LrParams {
-  const uint8_t* frames;   // [n][H][W][3] BGR
+  const uint8_t* frames;   // [n][H][W][3] BGR, or nullptr when `planes` is the source
+  const float* planes;     // [n][3][H][W] float32 (post-resize of SR frames, row f4), top-left hc x wc region used
   int n, H, W, hc, wc, oh, ow;
   const int32_t *xmin_w, *xsize_w, *xmin_h, *xsize_h;
   const float *wt_w, *wt_h;
@@ -88,14 +89,24 @@ __global__ void __launch_bounds__(256) lr_width_kernel(const LrParams p) {
     const int y = r % p.hc; r /= p.hc;
     const int c = r % 3;
     const int t = r / 3;
-    const uint8_t* row = p.frames + ((static_cast<long>(t) * p.H + y) * p.W) * 3 + (2 - c);
-    auto load = [&](int x) { return __fdiv_rn(static_cast<float>(row[static_cast<long>(x) * 3]), 255.0f); };
     float v;
-    if (p.ow == p.wc) {
-      v = load(ox);
+    if (p.frames != nullptr) {
+      const uint8_t* row = p.frames + ((static_cast<long>(t) * p.H + y) * p.W) * 3 + (2 - c);
+      auto load = [&](int x) { return __fdiv_rn(static_cast<float>(row[static_cast<long>(x) * 3]), 255.0f); };
+      if (p.ow == p.wc) {
+        v = load(ox);
+      } else {
+        const int x0 = p.xmin_w[ox];
+        v = aa_accumulate([&](int j) { return load(x0 + j); }, p.wt_w + static_cast<long>(ox) * p.taps_w, p.xsize_w[ox]);
+      }
     } else {
-      const int x0 = p.xmin_w[ox];
-      v = aa_accumulate([&](int j) { return load(x0 + j); }, p.wt_w + static_cast<long>(ox) * p.taps_w, p.xsize_w[ox]);
+      const float* row = p.planes + ((static_cast<long>(t) * 3 + c) * p.H + y) * p.W;
+      if (p.ow == p.wc) {
+        v = row[ox];
+      } else {
+        const int x0 = p.xmin_w[ox];
+        v = aa_accumulate([&](int j) { return row[x0 + j]; }, p.wt_w + static_cast<long>(ox) * p.taps_w, p.xsize_w[ox]);
+      }
     }
     p.tmp[idx] = v;
   }
@@ -172,7 +183,7 @@ extern "C" int savsr_lr_synthesize(savsr_ctx* ctx, const uint8_t* frames_bgr, in
   if (nframes == 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(st_);
   LrParams p;
-  p.frames = frames_bgr; p.n = nframes; p.H = height; p.W = width; p.hc = crop_h; p.wc = crop_w; p.oh = out_h; p.ow = out_w;
+  p.frames = frames_bgr; p.planes = nullptr; p.n = nframes; p.H = height; p.W = width; p.hc = crop_h; p.wc = crop_w; p.oh = out_h; p.ow = out_w;
   p.xmin_w = xmin_w; p.xsize_w = xsize_w; p.wt_w = weights_w; p.taps_w = taps_w;
   p.xmin_h = xmin_h; p.xsize_h = xsize_h; p.wt_h = weights_h; p.taps_h = taps_h;
   p.tmp = tmp; p.lr = lr; p.gt = gt;
@@ -184,6 +195,32 @@ extern "C" int savsr_lr_synthesize(savsr_ctx* ctx, const uint8_t* frames_bgr, in
   lr_width_kernel<<<blocks(static_cast<long>(nframes) * 3 * crop_h * out_w), 256, 0, st>>>(p);
   lr_height_kernel<<<blocks(static_cast<long>(nframes) * 3 * out_h * out_w), 256, 0, st>>>(p);
   if (gt != nullptr) gt_rgb_kernel<<<blocks(static_cast<long>(nframes) * 3 * crop_h * crop_w), 256, 0, st>>>(p);
+  SAVSR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int savsr_resize_aa(savsr_ctx* ctx, const float* src, int nframes, int height, int width, int out_h, int out_w,
+                               const int32_t* xmin_w, const int32_t* xsize_w, const float* weights_w, int taps_w,
+                               const int32_t* xmin_h, const int32_t* xsize_h, const float* weights_h, int taps_h, float* tmp,
+                               float* dst, savsr_stream st_) {
+  SAVSR_REQUIRE(ctx && src && tmp && dst, "savsr_resize_aa: null pointer");
+  SAVSR_REQUIRE(nframes >= 0 && height > 0 && width > 0 && out_h > 0 && out_w > 0, "savsr_resize_aa: bad shape");
+  SAVSR_REQUIRE(out_w == width || (xmin_w && xsize_w && weights_w && taps_w > 0), "savsr_resize_aa: width tables missing");
+  SAVSR_REQUIRE(out_h == height || (xmin_h && xsize_h && weights_h && taps_h > 0), "savsr_resize_aa: height tables missing");
+  if (nframes == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(st_);
+  LrParams p;
+  p.frames = nullptr; p.planes = src; p.n = nframes; p.H = height; p.W = width; p.hc = height; p.wc = width; p.oh = out_h; p.ow = out_w;
+  p.xmin_w = xmin_w; p.xsize_w = xsize_w; p.wt_w = weights_w; p.taps_w = taps_w;
+  p.xmin_h = xmin_h; p.xsize_h = xsize_h; p.wt_h = weights_h; p.taps_h = taps_h;
+  p.tmp = tmp; p.lr = dst; p.gt = nullptr;
+  auto blocks = [&](long total) {
+    long b = (total + 255) / 256;
+    const long cap = 16L * ctx->sm_count;
+    return static_cast<unsigned>(b < cap ? b : cap);
+  };
+  lr_width_kernel<<<blocks(static_cast<long>(nframes) * 3 * height * out_w), 256, 0, st>>>(p);
+  lr_height_kernel<<<blocks(static_cast<long>(nframes) * 3 * out_h * out_w), 256, 0, st>>>(p);
   SAVSR_CUDA(cudaGetLastError());
   return 0;
 }

@@ -95,6 +95,32 @@ def synthesize_lr(frames_bgr_u8: torch.Tensor, scale: Sequence[float], want_gt: 
     return lr, gt
 
 
+def resize_aa_bicubic(x: torch.Tensor, size: Tuple[int, int]) -> torch.Tensor:
+    """T.Resize(size, BICUBIC, antialias=True) of float32 frames [n,3,H,W] on the device: the reference's post-process for an
+    SR result whose size differs from the ground truth (lbasicsr/models/sr_model.py:291-304, row f4)."""
+    if not x.is_cuda:
+        raise RuntimeError("savsr_b200.datapath runs on CUDA only; there is no CPU fallback")
+    if x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError(f"expected [n,3,H,W], got {tuple(x.shape)}")
+    x = x.float().contiguous()
+    n, _, H, W = x.shape
+    oh, ow = int(size[0]), int(size[1])
+    if (oh, ow) == (H, W):
+        return x
+    dev = x.device
+    ctx = engine.context(dev.index if dev.index is not None else torch.cuda.current_device())
+    tw = aa_table(W, ow, dev) if ow != W else (None, None, None, 0)
+    th = aa_table(H, oh, dev) if oh != H else (None, None, None, 0)
+    tmp = torch.empty(n, 3, H, ow, dtype=torch.float32, device=dev)
+    out = torch.empty(n, 3, oh, ow, dtype=torch.float32, device=dev)
+    ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+    with torch.cuda.device(dev):
+        K.check(ctx.lib.savsr_resize_aa(ctx.handle, x.data_ptr(), n, H, W, oh, ow, ptr(tw[0]), ptr(tw[1]), ptr(tw[2]), tw[3],
+                                        ptr(th[0]), ptr(th[1]), ptr(th[2]), th[3], tmp.data_ptr(), out.data_ptr(),
+                                        torch.cuda.current_stream().cuda_stream))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ one clip, end to end
 def evaluate_clip(net: Callable[[torch.Tensor], torch.Tensor], frames_bgr_u8: torch.Tensor, scale: Sequence[float],
                   frames: Optional[Sequence[int]] = None, batch: int = 17, num_frames: int = 7,
@@ -108,8 +134,8 @@ def evaluate_clip(net: Callable[[torch.Tensor], torch.Tensor], frames_bgr_u8: to
     idx = list(range(lr.shape[0])) if frames is None else list(frames)
     sr = sharding.infer_clip(net, lr, idx, batch=batch, num_frames=num_frames)
     gt_sel = gt[torch.tensor(idx, dtype=torch.long, device=gt.device)] if idx else gt[:0]
-    if tuple(sr.shape) != tuple(gt_sel.shape):
-        raise AssertionError(f"Image shapes are different: {tuple(sr.shape)}, {tuple(gt_sel.shape)}.")   # psnr_ssim.py:26
+    if tuple(sr.shape) != tuple(gt_sel.shape):            # arbitrary-scale BI post-process, sr_model.py:291-294
+        sr = resize_aa_bicubic(sr, (gt_sel.shape[-2], gt_sel.shape[-1]))
     images, psnr = postproc.tensor2img_psnr(sr, gt_sel, want_image=want_images)
     ssim = postproc.ssim_y(sr, gt_sel)
     return dict(images=images, psnr_y=psnr, ssim_y=ssim, sr=sr)
