@@ -44,7 +44,9 @@ def launches(tag):
 KEYS = ["gpu__time_duration.sum", "sm__cycles_active.avg", "gpc__cycles_elapsed.avg.per_second", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "launch__shared_mem_per_block_dynamic", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
-        "sm__inst_executed_pipe_uniform.sum", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"]
+        "sm__inst_executed_pipe_uniform.sum", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
+        "lts__t_sectors_srcunit_tex_op_write.sum", "lts__t_sector_hit_rate.pct"]
 
 
 def raw(rep):
@@ -69,14 +71,22 @@ def conv(tag, reps):
         rd, wr = float(v["dram__bytes_read.sum"]), float(v["dram__bytes_write.sum"])
         out.append(f"* {rep}: {flops / t / 1e6:.0f} TFLOP/s under the profiler; DRAM {rd:.1f} {u['dram__bytes_read.sum']} read + {wr:.1f} "
                    f"{u['dram__bytes_write.sum']} written per launch; SM clock {float(v['gpc__cycles_elapsed.avg.per_second']):.2f} GHz.")
-    out += ["", "Reading: the kernel is bound by how fast ONE elected thread can issue `tcgen05.mma` and by the 128 B/clk shared-memory operand",
-            "feed: an M=128, N=64, K=16 SS-mode UMMA costs 48 cycles at best (scripts/umma_bench.cu, 54-58 from one issuing thread), i.e. 67 % of",
-            "the dense peak, and the chip runs at ~1.45 GHz under the 1 kW cap while this kernel is resident (clock64 / kernel time).",
-            "`sm__pipe_tensor_subpipe_hmma_cycles_active` is a nominal count (128 per M=128 UMMA) on this part, not a busy measurement.", ""]
+    out += ["", "Reading (see DESIGN.md section 4 for the measurements behind it):",
+            "* a/e/f are the history of the kernel (first version, resident weights, big-K batched with the per-pixel epilogue); g is the",
+            "  last capture with the per-pixel 32x32b epilogue: every 16-byte store instruction touched 32 different 128-byte lines",
+            "  (`l1tex__t_sectors_pipe_lsu_mem_global_op_st` = 31 sectors per request, L2 write sectors = 2x the bytes stored);",
+            "* s1g6 / s2g6 / s3g2 are the current kernel (16x256b TMEM loads over quad-ordered weight rows, compact MMA issue loop, two",
+            "  issuing warps): 8 lines per store request, store sectors halved, 20 fewer registers;",
+            "* the formulation tops out at 48 cycles per M=128, N=64, K=16 SS-mode UMMA (shared-memory operand feed; 67 % of the dense peak,",
+            "  scripts/umma_bench.cu); the kernel runs at 52-56 cycles per MMA in situ (in-kernel clock64 counters, scripts/profile_conv.py);",
+            "* the chip is power-capped while this kernel is resident (sw_power_cap; 1.45-1.55 GHz by clock64 / kernel time);",
+            "* `sm__pipe_tensor_subpipe_hmma_cycles_active` is a nominal count (128 per M=128 UMMA) on this part, not a busy measurement.", ""]
     open(os.path.join(P, f"{tag}_conv_ncu_summary.md"), "w").write("\n".join(out))
     last = cols[-1]
     json.dump({"dram_bytes_per_launch": (float(last[3]["dram__bytes_read.sum"]) + float(last[3]["dram__bytes_write.sum"])) * 1e6,
-               "launch": last[1], "algorithmic_bytes": None, "source": f"profiles/{tag}_conv_ncu_summary.md ({last[0]})"},
+               "launch": last[1],
+               # 2 convs x 17 samples x (3 source slots read + 1 destination slot written) x 144*180 px x 128 B + per-sample packed weights
+               "algorithmic_bytes": 2 * 17 * (3 + 1) * 144 * 180 * 128 + 2 * 17 * 64 * 192 * 9 * 2, "source": f"profiles/{tag}_conv_ncu_summary.md ({last[0]})"},
               open(os.path.join(P, "conv_traffic.json"), "w"), indent=1)
     print("\n".join(out[-12:]))
 
@@ -88,7 +98,11 @@ if __name__ == "__main__":
     px = 144 * 180
     conv(tag, [("conv_r01_a.ncu-rep", "6 convs 64->64, B=4, first version", 2.0 * 6 * 4 * px * 64 * 576),
                ("conv_r01_e.ncu-rep", "6 convs 128->64, B=4, resident weights", 2.0 * 6 * 4 * px * 64 * 1152),
-               ("conv_r01_f.ncu-rep", "2 convs 192->64, B=17, big-K batched", 2.0 * 2 * 17 * px * 64 * 1728)])
+               ("conv_r01_f.ncu-rep", "2 convs 192->64, B=17, big-K batched", 2.0 * 2 * 17 * px * 64 * 1728),
+               ("conv_r01_g.ncu-rep", "6 convs 128->64, B=17, dual issuer, per-pixel epilogue", 2.0 * 6 * 17 * px * 64 * 1152),
+               ("conv_r01_s1g6.ncu-rep", "6 convs 64->64, B=17, current", 2.0 * 6 * 17 * px * 64 * 576),
+               ("conv_r01_s2g6.ncu-rep", "6 convs 128->64, B=17, current", 2.0 * 6 * 17 * px * 64 * 1152),
+               ("conv_r01_s3g2.ncu-rep", "2 OSA convs 192->64, B=17, current", 2.0 * 2 * 17 * px * 64 * 1728)])
     src = os.path.join(G, f"bench_{tag}.json")
     if os.path.exists(src):
         line = [l for l in open(src) if l.startswith("{")][-1]
