@@ -257,6 +257,17 @@ int savsr_satu_gather(savsr_ctx* ctx, savsr_arena* lr, int x_slot, int sta_slot,
                       savsr_stream st);
 
 /*
+ * kernel_conv (1x1, 64 -> 64*25, LeakyReLU 0.1) and sta_conv (per-pixel 5x5 dynamic filtering, replicate padding on the
+ * h x w region) of STAUpsample in ONE kernel (savsr_arch.py:297-313, 326): the 25 per-pixel kernels are produced tap by
+ * tap on tcgen05 and consumed from TMEM, never written to memory.  a_slot: input of kernel_conv; x_slot: the feature
+ * that is filtered; dst_slot: result.  weights: savsr_pack_conv_weight of the TAP-MAJOR filter [25*64][64][1][1]
+ * (row t*64 + c = reference output channel c*25 + t), n_tile 64, SAVSR_ROWS_QUAD; bias fp32 [25][64] in the same order.
+ * Same result as savsr_conv (25 groups, ksize 1) + savsr_satu_sta except that the kernels are not rounded to 16 bit.
+ */
+int savsr_satu_kconv_sta(savsr_ctx* ctx, savsr_arena* arena, int a_slot, int x_slot, int dst_slot, int h, int w,
+                         const void* weights, const float* bias, float slope, savsr_stream st);
+
+/*
  * Tensor-core version of the HR stage: savsr_satu_gather followed by the 128->64 fusion conv (savsr_arch.py:364-374) in
  * one kernel; the compress / expand / fusion GEMMs run on tcgen05 with the tiles built in shared memory.
  * w_compress: savsr_pack_conv_weight of [32][64][1][1] (rows e*8+k), n_tile 16; w_expand: of [64][64][1][1] with input

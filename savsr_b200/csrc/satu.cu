@@ -138,6 +138,217 @@ __global__ void __launch_bounds__(256) satu_sta_kernel(const __nv_bfloat16* __re
   *reinterpret_cast<uint4*>(const_cast<__nv_bfloat16*>(arena) + ((static_cast<long>(dst_slot) * batch + n) * npix + pix) * kC + chunk * 8) = o;
 }
 
+
+// ------------------------------------------------------------------------------------------------ kernel_conv + sta_conv, fused
+// sta[p][c] = sum_{t in 5x5} x[clamp(p + d_t)][c] * K_t[p][c],   K_t = LeakyReLU_0.1(W_t a[p] + b_t)   (savsr_arch.py:297-313)
+// The unfused route materialises the 25 per-pixel kernels K_t (1600 channels, 83 MB per sample) and reads them back.  Here
+// each tap is one M=128 (8x16-pixel tile) x N=64 x K=64 GEMM on tcgen05 whose accumulator is consumed straight from TMEM:
+// the epilogue threads multiply it with the tap's neighbour feature (16-byte loads that hit L1) and keep the 25-tap sum
+// in registers, so K never leaves the SM.  Work unit = batch of 2 tiles sharing one pass over the 25 weight blocks (8 KB each,
+// streamed through a ring); TMEM holds 4 taps x 2 tiles of accumulators, so the tensor core runs up to 4 taps ahead.
+// Warps: 0 = TMA producer, 1 = MMA issuer, 2..17 = epilogue (TMEM lane quadrant = warp % 4; 2 column halves x 2 tiles).
+struct KstaParams {
+  CUtensorMap tm_tile;            // box [64 ch, 8, 16, 1] over the LR arena
+  const __nv_bfloat16* arena;
+  const uint8_t* weights;         // packed [25][64][64], rows in SAVSR_ROWS_QUAD order
+  const float* bias;              // [25][64]
+  float slope;
+  int batch, hp, wp, h, w;
+  int a_slot, x_slot, dst_slot;
+  int tiles_x, tiles_y;
+  int nbatches, chunk;            // work items = 2-tile batches; `chunk` consecutive ones per CTA
+  int fmt;
+};
+constexpr int kKstaThreads = 18 * 32;
+constexpr int kKstaWStages = 6;
+constexpr int kKstaSmem = 1024 + 4 * 16384 + kKstaWStages * 8192 + 512;
+
+__global__ void __launch_bounds__(kKstaThreads, 1) satu_kconv_sta_kernel(const __grid_constant__ KstaParams p) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;                       // [2 buffers][2 tiles][16 KB]
+  uint8_t* smem_w = smem + 4 * 16384;           // ring of weight blocks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_w + kKstaWStages * 8192);
+  uint64_t* a_full = bars;                      // [2]
+  uint64_t* a_empty = a_full + 2;               // [2]
+  uint64_t* w_full = a_empty + 2;               // [6]
+  uint64_t* w_empty = w_full + kKstaWStages;    // [6]
+  uint64_t* t_full = w_empty + kKstaWStages;    // [8]  accumulator (tap & 3) * 2 + tile
+  uint64_t* t_empty = t_full + 8;               // [8]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles = p.tiles_x * p.tiles_y;
+  const int per_img = (tiles + 1) >> 1;          // 2-tile batches per sample (the last one may hold a single tile)
+  const int item_begin = blockIdx.x * p.chunk;
+  const int item_end = min(item_begin + p.chunk, p.nbatches);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&p.tm_tile);
+    for (int i = 0; i < 2; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < kKstaWStages; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ producer ================================
+    if (lane == 0) {
+      int ws = 0, wph = 0;
+      for (int item = item_begin, it = 0; item < item_end; ++item, ++it) {
+        const int n = item / per_img, t0 = (item - n * per_img) * 2;
+        const int cnt = min(2, tiles - t0);
+        const int ab = it & 1;
+        mbar_wait(a_empty + ab, ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(a_full + ab, cnt * 16384u);
+        for (int j = 0; j < cnt; ++j) {
+          const int tj = t0 + j, ty = tj / p.tiles_x, tx = tj - ty * p.tiles_x;
+          tma_load_4d(smem_a + (ab * 2 + j) * 16384, &p.tm_tile, a_full + ab, 0, tx * kTileW, ty * kTileH, p.a_slot * p.batch + n);
+        }
+        for (int tap = 0; tap < 25; ++tap) {
+          mbar_wait(w_empty + ws, wph ^ 1);
+          mbar_expect_tx(w_full + ws, 8192u);
+          bulk_load(smem_w + ws * 8192, p.weights + tap * 8192, 8192u, w_full + ws);
+          if (++ws == kKstaWStages) { ws = 0; wph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    const uint32_t idesc = umma_idesc_f16(64, p.fmt);
+    constexpr uint32_t hi = desc_hi_1024();
+    const uint32_t a_lo0 = (smem_u32(smem_a) >> 4) & 0x3fffu, w_lo0 = (smem_u32(smem_w) >> 4) & 0x3fffu;
+    int ws = 0, wph = 0;
+    uint32_t use_bits = 0;
+    for (int item = item_begin, it = 0; item < item_end; ++item, ++it) {
+      const int n = item / per_img, t0 = (item - n * per_img) * 2;
+      const int cnt = min(2, tiles - t0);
+      const int ab = it & 1;
+      mbar_wait(a_full + ab, (it >> 1) & 1);
+      tc_fence_after();
+      for (int tap = 0; tap < 25; ++tap) {
+        mbar_wait(w_full + ws, wph);
+        tc_fence_after();
+        const uint32_t wl = w_lo0 + ws * (8192 >> 4);
+        for (int j = 0; j < cnt; ++j) {
+          const int acc = (tap & 3) * 2 + j;
+          mbar_wait(t_empty + acc, ((use_bits >> acc) & 1u) ^ 1u);
+          use_bits ^= 1u << acc;
+          tc_fence_after();
+          const uint32_t al = a_lo0 + (ab * 2 + j) * (16384 >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + acc * 64, make_desc64(hi, al + 2 * k), make_desc64(hi, wl + 2 * k), idesc, k ? 1u : 0u);
+            umma_commit(t_full + acc);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit(w_empty + ws);
+        __syncwarp();
+        if (++ws == kKstaWStages) { ws = 0; wph ^= 1; }
+      }
+      if (elect_one()) umma_commit(a_empty + ab);
+      __syncwarp();
+    }
+  } else {
+    // ================================ epilogue ================================
+    const int quad = warp & 3;
+    const int r = (warp - 2) >> 2;
+    const int half = r & 1, tj = r >> 1;
+    const int g = lane >> 2, q = lane & 3;
+    const int ch0 = half * 32 + q * 8;
+    const long npix = static_cast<long>(p.hp) * p.wp;
+    const float slope = p.slope;
+    uint32_t use_bits = 0;
+    for (int item = item_begin; item < item_end; ++item) {
+      const int n = item / per_img, t0 = (item - n * per_img) * 2;
+      const int cnt = min(2, tiles - t0);
+      if (tj >= cnt) continue;   // single-tile batch: the accumulators of tile 1 are not touched, their phases stay put
+      const int tile = t0 + tj, ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+      const int px = tx * kTileW + g;
+      const int py0 = ty * kTileH + quad * 4;
+      const __nv_bfloat16* xs = p.arena + (static_cast<long>(p.x_slot) * p.batch + n) * npix * kC + ch0;
+      float acc[4][8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
+      for (int tap = 0; tap < 25; ++tap) {
+        const int a = (tap & 3) * 2 + tj;
+        const int dy = tap / 5 - 2, dx = tap - (tap / 5) * 5 - 2;
+        // neighbour features first: their latency hides behind the accumulator wait
+        const int sx = min(max(px + dx, 0), p.w - 1);
+        uint4 nb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int sy = min(max(py0 + j + dy, 0), p.h - 1);
+          nb[j] = __ldg(reinterpret_cast<const uint4*>(xs + (static_cast<long>(sy) * p.wp + sx) * kC));
+        }
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + tap * 64 + ch0));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + tap * 64 + ch0) + 1);
+        const float bias[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        mbar_wait(t_full + a, (use_bits >> a) & 1u);
+        use_bits ^= 1u << a;
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(a * 64 + half * 32);
+        uint32_t ra[16], rb[16];
+        tmem_ld_16x256b_x4(taddr, ra);
+        tmem_ld_16x256b_x4(taddr + (16u << 16), rb);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t_empty + a);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = 2 * k + (e & 1);
+            {
+              const float t = __uint_as_float(ra[4 * k + e]) + bias[i];
+              const float kv = fmaxf(t, slope * t);   // LeakyReLU for 0 <= slope <= 1
+              const uint32_t w32 = i < 2 ? nb[e >> 1].x : i < 4 ? nb[e >> 1].y : i < 6 ? nb[e >> 1].z : nb[e >> 1].w;
+              acc[e >> 1][i] += kv * ((i & 1) ? h_hi(w32, p.fmt) : h_lo(w32, p.fmt));
+            }
+            {
+              const float t = __uint_as_float(rb[4 * k + e]) + bias[i];
+              const float kv = fmaxf(t, slope * t);
+              const uint32_t w32 = i < 2 ? nb[2 + (e >> 1)].x : i < 4 ? nb[2 + (e >> 1)].y : i < 6 ? nb[2 + (e >> 1)].z : nb[2 + (e >> 1)].w;
+              acc[2 + (e >> 1)][i] += kv * ((i & 1) ? h_hi(w32, p.fmt) : h_lo(w32, p.fmt));
+            }
+          }
+        }
+      }
+      // zeros outside the unpadded h x w region (like the unfused kernel); nothing outside the arena
+      __nv_bfloat16* d = const_cast<__nv_bfloat16*>(p.arena) + (static_cast<long>(p.dst_slot) * p.batch + n) * npix * kC + ch0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int py = py0 + j;
+        if (px < p.wp && py < p.hp) {
+          const bool in = px < p.w && py < p.h;
+          uint4 u;
+          u.x = in ? pack_h2(acc[j][0], acc[j][1], p.fmt) : 0u;
+          u.y = in ? pack_h2(acc[j][2], acc[j][3], p.fmt) : 0u;
+          u.z = in ? pack_h2(acc[j][4], acc[j][5], p.fmt) : 0u;
+          u.w = in ? pack_h2(acc[j][6], acc[j][7], p.fmt) : 0u;
+          *reinterpret_cast<uint4*>(d + (static_cast<long>(py) * p.wp + px) * kC) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ HR gather
 struct GatherParams {
   const __nv_bfloat16* lr;
@@ -597,6 +808,40 @@ extern "C" int savsr_satu_sta(savsr_ctx* ctx, savsr_arena* arena, int x_slot, in
   const long ids = static_cast<long>(arena->height) * arena->width * 8;
   satu_sta_kernel<<<dim3(static_cast<unsigned>((ids + 255) / 256), arena->batch), 256, 0, static_cast<cudaStream_t>(st)>>>(
       arena->base, arena->batch, arena->height, arena->width, h, w, x_slot, kslot0, dst_slot, ctx->fmt);
+  SAVSR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int savsr_satu_kconv_sta(savsr_ctx* ctx, savsr_arena* arena, int a_slot, int x_slot, int dst_slot, int h, int w,
+                                    const void* weights, const float* bias, float slope, savsr_stream st) {
+  SAVSR_REQUIRE(ctx && arena && weights && bias, "savsr_satu_kconv_sta: null pointer");
+  SAVSR_REQUIRE(a_slot >= 0 && a_slot < arena->nslots && x_slot >= 0 && x_slot < arena->nslots && dst_slot >= 0 &&
+                dst_slot < arena->nslots, "savsr_satu_kconv_sta: slot out of range");
+  SAVSR_REQUIRE(dst_slot != a_slot && dst_slot != x_slot, "savsr_satu_kconv_sta: the destination slot must differ from both sources");
+  SAVSR_REQUIRE(h >= 1 && w >= 1 && h <= arena->height && w <= arena->width, "savsr_satu_kconv_sta: region %dx%d exceeds arena", h, w);
+  SAVSR_REQUIRE(slope >= 0.f && slope <= 1.f, "savsr_satu_kconv_sta: LeakyReLU slope %g outside [0, 1]", slope);
+  if (arena->batch == 0) return 0;
+  KstaParams p;
+  memset(&p, 0, sizeof(p));
+  p.tm_tile = arena->tm_tile;
+  p.arena = arena->base;
+  p.weights = static_cast<const uint8_t*>(weights);
+  p.bias = bias;
+  p.slope = slope;
+  p.batch = arena->batch; p.hp = arena->height; p.wp = arena->width; p.h = h; p.w = w;
+  p.a_slot = a_slot; p.x_slot = x_slot; p.dst_slot = dst_slot;
+  p.tiles_x = arena->tiles_x; p.tiles_y = arena->tiles_y;
+  const int tiles = p.tiles_x * p.tiles_y;
+  p.nbatches = arena->batch * ((tiles + 1) / 2);
+  p.chunk = (p.nbatches + ctx->sm_count - 1) / ctx->sm_count;
+  p.fmt = ctx->fmt;
+  const int grid = (p.nbatches + p.chunk - 1) / p.chunk;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SAVSR_CUDA(cudaFuncSetAttribute(satu_kconv_sta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKstaSmem));
+    attr_done = true;
+  }
+  satu_kconv_sta_kernel<<<grid, kKstaThreads, kKstaSmem, static_cast<cudaStream_t>(st)>>>(p);
   SAVSR_CUDA(cudaGetLastError());
   return 0;
 }

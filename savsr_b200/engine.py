@@ -14,6 +14,8 @@ PyTorch is used here only for device memory and streams.  There is no CPU path.
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 import math
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
@@ -281,7 +283,9 @@ class Plan:
         extra_needed = 5 + 5 + 5 + 1 + 2 + 1 + 6 + 2
         while len(pool_free) < extra_needed:
             pool_free.append(sl.get())
-        kslot0 = sl.get_contiguous(25)
+        # fused kernel_conv + sta (default) keeps the 25 per-pixel kernels in TMEM; SAVSR_SATU_UNFUSED=1 materialises them
+        self.satu_unfused = os.environ.get("SAVSR_SATU_UNFUSED", "0") == "1"
+        kslot0 = sl.get_contiguous(25) if self.satu_unfused else -1
         self.n_lr_slots = sl.n
         self.arena_lr_t = self._buf(self.n_lr_slots * B, self.hp, self.wp, 64, dtype=torch.bfloat16)
         self.arena_lr_t[zero * B:(zero + 1) * B].zero_()
@@ -410,10 +414,15 @@ class Plan:
         bk = self._p(u + ".kernel_conv.0.bias").view(64, 25).t().contiguous()
         wkp = self._pack(wk)
         bkp = self._dev(bk)
-        self._conv(lr, [self._group([A], kslot0 + tp, wkp + tp * 8192, bkp + tp * 256, act=L, slope=0.1) for tp in range(25)], ksize=1)
         STA, = take(1)
         lrh, hrh, hh, ww = lr.handle, hr.handle, self.h, self.w
-        self._emit(lambda st: lib.savsr_satu_sta(ctx, lrh, TR, kslot0, STA, hh, ww, st), kind="satu_sta")
+        if self.satu_unfused:
+            self._conv(lr, [self._group([A], kslot0 + tp, wkp + tp * 8192, bkp + tp * 256, act=L, slope=0.1) for tp in range(25)], ksize=1)
+            self._emit(lambda st: lib.savsr_satu_sta(ctx, lrh, TR, kslot0, STA, hh, ww, st), kind="satu_sta")
+        else:
+            kflops = 2.0 * B * self.hp * self.wp * 64 * 1600
+            self._emit(lambda st: lib.savsr_satu_kconv_sta(ctx, lrh, A, TR, STA, hh, ww, wkp, bkp, 0.1, st), kind="satu_kconv_sta",
+                       flops=kflops)
         self._tap("satu_sta", "lr", STA)
         sw = K.SatuWeights()
         sw.body0_w, sw.body0_b = self._ptr(u + ".body.0.weight"), self._ptr(u + ".body.0.bias")

@@ -44,6 +44,7 @@ CHECKS = {
     "satu_index_x4": "check_satu_index(144, 180, (4, 4))",
     "satu_table": "check_satu_table()",
     "satu_sta": "check_satu_sta()",
+    "satu_kconv_sta": "check_satu_kconv_sta()",
     "satu_gather": "check_satu_gather()",
     "satu_fused": "check_satu_fused()",
     "img_metrics": "check_img_metrics()",

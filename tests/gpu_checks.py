@@ -498,6 +498,32 @@ def check_satu_sta(B=2, h=13, w=15, seed=9):
     return dict(sta=assert_close("satu sta", got, ref))
 
 
+def check_satu_kconv_sta(B=2, h=13, w=15, seed=19):
+    """kernel_conv (1x1 64 -> 1600, LeakyReLU 0.1) + sta_conv in one kernel, kernels consumed from TMEM
+    (savsr_arch.py:297-313, 326), vs the oracle's two-step restatement on the same (bf16-rounded) operands."""
+    import torch.nn.functional as F
+    from oracle import savsr_oracle as O
+    torch.manual_seed(seed)
+    hp, wp = h + (h & 1), w + (w & 1)
+    ab = ArenaBox(3, B, hp, wp)
+    a = bf16_round(torch.randn(B, 64, hp, wp, device=DEV))
+    x = bf16_round(torch.randn(B, 64, hp, wp, device=DEV))
+    wk = bf16_round(torch.randn(1600, 64, 1, 1, device=DEV) * 0.1)           # reference layout: output channel c*25 + tap
+    bk = torch.randn(1600, device=DEV) * 0.1
+    ab.put(0, a); ab.put(1, x)
+    wt = wk.view(64, 25, 64).permute(1, 0, 2).reshape(1600, 64, 1, 1).contiguous()      # tap-major rows t*64 + c
+    bt = bk.view(64, 25).t().contiguous()
+    wp_ = pack_weight(wt)
+    K.check(K.load().savsr_satu_kconv_sta(ctx().handle, ab.a.handle, 0, 1, 2, h, w, wp_.data_ptr(), bt.data_ptr(), 0.1, _stream()))
+    torch.cuda.synchronize()
+    kern = F.leaky_relu(F.conv2d(a[..., :h, :w].cpu(), wk.cpu(), bk.cpu()), 0.1)
+    ref = O.satu_sta_conv(x[..., :h, :w].cpu(), kern)
+    full = ab.get(2)
+    got = full[..., :h, :w]
+    assert float(full[..., h:, :].abs().max() if hp > h else 0.0) == 0.0 and float(full[..., :, w:].abs().max() if wp > w else 0.0) == 0.0
+    return dict(sta=assert_close("fused kernel_conv + sta", got, ref))
+
+
 def check_satu_gather(B=2, h=13, w=15, scale=(2.7, 1.5), seed=1):
     """Fused HR gather + routed experts vs the oracle (savsr_arch.py:262-295, 353-373)."""
     from oracle import savsr_oracle as O

@@ -79,6 +79,12 @@ def test_satu_sta(G):
     G.check_satu_sta()
 
 
+def test_satu_kernel_conv_and_sta_fused(G):
+    G.check_satu_kconv_sta()
+    G.check_satu_kconv_sta(B=3, h=32, w=40, seed=3)      # several tiles per sample, even tile count
+    G.check_satu_kconv_sta(B=1, h=17, w=9, seed=4)       # odd sizes: padded column / row, single-tile batches
+
+
 def test_satu_gather(G):
     G.check_satu_gather()
 
@@ -113,6 +119,7 @@ def test_kernels_in_fp16_operand_format(G):
         G.check_osa_prologue(ci=192, B=2)
         G.check_ca()
         G.check_satu_sta()
+        G.check_satu_kconv_sta()
         G.check_satu_gather()
         G.check_satu_fused()
     finally:

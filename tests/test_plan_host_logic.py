@@ -38,9 +38,10 @@ def test_launch_census(recorded):
     assert names.count("savsr_ca_scale_residual") == 32              # 4 groups x 8 RCAB
     assert names.count("savsr_osadapt_mask") == 4
     assert names.count("savsr_osa_prologue") == 5 * 3 + 2 + 4        # l1 blocks 1-3 (both dirs batched), l2 x2, adapt x4
-    assert names.count("savsr_satu_sta") == 1 and names.count("savsr_satu_fused") == 1
-    # conv launches: l1 5*(first layer + 4*3 + 1) + l2 (1 + 2*3 + 1 + 1) + RG 4*(16 + 1 + mask + adapt) + conv_last + kernel_conv + fusion + tail
-    assert names.count("savsr_conv") == 5 * 14 + 9 + 4 * 19 + 1 + 1 + 1
+    # kernel_conv + sta_conv are one launch; the 25 per-pixel kernels are never materialised
+    assert names.count("savsr_satu_kconv_sta") == 1 and names.count("savsr_satu_sta") == 0 and names.count("savsr_satu_fused") == 1
+    # conv launches: l1 5*(first layer + 4*3 + 1) + l2 (1 + 2*3 + 1 + 1) + RG 4*(16 + 1 + mask + adapt) + conv_last + tail
+    assert names.count("savsr_conv") == 5 * 14 + 9 + 4 * 19 + 1 + 1
 
 
 def test_no_conv_writes_a_slot_it_reads(recorded):
@@ -80,9 +81,9 @@ def test_slots_written_before_read_and_hidden_states_persist(recorded):
             arena = id(args[1])
             assert (arena, args[2]) in written and (arena, args[3]) in written
             written[(arena, args[4])] = idx
-        elif name == "savsr_satu_sta":
+        elif name == "savsr_satu_kconv_sta":
             arena = id(args[1])
-            assert all((arena, args[3] + t) in written for t in range(25)) and (arena, args[2]) in written
+            assert (arena, args[2]) in written and (arena, args[3]) in written and args[4] not in (args[2], args[3])
             written[(arena, args[4])] = idx
         elif name == "savsr_satu_fused":
             assert (id(args[1]), args[2]) in written and (id(args[1]), args[3]) in written
