@@ -204,7 +204,8 @@ int savsr_ca_scale_residual(savsr_ctx* ctx, savsr_arena* arena, int t_slot, int 
  * in16: [batch][H*W][16] fp32 = ReLU(BN(conv64->16(x))) from savsr_conv(AUX16).  Runs AvgPool2d(2),
  * two conv16->16+BN+ReLU at half resolution, bilinear x2 upsample, conv16->1+BN, sigmoid.
  * Weights: BN already folded by the caller.  wa/wb: [16][16][3][3], wc: [1][16][3][3].
- * half0/half1: [batch][(H/2)*(W/2)][16] fp32 scratch.  mask out: [batch][H*W] fp32.              */
+ * half0/half1: [batch][(H/2)*(W/2)][16] fp32 scratch (half1 receives the nine per-tap projections of the last conv,
+ * which commutes with the upsample; contents are internal).  mask out: [batch][H*W] fp32.            */
 int savsr_osadapt_mask(savsr_ctx* ctx, const float* in16, int batch, int height, int width,
                        const float* wa, const float* ba, const float* wb, const float* bb,
                        const float* wc, const float* bc, float* half0, float* half1, float* mask,

@@ -331,84 +331,114 @@ __global__ void __launch_bounds__(256) ca_scale_residual_kernel(const CaParams p
   }
 }
 
-// ------------------------------------------------------------------------------------------------ OSAdapt mask tail
-// conv16->16 (3x3, pad 1) + bias + ReLU at half resolution.  kPool: input is full resolution and is
-// 2x2 average pooled on the fly (AvgPool2d(2), savsr_arch.py:193).  One pixel x 16 outputs per thread.
-template <bool kPool>
-__global__ void __launch_bounds__(128) mask_conv16_kernel(const float* __restrict__ in, const float* __restrict__ w,
-                                                          const float* __restrict__ b, float* __restrict__ out, int h2,
-                                                          int w2) {
-  __shared__ __align__(16) float w_s[9 * 16 * 16];  // [tap][ci][co]
+// OSAdapt mask tail at half resolution (savsr_arch.py:193-205).  Four threads share one half-resolution pixel: thread q
+// (= lane & 3) loads input channels 4q..4q+3 of every tap (one float4 per source pixel; nothing is fetched twice), forms
+// partial sums of all 16 outputs over its 4 channels, and a shuffle reduce-scatter leaves outputs 4q..4q+3 in thread q.
+//   kPool = true : input = AvgPool2d(2) of the full-resolution [B][H][W][16] map, fused into the loads;
+//   kProj = true : instead of the 16 ReLU outputs the kernel stores, per pixel, the NINE projections
+//                  d[t] = sum_c w_final[t][c] * out[c] of the final 16 -> 1 conv's taps (row stride 12 floats).
+// The final conv runs AFTER a bilinear x2 upsample; both are linear, so conv(up(h)) = sum_t up(d_t) shifted by tap t,
+// and the full-resolution kernel reads 36 scalars per pixel instead of 36 sixteen-channel vectors.
+template <bool kPool, bool kProj>
+__global__ void __launch_bounds__(256) mask_conv16_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                          const float* __restrict__ b, const float* __restrict__ wf,
+                                                          float* __restrict__ out, int h2, int w2) {
+  // [tap][ci][co] with 16 bytes of padding after every 4 input channels: the four threads of a quad read rows 4q + c,
+  // 256 bytes apart without the padding = the same banks, and every LDS.128 would take 16 wavefronts instead of 1
+  __shared__ __align__(16) float w_s[9 * 16 * 16 + 36 * 4];
+  __shared__ float wf_s[9 * 16];                    // [tap][ci] of the final conv (kProj)
   for (int i = threadIdx.x; i < 9 * 256; i += blockDim.x) {
     const int co = i & 15, ci = (i >> 4) & 15, tap = i >> 8;
-    w_s[i] = w[(co * 16 + ci) * 9 + tap];
+    w_s[i + (i >> 6) * 4] = w[(co * 16 + ci) * 9 + tap];
+  }
+  if (kProj) {
+    for (int i = threadIdx.x; i < 144; i += blockDim.x) wf_s[i] = wf[(i & 15) * 9 + (i >> 4)];
   }
   __syncthreads();
   const int n = blockIdx.y;
+  const int q = threadIdx.x & 3;
   const long npix2 = static_cast<long>(h2) * w2;
-  const long pix = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
-  if (pix >= npix2) return;
-  const int py = pix / w2, px = pix % w2;
+  const long pix = blockIdx.x * static_cast<long>(blockDim.x >> 2) + (threadIdx.x >> 2);
+  const bool live = pix < npix2;                    // whole quads are live or not; dead quads still run the shuffles
+  const int py = live ? pix / w2 : 0, px = live ? pix % w2 : 0;
   float acc[16];
 #pragma unroll
-  for (int o = 0; o < 16; ++o) acc[o] = b[o];
-  const int wf = 2 * w2;
+  for (int o = 0; o < 16; ++o) acc[o] = 0.f;
+  const int wfull = 2 * w2;
   const float* base = kPool ? in + static_cast<long>(n) * (4 * npix2) * 16 : in + static_cast<long>(n) * npix2 * 16;
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
     const int sy = py + tap / 3 - 1, sx = px + tap % 3 - 1;
-    if (sy < 0 || sy >= h2 || sx < 0 || sx >= w2) continue;
-    float a[16];
+    if (!live || sy < 0 || sy >= h2 || sx < 0 || sx >= w2) continue;
+    float4 a;
     if (kPool) {
-      const float4* p00 = reinterpret_cast<const float4*>(base + (static_cast<long>(2 * sy) * wf + 2 * sx) * 16);
-      const float4* p10 = reinterpret_cast<const float4*>(base + (static_cast<long>(2 * sy + 1) * wf + 2 * sx) * 16);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 q0 = p00[j], q1 = p00[4 + j], q2 = p10[j], q3 = p10[4 + j];
-        a[4 * j + 0] = 0.25f * ((q0.x + q1.x) + (q2.x + q3.x));
-        a[4 * j + 1] = 0.25f * ((q0.y + q1.y) + (q2.y + q3.y));
-        a[4 * j + 2] = 0.25f * ((q0.z + q1.z) + (q2.z + q3.z));
-        a[4 * j + 3] = 0.25f * ((q0.w + q1.w) + (q2.w + q3.w));
-      }
+      const float4 q0 = *reinterpret_cast<const float4*>(base + (static_cast<long>(2 * sy) * wfull + 2 * sx) * 16 + 4 * q);
+      const float4 q1 = *reinterpret_cast<const float4*>(base + (static_cast<long>(2 * sy) * wfull + 2 * sx + 1) * 16 + 4 * q);
+      const float4 q2 = *reinterpret_cast<const float4*>(base + (static_cast<long>(2 * sy + 1) * wfull + 2 * sx) * 16 + 4 * q);
+      const float4 q3 = *reinterpret_cast<const float4*>(base + (static_cast<long>(2 * sy + 1) * wfull + 2 * sx + 1) * 16 + 4 * q);
+      a.x = 0.25f * ((q0.x + q1.x) + (q2.x + q3.x)); a.y = 0.25f * ((q0.y + q1.y) + (q2.y + q3.y));
+      a.z = 0.25f * ((q0.z + q1.z) + (q2.z + q3.z)); a.w = 0.25f * ((q0.w + q1.w) + (q2.w + q3.w));
     } else {
-      const float4* q = reinterpret_cast<const float4*>(base + (static_cast<long>(sy) * w2 + sx) * 16);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 v = q[j];
-        a[4 * j + 0] = v.x; a[4 * j + 1] = v.y; a[4 * j + 2] = v.z; a[4 * j + 3] = v.w;
-      }
+      a = *reinterpret_cast<const float4*>(base + (static_cast<long>(sy) * w2 + sx) * 16 + 4 * q);
     }
+    const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-    for (int ci = 0; ci < 16; ++ci) {
-      const float4* wr = reinterpret_cast<const float4*>(w_s + (tap * 16 + ci) * 16);
+    for (int c = 0; c < 4; ++c) {
+      const float4* wr = reinterpret_cast<const float4*>(w_s + (tap * 16 + 4 * q + c) * 16 + (tap * 4 + q) * 4);
 #pragma unroll
       for (int o4 = 0; o4 < 4; ++o4) {
         const float4 wv = wr[o4];
-        acc[4 * o4 + 0] += a[ci] * wv.x; acc[4 * o4 + 1] += a[ci] * wv.y;
-        acc[4 * o4 + 2] += a[ci] * wv.z; acc[4 * o4 + 3] += a[ci] * wv.w;
+        acc[4 * o4 + 0] += av[c] * wv.x; acc[4 * o4 + 1] += av[c] * wv.y;
+        acc[4 * o4 + 2] += av[c] * wv.z; acc[4 * o4 + 3] += av[c] * wv.w;
       }
     }
   }
-  float4* d = reinterpret_cast<float4*>(out + (static_cast<long>(n) * npix2 + pix) * 16);
+  // reduce-scatter over the quad: 16 -> 8 (xor 2) -> 4 (xor 1); thread q ends with outputs 4q .. 4q+3
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
-    d[j] = make_float4(fmaxf(acc[4 * j], 0.f), fmaxf(acc[4 * j + 1], 0.f), fmaxf(acc[4 * j + 2], 0.f), fmaxf(acc[4 * j + 3], 0.f));
+  for (int off = 2, cnt = 8; off >= 1; off >>= 1, cnt >>= 1) {
+    const bool upper = (q & off) != 0;
+#pragma unroll
+    for (int i = 0; i < cnt; ++i) {
+      const float send = upper ? acc[i] : acc[i + cnt];
+      const float keep = upper ? acc[i + cnt] : acc[i];
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  float o4v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o4v[i] = fmaxf(acc[i] + b[4 * q + i], 0.f);
+  if (!kProj) {
+    if (live) *reinterpret_cast<float4*>(out + (static_cast<long>(n) * npix2 + pix) * 16 + 4 * q) = make_float4(o4v[0], o4v[1], o4v[2], o4v[3]);
+  } else {
+    float d[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      float v = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v += wf_s[t * 16 + 4 * q + i] * o4v[i];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      d[t] = v;
+    }
+    if (live && q < 3) {
+      float* dst = out + (static_cast<long>(n) * npix2 + pix) * 12 + 4 * q;
+      *reinterpret_cast<float4*>(dst) = q == 0 ? make_float4(d[0], d[1], d[2], d[3])
+                                     : q == 1 ? make_float4(d[4], d[5], d[6], d[7]) : make_float4(d[8], 0.f, 0.f, 0.f);
+    }
+  }
 }
 
-// bilinear x2 upsample (align_corners = False) + conv16->1 (3x3, pad 1) + bias (BN folded) + sigmoid.
-__global__ void __launch_bounds__(128) mask_final_kernel(const float* __restrict__ in, const float* __restrict__ w,
-                                                         const float* __restrict__ b, float* __restrict__ mask, int h2,
-                                                         int w2) {
-  __shared__ float w_s[9 * 16];  // [tap][ci]
-  for (int i = threadIdx.x; i < 144; i += blockDim.x) w_s[i] = w[(i & 15) * 9 + (i >> 4)];
-  __syncthreads();
+// mask = sigmoid(bias + sum_t bilinear_x2(d_t)(p + tap t)): the bilinear x2 upsample (align_corners = False) of the nine tap
+// projections written by mask_conv16_kernel<false, true>, zero outside the full-resolution image (conv padding 1).
+__global__ void __launch_bounds__(256) mask_final_kernel(const float* __restrict__ d, const float* __restrict__ b,
+                                                         float* __restrict__ mask, int h2, int w2) {
   const int n = blockIdx.y;
   const int H = 2 * h2, W = 2 * w2;
   const long npix = static_cast<long>(H) * W;
   const long pix = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (pix >= npix) return;
   const int py = pix / W, px = pix % W;
-  const float* base = in + static_cast<long>(n) * h2 * w2 * 16;
+  const float* base = d + static_cast<long>(n) * h2 * w2 * 12;
   float acc = b[0];
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
@@ -421,20 +451,9 @@ __global__ void __launch_bounds__(128) mask_final_kernel(const float* __restrict
     const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
     const int y1 = y0 + (y0 < h2 - 1 ? 1 : 0), x1 = x0 + (x0 < w2 - 1 ? 1 : 0);
     const float ly = fy - y0, lx = fx - x0;
-    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-    const float4* p00 = reinterpret_cast<const float4*>(base + (static_cast<long>(y0) * w2 + x0) * 16);
-    const float4* p01 = reinterpret_cast<const float4*>(base + (static_cast<long>(y0) * w2 + x1) * 16);
-    const float4* p10 = reinterpret_cast<const float4*>(base + (static_cast<long>(y1) * w2 + x0) * 16);
-    const float4* p11 = reinterpret_cast<const float4*>(base + (static_cast<long>(y1) * w2 + x1) * 16);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4 a = p00[j], bb = p01[j], cc = p10[j], d = p11[j];
-      const float* ws = w_s + tap * 16 + 4 * j;
-      acc += ws[0] * (w00 * a.x + w01 * bb.x + w10 * cc.x + w11 * d.x);
-      acc += ws[1] * (w00 * a.y + w01 * bb.y + w10 * cc.y + w11 * d.y);
-      acc += ws[2] * (w00 * a.z + w01 * bb.z + w10 * cc.z + w11 * d.z);
-      acc += ws[3] * (w00 * a.w + w01 * bb.w + w10 * cc.w + w11 * d.w);
-    }
+    const float v00 = base[(static_cast<long>(y0) * w2 + x0) * 12 + tap], v01 = base[(static_cast<long>(y0) * w2 + x1) * 12 + tap];
+    const float v10 = base[(static_cast<long>(y1) * w2 + x0) * 12 + tap], v11 = base[(static_cast<long>(y1) * w2 + x1) * 12 + tap];
+    acc += (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
   }
   mask[static_cast<long>(n) * npix + pix] = sigmoidf_(acc);
 }
@@ -669,11 +688,11 @@ extern "C" int savsr_osadapt_mask(savsr_ctx* ctx, const float* in16, int batch, 
   cudaStream_t st = static_cast<cudaStream_t>(st_);
   const int h2 = height / 2, w2 = width / 2;
   const long npix2 = static_cast<long>(h2) * w2;
-  dim3 g2(static_cast<unsigned>((npix2 + 127) / 128), batch);
-  mask_conv16_kernel<true><<<g2, 128, 0, st>>>(in16, wa, ba, half0, h2, w2);
-  mask_conv16_kernel<false><<<g2, 128, 0, st>>>(half0, wb, bb, half1, h2, w2);
-  dim3 g1(static_cast<unsigned>((4 * npix2 + 127) / 128), batch);
-  mask_final_kernel<<<g1, 128, 0, st>>>(half1, wc, bc, mask, h2, w2);
+  dim3 g2(static_cast<unsigned>((npix2 + 63) / 64), batch);   // 256 threads = 64 half-resolution pixels x 4 channel quarters
+  mask_conv16_kernel<true, false><<<g2, 256, 0, st>>>(in16, wa, ba, nullptr, half0, h2, w2);
+  mask_conv16_kernel<false, true><<<g2, 256, 0, st>>>(half0, wb, bb, wc, half1, h2, w2);   // half1 <- the nine tap projections
+  dim3 g1(static_cast<unsigned>((4 * npix2 + 255) / 256), batch);
+  mask_final_kernel<<<g1, 256, 0, st>>>(half1, bc, mask, h2, w2);
   SAVSR_CUDA(cudaGetLastError());
   return 0;
 }
