@@ -23,7 +23,8 @@ FMT_BF16, FMT_FP16 = 0, 1
 FMT_NAMES = {"bf16": FMT_BF16, "fp16": FMT_FP16}
 ROWS_LINEAR, ROWS_QUAD = 0, 1     # enum savsr_row_order: QUAD for savsr_conv n_tile 64, LINEAR for savsr_satu_fused
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libsavsr_sm100.so")
+# SAVSR_LIB_PATH: alternative build of the same ABI (A/B timing of kernel variants); default = the in-tree library
+LIB_PATH = os.environ.get("SAVSR_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libsavsr_sm100.so")
 
 
 class SavsrError(RuntimeError):

@@ -160,9 +160,13 @@ __global__ void __launch_bounds__(256) osa_linear_kernel(const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (blockIdx.x * 8 >= rows) return;
   const int stride = osa_scratch_stride(c.ci);
-  for (int i = threadIdx.x; i < L.batch * len; i += blockDim.x) {
+  // samples are split over blockIdx.z: 24-48 row blocks alone leave most SMs idle and each warp walking all samples
+  const int per = (L.batch + gridDim.z - 1) / gridDim.z;
+  const int n0 = blockIdx.z * per, n1 = min(L.batch, n0 + per);
+  if (n0 >= n1) return;
+  for (int i = threadIdx.x; i < (n1 - n0) * len; i += blockDim.x) {
     const int n = i / len, k = i - n * len;
-    s_in[i] = c.scratch[static_cast<long>(n) * stride + in_off + k];
+    s_in[i] = c.scratch[static_cast<long>(n0 + n) * stride + in_off + k];
   }
   __syncthreads();
   const int row = blockIdx.x * 8 + warp;
@@ -172,8 +176,8 @@ __global__ void __launch_bounds__(256) osa_linear_kernel(const __grid_constant__
 #pragma unroll
   for (int j = 0; j < 20; ++j) w[j] = lane + 32 * j < len ? __ldg(wr + lane + 32 * j) : 0.f;
   const float bias = B[row];
-  for (int n = 0; n < L.batch; ++n) {
-    const float* in = s_in + n * len;
+  for (int n = n0; n < n1; ++n) {
+    const float* in = s_in + (n - n0) * len;
     float acc = 0.f;
 #pragma unroll
     for (int j = 0; j < 20; ++j) if (lane + 32 * j < len) acc += w[j] * in[lane + 32 * j];
@@ -183,54 +187,63 @@ __global__ void __launch_bounds__(256) osa_linear_kernel(const __grid_constant__
   }
 }
 
-// ScaleAttention (savsr_arch.py:91-96): z = ReLU(BN(fc v)); ca/fa/sa = sigmoid heads; ka = softmax head (T = 1).
-// grid (batch, nconvs), 256 threads.
-__global__ void __launch_bounds__(256) osa_attention_kernel(const __grid_constant__ OsaLaunch L) {
+// ScaleAttention + kernel assembly in one launch.  W'[o,i,u,v] = fa[o] ca[i] sa[u,v] sum_k ka[k] bank[k,o,i,u,v]  -> packed
+// 16-bit K-blocks (n_tile 64, SAVSR_ROWS_QUAD).  grid (ceil(co*ci/256), nconvs, sample splits), thread = (o, i) with its 72
+// bank values in registers across the samples of the split.  Every block first recomputes the attention vectors of its
+// samples in shared memory (z = ReLU(BN(fc v)), sigmoid heads ca / fa / sa, softmax head ka: ~5 kMAC per sample, far
+// cheaper than a separate launch); block x = 0 also writes them to the scratch area (tests read them there).
+constexpr int kAsmMaxSamples = 8;
+__global__ void __launch_bounds__(256) osa_assemble_kernel(const __grid_constant__ OsaLaunch L) {
   const savsr_osa_params& c = L.c[blockIdx.y];
-  const int n = blockIdx.x;
-  __shared__ float z[32];
-  __shared__ float logit[8];
-  float* sc = c.scratch + static_cast<long>(n) * osa_scratch_stride(c.ci);
-  const float* v2 = sc + osa_off_v2(c.ci);
-  float* att = sc + osa_off_att(c.ci);
+  __shared__ float z_s[kAsmMaxSamples][32];
+  __shared__ float att_s[kAsmMaxSamples][64 * SAVSR_MAX_SRC + 64 + 9 + 8];
+  const int per = (L.batch + gridDim.z - 1) / gridDim.z;       // <= kAsmMaxSamples (checked by the launcher)
+  const int n0 = blockIdx.z * per, n1 = min(L.batch, n0 + per);
+  if (n0 >= n1 || blockIdx.x * blockDim.x >= c.co * c.ci) return;
+  const int ns = n1 - n0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int a = warp; a < c.att; a += 8) {
+  const int stride = osa_scratch_stride(c.ci);
+  const int nout = c.ci + c.co + 9 + 8;
+  // z[n][a] (savsr_arch.py:91-93)
+  for (int r = warp; r < ns * c.att; r += 8) {
+    const int n = r / c.att, a = r - n * c.att;
+    const float* v2 = c.scratch + static_cast<long>(n0 + n) * stride + osa_off_v2(c.ci);
     float acc = 0.f;
     for (int i = lane; i < c.ci; i += 32) acc += __ldg(c.fc_w + a * c.ci + i) * v2[i];
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) z[a] = fmaxf(acc * c.bn_scale[a] + c.bn_shift[a], 0.f);
+    if (lane == 0) z_s[n][a] = fmaxf(acc * c.bn_scale[a] + c.bn_shift[a], 0.f);
   }
   __syncthreads();
-  const int nout = c.ci + c.co + 9 + 8;
-  for (int j = threadIdx.x; j < nout; j += blockDim.x) {
+  // heads (94-96): sigmoid for channel / filter / spatial, logits for the kernel head
+  for (int r = threadIdx.x; r < ns * nout; r += blockDim.x) {
+    const int n = r / nout, j = r - n * nout;
     const float* w;
     float b;
-    int kind;  // 0 sigmoid, 1 softmax logit
-    int local;
-    if (j < c.ci) { w = c.ch_w + j * c.att; b = c.ch_b[j]; kind = 0; local = j; }
-    else if (j < c.ci + c.co) { local = j - c.ci; w = c.fl_w + local * c.att; b = c.fl_b[local]; kind = 0; }
-    else if (j < c.ci + c.co + 9) { local = j - c.ci - c.co; w = c.sp_w + local * c.att; b = c.sp_b[local]; kind = 0; }
-    else { local = j - c.ci - c.co - 9; w = c.kn_w + local * c.att; b = c.kn_b[local]; kind = 1; }
+    if (j < c.ci) { w = c.ch_w + j * c.att; b = c.ch_b[j]; }
+    else if (j < c.ci + c.co) { w = c.fl_w + (j - c.ci) * c.att; b = c.fl_b[j - c.ci]; }
+    else if (j < c.ci + c.co + 9) { w = c.sp_w + (j - c.ci - c.co) * c.att; b = c.sp_b[j - c.ci - c.co]; }
+    else { w = c.kn_w + (j - c.ci - c.co - 9) * c.att; b = c.kn_b[j - c.ci - c.co - 9]; }
     float acc = b;
-    for (int a = 0; a < c.att; ++a) acc += w[a] * z[a];
-    if (kind == 0) att[j] = sigmoidf_(acc);
-    else logit[local] = acc;
+    for (int a = 0; a < c.att; ++a) acc += __ldg(w + a) * z_s[n][a];
+    att_s[n][j] = j < c.ci + c.co + 9 ? sigmoidf_(acc) : acc;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float mx = logit[0];
-    for (int k = 1; k < 8; ++k) mx = fmaxf(mx, logit[k]);
+  if (threadIdx.x < ns) {   // softmax over the 8 kernel logits (temperature 1)
+    float* ka = att_s[threadIdx.x] + c.ci + c.co + 9;
+    float mx = ka[0];
+    for (int k = 1; k < 8; ++k) mx = fmaxf(mx, ka[k]);
     float e[8], sum = 0.f;
-    for (int k = 0; k < 8; ++k) { e[k] = expf(logit[k] - mx); sum += e[k]; }
-    for (int k = 0; k < 8; ++k) att[c.ci + c.co + 9 + k] = e[k] / sum;
+    for (int k = 0; k < 8; ++k) { e[k] = expf(ka[k] - mx); sum += e[k]; }
+    for (int k = 0; k < 8; ++k) ka[k] = e[k] / sum;
   }
-}
-
-// W'[o,i,u,v] = fa[o] ca[i] sa[u,v] sum_k ka[k] bank[k,o,i,u,v]  -> packed bf16 K-blocks (n_tile 64).
-// grid (ceil(co*ci/256), nconvs), thread = (o, i), bank values kept in registers across samples.
-__global__ void __launch_bounds__(256) osa_assemble_kernel(const __grid_constant__ OsaLaunch L) {
-  const savsr_osa_params& c = L.c[blockIdx.y];
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    for (int r = threadIdx.x; r < ns * nout; r += blockDim.x) {
+      const int n = r / nout, j = r - n * nout;
+      c.scratch[static_cast<long>(n0 + n) * stride + osa_off_att(c.ci) + j] = att_s[n][j];
+    }
+  }
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= c.co * c.ci) return;
   const int i = idx % c.ci, o = idx / c.ci;
@@ -246,12 +259,12 @@ __global__ void __launch_bounds__(256) osa_assemble_kernel(const __grid_constant
   const long sample_elems = static_cast<long>(c.co) * c.ci * 9;
   const int row = quad_row(o);   // SAVSR_ROWS_QUAD: the packed row that holds output channel o (the map is an involution)
   const int inner = row * 64 + ((((kk >> 3) ^ (row & 7)) << 3) | (kk & 7));
-  for (int n = 0; n < L.batch; ++n) {
-    const float* att = c.scratch + static_cast<long>(n) * osa_scratch_stride(c.ci) + osa_off_att(c.ci);
+  for (int n = 0; n < ns; ++n) {
+    const float* att = att_s[n];
     const float ca = att[i], fa = att[c.ci + o];
     const float* sa = att + c.ci + c.co;
     const float* ka = sa + 9;
-    uint16_t* dst = static_cast<uint16_t*>(c.packed) + n * sample_elems;
+    uint16_t* dst = static_cast<uint16_t*>(c.packed) + (n0 + n) * sample_elems;
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       float acc = 0.f;
@@ -641,17 +654,19 @@ extern "C" int savsr_osa_prologue(savsr_ctx* ctx, const savsr_osa_params* convs,
   L.inv_h = inv_scale_h; L.inv_w = inv_scale_w;
   L.fmt = ctx->fmt;
   osa_pool_kernel<<<dim3(max_ci / 64, batch, nconvs), kOsaThreads, 0, st>>>(L);
-  const size_t lin_smem = static_cast<size_t>(batch) * 2 * max_ci * sizeof(float);
+  const int lin_split = batch >= 12 ? 3 : (batch >= 4 ? 2 : 1);
+  const size_t lin_smem = static_cast<size_t>((batch + lin_split - 1) / lin_split) * 2 * max_ci * sizeof(float);
   SAVSR_REQUIRE(lin_smem <= 200 * 1024, "savsr_osa_prologue: batch %d too large for the routing kernel's shared memory", batch);
   static bool lin_attr = false;
   if (lin_smem > 48 * 1024 && !lin_attr) {
     SAVSR_CUDA(cudaFuncSetAttribute(osa_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     lin_attr = true;
   }
-  osa_linear_kernel<<<dim3((2 * max_ci + 7) / 8, nconvs), 256, lin_smem, st>>>(L, 0);
-  osa_linear_kernel<<<dim3((max_ci + 7) / 8, nconvs), 256, lin_smem, st>>>(L, 1);
-  osa_attention_kernel<<<dim3(batch, nconvs), 256, 0, st>>>(L);
-  osa_assemble_kernel<<<dim3((64 * max_ci + 255) / 256, nconvs), 256, 0, st>>>(L);
+  osa_linear_kernel<<<dim3((2 * max_ci + 7) / 8, nconvs, lin_split), 256, lin_smem, st>>>(L, 0);
+  osa_linear_kernel<<<dim3((max_ci + 7) / 8, nconvs, lin_split), 256, lin_smem, st>>>(L, 1);
+  int asm_split = batch >= 16 ? 4 : (batch >= 6 ? 2 : 1);
+  while ((batch + asm_split - 1) / asm_split > kAsmMaxSamples) ++asm_split;
+  osa_assemble_kernel<<<dim3((64 * max_ci + 255) / 256, nconvs, asm_split), 256, 0, st>>>(L);
   SAVSR_CUDA(cudaGetLastError());
   return 0;
 }

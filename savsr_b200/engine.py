@@ -228,7 +228,7 @@ class Plan:
         inv_w = float(np.float32(1.0) / np.float32(self.scale[1]))
         lib, ctx, n, B = self.lib, self.ctx.handle, len(convs), self.B
         npart, npix = self.lr.tiles * 4, self.hp * self.wp
-        self._emit(lambda st: lib.savsr_osa_prologue(ctx, arr, n, B, npart, npix, inv_h, inv_w, st), launches=5, kind="osa_prologue")
+        self._emit(lambda st: lib.savsr_osa_prologue(ctx, arr, n, B, npart, npix, inv_h, inv_w, st), launches=4, kind="osa_prologue")
 
     def _pool(self, key: str) -> int:
         """Partial-sum buffer [B][tiles*4][64] written by a conv epilogue (cached per producing conv)."""
