@@ -59,6 +59,18 @@ def test_forward_vs_oracle_with_stage_errors(G, kw):
     assert info["psnr_vs_oracle"] > 55.0
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_forward_random_shapes_and_scales(G, seed):
+    """Edge sweep: random odd / tiny frame sizes, batch sizes and asymmetric non-integer scales (up to x8) vs the oracle."""
+    import random
+    rnd = random.Random(1000 + seed)
+    h, w = rnd.randint(5, 37), rnd.randint(5, 41)
+    scale = (rnd.choice([1.1, 1.5, 2, 2.3, 3, 3.9, 4, 6.25, 8]), rnd.choice([1.2, 1.7, 2, 2.7, 3.5, 4, 5.1, 7.3]))
+    info = G.check_forward(b=rnd.randint(1, 3), h=h, w=w, scale=scale, sd_seed=seed % 3, in_seed=77 + seed, impl="halo", graph=bool(seed & 1),
+                           tol=TOL["bf16"][0], stage_tol=TOL["bf16"][1])
+    assert info["psnr_vs_oracle"] > 55.0, info
+
+
 def test_fp16_path_meets_the_fp32_criterion_with_stage_errors(G):
     for kw in (dict(b=1, h=16, w=20, scale=(2, 2)), dict(b=2, h=13, w=15, scale=(1.5, 4), sd_seed=1, in_seed=1236),
                dict(b=1, h=31, w=31, scale=(3, 3), sd_seed=2)):
