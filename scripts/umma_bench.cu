@@ -359,6 +359,29 @@ int main() {
   run_pair<128>(iters, d_out);
   run_pair<256>(iters, d_out);
   if (getenv("PAIR_ONLY")) return 0;
+
+  if (getenv("SUSTAINED")) {
+    // sustained (power-limited) rate: wall time per MMA over ~0.2 s of back-to-back launches on all SMs, single-CTA vs CTA-pair
+    const int it = 1 << 16;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const size_t smem1 = 1024 + 48 * 1024 + 64 * 128;
+    cudaFuncSetAttribute(bench<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+    cudaFuncSetAttribute(bench_pair<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+    for (int rep = 0; rep < 3; ++rep) {
+      float ms1 = 0, ms2 = 0;
+      cudaEventRecord(e0);
+      for (int l = 0; l < 20; ++l) bench<128, 64><<<148, 128, smem1>>>(it, d_out);
+      cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms1, e0, e1);
+      cudaEventRecord(e0);
+      for (int l = 0; l < 20; ++l) bench_pair<64><<<148, 128, smem1>>>(it, d_out, 1024);
+      cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms2, e0, e1);
+      // per SM: single = it*4 MMAs of M=128 per launch; pair = it*4 MMAs of M=256 per 2 SMs = it*2 M=128-equivalents per SM
+      const double n1 = 20.0 * it * 4, n2 = 20.0 * it * 4;   // M=128-equivalent MMAs per SM (pair: each SM executes its half of every MMA)
+      printf("sustained rep %d: cta_group::1 %.2f ns per M=128,N=64 MMA per SM (%.0f TFLOP/s chip) | cta_group::2 %.2f ns (%.0f TFLOP/s chip)\n", rep,
+             ms1 * 1e6 / n1, 148 * 2.0 * 128 * 64 * 16 / (ms1 * 1e6 / n1) / 1e3, ms2 * 1e6 / n2, 148 * 2.0 * 128 * 64 * 16 / (ms2 * 1e6 / n2) / 1e3);
+    }
+    return 0;
+  }
   {
     const size_t smem = 1024 + 24 * 1024 + 9 * 8192;
     cudaFuncSetAttribute(bench_conv_rolled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
