@@ -13,6 +13,15 @@ __host__ __device__ constexpr uint32_t idesc_mn(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+__device__ int g_random_fill = 0;   // 1: pseudo-random bf16 operands in (-2, 2) instead of the constant 1.0 (data-dependent power)
+__device__ __forceinline__ uint32_t fill_word(int i) {
+  if (!g_random_fill) return 0x3c003c00u;
+  uint32_t h = static_cast<uint32_t>(i) * 2654435761u + blockIdx.x * 40503u;
+  h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+  // two bf16 values: random sign and mantissa, exponent 126..127 (|x| in [0.5, 2))
+  const uint32_t lo = ((h & 0x8000u) | 0x3f00u | (h & 0xffu)), hi = (((h >> 16) & 0x8000u) | 0x3f00u | ((h >> 16) & 0xffu));
+  return lo | (hi << 16);
+}
 template <int M, int N>
 __global__ void __launch_bounds__(128, 1) bench(int iters, long long* out, int a_off = 0, int a_sbo = 1024) {
   extern __shared__ uint8_t raw[];
@@ -20,7 +29,7 @@ __global__ void __launch_bounds__(128, 1) bench(int iters, long long* out, int a
   __shared__ uint64_t bar;
   __shared__ uint32_t slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < (48 * 1024 + N * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  for (int i = threadIdx.x; i < (48 * 1024 + N * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = fill_word(i);
   if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (warp == 0) tmem_alloc<512>(&slot);
@@ -278,7 +287,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) bench_pair(i
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-  for (int i = threadIdx.x; i < (48 * 1024 + N * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  for (int i = threadIdx.x; i < (48 * 1024 + N * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = fill_word(i);
   if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (warp == 0) {
@@ -367,7 +376,9 @@ int main() {
     const size_t smem1 = 1024 + 48 * 1024 + 64 * 128;
     cudaFuncSetAttribute(bench<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
     cudaFuncSetAttribute(bench_pair<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-    for (int rep = 0; rep < 3; ++rep) {
+    for (int rep = 0; rep < 4; ++rep) {
+      const int rnd = rep >= 2;
+      cudaMemcpyToSymbol(g_random_fill, &rnd, sizeof(int));
       float ms1 = 0, ms2 = 0;
       cudaEventRecord(e0);
       for (int l = 0; l < 20; ++l) bench<128, 64><<<148, 128, smem1>>>(it, d_out);
@@ -377,7 +388,7 @@ int main() {
       cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms2, e0, e1);
       // per SM: single = it*4 MMAs of M=128 per launch; pair = it*4 MMAs of M=256 per 2 SMs = it*2 M=128-equivalents per SM
       const double n1 = 20.0 * it * 4, n2 = 20.0 * it * 4;   // M=128-equivalent MMAs per SM (pair: each SM executes its half of every MMA)
-      printf("sustained rep %d: cta_group::1 %.2f ns per M=128,N=64 MMA per SM (%.0f TFLOP/s chip) | cta_group::2 %.2f ns (%.0f TFLOP/s chip)\n", rep,
+      printf("sustained rep %d (%s operands): cta_group::1 %.2f ns per M=128,N=64 MMA per SM (%.0f TFLOP/s chip) | cta_group::2 %.2f ns (%.0f TFLOP/s chip)\n", rep, rnd ? "random" : "constant",
              ms1 * 1e6 / n1, 148 * 2.0 * 128 * 64 * 16 / (ms1 * 1e6 / n1) / 1e3, ms2 * 1e6 / n2, 148 * 2.0 * 128 * 64 * 16 / (ms2 * 1e6 / n2) / 1e3);
     }
     return 0;
