@@ -1,0 +1,46 @@
+#!/usr/bin/env python
+"""Frame-sharded clip evaluation on N GPUs (torchrun) vs the same clip on one GPU: the gathered frames must be identical.
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29577 scripts/multi_gpu_check.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import savsr_b200  # noqa: E402
+from oracle.state_dict_fixture import make_state_dict  # noqa: E402
+from savsr_b200 import datapath, sharding  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    T, H, W, scale = 11, 96, 128, (4, 4)
+    frames = torch.from_numpy(np.random.default_rng(3).integers(0, 256, size=(T, H, W, 3), dtype=np.uint8)).to(dev)
+    net = savsr_b200.SAVSR().to(dev).eval()
+    net.load_state_dict(make_state_dict(0))
+    net.set_scale(scale)
+    mine = sharding.shard_frames(T, rank, world)                       # the reference's rank-strided split
+    with torch.no_grad():
+        res = datapath.evaluate_clip(net, frames, scale, frames=mine, batch=3)
+        full = sharding.gather_outputs(res["sr"], mine, T)              # NCCL all-gather, ragged shards padded
+        psnr = sharding.gather_outputs(res["psnr_y"].float().view(-1, 1), mine, T).view(-1)
+        ref = datapath.evaluate_clip(net, frames, scale, batch=4)      # every rank also runs the whole clip alone
+    same = bool(torch.equal(full, ref["sr"]))
+    dp = float((psnr - ref["psnr_y"].float()).abs().max())
+    ok = torch.tensor([int(same and dp < 1e-4)], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"world {world}: sharded + gathered clip identical to the single-GPU clip on every rank: {bool(ok.item())} "
+              f"(frames {T}, {H}x{W}, x{scale[0]}; PSNR-Y max diff {dp:.2e} dB; mean PSNR-Y {float(ref['psnr_y'].mean()):.3f} dB)")
+    dist.destroy_process_group()
+    sys.exit(0 if ok.item() else 1)
+
+
+if __name__ == "__main__":
+    main()
