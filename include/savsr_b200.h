@@ -45,7 +45,8 @@ typedef void* savsr_stream;             /* cudaStream_t                         
 enum savsr_format { SAVSR_FMT_BF16 = 0, SAVSR_FMT_FP16 = 1 };
 /* Row (output channel) order inside a packed n_tile = 64 weight block.  LINEAR: row n = channel n.  QUAD: row n =
  * channel with the bit fields [2:1] and [4:3] of n swapped -- the order savsr_conv requires for n_tile 64 (its epilogue
- * reads the accumulator with 16x256b TMEM loads and stores 16 contiguous bytes per thread).  savsr_satu_fused takes LINEAR. */
+ * reads the accumulator with 16x256b TMEM loads and stores 16 contiguous bytes per thread); savsr_satu_fused takes QUAD for
+ * its fusion weights (same epilogue) and LINEAR for the compress / expand expert matrices. */
 enum savsr_row_order { SAVSR_ROWS_LINEAR = 0, SAVSR_ROWS_QUAD = 1 };
 
 enum savsr_act { SAVSR_ACT_NONE = 0, SAVSR_ACT_LRELU = 1, SAVSR_ACT_RELU = 2 };
@@ -272,7 +273,8 @@ int savsr_satu_kconv_sta(savsr_ctx* ctx, savsr_arena* arena, int a_slot, int x_s
  * Tensor-core version of the HR stage: savsr_satu_gather followed by the 128->64 fusion conv (savsr_arch.py:364-374) in
  * one kernel; the compress / expand / fusion GEMMs run on tcgen05 with the tiles built in shared memory.
  * w_compress: savsr_pack_conv_weight of [32][64][1][1] (rows e*8+k), n_tile 16; w_expand: of [64][64][1][1] with input
- * columns e*8+k (32..63 zero), n_tile 64; w_fusion: of the fusion filter [64][128][1][1], n_tile 64.
+ * columns e*8+k (32..63 zero), n_tile 64; w_fusion: of the fusion filter [64][128][1][1], n_tile 64,
+ * SAVSR_ROWS_QUAD (w_compress and w_expand: SAVSR_ROWS_LINEAR).
  * Writes the fused HR feature (bf16) to hr slot dst_slot.
  */
 int savsr_satu_fused(savsr_ctx* ctx, savsr_arena* lr, int x_slot, int sta_slot, int h, int w, savsr_arena* hr,

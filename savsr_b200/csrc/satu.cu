@@ -743,24 +743,31 @@ __global__ void __launch_bounds__(kFusedThreads, 2) satu_fused_kernel(const Fuse
     }
     mbar_wait(bar, phase); phase ^= 1;
     tc_fence_after();
-    // ---- P7: + bias -> bf16 HR feature (each thread: one pixel, 32 channels = 64 contiguous bytes)
+    // ---- P7: + bias -> 16-bit HR feature.  16x256b TMEM loads over SAVSR_ROWS_QUAD-ordered fusion weights: thread
+    // (g, q) holds pixels g + 8 j of its quadrant and the 8 consecutive channels half * 32 + 8 q .., so a store
+    // instruction writes 64 contiguous bytes per thread quad, 8 lines per warp (one pixel per lane touched 32 lines).
     {
-      const long pix = pix0 + row;
-      const bool valid = pix < NPIX;
-      uint4* d = reinterpret_cast<uint4*>(p.hr + ((static_cast<long>(p.dst_slot) * p.batch + n) * NPIX + pix) * kC + half * 32);
+      const int g = lane >> 2, q = lane & 3;
+      uint32_t ya[16], yb[16];
+      tmem_ld_16x256b_x4(tY + lane_addr + half * 32, ya);
+      tmem_ld_16x256b_x4(tY + lane_addr + (16u << 16) + half * 32, yb);
+      tmem_ld_wait();
+      const int ch0 = half * 32 + q * 8;
+      float bias8[8];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        uint32_t y[16];
-        tmem_ld16(tY + lane_addr + half * 32 + 16 * j, y);
-        tmem_ld_wait();
-        if (valid) {
+      for (int i = 0; i < 8; ++i) bias8[i] = sbias[ch0 + i];
 #pragma unroll
-          for (int c2 = 0; c2 < 2; ++c2) {
-            float v[8];
+      for (int j = 0; j < 4; ++j) {
+        const long pix = pix0 + quad * 32 + g + 8 * j;
+        if (pix < NPIX) {
+          const uint32_t* y = j < 2 ? ya : yb;
+          float v[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(y[8 * c2 + e]) + sbias[half * 32 + 16 * j + 8 * c2 + e];
-            d[2 * j + c2] = pack8(v, p.fmt);
+          for (int k = 0; k < 4; ++k) {
+            v[2 * k] = __uint_as_float(y[4 * k + 2 * (j & 1)]) + bias8[2 * k];
+            v[2 * k + 1] = __uint_as_float(y[4 * k + 2 * (j & 1) + 1]) + bias8[2 * k + 1];
           }
+          *reinterpret_cast<uint4*>(p.hr + ((static_cast<long>(p.dst_slot) * p.batch + n) * NPIX + pix) * kC + ch0) = pack8(v, p.fmt);
         }
       }
     }

@@ -449,7 +449,7 @@ class Plan:
         we_all = torch.zeros(64, 64, 1, 1, device=self.device)
         we_all[:, :32, 0, 0] = self._p(u + ".weight_expand").view(4, 64, 8).permute(1, 0, 2).reshape(64, 32)   # cols e*8+k
         pwc, pwe = self._pack(wc_all, n_tile=16), self._pack(we_all, rows=K.ROWS_LINEAR)
-        pwf = self._pack(self._p(u + ".fusion.weight"), rows=K.ROWS_LINEAR)
+        pwf = self._packp(u + ".fusion.weight")                       # QUAD rows: same 16x256b epilogue as the convs
         fb = self._ptr(u + ".fusion.bias")
         self._emit(lambda st: lib.savsr_satu_fused(ctx, lrh, TR, STA, hh, ww, hrh, 0, tab, by, bx, pwc, pwe, pwf, fb, st),
                    kind="satu_fused", flops=2.0 * B * self.H * self.W * (64 * 32 + 32 * 64 + 128 * 64))

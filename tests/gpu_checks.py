@@ -570,7 +570,7 @@ def check_satu_fused(B=2, h=13, w=15, scale=(2.7, 1.5), seed=1):
     we_all = torch.zeros(64, 64, 1, 1)
     we_all[:, :32, 0, 0] = sd["upsample.weight_expand"].view(4, 64, 8).permute(1, 0, 2).reshape(64, 32)
     pwc, pwe = pack_weight(wc_all, n_tile=16), pack_weight(we_all, rows=K.ROWS_LINEAR)
-    pwf = pack_weight(sd["upsample.fusion.weight"], rows=K.ROWS_LINEAR)
+    pwf = pack_weight(sd["upsample.fusion.weight"])               # QUAD rows
     fb = sd["upsample.fusion.bias"].to(DEV).contiguous()
     K.check(K.load().savsr_satu_fused(ctx().handle, lr.a.handle, 0, 1, h, w, hr.a.handle, 0, table.data_ptr(), by.data_ptr(), bx.data_ptr(),
                                       pwc.data_ptr(), pwe.data_ptr(), pwf.data_ptr(), fb.data_ptr(), _stream()))
