@@ -31,8 +31,7 @@ so agreement with the golden vectors is a meaningful check of the restatement.
 """
 from __future__ import annotations
 
-import math
-from typing import Dict, List, Optional, Sequence, Tuple, Union
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 import torch

@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import math
 import os
-from typing import Dict, Optional, Tuple, Union
+from typing import Dict, Tuple, Union
 
 import torch
 import torch.nn as nn

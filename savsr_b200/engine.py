@@ -17,7 +17,6 @@ from __future__ import annotations
 import os
 
 import ctypes as C
-import math
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np

@@ -7,7 +7,7 @@ path; only the optional gather of results uses ``torch.distributed`` (NCCL on GP
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Sequence, Tuple
+from typing import Callable, List, Optional, Sequence
 
 import torch
 

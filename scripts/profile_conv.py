@@ -3,7 +3,6 @@
 usage: profile_conv.py [nsrc] [ngroups] [batch] [impl] [ksize] [reps] [pool 0/1] [res1 0/1]"""
 import os
 import sys
-import time
 
 import torch
 

@@ -1,7 +1,6 @@
 """A recording stand-in for libsavsr_sm100 so the host-side plan logic can be tested without a GPU.
 Test infrastructure only: every compute entry point just records its arguments and returns 0."""
 import contextlib
-import ctypes as C
 from types import SimpleNamespace
 
 import torch

@@ -1,6 +1,5 @@
 """CPU-only: the host-side forward plan (slot allocation, launch order, grouping) against a recording fake
 of the C library.  Checks the dataflow invariants the kernels rely on; no compute happens here."""
-import ctypes as C
 
 import pytest
 import torch
