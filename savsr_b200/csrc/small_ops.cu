@@ -204,29 +204,42 @@ __global__ void __launch_bounds__(256) osa_assemble_kernel(const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int stride = osa_scratch_stride(c.ci);
   const int nout = c.ci + c.co + 9 + 8;
-  // z[n][a] (savsr_arch.py:91-93)
-  for (int r = warp; r < ns * c.att; r += 8) {
-    const int n = r / c.att, a = r - n * c.att;
-    const float* v2 = c.scratch + static_cast<long>(n0 + n) * stride + osa_off_v2(c.ci);
-    float acc = 0.f;
-    for (int i = lane; i < c.ci; i += 32) acc += __ldg(c.fc_w + a * c.ci + i) * v2[i];
+  // z[n][a] (savsr_arch.py:91-93): one warp per attention channel, its fc row held in registers across the samples
+  for (int a = warp; a < c.att; a += 8) {
+    float wr[10];   // ceil(320 / 32)
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) z_s[n][a] = fmaxf(acc * c.bn_scale[a] + c.bn_shift[a], 0.f);
+    for (int j = 0; j < 10; ++j) wr[j] = lane + 32 * j < c.ci ? __ldg(c.fc_w + a * c.ci + lane + 32 * j) : 0.f;
+    const float bs = c.bn_scale[a], bh = c.bn_shift[a];
+    for (int n = 0; n < ns; ++n) {
+      const float* v2 = c.scratch + static_cast<long>(n0 + n) * stride + osa_off_v2(c.ci);
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 10; ++j) if (lane + 32 * j < c.ci) acc += wr[j] * v2[lane + 32 * j];
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      if (lane == 0) z_s[n][a] = fmaxf(acc * bs + bh, 0.f);
+    }
   }
   __syncthreads();
-  // heads (94-96): sigmoid for channel / filter / spatial, logits for the kernel head
-  for (int r = threadIdx.x; r < ns * nout; r += blockDim.x) {
-    const int n = r / nout, j = r - n * nout;
+  // heads (94-96): sigmoid for channel / filter / spatial, logits for the kernel head; one output per thread, its weight row
+  // (att <= 32 floats) loaded once and applied to every sample of the split
+  for (int j = threadIdx.x; j < nout; j += blockDim.x) {
     const float* w;
     float b;
     if (j < c.ci) { w = c.ch_w + j * c.att; b = c.ch_b[j]; }
     else if (j < c.ci + c.co) { w = c.fl_w + (j - c.ci) * c.att; b = c.fl_b[j - c.ci]; }
     else if (j < c.ci + c.co + 9) { w = c.sp_w + (j - c.ci - c.co) * c.att; b = c.sp_b[j - c.ci - c.co]; }
     else { w = c.kn_w + (j - c.ci - c.co - 9) * c.att; b = c.kn_b[j - c.ci - c.co - 9]; }
-    float acc = b;
-    for (int a = 0; a < c.att; ++a) acc += __ldg(w + a) * z_s[n][a];
-    att_s[n][j] = j < c.ci + c.co + 9 ? sigmoidf_(acc) : acc;
+    float wv[32];
+#pragma unroll
+    for (int a = 0; a < 32; ++a) wv[a] = a < c.att ? __ldg(w + a) : 0.f;
+    const bool sig = j < c.ci + c.co + 9;
+    for (int n = 0; n < ns; ++n) {
+      float acc = b;
+#pragma unroll
+      for (int a = 0; a < 32; ++a) if (a < c.att) acc += wv[a] * z_s[n][a];
+      att_s[n][j] = sig ? sigmoidf_(acc) : acc;
+    }
   }
   __syncthreads();
   if (threadIdx.x < ns) {   // softmax over the 8 kernel logits (temperature 1)
