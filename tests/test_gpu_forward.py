@@ -71,6 +71,14 @@ def test_forward_random_shapes_and_scales(G, seed):
     assert info["psnr_vs_oracle"] > 55.0, info
 
 
+def test_unfused_satu_route_matches_too(G, monkeypatch):
+    """SAVSR_SATU_UNFUSED=1 keeps the two-step route (25 materialised per-pixel kernels + savsr_satu_sta) alive as an
+    independent check of the fused kernel_conv + sta kernel: both must agree with the oracle."""
+    monkeypatch.setenv("SAVSR_SATU_UNFUSED", "1")
+    info = G.check_forward(b=2, h=13, w=15, scale=(1.5, 4), sd_seed=1, in_seed=1236, impl="halo", tol=MAX_ABS_TOL, stage_tol=STAGE_REL_TOL)
+    assert info["launches"] > 320          # the extra 25-group 1x1 conv launch + sta
+
+
 def test_fp16_path_meets_the_fp32_criterion_with_stage_errors(G):
     for kw in (dict(b=1, h=16, w=20, scale=(2, 2)), dict(b=2, h=13, w=15, scale=(1.5, 4), sd_seed=1, in_seed=1236),
                dict(b=1, h=31, w=31, scale=(3, 3), sd_seed=2)):
