@@ -91,6 +91,31 @@ def conv(tag, reps):
     print("\n".join(out[-12:]))
 
 
+OTHER_KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread", "launch__grid_size",
+              "launch__block_size", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+              "lts__throughput.avg.pct_of_peak_sustained_elapsed", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+              "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+              "l1tex__t_sector_hit_rate.pct", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum"]
+
+
+def others(tag, reps):
+    """One `ncu --set full` capture each of the largest non-conv kernels, inside a Vid4 x4 forward of 17 windows."""
+    out = [f"# {tag}: `ncu --set full` captures of the non-conv kernels (one launch each, inside a forward of 17 Vid4 windows, x4)", "",
+           "Command: `ncu --set full --clock-control none --import-source on -k regex:<kernel> -c 1 python scripts/quick_perf.py halo 17`", ""]
+    cols = []
+    for rep, desc, note in reps:
+        if os.path.exists(os.path.join(G, rep)):
+            v, u = raw(rep)
+            cols.append((rep, desc, note, v, u))
+    out += ["| metric | " + " | ".join(f"{d}" for _, d, _, _, _ in cols) + " |", "|---|" + "---|" * len(cols)]
+    for k in OTHER_KEYS:
+        out.append(f"| `{k}` | " + " | ".join(f"{c[3].get(k, '-')} {c[4].get(k, '')}".strip() for c in cols) + " |")
+    out.append("")
+    for rep, desc, note, v, u in cols:
+        out.append(f"* {desc} ({rep}): {note}")
+    open(os.path.join(P, f"{tag}_other_kernels_ncu_summary.md"), "w").write("\n".join(out) + "\n")
+
+
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(P, exist_ok=True)
@@ -103,6 +128,14 @@ if __name__ == "__main__":
                ("conv_r01_s1g6.ncu-rep", "6 convs 64->64, B=17, current", 2.0 * 6 * 17 * px * 64 * 576),
                ("conv_r01_s2g6.ncu-rep", "6 convs 128->64, B=17, current", 2.0 * 6 * 17 * px * 64 * 1152),
                ("conv_r01_s3g2.ncu-rep", "2 OSA convs 192->64, B=17, current", 2.0 * 2 * 17 * px * 64 * 1728)])
+    others(tag, [("satu_fused_r01.ncu-rep", "satu_fused_kernel",
+                  "gather x2 + routed experts + 128->64 fusion per 128 HR pixels; algorithmic bytes per launch = 17 x (2 x 3.3 MB LR features "
+                  "+ 53 MB HR feature written); the gathers run out of L1 / L2, the kernel is issue- and latency-bound (2 CTAs per SM overlap phases)"),
+                 ("kconv_sta_r01.ncu-rep", "satu_kconv_sta_kernel",
+                  "25 taps x (M=128, N=64, K=64) on tcgen05, per-pixel kernels consumed from TMEM; bound by the CUDA-core epilogue "
+                  "(5 instructions per kernel element); DRAM traffic = two LR features in, one out"),
+                 ("ca_r01.ncu-rep", "ca_scale_residual_kernel",
+                  "dst = x + t * y: 3 x 56 MB per launch (17 windows), HBM-bound")])
     src = os.path.join(G, f"bench_{tag}.json")
     if os.path.exists(src):
         line = [l for l in open(src) if l.startswith("{")][-1]
