@@ -83,6 +83,8 @@ def test_satu_kernel_conv_and_sta_fused(G):
     G.check_satu_kconv_sta()
     G.check_satu_kconv_sta(B=3, h=32, w=40, seed=3)      # several tiles per sample, even tile count
     G.check_satu_kconv_sta(B=1, h=17, w=9, seed=4)       # odd sizes: padded column / row, single-tile batches
+    G.check_satu_kconv_sta(B=3, h=16, w=24, seed=5)      # 3 tiles per sample: a single-tile batch between samples
+    G.check_satu_kconv_sta(B=2, h=48, w=40, seed=6)      # 15 tiles per sample, several CTAs, odd count
 
 
 def test_satu_gather(G):
