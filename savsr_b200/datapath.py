@@ -139,3 +139,62 @@ def evaluate_clip(net: Callable[[torch.Tensor], torch.Tensor], frames_bgr_u8: to
     images, psnr = postproc.tensor2img_psnr(sr, gt_sel, want_image=want_images)
     ssim = postproc.ssim_y(sr, gt_sel)
     return dict(images=images, psnr_y=psnr, ssim_y=ssim, sr=sr)
+
+
+# ------------------------------------------------------------------------------------------------ clip prefetch
+class ClipPrefetcher:
+    """Uploads the NEXT clip's decoded uint8 frames on a side stream while the current clip is being processed -- the role
+    of the reference's CUDAPrefetcher (lbasicsr/data/prefetch_dataloader.py:84-125) for whole clips.  `clips` yields
+    (name, uint8 [T,H,W,3] BGR host tensor or ndarray); pinned host tensors make the copy truly asynchronous.
+
+        for name, frames in ClipPrefetcher(clips, device):      # frames: uint8 CUDA tensor, ready on the current stream
+            res = evaluate_clip(net, frames, scale)
+    """
+
+    def __init__(self, clips, device):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("savsr_b200.datapath runs on CUDA only; there is no CPU fallback")
+        self._it = iter(clips)
+        self._stream = torch.cuda.Stream(self.device)
+        self._next = None
+        self._preload()
+
+    def _preload(self):
+        try:
+            name, frames = next(self._it)
+        except StopIteration:
+            self._next = None
+            return
+        host = frames if torch.is_tensor(frames) else torch.from_numpy(frames)
+        if host.dtype != torch.uint8 or host.dim() != 4 or host.shape[-1] != 3:
+            raise ValueError(f"clip {name!r}: expected uint8 [T,H,W,3], got {host.dtype} {tuple(host.shape)}")
+        with torch.cuda.stream(self._stream):
+            dev = host.to(self.device, non_blocking=True)
+        self._next = (name, dev, host)           # keep the host tensor alive until the copy has been consumed
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._next is None:
+            raise StopIteration
+        torch.cuda.current_stream(self.device).wait_stream(self._stream)
+        name, dev, _host = self._next
+        dev.record_stream(torch.cuda.current_stream(self.device))
+        self._preload()
+        return name, dev
+
+
+def evaluate_clips(net: Callable[[torch.Tensor], torch.Tensor], clips, scale: Sequence[float], device, batch: int = 17,
+                   num_frames: int = 7, want_images: bool = False) -> Dict[str, Dict[str, float]]:
+    """Per-clip averages like the reference's validation summary (video_base_model.py:132-146): {clip: {"psnr_y", "ssim_y"}}
+    plus the dataset average under the key "average".  Uploads of clip i+1 overlap the processing of clip i."""
+    out: Dict[str, Dict[str, float]] = {}
+    for name, frames in ClipPrefetcher(clips, device):
+        res = evaluate_clip(net, frames, scale, batch=batch, num_frames=num_frames, want_images=want_images)
+        out[name] = dict(psnr_y=float(res["psnr_y"].mean()), ssim_y=float(res["ssim_y"].mean()))
+    if out:
+        out["average"] = dict(psnr_y=sum(v["psnr_y"] for v in out.values()) / len(out),
+                              ssim_y=sum(v["ssim_y"] for v in out.values()) / len(out))
+    return out

@@ -18,6 +18,8 @@ def frame_window_indices(crt_idx: int, n_frames: int, num_frames: int = 7) -> Li
         raise ValueError("num_frames should be an odd number.")
     last = n_frames - 1
     pad = num_frames // 2
+    if n_frames <= pad:     # the reflected index -i (or 2 * last - i) would leave the clip; the reference raises IndexError here
+        raise ValueError(f"a clip of {n_frames} frames is too short for reflection padding of a {num_frames}-frame window")
     out = []
     for i in range(crt_idx - pad, crt_idx + pad + 1):
         if i < 0:

@@ -697,6 +697,28 @@ def check_evaluate_clip(seed=5):
     return dict(sr_max_abs=err, psnr_delta_db=dpsnr, psnr=[round(float(v), 3) for v in res["psnr_y"]])
 
 
+def check_clip_prefetch(seed=8):
+    """ClipPrefetcher + evaluate_clips: same per-clip metrics as evaluating each clip alone; pinned and pageable hosts."""
+    import savsr_b200
+    from oracle.state_dict_fixture import make_state_dict
+    from savsr_b200 import datapath
+    rng = np.random.default_rng(seed)
+    clips = [(f"clip{i}", rng.integers(0, 256, size=(4 + i, 32, 40, 3), dtype=np.uint8)) for i in range(3)]
+    hosts = [(n, torch.from_numpy(f).pin_memory() if i % 2 == 0 else f) for i, (n, f) in enumerate(clips)]
+    net = savsr_b200.SAVSR().to(DEV).eval()
+    net.load_state_dict(make_state_dict(0))
+    net.set_scale((2, 2))
+    with torch.no_grad():
+        got = datapath.evaluate_clips(net, hosts, (2, 2), DEV, batch=2)
+        for name, frames in clips:
+            ref = datapath.evaluate_clip(net, torch.from_numpy(frames).to(DEV), (2, 2), batch=3)
+            assert abs(got[name]["psnr_y"] - float(ref["psnr_y"].mean())) < 1e-9, name
+            assert abs(got[name]["ssim_y"] - float(ref["ssim_y"].mean())) < 1e-12, name
+    assert set(got) == {"clip0", "clip1", "clip2", "average"}
+    assert abs(got["average"]["psnr_y"] - sum(got[f"clip{i}"]["psnr_y"] for i in range(3)) / 3) < 1e-12
+    return got
+
+
 # ------------------------------------------------------------------------------------------------ whole forward
 TAPS = ("f2p_last", "p2f_last", "align", "rg0", "rg3", "trunk", "satu_sta", "satu_out")
 

@@ -108,6 +108,10 @@ def test_device_clip_evaluation_loop(G):
     G.check_evaluate_clip()
 
 
+def test_clip_prefetcher_and_dataset_summary(G):
+    G.check_clip_prefetch()
+
+
 def test_kernels_in_fp16_operand_format(G):
     """The same entry points with the context switched to the fp16 storage / operand format."""
     G.set_precision("fp16")

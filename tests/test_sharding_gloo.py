@@ -22,6 +22,9 @@ def test_reflection_window_indices():
     assert sharding.frame_window_indices(33, 34) == [30, 31, 32, 33, 32, 31, 30]
     assert sharding.frame_window_indices(10, 34) == [7, 8, 9, 10, 11, 12, 13]
     assert sharding.frame_window_indices(0, 5, 5) == [2, 1, 0, 1, 2]
+    assert sharding.frame_window_indices(1, 4) == [2, 1, 0, 1, 2, 3, 2]               # shortest clip a 7-frame window supports
+    with pytest.raises(ValueError, match="too short"):
+        sharding.frame_window_indices(0, 3)                                         # reflection would index frame 3 of 3
 
 
 def test_shard_frames_partition():
