@@ -53,39 +53,65 @@ def flops_per_frame(h, w, H, W):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock / power / throttle reasons sampled while the timed region runs: NVML every 20 ms when `pynvml` imports,
+    else one nvidia-smi call per 200 ms."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()   # rows: (sm MHz, max MHz, watts, {reasons})
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; CUDA_VISIBLE_DEVICES may remap torch's index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n, h = self.nvml, self.handle
+        sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        watts = n.nvmlDeviceGetPowerUsage(h) / 1e3
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        self.rows.append((float(sm), float(mx), watts, {name for name, bit in self.BITS if mask & bit}))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+            r = [c.strip() for c in out.split(",")]
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            self.rows.append((float(r[0]), float(r[1]), float(r[2]), {nm for nm, v in zip(names, r[3:7]) if v.lower().startswith("active")}))
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.02 if self.nvml is not None else 0.2)
 
     def stop(self) -> dict:
         self._stop_evt.set()
         self.join(timeout=6)
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+        sm = [r[0] for r in self.rows]
+        reasons = set().union(*[r[3] for r in self.rows]) if self.rows else set()
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(r[1] for r in self.rows) if self.rows else None,
+                    reasons=sorted(reasons), samples=len(sm), power_w_avg=round(statistics.median(r[2] for r in self.rows), 1) if self.rows else None,
+                    source="nvml" if self.nvml is not None else "nvidia-smi")
 
 
 def measured_peaks():
