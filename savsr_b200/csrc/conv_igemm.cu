@@ -253,6 +253,7 @@ struct EpiQuad {
   int res1_slot, res2_slot, dst_slot;
   bool has_mask;
   float* pool;
+  float psum[8];      // pooled sums of the current run of tiles (same conv, same sample), reduced across lanes at its end
 };
 
 __device__ __forceinline__ void epiq_prefetch(const ConvParams& p, const savsr_conv_group& g, int gi, int n, int tile, int quad,
@@ -305,9 +306,10 @@ __device__ __forceinline__ void epiq_prefetch(const ConvParams& p, const savsr_c
 // mask / residuals, then calls `next()` -- the caller starts the NEXT tile's epiq_prefetch into `c` there, so those loads
 // have the stores, the pooling and the next accumulator wait to land (when the epilogue is the critical path, as in
 // single-source convs, nothing else would hide their latency) -- and finally packs, stores and pools this tile.
+// `last_of_run`: the next tile this warp will process belongs to another (conv, sample) or there is none.
 template <class Release, class Next>
 __device__ __forceinline__ void epiq_finish(const ConvParams& p, int n, int tile, int quad, int lane, int half, uint32_t taddr,
-                                            EpiQuad& c, Release release, Next next) {
+                                            EpiQuad& c, bool last_of_run, Release release, Next next) {
   uint32_t ra[16], rb[16];
   tmem_ld_16x256b_x4(taddr, ra);
   tmem_ld_16x256b_x4(taddr + (16u << 16), rb);
@@ -370,29 +372,36 @@ __device__ __forceinline__ void epiq_finish(const ConvParams& p, int n, int tile
     }
   }
   if (pool != nullptr) {
-    // Channel sums of the (pre-rounding) outputs over the valid pixels of this quadrant: 4 rows in the thread, then a
-    // shuffle reduce-scatter over the 8 thread groups (7 shuffles) leaves channel ch0 + 4 b4 + 2 b3 + b2 (b = lane
-    // bits) in each lane.  Deterministic; one partial per (tile, quadrant) as before.
-    float s[8];
+    // Channel sums of the (pre-rounding) outputs over the valid pixels: accumulated per thread over the warp's run of
+    // tiles of one (conv, sample) -- the shuffle chain at the end of every tile used to delay the next tile's start --
+    // and reduced across the 8 thread groups (7 shuffles, reduce-scatter: channel ch0 + 4 b4 + 2 b3 + b2 per lane) only
+    // when the run ends.  The run's total lands in the partial-sum slot of its last tile, the other tiles' slots get zero:
+    // consumers still add all tiles * 4 slots per sample.  Deterministic (the tile -> CTA partition is fixed per launch).
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      s[i] = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) s[i] += ((valid >> j) & 1u) ? v[j][i] : 0.f;
-    }
-#pragma unroll
-    for (int off = 16, cnt = 4; off >= 4; off >>= 1, cnt >>= 1) {
-      const bool upper = (lane & off) != 0;
-#pragma unroll
-      for (int i = 0; i < cnt; ++i) {
-        const float send = upper ? s[i] : s[i + cnt];
-        const float keep = upper ? s[i + cnt] : s[i];
-        s[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-      }
+      for (int j = 0; j < 4; ++j) c.psum[i] += ((valid >> j) & 1u) ? v[j][i] : 0.f;
     }
     const int npart = p.tiles_x * p.tiles_y * 4;
     const int ch = ch0 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-    pool[(static_cast<long>(n) * npart + tile * 4 + quad) * kC + ch] = s[0];
+    float total = 0.f;
+    if (last_of_run) {   // warp-uniform
+      float s[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] = c.psum[i]; c.psum[i] = 0.f; }
+#pragma unroll
+      for (int off = 16, cnt = 4; off >= 4; off >>= 1, cnt >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < cnt; ++i) {
+          const float send = upper ? s[i] : s[i + cnt];
+          const float keep = upper ? s[i + cnt] : s[i];
+          s[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      total = s[0];
+    }
+    pool[(static_cast<long>(n) * npart + tile * 4 + quad) * kC + ch] = total;
   }
 }
 
@@ -653,6 +662,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
       EpiQuad eq;
       ec.bias_group = -1;
       eq.bias_group = -1;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) eq.psum[i] = 0.f;
       int it = 0;
       int tile = item_begin % tiles;
       int gn = item_begin / tiles;
@@ -673,7 +684,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN + half * 32);
         if constexpr (BN == 64) {
-          epiq_finish(p, n, tile, quad, lane, half, taddr, eq, [&] { if (lane == 0) mbar_arrive(t_empty + acc); }, [&] {
+          epiq_finish(p, n, tile, quad, lane, half, taddr, eq, item + 1 >= item_end || tile + 1 == tiles,
+                      [&] { if (lane == 0) mbar_arrive(t_empty + acc); }, [&] {
             if (item + 1 < item_end) {
               const int nt = tile + 1 == tiles ? 0 : tile + 1, ngn = tile + 1 == tiles ? gn + 1 : gn;
               epiq_prefetch(p, p.g[ngn / p.batch], ngn / p.batch, ngn % p.batch, nt, quad, lane, half, eq);
@@ -931,6 +943,8 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
     const int half = (warp - 2) >> 2;
     EpiQuad eq;
     eq.bias_group = -1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) eq.psum[i] = 0.f;
     long long dbg_tf = 0, dbg_t0 = clock64();
     if (item < item_end) epiq_prefetch(p, p.g[gn / p.batch], gn / p.batch, gn % p.batch, tile, quad, lane, half, eq);
     while (item < item_end) {
@@ -945,7 +959,8 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
         use_bits ^= 1u << acc;
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN + half * 32);
-        epiq_finish(p, n, tile + j, quad, lane, half, taddr, eq, [&] { if (lane == 0) mbar_arrive(t_empty + acc); }, [&] {
+        epiq_finish(p, n, tile + j, quad, lane, half, taddr, eq, item + j + 1 >= item_end || tile + j + 1 == tiles,
+                    [&] { if (lane == 0) mbar_arrive(t_empty + acc); }, [&] {
           if (item + j + 1 < item_end) {   // a batch never straddles a (conv, sample) boundary
             const int nt = tile + j + 1 == tiles ? 0 : tile + j + 1, ngn = tile + j + 1 == tiles ? gn + 1 : gn;
             epiq_prefetch(p, p.g[ngn / p.batch], ngn / p.batch, ngn % p.batch, nt, quad, lane, half, eq);
