@@ -12,7 +12,9 @@
  *   - plain pointers and sizes only; no torch types.  All pointers are DEVICE pointers unless noted.
  *   - the caller owns and allocates every buffer (inputs, outputs, activation arenas, scratch).
  *     The library never allocates device memory, never synchronises, and launches only on the
- *     stream it is given (so every call is CUDA-graph capturable).
+ *     stream it is given (so every call is CUDA-graph capturable).  It holds no process-wide mutable
+ *     state: everything lives in the savsr_ctx (one per device); launchers switch to the context's
+ *     device for the duration of the call and restore the caller's current device.
  *   - every function returns 0 on success, non-zero on error; savsr_last_error() returns a
  *     thread-local message.  A device without sm_100 tensor-core support is an error, never a
  *     fallback.
@@ -29,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SAVSR_ABI_VERSION 2
+#define SAVSR_ABI_VERSION 3
 #define SAVSR_MAX_SRC 5      /* most 64-channel sources one conv concatenates (OSA 320->64)      */
 #define SAVSR_MAX_GROUPS 25  /* most independent convolutions batched into one launch            */
 #define SAVSR_TILE_W 8       /* output tile = 8 x 16 pixels = 128 GEMM rows (one UMMA M)         */
@@ -100,6 +102,13 @@ typedef struct savsr_rgb_skip {
   int32_t h, w;        /* LR size (unpadded)                                                      */
 } savsr_rgb_skip;
 
+/* Tuning / bring-up knobs of a context (savsr_ctx_set_option).  The library reads no environment variables. */
+enum savsr_option {
+  SAVSR_OPT_BIGK_ALL = 0,     /* 1 (default): every 3x3 HALO N=64 conv runs on the batched dual-issuer kernel; 0: only K > 18 blocks */
+  SAVSR_OPT_BIGK_ISSUERS = 1, /* MMA-issuing warps of that kernel: 2 (default) or 1                                                  */
+  SAVSR_OPT_COUNT = 2
+};
+
 /* ---- library / context ------------------------------------------------------------------- */
 int savsr_abi_version(void);
 const char* savsr_last_error(void);
@@ -110,6 +119,9 @@ int savsr_ctx_sm_count(const savsr_ctx* ctx);
 /* Select the 16-bit format used by every later call on this context (default SAVSR_FMT_BF16). */
 int savsr_ctx_set_format(savsr_ctx* ctx, int format);
 int savsr_ctx_get_format(const savsr_ctx* ctx);
+/* option: enum savsr_option.  Returns non-zero for an unknown option or an out-of-range value. */
+int savsr_ctx_set_option(savsr_ctx* ctx, int option, int value);
+int savsr_ctx_get_option(const savsr_ctx* ctx, int option);
 
 /* ---- activation arenas --------------------------------------------------------------------- */
 /* Bytes the caller must allocate (256-byte aligned) for an arena of that shape. */
@@ -146,24 +158,9 @@ int savsr_conv(savsr_ctx* ctx, savsr_arena* arena, const savsr_conv_group* group
                savsr_stream st);
 
 /*
- * First-layer convs on the fp32 NCHW input window (savsr_arch.py:456-457 conv_sup / conv_c with the
- * frame gather of 447-454 and the reflect pad of 670-690 fused in):
- * dst = LeakyReLU_0.2(conv3x3(cat(frames[fidx[0..nf)]) ) + bias), written to arena slot dst_slot.
- */
-typedef struct savsr_front_group {
-  int32_t frame[2];
-  int32_t nframes;      /* 1 (conv_c) or 2 (conv_sup) */
-  int32_t dst_slot;
-  const float* weight;  /* fp32 OIHW [64][3*nframes][3][3] */
-  const float* bias;    /* [64] */
-} savsr_front_group;
-int savsr_front_conv(savsr_ctx* ctx, savsr_arena* arena, const float* x, int t, int h, int w,
-                     const savsr_front_group* groups, int ngroups, savsr_stream st);
-
-/*
- * Tensor-core route for the same first layer: pack the fp32 window into ONE arena slot (channel 3f+c = frame f,
- * colour c; remaining channels zero; reflect pad of savsr_arch.py:670-690 fused), after which conv_c / conv_sup are
- * ordinary savsr_conv launches with zero-expanded [64][64][3][3] weights.
+ * First layer (savsr_arch.py:456-457 conv_sup / conv_c with the frame gather of 447-454): pack the fp32 window into ONE
+ * arena slot (channel 3f+c = frame f, colour c; remaining channels zero; reflect pad of savsr_arch.py:670-690 fused),
+ * after which conv_c / conv_sup are ordinary savsr_conv launches with zero-expanded [64][64][3][3] weights.
  */
 int savsr_pack_frames(savsr_ctx* ctx, savsr_arena* arena, const float* x, int t, int h, int w, int dst_slot,
                       savsr_stream st);
@@ -240,31 +237,11 @@ int savsr_satu_index(savsr_ctx* ctx, const savsr_satu_weights* wts, int h, int w
                      int32_t* corner_x, float* table, savsr_stream st);
 
 /*
- * Spatio-temporal filtering (savsr_arch.py:297-313): sta[c] = sum_{u,v} xpad[y+u, x+v, c] * K[tap=u*5+v][c]
- * with K the LeakyReLU_0.1'd kernel_conv output held tap-major in 25 arena slots kslot0..kslot0+24,
- * replicate padding on the unpadded h x w region.  x_slot -> dst_slot.
- */
-int savsr_satu_sta(savsr_ctx* ctx, savsr_arena* arena, int x_slot, int kslot0, int dst_slot, int h,
-                   int w, savsr_stream st);
-
-/*
- * Fused HR gather (savsr_arch.py:364-373): for every HR pixel, bilinear-gather x and sta at the base
- * coordinate + learned offset (zeros padding, align_corners=True), apply the routed compress/expand
- * experts (matrix-free two-stage form) and write  hr slot `sta_dst` = sampled sta,  `fea_dst` = fea
- * (the two operands of the 128->64 fusion conv).  lr: LR arena, hr: HR arena (H x W).
- */
-int savsr_satu_gather(savsr_ctx* ctx, savsr_arena* lr, int x_slot, int sta_slot, int h, int w,
-                      savsr_arena* hr, int sta_dst, int fea_dst, const float* table,
-                      const float* base_y, const float* base_x, const savsr_satu_weights* wts,
-                      savsr_stream st);
-
-/*
  * kernel_conv (1x1, 64 -> 64*25, LeakyReLU 0.1) and sta_conv (per-pixel 5x5 dynamic filtering, replicate padding on the
  * h x w region) of STAUpsample in ONE kernel (savsr_arch.py:297-313, 326): the 25 per-pixel kernels are produced tap by
  * tap on tcgen05 and consumed from TMEM, never written to memory.  a_slot: input of kernel_conv; x_slot: the feature
  * that is filtered; dst_slot: result.  weights: savsr_pack_conv_weight of the TAP-MAJOR filter [25*64][64][1][1]
  * (row t*64 + c = reference output channel c*25 + t), n_tile 64, SAVSR_ROWS_QUAD; bias fp32 [25][64] in the same order.
- * Same result as savsr_conv (25 groups, ksize 1) + savsr_satu_sta except that the kernels are not rounded to 16 bit.
  */
 int savsr_satu_kconv_sta(savsr_ctx* ctx, savsr_arena* arena, int a_slot, int x_slot, int dst_slot, int h, int w,
                          const void* weights, const float* bias, float slope, savsr_stream st);

@@ -11,6 +11,7 @@ import ctypes as C
 import os
 from typing import Optional
 
+ABI_VERSION = 3
 MAX_SRC = 5
 MAX_GROUPS = 25
 TILE_W, TILE_H = 8, 16
@@ -21,6 +22,7 @@ IMPL_TAP, IMPL_HALO, IMPL_CHECK = 0, 1, 2
 IMPL_NAMES = {"tap": IMPL_TAP, "halo": IMPL_HALO, "check": IMPL_CHECK}
 FMT_BF16, FMT_FP16 = 0, 1
 FMT_NAMES = {"bf16": FMT_BF16, "fp16": FMT_FP16}
+OPT_BIGK_ALL, OPT_BIGK_ISSUERS = 0, 1   # enum savsr_option
 ROWS_LINEAR, ROWS_QUAD = 0, 1     # enum savsr_row_order: QUAD for savsr_conv n_tile 64, LINEAR for savsr_satu_fused
 
 # SAVSR_LIB_PATH: alternative build of the same ABI (A/B timing of kernel variants); default = the in-tree library
@@ -54,11 +56,6 @@ class RgbSkip(C.Structure):
     _fields_ = [("x", C.c_void_p), ("t", C.c_int32), ("centre", C.c_int32), ("h", C.c_int32), ("w", C.c_int32)]
 
 
-class FrontGroup(C.Structure):
-    _fields_ = [("frame", C.c_int32 * 2), ("nframes", C.c_int32), ("dst_slot", C.c_int32),
-                ("weight", C.c_void_p), ("bias", C.c_void_p)]
-
-
 class OsaParams(C.Structure):
     _fields_ = [
         ("ci", C.c_int32), ("co", C.c_int32), ("att", C.c_int32),
@@ -89,6 +86,8 @@ SIGNATURES = {
     "savsr_ctx_sm_count": (_I, [_VP]),
     "savsr_ctx_set_format": (_I, [_VP, _I]),
     "savsr_ctx_get_format": (_I, [_VP]),
+    "savsr_ctx_set_option": (_I, [_VP, _I, _I]),
+    "savsr_ctx_get_option": (_I, [_VP, _I]),
     "savsr_arena_bytes": (_SZ, [_I, _I, _I, _I]),
     "savsr_arena_create": (_I, [_VP, _VP, _I, _I, _I, _I, C.POINTER(_VP)]),
     "savsr_arena_destroy": (None, [_VP]),
@@ -98,14 +97,11 @@ SIGNATURES = {
     "savsr_packed_weight_bytes": (_SZ, [_I, _I, _I]),
     "savsr_pack_conv_weight": (_I, [_VP, _I, _I, _I, _I, _I, _I, _I, _VP, _VP]),
     "savsr_conv": (_I, [_VP, _VP, C.POINTER(ConvGroup), _I, _I, _I, _I, C.POINTER(RgbSkip), _I, _VP]),
-    "savsr_front_conv": (_I, [_VP, _VP, _VP, _I, _I, _I, C.POINTER(FrontGroup), _I, _VP]),
     "savsr_pack_frames": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "savsr_osa_prologue": (_I, [_VP, C.POINTER(OsaParams), _I, _I, _I, _I, _F, _F, _VP]),
     "savsr_ca_scale_residual": (_I, [_VP, _VP, _I, _I, _I, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "savsr_osadapt_mask": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "savsr_satu_index": (_I, [_VP, C.POINTER(SatuWeights), _I, _I, _I, _I, _F, _F] + [_VP] * 9 + [_VP]),
-    "savsr_satu_sta": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP]),
-    "savsr_satu_gather": (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _I, _I, _VP, _VP, _VP, C.POINTER(SatuWeights), _VP]),
     "savsr_satu_kconv_sta": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP, _VP, _F, _VP]),
     "savsr_satu_fused": (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "savsr_img_metrics": (_I, [_VP, _VP, _VP, _I, _I, _I, _VP, _VP, _VP]),
@@ -134,8 +130,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.savsr_abi_version() != 2:
-        raise SavsrError(f"ABI version mismatch: library {lib.savsr_abi_version()}, binding 2")
+    if lib.savsr_abi_version() != ABI_VERSION:
+        raise SavsrError(f"ABI version mismatch: library {lib.savsr_abi_version()}, binding {ABI_VERSION}")
     _lib = lib
     return lib
 
@@ -156,6 +152,9 @@ class Context:
         self.handle = h
         self.device = int(device)
         self.sm_count = self.lib.savsr_ctx_sm_count(h)
+
+    def set_option(self, option: int, value: int) -> None:
+        check(self.lib.savsr_ctx_set_option(self.handle, int(option), int(value)))
 
     def set_format(self, fmt: int) -> None:
         """16-bit storage / operand format (FMT_BF16 or FMT_FP16) used by every later call on this context."""

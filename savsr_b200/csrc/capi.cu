@@ -60,7 +60,7 @@ extern "C" int savsr_ctx_create(int device, savsr_ctx** out) {
   SAVSR_CUDA(cudaGetDeviceProperties(&prop, device));
   SAVSR_REQUIRE(prop.major == 10, "savsr_ctx_create: device %d is sm_%d%d; this library contains sm_100a code only "
                 "(tcgen05/TMEM/TMA) and has no fallback", device, prop.major, prop.minor);
-  SAVSR_CUDA(cudaSetDevice(device));
+  DeviceGuard guard(device);   // the caller's current device is restored on return
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   SAVSR_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -72,6 +72,8 @@ extern "C" int savsr_ctx_create(int device, savsr_ctx** out) {
   c->cc_major = prop.major;
   c->cc_minor = prop.minor;
   c->encode_tiled = fn;
+  c->opt[SAVSR_OPT_BIGK_ALL] = 1;
+  c->opt[SAVSR_OPT_BIGK_ISSUERS] = 2;
   *out = c;
   return 0;
 }
@@ -83,6 +85,18 @@ extern "C" int savsr_ctx_set_format(savsr_ctx* ctx, int format) {
   return 0;
 }
 extern "C" int savsr_ctx_get_format(const savsr_ctx* ctx) { return ctx ? ctx->fmt : -1; }
+
+extern "C" int savsr_ctx_set_option(savsr_ctx* ctx, int option, int value) {
+  SAVSR_REQUIRE(ctx, "savsr_ctx_set_option: null context");
+  SAVSR_REQUIRE(option >= 0 && option < SAVSR_OPT_COUNT, "savsr_ctx_set_option: unknown option %d", option);
+  if (option == SAVSR_OPT_BIGK_ALL) SAVSR_REQUIRE(value == 0 || value == 1, "savsr_ctx_set_option: BIGK_ALL must be 0 or 1, got %d", value);
+  if (option == SAVSR_OPT_BIGK_ISSUERS) SAVSR_REQUIRE(value == 1 || value == 2, "savsr_ctx_set_option: BIGK_ISSUERS must be 1 or 2, got %d", value);
+  ctx->opt[option] = value;
+  return 0;
+}
+extern "C" int savsr_ctx_get_option(const savsr_ctx* ctx, int option) {
+  return (ctx && option >= 0 && option < SAVSR_OPT_COUNT) ? ctx->opt[option] : -1;
+}
 
 extern "C" void savsr_ctx_destroy(savsr_ctx* ctx) { free(ctx); }
 extern "C" int savsr_ctx_sm_count(const savsr_ctx* ctx) { return ctx ? ctx->sm_count : 0; }

@@ -45,7 +45,33 @@ struct savsr_ctx {
   int cc_major, cc_minor;
   void* encode_tiled;  // PFN_cuTensorMapEncodeTiled
   int fmt;             // 16-bit storage / operand format of arenas and packed weights: SAVSR_FMT_BF16 or SAVSR_FMT_FP16
+  int opt[SAVSR_OPT_COUNT];   // enum savsr_option values (savsr_ctx_set_option)
+  uint32_t attr_mask;  // bit k: the dynamic shared-memory attribute of kernel k is set on THIS context's device
+  long long* conv_dbg; // SAVSR_DEBUG_COUNTERS builds only: device buffer [grid][8] for cycle counters, else unused
 };
+
+namespace savsr {
+// Kernels that need more than 48 KB of dynamic shared memory: the attribute belongs to the device (primary context), so
+// it is tracked per savsr_ctx, not per process.
+enum AttrBit { kAttrIgemm = 0 /* + template index, 6 variants */, kAttrBigk = 8, kAttrKsta = 9, kAttrSatuHr = 10, kAttrOsaLinear = 11,
+               kAttrFused = 12, kAttrBigk128 = 13 };
+template <class F>
+inline int ensure_smem_attr(savsr_ctx* ctx, int bit, F func, size_t bytes) {
+  if (ctx->attr_mask & (1u << bit)) return 0;
+  SAVSR_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+  ctx->attr_mask |= 1u << bit;
+  return 0;
+}
+// Launch on the context's device whatever the caller's current device is; restores it on scope exit.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+}  // namespace savsr
 
 struct savsr_arena {
   savsr_ctx* ctx;

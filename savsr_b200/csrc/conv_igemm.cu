@@ -31,6 +31,16 @@
 
 namespace savsr {
 
+// Cycle counters around the barrier waits are a bring-up aid: compiled in only with -DSAVSR_DEBUG_COUNTERS (the release
+// kernels execute no clock reads on the issue path).
+#ifdef SAVSR_DEBUG_COUNTERS
+#define DBG_CLOCK() clock64()
+#define DBG_ONLY(...) __VA_ARGS__
+#else
+#define DBG_CLOCK() 0ll
+#define DBG_ONLY(...)
+#endif
+
 constexpr int kMaxAStages = 4;
 constexpr int kHaloPitch = 10;                        // halo row pitch in pixels (tile width 8 + 2)
 constexpr int kHaloStageBytes = 23552;               // 10 x 18 x 128 = 23040, rounded up to 1 KB
@@ -494,9 +504,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
         for (int s = 0; s < nsrc; ++s) {
           const int img = g.src_slot[s] * p.batch + n;
           if constexpr (HALO) {
-            const long long c0 = clock64();
+            const long long c0 = DBG_CLOCK();
             mbar_wait(a_empty + sa, pa ^ 1);
-            dbg_ae += clock64() - c0;
+            dbg_ae += DBG_CLOCK() - c0;
             mbar_expect_tx(a_full + sa, kHaloPitch * (kTileH + 2) * 128u);
             tma_load_4d(smem_a + sa * kAStage, &p.tm_halo, a_full + sa, 0, x0 - 1, y0 - 1, img);
             if (++sa == kAStages) { sa = 0; pa ^= 1; }
@@ -522,7 +532,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
         }
         if (++tile == tiles) { tile = 0; ++gn; }
       }
-      if (p.dbg != nullptr) p.dbg[blockIdx.x * 8 + 6] = dbg_ae;
+      DBG_ONLY(if (p.dbg != nullptr) p.dbg[blockIdx.x * 8 + 6] = dbg_ae;)
+      (void)dbg_ae;
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
@@ -545,7 +556,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
     int gi = (item_begin / tiles) / p.batch;
     const uint32_t ps_mask = p.per_sample_mask;
     const int batch = p.batch;
-    long long dbg_te = 0, dbg_af = 0, dbg_t0 = clock64();
+    long long dbg_te = 0, dbg_af = 0, dbg_t0 = DBG_CLOCK();
     for (int item = item_begin; item < item_end; ++item, ++it) {
       const int key = gi * batch + (((ps_mask >> gi) & 1u) ? n : 0);
       bool fresh = false;
@@ -557,18 +568,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
         fresh = true;
       }
       const int acc = it & 1;
-      long long c0 = clock64();
+      long long c0 = DBG_CLOCK();
       mbar_wait(t_empty + acc, ((it >> 1) & 1) ^ 1);
-      dbg_te += clock64() - c0;
+      dbg_te += DBG_CLOCK() - c0;
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
       if (HALO && all_resident && !fresh) {
         // ---- fast path: weights resident and already landed; one wait + one elected region per source
         uint32_t b_lo = b_lo0;
         for (int s = 0; s < nsrc; ++s) {
-          c0 = clock64();
+          c0 = DBG_CLOCK();
           mbar_wait(a_full + sa, pa);
-          dbg_af += clock64() - c0;
+          dbg_af += DBG_CLOCK() - c0;
           tc_fence_after();
           const uint32_t al0 = a_lo0 + sa * (kAStage >> 4);
           if (elect_one()) {
@@ -646,12 +657,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
         if (++n == batch) { n = 0; ++gi; }
       }
     }
-    if (p.dbg != nullptr && lane == 0) {
-      p.dbg[blockIdx.x * 8 + 0] = clock64() - dbg_t0;
+    DBG_ONLY(if (p.dbg != nullptr && lane == 0) {
+      p.dbg[blockIdx.x * 8 + 0] = DBG_CLOCK() - dbg_t0;
       p.dbg[blockIdx.x * 8 + 1] = dbg_te;
       p.dbg[blockIdx.x * 8 + 2] = dbg_af;
       p.dbg[blockIdx.x * 8 + 3] = item_end - item_begin;
-    }
+    })
+    (void)dbg_te; (void)dbg_af; (void)dbg_t0;
   } else {
     // ================================ epilogue warps ================================
     const int quad = warp & 3;          // TMEM lane quadrant this warp may access (warp id % 4)
@@ -667,7 +679,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
       int it = 0;
       int tile = item_begin % tiles;
       int gn = item_begin / tiles;
-      long long dbg_tf = 0, dbg_t0 = clock64();
+      long long dbg_tf = 0, dbg_t0 = DBG_CLOCK();
       if constexpr (BN == 64) {
         if (item_begin < item_end) epiq_prefetch(p, p.g[gn / p.batch], gn / p.batch, gn % p.batch, tile, quad, lane, half, eq);
       }
@@ -678,9 +690,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
         const int acc = it & 1;
         // loads that do not depend on the accumulator fly while the tile's MMAs run
         if constexpr (BN != 64) epi_prefetch<NC>(p, g, gi, n, tile, quad, lane, 0, ec);
-        const long long c0 = clock64();
+        const long long c0 = DBG_CLOCK();
         mbar_wait(t_full + acc, (it >> 1) & 1);
-        dbg_tf += clock64() - c0;
+        dbg_tf += DBG_CLOCK() - c0;
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN + half * 32);
         if constexpr (BN == 64) {
@@ -705,10 +717,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
         }
         if (++tile == tiles) { tile = 0; ++gn; }
       }
-      if (p.dbg != nullptr && warp == 2 && lane == 0) {
-        p.dbg[blockIdx.x * 8 + 4] = clock64() - dbg_t0;
+      DBG_ONLY(if (p.dbg != nullptr && warp == 2 && lane == 0) {
+        p.dbg[blockIdx.x * 8 + 4] = DBG_CLOCK() - dbg_t0;
         p.dbg[blockIdx.x * 8 + 5] = dbg_tf;
-      }
+      })
+      (void)dbg_tf; (void)dbg_t0;
     }
   }
 
@@ -836,7 +849,7 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
     const uint32_t b_lo0 = (smem_u32(smem_b) >> 4) & 0x3fffu;
     int sa = 0, pa = 0;
     uint32_t u = 0;
-    long long dbg_te = 0, dbg_af = 0, dbg_sf = 0, dbg_t0 = clock64(), c0;
+    long long dbg_te = 0, dbg_af = 0, dbg_sf = 0, dbg_t0 = DBG_CLOCK(), c0;
     while (item < item_end) {
       const int cnt = min(kBatchTiles, min(item_end - item, tiles - tile));
       const int bb = bcount & 1;
@@ -852,19 +865,19 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
         __syncwarp();
       }
       cur_key = key;
-      c0 = clock64();
+      c0 = DBG_CLOCK();
 #pragma unroll
       for (int j = 0; j < kBatchTiles; ++j) {
         if (j < cnt && (j & own_mask) == my) mbar_wait(t_empty + bb * kBatchTiles + j, ((use_bits >> (bb * kBatchTiles + j)) & 1u) ^ 1u);
       }
-      dbg_te += clock64() - c0;
+      dbg_te += DBG_CLOCK() - c0;
       tc_fence_after();
       for (int s = 0; s < nsrc; ++s) {
         const int set = pinned ? s : static_cast<int>(u & 1);
         if (load) {
-          c0 = clock64();
+          c0 = DBG_CLOCK();
           mbar_wait(set_full + set, set_loads[set] & 1u);
-          dbg_sf += clock64() - c0;
+          dbg_sf += DBG_CLOCK() - c0;
           ++set_loads[set];
           tc_fence_after();
           ++u;
@@ -876,9 +889,9 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
             // BOTH issuers observe every stage fill in order and the stage is refilled only after both have passed it
             // (a_empty counts 2): mbarrier parity cannot distinguish phases two apart, so neither issuer may run
             // more than one fill ahead of, or behind, the barrier it waits on.
-            c0 = clock64();
+            c0 = DBG_CLOCK();
             mbar_wait(a_full + sa, pa);
-            dbg_af += clock64() - c0;
+            dbg_af += DBG_CLOCK() - c0;
             if ((j & own_mask) != my) {
               if (elect_one()) mbar_arrive(a_empty + sa);
               __syncwarp();
@@ -930,13 +943,14 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
       item += cnt; tile += cnt;
       if (tile == tiles) { tile = 0; ++gn; }
     }
-    if (p.dbg != nullptr && lane == 0 && my == 0) {
-      p.dbg[blockIdx.x * 8 + 0] = clock64() - dbg_t0;
+    DBG_ONLY(if (p.dbg != nullptr && lane == 0 && my == 0) {
+      p.dbg[blockIdx.x * 8 + 0] = DBG_CLOCK() - dbg_t0;
       p.dbg[blockIdx.x * 8 + 1] = dbg_te;
       p.dbg[blockIdx.x * 8 + 2] = dbg_af;
       p.dbg[blockIdx.x * 8 + 3] = item_end - item_begin;
       p.dbg[blockIdx.x * 8 + 7] = dbg_sf;
-    }
+    })
+    (void)dbg_te; (void)dbg_af; (void)dbg_sf; (void)dbg_t0;
   } else if (warp < 10) {   // (warp 10 is the optional second issuer; idle when p.issuers == 1)
     // ================================ epilogue warps ================================
     const int quad = warp & 3;
@@ -945,7 +959,7 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
     eq.bias_group = -1;
 #pragma unroll
     for (int i = 0; i < 8; ++i) eq.psum[i] = 0.f;
-    long long dbg_tf = 0, dbg_t0 = clock64();
+    long long dbg_tf = 0, dbg_t0 = DBG_CLOCK();
     if (item < item_end) epiq_prefetch(p, p.g[gn / p.batch], gn / p.batch, gn % p.batch, tile, quad, lane, half, eq);
     while (item < item_end) {
       const int cnt = min(kBatchTiles, min(item_end - item, tiles - tile));
@@ -953,9 +967,9 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
       const int n = gn % p.batch;
       for (int j = 0; j < cnt; ++j) {
         const int acc = bb * kBatchTiles + j;
-        const long long c0 = clock64();
+        const long long c0 = DBG_CLOCK();
         mbar_wait(t_full + acc, (use_bits >> acc) & 1u);
-        dbg_tf += clock64() - c0;
+        dbg_tf += DBG_CLOCK() - c0;
         use_bits ^= 1u << acc;
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN + half * 32);
@@ -971,10 +985,11 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
       item += cnt; tile += cnt;
       if (tile == tiles) { tile = 0; ++gn; }
     }
-    if (p.dbg != nullptr && warp == 2 && lane == 0) {
-      p.dbg[blockIdx.x * 8 + 4] = clock64() - dbg_t0;
+    DBG_ONLY(if (p.dbg != nullptr && warp == 2 && lane == 0) {
+      p.dbg[blockIdx.x * 8 + 4] = DBG_CLOCK() - dbg_t0;
       p.dbg[blockIdx.x * 8 + 5] = dbg_tf;
-    }
+    })
+    (void)dbg_tf; (void)dbg_t0;
   }
 
   tc_fence_before();
@@ -1081,11 +1096,8 @@ __global__ void arena_export_kernel(const uint16_t* __restrict__ src, float* __r
 template <int BN, int KS, bool HALO>
 static int launch_igemm(savsr_ctx* ctx, ConvParams& p, int total, cudaStream_t st) {
   const size_t smem = 1024 + kARegionBytes + kBBlocks * BN * 128 + 512;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SAVSR_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, KS, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_done = true;
-  }
+  constexpr int variant = (BN == 64 ? 0 : 3) + (KS == 1 ? 0 : (HALO ? 1 : 2));
+  if (int rc = ensure_smem_attr(ctx, kAttrIgemm + variant, conv_igemm_kernel<BN, KS, HALO>, smem)) return rc;
   // persistent CTAs over contiguous chunks of work items (weights stay resident within a chunk)
   p.chunk = (total + ctx->sm_count - 1) / ctx->sm_count;
   const int grid = (total + p.chunk - 1) / p.chunk;
@@ -1106,14 +1118,9 @@ static int launch_conv(savsr_ctx* ctx, ConvParams& p, int impl, cudaStream_t st)
   if (p.ntaps == 1) return launch_igemm<BN, 1, false>(ctx, p, total, st);
   if constexpr (BN == 64) {
     // the batched dual-issuer kernel is the default for every 3x3 HALO conv; SAVSR_BIGK_ALL=0 restricts it to K > 18 blocks
-    static const bool bigk_all = getenv("SAVSR_BIGK_ALL") == nullptr || atoi(getenv("SAVSR_BIGK_ALL")) != 0;
-    if (p.halo && (bigk_all || p.nsrc * p.ntaps > kBBlocks)) {
+    if (p.halo && (ctx->opt[SAVSR_OPT_BIGK_ALL] || p.nsrc * p.ntaps > kBBlocks)) {
       const size_t smem = 1024 + kARegionBytes + kBBlocks * BN * 128 + 512;
-      static bool attr_done = false;
-      if (!attr_done) {
-        SAVSR_CUDA(cudaFuncSetAttribute(conv_igemm_bigk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        attr_done = true;
-      }
+      if (int rc = ensure_smem_attr(ctx, kAttrBigk, conv_igemm_bigk_kernel, smem)) return rc;
       p.chunk = (total + ctx->sm_count - 1) / ctx->sm_count;
       const int grid = (total + p.chunk - 1) / p.chunk;
       conv_igemm_bigk_kernel<<<grid, kBigkThreads, smem, st>>>(p);
@@ -1129,9 +1136,10 @@ static int launch_conv(savsr_ctx* ctx, ConvParams& p, int impl, cudaStream_t st)
 
 using namespace savsr;
 
-static long long* g_conv_dbg = nullptr;
-// bring-up aid (not in the public header): device buffer [grid][8] receiving cycle counters of the next conv launches
-extern "C" void savsr_debug_conv_counters(long long* dev_buf) { g_conv_dbg = dev_buf; }
+#ifdef SAVSR_DEBUG_COUNTERS
+// bring-up builds only (not in the public header): device buffer [grid][8] receiving cycle counters of the context's next conv launches
+extern "C" void savsr_debug_conv_counters(savsr_ctx* ctx, long long* dev_buf) { if (ctx) ctx->conv_dbg = dev_buf; }
+#endif
 
 extern "C" size_t savsr_packed_weight_bytes(int co, int ci, int ksize) {
   return static_cast<size_t>(co) * ci * ksize * ksize * sizeof(__nv_bfloat16);
@@ -1179,6 +1187,7 @@ extern "C" int savsr_arena_export(savsr_arena* a, int slot, float* nchw, savsr_s
 extern "C" int savsr_conv(savsr_ctx* ctx, savsr_arena* arena, const savsr_conv_group* groups, int ngroups, int ksize,
                           int n_tile, int dst_mode, const savsr_rgb_skip* skip, int impl, savsr_stream st) {
   SAVSR_REQUIRE(ctx && arena && groups, "savsr_conv: null pointer");
+  DeviceGuard guard(ctx->device);
   SAVSR_REQUIRE(ngroups >= 0 && ngroups <= SAVSR_MAX_GROUPS, "savsr_conv: ngroups %d out of range [0,%d]", ngroups, SAVSR_MAX_GROUPS);
   SAVSR_REQUIRE(ksize == 1 || ksize == 3, "savsr_conv: ksize must be 1 or 3, got %d", ksize);
   SAVSR_REQUIRE(impl >= SAVSR_IMPL_TCGEN05_TAP && impl <= SAVSR_IMPL_CHECK, "savsr_conv: unknown impl %d", impl);
@@ -1224,9 +1233,8 @@ extern "C" int savsr_conv(savsr_ctx* ctx, savsr_arena* arena, const savsr_conv_g
   p.n_res = nkb <= kBBlocks ? nkb : kBBlocks - kRing;
   p.dst_mode = dst_mode;
   p.fmt = ctx->fmt;
-  p.dbg = g_conv_dbg;
-  static const int issuers = (getenv("SAVSR_BIGK_ISSUERS") != nullptr && atoi(getenv("SAVSR_BIGK_ISSUERS")) == 1) ? 1 : 2;
-  p.issuers = issuers;
+  p.dbg = ctx->conv_dbg;
+  p.issuers = ctx->opt[SAVSR_OPT_BIGK_ISSUERS];
   if (n_tile == 64) return launch_conv<64>(ctx, p, impl, static_cast<cudaStream_t>(st));
   return launch_conv<16>(ctx, p, impl, static_cast<cudaStream_t>(st));
 }

@@ -159,6 +159,7 @@ extern "C" int savsr_aa_max_taps(int in_size, int out_size) {
 extern "C" int savsr_aa_table(savsr_ctx* ctx, int in_size, int out_size, int max_taps, int32_t* xmin, int32_t* xsize,
                               float* weights, int32_t* overflow_flag, savsr_stream st) {
   SAVSR_REQUIRE(ctx && xmin && xsize && weights && overflow_flag, "savsr_aa_table: null pointer");
+  DeviceGuard guard(ctx->device);
   SAVSR_REQUIRE(in_size > 0 && out_size > 0, "savsr_aa_table: sizes must be positive (%d -> %d)", in_size, out_size);
   SAVSR_REQUIRE(max_taps >= savsr_aa_max_taps(in_size, out_size), "savsr_aa_table: max_taps %d < savsr_aa_max_taps = %d", max_taps,
                 savsr_aa_max_taps(in_size, out_size));
@@ -174,6 +175,7 @@ extern "C" int savsr_lr_synthesize(savsr_ctx* ctx, const uint8_t* frames_bgr, in
                                    const float* weights_w, int taps_w, const int32_t* xmin_h, const int32_t* xsize_h,
                                    const float* weights_h, int taps_h, float* tmp, float* lr, float* gt, savsr_stream st_) {
   SAVSR_REQUIRE(ctx && frames_bgr && tmp && lr, "savsr_lr_synthesize: null pointer");
+  DeviceGuard guard(ctx->device);
   SAVSR_REQUIRE(nframes >= 0 && height > 0 && width > 0, "savsr_lr_synthesize: bad frame shape");
   SAVSR_REQUIRE(crop_h > 0 && crop_h <= height && crop_w > 0 && crop_w <= width, "savsr_lr_synthesize: crop %dx%d outside the %dx%d frame",
                 crop_h, crop_w, height, width);
@@ -204,6 +206,7 @@ extern "C" int savsr_resize_aa(savsr_ctx* ctx, const float* src, int nframes, in
                                const int32_t* xmin_h, const int32_t* xsize_h, const float* weights_h, int taps_h, float* tmp,
                                float* dst, savsr_stream st_) {
   SAVSR_REQUIRE(ctx && src && tmp && dst, "savsr_resize_aa: null pointer");
+  DeviceGuard guard(ctx->device);
   SAVSR_REQUIRE(nframes >= 0 && height > 0 && width > 0 && out_h > 0 && out_w > 0, "savsr_resize_aa: bad shape");
   SAVSR_REQUIRE(out_w == width || (xmin_w && xsize_w && weights_w && taps_w > 0), "savsr_resize_aa: width tables missing");
   SAVSR_REQUIRE(out_h == height || (xmin_h && xsize_h && weights_h && taps_h > 0), "savsr_resize_aa: height tables missing");

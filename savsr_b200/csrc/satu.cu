@@ -104,41 +104,6 @@ __global__ void __launch_bounds__(128) satu_table_kernel(const savsr_satu_weight
   d[1] = make_float4(out[4], out[5], out[6], out[7]);
 }
 
-// sta[c] = sum_tap xpad[y+u, x+v, c] * K[tap][c], replicate padding on the h x w region (savsr_arch.py:297-313).
-// One (pixel, 8-channel chunk) per thread; 16-byte loads of bf16.
-__global__ void __launch_bounds__(256) satu_sta_kernel(const __nv_bfloat16* __restrict__ arena, int batch, int hp, int wp,
-                                                       int h, int w, int x_slot, int kslot0, int dst_slot, int fmt) {
-  const long npix = static_cast<long>(hp) * wp;
-  const long id = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
-  const int n = blockIdx.y;
-  if (id >= npix * 8) return;
-  const int chunk = id & 7;
-  const long pix = id >> 3;
-  const int py = pix / wp, px = pix % wp;
-  float acc[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  if (py < h && px < w) {
-    const __nv_bfloat16* xs = arena + (static_cast<long>(x_slot) * batch + n) * npix * kC;
-#pragma unroll 5
-    for (int tap = 0; tap < 25; ++tap) {
-      const int sy = min(max(py + tap / 5 - 2, 0), h - 1);
-      const int sx = min(max(px + tap % 5 - 2, 0), w - 1);
-      const uint4 xv = *reinterpret_cast<const uint4*>(xs + (static_cast<long>(sy) * wp + sx) * kC + chunk * 8);
-      const uint4 kv = *reinterpret_cast<const uint4*>(arena + ((static_cast<long>(kslot0 + tap) * batch + n) * npix + pix) * kC + chunk * 8);
-      acc[0] += h_lo(xv.x, fmt) * h_lo(kv.x, fmt); acc[1] += h_hi(xv.x, fmt) * h_hi(kv.x, fmt);
-      acc[2] += h_lo(xv.y, fmt) * h_lo(kv.y, fmt); acc[3] += h_hi(xv.y, fmt) * h_hi(kv.y, fmt);
-      acc[4] += h_lo(xv.z, fmt) * h_lo(kv.z, fmt); acc[5] += h_hi(xv.z, fmt) * h_hi(kv.z, fmt);
-      acc[6] += h_lo(xv.w, fmt) * h_lo(kv.w, fmt); acc[7] += h_hi(xv.w, fmt) * h_hi(kv.w, fmt);
-    }
-  }
-  uint4 o;
-  o.x = pack_h2(acc[0], acc[1], fmt); o.y = pack_h2(acc[2], acc[3], fmt);
-  o.z = pack_h2(acc[4], acc[5], fmt); o.w = pack_h2(acc[6], acc[7], fmt);
-  *reinterpret_cast<uint4*>(const_cast<__nv_bfloat16*>(arena) + ((static_cast<long>(dst_slot) * batch + n) * npix + pix) * kC + chunk * 8) = o;
-}
-
-
 // ------------------------------------------------------------------------------------------------ kernel_conv + sta_conv, fused
 // sta[p][c] = sum_{t in 5x5} x[clamp(p + d_t)][c] * K_t[p][c],   K_t = LeakyReLU_0.1(W_t a[p] + b_t)   (savsr_arch.py:297-313)
 // The unfused route materialises the 25 per-pixel kernels K_t (1600 channels, 83 MB per sample) and reads them back.  Here
@@ -349,20 +314,7 @@ __global__ void __launch_bounds__(kKstaThreads, 1) satu_kconv_sta_kernel(const _
   }
 }
 
-// ------------------------------------------------------------------------------------------------ HR gather
-struct GatherParams {
-  const __nv_bfloat16* lr;
-  __nv_bfloat16* hr;
-  const float* table;
-  const float* base_y;
-  const float* base_x;
-  const float* compress;  // [4][8][64]
-  const float* expand;    // [4][64][8]
-  int batch, hp, wp, h, w, H, W;
-  int x_slot, sta_slot, sta_dst, fea_dst;
-  int fmt;
-};
-
+// ------------------------------------------------------------------------------------------------ bilinear corners
 struct Corner4 {
   int off[4];   // element offset of the corner pixel inside the LR image (pixel index * 64), -1 = outside
   float wt[4];
@@ -386,147 +338,6 @@ __device__ __forceinline__ Corner4 make_corners(float gx, float gy, int h, int w
       c.wt[a * 2 + b] = wy[a] * wx[b];
     }
   return c;
-}
-
-constexpr int kGatherPix = 128;
-constexpr int kFStride = 65;
-
-// Block = 128 consecutive HR pixels of one sample.
-//  phase A: (pixel, 8-channel chunk) per thread-iteration: bilinear gather of x -> f (smem, fp32) and of
-//           sta -> HR slot sta_dst (bf16, coalesced 16-byte stores).
-//  phase B: one pixel per thread: t = sum_e r_e (Wc_e f), fea = sum_e r_e (We_e t) + f   (matrix-free; the
-//           single-sum shortcut is wrong because r is a per-expert sigmoid -- SURVEY.md A.3 item 5).
-//  phase C: coalesced bf16 store of fea -> HR slot fea_dst.
-__global__ void __launch_bounds__(kGatherPix) satu_gather_kernel(const GatherParams p) {
-  extern __shared__ __align__(16) float sm[];
-  float* f_s = sm;                                // [128][65]
-  float* wc_s = f_s + kGatherPix * kFStride;      // [64 c][32 (e*8+k)]
-  float* we_s = wc_s + 64 * 32;                   // [32 (e*8+k)][64 c]
-  Corner4* cx = reinterpret_cast<Corner4*>(we_s + 32 * 64);  // [128] corners for x
-  Corner4* cs = cx + kGatherPix;                             // [128] corners for sta
-  float* rt = reinterpret_cast<float*>(cs + kGatherPix);     // [128][4] routing
-
-  for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
-    const int c = i >> 5, j = i & 31;              // compress[e][k][c] with j = e*8+k
-    wc_s[i] = p.compress[j * 64 + c];
-    const int jj = i >> 6, cc = i & 63;            // expand[e][c][k] with jj = e*8+k
-    we_s[i] = p.expand[((jj >> 3) * 64 + cc) * 8 + (jj & 7)];
-  }
-  const int n = blockIdx.y;
-  const long NPIX = static_cast<long>(p.H) * p.W;
-  const long pix0 = blockIdx.x * static_cast<long>(kGatherPix);
-  {
-    const long pix = pix0 + threadIdx.x;
-    if (pix < NPIX) {
-      const int i = pix / p.W, j = pix % p.W;
-      const float4 t0 = *reinterpret_cast<const float4*>(p.table + pix * 8);
-      const float4 t1 = *reinterpret_cast<const float4*>(p.table + pix * 8 + 4);
-      const float bx = p.base_x[j], by = p.base_y[i];
-      const float wm1 = static_cast<float>(p.w - 1), hm1 = static_cast<float>(p.h - 1);
-      // grid = base + offset * 2 / (n - 1)   (savsr_arch.py:285-287)
-      cx[threadIdx.x] = make_corners(__fadd_rn(bx, __fdiv_rn(__fmul_rn(t0.x, 2.f), wm1)),
-                                     __fadd_rn(by, __fdiv_rn(__fmul_rn(t0.y, 2.f), hm1)), p.h, p.w, p.wp);
-      cs[threadIdx.x] = make_corners(__fadd_rn(bx, __fdiv_rn(__fmul_rn(t0.z, 2.f), wm1)),
-                                     __fadd_rn(by, __fdiv_rn(__fmul_rn(t0.w, 2.f), hm1)), p.h, p.w, p.wp);
-      rt[threadIdx.x * 4 + 0] = t1.x; rt[threadIdx.x * 4 + 1] = t1.y;
-      rt[threadIdx.x * 4 + 2] = t1.z; rt[threadIdx.x * 4 + 3] = t1.w;
-    }
-  }
-  __syncthreads();
-
-  const long lr_img = static_cast<long>(p.hp) * p.wp * kC;
-  const __nv_bfloat16* xs = p.lr + (static_cast<long>(p.x_slot) * p.batch + n) * lr_img;
-  const __nv_bfloat16* ss = p.lr + (static_cast<long>(p.sta_slot) * p.batch + n) * lr_img;
-  __nv_bfloat16* sta_out = p.hr + (static_cast<long>(p.sta_dst) * p.batch + n) * NPIX * kC;
-  __nv_bfloat16* fea_out = p.hr + (static_cast<long>(p.fea_dst) * p.batch + n) * NPIX * kC;
-
-  // ---- phase A
-  for (int it = 0; it < 8; ++it) {
-    const int id = it * kGatherPix + threadIdx.x;
-    const int lp = id >> 3, chunk = id & 7;
-    if (pix0 + lp >= NPIX) continue;
-    float a[8], b[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { a[e] = 0.f; b[e] = 0.f; }
-    const Corner4 c1 = cx[lp], c2 = cs[lp];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (c1.off[q] >= 0) {
-        const uint4 v = *reinterpret_cast<const uint4*>(xs + c1.off[q] + chunk * 8);
-        const float wgt = c1.wt[q];
-        a[0] += wgt * h_lo(v.x, p.fmt); a[1] += wgt * h_hi(v.x, p.fmt); a[2] += wgt * h_lo(v.y, p.fmt); a[3] += wgt * h_hi(v.y, p.fmt);
-        a[4] += wgt * h_lo(v.z, p.fmt); a[5] += wgt * h_hi(v.z, p.fmt); a[6] += wgt * h_lo(v.w, p.fmt); a[7] += wgt * h_hi(v.w, p.fmt);
-      }
-      if (c2.off[q] >= 0) {
-        const uint4 v = *reinterpret_cast<const uint4*>(ss + c2.off[q] + chunk * 8);
-        const float wgt = c2.wt[q];
-        b[0] += wgt * h_lo(v.x, p.fmt); b[1] += wgt * h_hi(v.x, p.fmt); b[2] += wgt * h_lo(v.y, p.fmt); b[3] += wgt * h_hi(v.y, p.fmt);
-        b[4] += wgt * h_lo(v.z, p.fmt); b[5] += wgt * h_hi(v.z, p.fmt); b[6] += wgt * h_lo(v.w, p.fmt); b[7] += wgt * h_hi(v.w, p.fmt);
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) f_s[lp * kFStride + chunk * 8 + e] = a[e];
-    uint4 o;
-    o.x = pack_h2(b[0], b[1], p.fmt); o.y = pack_h2(b[2], b[3], p.fmt); o.z = pack_h2(b[4], b[5], p.fmt); o.w = pack_h2(b[6], b[7], p.fmt);
-    *reinterpret_cast<uint4*>(sta_out + (pix0 + lp) * kC + chunk * 8) = o;
-  }
-  __syncthreads();
-
-  // ---- phase B
-  if (pix0 + threadIdx.x < NPIX) {
-    float* f = f_s + threadIdx.x * kFStride;
-    float u[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) u[j] = 0.f;
-#pragma unroll 4
-    for (int c = 0; c < 64; ++c) {
-      const float fc = f[c];
-      const float4* wr = reinterpret_cast<const float4*>(wc_s + c * 32);
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        const float4 wv = wr[j4];
-        u[4 * j4 + 0] += fc * wv.x; u[4 * j4 + 1] += fc * wv.y; u[4 * j4 + 2] += fc * wv.z; u[4 * j4 + 3] += fc * wv.w;
-      }
-    }
-    const float r[4] = {rt[threadIdx.x * 4 + 0], rt[threadIdx.x * 4 + 1], rt[threadIdx.x * 4 + 2], rt[threadIdx.x * 4 + 3]};
-    float t[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) t[k] = r[0] * u[k] + r[1] * u[8 + k] + r[2] * u[16 + k] + r[3] * u[24 + k];
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-#pragma unroll
-      for (int k = 0; k < 8; ++k) u[e * 8 + k] = r[e] * t[k];
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      float acc[32];
-#pragma unroll
-      for (int c = 0; c < 32; ++c) acc[c] = f[half * 32 + c];
-#pragma unroll 4
-      for (int j = 0; j < 32; ++j) {
-        const float vj = u[j];
-        const float4* wr = reinterpret_cast<const float4*>(we_s + j * 64 + half * 32);
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          const float4 wv = wr[c4];
-          acc[4 * c4 + 0] += vj * wv.x; acc[4 * c4 + 1] += vj * wv.y; acc[4 * c4 + 2] += vj * wv.z; acc[4 * c4 + 3] += vj * wv.w;
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < 32; ++c) f[half * 32 + c] = acc[c];
-    }
-  }
-  __syncthreads();
-
-  // ---- phase C
-  for (int it = 0; it < 8; ++it) {
-    const int id = it * kGatherPix + threadIdx.x;
-    const int lp = id >> 3, chunk = id & 7;
-    if (pix0 + lp >= NPIX) continue;
-    const float* f = f_s + lp * kFStride + chunk * 8;
-    uint4 o;
-    o.x = pack_h2(f[0], f[1], p.fmt); o.y = pack_h2(f[2], f[3], p.fmt); o.z = pack_h2(f[4], f[5], p.fmt); o.w = pack_h2(f[6], f[7], p.fmt);
-    *reinterpret_cast<uint4*>(fea_out + (pix0 + lp) * kC + chunk * 8) = o;
-  }
 }
 
 // ------------------------------------------------------------------------------------------------ fused HR kernel
@@ -779,8 +590,6 @@ __global__ void __launch_bounds__(kFusedThreads, 2) satu_fused_kernel(const Fuse
   if (warp == 0) { tc_fence_after(); tmem_dealloc<256>(tm); }
 }
 
-constexpr size_t kGatherSmem = sizeof(float) * (kGatherPix * kFStride + 64 * 32 + 32 * 64 + kGatherPix * 4) + 2 * kGatherPix * sizeof(Corner4);
-
 }  // namespace savsr
 
 using namespace savsr;
@@ -789,6 +598,7 @@ extern "C" int savsr_satu_index(savsr_ctx* ctx, const savsr_satu_weights* wts, i
                                 float s_w, float* rel_y, float* rel_x, int32_t* cell_y, int32_t* cell_x, float* base_y,
                                 float* base_x, int32_t* corner_y, int32_t* corner_x, float* table, savsr_stream st_) {
   SAVSR_REQUIRE(ctx, "savsr_satu_index: null context");
+  DeviceGuard guard(ctx->device);
   SAVSR_REQUIRE(h >= 2 && w >= 2 && H >= 1 && W >= 1, "savsr_satu_index: bad sizes lr %dx%d hr %dx%d", h, w, H, W);
   SAVSR_REQUIRE(s_h > 0.f && s_w > 0.f, "savsr_satu_index: scale must be positive, got (%g, %g)", s_h, s_w);
   cudaStream_t st = static_cast<cudaStream_t>(st_);
@@ -801,20 +611,6 @@ extern "C" int savsr_satu_index(savsr_ctx* ctx, const savsr_satu_weights* wts, i
     const long npix = static_cast<long>(H) * W;
     satu_table_kernel<<<static_cast<unsigned>((npix + 127) / 128), 128, 0, st>>>(*wts, H, W, s_h, s_w, table);
   }
-  SAVSR_CUDA(cudaGetLastError());
-  return 0;
-}
-
-extern "C" int savsr_satu_sta(savsr_ctx* ctx, savsr_arena* arena, int x_slot, int kslot0, int dst_slot, int h, int w,
-                              savsr_stream st) {
-  SAVSR_REQUIRE(ctx && arena, "savsr_satu_sta: null pointer");
-  SAVSR_REQUIRE(x_slot >= 0 && x_slot < arena->nslots && dst_slot >= 0 && dst_slot < arena->nslots && kslot0 >= 0 &&
-                kslot0 + 25 <= arena->nslots, "savsr_satu_sta: slot out of range");
-  SAVSR_REQUIRE(h >= 1 && w >= 1 && h <= arena->height && w <= arena->width, "savsr_satu_sta: region %dx%d exceeds arena", h, w);
-  if (arena->batch == 0) return 0;
-  const long ids = static_cast<long>(arena->height) * arena->width * 8;
-  satu_sta_kernel<<<dim3(static_cast<unsigned>((ids + 255) / 256), arena->batch), 256, 0, static_cast<cudaStream_t>(st)>>>(
-      arena->base, arena->batch, arena->height, arena->width, h, w, x_slot, kslot0, dst_slot, ctx->fmt);
   SAVSR_CUDA(cudaGetLastError());
   return 0;
 }
@@ -843,39 +639,9 @@ extern "C" int savsr_satu_kconv_sta(savsr_ctx* ctx, savsr_arena* arena, int a_sl
   p.chunk = (p.nbatches + ctx->sm_count - 1) / ctx->sm_count;
   p.fmt = ctx->fmt;
   const int grid = (p.nbatches + p.chunk - 1) / p.chunk;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SAVSR_CUDA(cudaFuncSetAttribute(satu_kconv_sta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKstaSmem));
-    attr_done = true;
-  }
+  DeviceGuard guard(ctx->device);
+  if (int rc = ensure_smem_attr(ctx, kAttrKsta, satu_kconv_sta_kernel, kKstaSmem)) return rc;
   satu_kconv_sta_kernel<<<grid, kKstaThreads, kKstaSmem, static_cast<cudaStream_t>(st)>>>(p);
-  SAVSR_CUDA(cudaGetLastError());
-  return 0;
-}
-
-extern "C" int savsr_satu_gather(savsr_ctx* ctx, savsr_arena* lr, int x_slot, int sta_slot, int h, int w, savsr_arena* hr,
-                                 int sta_dst, int fea_dst, const float* table, const float* base_y, const float* base_x,
-                                 const savsr_satu_weights* wts, savsr_stream st) {
-  SAVSR_REQUIRE(ctx && lr && hr && table && base_y && base_x && wts && wts->compress && wts->expand, "savsr_satu_gather: null pointer");
-  SAVSR_REQUIRE(lr->batch == hr->batch, "savsr_satu_gather: LR batch %d != HR batch %d", lr->batch, hr->batch);
-  SAVSR_REQUIRE(x_slot >= 0 && x_slot < lr->nslots && sta_slot >= 0 && sta_slot < lr->nslots, "savsr_satu_gather: LR slot out of range");
-  SAVSR_REQUIRE(sta_dst >= 0 && sta_dst < hr->nslots && fea_dst >= 0 && fea_dst < hr->nslots && sta_dst != fea_dst,
-                "savsr_satu_gather: HR slot out of range");
-  SAVSR_REQUIRE(h >= 2 && w >= 2 && h <= lr->height && w <= lr->width, "savsr_satu_gather: region %dx%d exceeds LR arena", h, w);
-  if (lr->batch == 0) return 0;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SAVSR_CUDA(cudaFuncSetAttribute(satu_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGatherSmem)));
-    attr_done = true;
-  }
-  GatherParams p;
-  p.lr = lr->base; p.hr = hr->base; p.table = table; p.base_y = base_y; p.base_x = base_x;
-  p.compress = wts->compress; p.expand = wts->expand;
-  p.batch = lr->batch; p.hp = lr->height; p.wp = lr->width; p.h = h; p.w = w; p.H = hr->height; p.W = hr->width;
-  p.x_slot = x_slot; p.sta_slot = sta_slot; p.sta_dst = sta_dst; p.fea_dst = fea_dst; p.fmt = ctx->fmt;
-  const long npix = static_cast<long>(p.H) * p.W;
-  satu_gather_kernel<<<dim3(static_cast<unsigned>((npix + kGatherPix - 1) / kGatherPix), lr->batch), kGatherPix, kGatherSmem,
-                       static_cast<cudaStream_t>(st)>>>(p);
   SAVSR_CUDA(cudaGetLastError());
   return 0;
 }
@@ -889,11 +655,8 @@ extern "C" int savsr_satu_fused(savsr_ctx* ctx, savsr_arena* lr, int x_slot, int
   SAVSR_REQUIRE(dst_slot >= 0 && dst_slot < hr->nslots, "savsr_satu_fused: HR slot out of range");
   SAVSR_REQUIRE(h >= 2 && w >= 2 && h <= lr->height && w <= lr->width, "savsr_satu_fused: region %dx%d exceeds LR arena", h, w);
   if (lr->batch == 0) return 0;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SAVSR_CUDA(cudaFuncSetAttribute(satu_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
-    attr_done = true;
-  }
+  DeviceGuard guard(ctx->device);
+  if (int rc = ensure_smem_attr(ctx, kAttrFused, satu_fused_kernel, kFusedSmem)) return rc;
   FusedParams p;
   p.lr = lr->base; p.hr = hr->base; p.table = table; p.base_y = base_y; p.base_x = base_x;
   p.w_compress = static_cast<const uint8_t*>(w_compress); p.w_expand = static_cast<const uint8_t*>(w_expand);

@@ -6,77 +6,7 @@
 
 namespace savsr {
 
-// ------------------------------------------------------------------------------------------------ first-layer convs
-constexpr int kMaxFront = 8;
-struct FrontParams {
-  savsr_front_group g[kMaxFront];
-  const float* x;
-  __nv_bfloat16* arena;
-  int ngroups, batch, t, h, w, hp, wp;
-  int fmt;
-};
-
-// dst = LeakyReLU_0.2(conv3x3(cat(frames)) + bias) on the reflect-padded (even-sized) frames.
-// grid (pixel blocks, batch, groups), 128 threads, one pixel x 64 output channels per thread.
-__global__ void __launch_bounds__(128) front_conv_kernel(const __grid_constant__ FrontParams p) {
-  __shared__ __align__(16) float w_s[54 * 64];  // [cin*9][64]
-  __shared__ float b_s[64];
-  const savsr_front_group& g = p.g[blockIdx.z];
-  const int cin = 3 * g.nframes;
-  const int kk = cin * 9;
-  for (int i = threadIdx.x; i < kk * 64; i += blockDim.x) {
-    const int o = i & 63, r = i >> 6;  // r = ci*9 + tap
-    w_s[i] = g.weight[o * kk + r];
-  }
-  if (threadIdx.x < 64) b_s[threadIdx.x] = g.bias[threadIdx.x];
-  __syncthreads();
-  const int n = blockIdx.y;
-  const long npix = static_cast<long>(p.hp) * p.wp;
-  const long pix = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
-  if (pix >= npix) return;
-  const int py = pix / p.wp, px = pix % p.wp;
-  float acc[64];
-#pragma unroll
-  for (int o = 0; o < 64; ++o) acc[o] = b_s[o];
-  const long plane = static_cast<long>(p.h) * p.w;
-  for (int f = 0; f < g.nframes; ++f) {
-    const float* fr = p.x + (static_cast<long>(n) * p.t + g.frame[f]) * 3 * plane;
-    for (int c = 0; c < 3; ++c) {
-#pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const int sy = py + tap / 3 - 1, sx = px + tap % 3 - 1;
-        float a = 0.f;
-        if (sy >= 0 && sy < p.hp && sx >= 0 && sx < p.wp) {
-          const int ry = sy < p.h ? sy : 2 * p.h - 2 - sy;  // reflect pad of savsr_arch.py:688
-          const int rx = sx < p.w ? sx : 2 * p.w - 2 - sx;
-          a = __ldg(fr + c * plane + static_cast<long>(ry) * p.w + rx);
-        }
-        const float4* wr = reinterpret_cast<const float4*>(w_s + ((f * 3 + c) * 9 + tap) * 64);
-#pragma unroll
-        for (int o4 = 0; o4 < 16; ++o4) {
-          const float4 wv = wr[o4];
-          acc[4 * o4 + 0] += a * wv.x; acc[4 * o4 + 1] += a * wv.y;
-          acc[4 * o4 + 2] += a * wv.z; acc[4 * o4 + 3] += a * wv.w;
-        }
-      }
-    }
-  }
-  uint4* d = reinterpret_cast<uint4*>(p.arena + ((static_cast<long>(g.dst_slot) * p.batch + n) * npix + pix) * kC);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float r[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float v = acc[8 * j + e];
-      r[e] = v > 0.f ? v : 0.2f * v;
-    }
-    uint4 u;
-    u.x = pack_h2(r[0], r[1], p.fmt); u.y = pack_h2(r[2], r[3], p.fmt);
-    u.z = pack_h2(r[4], r[5], p.fmt); u.w = pack_h2(r[6], r[7], p.fmt);
-    d[j] = u;
-  }
-}
-
+// ------------------------------------------------------------------------------------------------ first layer: frame packing
 // fp32 NCHW window [B][t][3][h][w] -> one bf16 arena slot whose channels 0..3t-1 are the frames' RGB planes
 // (channel 3f + c), the rest zero, reflect-padded to the even arena size (savsr_arch.py:670-690).  With this slot the
 // first-layer convs (conv_c / conv_sup, savsr_arch.py:456-457) run on the tensor-core kernel with zero-expanded weights.
@@ -599,34 +529,9 @@ __global__ void __launch_bounds__(256) ssim_y_kernel(const __grid_constant__ Ssi
   }
 }
 
-extern "C" int savsr_front_conv(savsr_ctx* ctx, savsr_arena* arena, const float* x, int t, int h, int w,
-                                const savsr_front_group* groups, int ngroups, savsr_stream st) {
-  SAVSR_REQUIRE(ctx && arena && x && groups, "savsr_front_conv: null pointer");
-  SAVSR_REQUIRE(ngroups >= 0 && ngroups <= kMaxFront, "savsr_front_conv: ngroups %d out of range [0,%d]", ngroups, kMaxFront);
-  SAVSR_REQUIRE(h >= 2 && w >= 2, "savsr_front_conv: LR frame %dx%d too small for reflect padding", h, w);
-  SAVSR_REQUIRE(arena->height == h + (h & 1) && arena->width == w + (w & 1),
-                "savsr_front_conv: arena %dx%d is not the even-padded size of %dx%d", arena->height, arena->width, h, w);
-  if (ngroups == 0) return 0;
-  FrontParams p;
-  memset(&p, 0, sizeof(p));
-  for (int i = 0; i < ngroups; ++i) {
-    const savsr_front_group& g = groups[i];
-    SAVSR_REQUIRE(g.nframes == 1 || g.nframes == 2, "savsr_front_conv: group %d nframes %d", i, g.nframes);
-    for (int f = 0; f < g.nframes; ++f) SAVSR_REQUIRE(g.frame[f] >= 0 && g.frame[f] < t, "savsr_front_conv: frame index %d out of range", g.frame[f]);
-    SAVSR_REQUIRE(g.dst_slot >= 0 && g.dst_slot < arena->nslots && g.weight && g.bias, "savsr_front_conv: bad group %d", i);
-    p.g[i] = g;
-  }
-  p.x = x; p.arena = arena->base; p.ngroups = ngroups; p.batch = arena->batch;
-  p.t = t; p.h = h; p.w = w; p.hp = arena->height; p.wp = arena->width; p.fmt = ctx->fmt;
-  const long npix = static_cast<long>(p.hp) * p.wp;
-  dim3 grid(static_cast<unsigned>((npix + 127) / 128), arena->batch, ngroups);
-  front_conv_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(st)>>>(p);
-  SAVSR_CUDA(cudaGetLastError());
-  return 0;
-}
-
 extern "C" int savsr_pack_frames(savsr_ctx* ctx, savsr_arena* arena, const float* x, int t, int h, int w, int dst_slot, savsr_stream st) {
   SAVSR_REQUIRE(ctx && arena && x, "savsr_pack_frames: null pointer");
+  DeviceGuard guard(ctx->device);
   SAVSR_REQUIRE(t >= 1 && 3 * t <= kC, "savsr_pack_frames: %d frames do not fit 64 channels", t);
   SAVSR_REQUIRE(h >= 2 && w >= 2, "savsr_pack_frames: LR frame %dx%d too small for reflect padding", h, w);
   SAVSR_REQUIRE(arena->height == h + (h & 1) && arena->width == w + (w & 1),
@@ -645,6 +550,7 @@ extern "C" int savsr_pack_frames(savsr_ctx* ctx, savsr_arena* arena, const float
 extern "C" int savsr_osa_prologue(savsr_ctx* ctx, const savsr_osa_params* convs, int nconvs, int batch, int npart,
                                   int npix, float inv_scale_h, float inv_scale_w, savsr_stream st_) {
   SAVSR_REQUIRE(ctx && convs, "savsr_osa_prologue: null pointer");
+  DeviceGuard guard(ctx->device);
   SAVSR_REQUIRE(nconvs >= 0 && nconvs <= kMaxOsa, "savsr_osa_prologue: nconvs %d out of range [0,%d]", nconvs, kMaxOsa);
   if (nconvs == 0 || batch == 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(st_);
@@ -670,10 +576,8 @@ extern "C" int savsr_osa_prologue(savsr_ctx* ctx, const savsr_osa_params* convs,
   const int lin_split = batch >= 12 ? 3 : (batch >= 4 ? 2 : 1);
   const size_t lin_smem = static_cast<size_t>((batch + lin_split - 1) / lin_split) * 2 * max_ci * sizeof(float);
   SAVSR_REQUIRE(lin_smem <= 200 * 1024, "savsr_osa_prologue: batch %d too large for the routing kernel's shared memory", batch);
-  static bool lin_attr = false;
-  if (lin_smem > 48 * 1024 && !lin_attr) {
-    SAVSR_CUDA(cudaFuncSetAttribute(osa_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    lin_attr = true;
+  if (lin_smem > 48 * 1024) {
+    if (int rc = ensure_smem_attr(ctx, kAttrOsaLinear, osa_linear_kernel, 200 * 1024)) return rc;
   }
   osa_linear_kernel<<<dim3((2 * max_ci + 7) / 8, nconvs, lin_split), 256, lin_smem, st>>>(L, 0);
   osa_linear_kernel<<<dim3((max_ci + 7) / 8, nconvs, lin_split), 256, lin_smem, st>>>(L, 1);
@@ -688,6 +592,7 @@ extern "C" int savsr_ca_scale_residual(savsr_ctx* ctx, savsr_arena* arena, int t
                                        const float* pool, int npart, const float* w1, const float* b1, const float* w2,
                                        const float* b2, float* y_scratch, savsr_stream st) {
   SAVSR_REQUIRE(ctx && arena && pool && w1 && b1 && w2 && b2 && y_scratch, "savsr_ca_scale_residual: null pointer");
+  DeviceGuard guard(ctx->device);
   SAVSR_REQUIRE(t_slot >= 0 && t_slot < arena->nslots && x_slot >= 0 && x_slot < arena->nslots && dst_slot >= 0 &&
                 dst_slot < arena->nslots, "savsr_ca_scale_residual: slot out of range");
   CaParams p;
@@ -711,6 +616,7 @@ extern "C" int savsr_osadapt_mask(savsr_ctx* ctx, const float* in16, int batch, 
                                   const float* ba, const float* wb, const float* bb, const float* wc, const float* bc,
                                   float* half0, float* half1, float* mask, savsr_stream st_) {
   SAVSR_REQUIRE(ctx && in16 && wa && ba && wb && bb && wc && bc && half0 && half1 && mask, "savsr_osadapt_mask: null pointer");
+  DeviceGuard guard(ctx->device);
   SAVSR_REQUIRE(height % 2 == 0 && width % 2 == 0, "savsr_osadapt_mask: size %dx%d must be even (pad_spatial)", height, width);
   if (batch == 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(st_);
@@ -728,6 +634,7 @@ extern "C" int savsr_osadapt_mask(savsr_ctx* ctx, const float* in16, int batch, 
 extern "C" int savsr_img_metrics(savsr_ctx* ctx, const float* sr, const float* gt, int batch, int height, int width, uint8_t* bgr_u8,
                                  double* sse_y, savsr_stream st_) {
   SAVSR_REQUIRE(ctx && sr, "savsr_img_metrics: null pointer");
+  DeviceGuard guard(ctx->device);
   SAVSR_REQUIRE(batch >= 0 && height > 0 && width > 0, "savsr_img_metrics: bad shape");
   SAVSR_REQUIRE(!sse_y || gt, "savsr_img_metrics: sse_y requested without a ground-truth frame");
   if (batch == 0) return 0;
@@ -749,6 +656,7 @@ extern "C" int savsr_ssim_y_blocks(int height, int width) {
 extern "C" int savsr_ssim_y(savsr_ctx* ctx, const float* sr, const float* gt, int batch, int height, int width, double* partials,
                             savsr_stream st) {
   SAVSR_REQUIRE(ctx && sr && gt && partials, "savsr_ssim_y: null pointer");
+  DeviceGuard guard(ctx->device);
   SAVSR_REQUIRE(batch >= 0 && height >= 11 && width >= 11, "savsr_ssim_y: frames of %dx%d are smaller than the 11x11 window", height, width);
   if (batch == 0) return 0;
   SsimParams p;

@@ -46,9 +46,32 @@ _contexts: Dict[int, K.Context] = {}
 
 
 def context(device_index: int) -> K.Context:
+    """One savsr_ctx per device.  Bring-up knobs come from the environment HERE (the library itself reads none)."""
     if device_index not in _contexts:
-        _contexts[device_index] = K.Context(device_index)
+        c = K.Context(device_index)
+        if os.environ.get("SAVSR_BIGK_ALL") is not None:
+            c.set_option(K.OPT_BIGK_ALL, int(os.environ["SAVSR_BIGK_ALL"] != "0"))
+        if os.environ.get("SAVSR_BIGK_ISSUERS") is not None:
+            c.set_option(K.OPT_BIGK_ISSUERS, int(os.environ["SAVSR_BIGK_ISSUERS"]))
+        _contexts[device_index] = c
     return _contexts[device_index]
+
+
+class WeightStore:
+    """Everything a plan derives from the weights alone -- packed tensor-core layouts, folded BatchNorm, zero-expanded
+    first-layer filters -- keyed by name and shared by all plans of one (module, device, precision, weights version).
+    A new (batch, h, w, scale) plan then only allocates its arenas and records its launch list (the reference YAMLs sweep
+    42-48 scales per run)."""
+
+    def __init__(self, version: tuple = ()):
+        self.version = version
+        self.cache: Dict[tuple, torch.Tensor] = {}
+
+    def get(self, key: tuple, make: Callable[[], torch.Tensor]) -> torch.Tensor:
+        t = self.cache.get(key)
+        if t is None:
+            t = self.cache[key] = make()
+        return t
 
 
 class _Slots:
@@ -78,7 +101,8 @@ class _Slots:
 
 class Plan:
     def __init__(self, params: Dict[str, torch.Tensor], batch: int, h: int, w: int, scale, device: torch.device,
-                 conv_impl: str = "tap", num_frame: int = 7, taps: Optional[Sequence[str]] = None, precision: str = "bf16"):
+                 conv_impl: str = "tap", num_frame: int = 7, taps: Optional[Sequence[str]] = None, precision: str = "bf16",
+                 store: Optional[WeightStore] = None):
         if device.type != "cuda":
             raise K.SavsrError("savsr_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
         if num_frame != 7:
@@ -98,13 +122,15 @@ class Plan:
         self.H, self.W = get_hw(h, w, self.scale)
         self.P = params
         self._keep: List[object] = []   # tensors / ctypes arrays referenced by raw pointers
+        self._pack_src: List[torch.Tensor] = []
         self.ops: List[Callable[[int], int]] = []
         self.op_meta: List[Tuple[str, float, int, str]] = []   # (kind, algorithmic FLOPs, kernel launches, detail) per op
         self.n_launches = 0
         self.taps = set(taps or ())
         self.tap_bufs: Dict[str, torch.Tensor] = {}
         self.graph: Optional[torch.cuda.CUDAGraph] = None
-        self._pack_cache: Dict[str, int] = {}
+        self.store = store if store is not None else WeightStore()
+        self.nbytes = 0                          # device memory owned by this plan (arenas, scratch, I/O staging)
         self._pool_cache: Dict[str, int] = {}
         self._osa_cache: Dict[str, Tuple[K.OsaParams, int, int]] = {}
         with torch.cuda.device(device), torch.no_grad():
@@ -115,6 +141,7 @@ class Plan:
     def _buf(self, *shape, dtype=torch.float32) -> torch.Tensor:
         t = torch.empty(*shape, dtype=dtype, device=self.device)
         self._keep.append(t)
+        self.nbytes += t.numel() * t.element_size()
         return t
 
     def _p(self, name: str) -> torch.Tensor:
@@ -127,28 +154,31 @@ class Plan:
     def _ptr(self, name: str) -> int:
         return self._p(name).data_ptr()
 
-    def _dev(self, t: torch.Tensor) -> int:
-        t = t.detach().to(self.device, torch.float32).contiguous()
-        self._keep.append(t)
-        return t.data_ptr()
+    def _derived(self, key, make: Callable[[], torch.Tensor]) -> torch.Tensor:
+        """fp32 device tensor computed from the weights alone (folded BN, zero-expanded filters ...), shared through the store."""
+        return self.store.get(("derived", key), lambda: make().detach().to(self.device, torch.float32).contiguous())
+
+    def _dev(self, key, make: Callable[[], torch.Tensor]) -> int:
+        return self._derived(key, make).data_ptr()
 
     def _packp(self, name: str) -> int:
-        """Packed copy of the conv parameter `name` (cached: the five propagation iterations share weights)."""
-        if name not in self._pack_cache:
-            self._pack_cache[name] = self._pack(self._p(name))
-        return self._pack_cache[name]
+        """Packed copy of the conv parameter `name` (shared: the five propagation iterations and every plan use one copy)."""
+        return self._pack(name, lambda: self._p(name))
 
-    def _pack(self, w: torch.Tensor, n_tile: int = 64, co_pad: Optional[int] = None, rows: int = K.ROWS_QUAD) -> int:
+    def _pack(self, key, make: Callable[[], torch.Tensor], n_tile: int = 64, co_pad: Optional[int] = None,
+              rows: int = K.ROWS_QUAD) -> int:
         """fp32 OIHW -> packed 16-bit tensor-core layout; returns the device pointer.  `rows`: row order of n_tile 64
-        blocks -- QUAD for everything savsr_conv consumes, LINEAR for the SATU expert / fusion GEMMs."""
-        w = w.detach().to(self.device, torch.float32).contiguous()
-        co_real, ci, ks, _ = w.shape
-        co = co_pad or co_real
-        out = self._buf(self.lib.savsr_packed_weight_bytes(co, ci, ks), dtype=torch.uint8)
-        self._keep.append(w)
-        K.check(self.lib.savsr_pack_conv_weight(w.data_ptr(), co_real, co, ci, ks, n_tile, self.fmt, rows, out.data_ptr(),
-                                                torch.cuda.current_stream().cuda_stream))
-        return out.data_ptr()
+        blocks -- QUAD for everything savsr_conv consumes, LINEAR for the SATU expert GEMMs.  Cached in the store by `key`."""
+        def build() -> torch.Tensor:
+            w = make().detach().to(self.device, torch.float32).contiguous()
+            co_real, ci, ks, _ = w.shape
+            co = co_pad or co_real
+            out = torch.empty(self.lib.savsr_packed_weight_bytes(co, ci, ks), dtype=torch.uint8, device=self.device)
+            K.check(self.lib.savsr_pack_conv_weight(w.data_ptr(), co_real, co, ci, ks, n_tile, self.fmt, rows, out.data_ptr(),
+                                                    torch.cuda.current_stream(self.device).cuda_stream))
+            self._pack_src.append(w)                 # the source must outlive the asynchronous pack kernel
+            return out
+        return self.store.get(("packed", key, n_tile, co_pad, rows, self.fmt), build).data_ptr()
 
     # ------------------------------------------------------------------ op emitters
     def _emit(self, fn: Callable[[int], int], launches: int = 1, kind: str = "other", flops: float = 0.0,
@@ -171,15 +201,22 @@ class Plan:
         return g
 
     def _conv(self, arena: K.Arena, groups: Sequence[K.ConvGroup], ksize: int = 3, n_tile: int = 64,
-              dst_mode: int = K.DST_ARENA, skip: Optional[K.RgbSkip] = None) -> None:
+              dst_mode: int = K.DST_ARENA, skip: Optional[K.RgbSkip] = None, alg_ci: Optional[Sequence[int]] = None,
+              alg_co: Optional[int] = None, kind: Optional[str] = None) -> None:
+        """Emit one batched savsr_conv launch.  `alg_ci` / `alg_co`: ALGORITHMIC input channels per group / output channels,
+        where they differ from the padded GEMM shape (first layer: 3 and 6 of 64; tail: 3 of 16) -- the FLOP count of the
+        roofline uses the reference's channel counts, never the zero padding."""
         arr = (K.ConvGroup * len(groups))(*groups)
         self._keep.append(arr)
         skip_ref = C.byref(skip) if skip is not None else None
         lib, ctx, ah, n, impl = self.lib, self.ctx.handle, arena.handle, len(groups), self.impl
-        co = 64 if n_tile == 64 else (3 if dst_mode == K.DST_RGB else 16)      # real output channels
-        flops = 2.0 * self.B * arena.height * arena.width * co * ksize * ksize * sum(64 * g.nsrc for g in groups)
+        co = alg_co if alg_co is not None else (64 if n_tile == 64 else 16)      # real output channels
+        ci = list(alg_ci) if alg_ci is not None else [64 * g.nsrc for g in groups]
+        flops = 2.0 * self.B * arena.height * arena.width * co * ksize * ksize * sum(ci)
+        osa = any(g.weight_sample_stride != 0 for g in groups)
         self._emit(lambda st: lib.savsr_conv(ctx, ah, arr, n, ksize, n_tile, dst_mode, skip_ref, impl, st),
-                   kind=f"conv{ksize}x{ksize}_n{n_tile}", flops=flops, detail=f"g{n}s{groups[0].nsrc}")
+                   kind=kind or f"conv{ksize}x{ksize}_n{n_tile}", flops=flops,
+                   detail=f"g{n}s{groups[0].nsrc}" + ("osa" if osa else ""))
 
     def _tap(self, name: str, arena: str, slot: int) -> None:
         """Test/debug hook: if `name` was requested in `taps`, snapshot the slot (fp32 NCHW) right here in the
@@ -198,15 +235,18 @@ class Plan:
         ci, co = 64 * nsrc, 64
         att = max(int(ci * 0.0625), 16)
         a = prefix + ".attention"
-        bn_s = self._p(a + ".bn.weight") / torch.sqrt(self._p(a + ".bn.running_var") + BN_EPS)
-        bn_b = self._p(a + ".bn.bias") - self._p(a + ".bn.running_mean") * bn_s
+        def bn_s():
+            return self._p(a + ".bn.weight") / torch.sqrt(self._p(a + ".bn.running_var") + BN_EPS)
+
+        def bn_b():
+            return self._p(a + ".bn.bias") - self._p(a + ".bn.running_mean") * bn_s()
         o = K.OsaParams()
         o.ci, o.co, o.att = ci, co, att
         o.bank = self._ptr(prefix + ".weight")
         o.r0_w, o.r0_b = self._ptr(prefix + ".scale_routing.0.weight"), self._ptr(prefix + ".scale_routing.0.bias")
         o.r2_w, o.r2_b = self._ptr(prefix + ".scale_routing.2.weight"), self._ptr(prefix + ".scale_routing.2.bias")
         o.fc_w = self._ptr(a + ".fc.weight")
-        o.bn_scale, o.bn_shift = self._dev(bn_s), self._dev(bn_b)
+        o.bn_scale, o.bn_shift = self._dev(a + ".bn_scale", bn_s), self._dev(a + ".bn_shift", bn_b)
         o.ch_w, o.ch_b = self._ptr(a + ".channel_fc.weight"), self._ptr(a + ".channel_fc.bias")
         o.fl_w, o.fl_b = self._ptr(a + ".filter_fc.weight"), self._ptr(a + ".filter_fc.bias")
         o.sp_w, o.sp_b = self._ptr(a + ".spatial_fc.weight"), self._ptr(a + ".spatial_fc.bias")
@@ -282,9 +322,6 @@ class Plan:
         extra_needed = 5 + 5 + 5 + 1 + 2 + 1 + 6 + 2
         while len(pool_free) < extra_needed:
             pool_free.append(sl.get())
-        # fused kernel_conv + sta (default) keeps the 25 per-pixel kernels in TMEM; SAVSR_SATU_UNFUSED=1 materialises them
-        self.satu_unfused = os.environ.get("SAVSR_SATU_UNFUSED", "0") == "1"
-        kslot0 = sl.get_contiguous(25) if self.satu_unfused else -1
         self.n_lr_slots = sl.n
         self.arena_lr_t = self._buf(self.n_lr_slots * B, self.hp, self.wp, 64, dtype=torch.bfloat16)
         self.arena_lr_t[zero * B:(zero + 1) * B].zero_()
@@ -307,15 +344,22 @@ class Plan:
             fgroups = []
             for d, p in enumerate(dirs):
                 c = centre[d]
-                wc = torch.zeros(64, 64, 3, 3, device=self.device)
-                wc[:, 3 * c:3 * c + 3] = self._p(p + ".conv_c.weight")
-                ws = torch.zeros(64, 64, 3, 3, device=self.device)
-                wsup = self._p(p + ".conv_sup.weight")
-                ws[:, 3 * (c - 1):3 * (c - 1) + 3] = wsup[:, 0:3]
-                ws[:, 3 * (c + 1):3 * (c + 1) + 3] = wsup[:, 3:6]
-                fgroups.append(self._group([FR], S0[d][0], self._pack(wc), self._ptr(p + ".conv_c.bias"), act=L))
-                fgroups.append(self._group([FR], S0[d][1], self._pack(ws), self._ptr(p + ".conv_sup.bias"), act=L))
-            self._conv(lr, fgroups)
+
+                def wc(p=p, c=c):
+                    wz = torch.zeros(64, 64, 3, 3, device=self.device)
+                    wz[:, 3 * c:3 * c + 3] = self._p(p + ".conv_c.weight")
+                    return wz
+
+                def ws(p=p, c=c):
+                    wz = torch.zeros(64, 64, 3, 3, device=self.device)
+                    wsup = self._p(p + ".conv_sup.weight")
+                    wz[:, 3 * (c - 1):3 * (c - 1) + 3] = wsup[:, 0:3]
+                    wz[:, 3 * (c + 1):3 * (c + 1) + 3] = wsup[:, 3:6]
+                    return wz
+                fgroups.append(self._group([FR], S0[d][0], self._pack((p, "conv_c@", c), wc), self._ptr(p + ".conv_c.bias"), act=L))
+                fgroups.append(self._group([FR], S0[d][1], self._pack((p, "conv_sup@", c), ws), self._ptr(p + ".conv_sup.bias"), act=L))
+            # algorithmic input channels of these launches are 3 and 6, not the 64 of the zero-expanded filters
+            self._conv(lr, fgroups, alg_ci=[3, 6, 3, 6])
             cur = [[S0[d][0], S0[d][1], hpast[d]] for d in range(2)]
             sets = [S1, S2]
             for j in range(4):
@@ -385,18 +429,20 @@ class Plan:
             m = pa + ".mask"
 
             def fold(conv: str, bn: str):
-                sc = self._p(bn + ".weight") / torch.sqrt(self._p(bn + ".running_var") + BN_EPS)
-                wf = self._p(conv + ".weight") * sc.view(-1, 1, 1, 1)
-                bf = (self._p(conv + ".bias") - self._p(bn + ".running_mean")) * sc + self._p(bn + ".bias")
-                return wf, bf
+                """conv + eval-mode BatchNorm -> (lazy folded weight, lazy folded bias), cached in the weight store"""
+                def sc():
+                    return self._p(bn + ".weight") / torch.sqrt(self._p(bn + ".running_var") + BN_EPS)
+                return (lambda: self._p(conv + ".weight") * sc().view(-1, 1, 1, 1),
+                        lambda: (self._p(conv + ".bias") - self._p(bn + ".running_mean")) * sc() + self._p(bn + ".bias"))
             w0, b0 = fold(m + ".0", m + ".1")
             wa, ba = fold(m + ".4", m + ".5")
             wb, bb = fold(m + ".7", m + ".8")
             wc, bc = fold(m + ".11", m + ".12")
-            self._conv(lr, [self._group([R], 0, self._pack(w0, n_tile=16), self._dev(b0), act=K.ACT_RELU, aux=in16.data_ptr())],
-                       n_tile=16, dst_mode=K.DST_AUX16)
-            args = (ctx, in16.data_ptr(), B, self.hp, self.wp, self._dev(wa), self._dev(ba), self._dev(wb), self._dev(bb),
-                    self._dev(wc), self._dev(bc), half0.data_ptr(), half1.data_ptr(), maskb.data_ptr())
+            self._conv(lr, [self._group([R], 0, self._pack(m + ".0+bn", w0, n_tile=16), self._dev(m + ".0+bn.bias", b0), act=K.ACT_RELU,
+                                        aux=in16.data_ptr())], n_tile=16, dst_mode=K.DST_AUX16)
+            args = (ctx, in16.data_ptr(), B, self.hp, self.wp, self._dev(m + ".4+bn.w", wa), self._dev(m + ".4+bn.b", ba),
+                    self._dev(m + ".7+bn.w", wb), self._dev(m + ".7+bn.b", bb), self._dev(m + ".11+bn.w", wc), self._dev(m + ".11+bn.b", bc),
+                    half0.data_ptr(), half1.data_ptr(), maskb.data_ptr())
             self._emit(lambda st, args=args: lib.savsr_osadapt_mask(*args, st), launches=3, kind="osadapt_mask")
             osa = self._osa_params(pa + ".adapt", 1, [plr])
             self._osa_prologue([osa[0]])
@@ -409,19 +455,15 @@ class Plan:
 
         # ---- 4. SATU (savsr_arch.py:315-376) + tail + bilinear skip (738-739)
         u = "upsample"
-        wk = self._p(u + ".kernel_conv.0.weight").view(64, 25, 64).permute(1, 0, 2).reshape(1600, 64, 1, 1)   # tap-major
-        bk = self._p(u + ".kernel_conv.0.bias").view(64, 25).t().contiguous()
-        wkp = self._pack(wk)
-        bkp = self._dev(bk)
+        wkp = self._pack(u + ".kernel_conv.tapmajor",
+                         lambda: self._p(u + ".kernel_conv.0.weight").view(64, 25, 64).permute(1, 0, 2).reshape(1600, 64, 1, 1))
+        bkp = self._dev(u + ".kernel_conv.tapmajor.bias", lambda: self._p(u + ".kernel_conv.0.bias").view(64, 25).t().contiguous())
         STA, = take(1)
         lrh, hrh, hh, ww = lr.handle, hr.handle, self.h, self.w
-        if self.satu_unfused:
-            self._conv(lr, [self._group([A], kslot0 + tp, wkp + tp * 8192, bkp + tp * 256, act=L, slope=0.1) for tp in range(25)], ksize=1)
-            self._emit(lambda st: lib.savsr_satu_sta(ctx, lrh, TR, kslot0, STA, hh, ww, st), kind="satu_sta")
-        else:
-            kflops = 2.0 * B * self.hp * self.wp * 64 * 1600
-            self._emit(lambda st: lib.savsr_satu_kconv_sta(ctx, lrh, A, TR, STA, hh, ww, wkp, bkp, 0.1, st), kind="satu_kconv_sta",
-                       flops=kflops)
+        # kernel_conv + sta_conv in one kernel: the 25 per-pixel kernels stay in TMEM (savsr_arch.py:297-313, 326)
+        kflops = 2.0 * B * self.hp * self.wp * 64 * 1600
+        self._emit(lambda st: lib.savsr_satu_kconv_sta(ctx, lrh, A, TR, STA, hh, ww, wkp, bkp, 0.1, st), kind="satu_kconv_sta",
+                   flops=kflops)
         self._tap("satu_sta", "lr", STA)
         sw = K.SatuWeights()
         sw.body0_w, sw.body0_b = self._ptr(u + ".body.0.weight"), self._ptr(u + ".body.0.bias")
@@ -441,13 +483,15 @@ class Plan:
         K.check(lib.savsr_satu_index(ctx, C.byref(sw), self.h, self.w, H, W, float(self.scale[0]), float(self.scale[1]),
                                      self.rel_y.data_ptr(), self.rel_x.data_ptr(), self.cell_y.data_ptr(), self.cell_x.data_ptr(),
                                      self.base_y.data_ptr(), self.base_x.data_ptr(), self.corner_y.data_ptr(),
-                                     self.corner_x.data_ptr(), self.table.data_ptr(), torch.cuda.current_stream().cuda_stream))
+                                     self.corner_x.data_ptr(), self.table.data_ptr(), self._stream().cuda_stream))
         tab, by, bx = self.table.data_ptr(), self.base_y.data_ptr(), self.base_x.data_ptr()
         # HR stage: gather + routed experts + 128->64 fusion in one tensor-core kernel (savsr_arch.py:364-374)
-        wc_all = self._p(u + ".weight_compress").reshape(32, 64, 1, 1)                               # rows e*8+k
-        we_all = torch.zeros(64, 64, 1, 1, device=self.device)
-        we_all[:, :32, 0, 0] = self._p(u + ".weight_expand").view(4, 64, 8).permute(1, 0, 2).reshape(64, 32)   # cols e*8+k
-        pwc, pwe = self._pack(wc_all, n_tile=16), self._pack(we_all, rows=K.ROWS_LINEAR)
+        def we_all():
+            wz = torch.zeros(64, 64, 1, 1, device=self.device)
+            wz[:, :32, 0, 0] = self._p(u + ".weight_expand").view(4, 64, 8).permute(1, 0, 2).reshape(64, 32)   # cols e*8+k
+            return wz
+        pwc = self._pack(u + ".compress_all", lambda: self._p(u + ".weight_compress").reshape(32, 64, 1, 1), n_tile=16)   # rows e*8+k
+        pwe = self._pack(u + ".expand_all", we_all, rows=K.ROWS_LINEAR)
         pwf = self._packp(u + ".fusion.weight")                       # QUAD rows: same 16x256b epilogue as the convs
         fb = self._ptr(u + ".fusion.bias")
         self._emit(lambda st: lib.savsr_satu_fused(ctx, lrh, TR, STA, hh, ww, hrh, 0, tab, by, bx, pwc, pwe, pwf, fb, st),
@@ -455,38 +499,49 @@ class Plan:
         self._tap("satu_out", "hr", 0)
         skip = K.RgbSkip(); skip.x = xin; skip.t = t; skip.centre = t // 2; skip.h = self.h; skip.w = self.w
         self._keep.append(skip)
-        bt = torch.zeros(16, device=self.device); bt[:3] = self._p("tail.bias")
-        self._conv(hr, [self._group([0], 0, self._pack(self._p("tail.weight"), n_tile=16, co_pad=16), self._dev(bt),
-                                    aux=self.out.data_ptr())], n_tile=16, dst_mode=K.DST_RGB, skip=skip)
-        torch.cuda.current_stream().synchronize()
+        def bt():
+            z = torch.zeros(16, device=self.device); z[:3] = self._p("tail.bias")
+            return z
+        self._conv(hr, [self._group([0], 0, self._pack("tail.weight@16", lambda: self._p("tail.weight"), n_tile=16, co_pad=16),
+                                    self._dev("tail.bias@16", bt), aux=self.out.data_ptr())], n_tile=16, dst_mode=K.DST_RGB, skip=skip,
+                   alg_co=3)
+        self._stream().synchronize()
+        self._pack_src.clear()
 
     # ------------------------------------------------------------------ execution
+    # Every entry point below runs under torch.cuda.device(self.device) and takes the current stream OF THAT DEVICE, so a
+    # module on cuda:1 works while the caller's current device is cuda:0 (the C launchers also switch device themselves).
+    def _stream(self) -> "torch.cuda.Stream":
+        return torch.cuda.current_stream(self.device)
+
     def run(self) -> None:
-        """Launch the whole forward on the current stream (x_in -> out)."""
-        self.ctx.set_format(self.fmt)           # the format is context state read at launch (baked into captured graphs)
-        st = torch.cuda.current_stream().cuda_stream
-        for op in self.ops:
-            rc = op(st)
-            if rc:
-                K.check(rc)
+        """Launch the whole forward on the device's current stream (x_in -> out)."""
+        with torch.cuda.device(self.device):
+            self.ctx.set_format(self.fmt)           # the format is context state read at launch (baked into captured graphs)
+            st = self._stream().cuda_stream
+            for op in self.ops:
+                rc = op(st)
+                if rc:
+                    K.check(rc)
 
     def run_profiled(self, detail: bool = False) -> Dict[str, Dict[str, float]]:
         """Eager run with a CUDA-event pair around every op on the launching stream.
         Returns {kind: {"ms": total device ms, "flops": algorithmic FLOPs, "ops": count, "launches": kernels}};
-        with `detail` the conv kinds are further split by (groups per launch, sources per group)."""
-        self.ctx.set_format(self.fmt)
-        stream = torch.cuda.current_stream()
-        st = stream.cuda_stream
-        evs = []
-        for op in self.ops:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            rc = op(st)
-            e1.record(stream)
-            if rc:
-                K.check(rc)
-            evs.append((e0, e1))
-        stream.synchronize()
+        with `detail` the conv kinds are further split by (groups per launch, sources per group, "osa" = per-sample weights)."""
+        with torch.cuda.device(self.device):
+            self.ctx.set_format(self.fmt)
+            stream = self._stream()
+            st = stream.cuda_stream
+            evs = []
+            for op in self.ops:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                rc = op(st)
+                e1.record(stream)
+                if rc:
+                    K.check(rc)
+                evs.append((e0, e1))
+            stream.synchronize()
         out: Dict[str, Dict[str, float]] = {}
         for (kind, flops, launches, tag), (e0, e1) in zip(self.op_meta, evs):
             d = out.setdefault(f"{kind}:{tag}" if (detail and tag) else kind, dict(ms=0.0, flops=0.0, ops=0, launches=0))
@@ -497,17 +552,42 @@ class Plan:
         """Capture run() into a CUDA graph (after one eager warm-up that sets kernel attributes)."""
         if self.graph is not None:
             return
-        self.run()
-        torch.cuda.synchronize(self.device)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.device(self.device):
             self.run()
-        self.graph = g
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.run()
+            self.graph = g
 
     def run_graph(self) -> None:
         if self.graph is None:
             self.capture()
-        self.graph.replay()
+        with torch.cuda.device(self.device):
+            self.graph.replay()
+
+    def forward_into(self, x: torch.Tensor, out: torch.Tensor, graph: bool = True) -> None:
+        """x [B,7,3,h,w] fp32 -> out [B,3,H,W] fp32 through the plan's staging buffers (graph replay reads / writes fixed
+        addresses), all on the device's current stream."""
+        with torch.cuda.device(self.device):
+            self.x_in.copy_(x, non_blocking=True)
+            if graph:
+                self.run_graph()
+            else:
+                self.run()
+            out.copy_(self.out, non_blocking=True)
+
+    def release(self) -> None:
+        """Drop the CUDA graph and every device buffer now (plan-cache eviction), instead of waiting for the collector."""
+        self.graph = None
+        self.ops.clear()
+        self._keep.clear()
+        self._pack_src.clear()
+        self.tap_bufs.clear()
+        for name in ("arena_lr_t", "arena_hr_t", "x_in", "out", "table", "lr", "hr"):
+            if hasattr(self, name):
+                setattr(self, name, None)
+        self.nbytes = 0
 
     def read_tap(self, name: str) -> torch.Tensor:
         """fp32 NCHW snapshot of a named intermediate requested via `taps` (test / debug only)."""

@@ -32,7 +32,6 @@ CHECKS = {
     "conv_per_sample_halo": "check_osa_conv_per_sample(impl=K.IMPL_HALO)",
     "conv_rgb": "check_conv_rgb()",
     "conv_per_sample": "check_osa_conv_per_sample()",
-    "front_conv": "check_front_conv()",
     "pack_frames": "check_pack_frames()",
     "osa_prologue_192": "check_osa_prologue(ci=192)",
     "osa_prologue_320": "check_osa_prologue(ci=320, B=1)",

@@ -74,6 +74,7 @@ class CpuPlan(engine.Plan):
         self.P = params
         self._keep, self.ops, self.op_meta, self.n_launches = [], [], [], 0
         self.taps, self.tap_bufs, self.graph = set(kw.get("taps", ())), {}, None
-        self._pack_cache, self._pool_cache, self._osa_cache = {}, {}, {}
+        self._pool_cache, self._osa_cache = {}, {}
+        self.store, self.nbytes, self._pack_src = kw.get("store") or engine.WeightStore(), 0, []
         with torch.no_grad():
             orig_build()

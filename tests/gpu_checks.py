@@ -270,26 +270,6 @@ def check_pack_roundtrip():
 
 
 # ------------------------------------------------------------------------------------------------ small ops
-def check_front_conv(B=2, h=13, w=15, seed=5):
-    """conv_c / conv_sup on the reflect-padded fp32 window (savsr_arch.py:456-457, 670-690)."""
-    torch.manual_seed(seed)
-    hp, wp = h + (h & 1), w + (w & 1)
-    ab = ArenaBox(2, B, hp, wp)
-    x = torch.rand(B, 7, 3, h, w, device=DEV)
-    wc = torch.randn(64, 3, 3, 3, device=DEV) * 0.2
-    bc = torch.randn(64, device=DEV) * 0.1
-    ws = torch.randn(64, 6, 3, 3, device=DEV) * 0.2
-    bs = torch.randn(64, device=DEV) * 0.1
-    g0 = K.FrontGroup(); g0.frame[0] = 4; g0.nframes = 1; g0.dst_slot = 0; g0.weight = wc.data_ptr(); g0.bias = bc.data_ptr()
-    g1 = K.FrontGroup(); g1.frame[0] = 3; g1.frame[1] = 5; g1.nframes = 2; g1.dst_slot = 1; g1.weight = ws.data_ptr(); g1.bias = bs.data_ptr()
-    arr = (K.FrontGroup * 2)(g0, g1)
-    K.check(K.load().savsr_front_conv(ctx().handle, ab.a.handle, x.data_ptr(), 7, h, w, arr, 2, _stream()))
-    xp = F.pad(x.reshape(-1, 3, h, w), [0, wp - w, 0, hp - h], mode="reflect").view(B, 7, 3, hp, wp) if (hp != h or wp != w) else x
-    ref0 = F.leaky_relu(F.conv2d(xp[:, 4], wc, bc, padding=1), 0.2)
-    ref1 = F.leaky_relu(F.conv2d(torch.cat([xp[:, 3], xp[:, 5]], 1), ws, bs, padding=1), 0.2)
-    return dict(conv_c=assert_close("front conv_c", ab.get(0), ref0), conv_sup=assert_close("front conv_sup", ab.get(1), ref1))
-
-
 def check_pack_frames(B=2, h=13, w=15, seed=11):
     """savsr_pack_frames + zero-expanded filters on the tensor-core conv == conv_c / conv_sup of the reference."""
     torch.manual_seed(seed)
@@ -480,24 +460,6 @@ def check_satu_table(h=13, w=15, scale=(2.7, 1.5), seed=1):
     return dict(table=assert_close("satu table", res["table"], ref, rel=1e-4, abs_=2e-6))
 
 
-def check_satu_sta(B=2, h=13, w=15, seed=9):
-    """sta_conv with replicate padding on the unpadded region (savsr_arch.py:297-313)."""
-    from oracle import savsr_oracle as O
-    torch.manual_seed(seed)
-    hp, wp = h + (h & 1), w + (w & 1)
-    ab = ArenaBox(27, B, hp, wp)
-    x = bf16_round(torch.randn(B, 64, hp, wp, device=DEV))
-    kern = bf16_round(torch.randn(B, 1600, hp, wp, device=DEV) * 0.2)       # reference layout: channel c*25 + tap
-    ab.put(0, x)
-    kt = kern.view(B, 64, 25, hp, wp)
-    for tp in range(25):
-        ab.put(1 + tp, kt[:, :, tp].contiguous())
-    K.check(K.load().savsr_satu_sta(ctx().handle, ab.a.handle, 0, 1, 26, h, w, _stream()))
-    ref = O.satu_sta_conv(x[..., :h, :w].cpu(), kern[..., :h, :w].cpu())
-    got = ab.get(26)[..., :h, :w]
-    return dict(sta=assert_close("satu sta", got, ref))
-
-
 def check_satu_kconv_sta(B=2, h=13, w=15, seed=19):
     """kernel_conv (1x1 64 -> 1600, LeakyReLU 0.1) + sta_conv in one kernel, kernels consumed from TMEM
     (savsr_arch.py:297-313, 326), vs the oracle's two-step restatement on the same (bf16-rounded) operands."""
@@ -522,33 +484,6 @@ def check_satu_kconv_sta(B=2, h=13, w=15, seed=19):
     got = full[..., :h, :w]
     assert float(full[..., h:, :].abs().max() if hp > h else 0.0) == 0.0 and float(full[..., :, w:].abs().max() if wp > w else 0.0) == 0.0
     return dict(sta=assert_close("fused kernel_conv + sta", got, ref))
-
-
-def check_satu_gather(B=2, h=13, w=15, scale=(2.7, 1.5), seed=1):
-    """Fused HR gather + routed experts vs the oracle (savsr_arch.py:262-295, 353-373)."""
-    from oracle import savsr_oracle as O
-    from oracle.state_dict_fixture import make_state_dict
-    sd = make_state_dict(seed)
-    # exaggerate the learned offsets so that corners move and the zero-padding border is exercised
-    sd["upsample.offset.weight"] = sd["upsample.offset.weight"] * 8
-    sd["upsample.st_offset.weight"] = sd["upsample.st_offset.weight"] * 8
-    torch.manual_seed(seed)
-    hp, wp = h + (h & 1), w + (w & 1)
-    res, H, W = satu_index(h, w, scale, sd)
-    lr = ArenaBox(2, B, hp, wp)
-    hr = ArenaBox(2, B, H, W)
-    x = bf16_round(torch.randn(B, 64, hp, wp, device=DEV)); sta = bf16_round(torch.randn(B, 64, hp, wp, device=DEV))
-    lr.put(0, x); lr.put(1, sta)
-    sw, keep = _satu_weights(sd)
-    table = res["table"].to(DEV); by = torch.from_numpy(res["base_y"]).to(DEV); bx = torch.from_numpy(res["base_x"]).to(DEV)
-    K.check(K.load().savsr_satu_gather(ctx().handle, lr.a.handle, 0, 1, h, w, hr.a.handle, 0, 1, table.data_ptr(), by.data_ptr(),
-                                       bx.data_ptr(), C.byref(sw), _stream()))
-    off, st_off, r = O.satu_heads(sd, "upsample", h, w, scale)
-    xc, sc = x[..., :h, :w].cpu(), sta[..., :h, :w].cpu()
-    fea0 = O.satu_gather(xc, scale, off)
-    fea = O.satu_expert_mix(sd, "upsample", fea0, r)
-    sta_s = O.satu_gather(sc, scale, st_off)
-    return dict(sta_sampled=assert_close("gather sta", hr.get(0), sta_s), fea=assert_close("gather fea", hr.get(1), fea))
 
 
 def check_satu_fused(B=2, h=13, w=15, scale=(2.7, 1.5), seed=1):

@@ -64,12 +64,12 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/savsr_b200.h but not exported"
     assert declared == set(_capi.SIGNATURES), declared ^ set(_capi.SIGNATURES)
-    assert lib.savsr_abi_version() == 2
+    assert lib.savsr_abi_version() == _capi.ABI_VERSION == 3
 
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_capi.ConvGroup) == 96 and _capi.ConvGroup.weight.offset == 48
-    assert ctypes.sizeof(_capi.RgbSkip) == 24 and ctypes.sizeof(_capi.FrontGroup) == 32
+    assert ctypes.sizeof(_capi.RgbSkip) == 24
     assert _capi.OsaParams.pool.offset == 16 + 16 * 8 and ctypes.sizeof(_capi.SatuWeights) == 96
 
 

