@@ -4,22 +4,29 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload vid4_x4] [--batch B]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-A "step" = super-resolving one synthetic Vid4-shaped clip (34 frames, 144x180 LR -> 576x720 HR at x4;
-every output frame is an independent 7-frame window, lbasicsr/models/video_base_model.py:50-59), in batches
-of `--batch` windows.  With N GPUs every rank processes its own clip (frames shard with no data-path
-collective; weak scaling).  Rank 0 prints ONE JSON line:
+A "step" = super-resolving one synthetic Vid4-shaped clip (34 frames, 144x180 LR -> 576x720 HR at x4; every output frame is
+an independent 7-frame window, lbasicsr/models/video_base_model.py:50-59), in batches of `--batch` windows.  With N GPUs every
+rank processes its own clip (frames shard with no data-path collective; weak scaling).  Rank 0 prints ONE JSON line:
 
-  value      HR Mpix/s, whole job, windows already resident in HBM when the timed region starts
-  e2e        same metric through the public API (savsr_b200.sharding.infer_clip on the savsr_b200.SAVSR module) with
-             the LR clip in pinned HOST memory and the HR result copied back to pinned host memory every step
-  roofline   dominant kernel (tcgen05 implicit-GEMM conv, N = 64): algorithmic FLOPs / CUDA-event time of those launches
-             measured live in an eager pass, against the measured bf16 peak of MEASURED_PEAKS.json
-  cpu_baseline  the oracle (CPU restatement of the reference, kind "port") on the host cores, bounded sample
-  pipeline   (informational) the reference's whole test loop minus the PNG codec through savsr_b200.datapath.evaluate_clip:
-             uint8 ground-truth frames in pinned host memory -> device LR synthesis -> net -> uint8 images + PSNR-Y + SSIM-Y
+  value         HR Mpix/s, whole job, windows already resident in HBM when the timed region starts
+  e2e           same metric through the public API (savsr_b200.sharding.infer_clip on the savsr_b200.SAVSR module) with the
+                LR clip in pinned HOST memory and the HR result copied back to pinned host memory every step
+  roofline      dominant kernel (tcgen05 implicit-GEMM 3x3 conv, N = 64): ALGORITHMIC FLOPs (reference channel counts, no zero
+                padding) / CUDA-event time of those launches, measured live in an eager pass, against the measured bf16 peak
+  roofline_osa  the same for the OSA-Conv launches alone (per-sample folded weights; north star: >= 60 % of the tensor peak)
+  roofline_satu SATU chain (kernel_conv+sta, HR gather/experts/fusion/tail): compulsory bytes / time vs the HBM peak AND
+                FLOPs / time vs the tensor peak (SATU is compute-bound under the compulsory byte count)
+  fp16          the same resident measurement with fp16 operands (the path that meets the <= 1e-3 fp32 criterion)
+  latency_b1    one window per call through SAVSR.forward (what lbasicsr/test.py does), VSR_runtime_test protocol
+  gpu_reference the reference's own PyTorch/cuDNN path on THIS GPU (cudnn.benchmark, TF32 on/off), b = 1 and b = batch
+  cfg4_strong   BASELINE config 4: 10 UDM10-shaped clips x 32 frames (320 frames, 180x318 -> 720x1272), FIXED work sharded
+                rank-strided over the N ranks (strong scaling), with the reference's metric reduction (dist.reduce of
+                [n_frames, n_metrics]) and, second figure, the gather of all HR frames to rank 0 inside the timed region
+  cpu_baseline  the reference's CPU path on the host cores, bounded sample
+  pipeline      (informational) the reference's whole test loop minus the PNG codec through savsr_b200.datapath.evaluate_clip
 
---impl reference times the reference's own CPU path (the pinned oracle port; the reference itself is a Python
-package that is not present on the GPU box) on this arm's workload/metric, rank 0 only.
+--impl reference times the reference's own CPU implementation of the path (the unmodified reference installed under
+baseline/_ref when present, else the pinned oracle port) on this arm's workload / metric, rank 0 only.
 """
 from __future__ import annotations
 
@@ -44,12 +51,37 @@ WORKLOADS = {  # name: (frames, h, w, scale)
     "udm10_x4": (32, 180, 318, (4, 4)),
     "cfg1_x2": (7, 64, 64, (2, 2)),
 }
+YAML_KWARGS = dict(num_in_ch=3, num_feat=64, num_frame=7, slid_win=3, fusion_win=5, interval=0, w1_num_block=4, w2_num_block=2,
+                   n_resgroups=4, n_resblocks=8, center_frame_idx=None)     # options/test/SAVSR/test_SAVSR_Vid4_asBI.yml:830-842
+SATU_KINDS = ("satu_kconv_sta", "satu_fused", "satu_hr", "satu_tail")
+
+
+def hw_out(h, w, scale):
+    return round(h * scale[0]), round(w * scale[1])          # savsr_arch.py:745-751 (python round)
 
 
 def flops_per_frame(h, w, H, W):
     """F = 2 * [22 888 128 hp wp + 104 000 h w + 19 904 H W]."""
     hp, wp = h + (h & 1), w + (w & 1)
     return 2.0 * (22888128.0 * hp * wp + 104000.0 * h * w + 19904.0 * H * W)
+
+
+def satu_flops_per_frame(h, w, H, W):
+    """kernel_conv 102 400 + sta_conv 1 600 MAC per LR px; body + heads + expert mix + fusion 18 176 and tail 1 728 per HR px."""
+    return 2.0 * (104000.0 * h * w + 19904.0 * H * W)
+
+
+def satu_compulsory_bytes(h, w, H, W):
+    """B_SATU = 4 (64 hw [x] + 64 hw [st_feat] + 3 hw [x_center] + 3 HW [out]) per frame (+0.49 MB of parameters per launch)."""
+    return 4.0 * (2 * 64 * h * w + 3 * h * w + 3 * H * W)
+
+
+def workload_config(name, world):
+    """The `config` object both arms print (identical keys and values, so the driver's same_config check holds)."""
+    frames, h, w, scale = WORKLOADS[name]
+    H, W = hw_out(h, w, scale)
+    return {"workload": name, "frames_per_clip": frames, "clips": world, "lr": [h, w], "hr": [H, W], "scale": list(scale),
+            "weights": "random init (seed 0)", "parallelism": f"frame-sharded x{world}, no data-path collective"}
 
 
 class ClockSampler(threading.Thread):
@@ -123,49 +155,229 @@ def measured_peaks():
     return dict(bf16_sustained=1400.0, bf16_burst=1590.0, hbm_gbs=6650.0, source="fallback")
 
 
-def cpu_oracle_time(sd_cpu, frames, h, w, scale, threads=None):
-    """Time the CPU oracle (restatement of the reference) on `frames` windows; returns (HR Mpix/s, seconds, threads)."""
-    from oracle import savsr_oracle as O           # only this leg of bench.py may touch oracle/
+# ------------------------------------------------------------------------------------------------ the reference itself
+def load_reference(state_dict=None, device="cpu"):
+    """The UNMODIFIED reference arch (lbasicsr/archs/savsr_arch.py) from baseline/_ref -- the offline install of /root/reference
+    (`pip install --no-index --no-deps --target baseline/_ref`, git-ignored, travels to the GPU box).  Returns (module, "reference"),
+    or (None, reason) when it is not installed / not importable."""
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_root, "lbasicsr")):
+        return None, "baseline/_ref not installed"
+    try:
+        if ref_root not in sys.path:
+            sys.path.insert(0, ref_root)
+        import logging
+        logging.disable(logging.INFO)
+        from lbasicsr.archs import build_network               # lbasicsr/archs/__init__.py:19-28
+        torch.manual_seed(0)
+        ref = build_network(dict(type="SAVSR", **YAML_KWARGS)).eval()
+        logging.disable(logging.NOTSET)
+        if state_dict is not None:
+            ref.load_state_dict({k: v.detach().cpu() for k, v in state_dict.items()}, strict=True)
+        return ref.to(device), "reference"
+    except Exception as e:  # noqa: BLE001 -- any import problem of the optional tree just selects the port
+        return None, f"baseline/_ref not importable: {type(e).__name__}: {e}"
+
+
+def cpu_reference_time(sd_cpu, frames, h, w, scale, threads=None):
+    """Time the reference's CPU path on `frames` windows: the real reference when baseline/_ref is importable (kind
+    "reference"), else the oracle port.  Returns (HR Mpix/s, seconds, threads, kind)."""
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    H, W = O.get_hw(h, w, scale)
+    H, W = hw_out(h, w, scale)
     x = torch.rand(1, 7, 3, h, w, generator=torch.Generator().manual_seed(1234))
+    ref, kind = load_reference(sd_cpu)
+    if ref is not None:
+        ref.set_scale(tuple(scale))
+        run = lambda inp: ref(inp)                  # noqa: E731
+    else:
+        from oracle import savsr_oracle as O           # only the CPU-baseline legs of bench.py may touch oracle/
+        kind = "port"
+        run = lambda inp: O.forward(sd_cpu, inp, scale)   # noqa: E731
     with torch.no_grad():
-        O.forward(sd_cpu, x[:, :, :, : min(h, 32), : min(w, 32)].contiguous(), scale)   # warm-up (thread pool, oneDNN primitives)
+        run(x[:, :, :, : min(h, 32), : min(w, 32)].contiguous())    # warm-up (thread pool, oneDNN primitives)
         t0 = time.perf_counter()
         for _ in range(frames):
-            O.forward(sd_cpu, x, scale)
+            run(x)
         dt = time.perf_counter() - t0
-    return frames * H * W / dt / 1e6, dt, threads
+    return frames * H * W / dt / 1e6, dt, threads, kind
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path (oracle port) on the host cores, rank 0 only."""
+    """--impl reference: the reference's CPU implementation of the path on the host cores, rank 0 only."""
     if rank != 0:
         return
     import savsr_b200
     frames, h, w, scale = WORKLOADS[args.workload]
     torch.manual_seed(0)
     sd = {k: v.detach().clone() for k, v in savsr_b200.SAVSR().state_dict().items()}
-    H, W = savsr_b200.get_HW(h, w, scale)
+    H, W = hw_out(h, w, scale)
     per_step = 1                                     # bounded sample: one output frame (one 7-frame window) per step
     for _ in range(min(args.warmup, 1)):
-        cpu_oracle_time(sd, 1, h, w, scale)
-    t_total, n = 0.0, 0
+        cpu_reference_time(sd, 1, h, w, scale)
+    t_total, n, kind, threads = 0.0, 0, "port", 1
     for _ in range(args.steps):
-        _, dt, threads = cpu_oracle_time(sd, per_step, h, w, scale)
+        _, dt, threads, kind = cpu_reference_time(sd, per_step, h, w, scale)
         t_total += dt; n += per_step
     val = n * H * W / t_total / 1e6
-    sample = f"{per_step} output frame(s) of the {args.workload} clip per step ({h}x{w} LR -> {H}x{W}), fp32, {threads} threads"
+    what = ("the unmodified reference (baseline/_ref, lbasicsr/archs/savsr_arch.py) on CPU" if kind == "reference"
+            else "oracle port of lbasicsr/archs/savsr_arch.py (pinned to the reference by tests/golden)")
+    sample = f"{per_step} output frame(s) of the {args.workload} clip per step ({h}x{w} LR -> {H}x{W}), fp32, {threads} threads; {what}"
     print(json.dumps({
         "impl": "reference", "metric": "hr_mpix_per_s", "value": round(val, 5), "unit": "HR Mpix/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * t_total / args.steps, 2), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "frames_per_clip": frames, "lr": [h, w], "hr": [H, W], "scale": list(scale),
-                   "note": "reference CPU path = oracle port of lbasicsr/archs/savsr_arch.py (pinned to the reference by tests/golden)"},
-        "cpu_baseline": {"value": round(val, 5), "unit": "HR Mpix/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": workload_config(args.workload, args.gpus),
+        "cpu_baseline": {"value": round(val, 5), "unit": "HR Mpix/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": round(val, 5), "unit": "HR Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+# ------------------------------------------------------------------------------------------------ GPU-side reference
+def vsr_runtime(fn, warm, reps):
+    """lbasicsr/metrics/runtime.py:36-66: warm-up, then per repetition an event pair + synchronize, mean ms (fewer repetitions
+    than the reference's 100 / 300 so that the default bench run stays short; stated in the output)."""
+    with torch.no_grad():
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+    return sum(ts) / len(ts)
+
+
+def gpu_reference(net, dev, h, w, scale, B):
+    """The reference's own path on this GPU: the unmodified reference module (baseline/_ref) -- else the oracle port -- on CUDA
+    with cudnn.benchmark = True (lbasicsr/test.py:15), TF32 convs on (PyTorch default = what the reference runs) and off."""
+    H, W = hw_out(h, w, scale)
+    sd = net.state_dict()
+    ref, kind = load_reference(sd, dev)
+    if ref is not None:
+        ref.set_scale(tuple(scale))
+        fwd = lambda x: ref(x)                       # noqa: E731
+    else:
+        from oracle import savsr_oracle as O            # device-aware restatement: the same ATen / cuDNN calls
+        note = kind
+        kind = "port"
+        sd_dev = {k: v.detach().to(dev) for k, v in sd.items()}
+        fwd = lambda x: O.forward(sd_dev, x, scale)  # noqa: E731
+    out = {"kind": kind, "protocol": "VSR_runtime_test (lbasicsr/metrics/runtime.py:36-66) with 10 warm-up + 30 repetitions at b=1, "
+                                     "2 + 3 at the batched size; cudnn.benchmark=True", "lr": [h, w], "hr": [H, W]}
+    if ref is None:
+        out["note"] = note
+    saved = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32)
+    torch.backends.cudnn.benchmark = True
+    x1 = torch.rand(1, 7, 3, h, w, device=dev, generator=torch.Generator(device=dev).manual_seed(1234))
+    xb = torch.rand(B, 7, 3, h, w, device=dev, generator=torch.Generator(device=dev).manual_seed(1235))
+    try:
+        for tf32 in (True, False):
+            torch.backends.cudnn.allow_tf32 = tf32
+            tag = "tf32" if tf32 else "fp32"
+            ms1 = vsr_runtime(lambda: fwd(x1), 10, 30)
+            out[f"b1_{tag}_ms"] = round(ms1, 3)
+            out[f"b1_{tag}_hr_mpix_s"] = round(H * W / ms1 / 1e3, 2)
+            try:
+                msb = vsr_runtime(lambda: fwd(xb), 2, 3)
+                out[f"b{B}_{tag}_ms"] = round(msb, 3)
+                out[f"b{B}_{tag}_hr_mpix_s"] = round(B * H * W / msb / 1e3, 2)
+            except torch.OutOfMemoryError as e:
+                out[f"b{B}_{tag}_error"] = f"OOM: {str(e)[:80]}"
+                torch.cuda.empty_cache()
+        # parity against the reference's own GPU arithmetic with TF32 off (informational; the gate is the CPU oracle)
+        torch.backends.cudnn.allow_tf32 = False
+        with torch.no_grad():
+            net.set_scale(scale)
+            y_ref = fwd(x1)
+            out["max_abs_ours_vs_gpu_reference_fp32"] = float((net(x1) - y_ref).abs().max())
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32 = saved
+        del ref
+        torch.cuda.empty_cache()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE config 4, strong scaling
+def run_cfg4(net, dev, rank, world, timed, steps=2, warmup=1, B=8):
+    """10 UDM10-shaped clips x 32 frames at x4, FIXED total work, sharded rank-strided over the ranks exactly like the
+    reference's loop (video_base_model.py:50: `for idx in range(rank, len(dataset), world_size)`), metrics on the device and
+    the reference's reduction (`dist.reduce` of [n_frames, n_metrics], video_base_model.py:106-113) inside the timed region."""
+    import torch.distributed as dist
+    from savsr_b200 import postproc, sharding
+    clips, T, h, w, scale = 10, 32, 180, 318, (4, 4)
+    H, W = hw_out(h, w, scale)
+    n_frames = clips * T
+    mine = sharding.shard_frames(n_frames, rank, world)
+    net.set_scale(scale)
+    lr_all = torch.rand(n_frames, 3, h, w, generator=torch.Generator().manual_seed(4321)).to(dev)     # identical on every rank
+    # 7-frame window of dataset item idx = frames of ITS clip with reflection padding at the clip ends (data_util.py:63-112)
+    widx = torch.tensor([[(i // T) * T + t for t in sharding.frame_window_indices(i % T, T)] for i in mine], device=dev)
+    gt = torch.rand(B, 3, H, W, device=dev, generator=torch.Generator(device=dev).manual_seed(99))   # synthetic ground truth, reused per batch
+    local_out = torch.empty(len(mine), 3, H, W, device=dev)
+    full_out = torch.empty(n_frames, 3, H, W, device=dev) if rank == 0 else None
+    batches = [(a, min(a + B, len(mine))) for a in range(0, len(mine), B)]
+    with torch.no_grad():
+        plans = {b - a: net.plan_for(lr_all[widx[a:b].reshape(-1)].view(b - a, 7, 3, h, w)) for a, b in batches}
+        for p in plans.values():
+            p.capture()
+    if len(mine) * world != n_frames or len(mine) % B:
+        raise RuntimeError("cfg4: 320 frames must divide evenly over the ranks and into batches of 8 (1/2/4/8 ranks do)")
+    n_local = len(mine)
+    # rank 0 receives every batch of every rank into its own buffer (no reuse hazards), then assembles clip order:
+    # global frame = rank + world * local index, i.e. full_out viewed as [n_local, world, ...]
+    recv = torch.empty(len(batches), world, B, 3, H, W, device=dev) if (rank == 0 and world > 1) else None
+    state = {}
+
+    def step(gather):
+        rows, works = [], []
+        with torch.no_grad():
+            for j, (a, b) in enumerate(batches):
+                win = lr_all[widx[a:b].reshape(-1)].view(b - a, 7, 3, h, w)
+                plans[b - a].forward_into(win, local_out[a:b])
+                _, psnr = postproc.tensor2img_psnr(local_out[a:b], gt[:b - a], want_image=False)
+                ssim = postproc.ssim_y(local_out[a:b], gt[:b - a])
+                rows.append(torch.stack([psnr, ssim], 1).float())
+                if gather and world > 1:      # this batch's frames travel to rank 0 while the next batch computes (NCCL's own stream)
+                    works.append(dist.gather(local_out[a:b], list(recv[j].unbind(0)) if rank == 0 else None, dst=0, async_op=True))
+                elif gather:
+                    full_out[a:b].copy_(local_out[a:b], non_blocking=True)
+            state["metrics"] = sharding.reduce_metrics(torch.cat(rows), mine, n_frames) if world > 1 else torch.cat(rows)
+            for wk in works:
+                wk.wait()
+            if works and rank == 0:
+                fo = full_out.view(n_local, world, 3, H, W)
+                for j, (a, b) in enumerate(batches):
+                    fo[a:b].copy_(recv[j].transpose(0, 1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    res = {}
+    for gather in (False, True):
+        for _ in range(warmup):
+            step(gather)
+        ms = timed(lambda: step(gather), steps)
+        res["gather" if gather else "reduce"] = ms / steps
+    mpix = n_frames * H * W / 1e6
+    out = {"workload": "udm10_x4_10clips", "scaling": "strong", "frames": n_frames, "clips": clips, "lr": [h, w], "hr": [H, W],
+           "scale": list(scale), "windows_per_forward": B, "frames_per_rank": len(mine), "steps": steps, "warmup": warmup,
+           "sharding": "rank-strided frames (video_base_model.py:50), no data-path collective",
+           "value": round(mpix / (res["reduce"] / 1e3), 2), "unit": "HR Mpix/s", "ms_per_step": round(res["reduce"], 3),
+           "frames_per_s": round(n_frames / (res["reduce"] / 1e3), 2),
+           "collective": f"dist.reduce of a [{n_frames}, 2] fp32 metric tensor to rank 0 ({n_frames * 2 * 4} bytes), inside the timed region",
+           "with_gather": {"value": round(mpix / (res["gather"] / 1e3), 2), "unit": "HR Mpix/s", "ms_per_step": round(res["gather"], 3),
+                           "collective": "dist.gather of every batch's HR frames to rank 0, asynchronous (overlaps the next batch), "
+                                         "plus one strided copy per batch on rank 0",
+                           "bytes_into_rank0": (world - 1) * n_local * 3 * H * W * 4,
+                           "exposed_ms": round(res["gather"] - res["reduce"], 3)},
+           "includes": "window gather, forward (CUDA graph), device tensor2img + PSNR-Y + SSIM-Y against a synthetic ground truth, the reduction"}
+    if rank == 0 and world > 1:
+        out["metrics_checksum"] = float(state["metrics"].double().sum())
+    del plans
+    net.release_plans()
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -180,6 +392,8 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("SAVSR_PRECISION", "bf16"), choices=["bf16", "fp16"],
                     help="16-bit operand format (fp32 accumulate): bf16 = throughput path, fp16 = <=1e-3 max-abs path, same speed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip fp16 / latency / gpu_reference / cfg4 legs (profiling runs)")
+    ap.add_argument("--no-cfg4", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -217,13 +431,17 @@ def main():
     windows = sharding.gather_windows(clip_host.to(dev), list(range(frames)))   # [frames, 7, 3, h, w] resident in HBM
     out_dev = torch.empty(frames, 3, H, W, device=dev)
     batches = [(i, min(i + B, frames)) for i in range(0, frames, B)]
-    plans = {}
-    with torch.no_grad():
-        for (a, b) in batches:
-            if b - a not in plans:
-                plan = net.plan_for(windows[a:b])
-                plan.x_in.copy_(windows[a:b]); plan.capture()
-                plans[b - a] = plan
+
+    def build_plans():
+        plans = {}
+        with torch.no_grad():
+            for (a, b) in batches:
+                if b - a not in plans:
+                    plan = net.plan_for(windows[a:b])
+                    plan.x_in.copy_(windows[a:b]); plan.capture()
+                    plans[b - a] = plan
+        return plans
+    plans = build_plans()
     launches_per_step = sum(plans[b - a].n_launches for a, b in batches)
 
     def step_resident():
@@ -294,35 +512,74 @@ def main():
     value = mpix_step * args.steps / (ms_total / 1e3)
     e2e = mpix_step * args.steps / (ms_e2e / 1e3)
 
-    # ---- roofline of the dominant kernel, measured live (eager pass, CUDA events around every op)
+    # ---- rooflines, measured live (eager pass with a CUDA-event pair around every op on the launching stream)
     peaks = measured_peaks()
     big = plans[max(plans)]
-    prof = big.run_profiled()
-    prof = big.run_profiled()
-    conv = prof.get("conv3x3_n64", dict(ms=0.0, flops=0.0, launches=0))
+    big.run_profiled()
+    prof = big.run_profiled(detail=True)
     total_ms = sum(d["ms"] for d in prof.values())
+    per_kind = {}
+    for k, d in prof.items():
+        e = per_kind.setdefault(k.split(":")[0], dict(ms=0.0, flops=0.0, launches=0))
+        e["ms"] += d["ms"]; e["flops"] += d["flops"]; e["launches"] += d["launches"]
+    conv = per_kind.get("conv3x3_n64", dict(ms=0.0, flops=0.0, launches=0))
     achieved = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] else 0.0
-    traffic, traffic_note = None, None
-    tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")
-    if os.path.exists(tpath):
-        tj = json.load(open(tpath))
-        traffic, traffic_note = tj.get("dram_bytes_per_launch"), f"ncu --set full, one launch: {tj.get('launch')} ({tj.get('source')})"
-    roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel<64,3,halo> (tcgen05 implicit-GEMM 3x3 conv, all launches of one forward)",
+
+    def traffic_of(fname):
+        tpath = os.path.join(ROOT, "profiles", fname)
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            return tj.get("dram_bytes_per_launch"), f"ncu --set full, one launch: {tj.get('launch')} ({tj.get('source')})"
+        return None, None
+    traffic, traffic_note = traffic_of("conv_traffic.json")
+    roofline = {"bound": "tensor", "kernel": "conv_igemm_bigk_kernel (tcgen05 implicit-GEMM 3x3 conv, N = 64; all launches of one forward)",
                 "achieved": round(achieved, 1), "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": round(achieved / peaks["bf16_sustained"], 4), "peak_source": peaks["source"] + " bf16 sustained",
+                "frac_of_burst_peak": round(achieved / peaks["bf16_burst"], 4),
+                "flops_counted": "algorithmic: 2 * px * 64 * 9 * Ci per conv and sample with the reference's Ci (3 / 6 for the first layer, not the "
+                                 "64 of the zero-expanded filters)",
+                "algorithmic_tflop_per_forward": round(conv["flops"] / 1e12, 3),
                 "traffic": traffic, "traffic_note": traffic_note, "share_of_step": round(conv["ms"] / total_ms, 3) if total_ms else None,
                 "launches": conv["launches"], "avg_launch_us": round(1e3 * conv["ms"] / max(conv["launches"], 1), 1),
-                "per_kind_ms": {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
+                "per_kind_ms": {k: round(v["ms"], 3) for k, v in sorted(per_kind.items(), key=lambda kv: -kv[1]["ms"])},
+                "per_conv_shape": {k: {"ms": round(d["ms"], 3), "tflops": round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 1), "launches": d["launches"]}
+                                   for k, d in sorted(prof.items()) if k.startswith("conv3x3_n64") and d["ms"] > 0}}
+    osa = [d for k, d in prof.items() if k.startswith("conv3x3_n64") and k.endswith("osa")]
+    osa_ms, osa_fl, osa_n = sum(d["ms"] for d in osa), sum(d["flops"] for d in osa), sum(d["launches"] for d in osa)
+    pro = per_kind.get("osa_prologue", dict(ms=0.0))
+    roofline_osa = {"bound": "tensor", "kernel": "OSA-Conv launches only (per-sample folded weights, savsr_arch.py:139-172)",
+                    "achieved": round(osa_fl / (osa_ms * 1e-3) / 1e12, 1) if osa_ms else None, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                    "frac": round(osa_fl / (osa_ms * 1e-3) / 1e12 / peaks["bf16_sustained"], 4) if osa_ms else None,
+                    "frac_of_burst_peak": round(osa_fl / (osa_ms * 1e-3) / 1e12 / peaks["bf16_burst"], 4) if osa_ms else None,
+                    "launches": osa_n, "conv_ms": round(osa_ms, 3), "prologue_ms": round(pro["ms"], 3),
+                    "frac_including_prologue": round(osa_fl / ((osa_ms + pro["ms"]) * 1e-3) / 1e12 / peaks["bf16_sustained"], 4) if osa_ms else None}
+    nb = big.B
+    satu_ms = sum(per_kind[k]["ms"] for k in SATU_KINDS if k in per_kind)
+    satu_bytes = satu_compulsory_bytes(h, w, H, W) * nb + 0.49e6
+    satu_fl = satu_flops_per_frame(h, w, H, W) * nb
+    extra = getattr(big, "satu_extra_bytes_per_sample", None)
+    s_traffic, s_note = traffic_of("satu_traffic.json")
+    roofline_satu = {"bound": "hbm", "kernels": [k for k in SATU_KINDS if k in per_kind],
+                     "ms_per_launch_set": round(satu_ms, 3), "us_per_frame": round(1e3 * satu_ms / nb, 2),
+                     "achieved": round(satu_bytes / (satu_ms * 1e-3) / 1e9, 1) if satu_ms else None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": round(satu_bytes / (satu_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4) if satu_ms else None,
+                     "compulsory_bytes_per_frame": satu_compulsory_bytes(h, w, H, W),
+                     "declared_extra_bytes_per_frame": extra,
+                     "compute": {"achieved": round(satu_fl / (satu_ms * 1e-3) / 1e12, 1) if satu_ms else None, "peak": peaks["bf16_sustained"],
+                                 "unit": "TFLOP/s", "frac": round(satu_fl / (satu_ms * 1e-3) / 1e12 / peaks["bf16_sustained"], 4) if satu_ms else None},
+                     "traffic": s_traffic, "traffic_note": s_note,
+                     "caveat": "SATU carries ~1 180 FLOP per compulsory byte, so under this byte count it is compute-bound: 70 % of HBM would "
+                               "mean ~4 us/frame (SURVEY.md D7); both fractions are printed"}
     whole = flops_per_frame(h, w, H, W) * frames * world * args.steps / (ms_total / 1e3) / 1e12
 
+    cfg = workload_config(args.workload, world)
     line = {
         "metric": "hr_mpix_per_s", "value": round(value, 2), "unit": "HR Mpix/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": args.workload, "frames_per_clip": frames, "clips": world, "lr": [h, w], "hr": [H, W],
-                   "scale": list(scale), "windows_per_forward": B, "conv_impl": args.conv_impl, "weights": "random init (seed 0)",
-                   "l2": "per-step working set (activation arenas, several GB) exceeds the 126 MB L2; no explicit flush",
-                   "parallelism": f"frame-sharded x{world}, no data-path collective"},
+        "config": cfg,
+        "run": {"windows_per_forward": B, "conv_impl": args.conv_impl,
+                "l2": "per-step working set (activation arenas, several GB) exceeds the 126 MB L2; no explicit flush"},
         "frames_per_s": round(frames * world * args.steps / (ms_total / 1e3), 2),
         "whole_forward_tflops": round(whole, 1),
         "e2e": {"value": round(e2e, 2), "unit": "HR Mpix/s", "ms_per_step": round(ms_e2e / args.steps, 3),
@@ -337,13 +594,65 @@ def main():
         "gpu_launches": launches_per_step * args.steps * world,
         "clocks": clocks,
         "roofline": roofline,
+        "roofline_osa": roofline_osa,
+        "roofline_satu": roofline_satu,
     }
+
+    extras = not args.no_extras
+    if extras and world == 1:
+        # ---- the fp16-operand path (meets the fp32 criterion), same resident measurement
+        other = "fp16" if args.precision == "bf16" else "bf16"
+        net.precision = other
+        plans_main, plans = plans, None
+        plans = build_plans()
+        for _ in range(3):
+            step_resident()
+        ms_o = timed(step_resident, args.steps)
+        line[other] = {"value": round(mpix_step * args.steps / (ms_o / 1e3), 2), "unit": "HR Mpix/s", "ms_per_step": round(ms_o / args.steps, 3),
+                       "dtype": other, "note": "same kernels, 16-bit operands in the other format, fp32 accumulate; fp16 meets max-abs <= 1e-3 "
+                                               "against the fp32 reference (tests/test_gpu_forward.py)"}
+        net.precision = args.precision
+        plans = plans_main
+        # ---- one window per call through the module (what lbasicsr/test.py does, video_base_model.py:50-59)
+        net.set_scale(scale)
+        x1 = windows[:1].clone()
+        with torch.no_grad():
+            net(x1)
+            first_build = net.last_plan_build_ms
+            s2 = (scale[0] - 0.1, scale[1] - 0.1)
+            net.set_scale(s2); net(x1)
+            next_build = net.last_plan_build_ms
+            net.set_scale(scale)
+        ms_b1 = vsr_runtime(lambda: net(x1), 10, 30)
+        line["latency_b1"] = {"ms": round(ms_b1, 3), "hr_mpix_s": round(H * W / ms_b1 / 1e3, 2), "api": "SAVSR.forward(x[1,7,3,h,w]) incl. plan lookup, "
+                              "input staging, CUDA-graph replay and a fresh output tensor", "protocol": "10 warm-up + 30 repetitions, event pair + synchronize each",
+                              "plan_build_ms": {"first_plan_b1": round(first_build, 1), "next_scale_b1": round(next_build, 1),
+                                                "note": "packed weights / folded BN are shared across plans of one weights version"}}
+        try:
+            line["gpu_reference"] = gpu_reference(net, dev, h, w, scale, B)
+            g = line["gpu_reference"]
+            if f"b{B}_tf32_hr_mpix_s" in g:
+                g["speedup_resident_vs_tf32_batched"] = round(value / g[f"b{B}_tf32_hr_mpix_s"], 2)
+            g["speedup_b1_vs_tf32"] = round(g["b1_tf32_ms"] / ms_b1, 2)
+        except Exception as e:  # noqa: BLE001
+            line["gpu_reference"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+    if extras and not args.no_cfg4:
+        plans = None
+        big = None
+        net.release_plans()
+        torch.cuda.empty_cache()
+        try:
+            line["cfg4_strong"] = run_cfg4(net, dev, rank, world, timed)
+        except Exception as e:  # noqa: BLE001
+            line["cfg4_strong"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
         n_cpu = 3
-        val, dt, threads = cpu_oracle_time(sd, n_cpu, h, w, scale)
-        line["cpu_baseline"] = {"value": round(val, 5), "unit": "HR Mpix/s", "cores": threads, "kind": "port",
-                                "sample": f"{n_cpu} output frames of the same clip shape ({h}x{w} -> {H}x{W}), oracle fp32, {dt:.1f} s"}
+        val, dt, threads, kind = cpu_reference_time(sd, n_cpu, h, w, scale)
+        line["cpu_baseline"] = {"value": round(val, 5), "unit": "HR Mpix/s", "cores": threads, "kind": kind,
+                                "sample": f"{n_cpu} output frames of the same clip shape ({h}x{w} -> {H}x{W}), fp32, {dt:.1f} s; "
+                                          + ("the unmodified reference (baseline/_ref)" if kind == "reference" else "oracle port")}
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:

@@ -131,7 +131,7 @@ def osa_attention(sd: SD, prefix: str, pooled: Tensor, scale) -> Tuple[Tensor, T
     s = normalize_scale(scale)
     b = pooled.shape[0]
     # NOTE order: (1/s_h, 1/s_w) -- ones/scale[0], ones/scale[1]  (143-145)
-    inv = torch.ones(1, 1) / s[0], torch.ones(1, 1) / s[1]
+    inv = torch.ones(1, 1, device=pooled.device) / s[0], torch.ones(1, 1, device=pooled.device) / s[1]
     info = torch.cat(inv, 1).repeat(b, 1)
     v = torch.cat([info, pooled], dim=1)
     v = F.relu(F.linear(v, sd[prefix + ".scale_routing.0.weight"], sd[prefix + ".scale_routing.0.bias"]))
@@ -270,21 +270,23 @@ def satu_sta_conv(x: Tensor, kern: Tensor, ks: int = 5) -> Tensor:
     return out
 
 
-def satu_mlp_input(h: int, w: int, scale) -> Tensor:
-    """4-channel MLP input (savsr_arch.py:326-340): [1/s_w, 1/s_h, R_y, R_x] (note channel 0 = 1/s_w)."""
+def satu_mlp_input(h: int, w: int, scale, device=None) -> Tensor:
+    """4-channel MLP input (savsr_arch.py:326-340): [1/s_w, 1/s_h, R_y, R_x] (note channel 0 = 1/s_w).
+    Always evaluated with CPU (true-division) semantics, then moved to `device` (the device-aware mode only serves the
+    GPU timing leg of bench.py; parity is defined on the CPU)."""
     s = normalize_scale(scale)
     H, W = get_hw(h, w, s)
     ry = torch.from_numpy(satu_rel_coord(H, s[0])).view(H, 1).expand(H, W)
     rx = torch.from_numpy(satu_rel_coord(W, s[1])).view(1, W).expand(H, W)
     c0 = torch.ones(H, W) / s[1]
     c1 = torch.ones(H, W) / s[0]
-    return torch.stack([c0, c1, ry, rx], 0).unsqueeze(0)
+    return torch.stack([c0, c1, ry, rx], 0).unsqueeze(0).to(device)
 
 
 def satu_heads(sd: SD, prefix: str, h: int, w: int, scale) -> Tuple[Tensor, Tensor, Tensor]:
     """body + offset / st_offset / routing heads (savsr_arch.py:344-351).
     Depends only on (scale, h, w).  Returns offset [1,2,H,W] (x then y), st_offset, routing [1,4,H,W]."""
-    inp = satu_mlp_input(h, w, scale)
+    inp = satu_mlp_input(h, w, scale, sd[prefix + ".body.0.weight"].device)
     e = F.relu(_conv(sd, prefix + ".body.0", inp))
     e = F.relu(_conv(sd, prefix + ".body.2", e))
     off = _conv(sd, prefix + ".offset", e)
@@ -297,8 +299,8 @@ def satu_grid(h: int, w: int, scale, offset: Tensor) -> Tensor:
     """Normalised sampling grid of STAUpsample.grid_sample (savsr_arch.py:262-288): [1,H,W,2] (x,y)."""
     s = normalize_scale(scale)
     H, W = get_hw(h, w, s)
-    gx = torch.from_numpy(satu_base_norm(W, w, s[1])).view(1, 1, W).expand(1, H, W)
-    gy = torch.from_numpy(satu_base_norm(H, h, s[0])).view(1, H, 1).expand(1, H, W)
+    gx = torch.from_numpy(satu_base_norm(W, w, s[1])).to(offset.device).view(1, 1, W).expand(1, H, W)
+    gy = torch.from_numpy(satu_base_norm(H, h, s[0])).to(offset.device).view(1, H, 1).expand(1, H, W)
     ox = offset[:, 0] * 2 / (w - 1)
     oy = offset[:, 1] * 2 / (h - 1)
     return torch.stack([gx + ox, gy + oy], dim=-1)
@@ -355,8 +357,9 @@ def pad_spatial(x: Tensor, multiple: int = 2) -> Tensor:
 def forward(sd: SD, x: Tensor, scale, probes: Optional[dict] = None) -> Tensor:
     """SAVSR.forward (savsr_arch.py:692-742) for the shipped configuration (interval=0).
 
-    sd: flat reference-layout state_dict, fp32 CPU tensors.
-    x : [b, 7, 3, h, w] fp32.  Returns [b, 3, H, W] fp32 (not clamped).
+    sd: flat reference-layout state_dict, fp32 tensors; x: [b, 7, 3, h, w] fp32 on the same device
+    (CPU for every parity check; bench.py's `gpu_reference` leg may place both on a CUDA device to time the same ATen /
+    cuDNN calls the reference makes there).  Returns [b, 3, H, W] fp32 (not clamped).
     """
     scale = normalize_scale(scale)
     b, t, c, h_in, w_in = x.shape
@@ -369,8 +372,8 @@ def forward(sd: SD, x: Tensor, scale, probes: Optional[dict] = None) -> Tensor:
     slid = 3
     n_it = t - slid + 1
 
-    ht_f2p = torch.zeros(b, nf, hp, wp)
-    ht_p2f = torch.zeros(b, nf, hp, wp)
+    ht_f2p = torch.zeros(b, nf, hp, wp, device=x.device)
+    ht_p2f = torch.zeros(b, nf, hp, wp, device=x.device)
     f2p: List[Tensor] = []
     p2f: List[Tensor] = []
     for idx in range(n_it):                                   # savsr_arch.py:708-719

@@ -504,7 +504,9 @@ class Plan:
             return z
         self._conv(hr, [self._group([0], 0, self._pack("tail.weight@16", lambda: self._p("tail.weight"), n_tile=16, co_pad=16),
                                     self._dev("tail.bias@16", bt), aux=self.out.data_ptr())], n_tile=16, dst_mode=K.DST_RGB, skip=skip,
-                   alg_co=3)
+                   alg_co=3, kind="satu_tail")
+        # declared traffic beyond the compulsory SATU bytes (per sample): the 16-bit sta intermediate and the 64-channel HR feature
+        self.satu_extra_bytes_per_sample = 2 * 64 * self.hp * self.wp * 2 + 2 * 64 * self.H * self.W * 2
         self._stream().synchronize()
         self._pack_src.clear()
 

@@ -78,25 +78,66 @@ def infer_clip(net: Callable[[torch.Tensor], torch.Tensor], clip: torch.Tensor, 
     return torch.cat(outs, 0)
 
 
-def gather_outputs(local: torch.Tensor, frames: Sequence[int], n_frames: int, group=None) -> Optional[torch.Tensor]:
-    """All-gather per-rank results [n_local, 3, H, W] into clip order [n_frames, 3, H, W] on every rank.
-    Ranks may own different numbers of frames (ragged): results are padded to the longest shard."""
+def gather_outputs(local: torch.Tensor, n_frames: int, rank: int, world_size: int, dst: Optional[int] = 0,
+                   contiguous: bool = False, group=None, out: Optional[torch.Tensor] = None,
+                   async_op: bool = False):
+    """Collect per-rank results [n_local, ...] (frames owned per `shard_frames(n_frames, rank, world_size, contiguous)`) into
+    clip order [n_frames, ...].  One pre-sized collective, no pickled metadata: every rank derives every other rank's frame
+    list from the same deterministic `shard_frames`, so only payload travels.
+
+    dst = r   : `dist.gather` to rank r (what writing the frames / logging needs; 1/world of an all-gather's traffic);
+                returns the assembled tensor on rank r and None elsewhere.
+    dst = None: `dist.all_gather_into_tensor`, every rank gets the clip.
+    Ragged shards are padded to the longest one (at most one frame per rank).
+    `async_op`: returns (work, finish) -- call finish() after work.wait() to obtain the result (lets the transfer of batch i
+    overlap the forward of batch i+1)."""
     import torch.distributed as dist
-    world = dist.get_world_size(group)
-    counts = [None] * world
-    dist.all_gather_object(counts, list(frames), group=group)
-    longest = max(len(c) for c in counts)
+    lists = [shard_frames(n_frames, r, world_size, contiguous) for r in range(world_size)]
+    longest = max(len(l) for l in lists)
     shape = list(local.shape[1:])
-    shapes = [None] * world
-    dist.all_gather_object(shapes, shape if local.numel() else None, group=group)
-    shape = next(s for s in shapes if s is not None)
-    pad = torch.zeros([longest] + shape, dtype=torch.float32, device=local.device)
-    if local.numel():
-        pad[:local.shape[0]] = local
-    bufs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(bufs, pad, group=group)
-    out = torch.empty([n_frames] + shape, dtype=torch.float32, device=local.device)
-    for r in range(world):
-        for j, f in enumerate(counts[r]):
-            out[f] = bufs[r][j]
-    return out
+    if local.shape[0] != len(lists[rank]):
+        raise ValueError(f"rank {rank} owns {len(lists[rank])} frames but passed {local.shape[0]}")
+    send = local
+    if local.shape[0] != longest:
+        send = torch.zeros([longest] + shape, dtype=local.dtype, device=local.device)
+        send[:local.shape[0]] = local
+    send = send.contiguous()
+    recv = None
+    if dst is None:
+        recv = torch.empty([world_size * longest] + shape, dtype=local.dtype, device=local.device)
+        work = dist.all_gather_into_tensor(recv, send, group=group, async_op=True)
+    else:
+        if rank == dst:
+            recv = torch.empty([world_size * longest] + shape, dtype=local.dtype, device=local.device)
+        work = dist.gather(send, list(recv.view([world_size, longest] + shape).unbind(0)) if rank == dst else None, dst=dst,
+                           group=group, async_op=True)
+
+    def finish() -> Optional[torch.Tensor]:
+        if recv is None:
+            return None
+        res = out if out is not None else torch.empty([n_frames] + shape, dtype=local.dtype, device=local.device)
+        blocks = recv.view([world_size, longest] + shape)
+        for r, fl in enumerate(lists):
+            if not fl:
+                continue
+            if contiguous:
+                res[fl[0]:fl[0] + len(fl)] = blocks[r, :len(fl)]
+            else:
+                res[r::world_size][:len(fl)] = blocks[r, :len(fl)]          # rank-strided shard = strided slice of the clip
+        return res
+
+    if async_op:
+        return work, finish
+    work.wait()
+    return finish()
+
+
+def reduce_metrics(local_rows: torch.Tensor, frames: Sequence[int], n_frames: int, dst: int = 0, group=None) -> torch.Tensor:
+    """The reference's own reduction (lbasicsr/models/video_base_model.py:36-37, 106-113): every rank fills its rows of a
+    zero [n_frames, n_metrics] tensor, then `dist.reduce(..., dst=0)` sums them.  Returns the tensor (complete on `dst`)."""
+    import torch.distributed as dist
+    full = torch.zeros(n_frames, local_rows.shape[1], dtype=local_rows.dtype, device=local_rows.device)
+    if len(frames):
+        full[torch.as_tensor(list(frames), device=local_rows.device)] = local_rows
+    dist.reduce(full, dst=dst, group=group)
+    return full

@@ -28,8 +28,8 @@ def main():
     mine = sharding.shard_frames(T, rank, world)                       # the reference's rank-strided split
     with torch.no_grad():
         res = datapath.evaluate_clip(net, frames, scale, frames=mine, batch=3)
-        full = sharding.gather_outputs(res["sr"], mine, T)              # NCCL all-gather, ragged shards padded
-        psnr = sharding.gather_outputs(res["psnr_y"].float().view(-1, 1), mine, T).view(-1)
+        full = sharding.gather_outputs(res["sr"], T, rank, world, dst=None)      # NCCL all-gather, ragged shards padded
+        psnr = sharding.gather_outputs(res["psnr_y"].float().view(-1, 1), T, rank, world, dst=None).view(-1)
         ref = datapath.evaluate_clip(net, frames, scale, batch=4)      # every rank also runs the whole clip alone
     same = bool(torch.equal(full, ref["sr"]))
     dp = float((psnr - ref["psnr_y"].float()).abs().max())

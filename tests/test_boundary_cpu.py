@@ -112,9 +112,11 @@ def test_bench_reference_arm_contract():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "hr_mpix_per_s" and line["unit"] == "HR Mpix/s"
     assert line["higher_is_better"] is True and line["vs_baseline"] is None and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"] and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["value"] == line["value"] and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "HR Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["config"]["workload"] == "cfg1_x2"
+    import bench
+    assert line["config"] == bench.workload_config("cfg1_x2", 1)      # both arms print the same config object
 
 
 def test_bench_our_arm_needs_a_gpu():

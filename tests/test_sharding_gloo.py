@@ -52,11 +52,27 @@ def _worker(rank, world, port, n_frames, ret):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         clip = torch.rand(n_frames, 3, 6, 8, generator=torch.Generator().manual_seed(7))
-        mine = sharding.shard_frames(n_frames, rank, world)
-        local = sharding.infer_clip(fake_net, clip, frames=mine, batch=2)
-        full = sharding.gather_outputs(local, mine, n_frames)
         ref = sharding.infer_clip(fake_net, clip, batch=3)
-        ret[rank] = bool(torch.equal(full, ref)) and len(mine) == len(range(rank, n_frames, world))
+        ok = True
+        for contiguous in (False, True):
+            mine = sharding.shard_frames(n_frames, rank, world, contiguous)
+            local = sharding.infer_clip(fake_net, clip, frames=mine, batch=2) if mine else torch.empty(0, 3, 12, 16)
+            # gather to rank 0 (one pre-sized dist.gather, ragged shards padded): rank 0 gets the clip, the others nothing
+            full = sharding.gather_outputs(local, n_frames, rank, world, dst=0, contiguous=contiguous)
+            ok &= (full is None) if rank != 0 else bool(torch.equal(full, ref))
+            # every rank gets the clip (all_gather_into_tensor), through the asynchronous interface
+            work, finish = sharding.gather_outputs(local, n_frames, rank, world, dst=None, contiguous=contiguous, async_op=True)
+            work.wait()
+            ok &= bool(torch.equal(finish(), ref))
+            # the reference's metric reduction (video_base_model.py:106-113): rows of the owned frames, summed on rank 0
+            rows = torch.stack([local.flatten(1).mean(1), local.flatten(1).amax(1)], 1) if mine else torch.empty(0, 2)
+            red = sharding.reduce_metrics(rows, mine, n_frames)
+            if rank == 0:
+                want = torch.stack([ref.flatten(1).mean(1), ref.flatten(1).amax(1)], 1)
+                ok &= bool(torch.allclose(red, want, atol=1e-6))
+        with pytest.raises(ValueError):
+            sharding.gather_outputs(torch.empty(n_frames + 1, 1), n_frames, rank, world)
+        ret[rank] = ok and len(sharding.shard_frames(n_frames, rank, world)) == len(range(rank, n_frames, world))
     finally:
         dist.destroy_process_group()
 
