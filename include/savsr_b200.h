@@ -47,8 +47,7 @@ typedef void* savsr_stream;             /* cudaStream_t                         
 enum savsr_format { SAVSR_FMT_BF16 = 0, SAVSR_FMT_FP16 = 1 };
 /* Row (output channel) order inside a packed n_tile = 64 weight block.  LINEAR: row n = channel n.  QUAD: row n =
  * channel with the bit fields [2:1] and [4:3] of n swapped -- the order savsr_conv requires for n_tile 64 (its epilogue
- * reads the accumulator with 16x256b TMEM loads and stores 16 contiguous bytes per thread); savsr_satu_fused takes QUAD for
- * its fusion weights (same epilogue) and LINEAR for the compress / expand expert matrices. */
+ * reads the accumulator with 16x256b TMEM loads and stores 16 contiguous bytes per thread), savsr_satu_kconv_sta likewise. */
 enum savsr_row_order { SAVSR_ROWS_LINEAR = 0, SAVSR_ROWS_QUAD = 1 };
 
 enum savsr_act { SAVSR_ACT_NONE = 0, SAVSR_ACT_LRELU = 1, SAVSR_ACT_RELU = 2 };
@@ -56,8 +55,7 @@ enum savsr_act { SAVSR_ACT_NONE = 0, SAVSR_ACT_LRELU = 1, SAVSR_ACT_RELU = 2 };
 /* how a convolution writes its result */
 enum savsr_dst_mode {
   SAVSR_DST_ARENA = 0, /* bf16 NHWC-64 arena slot (N = 64)                                       */
-  SAVSR_DST_AUX16 = 1, /* fp32 [batch][H*W][16] side buffer (N = 16; OSAdapt mask conv)          */
-  SAVSR_DST_RGB = 2    /* fp32 NCHW [batch][3][H][W] + bilinear skip of the LR centre frame      */
+  SAVSR_DST_AUX16 = 1  /* fp32 [batch][H*W][16] side buffer (N = 16; OSAdapt mask conv)          */
 };
 
 enum savsr_conv_impl {
@@ -69,8 +67,8 @@ enum savsr_conv_impl {
 /*
  * One convolution of a batched launch.  Replaces one nn.Conv2d / F.conv2d call of
  * savsr_arch.py (388-397 ResidualBlock convs, 429-442 WindowUnit_l1, 480-483 WindowUnit_l2,
- * 541-543 RCAB, 567 ResidualGroup.conv, 166 OSA-Conv grouped conv, 190/203 OSAdapt mask,
- * 227 kernel_conv, 260 fusion, 620 h_win_conv_h, 629 conv_last, 633 tail) together with the
+ * 541-543 RCAB, 567 ResidualGroup.conv, 166 OSA-Conv grouped conv, 190 OSAdapt mask,
+ * 620 h_win_conv_h, 629 conv_last) together with the
  * torch.cat feeding it (404, 412, 462, 498, 721, 374) and the elementwise ops that follow it.
  *
  *   acc = sum_{s < nsrc} sum_{tap} W[s, tap] * src_s(shifted by tap)          (zero padding)
@@ -92,15 +90,8 @@ typedef struct savsr_conv_group {
   const float* bias;            /* [N] fp32 or NULL                                              */
   const float* mask;            /* [batch][H*W] fp32 per-pixel multiplier or NULL (OSAdapt)      */
   float* pool;                  /* [batch][tiles*4][64] fp32 partial sums or NULL                */
-  void* aux_dst;                /* SAVSR_DST_AUX16 / SAVSR_DST_RGB destination                   */
+  void* aux_dst;                /* SAVSR_DST_AUX16 destination                                   */
 } savsr_conv_group;
-
-/* extra arguments of SAVSR_DST_RGB: out = conv + bias + bilinear(x_center -> H x W), savsr_arch.py:738-739 */
-typedef struct savsr_rgb_skip {
-  const float* x;      /* LR input window [batch][t][3][h][w] fp32 NCHW (the module's input)       */
-  int32_t t, centre;   /* frames per window, centre frame index                                   */
-  int32_t h, w;        /* LR size (unpadded)                                                      */
-} savsr_rgb_skip;
 
 /* Tuning / bring-up knobs of a context (savsr_ctx_set_option).  The library reads no environment variables. */
 enum savsr_option {
@@ -150,12 +141,10 @@ int savsr_pack_conv_weight(const float* w_oihw, int co_real, int co, int ci, int
 /* ---- convolutions (tensor-core hot path) ------------------------------------------------------- */
 /*
  * Batched implicit-GEMM convolution: `ngroups` independent convs x `batch` samples in one launch.
- * ksize 3 (pad 1) or 1.  n_tile = 64 (dst ARENA) or 16 (AUX16 / RGB).  src and dst arenas may be the
- * same object; they must have equal batch/height/width.
+ * ksize 3 (pad 1) or 1.  n_tile = 64 (dst ARENA) or 16 (AUX16).
  */
 int savsr_conv(savsr_ctx* ctx, savsr_arena* arena, const savsr_conv_group* groups, int ngroups,
-               int ksize, int n_tile, int dst_mode, const savsr_rgb_skip* skip, int impl,
-               savsr_stream st);
+               int ksize, int n_tile, int dst_mode, int impl, savsr_stream st);
 
 /*
  * First layer (savsr_arch.py:456-457 conv_sup / conv_c with the frame gather of 447-454): pack the fp32 window into ONE
@@ -247,17 +236,20 @@ int savsr_satu_kconv_sta(savsr_ctx* ctx, savsr_arena* arena, int a_slot, int x_s
                          const void* weights, const float* bias, float slope, savsr_stream st);
 
 /*
- * Tensor-core version of the HR stage: savsr_satu_gather followed by the 128->64 fusion conv (savsr_arch.py:364-374) in
- * one kernel; the compress / expand / fusion GEMMs run on tcgen05 with the tiles built in shared memory.
- * w_compress: savsr_pack_conv_weight of [32][64][1][1] (rows e*8+k), n_tile 16; w_expand: of [64][64][1][1] with input
- * columns e*8+k (32..63 zero), n_tile 64; w_fusion: of the fusion filter [64][128][1][1], n_tile 64,
- * SAVSR_ROWS_QUAD (w_compress and w_expand: SAVSR_ROWS_LINEAR).
- * Writes the fused HR feature (bf16) to hr slot dst_slot.
+ * The whole HR side of SATU and the tail in ONE kernel, without any HR-resolution intermediate in memory
+ * (savsr_arch.py:291 grid_sample x2, 353-370 routed compress / expand experts, 374 fusion, 738 tail conv, 739 bilinear skip):
+ *   F = gather(x, offset), S = gather(sta, st_offset) ; U = F Wc^T ; V[e*8+k] = r_e sum_e' r_e' U[e'*8+k]
+ *   Z[q][tap*3+c] = S[q] Wcs^T + F[q] Wcf^T + V[q] Wv^T + zbias       (fusion and tail composed on the host: both are linear)
+ *   out[p][c] = tail_bias[c] + sum over the 3x3 taps inside the image of Z[p + d_tap][tap*3+c] + bilinear(x_center)[p][c]
+ * weights: four [32 rows][128 B] K-major 128-byte-swizzled 16-bit tiles Wc | Wcf | Wcs | Wv (16 KB; rows of the last three =
+ * tap*3+c, 27 used; Wv uses K = 32), in the context's format; zbias fp32 [32]; tail_bias fp32 [3];
+ * x_in: the module's input window fp32 [batch][t][3][h][w]; out: fp32 NCHW [batch][3][H][W].
+ * savsr_b200/engine.py (satu_hr_compose / satu_hr_pack) builds the operands from the reference's parameters.
  */
-int savsr_satu_fused(savsr_ctx* ctx, savsr_arena* lr, int x_slot, int sta_slot, int h, int w, savsr_arena* hr,
-                     int dst_slot, const float* table, const float* base_y, const float* base_x,
-                     const void* w_compress, const void* w_expand, const void* w_fusion, const float* fusion_bias,
-                     savsr_stream st);
+int savsr_satu_hr(savsr_ctx* ctx, savsr_arena* lr, int x_slot, int sta_slot, int h, int w, int H, int W,
+                  const float* table, const float* base_y, const float* base_x, const void* weights,
+                  const float* zbias, const float* tail_bias, const float* x_in, int t, int centre, float* out,
+                  savsr_stream st);
 
 /* ---- post-processing / metrics on the device (next row 8f3) -------------------------------------------------------
  * tensor2img (lbasicsr/utils/img_util.py:38-94): sr fp32 NCHW [batch][3][H][W] RGB -> uint8 HWC BGR [batch][H][W][3]

@@ -17,13 +17,13 @@ MAX_GROUPS = 25
 TILE_W, TILE_H = 8, 16
 
 ACT_NONE, ACT_LRELU, ACT_RELU = 0, 1, 2
-DST_ARENA, DST_AUX16, DST_RGB = 0, 1, 2
+DST_ARENA, DST_AUX16 = 0, 1
 IMPL_TAP, IMPL_HALO, IMPL_CHECK = 0, 1, 2
 IMPL_NAMES = {"tap": IMPL_TAP, "halo": IMPL_HALO, "check": IMPL_CHECK}
 FMT_BF16, FMT_FP16 = 0, 1
 FMT_NAMES = {"bf16": FMT_BF16, "fp16": FMT_FP16}
 OPT_BIGK_ALL, OPT_BIGK_ISSUERS = 0, 1   # enum savsr_option
-ROWS_LINEAR, ROWS_QUAD = 0, 1     # enum savsr_row_order: QUAD for savsr_conv n_tile 64, LINEAR for savsr_satu_fused
+ROWS_LINEAR, ROWS_QUAD = 0, 1     # enum savsr_row_order: QUAD for everything savsr_conv / savsr_satu_kconv_sta consume with n_tile 64
 
 # SAVSR_LIB_PATH: alternative build of the same ABI (A/B timing of kernel variants); default = the in-tree library
 LIB_PATH = os.environ.get("SAVSR_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libsavsr_sm100.so")
@@ -50,10 +50,6 @@ class ConvGroup(C.Structure):
         ("pool", C.c_void_p),
         ("aux_dst", C.c_void_p),
     ]
-
-
-class RgbSkip(C.Structure):
-    _fields_ = [("x", C.c_void_p), ("t", C.c_int32), ("centre", C.c_int32), ("h", C.c_int32), ("w", C.c_int32)]
 
 
 class OsaParams(C.Structure):
@@ -96,14 +92,14 @@ SIGNATURES = {
     "savsr_arena_export": (_I, [_VP, _I, _VP, _VP]),
     "savsr_packed_weight_bytes": (_SZ, [_I, _I, _I]),
     "savsr_pack_conv_weight": (_I, [_VP, _I, _I, _I, _I, _I, _I, _I, _VP, _VP]),
-    "savsr_conv": (_I, [_VP, _VP, C.POINTER(ConvGroup), _I, _I, _I, _I, C.POINTER(RgbSkip), _I, _VP]),
+    "savsr_conv": (_I, [_VP, _VP, C.POINTER(ConvGroup), _I, _I, _I, _I, _I, _VP]),
     "savsr_pack_frames": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "savsr_osa_prologue": (_I, [_VP, C.POINTER(OsaParams), _I, _I, _I, _I, _F, _F, _VP]),
     "savsr_ca_scale_residual": (_I, [_VP, _VP, _I, _I, _I, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "savsr_osadapt_mask": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "savsr_satu_index": (_I, [_VP, C.POINTER(SatuWeights), _I, _I, _I, _I, _F, _F] + [_VP] * 9 + [_VP]),
     "savsr_satu_kconv_sta": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP, _VP, _F, _VP]),
-    "savsr_satu_fused": (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "savsr_satu_hr": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _VP, _VP]),
     "savsr_img_metrics": (_I, [_VP, _VP, _VP, _I, _I, _I, _VP, _VP, _VP]),
     "savsr_ssim_y_blocks": (_I, [_I, _I]),
     "savsr_ssim_y": (_I, [_VP, _VP, _VP, _I, _I, _I, _VP, _VP]),

@@ -54,7 +54,7 @@ namespace savsr {
 // Kernels that need more than 48 KB of dynamic shared memory: the attribute belongs to the device (primary context), so
 // it is tracked per savsr_ctx, not per process.
 enum AttrBit { kAttrIgemm = 0 /* + template index, 6 variants */, kAttrBigk = 8, kAttrKsta = 9, kAttrSatuHr = 10, kAttrOsaLinear = 11,
-               kAttrFused = 12, kAttrBigk128 = 13 };
+               kAttrFused = 12, kAttrBigk128 = 13, kAttrSatuHrBf16 = 14 };
 template <class F>
 inline int ensure_smem_attr(savsr_ctx* ctx, int bit, F func, size_t bytes) {
   if (ctx->attr_mask & (1u << bit)) return 0;
@@ -108,6 +108,16 @@ __device__ __forceinline__ float h_hi(uint32_t v, int fmt) {
 __device__ __forceinline__ float h_to_float(uint16_t raw, int fmt) { return h_lo(raw, fmt); }
 __device__ __forceinline__ uint16_t float_to_h(float x, int fmt) { return static_cast<uint16_t>(pack_h2(x, 0.f, fmt) & 0xffffu); }
 
+// ATen upsample_bilinear2d, align_corners = False (savsr_arch.py:739): source index and weight.
+__device__ __forceinline__ void bilinear_src(int dst, int in_size, int out_size, int& i0, int& i1, float& l1) {
+  const float scale = static_cast<float>(in_size) / static_cast<float>(out_size);
+  float src = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  i0 = static_cast<int>(src);
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - static_cast<float>(i0);
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(
@@ -119,6 +129,12 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+
+// Named barrier over a subset of the CTA's warps (id 1..15; `count` = participating threads, multiple of 32).
+__device__ __forceinline__ void named_barrier(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

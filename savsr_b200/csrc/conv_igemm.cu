@@ -54,7 +54,6 @@ struct ConvParams {
   CUtensorMap tm_tile;
   CUtensorMap tm_halo;
   savsr_conv_group g[SAVSR_MAX_GROUPS];
-  savsr_rgb_skip skip;
   __nv_bfloat16* arena;
   int ngroups, batch, height, width, tiles_x, tiles_y;
   int ntaps;            // 1 or 9
@@ -75,27 +74,16 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   return v;
 }
 
-// ATen upsample_bilinear2d, align_corners = False (savsr_arch.py:739): source index and weight.
-__device__ __forceinline__ void bilinear_src(int dst, int in_size, int out_size, int& i0, int& i1, float& l1) {
-  const float scale = static_cast<float>(in_size) / static_cast<float>(out_size);
-  float src = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
-  src = src < 0.f ? 0.f : src;
-  i0 = static_cast<int>(src);
-  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
-  l1 = src - static_cast<float>(i0);
-}
-
 // Epilogue shared by the tensor-core kernel and the checker, in two phases so that every global load that does
 // not depend on the accumulator (bias, residuals, mask, bilinear skip) is issued BEFORE waiting for the MMAs of the
 // tile and its latency hides behind them.  `v` holds NC consecutive accumulator columns (output channels
 // col0 .. col0+NC) of pixel m = quad * 32 + lane of the tile.
-// NC = 32: bf16 arena destination (two warps per quadrant); NC = 16: AUX16 / RGB destinations.
+// NC = 32: bf16 arena destination (two warps per quadrant); NC = 16: AUX16 destination.
 template <int NC>
 struct EpiCtx {
   float bias[NC];      // reloaded only when the conv (group) changes
   uint4 r1[NC / 8], r2[NC / 8];
   float mk;
-  float skip[3];
   long pix;
   bool valid;
   int bias_group;
@@ -147,22 +135,6 @@ __device__ __forceinline__ void epi_prefetch(const ConvParams& p, const savsr_co
       const uint4* r = reinterpret_cast<const uint4*>(p.arena + ((static_cast<long>(c.res2_slot) * p.batch + n) * npix + c.pix) * kC + col0);
 #pragma unroll
       for (int j = 0; j < NC / 8; ++j) c.r2[j] = r[j];
-    }
-  } else if (p.dst_mode == SAVSR_DST_RGB) {
-    if (c.valid) {  // bilinear skip of the LR centre frame (savsr_arch.py:739)
-      int y0, y1, x0, x1;
-      float ly, lx;
-      bilinear_src(py, p.skip.h, p.height, y0, y1, ly);
-      bilinear_src(px, p.skip.w, p.width, x0, x1, lx);
-      const long plane = static_cast<long>(p.skip.h) * p.skip.w;
-      const float* xc = p.skip.x + (static_cast<long>(n) * p.skip.t + p.skip.centre) * 3 * plane;
-#pragma unroll
-      for (int ch = 0; ch < 3; ++ch) {
-        const float* pl = xc + ch * plane;
-        const float a = __ldg(pl + y0 * p.skip.w + x0), b = __ldg(pl + y0 * p.skip.w + x1);
-        const float cc = __ldg(pl + y1 * p.skip.w + x0), d = __ldg(pl + y1 * p.skip.w + x1);
-        c.skip[ch] = (1.f - ly) * ((1.f - lx) * a + lx * b) + ly * ((1.f - lx) * cc + lx * d);
-      }
     }
   }
 }
@@ -229,16 +201,10 @@ __device__ __forceinline__ void epi_finish(const ConvParams& p, const savsr_conv
       c.pool[(static_cast<long>(n) * npart + tile * 4 + quad) * kC + col0 + lane] = v[0];
     }
   } else {
-    if (p.dst_mode == SAVSR_DST_AUX16) {
-      if (c.valid) {
-        float4* d = reinterpret_cast<float4*>(static_cast<float*>(g.aux_dst) + (n * npix + c.pix) * 16);
+    if (c.valid) {   // SAVSR_DST_AUX16
+      float4* d = reinterpret_cast<float4*>(static_cast<float*>(g.aux_dst) + (n * npix + c.pix) * 16);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) d[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      }
-    } else if (c.valid) {  // SAVSR_DST_RGB: fp32 NCHW output
-      float* out = static_cast<float*>(g.aux_dst) + static_cast<long>(n) * 3 * npix + c.pix;
-#pragma unroll
-      for (int ch = 0; ch < 3; ++ch) out[ch * npix] = v[ch] + c.skip[ch];
+      for (int j = 0; j < 4; ++j) d[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
   }
 }
@@ -669,7 +635,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
     const int quad = warp & 3;          // TMEM lane quadrant this warp may access (warp id % 4)
     const int half = (warp - 2) >> 2;   // which 32-column half of the accumulator (N = 64 only)
     if (BN == 64 || half == 0) {
-      constexpr int NC = 16;             // columns per warp of the N = 16 destinations (AUX16 / RGB)
+      constexpr int NC = 16;             // columns per warp of the N = 16 destination (AUX16)
       EpiCtx<NC> ec;
       EpiQuad eq;
       ec.bias_group = -1;
@@ -1185,15 +1151,14 @@ extern "C" int savsr_arena_export(savsr_arena* a, int slot, float* nchw, savsr_s
 }
 
 extern "C" int savsr_conv(savsr_ctx* ctx, savsr_arena* arena, const savsr_conv_group* groups, int ngroups, int ksize,
-                          int n_tile, int dst_mode, const savsr_rgb_skip* skip, int impl, savsr_stream st) {
+                          int n_tile, int dst_mode, int impl, savsr_stream st) {
   SAVSR_REQUIRE(ctx && arena && groups, "savsr_conv: null pointer");
   DeviceGuard guard(ctx->device);
   SAVSR_REQUIRE(ngroups >= 0 && ngroups <= SAVSR_MAX_GROUPS, "savsr_conv: ngroups %d out of range [0,%d]", ngroups, SAVSR_MAX_GROUPS);
   SAVSR_REQUIRE(ksize == 1 || ksize == 3, "savsr_conv: ksize must be 1 or 3, got %d", ksize);
   SAVSR_REQUIRE(impl >= SAVSR_IMPL_TCGEN05_TAP && impl <= SAVSR_IMPL_CHECK, "savsr_conv: unknown impl %d", impl);
-  SAVSR_REQUIRE((n_tile == 64 && dst_mode == SAVSR_DST_ARENA) || (n_tile == 16 && (dst_mode == SAVSR_DST_AUX16 || dst_mode == SAVSR_DST_RGB)),
+  SAVSR_REQUIRE((n_tile == 64 && dst_mode == SAVSR_DST_ARENA) || (n_tile == 16 && dst_mode == SAVSR_DST_AUX16),
                 "savsr_conv: n_tile %d does not match dst_mode %d", n_tile, dst_mode);
-  SAVSR_REQUIRE(dst_mode != SAVSR_DST_RGB || (skip && skip->x), "savsr_conv: SAVSR_DST_RGB needs the skip arguments");
   if (ngroups == 0) return 0;
 
   ConvParams p;
@@ -1217,7 +1182,6 @@ extern "C" int savsr_conv(savsr_ctx* ctx, savsr_arena* arena, const savsr_conv_g
     }
     p.g[i] = g;
   }
-  if (skip) p.skip = *skip;
   p.arena = arena->base;
   p.ngroups = ngroups;
   p.batch = arena->batch;

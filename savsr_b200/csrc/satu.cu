@@ -314,73 +314,7 @@ __global__ void __launch_bounds__(kKstaThreads, 1) satu_kconv_sta_kernel(const _
   }
 }
 
-// ------------------------------------------------------------------------------------------------ bilinear corners
-struct Corner4 {
-  int off[4];   // element offset of the corner pixel inside the LR image (pixel index * 64), -1 = outside
-  float wt[4];
-};
-
-// bilinear corners, zeros padding, align_corners = True (ATen grid_sampler_2d)
-__device__ __forceinline__ Corner4 make_corners(float gx, float gy, int h, int w, int wp) {
-  const float ix = unnormalize(gx, w), iy = unnormalize(gy, h);
-  const float x0f = floorf(ix), y0f = floorf(iy);
-  const int x0 = static_cast<int>(x0f), y0 = static_cast<int>(y0f);
-  const float tx = ix - x0f, ty = iy - y0f;
-  Corner4 c;
-  const int xs[2] = {x0, x0 + 1}, ys[2] = {y0, y0 + 1};
-  const float wx[2] = {1.f - tx, tx}, wy[2] = {1.f - ty, ty};
-#pragma unroll
-  for (int a = 0; a < 2; ++a)
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      const bool in = xs[b] >= 0 && xs[b] < w && ys[a] >= 0 && ys[a] < h;
-      c.off[a * 2 + b] = in ? (ys[a] * wp + xs[b]) * kC : -1;
-      c.wt[a * 2 + b] = wy[a] * wx[b];
-    }
-  return c;
-}
-
-// ------------------------------------------------------------------------------------------------ fused HR kernel
-// gather(x) -> routed experts -> + gather(sta) -> 128->64 fusion conv, one 128-pixel HR tile at a time, with the three
-// small GEMMs on tcgen05 (accumulators in TMEM) and the gathers / routing on CUDA cores:
-//   U[128,32] = F[128,64] Wc^T            (all 4 experts' compress matrices stacked, savsr_arch.py:353-355, 368)
-//   V[e*8+k]  = r_e * sum_e' r_e' U[e'*8+k]                                     (routing, per pixel, in registers)
-//   O[128,64] = V[128,32] We^T ; fea = O + F                                    (expand + residual, 357-370)
-//   Y[128,64] = [S | fea][128,128] Wf^T + b                                     (fusion, 374; S = gathered sta)
-// F, S, V, fea tiles are written by the threads as bf16 in the 128-byte-swizzled K-major layout the UMMA reads.
-// The chain is sequential per tile; two CTAs per SM overlap each other's phases.
-struct FusedParams {
-  const __nv_bfloat16* lr;
-  __nv_bfloat16* hr;
-  const float* table;
-  const float* base_y;
-  const float* base_x;
-  const uint8_t* w_compress;  // packed [32][64]  (4 KB)
-  const uint8_t* w_expand;    // packed [64][64]  (8 KB, K columns 32..63 zero)
-  const uint8_t* w_fusion;    // packed 2 x [64][64] (16 KB): sta block, fea block
-  const float* bias;          // [64]
-  int batch, hp, wp, h, w, H, W;
-  int x_slot, sta_slot, dst_slot;
-  int tiles_per_img;
-  int fmt;
-};
-
-constexpr int kFusedThreads = 256;   // 8 warps: warp w owns TMEM lane quadrant w & 3 and column half w >> 2
-constexpr int kFusedSmem = 1024 + 3 * 16384 + 4096 + 8192 + 16384 + 2 * 128 * 32 + 128 * 16 + 256 + 64;
-
-__device__ __forceinline__ void gather8(const __nv_bfloat16* img, const Corner4& c, int chunk, float (&a)[8], int fmt) {
-  uint4 v[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) v[q] = c.off[q] >= 0 ? *reinterpret_cast<const uint4*>(img + c.off[q] + chunk * 8) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-  for (int e = 0; e < 8; ++e) a[e] = 0.f;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float wgt = c.wt[q];
-    a[0] += wgt * h_lo(v[q].x, fmt); a[1] += wgt * h_hi(v[q].x, fmt); a[2] += wgt * h_lo(v[q].y, fmt); a[3] += wgt * h_hi(v[q].y, fmt);
-    a[4] += wgt * h_lo(v[q].z, fmt); a[5] += wgt * h_hi(v[q].z, fmt); a[6] += wgt * h_lo(v[q].w, fmt); a[7] += wgt * h_hi(v[q].w, fmt);
-  }
-}
+// ------------------------------------------------------------------------------------------------ operand-tile helpers
 __device__ __forceinline__ uint4 pack8(const float (&a)[8], int fmt) {
   uint4 o;
   o.x = pack_h2(a[0], a[1], fmt); o.y = pack_h2(a[2], a[3], fmt); o.z = pack_h2(a[4], a[5], fmt); o.w = pack_h2(a[6], a[7], fmt);
@@ -389,205 +323,381 @@ __device__ __forceinline__ uint4 pack8(const float (&a)[8], int fmt) {
 // byte offset of 16-byte chunk `c` of row `r` in a [rows][128 B] SWIZZLE_128B tile
 __device__ __forceinline__ int swz(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
 
-__global__ void __launch_bounds__(kFusedThreads, 2) satu_fused_kernel(const FusedParams p) {
+// ------------------------------------------------------------------------------------------------ HR stage, one kernel
+// Everything of SATU at HR resolution and the tail, without any HR-resolution intermediate in memory
+// (savsr_arch.py:344-376 STAUpsample.forward from the gathers on, 738-739 tail + bilinear skip):
+//
+//   F = bilinear gather of x at base + offset, S = bilinear gather of sta at base + st_offset   (zeros padding, align_corners)
+//   U = F Wc^T (4 experts' compress matrices stacked) ; V[e*8+k] = r_e * sum_e' r_e' U[e'*8+k]  (routing, per pixel)
+//   fea = V We^T + F ; Y = [S | fea] Wf^T + bf ; sr = conv3x3(Y; Wt) + bt + bilinear(x_center)
+//
+// Between the gathers and the output everything is LINEAR given V, so fusion and tail are composed on the host:
+//   Z[q][tap*3+c] = S[q] Wcs^T + F[q] Wcf^T + V[q] Wv^T + zb ,   Wcs|Wcf = Wt_tap Wf ,  Wv = Wcf We ,  zb = Wt_tap bf
+//   sr[p][c] = bt[c] + sum_tap Z[p + d_tap][tap*3+c]   over the taps whose pixel p + d_tap lies inside the image
+// i.e. per HR pixel 27 partial products instead of a 64-channel feature, summed over the 3x3 neighbourhood from shared memory.
+// A CTA owns a 32 x 13 block of HR pixels; it evaluates Z on the 34 x 15 ringed block (510 pixels = 4 M-tiles of 128, 1.23x
+// recompute) and loops over the samples of the batch with the sample-independent sampling corners of the block cached in smem.
+//
+// Warp roles (17 warps):   9..16  gather: build the F and S operand tiles (16-bit, 128-byte swizzled K-major) in a 2-stage ring
+//                          8      MMA issuer (tcgen05, accumulators U and Z in TMEM, double buffered)
+//                          0..7   consumers, two groups alternating tiles: routing (U -> V tile), Z -> smem, and, once per
+//                                 block and sample, the 9-tap sum + bias + bilinear skip -> fp32 NCHW stores (128 B per warp row)
+struct HrParams {
+  const __nv_bfloat16* lr;
+  const float* table;        // [H*W][8]: offset x,y | st_offset x,y | r0..r3
+  const float* base_y;
+  const float* base_x;
+  const uint8_t* weights;    // 4 x [32 rows][128 B] K-major swizzled: Wc (rows e*8+k) | Wcf | Wcs | Wv (K = 32), rows of Wcf/Wcs/Wv = tap*3+c
+  const float* zbias;        // [32]: zb[tap*3+c], 27 used
+  const float* tail_bias;    // [3]
+  const float* x_in;         // [batch][t][3][h][w] fp32 (bilinear skip of the centre frame)
+  float* out;                // [batch][3][H][W] fp32
+  int batch, hp, wp, h, w, H, W;
+  int x_slot, sta_slot;
+  int t, centre;
+  int regions_x, nregions;
+  int fmt;
+};
+
+constexpr int kHrRW = 32, kHrRH = 13;                  // interior block
+constexpr int kHrPW = kHrRW + 2, kHrPH = kHrRH + 2;    // ringed block 34 x 15 = 510 pixels
+constexpr int kHrPix = 512;                            // 4 M-tiles
+constexpr int kHrTiles = 4;
+constexpr int kHrConsumerWarps = 8, kHrGatherWarps = 16;
+constexpr int kHrIssuerWarp = kHrConsumerWarps;
+constexpr int kHrThreads = 32 * (kHrConsumerWarps + 1 + kHrGatherWarps);
+constexpr int kHrStages = 2;
+constexpr int kHrZK = 27;
+// shared-memory map (bytes from the 1024-aligned base)
+constexpr int kHrOffFS = 0;                                    // [stages][F 16 KB | S 16 KB]
+constexpr int kHrOffV = kHrOffFS + kHrStages * 32768;          // [2][16 KB]
+constexpr int kHrOffW = kHrOffV + 2 * 16384;                   // 16 KB
+constexpr int kHrOffZ = kHrOffW + 16384;                       // __half [2 buffers][27][512]: partial products of two (block, sample) pairs
+constexpr int kHrOffCO = kHrOffZ + 2 * kHrZK * kHrPix * 2;     // uint4 [2][512]: element offsets of the four corner pixels inside the LR image
+constexpr int kHrOffCW = kHrOffCO + 2 * kHrPix * 16;           // uint2 [2][512]: the four bilinear weights as 16-bit pairs (w00 w01 | w10 w11), 0 = outside
+constexpr int kHrOffBar = kHrOffCW + 2 * kHrPix * 8;
+constexpr int kHrSmem = 1024 + kHrOffBar + 512;   // 16 mbarriers, the TMEM slot, zbias[32]
+
+// Packed 16-bit arithmetic of the gather: out = sum_q w_q * v_q on two channels at a time (HFMA2), in the operand format itself.
+// The result feeds the tensor core as a 16-bit operand anyway; accumulating the four corners in that format costs about one
+// extra rounding and needs 4x fewer instructions than convert + fp32 FMA + convert back (the gather is instruction-bound).
+template <int FMT> struct Pk;
+template <> struct Pk<SAVSR_FMT_BF16> {
+  using T2 = __nv_bfloat162;
+  static __device__ __forceinline__ uint32_t pair(float a, float b) { T2 r = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&r); }
+  static __device__ __forceinline__ T2 lo(uint32_t w) { return __low2bfloat162(*reinterpret_cast<T2*>(&w)); }
+  static __device__ __forceinline__ T2 hi(uint32_t w) { return __high2bfloat162(*reinterpret_cast<T2*>(&w)); }
+};
+template <> struct Pk<SAVSR_FMT_FP16> {
+  using T2 = __half2;
+  static __device__ __forceinline__ uint32_t pair(float a, float b) { T2 r = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&r); }
+  static __device__ __forceinline__ T2 lo(uint32_t w) { return __low2half2(*reinterpret_cast<T2*>(&w)); }
+  static __device__ __forceinline__ T2 hi(uint32_t w) { return __high2half2(*reinterpret_cast<T2*>(&w)); }
+};
+template <int FMT>
+__device__ __forceinline__ uint32_t pk_mul(uint32_t v, typename Pk<FMT>::T2 w) {
+  typename Pk<FMT>::T2 r = __hmul2(*reinterpret_cast<typename Pk<FMT>::T2*>(&v), w);
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+template <int FMT>
+__device__ __forceinline__ uint32_t pk_fma(uint32_t v, typename Pk<FMT>::T2 w, uint32_t acc) {
+  typename Pk<FMT>::T2 r = __hfma2(*reinterpret_cast<typename Pk<FMT>::T2*>(&v), w, *reinterpret_cast<typename Pk<FMT>::T2*>(&acc));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+template <int FMT>
+__device__ __forceinline__ uint4 pk_blend(const uint4 (&v)[4], uint2 w) {
+  const typename Pk<FMT>::T2 w0 = Pk<FMT>::lo(w.x), w1 = Pk<FMT>::hi(w.x), w2 = Pk<FMT>::lo(w.y), w3 = Pk<FMT>::hi(w.y);
+  uint4 a;
+  a.x = pk_mul<FMT>(v[0].x, w0); a.y = pk_mul<FMT>(v[0].y, w0); a.z = pk_mul<FMT>(v[0].z, w0); a.w = pk_mul<FMT>(v[0].w, w0);
+  a.x = pk_fma<FMT>(v[1].x, w1, a.x); a.y = pk_fma<FMT>(v[1].y, w1, a.y); a.z = pk_fma<FMT>(v[1].z, w1, a.z); a.w = pk_fma<FMT>(v[1].w, w1, a.w);
+  a.x = pk_fma<FMT>(v[2].x, w2, a.x); a.y = pk_fma<FMT>(v[2].y, w2, a.y); a.z = pk_fma<FMT>(v[2].z, w2, a.z); a.w = pk_fma<FMT>(v[2].w, w2, a.w);
+  a.x = pk_fma<FMT>(v[3].x, w3, a.x); a.y = pk_fma<FMT>(v[3].y, w3, a.y); a.z = pk_fma<FMT>(v[3].z, w3, a.z); a.w = pk_fma<FMT>(v[3].w, w3, a.w);
+  return a;
+}
+
+// ATen upsample_bilinear2d (align_corners = False) source index / weight with the size ratio precomputed by the caller.
+__device__ __forceinline__ void bilinear_src_scaled(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
+  float src = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  i0 = static_cast<int>(src);
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - static_cast<float>(i0);
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kHrThreads, 1) satu_hr_kernel(const __grid_constant__ HrParams p) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* sF = smem;                 // F, later fea (in place)      [128][128 B]
-  uint8_t* sS = smem + 16384;         // gathered sta                 [128][128 B]
-  uint8_t* sV = smem + 32768;         // V (K = 32 used)              [128][128 B]
-  uint8_t* sWc = smem + 49152;        // [32][128 B]
-  uint8_t* sWe = sWc + 4096;          // [64][128 B]
-  uint8_t* sWf = sWe + 8192;          // 2 x [64][128 B]
-  Corner4* cx = reinterpret_cast<Corner4*>(sWf + 16384);
-  Corner4* cs = cx + 128;
-  float* rt = reinterpret_cast<float*>(cs + 128);   // [128][4] routing weights
-  float* sbias = rt + 128 * 4;                      // [64]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sbias + 64);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint8_t* sFS = smem + kHrOffFS;
+  uint8_t* sV = smem + kHrOffV;
+  uint8_t* sW = smem + kHrOffW;
+  __half* sZ = reinterpret_cast<__half*>(smem + kHrOffZ);
+  uint4* sCO = reinterpret_cast<uint4*>(smem + kHrOffCO);
+  uint2* sCW = reinterpret_cast<uint2*>(smem + kHrOffCW);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kHrOffBar);
+  uint64_t* fs_full = bars;            // [2]  gather warps -> issuer
+  uint64_t* fs_empty = bars + 2;       // [2]  issuer (commit) -> gather warps
+  uint64_t* u_full = bars + 4;         // [2]  issuer (commit) -> consumers
+  uint64_t* v_full = bars + 6;         // [2]  consumers -> issuer
+  uint64_t* z_full = bars + 8;         // [2]  issuer (commit) -> consumers
+  uint64_t* acc_empty = bars + 10;     // [2]  consumers -> issuer: U / Z accumulators of the buffer are free again
+  uint64_t* zb_full = bars + 12;       // [2]  consumers -> gather warps: all 27 x 510 partial products of a (block, sample) are in shared memory
+  uint64_t* zb_empty = bars + 14;      // [2]  gather warps -> consumers: that buffer has been summed and may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quad = warp & 3, half = warp >> 2;
-  const int row = quad * 32 + lane;                 // tile row (= TMEM lane) this thread serves in the register phases
-  for (int i = tid; i < (4096 + 8192 + 16384) / 16; i += kFusedThreads) {
-    const uint8_t* src = i < 256 ? p.w_compress + i * 16 : i < 768 ? p.w_expand + (i - 256) * 16 : p.w_fusion + (i - 768) * 16;
-    *reinterpret_cast<uint4*>(sWc + i * 16) = *reinterpret_cast<const uint4*>(src);
+  for (int i = tid; i < 16384 / 16; i += kHrThreads) *reinterpret_cast<uint4*>(sW + i * 16) = __ldg(reinterpret_cast<const uint4*>(p.weights) + i);
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(fs_full + i, kHrGatherWarps); mbar_init(fs_empty + i, 1); mbar_init(u_full + i, 1);
+      mbar_init(v_full + i, 4); mbar_init(z_full + i, 1); mbar_init(acc_empty + i, 4);
+      mbar_init(zb_full + i, 4 * kHrTiles); mbar_init(zb_empty + i, kHrGatherWarps);
+    }
+    fence_barrier_init();
   }
-  // zero the V tile once (chunks 4..7 of every row, the unused K half, are never written again)
-  for (int i = tid; i < 1024; i += kFusedThreads) *reinterpret_cast<uint4*>(sV + i * 16) = make_uint4(0, 0, 0, 0);
-  if (tid < 64) sbias[tid] = __ldg(p.bias + tid);
-  if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
-  if (warp == 0) tmem_alloc<256>(tmem_slot);
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == kHrIssuerWarp) tmem_alloc<128>(tmem_slot);
+  if (tid < 32) reinterpret_cast<float*>(tmem_slot + 4)[tid] = __ldg(p.zbias + tid);
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tm = *tmem_slot;
-  const uint32_t tU = tm, tO = tm + 32, tY = tm + 96;
-  const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-  constexpr uint32_t hi = desc_hi_1024();
-  const uint32_t loF = (smem_u32(sF) >> 4) & 0x3fff, loS = (smem_u32(sS) >> 4) & 0x3fff, loV = (smem_u32(sV) >> 4) & 0x3fff;
-  const uint32_t loWc = (smem_u32(sWc) >> 4) & 0x3fff, loWe = (smem_u32(sWe) >> 4) & 0x3fff, loWf = (smem_u32(sWf) >> 4) & 0x3fff;
-  uint32_t phase = 0;
+  const uint32_t tm = *tmem_slot;                  // columns: U0 [0,32) Z0 [32,64) U1 [64,96) Z1 [96,128)
   const long NPIX = static_cast<long>(p.H) * p.W;
   const long lr_img = static_cast<long>(p.hp) * p.wp * kC;
-  const int total = p.batch * p.tiles_per_img;
 
-  for (int t = blockIdx.x; t < total; t += gridDim.x) {
-    const int n = t / p.tiles_per_img;
-    const long pix0 = static_cast<long>(t - n * p.tiles_per_img) * 128;
-    // ---- P0: per-pixel sampling corners and routing weights (threads 0..127, one pixel each)
-    if (tid < 128) {
-      const long pix = pix0 + tid;
-      if (pix < NPIX) {
-        const int i = pix / p.W, j = pix - static_cast<long>(i) * p.W;
-        const float4 t0 = *reinterpret_cast<const float4*>(p.table + pix * 8);
-        const float4 t1 = *reinterpret_cast<const float4*>(p.table + pix * 8 + 4);
-        const float bx = p.base_x[j], by = p.base_y[i];
-        const float wm1 = static_cast<float>(p.w - 1), hm1 = static_cast<float>(p.h - 1);
-        cx[tid] = make_corners(__fadd_rn(bx, __fdiv_rn(__fmul_rn(t0.x, 2.f), wm1)), __fadd_rn(by, __fdiv_rn(__fmul_rn(t0.y, 2.f), hm1)), p.h, p.w, p.wp);
-        cs[tid] = make_corners(__fadd_rn(bx, __fdiv_rn(__fmul_rn(t0.z, 2.f), wm1)), __fadd_rn(by, __fdiv_rn(__fmul_rn(t0.w, 2.f), hm1)), p.h, p.w, p.wp);
-        *reinterpret_cast<float4*>(rt + tid * 4) = t1;
-      } else {
-        Corner4 z;
+  if (warp > kHrIssuerWarp) {
+    // ================================ gather warps (operand producers + the 9-tap tail) ================================
+    const int gtid = tid - 32 * (kHrIssuerWarp + 1);
+    constexpr int kGT = 32 * kHrGatherWarps;
+    const float wm1 = static_cast<float>(p.w - 1), hm1 = static_cast<float>(p.h - 1);
+    const float sk_sy = static_cast<float>(p.h) / static_cast<float>(p.H), sk_sx = static_cast<float>(p.w) / static_cast<float>(p.W);
+    const int plane = p.h * p.w;
+    const float bt0 = __ldg(p.tail_bias), bt1 = __ldg(p.tail_bias + 1), bt2 = __ldg(p.tail_bias + 2);
+    uint32_t it = 0, rn = 0;                     // running tile / (block, sample) counters of this CTA
+    int prevY0 = 0, prevX0 = 0, prevN = -1;      // the (block, sample) whose partial products are summed next
+
+    // sr[p][c] = bt[c] + sum over the 3x3 taps inside the image of Z[p + d_tap][tap*3+c] + bilinear skip; one HR pixel per thread
+    auto tail = [&](uint32_t k, int Y0, int X0, int n) {
+      const int zb = k & 1;
+      mbar_wait(zb_full + zb, (k >> 1) & 1u);
+      const __half* z0 = sZ + zb * (kHrZK * kHrPix);
+      if (gtid < kHrRW * kHrRH) {
+        const int iy = gtid >> 5, ix = gtid & 31;
+        const int Y = Y0 + 1 + iy, X = X0 + 1 + ix;
+        if (Y < p.H && X < p.W) {
+          int y0, y1, x0, x1;
+          float ly, lx;
+          bilinear_src_scaled(Y, sk_sy, p.h, y0, y1, ly);
+          bilinear_src_scaled(X, sk_sx, p.w, x0, x1, lx);
+          const float* xc = p.x_in + static_cast<long>(n * p.t + p.centre) * 3 * plane;
+          const int o00 = y0 * p.w + x0, o01 = y0 * p.w + x1, o10 = y1 * p.w + x0, o11 = y1 * p.w + x1;
+          float sk[3];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { z.off[q] = -1; z.wt[q] = 0.f; }
-        cx[tid] = z; cs[tid] = z;
-        *reinterpret_cast<float4*>(rt + tid * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-    __syncthreads();
-    // ---- P1: bilinear gathers, (pixel, 8-channel chunk) per thread-iteration: 8 lanes read one 128-byte pixel row
-    const __nv_bfloat16* xs = p.lr + (static_cast<long>(p.x_slot) * p.batch + n) * lr_img;
-    const __nv_bfloat16* ss = p.lr + (static_cast<long>(p.sta_slot) * p.batch + n) * lr_img;
-#pragma unroll 2
-    for (int it = 0; it < 4; ++it) {
-      const int id = it * kFusedThreads + tid;
-      const int lp = id >> 3, chunk = id & 7;
-      float a[8], b[8];
-      gather8(xs, cx[lp], chunk, a, p.fmt);
-      gather8(ss, cs[lp], chunk, b, p.fmt);
-      *reinterpret_cast<uint4*>(sF + swz(lp, chunk)) = pack8(a, p.fmt);
-      *reinterpret_cast<uint4*>(sS + swz(lp, chunk)) = pack8(b, p.fmt);
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    tc_fence_before();
-    __syncthreads();
-    // ---- P2: U = F Wc^T   (M 128, N 32, K 64)
-    if (warp == 0) {
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tU, make_desc64(hi, loF + 2 * k), make_desc64(hi, loWc + 2 * k), umma_idesc_f16(32, p.fmt), k ? 1u : 0u);
-        umma_commit(bar);
-      }
-      __syncwarp();
-    }
-    mbar_wait(bar, phase); phase ^= 1;
-    tc_fence_after();
-    // ---- P3: routing in registers -> V tile (warps 0-3)
-    if (half == 0) {
-      uint32_t u0[16], u1[16];
-      tmem_ld16(tU + lane_addr, u0);
-      tmem_ld16(tU + lane_addr + 16, u1);
-      tmem_ld_wait();
-      const float4 r = *reinterpret_cast<const float4*>(rt + row * 4);
-      float tk[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        tk[k] = r.x * __uint_as_float(u0[k]) + r.y * __uint_as_float(u0[8 + k]) + r.z * __uint_as_float(u1[k]) + r.w * __uint_as_float(u1[8 + k]);
-      const float re[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float v[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = re[e] * tk[k];
-        *reinterpret_cast<uint4*>(sV + swz(row, e)) = pack8(v, p.fmt);
-      }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    tc_fence_before();
-    __syncthreads();
-    // ---- P4: O = V We^T   (M 128, N 64, K 32)
-    if (warp == 0) {
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < 2; ++k) umma_bf16(tO, make_desc64(hi, loV + 2 * k), make_desc64(hi, loWe + 2 * k), umma_idesc_f16(64, p.fmt), k ? 1u : 0u);
-        umma_commit(bar);
-      }
-      __syncwarp();
-    }
-    mbar_wait(bar, phase); phase ^= 1;
-    tc_fence_after();
-    // ---- P5: fea = O + F, in place over the F tile (each warp: 32 rows x 32 columns)
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      uint32_t o[16];
-      tmem_ld16(tO + lane_addr + half * 32 + 16 * j, o);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c2 = 0; c2 < 2; ++c2) {
-        uint4* ptr = reinterpret_cast<uint4*>(sF + swz(row, half * 4 + 2 * j + c2));
-        const uint4 f = *ptr;
-        float v[8];
-        v[0] = __uint_as_float(o[8 * c2 + 0]) + h_lo(f.x, p.fmt); v[1] = __uint_as_float(o[8 * c2 + 1]) + h_hi(f.x, p.fmt);
-        v[2] = __uint_as_float(o[8 * c2 + 2]) + h_lo(f.y, p.fmt); v[3] = __uint_as_float(o[8 * c2 + 3]) + h_hi(f.y, p.fmt);
-        v[4] = __uint_as_float(o[8 * c2 + 4]) + h_lo(f.z, p.fmt); v[5] = __uint_as_float(o[8 * c2 + 5]) + h_hi(f.z, p.fmt);
-        v[6] = __uint_as_float(o[8 * c2 + 6]) + h_lo(f.w, p.fmt); v[7] = __uint_as_float(o[8 * c2 + 7]) + h_hi(f.w, p.fmt);
-        *ptr = pack8(v, p.fmt);
-      }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    tc_fence_before();
-    __syncthreads();
-    // ---- P6: Y = [S | fea] Wf^T   (M 128, N 64, K 128)
-    if (warp == 0) {
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tY, make_desc64(hi, loS + 2 * k), make_desc64(hi, loWf + 2 * k), umma_idesc_f16(64, p.fmt), k ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tY, make_desc64(hi, loF + 2 * k), make_desc64(hi, loWf + 512 + 2 * k), umma_idesc_f16(64, p.fmt), 1u);
-        umma_commit(bar);
-      }
-      __syncwarp();
-    }
-    mbar_wait(bar, phase); phase ^= 1;
-    tc_fence_after();
-    // ---- P7: + bias -> 16-bit HR feature.  16x256b TMEM loads over SAVSR_ROWS_QUAD-ordered fusion weights: thread
-    // (g, q) holds pixels g + 8 j of its quadrant and the 8 consecutive channels half * 32 + 8 q .., so a store
-    // instruction writes 64 contiguous bytes per thread quad, 8 lines per warp (one pixel per lane touched 32 lines).
-    {
-      const int g = lane >> 2, q = lane & 3;
-      uint32_t ya[16], yb[16];
-      tmem_ld_16x256b_x4(tY + lane_addr + half * 32, ya);
-      tmem_ld_16x256b_x4(tY + lane_addr + (16u << 16) + half * 32, yb);
-      tmem_ld_wait();
-      const int ch0 = half * 32 + q * 8;
-      float bias8[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) bias8[i] = sbias[ch0 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const long pix = pix0 + quad * 32 + g + 8 * j;
-        if (pix < NPIX) {
-          const uint32_t* y = j < 2 ? ya : yb;
-          float v[8];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            v[2 * k] = __uint_as_float(y[4 * k + 2 * (j & 1)]) + bias8[2 * k];
-            v[2 * k + 1] = __uint_as_float(y[4 * k + 2 * (j & 1) + 1]) + bias8[2 * k + 1];
+          for (int ch = 0; ch < 3; ++ch) {
+            const float* pl = xc + ch * plane;
+            const float a = __ldg(pl + o00), bb = __ldg(pl + o01), cc = __ldg(pl + o10), d = __ldg(pl + o11);
+            sk[ch] = (1.f - ly) * ((1.f - lx) * a + lx * bb) + ly * ((1.f - lx) * cc + lx * d);
           }
-          *reinterpret_cast<uint4*>(p.hr + ((static_cast<long>(p.dst_slot) * p.batch + n) * NPIX + pix) * kC + ch0) = pack8(v, p.fmt);
+          float acc0 = bt0, acc1 = bt1, acc2 = bt2;
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const bool vy = static_cast<unsigned>(Y + dy - 1) < static_cast<unsigned>(p.H);
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              const bool v = vy && static_cast<unsigned>(X + dx - 1) < static_cast<unsigned>(p.W);
+              const __half* z = z0 + ((dy * 3 + dx) * 3) * kHrPix + (iy + dy) * kHrPW + ix + dx;
+              acc0 += v ? __half2float(z[0]) : 0.f;
+              acc1 += v ? __half2float(z[kHrPix]) : 0.f;
+              acc2 += v ? __half2float(z[2 * kHrPix]) : 0.f;
+            }
+          }
+          float* o = p.out + static_cast<long>(n) * 3 * NPIX + static_cast<long>(Y) * p.W + X;
+          o[0] = acc0 + sk[0]; o[NPIX] = acc1 + sk[1]; o[2 * NPIX] = acc2 + sk[2];
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(zb_empty + zb);
+    };
+
+    for (int r = blockIdx.x; r < p.nregions; r += gridDim.x) {
+      const int Y0 = (r / p.regions_x) * kHrRH - 1, X0 = (r % p.regions_x) * kHrRW - 1;   // origin of the ringed block
+      named_barrier(2, kGT);             // every gather warp is done reading the previous block's corners
+      for (int i = gtid; i < kHrPix; i += kGT) {
+        const int py = i / kHrPW, px = i - py * kHrPW;
+        const int Y = Y0 + py, X = X0 + px;
+        uint4 co[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        uint2 cw[2] = {make_uint2(0, 0), make_uint2(0, 0)};
+        if (i < kHrPW * kHrPH && Y >= 0 && Y < p.H && X >= 0 && X < p.W) {
+          const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.table + (static_cast<long>(Y) * p.W + X) * 8));
+          const float bx = __ldg(p.base_x + X), by = __ldg(p.base_y + Y);
+          const float off[2][2] = {{t0.x, t0.y}, {t0.z, t0.w}};
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            // grid = base + offset * 2 / (n - 1) (savsr_arch.py:285-287), then ATen's align_corners un-normalisation
+            const float gx = __fadd_rn(bx, __fdiv_rn(__fmul_rn(off[s][0], 2.f), wm1));
+            const float gy = __fadd_rn(by, __fdiv_rn(__fmul_rn(off[s][1], 2.f), hm1));
+            const float ix = unnormalize(gx, p.w), iy = unnormalize(gy, p.h);
+            const float x0f = floorf(ix), y0f = floorf(iy);
+            const int x0 = static_cast<int>(x0f), y0 = static_cast<int>(y0f);
+            const float tx = ix - x0f, ty = iy - y0f;
+            const bool vx0 = x0 >= 0 && x0 < p.w, vx1 = x0 + 1 >= 0 && x0 + 1 < p.w;
+            const bool vy0 = y0 >= 0 && y0 < p.h, vy1 = y0 + 1 >= 0 && y0 + 1 < p.h;
+            const int xa = vx0 ? x0 : 0, xb = vx1 ? x0 + 1 : 0, ya = (vy0 ? y0 : 0) * p.wp, yb = (vy1 ? y0 + 1 : 0) * p.wp;
+            const float wx0 = vx0 ? 1.f - tx : 0.f, wx1 = vx1 ? tx : 0.f, wy0 = vy0 ? 1.f - ty : 0.f, wy1 = vy1 ? ty : 0.f;
+            co[s] = make_uint4((ya + xa) * kC, (ya + xb) * kC, (yb + xa) * kC, (yb + xb) * kC);
+            cw[s] = make_uint2(Pk<FMT>::pair(wy0 * wx0, wy0 * wx1), Pk<FMT>::pair(wy1 * wx0, wy1 * wx1));
+          }
+        }
+        sCO[i] = co[0]; sCO[kHrPix + i] = co[1];
+        sCW[i] = cw[0]; sCW[kHrPix + i] = cw[1];
+      }
+      named_barrier(2, kGT);
+      for (int n = 0; n < p.batch; ++n, ++rn) {
+        const __nv_bfloat16* img0 = p.lr + (static_cast<long>(p.x_slot) * p.batch + n) * lr_img;
+        const __nv_bfloat16* img1 = p.lr + (static_cast<long>(p.sta_slot) * p.batch + n) * lr_img;
+        for (int t = 0; t < kHrTiles; ++t, ++it) {
+          const int stage = it & 1;
+          mbar_wait(fs_empty + stage, ((it >> 1) & 1u) ^ 1u);
+          uint8_t* dst = sFS + stage * 32768;
+#pragma unroll 1
+          for (int id = gtid; id < 128 * 8; id += kGT) {
+            const int lp = id >> 3, chunk = id & 7;
+            const int i = t * 128 + lp;
+            const uint4 c0 = sCO[i], c1 = sCO[kHrPix + i];
+            const uint2 w0 = sCW[i], w1 = sCW[kHrPix + i];
+            const __nv_bfloat16* b0 = img0 + chunk * 8;
+            const __nv_bfloat16* b1 = img1 + chunk * 8;
+            uint4 v0[4], v1[4];
+            v0[0] = __ldg(reinterpret_cast<const uint4*>(b0 + c0.x)); v0[1] = __ldg(reinterpret_cast<const uint4*>(b0 + c0.y));
+            v0[2] = __ldg(reinterpret_cast<const uint4*>(b0 + c0.z)); v0[3] = __ldg(reinterpret_cast<const uint4*>(b0 + c0.w));
+            v1[0] = __ldg(reinterpret_cast<const uint4*>(b1 + c1.x)); v1[1] = __ldg(reinterpret_cast<const uint4*>(b1 + c1.y));
+            v1[2] = __ldg(reinterpret_cast<const uint4*>(b1 + c1.z)); v1[3] = __ldg(reinterpret_cast<const uint4*>(b1 + c1.w));
+            const int so = swz(lp, chunk);
+            *reinterpret_cast<uint4*>(dst + so) = pk_blend<FMT>(v0, w0);
+            *reinterpret_cast<uint4*>(dst + 16384 + so) = pk_blend<FMT>(v1, w1);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(fs_full + stage);
+        }
+        // the previous (block, sample) has long been through the tensor core by now: sum its taps while this one's tiles drain
+        if (prevN >= 0) tail(rn - 1, prevY0, prevX0, prevN);
+        prevY0 = Y0; prevX0 = X0; prevN = n;
+      }
+    }
+    if (prevN >= 0) tail(rn - 1, prevY0, prevX0, prevN);
+  } else if (warp == kHrIssuerWarp) {
+    // ================================ MMA issuer (warp-uniform control flow, elected issue) ================================
+    constexpr uint32_t hi = desc_hi_1024();
+    const uint32_t idesc = umma_idesc_f16(32, FMT), idesc64 = umma_idesc_f16(64, FMT);
+    const uint32_t loFS = (smem_u32(sFS) >> 4) & 0x3fff, loV = (smem_u32(sV) >> 4) & 0x3fff, loW = (smem_u32(sW) >> 4) & 0x3fff;
+    const uint32_t loWc = loW, loWcs = loW + (8192 >> 4), loWv = loW + (12288 >> 4);    // Wcf sits right behind Wc (rows 32..63 of the N = 64 tile)
+    int total = 0;
+    for (int r = blockIdx.x; r < p.nregions; r += gridDim.x) total += p.batch * kHrTiles;
+    for (int it = 0; it <= total; ++it) {
+      if (it > 0) {
+        // second GEMM of the previous tile: Z += V Wv^T (K = 32), as soon as the consumers have written its V tile
+        const int pb = (it - 1) & 1;
+        mbar_wait(v_full + pb, ((it - 1) >> 1) & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            umma_bf16(tm + pb * 64 + 32, make_desc64(hi, loV + pb * (16384 >> 4) + 2 * k), make_desc64(hi, loWv + 2 * k), idesc, 1u);
+          umma_commit(z_full + pb);
+        }
+        __syncwarp();
+      }
+      if (it == total) break;
+      const int b = it & 1;           // stage of the F/S ring == accumulator buffer
+      mbar_wait(fs_full + b, (it >> 1) & 1u);
+      mbar_wait(acc_empty + b, ((it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t loF = loFS + b * (32768 >> 4), loS = loF + (16384 >> 4);
+        // [U | Z] = F [Wc ; Wcf]^T in ONE N = 64 chain (the two weight tiles are adjacent in shared memory and U, Z adjacent in
+        // TMEM), so the F tile is read once; then Z += S Wcs^T
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tm + b * 64, make_desc64(hi, loF + 2 * k), make_desc64(hi, loWc + 2 * k), idesc64, k ? 1u : 0u);
+        umma_commit(u_full + b);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tm + b * 64 + 32, make_desc64(hi, loS + 2 * k), make_desc64(hi, loWcs + 2 * k), idesc, 1u);
+        umma_commit(fs_empty + b);     // the operand stage may be refilled once these MMAs have read it
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================================ consumers: routing (U -> V tile) and Z -> shared memory ================================
+    const int grp = warp >> 2, quad = warp & 3;
+    const int m = quad * 32 + lane;                         // tile row = TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    const float* zbv = reinterpret_cast<const float*>(tmem_slot + 4);   // zbias staged in shared memory by the prologue
+    uint32_t it0 = 0, rn = 0;                               // tile counter at the start of the current (block, sample); pair counter
+    for (int r = blockIdx.x; r < p.nregions; r += gridDim.x) {
+      const int Y0 = (r / p.regions_x) * kHrRH - 1, X0 = (r % p.regions_x) * kHrRW - 1;
+      for (int n = 0; n < p.batch; ++n, it0 += kHrTiles, ++rn) {
+        __half* zdst = sZ + (rn & 1) * (kHrZK * kHrPix);
+        for (int t = grp; t < kHrTiles; t += 2) {
+          const uint32_t it = it0 + t;
+          const int b = grp;                                // it & 1 == grp because it0 is a multiple of 4
+          const uint32_t par = (it >> 1) & 1u;
+          const int i = t * 128 + m;
+          const int py = i / kHrPW, px = i - py * kHrPW;
+          const int Y = Y0 + py, X = X0 + px;
+          float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < kHrPW * kHrPH && Y >= 0 && Y < p.H && X >= 0 && X < p.W)
+            rr = __ldg(reinterpret_cast<const float4*>(p.table + (static_cast<long>(Y) * p.W + X) * 8 + 4));
+          // ---- routing: U -> V
+          mbar_wait(u_full + b, par);
+          tc_fence_after();
+          {
+            uint32_t u0[16], u1[16];
+            tmem_ld16(tm + lane_addr + b * 64, u0);
+            tmem_ld16(tm + lane_addr + b * 64 + 16, u1);
+            tmem_ld_wait();
+            float tk[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              tk[k] = rr.x * __uint_as_float(u0[k]) + rr.y * __uint_as_float(u0[8 + k]) + rr.z * __uint_as_float(u1[k]) + rr.w * __uint_as_float(u1[8 + k]);
+            const float re[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float v[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[k] = re[e] * tk[k];
+              *reinterpret_cast<uint4*>(sV + b * 16384 + swz(m, e)) = pack8(v, FMT);
+            }
+          }
+          fence_proxy_async();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(v_full + b);
+          // ---- Z (+ the fusion bias seen through the tail taps) -> shared memory as fp16 partial products
+          mbar_wait(z_full + b, par);
+          tc_fence_after();
+          {
+            uint32_t z0[16], z1[16];
+            tmem_ld16(tm + lane_addr + b * 64 + 32, z0);
+            tmem_ld16(tm + lane_addr + b * 64 + 48, z1);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + b);
+            mbar_wait(zb_empty + (rn & 1), ((rn >> 1) & 1u) ^ 1u);      // the tail of pair rn - 2 has been summed
+#pragma unroll
+            for (int k = 0; k < 16; ++k) zdst[k * kHrPix + i] = __float2half_rn(__uint_as_float(z0[k]) + zbv[k]);
+#pragma unroll
+            for (int k = 16; k < kHrZK; ++k) zdst[k * kHrPix + i] = __float2half_rn(__uint_as_float(z1[k - 16]) + zbv[k]);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(zb_full + (rn & 1));
         }
       }
     }
-    tc_fence_before();
-    __syncthreads();   // the next tile overwrites cx/cs and the F/S/V tiles
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) { tc_fence_after(); tmem_dealloc<256>(tm); }
+  if (warp == kHrIssuerWarp) { tc_fence_after(); tmem_dealloc<128>(tm); }
 }
 
 }  // namespace savsr
@@ -646,28 +756,30 @@ extern "C" int savsr_satu_kconv_sta(savsr_ctx* ctx, savsr_arena* arena, int a_sl
   return 0;
 }
 
-extern "C" int savsr_satu_fused(savsr_ctx* ctx, savsr_arena* lr, int x_slot, int sta_slot, int h, int w, savsr_arena* hr, int dst_slot,
-                                const float* table, const float* base_y, const float* base_x, const void* w_compress,
-                                const void* w_expand, const void* w_fusion, const float* fusion_bias, savsr_stream st) {
-  SAVSR_REQUIRE(ctx && lr && hr && table && base_y && base_x && w_compress && w_expand && w_fusion && fusion_bias, "savsr_satu_fused: null pointer");
-  SAVSR_REQUIRE(lr->batch == hr->batch, "savsr_satu_fused: LR batch %d != HR batch %d", lr->batch, hr->batch);
-  SAVSR_REQUIRE(x_slot >= 0 && x_slot < lr->nslots && sta_slot >= 0 && sta_slot < lr->nslots, "savsr_satu_fused: LR slot out of range");
-  SAVSR_REQUIRE(dst_slot >= 0 && dst_slot < hr->nslots, "savsr_satu_fused: HR slot out of range");
-  SAVSR_REQUIRE(h >= 2 && w >= 2 && h <= lr->height && w <= lr->width, "savsr_satu_fused: region %dx%d exceeds LR arena", h, w);
-  if (lr->batch == 0) return 0;
+extern "C" int savsr_satu_hr(savsr_ctx* ctx, savsr_arena* lr, int x_slot, int sta_slot, int h, int w, int H, int W,
+                             const float* table, const float* base_y, const float* base_x, const void* weights,
+                             const float* zbias, const float* tail_bias, const float* x_in, int t, int centre, float* out,
+                             savsr_stream st) {
+  SAVSR_REQUIRE(ctx && lr && table && base_y && base_x && weights && zbias && tail_bias && x_in && out, "savsr_satu_hr: null pointer");
   DeviceGuard guard(ctx->device);
-  if (int rc = ensure_smem_attr(ctx, kAttrFused, satu_fused_kernel, kFusedSmem)) return rc;
-  FusedParams p;
-  p.lr = lr->base; p.hr = hr->base; p.table = table; p.base_y = base_y; p.base_x = base_x;
-  p.w_compress = static_cast<const uint8_t*>(w_compress); p.w_expand = static_cast<const uint8_t*>(w_expand);
-  p.w_fusion = static_cast<const uint8_t*>(w_fusion); p.bias = fusion_bias;
-  p.batch = lr->batch; p.hp = lr->height; p.wp = lr->width; p.h = h; p.w = w; p.H = hr->height; p.W = hr->width;
-  p.x_slot = x_slot; p.sta_slot = sta_slot; p.dst_slot = dst_slot; p.fmt = ctx->fmt;
-  const long npix = static_cast<long>(p.H) * p.W;
-  p.tiles_per_img = static_cast<int>((npix + 127) / 128);
-  const int total = p.batch * p.tiles_per_img;
-  const int grid = total < 2 * ctx->sm_count ? total : 2 * ctx->sm_count;
-  satu_fused_kernel<<<grid, kFusedThreads, kFusedSmem, static_cast<cudaStream_t>(st)>>>(p);
+  SAVSR_REQUIRE(x_slot >= 0 && x_slot < lr->nslots && sta_slot >= 0 && sta_slot < lr->nslots, "savsr_satu_hr: LR slot out of range");
+  SAVSR_REQUIRE(h >= 2 && w >= 2 && h <= lr->height && w <= lr->width, "savsr_satu_hr: region %dx%d exceeds LR arena", h, w);
+  SAVSR_REQUIRE(h < 65536 && w < 65536, "savsr_satu_hr: LR frames larger than 65535 pixels per side are not supported");
+  SAVSR_REQUIRE(H >= 1 && W >= 1 && t >= 1 && centre >= 0 && centre < t, "savsr_satu_hr: bad HR size %dx%d or window (%d, %d)", H, W, t, centre);
+  if (lr->batch == 0) return 0;
+  const bool fp16 = ctx->fmt == SAVSR_FMT_FP16;
+  if (int rc = fp16 ? ensure_smem_attr(ctx, kAttrSatuHr + 0, satu_hr_kernel<SAVSR_FMT_FP16>, kHrSmem)
+                    : ensure_smem_attr(ctx, kAttrSatuHrBf16, satu_hr_kernel<SAVSR_FMT_BF16>, kHrSmem)) return rc;
+  HrParams p;
+  p.lr = lr->base; p.table = table; p.base_y = base_y; p.base_x = base_x;
+  p.weights = static_cast<const uint8_t*>(weights); p.zbias = zbias; p.tail_bias = tail_bias; p.x_in = x_in; p.out = out;
+  p.batch = lr->batch; p.hp = lr->height; p.wp = lr->width; p.h = h; p.w = w; p.H = H; p.W = W;
+  p.x_slot = x_slot; p.sta_slot = sta_slot; p.t = t; p.centre = centre; p.fmt = ctx->fmt;
+  p.regions_x = (W + kHrRW - 1) / kHrRW;
+  p.nregions = p.regions_x * ((H + kHrRH - 1) / kHrRH);
+  const int grid = p.nregions < ctx->sm_count ? p.nregions : ctx->sm_count;
+  if (fp16) satu_hr_kernel<SAVSR_FMT_FP16><<<grid, kHrThreads, kHrSmem, static_cast<cudaStream_t>(st)>>>(p);
+  else satu_hr_kernel<SAVSR_FMT_BF16><<<grid, kHrThreads, kHrSmem, static_cast<cudaStream_t>(st)>>>(p);
   SAVSR_CUDA(cudaGetLastError());
   return 0;
 }

@@ -99,6 +99,43 @@ class _Slots:
         self.free.extend(slots)
 
 
+def satu_hr_compose(P: Dict[str, torch.Tensor], device: torch.device):
+    """Host-side composition of the linear chain fusion (1x1, 128->64) -> tail (3x3, 64->3), savsr_arch.py:374, 738, for
+    savsr_satu_hr: rows k = (dy*3+dx)*3 + c.  Returns fp32 (Wc [32,64], Wcf [27,64], Wcs [27,64], Wv [27,32], zb [32]):
+        Z[q][k] = S[q] Wcs^T + F[q] Wcf^T + V[q] Wv^T + zb ;   sr[p][c] = bt[c] + sum_tap Z[p + d_tap][tap*3+c]
+    (computed in float64, rounded once)."""
+    g = lambda name: P[name].detach().to(device, torch.float64)   # noqa: E731
+    u = "upsample"
+    Wf = g(u + ".fusion.weight").view(64, 128)
+    bf = g(u + ".fusion.bias")
+    Wt = g("tail.weight").permute(2, 3, 0, 1).reshape(27, 64)                           # [(dy,dx,c)][o]
+    comb = Wt @ Wf                                                                        # [27, 128]: in = [sta_s | fea] (374: sta first)
+    Wcs, Wcf = comb[:, :64], comb[:, 64:]
+    We = g(u + ".weight_expand").view(4, 64, 8).permute(1, 0, 2).reshape(64, 32)         # [c][e*8+k]
+    Wv = Wcf @ We                                                                         # fea = V We^T + F
+    Wc = g(u + ".weight_compress").reshape(32, 64)                                       # rows e*8+k
+    zb = torch.zeros(32, dtype=torch.float64, device=device)
+    zb[:27] = Wt @ bf
+    return Wc.float(), Wcf.float().contiguous(), Wcs.float().contiguous(), Wv.float(), zb.float()
+
+
+def satu_hr_pack(parts, fmt: int, device: torch.device) -> torch.Tensor:
+    """The four B operands of savsr_satu_hr (Wc | Wcf | Wcs | Wv) as [32 rows][128 B] K-major 128-byte-swizzled 16-bit tiles
+    (16 KB): the 16-byte chunk c of row n sits at chunk position c ^ (n & 7)."""
+    dt = torch.float16 if fmt == K.FMT_FP16 else torch.bfloat16
+    n = torch.arange(32, device=device).view(32, 1)
+    pos = torch.arange(8, device=device).view(1, 8) ^ (n & 7)                            # [32, 8]
+    tiles = []
+    for m in parts[:4]:
+        full = torch.zeros(32, 64, device=device)
+        full[:m.shape[0], :m.shape[1]] = m
+        src = full.to(dt).view(32, 8, 8)
+        tile = torch.zeros_like(src)
+        tile.scatter_(1, pos.view(32, 8, 1).expand(32, 8, 8), src)
+        tiles.append(tile.reshape(-1))
+    return torch.cat(tiles).view(torch.uint8).contiguous()
+
+
 class Plan:
     def __init__(self, params: Dict[str, torch.Tensor], batch: int, h: int, w: int, scale, device: torch.device,
                  conv_impl: str = "tap", num_frame: int = 7, taps: Optional[Sequence[str]] = None, precision: str = "bf16",
@@ -201,20 +238,19 @@ class Plan:
         return g
 
     def _conv(self, arena: K.Arena, groups: Sequence[K.ConvGroup], ksize: int = 3, n_tile: int = 64,
-              dst_mode: int = K.DST_ARENA, skip: Optional[K.RgbSkip] = None, alg_ci: Optional[Sequence[int]] = None,
-              alg_co: Optional[int] = None, kind: Optional[str] = None) -> None:
+              dst_mode: int = K.DST_ARENA, alg_ci: Optional[Sequence[int]] = None, alg_co: Optional[int] = None,
+              kind: Optional[str] = None) -> None:
         """Emit one batched savsr_conv launch.  `alg_ci` / `alg_co`: ALGORITHMIC input channels per group / output channels,
-        where they differ from the padded GEMM shape (first layer: 3 and 6 of 64; tail: 3 of 16) -- the FLOP count of the
+        where they differ from the padded GEMM shape (first layer: 3 and 6 of 64) -- the FLOP count of the
         roofline uses the reference's channel counts, never the zero padding."""
         arr = (K.ConvGroup * len(groups))(*groups)
         self._keep.append(arr)
-        skip_ref = C.byref(skip) if skip is not None else None
         lib, ctx, ah, n, impl = self.lib, self.ctx.handle, arena.handle, len(groups), self.impl
         co = alg_co if alg_co is not None else (64 if n_tile == 64 else 16)      # real output channels
         ci = list(alg_ci) if alg_ci is not None else [64 * g.nsrc for g in groups]
         flops = 2.0 * self.B * arena.height * arena.width * co * ksize * ksize * sum(ci)
         osa = any(g.weight_sample_stride != 0 for g in groups)
-        self._emit(lambda st: lib.savsr_conv(ctx, ah, arr, n, ksize, n_tile, dst_mode, skip_ref, impl, st),
+        self._emit(lambda st: lib.savsr_conv(ctx, ah, arr, n, ksize, n_tile, dst_mode, impl, st),
                    kind=kind or f"conv{ksize}x{ksize}_n{n_tile}", flops=flops,
                    detail=f"g{n}s{groups[0].nsrc}" + ("osa" if osa else ""))
 
@@ -223,7 +259,7 @@ class Plan:
         program, before later stages recycle it.  Not emitted in production plans."""
         if name not in self.taps:
             return
-        a = self.lr if arena == "lr" else self.hr
+        a = self.lr
         buf = self._buf(self.B, 64, a.height, a.width)
         self.tap_bufs[name] = buf
         lib, ah, ptr = self.lib, a.handle, buf.data_ptr()
@@ -326,9 +362,7 @@ class Plan:
         self.arena_lr_t = self._buf(self.n_lr_slots * B, self.hp, self.wp, 64, dtype=torch.bfloat16)
         self.arena_lr_t[zero * B:(zero + 1) * B].zero_()
         self.lr = K.Arena(self.ctx, self.arena_lr_t.data_ptr(), self.n_lr_slots, B, self.hp, self.wp)
-        self.arena_hr_t = self._buf(B, self.H, self.W, 64, dtype=torch.bfloat16)          # fused HR feature only
-        self.hr = K.Arena(self.ctx, self.arena_hr_t.data_ptr(), 1, B, self.H, self.W)
-        lr, hr = self.lr, self.hr
+        lr = self.lr
         self.x_in = self._buf(B, t, 3, self.h, self.w)
         self.out = self._buf(B, 3, self.H, self.W)
         xin = self.x_in.data_ptr()
@@ -459,7 +493,7 @@ class Plan:
                          lambda: self._p(u + ".kernel_conv.0.weight").view(64, 25, 64).permute(1, 0, 2).reshape(1600, 64, 1, 1))
         bkp = self._dev(u + ".kernel_conv.tapmajor.bias", lambda: self._p(u + ".kernel_conv.0.bias").view(64, 25).t().contiguous())
         STA, = take(1)
-        lrh, hrh, hh, ww = lr.handle, hr.handle, self.h, self.w
+        lrh, hh, ww = lr.handle, self.h, self.w
         # kernel_conv + sta_conv in one kernel: the 25 per-pixel kernels stay in TMEM (savsr_arch.py:297-313, 326)
         kflops = 2.0 * B * self.hp * self.wp * 64 * 1600
         self._emit(lambda st: lib.savsr_satu_kconv_sta(ctx, lrh, A, TR, STA, hh, ww, wkp, bkp, 0.1, st), kind="satu_kconv_sta",
@@ -485,28 +519,18 @@ class Plan:
                                      self.base_y.data_ptr(), self.base_x.data_ptr(), self.corner_y.data_ptr(),
                                      self.corner_x.data_ptr(), self.table.data_ptr(), self._stream().cuda_stream))
         tab, by, bx = self.table.data_ptr(), self.base_y.data_ptr(), self.base_x.data_ptr()
-        # HR stage: gather + routed experts + 128->64 fusion in one tensor-core kernel (savsr_arch.py:364-374)
-        def we_all():
-            wz = torch.zeros(64, 64, 1, 1, device=self.device)
-            wz[:, :32, 0, 0] = self._p(u + ".weight_expand").view(4, 64, 8).permute(1, 0, 2).reshape(64, 32)   # cols e*8+k
-            return wz
-        pwc = self._pack(u + ".compress_all", lambda: self._p(u + ".weight_compress").reshape(32, 64, 1, 1), n_tile=16)   # rows e*8+k
-        pwe = self._pack(u + ".expand_all", we_all, rows=K.ROWS_LINEAR)
-        pwf = self._packp(u + ".fusion.weight")                       # QUAD rows: same 16x256b epilogue as the convs
-        fb = self._ptr(u + ".fusion.bias")
-        self._emit(lambda st: lib.savsr_satu_fused(ctx, lrh, TR, STA, hh, ww, hrh, 0, tab, by, bx, pwc, pwe, pwf, fb, st),
-                   kind="satu_fused", flops=2.0 * B * self.H * self.W * (64 * 32 + 32 * 64 + 128 * 64))
-        self._tap("satu_out", "hr", 0)
-        skip = K.RgbSkip(); skip.x = xin; skip.t = t; skip.centre = t // 2; skip.h = self.h; skip.w = self.w
-        self._keep.append(skip)
-        def bt():
-            z = torch.zeros(16, device=self.device); z[:3] = self._p("tail.bias")
-            return z
-        self._conv(hr, [self._group([0], 0, self._pack("tail.weight@16", lambda: self._p("tail.weight"), n_tile=16, co_pad=16),
-                                    self._dev("tail.bias@16", bt), aux=self.out.data_ptr())], n_tile=16, dst_mode=K.DST_RGB, skip=skip,
-                   alg_co=3, kind="satu_tail")
-        # declared traffic beyond the compulsory SATU bytes (per sample): the 16-bit sta intermediate and the 64-channel HR feature
-        self.satu_extra_bytes_per_sample = 2 * 64 * self.hp * self.wp * 2 + 2 * 64 * self.H * self.W * 2
+        # HR stage + tail in ONE kernel (savsr_arch.py:364-376, 738-739): gathers, routed experts, and -- composed on the host because
+        # nothing between them is non-linear -- fusion 128->64 and the 3x3 tail as 27 per-tap partial products per HR pixel, summed
+        # over the neighbourhood in shared memory; bias + bilinear skip + fp32 NCHW stores.  No HR-resolution intermediate exists.
+        hw = self.store.get(("satu_hr_weights", self.fmt), lambda: satu_hr_pack(satu_hr_compose(P, self.device), self.fmt, self.device))
+        zb = self._dev("satu_hr.zbias", lambda: satu_hr_compose(P, self.device)[4])
+        tb = self._ptr("tail.bias")
+        hwp, outp, cen = hw.data_ptr(), self.out.data_ptr(), t // 2
+        hr_flops = 2.0 * B * self.H * self.W * (64 * 32 + 32 * 64 + 128 * 64 + 64 * 3 * 9)      # compress, expand, fusion, tail (reference counts)
+        self._emit(lambda st: lib.savsr_satu_hr(ctx, lrh, TR, STA, hh, ww, H, W, tab, by, bx, hwp, zb, tb, xin, t, cen, outp, st),
+                   kind="satu_hr", flops=hr_flops)
+        # declared traffic beyond the compulsory SATU bytes (per sample): only the 16-bit sta intermediate (written by kconv_sta, read here)
+        self.satu_extra_bytes_per_sample = 2 * 64 * self.hp * self.wp * 2
         self._stream().synchronize()
         self._pack_src.clear()
 
@@ -586,7 +610,7 @@ class Plan:
         self._keep.clear()
         self._pack_src.clear()
         self.tap_bufs.clear()
-        for name in ("arena_lr_t", "arena_hr_t", "x_in", "out", "table", "lr", "hr"):
+        for name in ("arena_lr_t", "x_in", "out", "table", "lr"):
             if hasattr(self, name):
                 setattr(self, name, None)
         self.nbytes = 0

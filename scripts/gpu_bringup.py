@@ -28,9 +28,7 @@ CHECKS = {
     "conv_halo_s5": "check_conv(impl=K.IMPL_HALO, ksize=3, nsrc=5, B=1, H=48, W=40)",
     "conv_aux16": "check_conv_aux16()",
     "conv_aux16_halo": "check_conv_aux16(impl=K.IMPL_HALO)",
-    "conv_rgb_halo": "check_conv_rgb(impl=K.IMPL_HALO)",
     "conv_per_sample_halo": "check_osa_conv_per_sample(impl=K.IMPL_HALO)",
-    "conv_rgb": "check_conv_rgb()",
     "conv_per_sample": "check_osa_conv_per_sample()",
     "pack_frames": "check_pack_frames()",
     "osa_prologue_192": "check_osa_prologue(ci=192)",
@@ -42,16 +40,14 @@ CHECKS = {
     "satu_index_2p7": "check_satu_index(144, 180, (2.7, 2.7))",
     "satu_index_x4": "check_satu_index(144, 180, (4, 4))",
     "satu_table": "check_satu_table()",
-    "satu_sta": "check_satu_sta()",
     "satu_kconv_sta": "check_satu_kconv_sta()",
-    "satu_gather": "check_satu_gather()",
-    "satu_fused": "check_satu_fused()",
+    "satu_hr": "check_satu_hr()",
+    "satu_hr_x4": "check_satu_hr(B=1, h=16, w=20, scale=(4, 4), seed=2)",
     "img_metrics": "check_img_metrics()",
     "lr_synthesis": "check_lr_synthesis()",
     "evaluate_clip": "check_evaluate_clip()",
     "conv_repeat_s1": "check_conv_repeatability(nsrc=1, ngroups=6, B=3)",
     "conv_repeat_s3": "check_conv_repeatability(nsrc=3, ngroups=2, B=4)",
-    "satu_fused_x4": "check_satu_fused(B=1, h=16, w=20, scale=(4, 4), seed=2)",
     "forward_check_impl": "check_forward(b=1, h=16, w=20, scale=(2, 2), impl='check')",
     "forward_tap": "check_forward(b=1, h=16, w=20, scale=(2, 2), impl='tap')",
     "forward_tap_odd_b2": "check_forward(b=2, h=13, w=15, scale=(1.5, 4), sd_seed=1, in_seed=1236, impl='tap')",

@@ -41,14 +41,20 @@ def test_forward_matches_reference_golden(G, path, impl, precision):
     ref = torch.from_numpy(g["out"])
     assert y.shape == ref.shape
     assert float((y - ref).abs().max()) < max_abs_tol
-    for key in ("f2p_last", "p2f_last", "align", "rg0", "rg3", "satu_out"):
-        t = taps[key][..., :h, :w] if key != "satu_out" else taps[key]
-        t = t.contiguous().flatten()
+    for key in ("f2p_last", "p2f_last", "align", "rg0", "rg3"):
+        t = taps[key][..., :h, :w].contiguous().flatten()
         idx = torch.linspace(0, t.numel() - 1, steps=min(257, t.numel())).long()
-        if tuple(g[f"probe.{key}.shape"]) != tuple((taps[key][..., :h, :w] if key != "satu_out" else taps[key]).shape):
+        if tuple(g[f"probe.{key}.shape"]) != tuple(taps[key][..., :h, :w].shape):
             continue                          # padded sizes: the golden probe was taken on the padded map
         samp = torch.from_numpy(g[f"probe.{key}.sample"])
         assert float((t[idx] - samp).abs().max()) < stage_tol * float(g[f"probe.{key}.absmax"]), key
+    # the SATU + tail branch on its own (the output is dominated by the bilinear skip): y - skip against the reference's tail probe
+    x = make_input(b, h, w, int(g["in_seed"]))
+    skip = torch.nn.functional.interpolate(x[:, 3], size=tuple(y.shape[-2:]), mode="bilinear", align_corners=False)
+    t = (y - skip).contiguous().flatten()
+    assert tuple(g["probe.tail.shape"]) == tuple(y.shape)
+    idx = torch.linspace(0, t.numel() - 1, steps=min(257, t.numel())).long()
+    assert float((t[idx] - torch.from_numpy(g["probe.tail.sample"])).abs().max()) < stage_tol * float(g["probe.tail.absmax"]), "tail"
 
 
 @pytest.mark.parametrize("kw", [dict(b=1, h=16, w=20, scale=(2, 2)), dict(b=2, h=13, w=15, scale=(1.5, 4), sd_seed=1, in_seed=1236),

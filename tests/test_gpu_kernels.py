@@ -33,11 +33,6 @@ def test_conv_aux16(G):
     G.check_conv_aux16()
 
 
-def test_conv_rgb_skip(G):
-    G.check_conv_rgb()
-    G.check_conv_rgb(B=1, h=16, w=16, scale=(4, 4), seed=12)
-
-
 def test_conv_per_sample_weights(G):
     G.check_osa_conv_per_sample()
 
@@ -78,9 +73,11 @@ def test_satu_kernel_conv_and_sta_fused(G):
     G.check_satu_kconv_sta(B=2, h=48, w=40, seed=6)      # 15 tiles per sample, several CTAs, odd count
 
 
-def test_satu_fused_tensor_core_hr_stage(G):
-    G.check_satu_fused()
-    G.check_satu_fused(B=1, h=16, w=20, scale=(4, 4), seed=2)
+@pytest.mark.parametrize("kw", [dict(), dict(B=1, h=16, w=20, scale=(4, 4), seed=2), dict(B=3, h=36, w=45, scale=(4, 4), seed=3, offset_gain=1.0),
+                                dict(B=2, h=30, w=22, scale=(1.5, 4), seed=4), dict(B=1, h=9, w=70, scale=(1.1, 1.2), seed=5),
+                                dict(B=2, h=21, w=33, scale=(3, 3), seed=6), dict(B=1, h=2, w=3, scale=(8, 7.3), seed=7)])
+def test_satu_hr_one_kernel(G, kw):
+    G.check_satu_hr(**kw)
 
 
 def test_device_tensor2img_and_psnr_y(G):
@@ -112,6 +109,6 @@ def test_kernels_in_fp16_operand_format(G):
         G.check_osa_prologue(ci=192, B=2)
         G.check_ca()
         G.check_satu_kconv_sta()
-        G.check_satu_fused()
+        G.check_satu_hr()
     finally:
         G.set_precision("bf16")

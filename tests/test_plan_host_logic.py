@@ -29,18 +29,19 @@ def test_launch_census(recorded):
     names = [c[0] for c in calls]
     build_time = names.count("savsr_pack_conv_weight")
     # distinct conv weights: l1 2*(4*3 conv0 + 1 conv1 + 4*3 conv2 + merge) + l2 (5 + 2*(5+5) + 1 + 1) + RG 4*(16+1)
-    # + mask.0 x4 + conv_last + kernel_conv + fusion + tail + zero-expanded first-layer filters (5 iterations x 2 dirs x 2)
-    # + the stacked compress / expand expert matrices
-    assert build_time == 2 * (12 + 1 + 12 + 1) + (5 + 20 + 1 + 1) + 68 + 4 + 1 + 1 + 1 + 1 + 20 + 2
+    # + mask.0 x4 + conv_last + kernel_conv + zero-expanded first-layer filters (5 iterations x 2 dirs x 2); the SATU HR
+    # operands (compress, fusion o tail composites) are packed on the host side of the boundary (engine.satu_hr_pack)
+    assert build_time == 2 * (12 + 1 + 12 + 1) + (5 + 20 + 1 + 1) + 68 + 4 + 1 + 1 + 20
     run = names[names.index("savsr_satu_index") + 1:] if False else names
     assert names.count("savsr_pack_frames") == 1
     assert names.count("savsr_ca_scale_residual") == 32              # 4 groups x 8 RCAB
     assert names.count("savsr_osadapt_mask") == 4
     assert names.count("savsr_osa_prologue") == 5 * 3 + 2 + 4        # l1 blocks 1-3 (both dirs batched), l2 x2, adapt x4
     # kernel_conv + sta_conv are one launch; the 25 per-pixel kernels are never materialised
-    assert names.count("savsr_satu_kconv_sta") == 1 and names.count("savsr_satu_sta") == 0 and names.count("savsr_satu_fused") == 1
-    # conv launches: l1 5*(first layer + 4*3 + 1) + l2 (1 + 2*3 + 1 + 1) + RG 4*(16 + 1 + mask + adapt) + conv_last + tail
-    assert names.count("savsr_conv") == 5 * 14 + 9 + 4 * 19 + 1 + 1
+    # ... and the whole HR side + tail + skip is one launch: no HR-resolution intermediate, no separate tail conv
+    assert names.count("savsr_satu_kconv_sta") == 1 and names.count("savsr_satu_hr") == 1 and names.count("savsr_satu_fused") == 0
+    # conv launches: l1 5*(first layer + 4*3 + 1) + l2 (1 + 2*3 + 1 + 1) + RG 4*(16 + 1 + mask + adapt) + conv_last
+    assert names.count("savsr_conv") == 5 * 14 + 9 + 4 * 19 + 1
 
 
 def test_no_conv_writes_a_slot_it_reads(recorded):
@@ -84,9 +85,8 @@ def test_slots_written_before_read_and_hidden_states_persist(recorded):
             arena = id(args[1])
             assert (arena, args[2]) in written and (arena, args[3]) in written and args[4] not in (args[2], args[3])
             written[(arena, args[4])] = idx
-        elif name == "savsr_satu_fused":
-            assert (id(args[1]), args[2]) in written and (id(args[1]), args[3]) in written
-            written[(id(args[6]), args[7])] = idx
+        elif name == "savsr_satu_hr":
+            assert (id(args[1]), args[2]) in written and (id(args[1]), args[3]) in written     # trunk output and sta
     assert zero_reads > 0                          # first iteration of both directions starts from zeros
 
 
