@@ -39,18 +39,21 @@ def main():
     arr = (K.ConvGroup * len(groups))(*groups)
     e0.record()
     for _ in range(reps):
-        K.check(K.load().savsr_conv(G.ctx().handle, ab.a.handle, arr, len(groups), ks, 64, K.DST_ARENA, None, impl, G._stream()))
+        K.check(K.load().savsr_conv(G.ctx().handle, ab.a.handle, arr, len(groups), ks, 64, K.DST_ARENA, impl, G._stream()))
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / reps
     flop = 2.0 * ng * B * H * W * 64 * 64 * nsrc * ks * ks
+    if os.environ.get("CONV_DBG") and not hasattr(K.load(), "savsr_debug_conv_counters"):
+        print("  (cycle counters need a library built with -DSAVSR_DEBUG_COUNTERS)")
+        os.environ.pop("CONV_DBG")
     if os.environ.get("CONV_DBG"):
         import ctypes
         dbg = torch.zeros(148, 8, dtype=torch.int64, device=G.DEV)
-        K.load().savsr_debug_conv_counters.argtypes = [ctypes.c_void_p]
-        K.load().savsr_debug_conv_counters(dbg.data_ptr())
-        K.check(K.load().savsr_conv(G.ctx().handle, ab.a.handle, arr, len(groups), ks, 64, K.DST_ARENA, None, impl, G._stream()))
+        K.load().savsr_debug_conv_counters.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        K.load().savsr_debug_conv_counters(G.ctx().handle, dbg.data_ptr())
+        K.check(K.load().savsr_conv(G.ctx().handle, ab.a.handle, arr, len(groups), ks, 64, K.DST_ARENA, impl, G._stream()))
         torch.cuda.synchronize()
-        K.load().savsr_debug_conv_counters(None)
+        K.load().savsr_debug_conv_counters(G.ctx().handle, None)
         d = dbg.float().cpu()
         d = d[d[:, 3] > 0]
         m = d.mean(0)
