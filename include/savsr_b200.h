@@ -154,6 +154,19 @@ int savsr_conv(savsr_ctx* ctx, savsr_arena* arena, const savsr_conv_group* group
 int savsr_pack_frames(savsr_ctx* ctx, savsr_arena* arena, const float* x, int t, int h, int w, int dst_slot,
                       savsr_stream st);
 
+/* ---- backward of the 3x3 convolution (next row 8f1: training step, lbasicsr/models/sr_model.py:101-128) ----------------------
+ * Data gradient: a 3x3 convolution of dY with the transposed, spatially flipped filter -- call savsr_conv with those weights
+ * (savsr_b200/autograd.py does).  Weight gradient, on tcgen05 with the pixel index as the contraction dimension:
+ *   dW[o][i][ky][kx] += sum_{n, p} dY[n][o][p] * X[n][i][p + (ky-1, kx-1)]                     (zero padding)
+ * dy_nchw16: 16-bit (context format) NCHW tensor [batch][64][height][pitch], pitch a multiple of 8 elements, pixels [width, pitch)
+ * of every row ZERO.  x3_nchw16: [3][batch][ci][height][pitch], ci = 64, 128, ... 320: X shifted along x by -1, 0, +1 pixel
+ * (copy d holds X[.., x + d - 1], zero where that leaves the row) -- TMA boxes start on 16-byte granules, so the one-pixel shifts of
+ * the contraction operand are materialised by the caller.  dw: fp32 [64][ci][3][3] (per_sample = 0) or
+ * [batch][64][ci][3][3] (per_sample = 1: the per-sample folded kernels of OSA-Conv), accumulated with atomics: zero it first.
+ */
+int savsr_conv_wgrad(savsr_ctx* ctx, const void* x3_nchw16, const void* dy_nchw16, int batch, int ci, int height, int width,
+                     int pitch, int per_sample, float* dw, savsr_stream st);
+
 /* ---- OSA-Conv prologue (savsr_arch.py:143-163, 91-96, 123-128) ---------------------------------- */
 typedef struct savsr_osa_params {
   int32_t ci, co, att;            /* in planes (64*nsrc), out planes (64), attention channels      */

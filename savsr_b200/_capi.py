@@ -93,6 +93,7 @@ SIGNATURES = {
     "savsr_packed_weight_bytes": (_SZ, [_I, _I, _I]),
     "savsr_pack_conv_weight": (_I, [_VP, _I, _I, _I, _I, _I, _I, _I, _VP, _VP]),
     "savsr_conv": (_I, [_VP, _VP, C.POINTER(ConvGroup), _I, _I, _I, _I, _I, _VP]),
+    "savsr_conv_wgrad": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP, _VP]),
     "savsr_pack_frames": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "savsr_osa_prologue": (_I, [_VP, C.POINTER(OsaParams), _I, _I, _I, _I, _F, _F, _VP]),
     "savsr_ca_scale_residual": (_I, [_VP, _VP, _I, _I, _I, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),

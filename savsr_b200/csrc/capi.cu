@@ -109,6 +109,7 @@ extern "C" size_t savsr_arena_bytes(int nslots, int batch, int height, int width
 extern "C" int savsr_arena_create(savsr_ctx* ctx, void* base, int nslots, int batch, int height, int width, savsr_arena** out) {
   SAVSR_REQUIRE(ctx && out, "savsr_arena_create: null pointer");
   *out = nullptr;
+  DeviceGuard guard(ctx->device);
   SAVSR_REQUIRE(base && (reinterpret_cast<uintptr_t>(base) & 255) == 0, "savsr_arena_create: base must be a 256-byte aligned device pointer");
   SAVSR_REQUIRE(nslots > 0 && batch > 0 && height > 0 && width > 0, "savsr_arena_create: empty arena (%d slots, batch %d, %dx%d)", nslots,
                 batch, height, width);

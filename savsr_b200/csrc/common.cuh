@@ -54,7 +54,7 @@ namespace savsr {
 // Kernels that need more than 48 KB of dynamic shared memory: the attribute belongs to the device (primary context), so
 // it is tracked per savsr_ctx, not per process.
 enum AttrBit { kAttrIgemm = 0 /* + template index, 6 variants */, kAttrBigk = 8, kAttrKsta = 9, kAttrSatuHr = 10, kAttrOsaLinear = 11,
-               kAttrFused = 12, kAttrBigk128 = 13, kAttrSatuHrBf16 = 14 };
+               kAttrFused = 12, kAttrBigk128 = 13, kAttrSatuHrBf16 = 14, kAttrWgrad = 15 };
 template <class F>
 inline int ensure_smem_attr(savsr_ctx* ctx, int bit, F func, size_t bytes) {
   if (ctx->attr_mask & (1u << bit)) return 0;
@@ -62,12 +62,17 @@ inline int ensure_smem_attr(savsr_ctx* ctx, int bit, F func, size_t bytes) {
   ctx->attr_mask |= 1u << bit;
   return 0;
 }
-// Launch on the context's device whatever the caller's current device is; restores it on scope exit.
+// Launch on the context's device whatever the caller's current device is; restores it on scope exit.  cudaSetDevice is called
+// even when the device already matches: it also binds the primary context to the calling THREAD, which a fresh thread (e.g.
+// autograd's backward worker) does not have yet -- the driver entry points (cuTensorMapEncodeTiled) fail with
+// CUDA_ERROR_INVALID_CONTEXT otherwise.
 struct DeviceGuard {
   int prev = -1;
   bool switched = false;
   explicit DeviceGuard(int device) {
-    if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+    const bool known = cudaGetDevice(&prev) == cudaSuccess;
+    const bool ok = cudaSetDevice(device) == cudaSuccess;
+    switched = known && ok && prev != device;
   }
   ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
 };

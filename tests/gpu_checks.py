@@ -507,6 +507,43 @@ def check_satu_hr(B=2, h=13, w=15, scale=(2.7, 1.5), seed=1, offset_gain=8.0):
     return info
 
 
+def check_conv_autograd(B=2, nsrc=2, H=16, W=20, per_sample=False, bias=True, seed=0):
+    """savsr_b200.autograd.conv3x3 (forward + tcgen05 dgrad + tcgen05 wgrad) vs fp32 autograd through F.conv2d on the same
+    16-bit-rounded operands (row f1, stage A; the reference trains through cuDNN: lbasicsr/models/sr_model.py:101-128)."""
+    from savsr_b200.autograd import conv3x3
+    torch.manual_seed(seed)
+    torch.backends.cudnn.allow_tf32 = False
+    Ci = 64 * nsrc
+    x = bf16_round(torch.randn(B, Ci, H, W, device=DEV)).requires_grad_(True)
+    wshape = (B, 64, Ci, 3, 3) if per_sample else (64, Ci, 3, 3)
+    w = bf16_round(torch.randn(*wshape, device=DEV) * 0.05).requires_grad_(True)
+    b = (torch.randn(64, device=DEV) * 0.1).requires_grad_(True) if (bias and not per_sample) else None
+    g = bf16_round(torch.randn(B, 64, H, W, device=DEV))
+    y = conv3x3(x, w, b)
+    (y * g).sum().backward()
+    got = dict(y=y.detach(), dx=x.grad.clone(), dw=w.grad.clone(), db=b.grad.clone() if b is not None else None)
+    x.grad = None; w.grad = None
+    if b is not None:
+        b.grad = None
+    if per_sample:
+        yr = F.conv2d(x.reshape(1, B * Ci, H, W), w.reshape(B * 64, Ci, 3, 3), None, 1, 1, 1, groups=B).view(B, 64, H, W)
+    else:
+        yr = F.conv2d(x, w, b, 1, 1)
+    (yr * g).sum().backward()
+    ref = dict(y=yr.detach(), dx=x.grad, dw=w.grad, db=b.grad if b is not None else None)
+    info = {}
+    for k in ("y", "dx", "dw", "db"):
+        if ref[k] is None:
+            continue
+        scale = float(ref[k].abs().max())
+        err = float((got[k] - ref[k]).abs().max())
+        # y and dx leave through a 16-bit arena slot (one rounding: 2^-8 relative); dw / db are fp32 sums of exact products
+        tol = (2.0 ** -7 if k in ("y", "dx") else 2e-4) * scale + 1e-6
+        info[k] = dict(max_abs=err, ref_absmax=scale)
+        assert err <= tol, (k, info[k], tol)
+    return info
+
+
 def check_img_metrics(n=3, H=37, W=53, seed=31):
     """tensor2img (bit-exact uint8 BGR) and PSNR-Y on the device vs the oracle's restatement of the reference metric chain."""
     from oracle import savsr_oracle as O

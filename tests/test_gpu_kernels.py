@@ -80,6 +80,15 @@ def test_satu_hr_one_kernel(G, kw):
     G.check_satu_hr(**kw)
 
 
+@pytest.mark.parametrize("kw", [dict(B=2, nsrc=1, H=16, W=20), dict(B=2, nsrc=2, H=16, W=20), dict(B=1, nsrc=3, H=13, W=15, seed=1),
+                                dict(B=3, nsrc=3, H=18, W=26, per_sample=True, seed=2), dict(B=2, nsrc=5, H=9, W=70, seed=3),
+                                dict(B=4, nsrc=2, H=64, W=64, seed=4), dict(B=2, nsrc=1, H=33, W=130, per_sample=True, seed=5),
+                                dict(B=1, nsrc=1, H=1, W=3, bias=False, seed=6)])
+def test_conv3x3_autograd_dgrad_wgrad(G, kw):
+    """Row f1 stage A: backward of the dominant op on tcgen05 (dgrad = forward kernel on flipped weights, wgrad = pixel contraction)."""
+    G.check_conv_autograd(**kw)
+
+
 def test_device_tensor2img_and_psnr_y(G):
     G.check_img_metrics()
 
