@@ -113,11 +113,19 @@ def _lrelu(x: Tensor, slope: float = 0.2) -> Tensor:
     return F.leaky_relu(x, slope)
 
 
+BN_TRAIN = False   # tests of the training row (8f1) set this: BatchNorm then normalises with the batch statistics (nn.BatchNorm2d.train())
+
+
 def _bn_eval(sd: SD, name: str, x: Tensor) -> Tensor:
-    """BatchNorm2d in eval mode (savsr_arch.py:26, 191-204): affine with running stats."""
-    rm, rv = sd[name + ".running_mean"], sd[name + ".running_var"]
+    """BatchNorm2d (savsr_arch.py:26, 191-204).  Eval mode (default): affine with running stats.  With BN_TRAIN: batch mean and
+    biased batch variance over (n, h, w), as nn.BatchNorm2d computes in train mode (running-stat updates are not modelled)."""
     g, b = sd[name + ".weight"], sd[name + ".bias"]
     shp = (1, -1, 1, 1)
+    if BN_TRAIN:
+        rm = x.mean(dim=(0, 2, 3))
+        rv = x.var(dim=(0, 2, 3), unbiased=False)
+    else:
+        rm, rv = sd[name + ".running_mean"], sd[name + ".running_var"]
     return (x - rm.view(shp)) / torch.sqrt(rv.view(shp) + BN_EPS) * g.view(shp) + b.view(shp)
 
 

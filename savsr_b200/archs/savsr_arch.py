@@ -219,6 +219,11 @@ class SAVSR(nn.Module):
         empty_cache(), as video_base_model.py:72-74 does every frame: the plan's arenas are not affected)."""
         if scale is not None:
             self.scale = scale
+        if self.training:
+            # optimisation path (sr_model.py:101-128 calls net_g(lq) in train mode): differentiable forward whose 3x3 convolutions
+            # (forward, dgrad, wgrad) run on the tcgen05 kernels -- savsr_b200/train.py
+            from savsr_b200 import train as _train
+            return _train.forward(self, x, self.scale)
         plan = self.plan_for(x)
         with torch.cuda.device(plan.device):
             out = torch.empty_like(plan.out)
@@ -269,8 +274,7 @@ class SAVSR(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("savsr_b200.SAVSR runs on CUDA (sm_100a) only; there is no CPU fallback")
         if self.training:
-            raise NotImplementedError("savsr_b200.SAVSR implements the inference forward; call .eval() first "
-                                      "(train-mode BatchNorm / backward are outside the hot path of this round)")
+            raise RuntimeError("plans are the inference path; in train mode forward() runs savsr_b200.train.forward")
         p0 = self.gamma
         if p0.device != x.device:
             raise RuntimeError(f"module parameters on {p0.device}, input on {x.device}")

@@ -544,6 +544,111 @@ def check_conv_autograd(B=2, nsrc=2, H=16, W=20, per_sample=False, bias=True, se
     return info
 
 
+def _grad_report(named_gpu, sd_cpu, keys):
+    """Error of the gradient per parameter tensor, GPU (16-bit operand convs) vs fp32 CPU autograd on the oracle:
+    |g - r| / max(|r|, 1e-3 * largest tensor-gradient norm of the block).  The floor matters: some true gradients are zero (a conv
+    bias in front of a train-mode BatchNorm; everything upstream of a BatchNorm over a batch of two 1x1 maps, whose output is +-1
+    whatever its input), where a pure relative error would compare rounding noise with rounding noise."""
+    big = max(float(sd_cpu[k].grad.norm()) for k in keys if sd_cpu[k].grad is not None)
+    rep = {}
+    for k in keys:
+        g, r = named_gpu[k].grad, sd_cpu[k].grad
+        assert (g is None) == (r is None), f"{k}: gradient present on one side only"
+        if r is None:
+            continue
+        rep[k] = float((g.cpu() - r).norm()) / max(float(r.norm()), 1e-3 * big)
+    return rep
+
+
+def check_train_block(block="residual_group", b=2, h=16, w=20, scale=(2.7, 1.5), seed=1, tol=0.04):
+    """Row f1 stage A: gradient parity of the train-mode blocks (3x3 convs on tcgen05 forward / dgrad / wgrad, train-mode BatchNorm,
+    OSA fold, pooled means) against fp32 autograd through the CPU oracle, for one WindowUnit_l1 and one ResidualGroup."""
+    import savsr_b200
+    from oracle import savsr_oracle as O
+    from oracle.state_dict_fixture import make_state_dict
+    from savsr_b200 import train as T
+    torch.manual_seed(seed)
+    sd = make_state_dict(seed)
+    net = savsr_b200.SAVSR().to(DEV)
+    net.load_state_dict(sd, strict=True)
+    net.train()
+    sd_cpu = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    tn = T._Net(net, training=True)
+    O.BN_TRAIN = True
+    try:
+        if block == "residual_group":
+            x = torch.randn(b, 64, h, w) * 0.3
+            prefix = "RG.1"
+            out = T.residual_group(tn, prefix, x.to(DEV))
+            ref = O.residual_group(sd_cpu, prefix, x)
+        elif block == "window_unit_l1":
+            frames = torch.rand(b, 3, 3, h, w)
+            hp = torch.randn(b, 64, h, w) * 0.2
+            prefix = "f2p_win"
+            out = T.window_unit_l1(tn, prefix, frames.to(DEV), hp.to(DEV), scale)
+            ref = O.window_unit_l1(sd_cpu, prefix, frames, hp, scale)
+        elif block == "osadapt":
+            x = torch.randn(b, 64, h, w) * 0.3
+            prefix = "adapt.2"
+            out = T.osadapt(tn, prefix, x.to(DEV), scale)
+            ref = O.osadapt(sd_cpu, prefix, x, scale)
+        else:
+            raise ValueError(block)
+        g = torch.randn_like(ref)
+        (out * g.to(DEV)).sum().backward()
+        (ref * g).sum().backward()
+    finally:
+        O.BN_TRAIN = False
+    keys = [k for k in sd if k.startswith(prefix + ".") and sd[k].is_floating_point() and "running_" not in k]
+    rep = _grad_report(dict(net.named_parameters()), sd_cpu, keys)
+    fwd = float((out.detach().cpu() - ref.detach()).abs().max() / (ref.detach().abs().max() + 1e-12))
+    worst = max(rep.items(), key=lambda kv: kv[1])
+    info = dict(forward_rel=fwd, n_tensors=len(rep), worst=worst, median=float(np.median(list(rep.values()))))
+    assert fwd < 0.02, info
+    assert all(np.isfinite(v) and v < tol for v in rep.values()), {k: v for k, v in rep.items() if not v < tol}
+    return info
+
+
+def check_train_step(b=2, h=16, w=20, scale=(2, 2), seed=0, steps=3):
+    """Whole-net training step (forward + backward through all 707 parameter tensors + Adam + EMA): loss and gradient norm against the
+    fp32 CPU oracle at step 0, every parameter receives a gradient, and the loss goes down over a few steps on a fixed batch."""
+    import savsr_b200
+    from oracle import savsr_oracle as O
+    from oracle.state_dict_fixture import make_input, make_state_dict
+    from savsr_b200 import train as T
+    sd = make_state_dict(seed)
+    net = savsr_b200.SAVSR().to(DEV)
+    net.load_state_dict(sd, strict=True)
+    x = make_input(b, h, w, 1234 + seed)
+    H, W = O.get_hw(h, w, scale)
+    gt = torch.rand(b, 3, H, W, generator=torch.Generator().manual_seed(5))
+    sd_cpu = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    O.BN_TRAIN = True
+    try:
+        ref_loss = T.charbonnier(O.forward(sd_cpu, x, scale), gt)
+        ref_loss.backward()
+    finally:
+        O.BN_TRAIN = False
+    tr = T.Trainer(net, lr=2e-4)
+    net.set_scale(scale); net.train()
+    out = net(x.to(DEV))
+    loss0 = T.charbonnier(out, gt.to(DEV))
+    loss0.backward()
+    params = dict(net.named_parameters())
+    missing = [k for k, p in params.items() if p.grad is None]
+    assert not missing, f"{len(missing)} parameters without gradient, e.g. {missing[:3]}"
+    gn = float(torch.sqrt(sum((p.grad.float() ** 2).sum() for p in params.values())))
+    rn = float(torch.sqrt(sum((v.grad ** 2).sum() for k, v in sd_cpu.items() if v.is_floating_point() and v.grad is not None)))
+    info = dict(loss=float(loss0), ref_loss=float(ref_loss), grad_norm=gn, ref_grad_norm=rn)
+    assert abs(float(loss0) - float(ref_loss)) < 2e-3 * max(1.0, abs(float(ref_loss))), info
+    assert abs(gn - rn) < 0.05 * rn, info
+    losses = [float(tr.step(x.to(DEV), gt.to(DEV), scale)) for _ in range(steps)]
+    info["losses"] = losses
+    assert losses[-1] < losses[0], info
+    assert int(net.adapt[0].mask[1].num_batches_tracked) - int(sd["adapt.0.mask.1.num_batches_tracked"]) == steps + 1   # BatchNorm ran in train mode
+    return info
+
+
 def check_img_metrics(n=3, H=37, W=53, seed=31):
     """tensor2img (bit-exact uint8 BGR) and PSNR-Y on the device vs the oracle's restatement of the reference metric chain."""
     from oracle import savsr_oracle as O
