@@ -380,13 +380,105 @@ def run_cfg4(net, dev, rank, world, timed, steps=2, warmup=1, B=8):
     return out
 
 
+# ------------------------------------------------------------------------------------------------ BASELINE config 5: training step
+TRAIN_SCALES = [(2, 2), (3, 3), (4, 4), (1.5, 4), (2.7, 2.7), (1.1, 1.1), (3.5, 2), (4, 1.5)]    # a slice of the 60-entry list of vimeo90k_dataset.py:178-202
+
+
+def run_train(args, rank, world, local_rank):
+    """`--workload train_cfg5`: the optimisation step of lbasicsr/models/sr_model.py:101-128 on synthetic Vimeo90K-shaped batches
+    (7 x 3 x 64 x 64 LR crops, 4 per GPU, one scale per step, data-parallel over the ranks with DistributedDataParallel / NCCL).
+    Row f1 is staged: the 3x3 convolutions (forward, dgrad, wgrad) run on the tcgen05 kernels, the glue on ATen; the same step of
+    the unmodified reference (cuDNN) is timed beside it when baseline/_ref is installed."""
+    import torch.distributed as dist
+    import savsr_b200
+    from savsr_b200 import train as T
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    per_gpu, h, w = 4, 64, 64
+    torch.manual_seed(0)
+    net = savsr_b200.SAVSR().to(dev)
+    model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank]) if world > 1 else net
+    graph = world == 1 and not args.no_train_graph          # one CUDA graph per scale for the whole step (single process)
+    tr = T.Trainer(model, use_graph=graph)
+    gen = torch.Generator().manual_seed(100 + rank)
+    lq_host = torch.rand(per_gpu, 7, 3, h, w, generator=gen).pin_memory()
+    gts = {s: torch.rand(per_gpu, 3, *hw_out(h, w, s), generator=gen).pin_memory() for s in TRAIN_SCALES}
+
+    def step(i):
+        s = TRAIN_SCALES[i % len(TRAIN_SCALES)]
+        loss = tr.step(lq_host.to(dev, non_blocking=True), gts[s].to(dev, non_blocking=True), s)
+        return loss
+
+    def timed_steps(fn, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for i in range(n):
+            last = fn(i)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), float(last)
+
+    for i in range(max(args.warmup, 2) if not graph else len(TRAIN_SCALES)):      # with graphs: capture every scale before timing
+        step(i)
+    ms, loss = timed_steps(step, args.steps)
+    line = {"metric": "train_samples_per_s", "value": round(per_gpu * world * args.steps / (ms / 1e3), 2), "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 2), "ms_per_step": round(ms / args.steps, 2), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 conv operands, fp32 master weights / accumulation", "data": "synthetic",
+            "config": {"workload": "train_cfg5", "per_gpu_batch": per_gpu, "global_batch": per_gpu * world, "lr_crop": [h, w], "frames": 7,
+                       "scales": [list(s) for s in TRAIN_SCALES], "optimizer": "Adam 2e-4 (0.9, 0.99), Charbonnier, EMA 0.999",
+                       "parallelism": f"DistributedDataParallel x{world} (NCCL gradient all-reduce, 75.6 MB fp32)" if world > 1 else "single GPU"},
+            "last_loss": round(loss, 5), "cuda_graph_per_scale": bool(graph),
+            "stage": "f1 staged: 3x3 convs (fwd / dgrad / wgrad, 98 % of the FLOPs) on tcgen05 through savsr_b200.autograd.conv3x3, each call "
+                     "still converting NCHW fp32 <-> the NHWC 16-bit arena; glue ops on ATen"}
+    if world == 1 and not args.no_extras:
+        ref, kind = load_reference(net.state_dict(), dev)
+        if ref is not None:
+            ref.train()
+            opt = torch.optim.Adam(ref.parameters(), lr=2e-4, betas=(0.9, 0.99))
+            saved = torch.backends.cudnn.benchmark
+            torch.backends.cudnn.benchmark = True
+
+            def ref_step(i):
+                s = TRAIN_SCALES[i % len(TRAIN_SCALES)]
+                ref.set_scale(s)
+                opt.zero_grad(set_to_none=True)
+                out = ref(lq_host.to(dev, non_blocking=True))
+                l = T.charbonnier(out, gts[s].to(dev, non_blocking=True))
+                l.backward()
+                opt.step()
+                return l.detach()
+            for i in range(len(TRAIN_SCALES)):
+                ref_step(i)                                   # cudnn.benchmark autotunes per shape
+            rms, rloss = timed_steps(ref_step, args.steps)
+            torch.backends.cudnn.benchmark = saved
+            line["gpu_reference"] = {"kind": kind, "ms_per_step": round(rms / args.steps, 2), "samples_per_s": round(per_gpu * args.steps / (rms / 1e3), 2),
+                                     "what": "the unmodified reference module in train mode on this GPU (cuDNN TF32 fprop / dgrad / wgrad, cudnn.benchmark), same step"}
+        else:
+            line["gpu_reference"] = {"unavailable": kind}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="vid4_x4", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="vid4_x4", choices=sorted(WORKLOADS) + ["train_cfg5"])
     ap.add_argument("--batch", type=int, default=17, help="windows per forward")
     ap.add_argument("--conv-impl", default=os.environ.get("SAVSR_CONV_IMPL", "halo"), choices=["halo", "tap"])
     ap.add_argument("--precision", default=os.environ.get("SAVSR_PRECISION", "bf16"), choices=["bf16", "fp16"],
@@ -394,13 +486,21 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip fp16 / latency / gpu_reference / cfg4 legs (profiling runs)")
     ap.add_argument("--no-cfg4", action="store_true")
+    ap.add_argument("--no-train-graph", action="store_true", help="train_cfg5: issue the step eagerly instead of replaying one CUDA graph per scale")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
+        if args.workload == "train_cfg5":
+            raise SystemExit("--impl reference is defined for the inference workloads (the metric of BASELINE.json)")
         run_reference(args, rank, world)
+        return
+    if args.workload == "train_cfg5":
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py --workload train_cfg5 needs a CUDA device (sm_100a); there is no CPU fallback")
+        run_train(args, rank, world, local_rank)
         return
 
     import torch.distributed as dist

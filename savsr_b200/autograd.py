@@ -41,8 +41,7 @@ def _pack(ctx: K.Context, w: torch.Tensor, st: int) -> torch.Tensor:
     out = torch.empty(ctx.lib.savsr_packed_weight_bytes(co, ci, 3), dtype=torch.uint8, device=w.device)
     K.check(ctx.lib.savsr_pack_conv_weight(w.data_ptr(), co, co, ci, 3, 64, ctx.lib.savsr_ctx_get_format(ctx.handle), K.ROWS_QUAD,
                                            out.data_ptr(), st))
-    out._savsr_src = w            # the fp32 source must outlive the asynchronous pack kernel
-    return out
+    return out                    # (temporaries are safe to drop: the caching allocator reuses memory in stream order only)
 
 
 def _group(src, dst, weight: torch.Tensor, bias: Optional[torch.Tensor], wstride: int) -> K.ConvGroup:
@@ -70,7 +69,7 @@ def _nchw16(t: torch.Tensor, dt: torch.dtype) -> torch.Tensor:
 
 
 def _nchw16_shifted(t: torch.Tensor, dt: torch.dtype) -> torch.Tensor:
-    """fp32 [B, C, H, W] -> 16-bit [3, B, C, H, pitch]: copy d holds X[.., x + d - 1] (zero outside the row): the three x-shifted
+    """[B, C, H, W] (fp32 or 16-bit) -> 16-bit [3, B, C, H, pitch]: copy d holds X[.., x + d - 1] (zero outside the row): the three x-shifted
     views of the contraction operand of savsr_conv_wgrad (TMA boxes cannot start off a 16-byte granule)."""
     B, C, H, W = t.shape
     pitch = (W + 7) // 8 * 8
@@ -103,7 +102,6 @@ class _Conv3x3(torch.autograd.Function):
             for s in range(nsrc):
                 chunk = xs[:, 64 * s:64 * s + 64].contiguous()
                 K.check(c.lib.savsr_arena_import(arena.handle, s, chunk.data_ptr(), st))
-                chunk.record_stream(torch.cuda.current_stream())
             wp = _pack(c, weight.reshape(-1, Ci, 3, 3), st)
             b32 = bias.detach().float().contiguous() if bias is not None else None
             g = _group(list(range(nsrc)), nsrc, wp, b32, 64 * Ci * 9 * 2 if per_sample else 0)
@@ -111,9 +109,7 @@ class _Conv3x3(torch.autograd.Function):
             K.check(c.lib.savsr_conv(c.handle, arena.handle, arr, 1, 3, 64, K.DST_ARENA, K.IMPL_HALO, st))
             y = torch.empty(B, 64, H, W, dtype=torch.float32, device=x.device)
             K.check(c.lib.savsr_arena_export(arena.handle, nsrc, y.data_ptr(), st))
-            for t in (arena_t, wp):
-                t.record_stream(torch.cuda.current_stream())
-        ctx.save_for_backward(_nchw16_shifted(xs, dt), weight)
+        ctx.save_for_backward(xs.to(dt), weight)       # 16-bit copy of the input: all the weight gradient needs
         ctx.has_bias = bias is not None
         ctx.width = W
         return y
@@ -122,8 +118,8 @@ class _Conv3x3(torch.autograd.Function):
     def backward(ctx, dy: torch.Tensor):
         x16, weight = ctx.saved_tensors
         c = _ctx_of(dy)
-        _, B, Ci, H, pitch = x16.shape
-        W = ctx.width
+        B, Ci, H, W = x16.shape
+        pitch = (W + 7) // 8 * 8
         per_sample = weight.dim() == 5
         nsrc = Ci // 64
         dt = x16.dtype
@@ -150,14 +146,12 @@ class _Conv3x3(torch.autograd.Function):
                     part = torch.empty(B, 64, H, W, dtype=torch.float32, device=dy.device)
                     K.check(c.lib.savsr_arena_export(arena.handle, s, part.data_ptr(), st))
                     dx[:, 64 * s:64 * s + 64] = part
-                for t in [arena_t] + keep:
-                    t.record_stream(torch.cuda.current_stream())
             if ctx.needs_input_grad[1]:
                 dy16 = _nchw16(dy, dt)
+                x3 = _nchw16_shifted(x16, dt)                # the three x-shifted views, built only now (transient)
                 dw = torch.zeros(weight.shape, dtype=torch.float32, device=dy.device)
-                K.check(c.lib.savsr_conv_wgrad(c.handle, x16.data_ptr(), dy16.data_ptr(), B, Ci, H, W, pitch, 1 if per_sample else 0,
+                K.check(c.lib.savsr_conv_wgrad(c.handle, x3.data_ptr(), dy16.data_ptr(), B, Ci, H, W, pitch, 1 if per_sample else 0,
                                                dw.data_ptr(), st))
-                dy16.record_stream(torch.cuda.current_stream())
             if ctx.has_bias and ctx.needs_input_grad[2]:
                 db = dy.sum(dim=(0, 2, 3))
         return dx, dw, db

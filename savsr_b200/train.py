@@ -69,7 +69,7 @@ def osconv(net: _Net, prefix: str, x: Tensor, scale) -> Tensor:
     b, ci = x.shape[0], x.shape[1]
     P = net.P
     pooled = x.mean(dim=(2, 3))
-    info = x.new_tensor([1.0 / s[0], 1.0 / s[1]]).view(1, 2).expand(b, 2)               # (1/s_h, 1/s_w), savsr_arch.py:143-145
+    info = torch.cat([x.new_full((b, 1), 1.0 / s[0]), x.new_full((b, 1), 1.0 / s[1])], 1)   # (1/s_h, 1/s_w), savsr_arch.py:143-145; fill kernels: graph-capturable
     v = torch.cat([info, pooled], 1)
     v = F.relu(F.linear(v, P[prefix + ".scale_routing.0.weight"], P[prefix + ".scale_routing.0.bias"]))
     v = F.relu(F.linear(v, P[prefix + ".scale_routing.2.weight"], P[prefix + ".scale_routing.2.bias"]))
@@ -221,19 +221,24 @@ def charbonnier(pred: Tensor, target: Tensor, eps: float = 1e-12) -> Tensor:
 class Trainer:
     """One optimisation step as lbasicsr/models/sr_model.py:101-128 + asvsr_model.py:21-29 run it: set the batch's scale, forward,
     Charbonnier, backward, Adam (train YAML: lr 2e-4, betas 0.9 / 0.99), EMA of the weights (base_model.py:75-82, decay 0.999).
-    `net` may be wrapped in DistributedDataParallel by the caller (base_model.py:98-99): gradients then all-reduce over NCCL."""
+    `net` may be wrapped in DistributedDataParallel by the caller (base_model.py:98-99): gradients then all-reduce over NCCL.
 
-    def __init__(self, net: torch.nn.Module, lr: float = 2e-4, betas=(0.9, 0.99), ema_decay: float = 0.999):
+    use_graph: capture the whole step (forward, backward, Adam, EMA) into one CUDA graph per (scale, batch shape) and replay it.
+    At the training shape (4 x 7 x 3 x 64 x 64 per GPU) a step is ~20 000 small kernels and purely launch-bound when issued from
+    Python; the graph removes that.  Single-process only (not combined with DistributedDataParallel here)."""
+
+    def __init__(self, net: torch.nn.Module, lr: float = 2e-4, betas=(0.9, 0.99), ema_decay: float = 0.999, use_graph: bool = False):
         self.net = net
         self.core = net.module if hasattr(net, "module") else net
-        self.opt = torch.optim.Adam([p for p in net.parameters() if p.requires_grad], lr=lr, betas=betas)
+        if use_graph and self.core is not net:
+            raise ValueError("use_graph is for a single process; with DistributedDataParallel run the eager step")
+        self.use_graph = use_graph
+        self.opt = torch.optim.Adam([p for p in net.parameters() if p.requires_grad], lr=lr, betas=betas, capturable=use_graph)
         self.ema_decay = ema_decay
         self.ema = {k: v.detach().clone() for k, v in self.core.named_parameters()} if ema_decay > 0 else None
+        self._graphs = {}
 
-    def step(self, lq: Tensor, gt: Tensor, scale) -> Tensor:
-        self.core.set_scale(scale)
-        self.net.train()
-        self.opt.zero_grad(set_to_none=True)
+    def _step_body(self, lq: Tensor, gt: Tensor) -> Tensor:
         loss = charbonnier(self.net(lq), gt)
         loss.backward()
         self.opt.step()
@@ -242,3 +247,31 @@ class Trainer:
                 for k, v in self.core.named_parameters():
                     self.ema[k].mul_(self.ema_decay).add_(v.detach(), alpha=1 - self.ema_decay)
         return loss.detach()
+
+    def step(self, lq: Tensor, gt: Tensor, scale) -> Tensor:
+        self.core.set_scale(scale)
+        self.net.train()
+        if not self.use_graph:
+            self.opt.zero_grad(set_to_none=True)
+            return self._step_body(lq, gt)
+        key = (tuple(normalize_scale(scale)), tuple(lq.shape), tuple(gt.shape))
+        ent = self._graphs.get(key)
+        if ent is None:
+            s_lq, s_gt = lq.clone(), gt.clone()
+            side = torch.cuda.Stream(lq.device)
+            side.wait_stream(torch.cuda.current_stream(lq.device))
+            with torch.cuda.stream(side):                       # warm-up outside the graph: kernel attributes, optimizer state, cuDNN plans
+                for _ in range(2):
+                    self.opt.zero_grad(set_to_none=True)
+                    self._step_body(s_lq, s_gt)
+            torch.cuda.current_stream(lq.device).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            self.opt.zero_grad(set_to_none=True)
+            with torch.cuda.graph(g):
+                s_loss = self._step_body(s_lq, s_gt)
+            ent = self._graphs[key] = (g, s_lq, s_gt, s_loss)
+        g, s_lq, s_gt, s_loss = ent
+        s_lq.copy_(lq, non_blocking=True)
+        s_gt.copy_(gt, non_blocking=True)
+        g.replay()
+        return s_loss

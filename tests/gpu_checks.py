@@ -546,9 +546,10 @@ def check_conv_autograd(B=2, nsrc=2, H=16, W=20, per_sample=False, bias=True, se
 
 def _grad_report(named_gpu, sd_cpu, keys):
     """Error of the gradient per parameter tensor, GPU (16-bit operand convs) vs fp32 CPU autograd on the oracle:
-    |g - r| / max(|r|, 1e-3 * largest tensor-gradient norm of the block).  The floor matters: some true gradients are zero (a conv
-    bias in front of a train-mode BatchNorm; everything upstream of a BatchNorm over a batch of two 1x1 maps, whose output is +-1
-    whatever its input), where a pure relative error would compare rounding noise with rounding noise."""
+    |g - r| / max(|r|, 1e-2 * largest tensor-gradient norm of the block).  The floor matters: some true gradients are zero or
+    ill-conditioned (a conv bias in front of a train-mode BatchNorm; everything upstream of ScaleAttention's BatchNorm over a batch
+    of two 1x1 maps, whose output is +-1 whatever its input: scale_routing), where a pure relative error would compare rounding
+    noise with rounding noise (and the fp32 atomics of the weight gradient make that noise vary from run to run)."""
     big = max(float(sd_cpu[k].grad.norm()) for k in keys if sd_cpu[k].grad is not None)
     rep = {}
     for k in keys:
@@ -556,7 +557,7 @@ def _grad_report(named_gpu, sd_cpu, keys):
         assert (g is None) == (r is None), f"{k}: gradient present on one side only"
         if r is None:
             continue
-        rep[k] = float((g.cpu() - r).norm()) / max(float(r.norm()), 1e-3 * big)
+        rep[k] = float((g.cpu() - r).norm()) / max(float(r.norm()), 1e-2 * big)
     return rep
 
 
