@@ -72,7 +72,7 @@ enum savsr_conv_impl {
  * torch.cat feeding it (404, 412, 462, 498, 721, 374) and the elementwise ops that follow it.
  *
  *   acc = sum_{s < nsrc} sum_{tap} W[s, tap] * src_s(shifted by tap)          (zero padding)
- *   v   = act(acc + bias) ; v *= mask[pixel] ; v += res1 ; v += res2_scale * res2 ; store v
+ *   v   = act(acc + bias) ; v *= mask[pixel] ; v += res1 ; v += res2_scale * res2 ; store v      (LeakyReLU slope in [0, 1])
  *   pool (optional): per-(sample, tile-warp) partial channel sums of v, consumed by the next
  *   OSA-Conv / channel-attention global average pool (savsr_arch.py:146, 515).
  */
@@ -91,6 +91,10 @@ typedef struct savsr_conv_group {
   const float* mask;            /* [batch][H*W] fp32 per-pixel multiplier or NULL (OSAdapt)      */
   float* pool;                  /* [batch][tiles*4][64] fp32 partial sums or NULL                */
   void* aux_dst;                /* SAVSR_DST_AUX16 destination                                   */
+  int32_t src_channels;         /* 0 (= 64) or 16 / 32 / 48: only this many LEADING channels of every source carry data, the
+                                   rest are zero in the arena AND in the filter (first layer: 21 frame channels of 64); the
+                                   tensor-core K loop skips the zero part.  Same value for all groups of a launch.          */
+  int32_t reserved_;
 } savsr_conv_group;
 
 /* Tuning / bring-up knobs of a context (savsr_ctx_set_option).  The library reads no environment variables. */

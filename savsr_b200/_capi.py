@@ -49,6 +49,8 @@ class ConvGroup(C.Structure):
         ("mask", C.c_void_p),
         ("pool", C.c_void_p),
         ("aux_dst", C.c_void_p),
+        ("src_channels", C.c_int32),
+        ("reserved_", C.c_int32),
     ]
 
 

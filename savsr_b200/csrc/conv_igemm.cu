@@ -66,6 +66,7 @@ struct ConvParams {
   int dst_mode;
   int fmt;              // enum savsr_format of the arena and the packed weights
   int issuers;          // batched kernel: MMA-issuing warps, 2 (default) or 1 (bring-up knob SAVSR_BIGK_ISSUERS)
+  int ksteps;           // K = 16 steps per tap that carry data: 4 = all 64 channels of a source; fewer when the groups declare src_channels
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
@@ -88,7 +89,7 @@ struct EpiCtx {
   bool valid;
   int bias_group;
   // per-conv constants hoisted out of the per-element code (reloaded only when the conv changes)
-  float neg_slope;     // activation as max(v,0) + neg_slope * min(v,0): 1 = none, 0 = ReLU, s = LeakyReLU(s)
+  float neg_slope;     // activation as max(t, neg_slope * t), 0 <= neg_slope <= 1: 1 = none, 0 = ReLU, s = LeakyReLU(s)
   float res2_scale;
   int res1_slot, res2_slot, dst_slot;
   bool has_mask;
@@ -152,7 +153,7 @@ __device__ __forceinline__ void epi_finish(const ConvParams& p, const savsr_conv
 #pragma unroll
   for (int j = 0; j < NC; ++j) {
     const float t = v[j] + c.bias[j];
-    v[j] = fmaxf(t, 0.f) + ns * fminf(t, 0.f);   // none / ReLU / LeakyReLU without branches
+    v[j] = fmaxf(t, ns * t);   // none / ReLU / LeakyReLU without branches (slope in [0, 1]); two instructions
   }
   if constexpr (NC == 32) {
     if (c.has_mask) {
@@ -311,7 +312,8 @@ __device__ __forceinline__ void epiq_finish(const ConvParams& p, int n, int tile
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float t = v[j][i] + c.bias[i];
-      v[j][i] = fmaxf(t, 0.f) + ns * fminf(t, 0.f);   // none / ReLU / LeakyReLU without branches
+      v[j][i] = fmaxf(t, ns * t);   // none / ReLU / LeakyReLU without branches (slope in [0, 1]): the epilogue's instruction count is
+                                    // what limits single-source convs, every instruction per element counts
     }
   }
   if (c.has_mask) {
@@ -353,10 +355,16 @@ __device__ __forceinline__ void epiq_finish(const ConvParams& p, int n, int tile
     // and reduced across the 8 thread groups (7 shuffles, reduce-scatter: channel ch0 + 4 b4 + 2 b3 + b2 per lane) only
     // when the run ends.  The run's total lands in the partial-sum slot of its last tile, the other tiles' slots get zero:
     // consumers still add all tiles * 4 slots per sample.  Deterministic (the tile -> CTA partition is fixed per launch).
+    if (valid == 0xfu) {   // interior pixels (all but the tiles on the right / bottom image edge): plain adds
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 8; ++i) c.psum[i] += (v[0][i] + v[1][i]) + (v[2][i] + v[3][i]);
+    } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) c.psum[i] += ((valid >> j) & 1u) ? v[j][i] : 0.f;
+      for (int i = 0; i < 8; ++i) {
+        const float a0 = (valid & 1u) ? v[0][i] : 0.f, a1 = (valid & 2u) ? v[1][i] : 0.f;
+        const float a2 = (valid & 4u) ? v[2][i] : 0.f, a3 = (valid & 8u) ? v[3][i] : 0.f;
+        c.psum[i] += (a0 + a1) + (a2 + a3);
+      }
     }
     const int npart = p.tiles_x * p.tiles_y * 4;
     const int ch = ch0 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
@@ -871,18 +879,36 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
                 // (UTCHMMA / UIADD3.64 pairs) issues at 50, the tensor core retiring one N = 64 MMA per 48
                 // (scripts/umma_bench.cu, "rolled tap loop").
                 uint32_t al = al0, bl = bl0, acc = s ? 1u : 0u;
+                if (p.ksteps == 4) {
 #pragma unroll 1
-                for (int dy = 0; dy < 3; ++dy) {
+                  for (int dy = 0; dy < 3; ++dy) {
 #pragma unroll
-                  for (int dx = 0; dx < 3; ++dx) {
+                    for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                      umma_bf16(d_tmem, make_desc(a_hi, al + dx * 8 + 2 * k), make_desc(b_hi, bl + dx * (kBBytes >> 4) + 2 * k), idesc, acc);
-                      acc = 1u;
+                      for (int k = 0; k < 4; ++k) {
+                        umma_bf16(d_tmem, make_desc(a_hi, al + dx * 8 + 2 * k), make_desc(b_hi, bl + dx * (kBBytes >> 4) + 2 * k), idesc, acc);
+                        acc = 1u;
+                      }
                     }
+                    al += kHaloPitch * 8;
+                    bl += 3 * (kBBytes >> 4);
                   }
-                  al += kHaloPitch * 8;
-                  bl += 3 * (kBBytes >> 4);
+                } else {
+                  // sources whose trailing channels are zero by construction (the packed 7 x 3 input frames of the first layer):
+                  // the K steps over those channels would multiply zeros by zero-expanded filter columns -- skip them
+#pragma unroll 1
+                  for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll 1
+                      for (int k = 0; k < p.ksteps; ++k) {
+                        umma_bf16(d_tmem, make_desc(a_hi, al + dx * 8 + 2 * k), make_desc(b_hi, bl + dx * (kBBytes >> 4) + 2 * k), idesc, acc);
+                        acc = 1u;
+                      }
+                    }
+                    al += kHaloPitch * 8;
+                    bl += 3 * (kBBytes >> 4);
+                  }
                 }
                 umma_commit(a_empty + sa);
               }
@@ -1170,6 +1196,9 @@ extern "C" int savsr_conv(savsr_ctx* ctx, savsr_arena* arena, const savsr_conv_g
     SAVSR_REQUIRE(g.nsrc >= 1 && g.nsrc <= SAVSR_MAX_SRC, "savsr_conv: group %d nsrc %d out of range", i, g.nsrc);
     SAVSR_REQUIRE(g.weight != nullptr, "savsr_conv: group %d has no weights", i);
     SAVSR_REQUIRE(g.nsrc == groups[0].nsrc, "savsr_conv: all groups of a launch must have the same nsrc (%d vs %d)", g.nsrc, groups[0].nsrc);
+    SAVSR_REQUIRE(g.src_channels == groups[0].src_channels && g.src_channels >= 0 && g.src_channels <= 64 && g.src_channels % 16 == 0,
+                  "savsr_conv: src_channels (%d) must be 0, 16, 32, 48 or 64 and equal for all groups of a launch", g.src_channels);
+    SAVSR_REQUIRE(g.act != SAVSR_ACT_LRELU || (g.slope >= 0.f && g.slope <= 1.f), "savsr_conv: group %d LeakyReLU slope %g outside [0, 1]", i, g.slope);
     for (int s = 0; s < g.nsrc; ++s) {
       SAVSR_REQUIRE(g.src_slot[s] >= 0 && g.src_slot[s] < arena->nslots, "savsr_conv: group %d source slot %d out of range", i, g.src_slot[s]);
       SAVSR_REQUIRE(dst_mode != SAVSR_DST_ARENA || g.src_slot[s] != g.dst_slot, "savsr_conv: group %d writes slot %d that it also convolves", i, g.dst_slot);
@@ -1199,6 +1228,7 @@ extern "C" int savsr_conv(savsr_ctx* ctx, savsr_arena* arena, const savsr_conv_g
   p.fmt = ctx->fmt;
   p.dbg = ctx->conv_dbg;
   p.issuers = ctx->opt[SAVSR_OPT_BIGK_ISSUERS];
+  p.ksteps = groups[0].src_channels ? groups[0].src_channels / 16 : 4;   // honoured by the batched 3x3 kernel; the others always run all four
   if (n_tile == 64) return launch_conv<64>(ctx, p, impl, static_cast<cudaStream_t>(st));
   return launch_conv<16>(ctx, p, impl, static_cast<cudaStream_t>(st));
 }

@@ -226,7 +226,7 @@ class Plan:
 
     def _group(self, src: Sequence[int], dst: int, weight: int, bias: int = 0, act: int = K.ACT_NONE, slope: float = 0.2,
                res1: int = -1, res2: int = -1, res2_scale: float = 0.0, wstride: int = 0, mask: int = 0, pool: int = 0,
-               aux: int = 0) -> K.ConvGroup:
+               aux: int = 0, src_channels: int = 0) -> K.ConvGroup:
         g = K.ConvGroup()
         for i, s in enumerate(src):
             g.src_slot[i] = s
@@ -235,6 +235,7 @@ class Plan:
         g.act, g.slope = act, slope
         g.weight, g.weight_sample_stride = weight, wstride
         g.bias, g.mask, g.pool, g.aux_dst = bias or None, mask or None, pool or None, aux or None
+        g.src_channels = src_channels
         return g
 
     def _conv(self, arena: K.Arena, groups: Sequence[K.ConvGroup], ksize: int = 3, n_tile: int = 64,
@@ -390,8 +391,9 @@ class Plan:
                     wz[:, 3 * (c - 1):3 * (c - 1) + 3] = wsup[:, 0:3]
                     wz[:, 3 * (c + 1):3 * (c + 1) + 3] = wsup[:, 3:6]
                     return wz
-                fgroups.append(self._group([FR], S0[d][0], self._pack((p, "conv_c@", c), wc), self._ptr(p + ".conv_c.bias"), act=L))
-                fgroups.append(self._group([FR], S0[d][1], self._pack((p, "conv_sup@", c), ws), self._ptr(p + ".conv_sup.bias"), act=L))
+                # the frames slot carries 7 x 3 = 21 channels: the K loop runs over the first 32 only
+                fgroups.append(self._group([FR], S0[d][0], self._pack((p, "conv_c@", c), wc), self._ptr(p + ".conv_c.bias"), act=L, src_channels=32))
+                fgroups.append(self._group([FR], S0[d][1], self._pack((p, "conv_sup@", c), ws), self._ptr(p + ".conv_sup.bias"), act=L, src_channels=32))
             # algorithmic input channels of these launches are 3 and 6, not the 64 of the zero-expanded filters
             self._conv(lr, fgroups, alg_ci=[3, 6, 3, 6])
             cur = [[S0[d][0], S0[d][1], hpast[d]] for d in range(2)]

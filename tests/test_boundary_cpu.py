@@ -68,7 +68,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert ctypes.sizeof(_capi.ConvGroup) == 96 and _capi.ConvGroup.weight.offset == 48
+    assert ctypes.sizeof(_capi.ConvGroup) == 104 and _capi.ConvGroup.weight.offset == 48 and _capi.ConvGroup.src_channels.offset == 96
     assert _capi.OsaParams.pool.offset == 16 + 16 * 8 and ctypes.sizeof(_capi.SatuWeights) == 96
 
 
