@@ -271,9 +271,11 @@ int savsr_satu_hr(savsr_ctx* ctx, savsr_arena* lr, int x_slot, int sta_slot, int
 /* ---- post-processing / metrics on the device (next row 8f3) -------------------------------------------------------
  * tensor2img (lbasicsr/utils/img_util.py:38-94): sr fp32 NCHW [batch][3][H][W] RGB -> uint8 HWC BGR [batch][H][W][3]
  * (clamp, *255, round half to even), and, when gt is given, the per-frame sum of squared Y-channel differences of the two
- * uint8 images (metric_util.py:32-45, color_util.py:38-68, psnr_ssim.py:11-48 with crop_border 0) in float64:
- * PSNR_Y = 10 log10(255^2 * H*W / sse_y).  bgr_u8 and sse_y may each be NULL.
+ * uint8 images (metric_util.py:32-45, color_util.py:38-68, psnr_ssim.py:11-48 with crop_border 0) in float64, as one partial
+ * sum per thread block: sse_y [batch][savsr_img_metrics_blocks(ctx, H, W)], SSE_n = sum(sse_y[n]) in a fixed order (bit-reproducible),
+ * PSNR_Y = 10 log10(255^2 * H*W / SSE_n).  bgr_u8 and sse_y may each be NULL.
  */
+int savsr_img_metrics_blocks(const savsr_ctx* ctx, int height, int width);
 int savsr_img_metrics(savsr_ctx* ctx, const float* sr, const float* gt, int batch, int height, int width,
                       uint8_t* bgr_u8, double* sse_y, savsr_stream st);
 

@@ -911,6 +911,10 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
                   }
                 }
                 umma_commit(a_empty + sa);
+                // the tile's accumulator is complete once its LAST source has been applied: hand it to the epilogue right away
+                // instead of at the end of the batch (the epilogue of tiles 0, 1 then overlaps the MMAs of tiles 2, 3: shorter
+                // pipeline fill and drain per launch, accumulators recycle earlier)
+                if (s == nsrc - 1) umma_commit(t_full + bb * kBatchTiles + j);
               }
               __syncwarp();
             }
@@ -922,12 +926,6 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
           __syncwarp();
         }
       }
-      if (elect_one()) {
-#pragma unroll
-        for (int j = 0; j < kBatchTiles; ++j)
-          if (j < cnt && (j & own_mask) == my) umma_commit(t_full + bb * kBatchTiles + j);
-      }
-      __syncwarp();
 #pragma unroll
       for (int j = 0; j < kBatchTiles; ++j)
         if (j < cnt) use_bits ^= 1u << (bb * kBatchTiles + j);

@@ -416,8 +416,8 @@ __global__ void __launch_bounds__(256) mask_final_kernel(const float* __restrict
 
 // ------------------------------------------------------------------------------------------------ post-processing (8f3)
 // tensor2img (img_util.py:38-94): clamp[0,1] -> *255 -> round half-to-even -> uint8, RGB -> BGR, HWC; and the squared
-// Y-channel difference against a ground-truth frame (metric_util.py:32-45, psnr_ssim.py:11-48), accumulated per frame
-// in double.  grid (blocks, batch), 256 threads.
+// Y-channel difference against a ground-truth frame (metric_util.py:32-45, psnr_ssim.py:11-48), accumulated in double, one
+// partial sum per block (deterministic, like ssim_y).  grid (blocks, batch), 256 threads.
 __device__ __forceinline__ float y_of_u8(int b, int g, int r) {
   const double d = (static_cast<double>(static_cast<float>(b) / 255.f) * 24.966 + static_cast<double>(static_cast<float>(g) / 255.f) * 128.553) +
                    static_cast<double>(static_cast<float>(r) / 255.f) * 65.481 + 16.0;
@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(256) img_metrics_kernel(const float* __restric
     if (threadIdx.x == 0) {
       double t = 0.0;
       for (int i = 0; i < 8; ++i) t += red[i];
-      atomicAdd(sse + n, t);
+      sse[static_cast<long>(n) * gridDim.x + blockIdx.x] = t;   // one partial per block, summed by the caller in a fixed order: bit-reproducible
     }
   }
 }
@@ -631,6 +631,17 @@ extern "C" int savsr_osadapt_mask(savsr_ctx* ctx, const float* in16, int batch, 
   return 0;
 }
 
+static long img_metrics_grid(const savsr_ctx* ctx, int height, int width) {
+  const long npix = static_cast<long>(height) * width;
+  long blocks = (npix + 255) / 256;
+  if (blocks > 4L * ctx->sm_count) blocks = 4L * ctx->sm_count;
+  return blocks;
+}
+
+extern "C" int savsr_img_metrics_blocks(const savsr_ctx* ctx, int height, int width) {
+  return (ctx && height > 0 && width > 0) ? static_cast<int>(img_metrics_grid(ctx, height, width)) : 0;
+}
+
 extern "C" int savsr_img_metrics(savsr_ctx* ctx, const float* sr, const float* gt, int batch, int height, int width, uint8_t* bgr_u8,
                                  double* sse_y, savsr_stream st_) {
   SAVSR_REQUIRE(ctx && sr, "savsr_img_metrics: null pointer");
@@ -639,10 +650,7 @@ extern "C" int savsr_img_metrics(savsr_ctx* ctx, const float* sr, const float* g
   SAVSR_REQUIRE(!sse_y || gt, "savsr_img_metrics: sse_y requested without a ground-truth frame");
   if (batch == 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(st_);
-  if (sse_y) SAVSR_CUDA(cudaMemsetAsync(sse_y, 0, sizeof(double) * batch, st));
-  const long npix = static_cast<long>(height) * width;
-  long blocks = (npix + 255) / 256;
-  if (blocks > 4L * ctx->sm_count) blocks = 4L * ctx->sm_count;
+  const long blocks = img_metrics_grid(ctx, height, width);
   img_metrics_kernel<<<dim3(static_cast<unsigned>(blocks), batch), 256, 0, st>>>(sr, gt, height, width, bgr_u8, sse_y);
   SAVSR_CUDA(cudaGetLastError());
   return 0;

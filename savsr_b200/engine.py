@@ -584,7 +584,9 @@ class Plan:
             self.run()
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # an explicit capture stream ON THIS PLAN'S DEVICE: torch's default capture stream is created once per process on
+            # whatever device was current then, and capturing through it on another device records an empty graph
+            with torch.cuda.graph(g, stream=torch.cuda.Stream(self.device)):
                 self.run()
             self.graph = g
 

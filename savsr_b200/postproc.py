@@ -27,14 +27,15 @@ def tensor2img_psnr(sr: torch.Tensor, gt: Optional[torch.Tensor] = None, want_im
     n, _, H, W = sr.shape
     ctx = engine.context(sr.device.index if sr.device.index is not None else torch.cuda.current_device())
     img = torch.empty(n, H, W, 3, dtype=torch.uint8, device=sr.device) if want_image else None
-    sse = torch.empty(n, dtype=torch.float64, device=sr.device) if gt is not None else None
+    nb = ctx.lib.savsr_img_metrics_blocks(ctx.handle, H, W)
+    part = torch.empty(n, nb, dtype=torch.float64, device=sr.device) if gt is not None else None
     with torch.cuda.device(sr.device):
         K.check(ctx.lib.savsr_img_metrics(ctx.handle, sr.data_ptr(), gt.data_ptr() if gt is not None else None, n, H, W,
-                                          img.data_ptr() if img is not None else None, sse.data_ptr() if sse is not None else None,
+                                          img.data_ptr() if img is not None else None, part.data_ptr() if part is not None else None,
                                           torch.cuda.current_stream().cuda_stream))
     psnr = None
-    if sse is not None:
-        mse = sse / float(H * W)
+    if part is not None:
+        mse = part.sum(dim=1) / float(H * W)          # per-block partials, fixed summation order: bit-reproducible
         psnr = torch.where(mse == 0, torch.full_like(mse, math.inf), 10.0 * torch.log10(255.0 * 255.0 / mse))
     return img, psnr
 

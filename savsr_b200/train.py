@@ -267,7 +267,7 @@ class Trainer:
             torch.cuda.current_stream(lq.device).wait_stream(side)
             g = torch.cuda.CUDAGraph()
             self.opt.zero_grad(set_to_none=True)
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=torch.cuda.Stream(lq.device)):        # capture stream on the data's device (cf. engine.Plan.capture)
                 s_loss = self._step_body(s_lq, s_gt)
             ent = self._graphs[key] = (g, s_lq, s_gt, s_loss)
         g, s_lq, s_gt, s_loss = ent

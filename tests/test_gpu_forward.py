@@ -188,6 +188,33 @@ def test_training_step_whole_net(G):
     assert info["losses"][-1] < info["losses"][0]
 
 
+def test_second_device_in_one_process(G):
+    """Advisor finding (round 1): kernel attributes are per device and launches must follow the module's device, not the caller's
+    current device.  One process, module on cuda:1 while cuda:0 is current; result must equal the cuda:0 result bit for bit."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    import savsr_b200
+    from oracle.state_dict_fixture import make_input, make_state_dict
+    sd = make_state_dict(1)
+    x = make_input(2, 18, 22, 5)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        net = savsr_b200.SAVSR().to(dev)
+        net.load_state_dict(sd, strict=True)
+        net.eval(); net.set_scale((2.7, 1.5))
+        torch.cuda.set_device(0)                                   # the caller's current device stays cuda:0 throughout
+        with torch.no_grad():
+            y = net(x.to(dev))
+            y2 = net(x.flip(0).to(dev))                            # second call, other input: a real CUDA-graph replay on that device
+            net.use_graph = False
+            y3 = net(x.flip(0).to(dev))                            # the same eagerly
+        assert y.device == torch.device(dev) and torch.equal(y2, y3) and not torch.equal(y, y2)
+        assert torch.equal(y2.flip(0), y)                          # windows are independent: flipping the batch flips the result
+        assert torch.cuda.current_device() == 0
+        outs.append(y.cpu())
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_module_api_errors(G):
     import savsr_b200
     net = savsr_b200.SAVSR().cuda()
