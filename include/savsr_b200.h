@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SAVSR_ABI_VERSION 3
+#define SAVSR_ABI_VERSION 4
 #define SAVSR_MAX_SRC 5      /* most 64-channel sources one conv concatenates (OSA 320->64)      */
 #define SAVSR_MAX_GROUPS 25  /* most independent convolutions batched into one launch            */
 #define SAVSR_TILE_W 8       /* output tile = 8 x 16 pixels = 128 GEMM rows (one UMMA M)         */
@@ -170,6 +170,75 @@ int savsr_pack_frames(savsr_ctx* ctx, savsr_arena* arena, const float* x, int t,
  */
 int savsr_conv_wgrad(savsr_ctx* ctx, const void* x3_nchw16, const void* dy_nchw16, int batch, int ci, int height, int width,
                      int pitch, int per_sample, float* dw, savsr_stream st);
+
+/* ---- native training step (row 8f1, stage B) ---------------------------------------------------------------------------------
+ * The reference's optimisation step (lbasicsr/models/sr_model.py:101-128: forward, Charbonnier, autograd backward through cuDNN
+ * dgrad / wgrad, Adam; base_model.py:75-82 EMA) as launches on the activation arena.  Gradients of activations live in slots of
+ * the same arena; the weight gradient reads pixel-contiguous copies from a second caller-owned buffer, the "T-arena":
+ * 16-bit NCHW, T-slot t = [batch][64][height][pitch] (pitch = width rounded up to a multiple of 8; the padding columns must be
+ * zero: allocate it zeroed, these kernels never write non-zero values there).  savsr_b200/trainplan.py drives them.
+ * Every `entries` array below is HOST memory (copied into the launch), at most 32 entries per call; `*_dev` arrays are DEVICE memory.
+ */
+typedef struct savsr_axpby {
+  int32_t dst_slot, x_slot, y_slot;   /* y_slot -1: dst = alpha * x                                              */
+  float alpha, beta;                  /* dst = alpha * x + beta * y (dst may alias x or y)                       */
+} savsr_axpby;
+int savsr_slot_axpby(savsr_ctx* ctx, savsr_arena* arena, const savsr_axpby* entries, int n, savsr_stream st);
+
+/* Gradient entering a convolution whose epilogue was v = act(acc + bias) (+ pooled mean taken from v):
+ *   g = (dV * cscale[n][c] + cadd_mul * cadd[n][c]) * act'(out)       act' from the sign of the stored output
+ * written to g_slot (NHWC, operand of the data gradient; may equal dv_slot), to T-slot gt_tslot (operand of the weight
+ * gradient) and summed over (n, y, x) into dbias (+=).  cscale: RCAB channel attention (savsr_arch.py:547-549); cadd: the
+ * gradient of a global average pool of the output (OSA-Conv / channel attention inputs, savsr_arch.py:146, 515). */
+typedef struct savsr_grad_prep_entry {
+  int32_t dv_slot, out_slot, g_slot, gt_tslot;   /* g_slot / gt_tslot -1: not written                            */
+  int32_t act;                                   /* enum savsr_act of the forward epilogue                       */
+  float slope;
+  const float* cscale; int64_t cscale_stride;    /* [batch][stride] fp32, 64 used; NULL = 1                      */
+  const float* cadd; int64_t cadd_stride; float cadd_mul;   /* NULL = 0                                          */
+  int32_t reserved_;
+  float* dbias;                                  /* [64] fp32 or NULL                                            */
+} savsr_grad_prep_entry;
+int savsr_grad_prep(savsr_ctx* ctx, savsr_arena* arena, void* tbase, int ntslots, int pitch, const savsr_grad_prep_entry* entries, int n,
+                    savsr_stream st);
+
+/* Arena slot -> T-slots t_slot, t_slot + 1, t_slot + 2 = the activation shifted along x by -1, 0, +1 pixel (copy d holds
+ * X[.., x + d - 1], zero outside the row): TMA boxes start on 16-byte granules, so the shifts are materialised. */
+typedef struct savsr_nchw3 { int32_t x_slot, t_slot; } savsr_nchw3;
+int savsr_slot_to_nchw3(savsr_ctx* ctx, savsr_arena* arena, void* tbase, int ntslots, int pitch, const savsr_nchw3* entries, int n,
+                        savsr_stream st);
+
+/* One (64 output channels x 64 input channels) corner of an fp32 OIHW filter [co_total][ci_total][k][k] -> k*k tensor-core blocks
+ * [64][64] (16-bit, context format, SAVSR_ROWS_QUAD, 128-byte swizzle; k*k*8192 bytes at dst).  transposed = 0: rows = output
+ * channels o_base.., K = input channels i_base.. (forward operand: block (source s, tap) of savsr_pack_conv_weight).
+ * transposed = 1: rows = input channels, K = output channels, taps flipped: the operand of the data gradient
+ * dX = conv(dY, W^T flipped).  Channels beyond co_total / ci_total read as zero. */
+typedef struct savsr_pack_chunk {
+  const float* w;
+  void* dst;
+  int32_t co_total, ci_total, o_base, i_base, ksize, transposed;
+} savsr_pack_chunk;
+int savsr_pack_conv_chunks(savsr_ctx* ctx, const savsr_pack_chunk* chunks_dev, int first, int count, savsr_stream st);
+
+/* Weight gradients of many convolutions in one persistent tcgen05 launch (the kernel of savsr_conv_wgrad, table-driven).
+ * Item = one (convolution, 64-channel source):   dw[(o_off + o) * ci_total + ci_off + i][tap] += sum_{n,p} g[n][o][p] x[n][i][p + tap]
+ * x_tslot: first of the source's three shifted T-slots (savsr_slot_to_nchw3); g_tslot: the T-slot savsr_grad_prep wrote.
+ * ksize 3: dw is [..][ci_total][3][3]; ksize 1: [..][ci_total] (centre tap).  per_sample: dw advances sample_stride floats per
+ * sample (the folded kernels of OSA-Conv).  dw is accumulated with atomics: zero it first. */
+typedef struct savsr_wgrad_item {
+  int32_t x_tslot, g_tslot;
+  float* dw;
+  int32_t ci_total, ci_off, o_off, ksize, per_sample, reserved_;
+  int64_t sample_stride;
+} savsr_wgrad_item;
+int savsr_conv_wgrad_batched(savsr_ctx* ctx, const void* tbase, int ntslots, int batch, int height, int width, int pitch,
+                             const savsr_wgrad_item* items_dev, int first, int count, savsr_stream st);
+
+/* torch.optim.Adam (no weight decay, no amsgrad; sr_model.py:77-89, train YAML lr 2e-4, betas 0.9 / 0.99) followed by the EMA of
+ * base_model.py:75-82, over flat fp32 buffers.  step_dev: device scalar holding the step count t >= 1 as a float (bias corrections
+ * 1 - beta^t).  grad_scale multiplies the gradient first (1 / world size after a summing all-reduce).  ema may be NULL. */
+int savsr_adam_ema(savsr_ctx* ctx, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, long n, float lr,
+                   float beta1, float beta2, float eps, const float* step_dev, float ema_decay, float grad_scale, savsr_stream st);
 
 /* ---- OSA-Conv prologue (savsr_arch.py:143-163, 91-96, 123-128) ---------------------------------- */
 typedef struct savsr_osa_params {

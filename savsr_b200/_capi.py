@@ -11,7 +11,7 @@ import ctypes as C
 import os
 from typing import Optional
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_SRC = 5
 MAX_GROUPS = 25
 TILE_W, TILE_H = 8, 16
@@ -74,6 +74,35 @@ class SatuWeights(C.Structure):
         "st_offset_w", "st_offset_b", "compress", "expand")]
 
 
+class Axpby(C.Structure):
+    _fields_ = [("dst_slot", C.c_int32), ("x_slot", C.c_int32), ("y_slot", C.c_int32), ("alpha", C.c_float), ("beta", C.c_float)]
+
+
+class GradPrep(C.Structure):
+    _fields_ = [("dv_slot", C.c_int32), ("out_slot", C.c_int32), ("g_slot", C.c_int32), ("gt_tslot", C.c_int32),
+                ("act", C.c_int32), ("slope", C.c_float),
+                ("cscale", C.c_void_p), ("cscale_stride", C.c_int64),
+                ("cadd", C.c_void_p), ("cadd_stride", C.c_int64), ("cadd_mul", C.c_float), ("reserved_", C.c_int32),
+                ("dbias", C.c_void_p)]
+
+
+class Nchw3(C.Structure):
+    _fields_ = [("x_slot", C.c_int32), ("t_slot", C.c_int32)]
+
+
+class PackChunk(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("dst", C.c_void_p), ("co_total", C.c_int32), ("ci_total", C.c_int32), ("o_base", C.c_int32),
+                ("i_base", C.c_int32), ("ksize", C.c_int32), ("transposed", C.c_int32)]
+
+
+class WgradItem(C.Structure):
+    _fields_ = [("x_tslot", C.c_int32), ("g_tslot", C.c_int32), ("dw", C.c_void_p), ("ci_total", C.c_int32), ("ci_off", C.c_int32),
+                ("o_off", C.c_int32), ("ksize", C.c_int32), ("per_sample", C.c_int32), ("reserved_", C.c_int32),
+                ("sample_stride", C.c_int64)]
+
+MAX_TRAIN_ENTRIES = 32
+
+
 # name -> (restype, argtypes); every symbol declared in include/savsr_b200.h
 _VP, _I, _F, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 SIGNATURES = {
@@ -96,6 +125,12 @@ SIGNATURES = {
     "savsr_pack_conv_weight": (_I, [_VP, _I, _I, _I, _I, _I, _I, _I, _VP, _VP]),
     "savsr_conv": (_I, [_VP, _VP, C.POINTER(ConvGroup), _I, _I, _I, _I, _I, _VP]),
     "savsr_conv_wgrad": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP, _VP]),
+    "savsr_slot_axpby": (_I, [_VP, _VP, C.POINTER(Axpby), _I, _VP]),
+    "savsr_grad_prep": (_I, [_VP, _VP, _VP, _I, _I, C.POINTER(GradPrep), _I, _VP]),
+    "savsr_slot_to_nchw3": (_I, [_VP, _VP, _VP, _I, _I, C.POINTER(Nchw3), _I, _VP]),
+    "savsr_pack_conv_chunks": (_I, [_VP, _VP, _I, _I, _VP]),
+    "savsr_conv_wgrad_batched": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP, _I, _I, _VP]),
+    "savsr_adam_ema": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_long, _F, _F, _F, _F, _VP, _F, _F, _VP]),
     "savsr_pack_frames": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "savsr_osa_prologue": (_I, [_VP, C.POINTER(OsaParams), _I, _I, _I, _I, _F, _F, _VP]),
     "savsr_ca_scale_residual": (_I, [_VP, _VP, _I, _I, _I, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),

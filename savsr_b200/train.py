@@ -64,12 +64,13 @@ def _lrelu(x: Tensor, slope: float = 0.2) -> Tensor:
 
 
 # ------------------------------------------------------------------------------------------------ OSA-Conv (savsr_arch.py:139-172)
-def osconv(net: _Net, prefix: str, x: Tensor, scale) -> Tensor:
+def osa_fold(net: _Net, prefix: str, pooled: Tensor, scale) -> Tensor:
+    """pooled [b, ci] = mean(x) -> the per-sample folded kernels [b, co, ci, 3, 3] of OSA-Conv: scale_routing (savsr_arch.py:123-128),
+    ScaleAttention with train-mode BatchNorm (91-96), bank mix and the four attentions folded into the kernel (158-163)."""
     s = normalize_scale(scale)
-    b, ci = x.shape[0], x.shape[1]
+    b, ci = pooled.shape
     P = net.P
-    pooled = x.mean(dim=(2, 3))
-    info = torch.cat([x.new_full((b, 1), 1.0 / s[0]), x.new_full((b, 1), 1.0 / s[1])], 1)   # (1/s_h, 1/s_w), savsr_arch.py:143-145; fill kernels: graph-capturable
+    info = torch.cat([pooled.new_full((b, 1), 1.0 / s[0]), pooled.new_full((b, 1), 1.0 / s[1])], 1)   # (1/s_h, 1/s_w), savsr_arch.py:143-145; fill kernels: graph-capturable
     v = torch.cat([info, pooled], 1)
     v = F.relu(F.linear(v, P[prefix + ".scale_routing.0.weight"], P[prefix + ".scale_routing.0.bias"]))
     v = F.relu(F.linear(v, P[prefix + ".scale_routing.2.weight"], P[prefix + ".scale_routing.2.bias"]))
@@ -82,8 +83,11 @@ def osconv(net: _Net, prefix: str, x: Tensor, scale) -> Tensor:
     bank = P[prefix + ".weight"]                                                          # [8, 64, ci, 3, 3]
     co = bank.shape[1]
     w = torch.einsum("bk,koiuv->boiuv", ka, bank)
-    w = w * sa.view(b, 1, 1, 3, 3) * ca.view(b, 1, ci, 1, 1) * fa.view(b, co, 1, 1, 1)  # all four attentions folded into the kernel
-    return conv3x3(x, w)                                                                  # per-sample kernels, no bias (savsr_arch.py:166)
+    return w * sa.view(b, 1, 1, 3, 3) * ca.view(b, 1, ci, 1, 1) * fa.view(b, co, 1, 1, 1)  # all four attentions folded into the kernel
+
+
+def osconv(net: _Net, prefix: str, x: Tensor, scale) -> Tensor:
+    return conv3x3(x, osa_fold(net, prefix, x.mean(dim=(2, 3)), scale))                   # per-sample kernels, no bias (savsr_arch.py:166)
 
 
 # ------------------------------------------------------------------------------------------------ trunk blocks
@@ -133,16 +137,20 @@ def residual_group(net: _Net, prefix: str, x: Tensor) -> Tensor:
     return net.conv(prefix + ".conv", t) + x
 
 
-def osadapt(net: _Net, prefix: str, x: Tensor, scale) -> Tensor:
-    """savsr_arch.py:186-214"""
+def osadapt_mask(net: _Net, prefix: str, x: Tensor) -> Tensor:
+    """The mask net of OSAdapt (savsr_arch.py:189-206) -> [b, 1, h, w]"""
     m = prefix + ".mask"
     t = F.relu(net.bn(m + ".1", net.conv(m + ".0", x)))
     t = F.avg_pool2d(t, 2)
     t = F.relu(net.bn(m + ".5", net.conv(m + ".4", t)))
     t = F.relu(net.bn(m + ".8", net.conv(m + ".7", t)))
     t = F.interpolate(t, scale_factor=2, mode="bilinear", align_corners=False)
-    mask = torch.sigmoid(net.bn(m + ".12", net.conv(m + ".11", t)))
-    return x + osconv(net, prefix + ".adapt", x, scale) * mask
+    return torch.sigmoid(net.bn(m + ".12", net.conv(m + ".11", t)))
+
+
+def osadapt(net: _Net, prefix: str, x: Tensor, scale) -> Tensor:
+    """savsr_arch.py:186-214"""
+    return x + osconv(net, prefix + ".adapt", x, scale) * osadapt_mask(net, prefix, x)
 
 
 # ------------------------------------------------------------------------------------------------ SATU (savsr_arch.py:315-376)

@@ -650,6 +650,53 @@ def check_train_step(b=2, h=16, w=20, scale=(2, 2), seed=0, steps=3):
     return info
 
 
+def check_trainplan(b=2, h=16, w=20, scale=(2, 2), seed=0, tol_worst=0.25, tol_cos=0.995, steps=0, graph=False):
+    """Row f1 stage B: the NATIVE training step (savsr_b200.trainplan: arena-resident forward / dgrad / batched wgrad, table-driven
+    weight packing) against fp32 CPU autograd through the oracle: loss, per-parameter gradient error
+    |g - r| / max(|r|, 1 % of the largest tensor gradient), and the cosine of the whole flat gradient."""
+    import savsr_b200
+    from oracle import savsr_oracle as O
+    from oracle.state_dict_fixture import make_input, make_state_dict
+    from savsr_b200 import train as T
+    from savsr_b200 import trainplan as TP
+    sd = make_state_dict(seed)
+    net = savsr_b200.SAVSR().to(DEV)
+    net.load_state_dict(sd, strict=True)
+    net.set_scale(scale); net.train()
+    x = make_input(b, h, w, 1234 + seed)
+    H, W = O.get_hw(h, w, scale)
+    gt = torch.rand(b, 3, H, W, generator=torch.Generator().manual_seed(5))
+    sd_cpu = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    O.BN_TRAIN = True
+    try:
+        ref_loss = T.charbonnier(O.forward(sd_cpu, x, scale), gt)
+        ref_loss.backward()
+    finally:
+        O.BN_TRAIN = False
+    tr = TP.NativeTrainer(net, use_graph=graph)
+    plan = tr.plan_for(x.to(DEV), scale)
+    plan.x_in.copy_(x.to(DEV)); plan.gt.copy_(gt.to(DEV))
+    loss = tr._fwd_bwd(plan)
+    torch.cuda.synchronize()
+    params = dict(net.named_parameters())
+    keys = [k for k in params if sd_cpu[k].grad is not None]
+    rep = _grad_report(params, sd_cpu, keys)
+    gflat = torch.cat([params[k].grad.flatten().cpu() for k in keys])
+    rflat = torch.cat([sd_cpu[k].grad.flatten() for k in keys])
+    cos = float(torch.dot(gflat, rflat) / (gflat.norm() * rflat.norm()))
+    worst = sorted(rep.items(), key=lambda kv: -kv[1])[:5]
+    info = dict(loss=float(loss), ref_loss=float(ref_loss), cos=cos, grad_norm=float(gflat.norm()), ref_grad_norm=float(rflat.norm()),
+                worst=worst, median=float(np.median(list(rep.values()))), launches=dict(plan.launches), slots=plan.n_slots, tslots=plan.n_tslots)
+    assert abs(float(loss) - float(ref_loss)) < 2e-3 * max(1.0, abs(float(ref_loss))), info
+    assert np.isfinite(cos) and cos > tol_cos, info
+    assert all(np.isfinite(v) and v < tol_worst for v in rep.values()), info
+    if steps:
+        losses = [float(tr.step(x.to(DEV), gt.to(DEV), scale)) for _ in range(steps)]
+        info["losses"] = losses
+        assert all(np.isfinite(l) for l in losses) and losses[-1] < losses[0], info
+    return info
+
+
 def check_img_metrics(n=3, H=37, W=53, seed=31):
     """tensor2img (bit-exact uint8 BGR) and PSNR-Y on the device vs the oracle's restatement of the reference metric chain."""
     from oracle import savsr_oracle as O

@@ -1,0 +1,116 @@
+"""CPU-only: the host side of the native training plan (savsr_b200/trainplan.py) against the recording fake of the C library:
+the backward launch list is generated from the forward list, so the dataflow invariants the kernels rely on are checked here
+(every gradient slot is written before it is read or accumulated, no launch accumulates twice into one slot, every weight
+gets a weight-gradient item whose operands exist).  No kernel runs; the ATen islands execute on CPU tensors."""
+import contextlib
+
+import pytest
+import torch
+
+from fake_lib import mocked_engine
+from savsr_b200 import _capi as K
+
+
+@pytest.fixture(scope="module")
+def recorded():
+    import savsr_b200
+    from savsr_b200 import trainplan as TP
+    torch.manual_seed(0)
+    net = savsr_b200.SAVSR()
+    with mocked_engine() as lib:
+        saved = (TP.context, TP._require_cuda)
+        TP.context = lambda idx: __import__("savsr_b200.engine", fromlist=["context"]).context(idx)
+        TP._require_cuda = lambda dev: None
+        try:
+            tr = TP.NativeTrainer(net, use_graph=False)
+            lq = torch.rand(2, 7, 3, 16, 24)
+            gt = torch.rand(2, 3, 32, 48)
+            plan = tr.plan_for(lq, (2, 2))
+            lib.calls.clear()
+            loss = tr.step(lq, gt, (2, 2))
+            calls = list(lib.calls)
+        finally:
+            TP.context, TP._require_cuda = saved
+    return net, tr, plan, calls, loss
+
+
+def _entries(args, idx_arr, idx_n):
+    arr, n = args[idx_arr], args[idx_n]
+    return [arr[i] for i in range(n)]
+
+
+def test_step_runs_and_census(recorded):
+    net, tr, plan, calls, loss = recorded
+    names = [c[0] for c in calls]
+    assert torch.isfinite(loss)
+    assert names.count("savsr_pack_frames") == 1
+    assert names.count("savsr_adam_ema") == 1
+    assert names.count("savsr_ca_scale_residual") == 32
+    # one table-driven pack of the shared filters + one per OSA-Conv (per-sample folded kernels): l1 5 x 3 x 2 dirs, l2 2, adapt 4
+    assert names.count("savsr_pack_conv_chunks") == 1 + 30 + 2 + 4
+    # weight gradients: one inline launch per OSA-Conv launch (l1: both directions share one) + the final batched launch
+    assert names.count("savsr_conv_wgrad_batched") == 15 + 2 + 4 + 1
+    # forward convolutions as in the inference plan, minus the N = 16 mask convs (mask net = ATen island here)
+    fwd_convs = 5 * 14 + 9 + 4 * 18 + 1
+    assert names.count("savsr_conv") > 2 * fwd_convs
+
+
+def test_gradient_slots_are_written_before_use(recorded):
+    net, tr, plan, calls, _ = recorded
+    written = set()          # slots holding data
+    for name, args in calls:
+        if name == "savsr_pack_frames":
+            written.add(args[6])
+        elif name == "savsr_arena_import":
+            written.add(args[1])
+        elif name == "savsr_arena_export":
+            assert args[1] in written, f"export of slot {args[1]} before it was written"
+        elif name == "savsr_conv":
+            dsts = []
+            for g in _entries(args, 2, 3):
+                for i in range(g.nsrc):
+                    assert g.src_slot[i] in written or g.src_slot[i] == 0, f"conv reads unwritten slot {g.src_slot[i]}"
+                if g.res1_slot >= 0:
+                    assert g.res1_slot in written
+                dsts.append(g.dst_slot)
+            assert len(set(dsts)) == len(dsts), "two groups of one launch write the same slot"
+            written.update(dsts)
+        elif name == "savsr_slot_axpby":
+            dsts = []
+            for e in _entries(args, 2, 3):
+                assert e.x_slot in written or e.x_slot == 0
+                assert e.y_slot < 0 or e.y_slot in written or e.y_slot == 0
+                dsts.append(e.dst_slot)
+            assert len(set(dsts)) == len(dsts)
+            written.update(dsts)
+        elif name == "savsr_ca_scale_residual":
+            assert args[2] in written and args[3] in written
+            written.add(args[4])
+        elif name == "savsr_grad_prep":
+            for e in _entries(args, 5, 6):
+                assert e.dv_slot in written
+                assert e.act == K.ACT_NONE or e.out_slot in written
+                if e.g_slot >= 0:
+                    written.add(e.g_slot)
+
+
+def test_every_trunk_weight_has_a_weight_gradient_item(recorded):
+    net, tr, plan, calls, _ = recorded
+    G = tr.flat.G
+    targets = {}
+    for it in plan.witems:
+        targets.setdefault(it.dw, []).append(it)
+    want = [n for n, p in net.named_parameters() if n.endswith(".weight") and p.dim() == 4 and p.shape[0] % 64 == 0 and p.shape[1] % 64 == 0
+            and not n.startswith("upsample.")]
+    for n in want:
+        its = targets.get(G[n].data_ptr())
+        assert its, f"no weight-gradient item for {n}"
+        ci, co = G[n].shape[1], G[n].shape[0]
+        uses = len(its) // ((ci // 64) * (co // 64))
+        assert len(its) == uses * (ci // 64) * (co // 64), n
+        assert {it.ci_off for it in its} == set(range(0, ci, 64)) and {it.o_off for it in its} == set(range(0, co, 64)), n
+    # shared l1 weights are used once per propagation iteration
+    assert len(targets[G["f2p_win.blocks.1.conv2.0.weight"].data_ptr()]) == 5 * 2
+    # T-slots: every item's operands lie inside the T-arena
+    for it in plan.witems:
+        assert 0 <= it.x_tslot and it.x_tslot + 3 <= plan.n_tslots and 0 <= it.g_tslot < plan.n_tslots
