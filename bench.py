@@ -399,9 +399,17 @@ def run_train(args, rank, world, local_rank):
     per_gpu, h, w = 4, 64, 64
     torch.manual_seed(0)
     net = savsr_b200.SAVSR().to(dev)
-    model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank]) if world > 1 else net
-    graph = world == 1 and not args.no_train_graph          # one CUDA graph per scale for the whole step (single process)
-    tr = T.Trainer(model, use_graph=graph)
+    native = args.train_engine == "native"
+    if native:
+        # stage B: the static launch list of savsr_b200/trainplan.py (arena-resident forward / dgrad / batched wgrad, native attention
+        # backward, flat Adam + EMA), one CUDA graph per scale; data parallelism = one NCCL all-reduce of the flat gradient buffer
+        from savsr_b200 import trainplan as TP
+        graph = not args.no_train_graph
+        tr = TP.NativeTrainer(net, use_graph=graph, world_size=world)
+    else:
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank]) if world > 1 else net
+        graph = world == 1 and not args.no_train_graph          # one CUDA graph per scale for the whole step (single process)
+        tr = T.Trainer(model, use_graph=graph)
     gen = torch.Generator().manual_seed(100 + rank)
     lq_host = torch.rand(per_gpu, 7, 3, h, w, generator=gen).pin_memory()
     gts = {s: torch.rand(per_gpu, 3, *hw_out(h, w, s), generator=gen).pin_memory() for s in TRAIN_SCALES}
@@ -429,7 +437,7 @@ def run_train(args, rank, world, local_rank):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), float(last)
 
-    for i in range(max(args.warmup, 2) if not graph else len(TRAIN_SCALES)):      # with graphs: capture every scale before timing
+    for i in range(max(max(args.warmup, 2), len(TRAIN_SCALES) if graph else 0)):      # with graphs: capture every scale before timing
         step(i)
     ms, loss = timed_steps(step, args.steps)
     line = {"metric": "train_samples_per_s", "value": round(per_gpu * world * args.steps / (ms / 1e3), 2), "unit": "samples/s", "n_gpus": world,
@@ -438,9 +446,18 @@ def run_train(args, rank, world, local_rank):
             "config": {"workload": "train_cfg5", "per_gpu_batch": per_gpu, "global_batch": per_gpu * world, "lr_crop": [h, w], "frames": 7,
                        "scales": [list(s) for s in TRAIN_SCALES], "optimizer": "Adam 2e-4 (0.9, 0.99), Charbonnier, EMA 0.999",
                        "parallelism": f"DistributedDataParallel x{world} (NCCL gradient all-reduce, 75.6 MB fp32)" if world > 1 else "single GPU"},
-            "last_loss": round(loss, 5), "cuda_graph_per_scale": bool(graph),
-            "stage": "f1 staged: 3x3 convs (fwd / dgrad / wgrad, 98 % of the FLOPs) on tcgen05 through savsr_b200.autograd.conv3x3, each call "
-                     "still converting NCHW fp32 <-> the NHWC 16-bit arena; glue ops on ATen"}
+            "last_loss": round(loss, 5), "cuda_graph_per_scale": bool(graph), "engine": args.train_engine}
+    if native:
+        plan = next(iter(tr.plans.values()))
+        line["config"]["parallelism"] = (f"data parallel x{world}: one NCCL all-reduce of the flat fp32 gradient buffer ({tr.flat.n * 4 / 1e6:.1f} MB) per step"
+                                         if world > 1 else "single GPU")
+        line["stage"] = ("f1 stage B: static forward + backward launch list on the 16-bit NHWC arena (savsr_b200/trainplan.py): every trunk convolution "
+                         "forward / dgrad / batched wgrad on tcgen05 with no layout conversion in between, OSA-Conv attention (train-mode BatchNorm) and "
+                         "channel attention forward + backward native, table-driven weight packing, flat Adam + EMA; ATen islands: OSAdapt mask net, SATU + tail + loss")
+        line["plan"] = {"launches_native_estimate": plan.launches, "arena_slots": plan.n_slots, "t_slots": plan.n_tslots, "plan_gb": round(plan.nbytes / 2 ** 30, 2)}
+    else:
+        line["stage"] = ("f1 stage A: 3x3 convs (fwd / dgrad / wgrad, 98 % of the FLOPs) on tcgen05 through savsr_b200.autograd.conv3x3, each call "
+                         "still converting NCHW fp32 <-> the NHWC 16-bit arena; glue ops on ATen")
     if world == 1 and not args.no_extras:
         ref, kind = load_reference(net.state_dict(), dev)
         if ref is not None:
@@ -486,6 +503,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip fp16 / latency / gpu_reference / cfg4 legs (profiling runs)")
     ap.add_argument("--no-cfg4", action="store_true")
+    ap.add_argument("--train-engine", default="native", choices=["native", "autograd"],
+                    help="train_cfg5: native = savsr_b200.trainplan (static launch list, stage B); autograd = savsr_b200.train.Trainer (stage A)")
     ap.add_argument("--no-train-graph", action="store_true", help="train_cfg5: issue the step eagerly instead of replaying one CUDA graph per scale")
     args = ap.parse_args()
 

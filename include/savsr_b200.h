@@ -266,6 +266,46 @@ int savsr_osa_prologue(savsr_ctx* ctx, const savsr_osa_params* convs, int nconvs
                        int npart, int npix, float inv_scale_h, float inv_scale_w, savsr_stream st);
 /* test hook: per sample, scratch + 4*ci + 8 holds the attention vectors [ca(ci) | fa(co) | sa(9) | ka(8)] */
 
+/* Train-mode OSA-Conv prologue (savsr_arch.py:139-163 with ScaleAttention's BatchNorm on BATCH statistics, as nn.BatchNorm2d does
+ * in train mode: biased variance normalises, running statistics move by `momentum` with the unbiased variance) and its backward.
+ * convs[i] as for savsr_osa_prologue (bn_scale / bn_shift unused; scratch must be private to this convolution: it keeps the
+ * forward's intermediate vectors for the backward); batch <= 8.  Besides convs[i].packed (forward operand, [n][s][9][64][64]) the
+ * folded kernels are also written transposed + flipped (data-gradient operand) to extra[i].packed_t as [s][n][9][64][64]. */
+typedef struct savsr_osa_train {
+  const float* bn_weight; const float* bn_bias;   /* [att]                                                        */
+  float* running_mean; float* running_var;        /* [att], updated in place; both NULL = not tracked             */
+  float momentum, eps;
+  float* state;                                   /* savsr_osa_train_state_floats(batch) floats, kept for backward */
+  void* packed_t;
+} savsr_osa_train;
+/* Gradient side of one OSA-Conv.  dwfold: fp32 [batch][64][ci][3][3] weight gradient of the folded kernels (from
+ * savsr_conv_wgrad_batched, per_sample) -- consumed AND zeroed.  d_*: gradients of the parameters, accumulated (+=).
+ * datt: [batch][ci + 64 + 17] scratch, zero on entry, left zero.  dvec: savsr_osa_train_dvec_floats(batch, ci) floats scratch.
+ * dpool: out [batch][ci] = gradient of the pooled means (savsr_grad_prep cadd of the producing convolutions). */
+typedef struct savsr_osa_grads {
+  float* dwfold;
+  float* d_bank;
+  float* d_r0_w; float* d_r0_b; float* d_r2_w; float* d_r2_b;
+  float* d_fc_w; float* d_bn_w; float* d_bn_b;
+  float* d_ch_w; float* d_ch_b; float* d_fl_w; float* d_fl_b; float* d_sp_w; float* d_sp_b; float* d_kn_w; float* d_kn_b;
+  float* datt; float* dvec; float* dpool;
+} savsr_osa_grads;
+size_t savsr_osa_train_state_floats(int batch);
+size_t savsr_osa_train_dvec_floats(int batch, int ci);
+int savsr_osa_prologue_train(savsr_ctx* ctx, const savsr_osa_params* convs, const savsr_osa_train* extra, int nconvs, int batch,
+                             int npart, int npix, float inv_scale_h, float inv_scale_w, savsr_stream st);
+int savsr_osa_fold_backward(savsr_ctx* ctx, const savsr_osa_params* convs, const savsr_osa_train* extra, const savsr_osa_grads* grads,
+                            int nconvs, int batch, savsr_stream st);
+
+/* Backward of the RCAB channel attention dst = x + t * y, y = sigmoid(W2 relu(W1 mean(t) + b1) + b2) (savsr_arch.py:514-524):
+ * savsr_slot_channel_dot: out[n][c] += sum_p a[n,p,c] b[n,p,c] over two arena slots (dy = <dout, t>; out zero on entry);
+ * savsr_ca_backward: from dy (consumed and zeroed) and the saved y: parameter gradients (+=) and dmean [batch][64], the gradient of
+ * the pooled mean; the gradient of t itself is dout * y + dmean / npix (savsr_grad_prep cscale / cadd). */
+int savsr_slot_channel_dot(savsr_ctx* ctx, savsr_arena* arena, int a_slot, int b_slot, float* out, savsr_stream st);
+int savsr_ca_backward(savsr_ctx* ctx, const float* pool, int npart, int npix, int batch, const float* w1, const float* b1, const float* w2,
+                      const float* b2, const float* y, float* dy, float* dw1, float* db1, float* dw2, float* db2, float* dmean,
+                      savsr_stream st);
+
 /* ---- RCAB channel attention (savsr_arch.py:514-524, 547-549) --------------------------------------
  * y = sigmoid(W2 relu(W1 mean(t) + b1) + b2) ; dst = x + t * y        (t, x, dst: arena slots)
  * Two launches: the per-sample channel-scale vector, then the streaming pass.                      */

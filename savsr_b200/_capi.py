@@ -100,6 +100,17 @@ class WgradItem(C.Structure):
                 ("o_off", C.c_int32), ("ksize", C.c_int32), ("per_sample", C.c_int32), ("reserved_", C.c_int32),
                 ("sample_stride", C.c_int64)]
 
+
+class OsaTrain(C.Structure):
+    _fields_ = [("bn_weight", C.c_void_p), ("bn_bias", C.c_void_p), ("running_mean", C.c_void_p), ("running_var", C.c_void_p),
+                ("momentum", C.c_float), ("eps", C.c_float), ("state", C.c_void_p), ("packed_t", C.c_void_p)]
+
+
+class OsaGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "dwfold", "d_bank", "d_r0_w", "d_r0_b", "d_r2_w", "d_r2_b", "d_fc_w", "d_bn_w", "d_bn_b", "d_ch_w", "d_ch_b", "d_fl_w", "d_fl_b",
+        "d_sp_w", "d_sp_b", "d_kn_w", "d_kn_b", "datt", "dvec", "dpool")]
+
 MAX_TRAIN_ENTRIES = 32
 
 
@@ -131,6 +142,12 @@ SIGNATURES = {
     "savsr_pack_conv_chunks": (_I, [_VP, _VP, _I, _I, _VP]),
     "savsr_conv_wgrad_batched": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP, _I, _I, _VP]),
     "savsr_adam_ema": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_long, _F, _F, _F, _F, _VP, _F, _F, _VP]),
+    "savsr_osa_train_state_floats": (_SZ, [_I]),
+    "savsr_osa_train_dvec_floats": (_SZ, [_I, _I]),
+    "savsr_osa_prologue_train": (_I, [_VP, C.POINTER(OsaParams), C.POINTER(OsaTrain), _I, _I, _I, _I, _F, _F, _VP]),
+    "savsr_osa_fold_backward": (_I, [_VP, C.POINTER(OsaParams), C.POINTER(OsaTrain), C.POINTER(OsaGrads), _I, _I, _VP]),
+    "savsr_slot_channel_dot": (_I, [_VP, _VP, _I, _I, _VP, _VP]),
+    "savsr_ca_backward": (_I, [_VP, _VP, _I, _I, _I] + [_VP] * 11 + [_VP]),
     "savsr_pack_frames": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "savsr_osa_prologue": (_I, [_VP, C.POINTER(OsaParams), _I, _I, _I, _I, _F, _F, _VP]),
     "savsr_ca_scale_residual": (_I, [_VP, _VP, _I, _I, _I, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),

@@ -547,6 +547,34 @@ extern "C" int savsr_pack_frames(savsr_ctx* ctx, savsr_arena* arena, const float
   return 0;
 }
 
+namespace savsr {
+// Pooling + the two scale_routing layers (no BatchNorm in them): shared by the inference prologue and the train-mode one (train_attn.cu).
+int osa_prologue_front(savsr_ctx* ctx, const savsr_osa_params* convs, int nconvs, int batch, int npart, int npix, float inv_scale_h,
+                       float inv_scale_w, cudaStream_t st) {
+  OsaLaunch L;
+  memset(&L, 0, sizeof(L));
+  int max_ci = 0;
+  for (int i = 0; i < nconvs; ++i) {
+    L.c[i] = convs[i];
+    max_ci = convs[i].ci > max_ci ? convs[i].ci : max_ci;
+  }
+  L.nconvs = nconvs; L.batch = batch; L.npart = npart; L.npix = npix;
+  L.inv_h = inv_scale_h; L.inv_w = inv_scale_w;
+  L.fmt = ctx->fmt;
+  osa_pool_kernel<<<dim3(max_ci / 64, batch, nconvs), kOsaThreads, 0, st>>>(L);
+  const int lin_split = batch >= 12 ? 3 : (batch >= 4 ? 2 : 1);
+  const size_t lin_smem = static_cast<size_t>((batch + lin_split - 1) / lin_split) * 2 * max_ci * sizeof(float);
+  SAVSR_REQUIRE(lin_smem <= 200 * 1024, "savsr_osa_prologue: batch %d too large for the routing kernel's shared memory", batch);
+  if (lin_smem > 48 * 1024) {
+    if (int rc = ensure_smem_attr(ctx, kAttrOsaLinear, osa_linear_kernel, 200 * 1024)) return rc;
+  }
+  osa_linear_kernel<<<dim3((2 * max_ci + 7) / 8, nconvs, lin_split), 256, lin_smem, st>>>(L, 0);
+  osa_linear_kernel<<<dim3((max_ci + 7) / 8, nconvs, lin_split), 256, lin_smem, st>>>(L, 1);
+  SAVSR_CUDA(cudaGetLastError());
+  return 0;
+}
+}  // namespace savsr
+
 extern "C" int savsr_osa_prologue(savsr_ctx* ctx, const savsr_osa_params* convs, int nconvs, int batch, int npart,
                                   int npix, float inv_scale_h, float inv_scale_w, savsr_stream st_) {
   SAVSR_REQUIRE(ctx && convs, "savsr_osa_prologue: null pointer");
@@ -572,15 +600,7 @@ extern "C" int savsr_osa_prologue(savsr_ctx* ctx, const savsr_osa_params* convs,
   L.nconvs = nconvs; L.batch = batch; L.npart = npart; L.npix = npix;
   L.inv_h = inv_scale_h; L.inv_w = inv_scale_w;
   L.fmt = ctx->fmt;
-  osa_pool_kernel<<<dim3(max_ci / 64, batch, nconvs), kOsaThreads, 0, st>>>(L);
-  const int lin_split = batch >= 12 ? 3 : (batch >= 4 ? 2 : 1);
-  const size_t lin_smem = static_cast<size_t>((batch + lin_split - 1) / lin_split) * 2 * max_ci * sizeof(float);
-  SAVSR_REQUIRE(lin_smem <= 200 * 1024, "savsr_osa_prologue: batch %d too large for the routing kernel's shared memory", batch);
-  if (lin_smem > 48 * 1024) {
-    if (int rc = ensure_smem_attr(ctx, kAttrOsaLinear, osa_linear_kernel, 200 * 1024)) return rc;
-  }
-  osa_linear_kernel<<<dim3((2 * max_ci + 7) / 8, nconvs, lin_split), 256, lin_smem, st>>>(L, 0);
-  osa_linear_kernel<<<dim3((max_ci + 7) / 8, nconvs, lin_split), 256, lin_smem, st>>>(L, 1);
+  if (int rc = osa_prologue_front(ctx, convs, nconvs, batch, npart, npix, inv_scale_h, inv_scale_w, st)) return rc;
   int asm_split = batch >= 16 ? 4 : (batch >= 6 ? 2 : 1);
   while ((batch + asm_split - 1) / asm_split > kAsmMaxSamples) ++asm_split;
   osa_assemble_kernel<<<dim3((64 * max_ci + 255) / 256, nconvs, asm_split), 256, 0, st>>>(L);

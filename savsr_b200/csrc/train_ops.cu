@@ -57,20 +57,27 @@ struct GradPrepLaunch {
   savsr_grad_prep_entry e[kMaxTrainEntries];
 };
 
-__device__ __forceinline__ void store_plane_vec(uint16_t* plane_row, const uint32_t* tile, int seg, int c, int row_shift) {
-  const uint16_t* t16 = reinterpret_cast<const uint16_t*>(tile);
-  uint32_t w[4];
+// tile word address of (pixel row r, channel-pair word w): 33 words per row, and rows >= 32 shifted by 4 banks so that the eight
+// 8-pixel segments a warp reads in the transposed pass fall into distinct banks
+__device__ __forceinline__ int tile_word(int r, int w) { return r * 33 + (r >> 5) * 4 + w; }
+constexpr int kTileWords = 66 * 33 + 12;
+
+// One thread = one channel PAIR x 8 consecutive pixels: eight 32-bit shared loads -> two 16-byte global stores (channels 2cp, 2cp+1).
+__device__ __forceinline__ void store_plane_pair(uint16_t* plane_row0, long plane_elems, const uint32_t* tile, int seg, int cp, int row_shift) {
+  uint32_t w[8];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint32_t lo = t16[(seg * 8 + 2 * j + row_shift) * 66 + c];
-    const uint32_t hi = t16[(seg * 8 + 2 * j + 1 + row_shift) * 66 + c];
-    w[j] = lo | (hi << 16);
-  }
-  *reinterpret_cast<uint4*>(plane_row + seg * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+  for (int j = 0; j < 8; ++j) w[j] = tile[tile_word(seg * 8 + j + row_shift, cp)];
+  uint4 lo, hi;
+  lo.x = (w[0] & 0xffffu) | (w[1] << 16); hi.x = (w[0] >> 16) | (w[1] & 0xffff0000u);
+  lo.y = (w[2] & 0xffffu) | (w[3] << 16); hi.y = (w[2] >> 16) | (w[3] & 0xffff0000u);
+  lo.z = (w[4] & 0xffffu) | (w[5] << 16); hi.z = (w[4] >> 16) | (w[5] & 0xffff0000u);
+  lo.w = (w[6] & 0xffffu) | (w[7] << 16); hi.w = (w[6] >> 16) | (w[7] & 0xffff0000u);
+  *reinterpret_cast<uint4*>(plane_row0 + (2 * cp) * plane_elems + seg * 8) = lo;
+  *reinterpret_cast<uint4*>(plane_row0 + (2 * cp + 1) * plane_elems + seg * 8) = hi;
 }
 
 __global__ void __launch_bounds__(256) grad_prep_kernel(const __grid_constant__ GradPrepLaunch L) {
-  __shared__ uint32_t tile[64 * 33];
+  __shared__ uint32_t tile[kTileWords];
   __shared__ float sdb[64];
   const savsr_grad_prep_entry& e = L.e[blockIdx.z];
   const int y = blockIdx.x, n = blockIdx.y, t = threadIdx.x, fmt = L.fmt;
@@ -116,16 +123,13 @@ __global__ void __launch_bounds__(256) grad_prep_kernel(const __grid_constant__ 
         o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         if (gd) *reinterpret_cast<uint4*>(gd + x * kC + ch8 * 8) = o;
       }
-      uint32_t* tw = tile + pp * 33 + ch8 * 4;
+      uint32_t* tw = tile + tile_word(pp, ch8 * 4);
       tw[0] = o.x; tw[1] = o.y; tw[2] = o.z; tw[3] = o.w;
     }
     __syncthreads();
     if (tplane) {
-#pragma unroll
-      for (int it = 0; it < 2; ++it) {
-        const int idx = it * 256 + t, seg = idx & 7, c = idx >> 3;
-        if (x0 + seg * 8 < L.pitch) store_plane_vec(tplane + c * plane_elems + x0, tile, seg, c, 0);
-      }
+      const int seg = t & 7, cp = t >> 3;
+      if (x0 + seg * 8 < L.pitch) store_plane_pair(tplane + x0, plane_elems, tile, seg, cp, 0);
     }
   }
   if (e.dbias) {
@@ -145,7 +149,7 @@ struct Nchw3Launch {
 
 // copy d (d = 0, 1, 2) holds X[.., x + d - 1], zero where that leaves the row: the tile carries one halo pixel on each side
 __global__ void __launch_bounds__(256) slot_to_nchw3_kernel(const __grid_constant__ Nchw3Launch L) {
-  __shared__ uint32_t tile[66 * 33];
+  __shared__ uint32_t tile[kTileWords];
   const savsr_nchw3& e = L.e[blockIdx.z];
   const int y = blockIdx.x, n = blockIdx.y, t = threadIdx.x;
   const long row_elems = static_cast<long>(L.width) * kC;
@@ -160,18 +164,14 @@ __global__ void __launch_bounds__(256) slot_to_nchw3_kernel(const __grid_constan
       const int pp = idx >> 3, ch8 = idx & 7, x = x0 - 1 + pp;
       uint4 o = make_uint4(0, 0, 0, 0);
       if (x >= 0 && x < L.width) o = *reinterpret_cast<const uint4*>(src + x * kC + ch8 * 8);
-      uint32_t* tw = tile + pp * 33 + ch8 * 4;
+      uint32_t* tw = tile + tile_word(pp, ch8 * 4);
       tw[0] = o.x; tw[1] = o.y; tw[2] = o.z; tw[3] = o.w;
     }
     __syncthreads();
+    const int seg = t & 7, cp = t >> 3;
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-#pragma unroll
-      for (int it = 0; it < 2; ++it) {
-        const int idx = it * 256 + t, seg = idx & 7, c = idx >> 3;
-        if (x0 + seg * 8 < L.pitch) store_plane_vec(tplane + d * tslot_elems + c * plane_elems + x0, tile, seg, c, d);
-      }
-    }
+    for (int d = 0; d < 3; ++d)
+      if (x0 + seg * 8 < L.pitch) store_plane_pair(tplane + d * tslot_elems + x0, plane_elems, tile, seg, cp, d);
   }
 }
 

@@ -164,9 +164,9 @@ def satu(net: _Net, prefix: str, x: Tensor, scale, st_feat: Tensor) -> Tensor:
     b, c, h, w = x.shape
     H, W = get_hw(h, w, s)
     dev = x.device
-    kern = _lrelu(net.conv(prefix + ".kernel_conv.0", st_feat), 0.1).view(b, c, 5, 5, h, w)
+    kern = _lrelu(net.conv(prefix + ".kernel_conv.0", st_feat), 0.1).view(b, c, 25, h * w)                 # channel c * 25 + (u * 5 + v)
     xp = F.pad(x, (2, 2, 2, 2), mode="replicate")
-    sta = sum(xp[:, :, u:u + h, v:v + w] * kern[:, :, u, v] for u in range(5) for v in range(5))          # sta_conv, 297-313
+    sta = (F.unfold(xp, 5).view(b, c, 25, h * w) * kern).sum(2).view(b, c, h, w)                          # sta_conv, 297-313: one im2col + one reduction
     ry = _rel_coord(H, s[0], dev).view(H, 1).expand(H, W)
     rx = _rel_coord(W, s[1], dev).view(1, W).expand(H, W)
     inp = torch.stack([torch.full((H, W), 1.0 / s[1], device=dev), torch.full((H, W), 1.0 / s[0], device=dev), ry, rx], 0)[None]

@@ -214,40 +214,85 @@ class _Spec:
 
 
 class _Osa:
-    """State of one OSA-Conv (savsr_arch.py:139-172) inside a plan: the fold island and its per-sample packed kernels."""
+    """State of one OSA-Conv (savsr_arch.py:139-172) inside a plan: pooled means -> scale_routing -> ScaleAttention (train-mode
+    BatchNorm) -> per-sample folded kernels in both operand orientations, and the buffers of its backward."""
 
     def __init__(self, plan: "TrainPlan", prefix: str, srcs: Sequence[int], pools: Sequence[torch.Tensor]):
         self.prefix, self.srcs, self.pools = prefix, list(srcs), list(pools)
         B, dev = plan.B, plan.device
         self.ci = 64 * len(srcs)
         self.nsrc = len(srcs)
-        self.wfold = torch.zeros(B, 64, self.ci, 3, 3, device=dev)
-        self.dwfold = torch.zeros(B, 64, self.ci, 3, 3, device=dev)
-        self.dpool = torch.zeros(B, self.ci, device=dev)
+        ci = self.ci
+        self.dwfold = torch.zeros(B, 64, ci, 3, 3, device=dev)
+        self.dpool = torch.zeros(B, ci, device=dev)
         self.packed_fwd = torch.zeros(B * self.nsrc * CHUNK3, dtype=torch.uint8, device=dev)      # [n][s][9][64][64]
         self.packed_bwd = torch.zeros(self.nsrc * B * CHUNK3, dtype=torch.uint8, device=dev)      # [s][n][9][64][64]
-        self.chunk_first = len(plan.chunks)
-        for n in range(B):
-            for s in range(self.nsrc):
-                plan._chunk(self.wfold[n], self.packed_fwd.data_ptr() + (n * self.nsrc + s) * CHUNK3, 64, self.ci, 0, s * 64, 3, 0)
-                plan._chunk(self.wfold[n], self.packed_bwd.data_ptr() + (s * B + n) * CHUNK3, 64, self.ci, 0, s * 64, 3, 1)
-        self.chunk_count = len(plan.chunks) - self.chunk_first
         self.fwd_stride = self.nsrc * CHUNK3
-        self.graph_out = None
-        self.leaf = None
-        names = [prefix + ".weight"] + [f"{prefix}.scale_routing.{i}.{k}" for i in (0, 2) for k in ("weight", "bias")]
         a = prefix + ".attention"
+        names = [prefix + ".weight"] + [f"{prefix}.scale_routing.{i}.{k}" for i in (0, 2) for k in ("weight", "bias")]
         names += [a + ".fc.weight", a + ".bn.weight", a + ".bn.bias"] + [f"{a}.{hd}.{k}" for hd in ("channel_fc", "filter_fc", "spatial_fc", "kernel_fc")
                                                                           for k in ("weight", "bias")]
         self.param_names = names
+        if plan.native_attn:
+            P, G, Bf = plan.P, plan.G, plan.net.B
+            lib = plan.lib
+            self.scratch = torch.zeros(B, 5 * ci + 192, device=dev)
+            self.state = torch.zeros(int(lib.savsr_osa_train_state_floats(B)), device=dev)
+            self.datt = torch.zeros(B, ci + 64 + 17, device=dev)
+            self.dvec = torch.zeros(int(lib.savsr_osa_train_dvec_floats(B, ci)), device=dev)
+            o = K.OsaParams()
+            o.ci, o.co, o.att = ci, 64, max(int(ci * 0.0625), 16)
+            o.bank = P[prefix + ".weight"].data_ptr()
+            o.r0_w, o.r0_b = P[prefix + ".scale_routing.0.weight"].data_ptr(), P[prefix + ".scale_routing.0.bias"].data_ptr()
+            o.r2_w, o.r2_b = P[prefix + ".scale_routing.2.weight"].data_ptr(), P[prefix + ".scale_routing.2.bias"].data_ptr()
+            o.fc_w = P[a + ".fc.weight"].data_ptr()
+            o.bn_scale = o.bn_shift = None
+            o.ch_w, o.ch_b = P[a + ".channel_fc.weight"].data_ptr(), P[a + ".channel_fc.bias"].data_ptr()
+            o.fl_w, o.fl_b = P[a + ".filter_fc.weight"].data_ptr(), P[a + ".filter_fc.bias"].data_ptr()
+            o.sp_w, o.sp_b = P[a + ".spatial_fc.weight"].data_ptr(), P[a + ".spatial_fc.bias"].data_ptr()
+            o.kn_w, o.kn_b = P[a + ".kernel_fc.weight"].data_ptr(), P[a + ".kernel_fc.bias"].data_ptr()
+            for i, pp in enumerate(pools):
+                o.pool[i] = pp.data_ptr()
+            o.scratch, o.packed = self.scratch.data_ptr(), self.packed_fwd.data_ptr()
+            t = K.OsaTrain()
+            t.bn_weight, t.bn_bias = P[a + ".bn.weight"].data_ptr(), P[a + ".bn.bias"].data_ptr()
+            t.running_mean, t.running_var = Bf[a + ".bn.running_mean"].data_ptr(), Bf[a + ".bn.running_var"].data_ptr()
+            t.momentum, t.eps = T.BN_MOMENTUM, T.BN_EPS
+            t.state, t.packed_t = self.state.data_ptr(), self.packed_bwd.data_ptr()
+            g = K.OsaGrads()
+            g.dwfold, g.d_bank = self.dwfold.data_ptr(), G[prefix + ".weight"].data_ptr()
+            g.d_r0_w, g.d_r0_b = G[prefix + ".scale_routing.0.weight"].data_ptr(), G[prefix + ".scale_routing.0.bias"].data_ptr()
+            g.d_r2_w, g.d_r2_b = G[prefix + ".scale_routing.2.weight"].data_ptr(), G[prefix + ".scale_routing.2.bias"].data_ptr()
+            g.d_fc_w, g.d_bn_w, g.d_bn_b = G[a + ".fc.weight"].data_ptr(), G[a + ".bn.weight"].data_ptr(), G[a + ".bn.bias"].data_ptr()
+            g.d_ch_w, g.d_ch_b = G[a + ".channel_fc.weight"].data_ptr(), G[a + ".channel_fc.bias"].data_ptr()
+            g.d_fl_w, g.d_fl_b = G[a + ".filter_fc.weight"].data_ptr(), G[a + ".filter_fc.bias"].data_ptr()
+            g.d_sp_w, g.d_sp_b = G[a + ".spatial_fc.weight"].data_ptr(), G[a + ".spatial_fc.bias"].data_ptr()
+            g.d_kn_w, g.d_kn_b = G[a + ".kernel_fc.weight"].data_ptr(), G[a + ".kernel_fc.bias"].data_ptr()
+            g.datt, g.dvec, g.dpool = self.datt.data_ptr(), self.dvec.data_ptr(), self.dpool.data_ptr()
+            self.params, self.extra, self.grads = o, t, g
+            nbt = a + ".bn.num_batches_tracked"
+            if nbt in Bf:
+                plan.nbt_counts[nbt] = plan.nbt_counts.get(nbt, 0) + 1
+        else:
+            self.wfold = torch.zeros(B, 64, ci, 3, 3, device=dev)
+            self.chunk_first = len(plan.chunks)
+            for n in range(B):
+                for s in range(self.nsrc):
+                    plan._chunk(self.wfold[n], self.packed_fwd.data_ptr() + (n * self.nsrc + s) * CHUNK3, 64, ci, 0, s * 64, 3, 0)
+                    plan._chunk(self.wfold[n], self.packed_bwd.data_ptr() + (s * B + n) * CHUNK3, 64, ci, 0, s * 64, 3, 1)
+            self.chunk_count = len(plan.chunks) - self.chunk_first
+            self.graph_out = None
+            self.leaf = None
 
 
 class TrainPlan:
     """Forward + backward launch list of one (batch, h, w, scale).  h and w must be even (the training crops are 64 x 64)."""
 
     def __init__(self, module: torch.nn.Module, flat: FlatParams, weights: TrainWeights, batch: int, h: int, w: int, scale,
-                 precision: str = "bf16"):
+                 precision: str = "bf16", native_attn: bool = True):
         device = flat.device
+        self.native_attn = native_attn and batch <= 8      # False: the attention MLPs run as ATen islands (cross-check / larger batches)
+        self.nbt_counts: Dict[str, int] = {}
         if h % 2 or w % 2 or h < 2 or w < 2:
             raise ValueError(f"TrainPlan needs even LR sizes >= 2 (training crops), got {h}x{w}")
         if precision != "bf16":
@@ -282,6 +327,7 @@ class TrainPlan:
         self.witems: List[K.WgradItem] = []
         self.deferred: List[int] = []         # indices into witems, run by the final batched launch
         self.launches = {"fwd": 0, "bwd": 0}
+        self.kinds: Dict[int, str] = {}
         self.arena: Optional[K.Arena] = None
         self.loss: Optional[torch.Tensor] = None
         with torch.cuda.device(device):
@@ -298,9 +344,11 @@ class TrainPlan:
         self.n_tslots += k
         return t
 
-    def _emit(self, fn: Callable[[int], None], launches: int = 1) -> None:
+    def _emit(self, fn: Callable[[int], None], launches: int = 1, kind: str = "other") -> None:
         self._emit_to.append(fn)
-        self.launches["fwd" if self._emit_to is self.fwd_ops else "bwd"] += launches
+        phase = "fwd" if self._emit_to is self.fwd_ops else "bwd"
+        self.kinds[id(fn)] = f"{phase}:{kind}"
+        self.launches[phase] += launches
 
     def _chunk(self, w: torch.Tensor, dst_ptr: int, co: int, ci: int, o_base: int, i_base: int, ksize: int, transposed: int) -> None:
         ch = K.PackChunk()
@@ -339,7 +387,7 @@ class TrainPlan:
                 e.dst_slot, e.x_slot, e.y_slot, e.alpha, e.beta = d, x, y, a, b
             self._keep.append(arr)
             lib, ctx, n = self.lib, self.ctx.handle, len(part)
-            self._emit(lambda st, arr=arr, n=n: K.check(lib.savsr_slot_axpby(ctx, self._ah(), arr, n, st)))
+            self._emit(lambda st, arr=arr, n=n: K.check(lib.savsr_slot_axpby(ctx, self._ah(), arr, n, st)), kind="axpby")
 
     def _accumulate(self, pairs: Sequence[Tuple[int, int]], scale: float = 1.0) -> None:
         """grad(target) += scale * slot for (target activation, gradient slot) pairs, batched into one launch."""
@@ -358,7 +406,7 @@ class TrainPlan:
             arr = (K.ConvGroup * len(part))(*part)
             self._keep.append(arr)
             lib, ctx, n = self.lib, self.ctx.handle, len(part)
-            self._emit(lambda st, arr=arr, n=n: K.check(lib.savsr_conv(ctx, self._ah(), arr, n, ksize, 64, K.DST_ARENA, K.IMPL_HALO, st)))
+            self._emit(lambda st, arr=arr, n=n: K.check(lib.savsr_conv(ctx, self._ah(), arr, n, ksize, 64, K.DST_ARENA, K.IMPL_HALO, st)), kind=f"conv{ksize}")
 
     @staticmethod
     def _group(src: Sequence[int], dst: int, weight: int, bias: int = 0, act: int = K.ACT_NONE, slope: float = 0.2, res1: int = -1,
@@ -391,12 +439,12 @@ class TrainPlan:
                 e.x_slot, e.t_slot = s, t
             self._keep.append(arr)
             lib, ctx, n = self.lib, self.ctx.handle, len(part)
-            self._emit(lambda st, arr=arr, n=n: K.check(lib.savsr_slot_to_nchw3(ctx, self._ah(), self.tarena.data_ptr(), self.n_tslots, self.pitch, arr, n, st)))
+            self._emit(lambda st, arr=arr, n=n: K.check(lib.savsr_slot_to_nchw3(ctx, self._ah(), self.tarena.data_ptr(), self.n_tslots, self.pitch, arr, n, st)), kind="nchw3")
 
     def _wgrad_launch(self, first: int, count: int) -> None:
         lib, ctx = self.lib, self.ctx.handle
         self._emit(lambda st: K.check(lib.savsr_conv_wgrad_batched(ctx, self.tarena.data_ptr(), self.n_tslots, self.B, self.h, self.w, self.pitch,
-                                                                   self.witems_dev.data_ptr(), first, count, st)))
+                                                                   self.witems_dev.data_ptr(), first, count, st)), kind="wgrad")
 
     # ------------------------------------------------------------------ convolution: forward + backward builder
     def _weight_ptr(self, sp: _Spec) -> Tuple[int, int]:
@@ -453,7 +501,7 @@ class TrainPlan:
             arr = (K.GradPrep * len(part))(*part)
             self._keep.append(arr)
             lib, ctx, n = self.lib, self.ctx.handle, len(part)
-            self._emit(lambda st, arr=arr, n=n: K.check(lib.savsr_grad_prep(ctx, self._ah(), self.tarena.data_ptr(), self.n_tslots, self.pitch, arr, n, st)))
+            self._emit(lambda st, arr=arr, n=n: K.check(lib.savsr_grad_prep(ctx, self._ah(), self.tarena.data_ptr(), self.n_tslots, self.pitch, arr, n, st)), kind="grad_prep")
         # 2. fused residuals (act NONE only): d res1 += g
         self._accumulate([(sp.res1, gslot[sp.dst]) for sp in live if sp.res1 >= 0])
         # 3. data gradients: contributions to one activation from the shared-weight convs of this launch are K-stacked
@@ -549,7 +597,7 @@ class TrainPlan:
             if tgt in self.noreq:
                 continue
             tmp = self._new_slot()
-            self._emit(lambda st, tmp=tmp, fetch=fetch: self._import(tmp, fetch()))
+            self._emit(lambda st, tmp=tmp, fetch=fetch: self._import(tmp, fetch()), kind="import")
             acc.append((tgt, tmp))
         self._accumulate(acc)
 
@@ -572,7 +620,7 @@ class TrainPlan:
                 o.graph_out = T.osa_fold(net, pre, o.leaf, self.scale)
             o.wfold.copy_(o.graph_out.detach())
             K.check(self.lib.savsr_pack_conv_chunks(self.ctx.handle, self.chunks_dev.data_ptr(), o.chunk_first, o.chunk_count, st))
-        self._emit(fwd, launches=30)
+        self._emit(fwd, launches=30, kind="island_osa")
 
     def _osa_backward(self, o: _Osa, producers: Sequence[int]) -> None:
         """After the per-sample weight gradients (dwfold) are in: backward of the fold island; the gradient of the pooled means
@@ -584,7 +632,7 @@ class TrainPlan:
             self._param_grads(o.param_names, grads[1:])
             o.dwfold.zero_()
             o.graph_out = None
-        self._emit(bwd, launches=60)
+        self._emit(bwd, launches=60, kind="island_osa")
         for s, slot in enumerate(producers):
             self.prep_mod.setdefault(slot, {})["cadd"] = (o.dpool.data_ptr() + s * 64 * 4, o.ci, 1.0 / float(self.npix))
 
@@ -594,10 +642,28 @@ class TrainPlan:
         osas = [_Osa(self, p, srcs[d], pools[d]) for d, p in enumerate(prefixes)]
         self._keep.extend(osas)
         # builders run in reverse: the fold backward is registered FIRST so that it runs AFTER the conv backward (which produces dwfold)
-        for d, o in enumerate(osas):
-            self._builders.append(lambda o=o, d=d: self._osa_backward(o, srcs[d]))
-        for o in osas:
-            self._osa_fold(o)
+        if self.native_attn:
+            n = len(osas)
+            pa = (K.OsaParams * n)(*[o.params for o in osas])
+            ta = (K.OsaTrain * n)(*[o.extra for o in osas])
+            ga = (K.OsaGrads * n)(*[o.grads for o in osas])
+            self._keep += [pa, ta, ga]
+            lib, ctx, B, npart, npix = self.lib, self.ctx.handle, self.B, self.npart, self.npix
+            inv_h = float(np.float32(1.0) / np.float32(self.scale[0]))
+            inv_w = float(np.float32(1.0) / np.float32(self.scale[1]))
+
+            def bwd():
+                self._emit(lambda st: K.check(lib.savsr_osa_fold_backward(ctx, pa, ta, ga, n, B, st)), launches=3, kind="osa_bwd")
+                for d, o in enumerate(osas):
+                    for s, slot in enumerate(srcs[d]):
+                        self.prep_mod.setdefault(slot, {})["cadd"] = (o.dpool.data_ptr() + s * 64 * 4, o.ci, 1.0 / float(npix))
+            self._builders.append(bwd)
+            self._emit(lambda st: K.check(lib.savsr_osa_prologue_train(ctx, pa, ta, n, B, npart, npix, inv_h, inv_w, st)), launches=4, kind="osa_fwd")
+        else:
+            for d, o in enumerate(osas):
+                self._builders.append(lambda o=o, d=d: self._osa_backward(o, srcs[d]))
+            for o in osas:
+                self._osa_fold(o)
         self._conv([_Spec(srcs[d], dsts[d], osa=osas[d], act=act) for d in range(len(prefixes))])
 
     def _residual_block(self, prefixes: Sequence[str], xs: Sequence[Sequence[int]]) -> List[List[int]]:
@@ -635,24 +701,31 @@ class TrainPlan:
         w1, b1, w2, b2 = (self.P[n] for n in names)
         lib, ctx, npart = self.lib, self.ctx.handle, self.npart
         self._emit(lambda st: K.check(lib.savsr_ca_scale_residual(ctx, self._ah(), t2, x, out, pool.data_ptr(), npart, w1.data_ptr(), b1.data_ptr(),
-                                                                  w2.data_ptr(), b2.data_ptr(), y.data_ptr(), st)), launches=2)
+                                                                  w2.data_ptr(), b2.data_ptr(), y.data_ptr(), st)), launches=2, kind="ca")
 
         def bwd():
             if out not in self.gmap:
                 return
             g = self.gmap[out]
-            # dy[n][c] = sum_p dout * t2: export-free reduction on the 16-bit slots (small: B x 64 outputs)
-            def run(st):
-                do = self._slot_view(g).float()
-                tt = self._slot_view(t2).float()
-                dy.copy_((do * tt).sum(dim=(1, 2)))
-                mean = (pool.sum(1) / float(self.npix)).detach().requires_grad_(True)
-                with torch.enable_grad():
-                    yy = torch.sigmoid(F.linear(F.relu(F.linear(mean, w1.view(w1.shape[0], -1), b1)), w2.view(w2.shape[0], -1), b2))
-                grads = torch.autograd.grad(yy, [mean, w1, b1, w2, b2], dy)
-                dmean.copy_(grads[0])
-                self._param_grads(names, grads[1:])
-            self._emit(run, launches=25)
+            if self.native_attn:
+                gp = [self.G[n] for n in names]
+                npix = self.npix
+                self._emit(lambda st: K.check(lib.savsr_slot_channel_dot(ctx, self._ah(), g, t2, dy.data_ptr(), st)), kind="ca_bwd")
+                self._emit(lambda st: K.check(lib.savsr_ca_backward(ctx, pool.data_ptr(), npart, npix, self.B, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                                                                    b2.data_ptr(), y.data_ptr(), dy.data_ptr(), gp[0].data_ptr(), gp[1].data_ptr(),
+                                                                    gp[2].data_ptr(), gp[3].data_ptr(), dmean.data_ptr(), st)), kind="ca_bwd")
+            else:
+                def run(st):
+                    do = self._slot_view(g).float()
+                    tt = self._slot_view(t2).float()
+                    dy.copy_((do * tt).sum(dim=(1, 2)))
+                    mean = (pool.sum(1) / float(self.npix)).detach().requires_grad_(True)
+                    with torch.enable_grad():
+                        yy = torch.sigmoid(F.linear(F.relu(F.linear(mean, w1.view(w1.shape[0], -1), b1)), w2.view(w2.shape[0], -1), b2))
+                    grads = torch.autograd.grad(yy, [mean, w1, b1, w2, b2], dy)
+                    dmean.copy_(grads[0])
+                    self._param_grads(names, grads[1:])
+                self._emit(run, launches=25, kind="island_ca")
             self.gmap[t2] = g
             self.shared.add(g)
             self.prep_mod[t2] = {"cscale": (y.data_ptr(), 64), "cadd": (dmean.data_ptr(), 64, 1.0 / float(self.npix))}
@@ -680,7 +753,7 @@ class TrainPlan:
                 hh = leaves[0] + leaves[1] * T.osadapt_mask(net, prefix, leaves[0]) + self.P["gamma"] * leaves[2]
             st8["leaves"], st8["out"] = leaves, hh
             self._import(out, hh.detach())
-        self._emit(fwd, launches=40)
+        self._emit(fwd, launches=40, kind="island_osadapt")
 
         def bwd():
             if out not in self.gmap:
@@ -694,7 +767,7 @@ class TrainPlan:
                 st8["grads"] = grads[:3]
                 self._param_grads(names, grads[3:])
                 st8["out"] = None
-            self._emit(run, launches=80)
+            self._emit(run, launches=80, kind="island_osadapt")
             self._import_grads([(s, (lambda i=i: st8["grads"][i])) for i, s in enumerate((r_slot, a, share))])
         self._builders.append(bwd)
         return out
@@ -714,7 +787,7 @@ class TrainPlan:
         self.x_in = self._buf(B, t, 3, self.h, self.w)
         self.gt = self._buf(B, 3, self.H, self.Wd)
         xin, hh, ww = self.x_in.data_ptr(), self.h, self.w
-        self._emit(lambda st: K.check(lib.savsr_pack_frames(ctx, self._ah(), xin, t, hh, ww, FR, st)))
+        self._emit(lambda st: K.check(lib.savsr_pack_frames(ctx, self._ah(), xin, t, hh, ww, FR, st)), kind="pack_frames")
         dirs = ("f2p_win", "p2f_win")
         n_it = t - 3 + 1
         Fs: List[List[int]] = [[0] * n_it for _ in dirs]
@@ -776,7 +849,7 @@ class TrainPlan:
             grads = torch.autograd.grad(loss, leaves + params, allow_unused=True)
             st8["grads"] = grads[:2]
             self._param_grads(names, grads[2:])
-        self._emit(loss_fwd, launches=400)
+        self._emit(loss_fwd, launches=400, kind="island_satu_loss")
 
         # ---- backward program: builders in reverse order of the forward
         self._emit_to = self.bwd_ops
@@ -822,7 +895,31 @@ class TrainPlan:
                 op(st)
             for op in self.bwd_ops:
                 op(st)
+            if self.nbt_counts:                          # BatchNorms evaluated by native kernels: one counter bump per forward call, as nn.BatchNorm2d does
+                torch._foreach_add_([self.net.B[n] for n in self.nbt_counts], [int(c) for c in self.nbt_counts.values()])
         return self.loss
+
+
+    def run_profiled(self) -> Dict[str, Dict[str, float]]:
+        """Eager forward + backward with a CUDA-event pair around every op: {phase:kind: {"ms", "ops"}} (islands include their ATen launches)."""
+        out: Dict[str, Dict[str, float]] = {}
+        with torch.cuda.device(self.device):
+            self.ctx.set_format(self.fmt)
+            stream = torch.cuda.current_stream(self.device)
+            st = stream.cuda_stream
+            self._keep_step.clear()
+            evs = []
+            for op in self.fwd_ops + self.bwd_ops:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                op(st)
+                e1.record(stream)
+                evs.append((self.kinds.get(id(op), "?"), e0, e1))
+            stream.synchronize()
+        for kind, e0, e1 in evs:
+            d = out.setdefault(kind, dict(ms=0.0, ops=0))
+            d["ms"] += e0.elapsed_time(e1); d["ops"] += 1
+        return out
 
 
 # ====================================================================================================== trainer
@@ -832,8 +929,9 @@ class NativeTrainer:
     (scale, batch shape).  lr / betas: the train YAML's Adam (2e-4, 0.9 / 0.99); EMA 0.999 (base_model.py:75-82)."""
 
     def __init__(self, net: torch.nn.Module, lr: float = 2e-4, betas=(0.9, 0.99), eps: float = 1e-8, ema_decay: float = 0.999,
-                 use_graph: bool = True, world_size: int = 1):
+                 use_graph: bool = True, world_size: int = 1, native_attn: bool = True):
         self.net = net
+        self.native_attn = native_attn
         self.flat = FlatParams(net, ema=ema_decay > 0)
         dev = self.flat.device
         self.ctx = context(_dev_index(dev))
@@ -853,7 +951,7 @@ class NativeTrainer:
         b, t, c, h, w = lq.shape
         key = (tuple(normalize_scale(scale)), b, h, w)
         if key not in self.plans:
-            self.plans[key] = TrainPlan(self.net, self.flat, self.weights, b, h, w, scale)
+            self.plans[key] = TrainPlan(self.net, self.flat, self.weights, b, h, w, scale, native_attn=self.native_attn)
         return self.plans[key]
 
     def _fwd_bwd(self, plan: TrainPlan) -> torch.Tensor:

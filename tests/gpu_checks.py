@@ -650,7 +650,7 @@ def check_train_step(b=2, h=16, w=20, scale=(2, 2), seed=0, steps=3):
     return info
 
 
-def check_trainplan(b=2, h=16, w=20, scale=(2, 2), seed=0, tol_worst=0.25, tol_cos=0.995, steps=0, graph=False):
+def check_trainplan(b=2, h=16, w=20, scale=(2, 2), seed=0, tol_worst=0.10, tol_cos=0.999, steps=0, graph=False, native_attn=True):
     """Row f1 stage B: the NATIVE training step (savsr_b200.trainplan: arena-resident forward / dgrad / batched wgrad, table-driven
     weight packing) against fp32 CPU autograd through the oracle: loss, per-parameter gradient error
     |g - r| / max(|r|, 1 % of the largest tensor gradient), and the cosine of the whole flat gradient."""
@@ -673,7 +673,7 @@ def check_trainplan(b=2, h=16, w=20, scale=(2, 2), seed=0, tol_worst=0.25, tol_c
         ref_loss.backward()
     finally:
         O.BN_TRAIN = False
-    tr = TP.NativeTrainer(net, use_graph=graph)
+    tr = TP.NativeTrainer(net, use_graph=graph, native_attn=native_attn)
     plan = tr.plan_for(x.to(DEV), scale)
     plan.x_in.copy_(x.to(DEV)); plan.gt.copy_(gt.to(DEV))
     loss = tr._fwd_bwd(plan)
@@ -681,13 +681,15 @@ def check_trainplan(b=2, h=16, w=20, scale=(2, 2), seed=0, tol_worst=0.25, tol_c
     params = dict(net.named_parameters())
     keys = [k for k in params if sd_cpu[k].grad is not None]
     rep = _grad_report(params, sd_cpu, keys)
-    gflat = torch.cat([params[k].grad.flatten().cpu() for k in keys])
-    rflat = torch.cat([sd_cpu[k].grad.flatten() for k in keys])
+    gflat = torch.cat([params[k].grad.flatten().cpu() for k in keys]).double()
+    rflat = torch.cat([sd_cpu[k].grad.flatten() for k in keys]).double()
     cos = float(torch.dot(gflat, rflat) / (gflat.norm() * rflat.norm()))
     worst = sorted(rep.items(), key=lambda kv: -kv[1])[:5]
-    info = dict(loss=float(loss), ref_loss=float(ref_loss), cos=cos, grad_norm=float(gflat.norm()), ref_grad_norm=float(rflat.norm()),
+    nbt = int(net.f2p_win.blocks[1].osconv.attention.bn.num_batches_tracked) - int(sd["f2p_win.blocks.1.osconv.attention.bn.num_batches_tracked"])
+    assert nbt == 5, nbt                      # the shared l1 BatchNorm ran once per propagation iteration, in train mode
+    info = dict(loss=float(loss), ref_loss=float(ref_loss.detach()), cos=cos, grad_norm=float(gflat.norm()), ref_grad_norm=float(rflat.norm()),
                 worst=worst, median=float(np.median(list(rep.values()))), launches=dict(plan.launches), slots=plan.n_slots, tslots=plan.n_tslots)
-    assert abs(float(loss) - float(ref_loss)) < 2e-3 * max(1.0, abs(float(ref_loss))), info
+    assert abs(float(loss) - float(ref_loss.detach())) < 2e-3 * max(1.0, abs(float(ref_loss.detach()))), info
     assert np.isfinite(cos) and cos > tol_cos, info
     assert all(np.isfinite(v) and v < tol_worst for v in rep.values()), info
     if steps:

@@ -224,3 +224,22 @@ def test_module_api_errors(G):
     net.set_scale(2)
     y = net(torch.rand(1, 7, 3, 8, 10, device="cuda"))
     assert tuple(y.shape) == (1, 3, 16, 20) and y.dtype == torch.float32
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", [dict(), dict(scale=(1.5, 4), seed=1, b=3, h=12, w=24), dict(native_attn=False)],
+                         ids=["x2", "x1.5x4_b3", "aten_attention_islands"])
+def test_native_training_plan_gradients_match_the_oracle(G, kw):
+    """Row f1 stage B: the static forward + backward launch list (savsr_b200.trainplan) against fp32 CPU autograd through the oracle on
+    the WHOLE net: loss to 2e-3, every parameter tensor's gradient within 10 % of max(|r|, 1 % of the largest tensor gradient)
+    (measured worst 4.5 %, median 0.07 %), cosine of the flat gradient > 0.999.  Gradients are stored in bf16 between layers."""
+    info = G.check_trainplan(**kw)
+    print(info)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "cuda_graph"])
+def test_native_training_steps_reduce_the_loss(G, graph):
+    """Pack -> forward -> backward -> Adam + EMA for a few steps on a fixed batch, eagerly and as replayed CUDA graphs."""
+    info = G.check_trainplan(steps=4, graph=graph)
+    print(info["losses"])

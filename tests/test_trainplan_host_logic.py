@@ -46,8 +46,11 @@ def test_step_runs_and_census(recorded):
     assert names.count("savsr_pack_frames") == 1
     assert names.count("savsr_adam_ema") == 1
     assert names.count("savsr_ca_scale_residual") == 32
-    # one table-driven pack of the shared filters + one per OSA-Conv (per-sample folded kernels): l1 5 x 3 x 2 dirs, l2 2, adapt 4
-    assert names.count("savsr_pack_conv_chunks") == 1 + 30 + 2 + 4
+    # ONE table-driven pack of the shared filters; the per-sample folded kernels of OSA-Conv are written packed by its prologue
+    assert names.count("savsr_pack_conv_chunks") == 1
+    # train-mode OSA prologue / fold backward: l1 5 iterations x 3 blocks (both directions per launch), l2 2, adapt 4
+    assert names.count("savsr_osa_prologue_train") == 15 + 2 + 4 and names.count("savsr_osa_fold_backward") == 15 + 2 + 4
+    assert names.count("savsr_slot_channel_dot") == 32 and names.count("savsr_ca_backward") == 32
     # weight gradients: one inline launch per OSA-Conv launch (l1: both directions share one) + the final batched launch
     assert names.count("savsr_conv_wgrad_batched") == 15 + 2 + 4 + 1
     # forward convolutions as in the inference plan, minus the N = 16 mask convs (mask net = ATen island here)
