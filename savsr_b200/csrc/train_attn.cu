@@ -14,6 +14,7 @@
 namespace savsr {
 
 constexpr int kMaxOsaT = 4;
+static_assert(sizeof(savsr_osa_train) == 56 && sizeof(savsr_osa_grads) == 160, "C ABI struct layout changed: update savsr_b200/_capi.py");
 constexpr int kMaxBatchT = 8;      // samples per launch of the train-mode attention kernels
 __host__ __device__ inline int osat_scratch_stride(int ci) { return 5 * ci + 192; }
 __host__ __device__ inline int osat_off_h1(int ci) { return ci + 8; }

@@ -17,6 +17,9 @@
 namespace savsr {
 
 constexpr int kMaxTrainEntries = 32;
+// layouts the ctypes binding (savsr_b200/_capi.py) mirrors
+static_assert(sizeof(savsr_axpby) == 20 && sizeof(savsr_nchw3) == 8 && sizeof(savsr_grad_prep_entry) == 72 && sizeof(savsr_pack_chunk) == 40 &&
+              sizeof(savsr_wgrad_item) == 48, "C ABI struct layout changed: update savsr_b200/_capi.py and tests/test_boundary_cpu.py");
 
 // ------------------------------------------------------------------------------------------------ slot axpby
 struct AxpbyLaunch {

@@ -48,17 +48,33 @@ def gather_windows(clip: torch.Tensor, frames: Sequence[int], num_frames: int = 
     return clip[idx.reshape(-1)].reshape(len(frames), num_frames, *clip.shape[1:])
 
 
+def batch_schedule(n: int, batch) -> list:
+    """[(start, stop), ...] covering n frames.  `batch` is an int (equal batches, the last one ragged) or a sequence of batch
+    sizes used in order (the last entry repeats): e.g. (26, 8) runs one large forward and a short final one, so that the
+    device-to-host copy that cannot overlap anything -- the last batch's -- is small."""
+    sizes = [int(batch)] if isinstance(batch, int) else [int(b) for b in batch]
+    if not sizes or min(sizes) < 1:
+        raise ValueError(f"batch sizes must be positive, got {batch!r}")
+    out, i, k = [], 0, 0
+    while i < n:
+        b = sizes[min(k, len(sizes) - 1)]
+        out.append((i, min(i + b, n)))
+        i += b
+        k += 1
+    return out
+
+
 def infer_clip(net: Callable[[torch.Tensor], torch.Tensor], clip: torch.Tensor, frames: Optional[Sequence[int]] = None,
-               batch: int = 1, num_frames: int = 7, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Run `net` on the windows of `frames` (default: all), `batch` windows per forward.
+               batch=1, num_frames: int = 7, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Run `net` on the windows of `frames` (default: all), `batch` windows per forward (int or a schedule, see batch_schedule).
     Returns [len(frames), 3, H, W].  The last, ragged batch is run at its own size.
     If `out` (e.g. a pinned host tensor) is given, each batch is copied into it on a side stream while the next
     batch computes, and `out` is returned once all copies are enqueued behind the current stream."""
     frames = list(range(clip.shape[0])) if frames is None else list(frames)
     copy_stream = torch.cuda.Stream(clip.device) if (out is not None and clip.is_cuda) else None
     outs = []
-    for i in range(0, len(frames), batch):
-        chunk = frames[i:i + batch]
+    for i, j in batch_schedule(len(frames), batch):
+        chunk = frames[i:j]
         y = net(gather_windows(clip, chunk, num_frames))
         if out is None:
             outs.append(y)

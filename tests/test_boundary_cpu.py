@@ -64,12 +64,17 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/savsr_b200.h but not exported"
     assert declared == set(_capi.SIGNATURES), declared ^ set(_capi.SIGNATURES)
-    assert lib.savsr_abi_version() == _capi.ABI_VERSION == 3
+    assert lib.savsr_abi_version() == _capi.ABI_VERSION == 4
 
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_capi.ConvGroup) == 104 and _capi.ConvGroup.weight.offset == 48 and _capi.ConvGroup.src_channels.offset == 96
     assert _capi.OsaParams.pool.offset == 16 + 16 * 8 and ctypes.sizeof(_capi.SatuWeights) == 96
+    # training entry points (train_ops.cu / train_attn.cu carry the matching static_asserts on the C side)
+    assert ctypes.sizeof(_capi.Axpby) == 20 and ctypes.sizeof(_capi.Nchw3) == 8
+    assert ctypes.sizeof(_capi.GradPrep) == 72 and _capi.GradPrep.cscale.offset == 24 and _capi.GradPrep.dbias.offset == 64
+    assert ctypes.sizeof(_capi.PackChunk) == 40 and ctypes.sizeof(_capi.WgradItem) == 48 and _capi.WgradItem.sample_stride.offset == 40
+    assert ctypes.sizeof(_capi.OsaTrain) == 56 and _capi.OsaTrain.state.offset == 40 and ctypes.sizeof(_capi.OsaGrads) == 160
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
