@@ -161,37 +161,37 @@ __global__ void __launch_bounds__(256) osa_assemble_train_kernel(const __grid_co
 __global__ void __launch_bounds__(128) osa_unfold_bwd_kernel(const __grid_constant__ OsaTrainLaunch L) {
   const savsr_osa_params& c = L.c[blockIdx.y];
   const savsr_osa_grads& g = L.g[blockIdx.y];
-  extern __shared__ float sm[];                       // att [B][nout] | datt [B][nout]
+  extern __shared__ float sm[];                       // att [B][nout] | part [4 warps][B][18]
   if (blockIdx.x * blockDim.x >= c.co * c.ci) return;
   const int B = L.batch;
   const int nout = c.ci + c.co + 9 + 8;
   const int stride = osat_scratch_stride(c.ci);
   float* att_s = sm;
-  float* datt_s = sm + B * nout;
+  float* part = sm + B * nout;
   for (int r = threadIdx.x; r < B * nout; r += blockDim.x) {
     const int n = r / nout, j = r - n * nout;
     att_s[r] = c.scratch[static_cast<long>(n) * stride + osat_off_att(c.ci) + j];
-    datt_s[r] = 0.f;
   }
   __syncthreads();
+  // a warp = 32 consecutive input channels of ONE output channel (ci is a multiple of 64): d fa reduces inside the warp, d ka / d sa
+  // across the whole block, d ca is per thread.  No shared-memory float atomics (they compile to CAS loops).
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = idx < c.co * c.ci;
-  const int i = active ? idx % c.ci : 0, o = active ? idx / c.ci : 0;
+  const int i = idx % c.ci, o = idx / c.ci;
   const long per_k = static_cast<long>(c.co) * c.ci * 9;
   const long pos = (static_cast<long>(o) * c.ci + i) * 9;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float bk[8][9];                                      // the 72 bank values of this filter position: all loads in flight at once
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
 #pragma unroll
-    for (int u = 0; u < 9; ++u) bk[k][u] = active ? __ldg(c.bank + k * per_k + pos + u) : 0.f;
+    for (int u = 0; u < 9; ++u) bk[k][u] = __ldg(c.bank + k * per_k + pos + u);
   }
   for (int b0 = 0; b0 < B; b0 += 4) {
     float t[4][9], fc[4];
 #pragma unroll
     for (int bb = 0; bb < 4; ++bb) {
       const int b = b0 + bb;
-      const bool ok = active && b < B;
+      const bool ok = b < B;
       float* src = g.dwfold + b * per_k + pos;
 #pragma unroll
       for (int u = 0; u < 9; ++u) { t[bb][u] = ok ? src[u] : 0.f; if (ok) src[u] = 0.f; }
@@ -217,13 +217,11 @@ __global__ void __launch_bounds__(128) osa_unfold_bwd_kernel(const __grid_consta
         }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) dka += __shfl_xor_sync(0xffffffffu, dka, off);
-        if (lane == 0) atomicAdd(datt_s + b * nout + c.ci + c.co + 9 + k, dka);
+        if (lane == 0) part[(warp * B + b) * 18 + 9 + k] = dka;
       }
-      if (active) {
-        float* dst = g.d_bank + k * per_k + pos;
+      float* dst = g.d_bank + k * per_k + pos;
 #pragma unroll
-        for (int u = 0; u < 9; ++u) dst[u] += db[u];
-      }
+      for (int u = 0; u < 9; ++u) dst[u] += db[u];
     }
 #pragma unroll
     for (int bb = 0; bb < 4; ++bb) {
@@ -242,17 +240,22 @@ __global__ void __launch_bounds__(128) osa_unfold_bwd_kernel(const __grid_consta
         float ds = fa * ca * P;
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, off);
-        if (lane == 0) atomicAdd(datt_s + b * nout + c.ci + c.co + u, ds);
+        if (lane == 0) part[(warp * B + b) * 18 + u] = ds;
       }
-      if (active) {
-        atomicAdd(datt_s + b * nout + c.ci + o, ca * sp);      // d fa[o]
-        atomicAdd(datt_s + b * nout + i, fa * sp);             // d ca[i]
-      }
+      atomicAdd(g.datt + b * nout + i, fa * sp);                // d ca[i]: one global reduction per thread
+      float dfa = ca * sp;                                      // d fa[o]: the warp shares o
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) dfa += __shfl_xor_sync(0xffffffffu, dfa, off);
+      if (lane == 0) atomicAdd(g.datt + b * nout + c.ci + o, dfa);
     }
   }
   __syncthreads();
-  for (int r = threadIdx.x; r < B * nout; r += blockDim.x)
-    if (datt_s[r] != 0.f) atomicAdd(g.datt + r, datt_s[r]);
+  for (int r = threadIdx.x; r < B * 17; r += blockDim.x) {      // d sa (9) and d ka (8) of the block
+    const int b = r / 17, q = r - b * 17;
+    float v = 0.f;
+    for (int w = 0; w < 4; ++w) v += part[(w * B + b) * 18 + q];
+    atomicAdd(g.datt + b * nout + c.ci + c.co + q, v);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ backward 2: vectors
@@ -501,27 +504,33 @@ struct CaBwdParams {
   float* dmean;         // [B][64] out
   int batch;
 };
-// one CTA, 256 threads; thread = (sample n = tid / 64, channel c = tid % 64) for up to four samples at a time
-__global__ void __launch_bounds__(256) ca_backward_kernel(const CaBwdParams p) {
+// one CTA, 1024 threads: the pooled partial sums are reduced by 16 ranges x 64 channels with all loads in flight, the rest is tiny
+__global__ void __launch_bounds__(1024) ca_backward_kernel(const CaBwdParams p) {
+  __shared__ float part[16][kMaxBatchT][64];
   __shared__ float mean[kMaxBatchT][64], ds[kMaxBatchT][64], hid[kMaxBatchT][4], dhid[kMaxBatchT][4];
   const int tid = threadIdx.x;
   const int B = p.batch;
-  __shared__ float part[4][kMaxBatchT][64];
   {
-    const int c = tid & 63, q4 = tid >> 6;                     // 4 partial ranges x 64 channels
+    const int c = tid & 63, q16 = tid >> 6;
     for (int n = 0; n < B; ++n) {
       const float* src = p.pool + static_cast<long>(n) * p.npart * kC;
-      float a0 = 0.f, a1 = 0.f;
-      int q = q4;
-      for (; q + 4 < p.npart; q += 8) { a0 += src[q * kC + c]; a1 += src[(q + 4) * kC + c]; }
-      if (q < p.npart) a0 += src[q * kC + c];
-      part[q4][n][c] = a0 + a1;
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
+      int q = q16;
+      for (; q + 48 < p.npart; q += 64) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] += src[(q + 16 * j) * kC + c];
+      }
+      for (; q < p.npart; q += 16) a[0] += src[q * kC + c];
+      part[q16][n][c] = (a[0] + a[1]) + (a[2] + a[3]);
     }
   }
   __syncthreads();
-  for (int r = tid; r < B * 64; r += 256) {
+  for (int r = tid; r < B * 64; r += blockDim.x) {
     const int n = r >> 6, c = r & 63;
-    mean[n][c] = (part[0][n][c] + part[1][n][c] + part[2][n][c] + part[3][n][c]) * p.inv_npix;
+    float m = 0.f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) m += part[q][n][c];
+    mean[n][c] = m * p.inv_npix;
     const float yy = p.y[r];
     ds[n][c] = p.dy[r] * yy * (1.f - yy);
     p.dy[r] = 0.f;
@@ -535,7 +544,7 @@ __global__ void __launch_bounds__(256) ca_backward_kernel(const CaBwdParams p) {
     dhid[n][k] = a > 0.f ? d : 0.f;
   }
   __syncthreads();
-  {                                                            // weight gradients: 256 threads = w2 [64][4] and w1 [4][64]
+  if (tid < 256) {                                             // weight gradients: 256 threads = w2 [64][4] and w1 [4][64]
     const int c = tid >> 2, k = tid & 3;
     float a2 = 0.f, a1 = 0.f;
     for (int n = 0; n < B; ++n) { a2 += ds[n][c] * hid[n][k]; a1 += dhid[n][k] * mean[n][c]; }
@@ -544,7 +553,7 @@ __global__ void __launch_bounds__(256) ca_backward_kernel(const CaBwdParams p) {
     if (tid < 64) { float s = 0.f; for (int n = 0; n < B; ++n) s += ds[n][tid]; p.db2[tid] += s; }
     if (tid < 4) { float s = 0.f; for (int n = 0; n < B; ++n) s += dhid[n][tid]; p.db1[tid] += s; }
   }
-  for (int r = tid; r < B * 64; r += 256) {
+  for (int r = tid; r < B * 64; r += blockDim.x) {
     const int n = r >> 6, c = r & 63;
     float a = 0.f;
 #pragma unroll
@@ -616,7 +625,7 @@ extern "C" int savsr_osa_fold_backward(savsr_ctx* ctx, const savsr_osa_params* c
   int max_ci = 0;
   for (int i = 0; i < nconvs; ++i) max_ci = convs[i].ci > max_ci ? convs[i].ci : max_ci;
   const int nout = max_ci + 64 + 17;
-  const size_t smem1 = static_cast<size_t>(2) * batch * nout * sizeof(float);
+  const size_t smem1 = (static_cast<size_t>(batch) * nout + 4 * static_cast<size_t>(batch) * 18) * sizeof(float);
   SAVSR_REQUIRE(smem1 <= 48 * 1024, "savsr_osa_fold_backward: batch %d too large", batch);
   osa_unfold_bwd_kernel<<<dim3((64 * max_ci + 127) / 128, nconvs), 128, smem1, st>>>(L);
   const size_t smem2 = (static_cast<size_t>(batch) * nout + batch * 32 + 3 * static_cast<size_t>(batch) * max_ci + 16) * sizeof(float);
@@ -653,7 +662,7 @@ extern "C" int savsr_ca_backward(savsr_ctx* ctx, const float* pool, int npart, i
   CaBwdParams p;
   p.pool = pool; p.npart = npart; p.inv_npix = 1.f / static_cast<float>(npix);
   p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.dy = dy; p.y = y; p.dw1 = dw1; p.db1 = db1; p.dw2 = dw2; p.db2 = db2; p.dmean = dmean; p.batch = batch;
-  ca_backward_kernel<<<1, 256, 0, static_cast<cudaStream_t>(st)>>>(p);
+  ca_backward_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(st)>>>(p);
   SAVSR_CUDA(cudaGetLastError());
   return 0;
 }

@@ -81,10 +81,8 @@ __device__ __forceinline__ void store_plane_pair(uint16_t* plane_row0, long plan
 
 __global__ void __launch_bounds__(256) grad_prep_kernel(const __grid_constant__ GradPrepLaunch L) {
   __shared__ uint32_t tile[kTileWords];
-  __shared__ float sdb[64];
   const savsr_grad_prep_entry& e = L.e[blockIdx.z];
   const int y = blockIdx.x, n = blockIdx.y, t = threadIdx.x, fmt = L.fmt;
-  if (t < 64) sdb[t] = 0.f;
   const long row_elems = static_cast<long>(L.width) * kC;
   const long slot_elems = static_cast<long>(L.batch) * L.height * row_elems;
   const long row_off = (static_cast<long>(n) * L.height + y) * row_elems;
@@ -136,10 +134,26 @@ __global__ void __launch_bounds__(256) grad_prep_kernel(const __grid_constant__ 
     }
   }
   if (e.dbias) {
+    // lanes l, l+8, l+16, l+24 of a warp hold the same eight channels: two shuffle steps, then one row of partials per warp
+    // (shared-memory float atomics compile to CAS loops: measured as the top stall of the first version of this kernel)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&sdb[ch8 * 8 + j], db[j]);
+    for (int j = 0; j < 8; ++j) {
+      db[j] += __shfl_xor_sync(0xffffffffu, db[j], 8);
+      db[j] += __shfl_xor_sync(0xffffffffu, db[j], 16);
+    }
+    __syncthreads();                                   // the tile is free: reuse it as [8 warps][64 channels]
+    float* part = reinterpret_cast<float*>(tile);
+    if ((t & 31) < 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) part[(t >> 5) * 64 + ch8 * 8 + j] = db[j];
+    }
     __syncthreads();
-    if (t < 64) atomicAdd(e.dbias + t, sdb[t]);
+    if (t < 64) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += part[w * 64 + t];
+      atomicAdd(e.dbias + t, v);
+    }
   }
 }
 

@@ -839,14 +839,19 @@ class TrainPlan:
 
         def loss_fwd(st):
             leaves = [self._export(s).requires_grad_(True) for s in (TR, A)]
-            with torch.enable_grad():
-                sr = net.conv("tail", T.satu(net, "upsample", leaves[0], self.scale, leaves[1]))
-                sr = sr + F.interpolate(self.x_in[:, t // 2], size=(self.H, self.Wd), mode="bilinear", align_corners=False)
-                loss = T.charbonnier(sr, self.gt)
-            self.sr = sr.detach()
-            self.loss = loss.detach()
-            params = [self.P[n] for n in names]
-            grads = torch.autograd.grad(loss, leaves + params, allow_unused=True)
+            tf32 = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = True        # the expert mixes and their weight gradients (K = B*H*W) on tensor cores, like the convs around them
+            try:
+                with torch.enable_grad():
+                    sr = net.conv("tail", T.satu(net, "upsample", leaves[0], self.scale, leaves[1]))
+                    sr = sr + F.interpolate(self.x_in[:, t // 2], size=(self.H, self.Wd), mode="bilinear", align_corners=False)
+                    loss = T.charbonnier(sr, self.gt)
+                self.sr = sr.detach()
+                self.loss = loss.detach()
+                params = [self.P[n] for n in names]
+                grads = torch.autograd.grad(loss, leaves + params, allow_unused=True)
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = tf32
             st8["grads"] = grads[:2]
             self._param_grads(names, grads[2:])
         self._emit(loss_fwd, launches=400, kind="island_satu_loss")
