@@ -225,10 +225,15 @@ int savsr_pack_conv_chunks(savsr_ctx* ctx, const savsr_pack_chunk* chunks_dev, i
  * x_tslot: first of the source's three shifted T-slots (savsr_slot_to_nchw3); g_tslot: the T-slot savsr_grad_prep wrote.
  * ksize 3: dw is [..][ci_total][3][3]; ksize 1: [..][ci_total] (centre tap).  per_sample: dw advances sample_stride floats per
  * sample (the folded kernels of OSA-Conv).  dw is accumulated with atomics: zero it first. */
+enum savsr_wgrad_layout {
+  SAVSR_WGRAD_OIHW = 0, /* dw[o][i][ky][kx]: the parameter's own layout (scalar atomics)                                     */
+  SAVSR_WGRAD_TIO = 1   /* dw[tap][i][64]: output channels contiguous, 16-byte vector atomics (4x fewer reductions); used for the
+                           per-sample gradients of OSA-Conv's folded kernels, whose only reader is savsr_osa_fold_backward; ksize 3, co 64 */
+};
 typedef struct savsr_wgrad_item {
   int32_t x_tslot, g_tslot;
   float* dw;
-  int32_t ci_total, ci_off, o_off, ksize, per_sample, reserved_;
+  int32_t ci_total, ci_off, o_off, ksize, per_sample, layout;
   int64_t sample_stride;
 } savsr_wgrad_item;
 int savsr_conv_wgrad_batched(savsr_ctx* ctx, const void* tbase, int ntslots, int batch, int height, int width, int pitch,

