@@ -311,6 +311,34 @@ int savsr_ca_backward(savsr_ctx* ctx, const float* pool, int npart, int npix, in
                       const float* b2, const float* y, float* dy, float* dw1, float* db1, float* dw2, float* db2, float* dmean,
                       savsr_stream st);
 
+/* Train-mode OSAdapt mask net + combination (savsr_arch.py:186-214, 727-732), everything after the 64 -> 16 convolution:
+ *   m0 (from savsr_conv, N = 16, no activation) -> BN1 -> ReLU -> AvgPool2 -> conv4 -> BN5 -> ReLU -> conv7 -> BN8 -> ReLU -> bilinear x2
+ *   -> conv11 -> BN12 -> sigmoid = mask ;   out = R + a * mask + gamma * share           (a = OSA-Conv(R); R, a, share, out: arena slots)
+ * BatchNorm on batch statistics (indices 0..3 = BN1, BN5, BN8, BN12), running statistics updated in place when given.  All maps are
+ * fp32 channel-last: m0, t5 [batch][H*W][16]; t2, m4, t3, m7 [batch][(H/2)*(W/2)][16]; m11, mask [batch][H*W]; they stay alive for the
+ * backward.  stat: 4 x 32 floats (mean | rstd per layer); sums: 64 doubles of scratch, zero on entry, left zero; coef: 4 x 48 floats.
+ * savsr_mask_backward_train: from the gradient of `out` (dh_slot): da_slot = dh * mask, gshare_slot = gamma * dh (the caller accumulates
+ * them and dh itself into the gradients of a, share and R), the gradients of every parameter of the mask net and of gamma (+=), and the
+ * gradient of m0 as the first 16 channels of arena slot dm0_slot (channels 16..63 are not written: keep them zero) -- the operand of the
+ * tensor-core data / weight gradient of the 64 -> 16 convolution.  dmask .. dt2: scratch of the sizes of mask, m11, t2 (x5). */
+typedef struct savsr_mask_train {
+  const float *w4, *b4, *w7, *b7, *w11, *b11;
+  const float* bn_w[4]; const float* bn_b[4];
+  float* bn_rm[4]; float* bn_rv[4];
+  const float* gamma;
+  float momentum, eps;
+  float *m0, *t2, *m4, *t3, *m7, *t5, *m11, *mask;
+  float* stat; double* sums; float* coef;
+  float *d_w4, *d_b4, *d_w7, *d_b7, *d_w11, *d_b11;
+  float* d_bn_w[4]; float* d_bn_b[4];
+  float* d_gamma;
+  float *dmask, *dm11, *dt4, *dm7, *dt3, *dm4, *dt2;
+} savsr_mask_train;
+int savsr_mask_forward_train(savsr_ctx* ctx, savsr_arena* arena, const savsr_mask_train* m, int r_slot, int a_slot, int share_slot, int out_slot,
+                             savsr_stream st);
+int savsr_mask_backward_train(savsr_ctx* ctx, savsr_arena* arena, const savsr_mask_train* m, int dh_slot, int a_slot, int share_slot, int da_slot,
+                              int gshare_slot, int dm0_slot, savsr_stream st);
+
 /* ---- RCAB channel attention (savsr_arch.py:514-524, 547-549) --------------------------------------
  * y = sigmoid(W2 relu(W1 mean(t) + b1) + b2) ; dst = x + t * y        (t, x, dst: arena slots)
  * Two launches: the per-sample channel-scale vector, then the streaming pass.                      */

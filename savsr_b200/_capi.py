@@ -112,6 +112,16 @@ class OsaGrads(C.Structure):
         "dwfold", "d_bank", "d_r0_w", "d_r0_b", "d_r2_w", "d_r2_b", "d_fc_w", "d_bn_w", "d_bn_b", "d_ch_w", "d_ch_b", "d_fl_w", "d_fl_b",
         "d_sp_w", "d_sp_b", "d_kn_w", "d_kn_b", "datt", "dvec", "dpool")]
 
+
+class MaskTrain(C.Structure):
+    _fields_ = ([(n, C.c_void_p) for n in ("w4", "b4", "w7", "b7", "w11", "b11")]
+                + [("bn_w", C.c_void_p * 4), ("bn_b", C.c_void_p * 4), ("bn_rm", C.c_void_p * 4), ("bn_rv", C.c_void_p * 4),
+                   ("gamma", C.c_void_p), ("momentum", C.c_float), ("eps", C.c_float)]
+                + [(n, C.c_void_p) for n in ("m0", "t2", "m4", "t3", "m7", "t5", "m11", "mask", "stat", "sums", "coef",
+                                             "d_w4", "d_b4", "d_w7", "d_b7", "d_w11", "d_b11")]
+                + [("d_bn_w", C.c_void_p * 4), ("d_bn_b", C.c_void_p * 4), ("d_gamma", C.c_void_p)]
+                + [(n, C.c_void_p) for n in ("dmask", "dm11", "dt4", "dm7", "dt3", "dm4", "dt2")])
+
 MAX_TRAIN_ENTRIES = 32
 
 
@@ -149,6 +159,8 @@ SIGNATURES = {
     "savsr_osa_fold_backward": (_I, [_VP, C.POINTER(OsaParams), C.POINTER(OsaTrain), C.POINTER(OsaGrads), _I, _I, _VP]),
     "savsr_slot_channel_dot": (_I, [_VP, _VP, _I, _I, _VP, _VP]),
     "savsr_ca_backward": (_I, [_VP, _VP, _I, _I, _I] + [_VP] * 11 + [_VP]),
+    "savsr_mask_forward_train": (_I, [_VP, _VP, C.POINTER(MaskTrain), _I, _I, _I, _I, _VP]),
+    "savsr_mask_backward_train": (_I, [_VP, _VP, C.POINTER(MaskTrain), _I, _I, _I, _I, _I, _I, _VP]),
     "savsr_pack_frames": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "savsr_osa_prologue": (_I, [_VP, C.POINTER(OsaParams), _I, _I, _I, _I, _F, _F, _VP]),
     "savsr_ca_scale_residual": (_I, [_VP, _VP, _I, _I, _I, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),

@@ -176,6 +176,19 @@ class TrainWeights:
             self._scatter_dst.append(G[:, src0:src0 + 3]); self._scatter_src.append(gz[:, dst0:dst0 + 3])
         return key
 
+    def scratch_grad(self, key, shape, scatter_to: Optional[torch.Tensor] = None, rows: Optional[int] = None) -> torch.Tensor:
+        """A zero-per-step fp32 gradient staging buffer shared by all plans (keyed); its first `rows` rows are added to `scatter_to`
+        after the backward (the tensor-core weight gradient always writes 64 output-channel rows)."""
+        k = ("scratch", key)
+        if k not in self._bufs:
+            buf = torch.zeros(*shape, device=self.dev)
+            self._bufs[k] = buf
+            self.scratch_grads.append(buf)
+            if scatter_to is not None:
+                self._scatter_dst.append(scatter_to)
+                self._scatter_src.append(buf[:rows] if rows is not None else buf)
+        return self._bufs[k]
+
     # ---- per step
     def finalize(self) -> None:
         if self.table is not None:
@@ -289,9 +302,11 @@ class TrainPlan:
     """Forward + backward launch list of one (batch, h, w, scale).  h and w must be even (the training crops are 64 x 64)."""
 
     def __init__(self, module: torch.nn.Module, flat: FlatParams, weights: TrainWeights, batch: int, h: int, w: int, scale,
-                 precision: str = "bf16", native_attn: bool = True):
+                 precision: str = "bf16", native_attn: bool = True, native_mask: bool = True):
         device = flat.device
         self.native_attn = native_attn and batch <= 8      # False: the attention MLPs run as ATen islands (cross-check / larger batches)
+        self.native_mask = native_mask                      # False: the OSAdapt mask net + combination run as an ATen island (cross-check)
+        self._mask_scratch: Optional[dict] = None
         self.nbt_counts: Dict[str, int] = {}
         if h % 2 or w % 2 or h < 2 or w < 2:
             raise ValueError(f"TrainPlan needs even LR sizes >= 2 (training crops), got {h}x{w}")
@@ -750,6 +765,9 @@ class TrainPlan:
         a = self._new_slot()
         out = self._new_slot()
         self._osa_conv([prefix + ".adapt"], [[r_slot]], [[plr]], [a], K.ACT_NONE)
+        if self.native_mask:
+            self._osadapt_native(prefix, r_slot, a, share, out)
+            return out
         net = self.net
         m = prefix + ".mask"
         names = [f"{m}.{i}.{k}" for i in (0, 1, 4, 5, 7, 8, 11, 12) for k in ("weight", "bias")] + ["gamma"]
@@ -779,6 +797,81 @@ class TrainPlan:
             self._import_grads([(s, (lambda i=i: st8["grads"][i])) for i, s in enumerate((r_slot, a, share))])
         self._builders.append(bwd)
         return out
+
+    def _osadapt_native(self, prefix: str, r_slot: int, a: int, share: int, out: int) -> None:
+        """Mask net + combination on the native kernels (train_mask.cu): the 64 -> 16 convolution forward / dgrad / wgrad on tensor cores
+        (N = 16 forward; its gradient as a 16-of-64-channel arena slot through the ordinary data- / weight-gradient path), the rest on
+        CUDA cores with batch-statistics BatchNorm."""
+        B, P, Q, dev = self.B, self.npix, (self.h // 2) * (self.w // 2), self.device
+        Pm, G, Bf = self.P, self.G, self.net.B
+        lib, ctx = self.lib, self.ctx.handle
+        m = prefix + ".mask"
+        if self._mask_scratch is None:             # backward scratch shared by the four OSAdapts of the plan (they run one after the other)
+            z = lambda *sh, dt=torch.float32: self._buf(*sh, dtype=dt)      # noqa: E731
+            self._mask_scratch = dict(dmask=z(B, P), dm11=z(B, P), dt4=z(B, Q, 16), dm7=z(B, Q, 16), dt3=z(B, Q, 16), dm4=z(B, Q, 16), dt2=z(B, Q, 16),
+                                      sums=z(64, dt=torch.float64), dm0_slot=self._new_slot())
+        sc = self._mask_scratch
+        act = dict(m0=self._buf(B, P, 16), t2=self._buf(B, Q, 16), m4=self._buf(B, Q, 16), t3=self._buf(B, Q, 16), m7=self._buf(B, Q, 16),
+                   t5=self._buf(B, P, 16), m11=self._buf(B, P), mask=self._buf(B, P), stat=self._buf(4 * 32), coef=self._buf(4 * 48))
+        mt = K.MaskTrain()
+        mt.w4, mt.b4, mt.w7, mt.b7 = (Pm[f"{m}.{k}"].data_ptr() for k in ("4.weight", "4.bias", "7.weight", "7.bias"))
+        mt.w11, mt.b11 = Pm[m + ".11.weight"].data_ptr(), Pm[m + ".11.bias"].data_ptr()
+        mt.d_w4, mt.d_b4, mt.d_w7, mt.d_b7 = (G[f"{m}.{k}"].data_ptr() for k in ("4.weight", "4.bias", "7.weight", "7.bias"))
+        mt.d_w11, mt.d_b11 = G[m + ".11.weight"].data_ptr(), G[m + ".11.bias"].data_ptr()
+        for l, idx in enumerate((1, 5, 8, 12)):
+            mt.bn_w[l], mt.bn_b[l] = Pm[f"{m}.{idx}.weight"].data_ptr(), Pm[f"{m}.{idx}.bias"].data_ptr()
+            mt.d_bn_w[l], mt.d_bn_b[l] = G[f"{m}.{idx}.weight"].data_ptr(), G[f"{m}.{idx}.bias"].data_ptr()
+            mt.bn_rm[l], mt.bn_rv[l] = Bf[f"{m}.{idx}.running_mean"].data_ptr(), Bf[f"{m}.{idx}.running_var"].data_ptr()
+            nbt = f"{m}.{idx}.num_batches_tracked"
+            if nbt in Bf:
+                self.nbt_counts[nbt] = self.nbt_counts.get(nbt, 0) + 1
+        mt.gamma, mt.d_gamma = Pm["gamma"].data_ptr(), G["gamma"].data_ptr()
+        mt.momentum, mt.eps = T.BN_MOMENTUM, T.BN_EPS
+        for k, v in act.items():
+            setattr(mt, k, v.data_ptr())
+        for k in ("dmask", "dm11", "dt4", "dm7", "dt3", "dm4", "dt2", "sums"):
+            setattr(mt, k, sc[k].data_ptr())
+        self._keep.append(mt)
+        # forward: pack the 64 -> 16 filter (N = 16 blocks), convolve into m0, then the rest of the net
+        w0, b0 = Pm[m + ".0.weight"], Pm[m + ".0.bias"]
+        packed16 = self._buf(int(lib.savsr_packed_weight_bytes(16, 64, 3)), dtype=torch.uint8)
+        self._emit(lambda st: K.check(lib.savsr_pack_conv_weight(w0.data_ptr(), 16, 16, 64, 3, 16, self.fmt, K.ROWS_LINEAR, packed16.data_ptr(), st)), kind="mask_fwd")
+        g0 = self._group([r_slot], 0, packed16.data_ptr(), b0.data_ptr())
+        g0.aux_dst = act["m0"].data_ptr()
+        arr = (K.ConvGroup * 1)(g0)
+        self._keep.append(arr)
+        self._emit(lambda st: K.check(lib.savsr_conv(ctx, self._ah(), arr, 1, 3, 16, K.DST_AUX16, K.IMPL_HALO, st)), kind="mask_fwd")
+        self._emit(lambda st: K.check(lib.savsr_mask_forward_train(ctx, self._ah(), C.byref(mt), r_slot, a, share, out, st)), launches=14, kind="mask_fwd")
+        wkey = m + ".0.weight"
+
+        def bwd():
+            if out not in self.gmap:
+                return
+            g = self.gmap[out]
+            da, gs, dm0 = self._new_slot(), self._new_slot(), sc["dm0_slot"]
+            self._emit(lambda st: K.check(lib.savsr_mask_backward_train(ctx, self._ah(), C.byref(mt), g, a, share, da, gs, dm0, st)), launches=22, kind="mask_bwd")
+            self.gmap[a] = da                                      # a has one consumer: this is its whole gradient
+            self._accumulate([(r_slot, g), (share, gs)])
+            # the 64 -> 16 convolution: its output gradient sits in channels 0..15 of slot dm0 (the rest zero)
+            gt = self._new_tslots(1)
+            dw64 = self.W.scratch_grad(("mask0.w", prefix), (64, 64, 3, 3), scatter_to=G[wkey], rows=16)
+            db64 = self.W.scratch_grad(("mask0.b", prefix), (64,), scatter_to=G[m + ".0.bias"], rows=16)
+            e = K.GradPrep()
+            e.dv_slot, e.out_slot, e.g_slot, e.gt_tslot, e.act, e.slope = dm0, -1, -1, gt, K.ACT_NONE, 0.0
+            e.cscale, e.cscale_stride, e.cadd, e.cadd_stride, e.cadd_mul = None, 0, None, 0, 0.0
+            e.dbias = db64.data_ptr()
+            parr = (K.GradPrep * 1)(e)
+            self._keep.append(parr)
+            self._emit(lambda st: K.check(lib.savsr_grad_prep(ctx, self._ah(), self.tarena.data_ptr(), self.n_tslots, self.pitch, parr, 1, st)), kind="grad_prep")
+            d, r = self._gdst(r_slot)
+            self._conv_launch([self._group([dm0], d, self.W.dgrad(((wkey, 0, 0),)), res1=r, src_channels=16)])
+            it = K.WgradItem()
+            it.g_tslot, it.ksize, it.dw, it.ci_total, it.ci_off, it.o_off = gt, 3, dw64.data_ptr(), 64, 0, 0
+            it.per_sample, it.sample_stride, it.layout = 0, 0, K.WGRAD_OIHW
+            self._wsrc.append(r_slot)
+            self.witems.append(it)
+            self.deferred.append(len(self.witems) - 1)
+        self._builders.append(bwd)
 
     # ------------------------------------------------------------------ program construction
     def _build(self) -> None:
@@ -952,9 +1045,9 @@ class NativeTrainer:
     (scale, batch shape).  lr / betas: the train YAML's Adam (2e-4, 0.9 / 0.99); EMA 0.999 (base_model.py:75-82)."""
 
     def __init__(self, net: torch.nn.Module, lr: float = 2e-4, betas=(0.9, 0.99), eps: float = 1e-8, ema_decay: float = 0.999,
-                 use_graph: bool = True, world_size: int = 1, native_attn: bool = True):
+                 use_graph: bool = True, world_size: int = 1, native_attn: bool = True, native_mask: bool = True):
         self.net = net
-        self.native_attn = native_attn
+        self.native_attn, self.native_mask = native_attn, native_mask
         self.flat = FlatParams(net, ema=ema_decay > 0)
         dev = self.flat.device
         self.ctx = context(_dev_index(dev))
@@ -974,7 +1067,7 @@ class NativeTrainer:
         b, t, c, h, w = lq.shape
         key = (tuple(normalize_scale(scale)), b, h, w)
         if key not in self.plans:
-            self.plans[key] = TrainPlan(self.net, self.flat, self.weights, b, h, w, scale, native_attn=self.native_attn)
+            self.plans[key] = TrainPlan(self.net, self.flat, self.weights, b, h, w, scale, native_attn=self.native_attn, native_mask=self.native_mask)
         return self.plans[key]
 
     def _fwd_bwd(self, plan: TrainPlan) -> torch.Tensor:

@@ -650,7 +650,7 @@ def check_train_step(b=2, h=16, w=20, scale=(2, 2), seed=0, steps=3):
     return info
 
 
-def check_trainplan(b=2, h=16, w=20, scale=(2, 2), seed=0, tol_worst=0.10, tol_cos=0.999, steps=0, graph=False, native_attn=True):
+def check_trainplan(b=2, h=16, w=20, scale=(2, 2), seed=0, tol_worst=0.10, tol_cos=0.999, steps=0, graph=False, native_attn=True, native_mask=True):
     """Row f1 stage B: the NATIVE training step (savsr_b200.trainplan: arena-resident forward / dgrad / batched wgrad, table-driven
     weight packing) against fp32 CPU autograd through the oracle: loss, per-parameter gradient error
     |g - r| / max(|r|, 1 % of the largest tensor gradient), and the cosine of the whole flat gradient."""
@@ -673,7 +673,7 @@ def check_trainplan(b=2, h=16, w=20, scale=(2, 2), seed=0, tol_worst=0.10, tol_c
         ref_loss.backward()
     finally:
         O.BN_TRAIN = False
-    tr = TP.NativeTrainer(net, use_graph=graph, native_attn=native_attn)
+    tr = TP.NativeTrainer(net, use_graph=graph, native_attn=native_attn, native_mask=native_mask)
     plan = tr.plan_for(x.to(DEV), scale)
     plan.x_in.copy_(x.to(DEV)); plan.gt.copy_(gt.to(DEV))
     loss = tr._fwd_bwd(plan)

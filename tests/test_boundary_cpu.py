@@ -74,6 +74,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_capi.Axpby) == 20 and ctypes.sizeof(_capi.Nchw3) == 8
     assert ctypes.sizeof(_capi.GradPrep) == 72 and _capi.GradPrep.cscale.offset == 24 and _capi.GradPrep.dbias.offset == 64
     assert ctypes.sizeof(_capi.PackChunk) == 40 and ctypes.sizeof(_capi.WgradItem) == 48 and _capi.WgradItem.sample_stride.offset == 40
+    assert ctypes.sizeof(_capi.MaskTrain) == 456 and _capi.MaskTrain.gamma.offset == 176 and _capi.MaskTrain.dmask.offset == 400
     assert ctypes.sizeof(_capi.OsaTrain) == 56 and _capi.OsaTrain.state.offset == 40 and ctypes.sizeof(_capi.OsaGrads) == 160
 
 

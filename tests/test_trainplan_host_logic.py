@@ -51,6 +51,7 @@ def test_step_runs_and_census(recorded):
     # train-mode OSA prologue / fold backward: l1 5 iterations x 3 blocks (both directions per launch), l2 2, adapt 4
     assert names.count("savsr_osa_prologue_train") == 15 + 2 + 4 and names.count("savsr_osa_fold_backward") == 15 + 2 + 4
     assert names.count("savsr_slot_channel_dot") == 32 and names.count("savsr_ca_backward") == 32
+    assert names.count("savsr_mask_forward_train") == 4 and names.count("savsr_mask_backward_train") == 4
     # weight gradients: one inline launch per OSA-Conv launch (l1: both directions share one) + the final batched launch
     assert names.count("savsr_conv_wgrad_batched") == 15 + 2 + 4 + 1
     # forward convolutions as in the inference plan, minus the N = 16 mask convs (mask net = ATen island here)
@@ -89,6 +90,12 @@ def test_gradient_slots_are_written_before_use(recorded):
         elif name == "savsr_ca_scale_residual":
             assert args[2] in written and args[3] in written
             written.add(args[4])
+        elif name == "savsr_mask_forward_train":
+            assert all(a in written for a in args[3:6])
+            written.add(args[6])
+        elif name == "savsr_mask_backward_train":
+            assert all(a in written for a in args[3:6])
+            written.update(args[6:9])
         elif name == "savsr_grad_prep":
             for e in _entries(args, 5, 6):
                 assert e.dv_slot in written
