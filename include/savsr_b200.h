@@ -339,6 +339,15 @@ int savsr_mask_forward_train(savsr_ctx* ctx, savsr_arena* arena, const savsr_mas
 int savsr_mask_backward_train(savsr_ctx* ctx, savsr_arena* arena, const savsr_mask_train* m, int dh_slot, int a_slot, int share_slot, int da_slot,
                               int gshare_slot, int dm0_slot, savsr_stream st);
 
+/* sta_conv of STAUpsample fused with kernel_conv's LeakyReLU, for the training step (savsr_arch.py:297-313, 226-228), fp32 NCHW:
+ *   out[b,c,p] = sum_{t<25} x[b,c,clamp(p + d_t)] * lrelu(kpre[b, c*25 + t, p])     (replicate padding; t = 5 u + v, d_t = (u - 2, v - 2))
+ * x, out, dout, dx: [batch][channels][height][width]; kpre, dkpre: [batch][channels*25][height][width] (the output of kernel_conv BEFORE
+ * its activation).  backward writes dx and dkpre (no accumulation). */
+int savsr_sta_lrelu_forward(savsr_ctx* ctx, const float* x, const float* kpre, float* out, int batch, int channels, int height, int width,
+                            float slope, savsr_stream st);
+int savsr_sta_lrelu_backward(savsr_ctx* ctx, const float* x, const float* kpre, const float* dout, float* dx, float* dkpre, int batch, int channels,
+                             int height, int width, float slope, savsr_stream st);
+
 /* ---- RCAB channel attention (savsr_arch.py:514-524, 547-549) --------------------------------------
  * y = sigmoid(W2 relu(W1 mean(t) + b1) + b2) ; dst = x + t * y        (t, x, dst: arena slots)
  * Two launches: the per-sample channel-scale vector, then the streaming pass.                      */

@@ -161,6 +161,8 @@ SIGNATURES = {
     "savsr_ca_backward": (_I, [_VP, _VP, _I, _I, _I] + [_VP] * 11 + [_VP]),
     "savsr_mask_forward_train": (_I, [_VP, _VP, C.POINTER(MaskTrain), _I, _I, _I, _I, _VP]),
     "savsr_mask_backward_train": (_I, [_VP, _VP, C.POINTER(MaskTrain), _I, _I, _I, _I, _I, _I, _VP]),
+    "savsr_sta_lrelu_forward": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _F, _VP]),
+    "savsr_sta_lrelu_backward": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _F, _VP]),
     "savsr_pack_frames": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "savsr_osa_prologue": (_I, [_VP, C.POINTER(OsaParams), _I, _I, _I, _I, _F, _F, _VP]),
     "savsr_ca_scale_residual": (_I, [_VP, _VP, _I, _I, _I, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),

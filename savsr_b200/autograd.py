@@ -164,3 +164,41 @@ def conv3x3(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] 
     if weight.dim() == 5 and bias is not None:
         raise ValueError("conv3x3: per-sample kernels take no bias (OSA-Conv has none, savsr_arch.py:166)")
     return _Conv3x3.apply(x, weight, bias)
+
+
+class _StaLrelu(torch.autograd.Function):
+    """sta_conv of STAUpsample fused with kernel_conv's LeakyReLU (savsr_arch.py:297-313, 226-228) on libsavsr_sm100:
+    out[b,c,p] = sum_t x[b,c,clamp(p + d_t)] * lrelu(kpre[b, c*25 + t, p]).  The 25-tap unfold of x and the activated per-pixel kernels are
+    never materialised, in either direction."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, kpre: torch.Tensor, slope: float):
+        c = _ctx_of(x)
+        B, C, H, W = x.shape
+        if kpre.shape != (B, C * 25, H, W):
+            raise ValueError(f"sta_lrelu: kpre {tuple(kpre.shape)} does not match x {tuple(x.shape)} (5x5 kernels per channel)")
+        x32, k32 = x.detach().float().contiguous(), kpre.detach().float().contiguous()
+        out = torch.empty_like(x32)
+        with torch.cuda.device(x.device):
+            K.check(c.lib.savsr_sta_lrelu_forward(c.handle, x32.data_ptr(), k32.data_ptr(), out.data_ptr(), B, C, H, W, float(slope),
+                                                  torch.cuda.current_stream().cuda_stream))
+        ctx.save_for_backward(x32, k32)
+        ctx.slope = float(slope)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout: torch.Tensor):
+        x32, k32 = ctx.saved_tensors
+        c = _ctx_of(dout)
+        B, C, H, W = x32.shape
+        d32 = dout.detach().float().contiguous()
+        dx, dk = torch.empty_like(x32), torch.empty_like(k32)
+        with torch.cuda.device(dout.device):
+            K.check(c.lib.savsr_sta_lrelu_backward(c.handle, x32.data_ptr(), k32.data_ptr(), d32.data_ptr(), dx.data_ptr(), dk.data_ptr(), B, C, H, W,
+                                                   ctx.slope, torch.cuda.current_stream().cuda_stream))
+        return dx, dk, None
+
+
+def sta_lrelu(x: torch.Tensor, kpre: torch.Tensor, slope: float = 0.1) -> torch.Tensor:
+    """Differentiable per-pixel 5x5 dynamic filtering with replicate padding; kpre = kernel_conv's output before its LeakyReLU."""
+    return _StaLrelu.apply(x, kpre, slope)

@@ -474,3 +474,100 @@ extern "C" int savsr_mask_backward_train(savsr_ctx* ctx, savsr_arena* arena, con
   SAVSR_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ SATU: per-pixel 5x5 dynamic filter
+// sta_conv of STAUpsample (savsr_arch.py:297-313) fused with the LeakyReLU of kernel_conv (226-228), for the training step:
+//   out[b,c,p] = sum_t x[b,c,clamp(p + d_t)] * lrelu(kpre[b, c*25 + t, p])            (replicate padding, t = 5 u + v, d_t = (u-2, v-2))
+// fp32 NCHW tensors (the island around it is ATen).  Without this fusion the framework materialises the 25-tap unfold of x, the
+// activated kernels and two more products of that size (105 MB each at 4 x 64 x 64) in both directions.
+namespace savsr {
+__global__ void __launch_bounds__(256) sta_lrelu_fwd_kernel(const float* __restrict__ x, const float* __restrict__ kpre, float* __restrict__ out,
+                                                            long planes, int h, int w, float slope) {
+  const long npix = static_cast<long>(h) * w, total = planes * npix;
+  for (long e = blockIdx.x * 256L + threadIdx.x; e < total; e += gridDim.x * 256L) {
+    const long pl = e / npix, p = e - pl * npix;
+    const int yy = p / w, xx = p - static_cast<long>(yy) * w;
+    const float* xs = x + pl * npix;
+    const float* ks = kpre + pl * 25 * npix + p;
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 25; ++t) {
+      const int sy = min(max(yy + t / 5 - 2, 0), h - 1), sx = min(max(xx + t % 5 - 2, 0), w - 1);
+      const float k = ks[t * npix];
+      acc += xs[sy * w + sx] * (k > 0.f ? k : slope * k);
+    }
+    out[e] = acc;
+  }
+}
+// d kpre[b, c*25 + t, p] = dout[b,c,p] * x[b,c,clamp(p + d_t)] * lrelu'(kpre)
+__global__ void __launch_bounds__(256) sta_lrelu_bwd_k_kernel(const float* __restrict__ x, const float* __restrict__ kpre, const float* __restrict__ dout,
+                                                              float* __restrict__ dkpre, long planes, int h, int w, float slope) {
+  const long npix = static_cast<long>(h) * w, total = planes * npix;
+  for (long e = blockIdx.x * 256L + threadIdx.x; e < total; e += gridDim.x * 256L) {
+    const long pl = e / npix, p = e - pl * npix;
+    const int yy = p / w, xx = p - static_cast<long>(yy) * w;
+    const float* xs = x + pl * npix;
+    const long kb = pl * 25 * npix + p;
+    const float g = dout[e];
+#pragma unroll
+    for (int t = 0; t < 25; ++t) {
+      const int sy = min(max(yy + t / 5 - 2, 0), h - 1), sx = min(max(xx + t % 5 - 2, 0), w - 1);
+      dkpre[kb + t * npix] = g * xs[sy * w + sx] * (kpre[kb + t * npix] > 0.f ? 1.f : slope);
+    }
+  }
+}
+// d x[b,c,p'] = sum over (p, t) with clamp(p + d_t) = p' of dout[b,c,p] * lrelu(kpre[b, c*25 + t, p]).  Gather form: for an interior
+// coordinate the source is unique (p = p' - d_t); on a border every p whose shifted coordinate was clamped onto it contributes.
+__device__ __forceinline__ void sta_sources(int target, int d, int size, int& lo, int& hi) {
+  // all s in [0, size) with clamp(s + d, 0, size - 1) == target
+  if (target > 0 && target < size - 1) { lo = hi = target - d; if (lo < 0 || lo >= size) { lo = 1; hi = 0; } return; }
+  if (target == 0) { lo = 0; hi = min(size - 1, -d); if (size == 1) hi = 0; return; }          // s + d <= 0
+  lo = max(0, size - 1 - d); hi = size - 1;                                                     // s + d >= size - 1
+}
+__global__ void __launch_bounds__(256) sta_lrelu_bwd_x_kernel(const float* __restrict__ kpre, const float* __restrict__ dout, float* __restrict__ dx,
+                                                              long planes, int h, int w, float slope) {
+  const long npix = static_cast<long>(h) * w, total = planes * npix;
+  for (long e = blockIdx.x * 256L + threadIdx.x; e < total; e += gridDim.x * 256L) {
+    const long pl = e / npix, p = e - pl * npix;
+    const int ty = p / w, tx = p - static_cast<long>(ty) * w;
+    const float* ds = dout + pl * npix;
+    const float* ks = kpre + pl * 25 * npix;
+    float acc = 0.f;
+    for (int t = 0; t < 25; ++t) {
+      int y0, y1, x0, x1;
+      sta_sources(ty, t / 5 - 2, h, y0, y1);
+      sta_sources(tx, t % 5 - 2, w, x0, x1);
+      for (int sy = y0; sy <= y1; ++sy)
+        for (int sx = x0; sx <= x1; ++sx) {
+          const float k = ks[t * npix + sy * w + sx];
+          acc += ds[sy * w + sx] * (k > 0.f ? k : slope * k);
+        }
+    }
+    dx[e] = acc;
+  }
+}
+}  // namespace savsr
+
+extern "C" int savsr_sta_lrelu_forward(savsr_ctx* ctx, const float* x, const float* kpre, float* out, int batch, int channels, int height, int width,
+                                       float slope, savsr_stream st) {
+  SAVSR_REQUIRE(ctx && x && kpre && out, "savsr_sta_lrelu_forward: null pointer");
+  SAVSR_REQUIRE(batch >= 1 && channels >= 1 && height >= 1 && width >= 1, "savsr_sta_lrelu_forward: empty problem");
+  DeviceGuard guard(ctx->device);
+  const long planes = static_cast<long>(batch) * channels;
+  sta_lrelu_fwd_kernel<<<blocks_for(ctx, planes * height * width, 256), 256, 0, static_cast<cudaStream_t>(st)>>>(x, kpre, out, planes, height, width, slope);
+  SAVSR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int savsr_sta_lrelu_backward(savsr_ctx* ctx, const float* x, const float* kpre, const float* dout, float* dx, float* dkpre, int batch, int channels,
+                                        int height, int width, float slope, savsr_stream st) {
+  SAVSR_REQUIRE(ctx && x && kpre && dout && dx && dkpre, "savsr_sta_lrelu_backward: null pointer");
+  SAVSR_REQUIRE(batch >= 1 && channels >= 1 && height >= 1 && width >= 1, "savsr_sta_lrelu_backward: empty problem");
+  DeviceGuard guard(ctx->device);
+  const long planes = static_cast<long>(batch) * channels;
+  const int blocks = blocks_for(ctx, planes * height * width, 256);
+  sta_lrelu_bwd_k_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(st)>>>(x, kpre, dout, dkpre, planes, height, width, slope);
+  sta_lrelu_bwd_x_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(st)>>>(kpre, dout, dx, planes, height, width, slope);
+  SAVSR_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -17,6 +17,7 @@ from typing import Dict, List, Optional
 import torch
 import torch.nn.functional as F
 
+from . import autograd as _A
 from .autograd import conv3x3
 from .engine import get_hw, normalize_scale
 
@@ -164,9 +165,7 @@ def satu(net: _Net, prefix: str, x: Tensor, scale, st_feat: Tensor) -> Tensor:
     b, c, h, w = x.shape
     H, W = get_hw(h, w, s)
     dev = x.device
-    kern = _lrelu(net.conv(prefix + ".kernel_conv.0", st_feat), 0.1).view(b, c, 25, h * w)                 # channel c * 25 + (u * 5 + v)
-    xp = F.pad(x, (2, 2, 2, 2), mode="replicate")
-    sta = (F.unfold(xp, 5).view(b, c, 25, h * w) * kern).sum(2).view(b, c, h, w)                          # sta_conv, 297-313: one im2col + one reduction
+    sta = _A.sta_lrelu(x, net.conv(prefix + ".kernel_conv.0", st_feat), 0.1)                               # kernel_conv's LeakyReLU + sta_conv (297-313), fused natively
     ry = _rel_coord(H, s[0], dev).view(H, 1).expand(H, W)
     rx = _rel_coord(W, s[1], dev).view(1, W).expand(H, W)
     inp = torch.stack([torch.full((H, W), 1.0 / s[1], device=dev), torch.full((H, W), 1.0 / s[0], device=dev), ry, rx], 0)[None]

@@ -650,6 +650,28 @@ def check_train_step(b=2, h=16, w=20, scale=(2, 2), seed=0, steps=3):
     return info
 
 
+def check_sta_lrelu(B=2, C=5, h=7, w=9, seed=3):
+    """The fused sta_conv + LeakyReLU op of the training step (savsr_b200.autograd.sta_lrelu) against its ATen formulation
+    (replicate pad -> unfold -> product with the activated kernels -> sum over the 25 taps), forward and both gradients, fp32."""
+    import torch.nn.functional as F
+    from savsr_b200 import autograd as A
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, C, h, w, generator=g).to(DEV).requires_grad_(True)
+    k = torch.randn(B, C * 25, h, w, generator=g).to(DEV).requires_grad_(True)
+    go = torch.randn(B, C, h, w, generator=g).to(DEV)
+    out = A.sta_lrelu(x, k, 0.1)
+    gx, gk = torch.autograd.grad(out, [x, k], go)
+    kern = F.leaky_relu(k, 0.1).view(B, C, 25, h * w)
+    ref = (F.unfold(F.pad(x, (2, 2, 2, 2), mode="replicate"), 5).view(B, C, 25, h * w) * kern).sum(2).view(B, C, h, w)
+    rx, rk = torch.autograd.grad(ref, [x, k], go)
+    info = {}
+    for name, a, b in (("out", out, ref), ("dx", gx, rx), ("dk", gk, rk)):
+        err = float((a - b).abs().max())
+        info[name] = err
+        assert err <= 2e-5 * max(1.0, float(b.abs().max())), (name, err)
+    return info
+
+
 def check_trainplan(b=2, h=16, w=20, scale=(2, 2), seed=0, tol_worst=0.10, tol_cos=0.999, steps=0, graph=False, native_attn=True, native_mask=True):
     """Row f1 stage B: the NATIVE training step (savsr_b200.trainplan: arena-resident forward / dgrad / batched wgrad, table-driven
     weight packing) against fp32 CPU autograd through the oracle: loss, per-parameter gradient error

@@ -121,3 +121,11 @@ def test_kernels_in_fp16_operand_format(G):
         G.check_satu_hr()
     finally:
         G.set_precision("bf16")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 5, 7, 9), (1, 3, 2, 3), (1, 2, 1, 6), (2, 64, 16, 20)])
+def test_sta_lrelu_matches_the_aten_formulation(G, shape):
+    """Training: kernel_conv's LeakyReLU + sta_conv fused (replicate padding, 25 taps), forward and gradients, incl. maps smaller than the 5x5 window."""
+    B, C, h, w = shape
+    print(G.check_sta_lrelu(B, C, h, w))
