@@ -576,6 +576,34 @@ class Plan:
             d["ms"] += e0.elapsed_time(e1); d["flops"] += flops; d["ops"] += 1; d["launches"] += launches
         return out
 
+    def time_ops_graph(self, select: Callable[[str, str], bool], reps: int = 5) -> Dict[str, float]:
+        """Device time of a SUBSET of the plan's ops (select(kind, detail)) replayed back to back as their own CUDA graph: the sustained
+        per-launch duration of one kernel family under the same conditions as the timed forward (graph launch, power-capped clocks),
+        which an eager pass with an event pair around every op does not give (idle gaps between ops let the clocks recover).
+        Results are not meaningful (ops run out of program order on whatever the arenas hold); only the timing is used."""
+        idx = [i for i, (kind, _, _, detail) in enumerate(self.op_meta) if select(kind, detail)]
+        if not idx:
+            return dict(ms=0.0, flops=0.0, launches=0, ops=0)
+        with torch.cuda.device(self.device):
+            self.ctx.set_format(self.fmt)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=torch.cuda.Stream(self.device)):
+                st = torch.cuda.current_stream(self.device).cuda_stream
+                for i in idx:
+                    rc = self.ops[i](st)
+                    if rc:
+                        K.check(rc)
+            stream = self._stream()
+            g.replay()                                   # warm-up
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps):
+                g.replay()
+            e1.record(stream)
+            stream.synchronize()
+        return dict(ms=e0.elapsed_time(e1) / reps, flops=sum(self.op_meta[i][1] for i in idx), launches=sum(self.op_meta[i][2] for i in idx), ops=len(idx))
+
     def capture(self) -> None:
         """Capture run() into a CUDA graph (after one eager warm-up that sets kernel attributes)."""
         if self.graph is not None:
