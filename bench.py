@@ -411,6 +411,7 @@ def run_train(args, rank, world, local_rank):
         graph = not args.no_train_graph
         tr = TP.NativeTrainer(net, use_graph=graph, world_size=world)
     else:
+        net.native_training = False                             # stage A: the ATen tape with the 3x3 convolutions on tcgen05 (savsr_b200/train.py)
         model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank]) if world > 1 else net
         graph = world == 1 and not args.no_train_graph          # one CUDA graph per scale for the whole step (single process)
         tr = T.Trainer(model, use_graph=graph)

@@ -206,6 +206,7 @@ class SAVSR(nn.Module):
         # 16-bit operand format: "bf16" (throughput path, wide range) or "fp16" (same speed, 10-bit mantissa: meets the
         # <= 1e-3 max-abs bound against the fp32 reference; needs activations below 65504)
         self.precision = os.environ.get("SAVSR_PRECISION", "bf16")
+        self.native_training = os.environ.get("SAVSR_NATIVE_TRAIN", "1") != "0"     # train-mode forward on the native launch list (trainplan.py)
         self.debug_taps: Tuple[str, ...] = ()
         self.last_plan_build_ms = 0.0
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate_weights())
@@ -220,8 +221,17 @@ class SAVSR(nn.Module):
         if scale is not None:
             self.scale = scale
         if self.training:
-            # optimisation path (sr_model.py:101-128 calls net_g(lq) in train mode): differentiable forward whose 3x3 convolutions
-            # (forward, dgrad, wgrad) run on the tcgen05 kernels -- savsr_b200/train.py
+            # optimisation path (sr_model.py:101-128 calls net_g(lq) in train mode).  Default: the native launch list of
+            # savsr_b200/trainplan.py behind ONE autograd node (forward + backward of every trunk op on libsavsr_sm100; the caller's loss,
+            # optimizer, EMA and DistributedDataParallel work on the module's parameters as usual).  Fallback (odd sizes, batch > 8 per GPU,
+            # no_grad, native_training = False): savsr_b200/train.py, the ATen tape with the 3x3 convolutions on the tcgen05 kernels.
+            from savsr_b200 import trainplan as _tp
+            if self.native_training and torch.is_grad_enabled() and self.precision == "bf16" and _tp.ModuleTraining.supports(x):
+                st = self.__dict__.get("_train_state")
+                if st is None or not st.flat.intact():
+                    st = _tp.ModuleTraining(self)
+                    self.__dict__["_train_state"] = st
+                return st.forward(x, self.scale)
             from savsr_b200 import train as _train
             return _train.forward(self, x, self.scale)
         plan = self.plan_for(x)

@@ -246,7 +246,7 @@ class Trainer:
         self._graphs = {}
 
     def _step_body(self, lq: Tensor, gt: Tensor) -> Tensor:
-        loss = charbonnier(self.net(lq), gt)
+        loss = charbonnier(self.net(lq), gt)           # the module's train-mode forward: native launch list unless core.native_training is False
         loss.backward()
         self.opt.step()
         if self.ema is not None:

@@ -56,7 +56,7 @@ class FlatParams:
     """The module's parameters re-pointed into ONE flat fp32 buffer, with flat gradient / Adam moment / EMA buffers beside it
     (views keep the reference's names and shapes, so state_dict / load_state_dict / external optimizers keep working)."""
 
-    def __init__(self, module: torch.nn.Module, ema: bool = True):
+    def __init__(self, module: torch.nn.Module, ema: bool = True, assign_grads: bool = True):
         named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
         if not named:
             raise ValueError("module has no trainable parameters")
@@ -80,11 +80,18 @@ class FlatParams:
                 view = self.p[o:o + k].view(p.shape)
                 view.copy_(p.data)
                 p.data = view
-                p.grad = self.g[o:o + k].view(p.shape)
-                self.P[n], self.G[n] = p, p.grad
+                gview = self.g[o:o + k].view(p.shape)
+                if assign_grads:
+                    p.grad = gview
+                self.P[n], self.G[n] = p, gview
         self.ema = self.p.clone() if ema else None
         self.offsets = offs
+        self.ptrs = [p.data_ptr() for p in self.P.values()]
         self.step_t = torch.zeros(1, device=dev)              # Adam step count as a device scalar (graph replay reads it)
+
+    def intact(self) -> bool:
+        """False once something re-allocated the parameters (.to(), .half(), a replaced Parameter): the flat views are then stale."""
+        return all(p.data_ptr() == q for p, q in zip(self.P.values(), self.ptrs))
 
     def ema_view(self, name: str) -> torch.Tensor:
         o, p = self.offsets[name], self.P[name]
@@ -302,8 +309,10 @@ class TrainPlan:
     """Forward + backward launch list of one (batch, h, w, scale).  h and w must be even (the training crops are 64 x 64)."""
 
     def __init__(self, module: torch.nn.Module, flat: FlatParams, weights: TrainWeights, batch: int, h: int, w: int, scale,
-                 precision: str = "bf16", native_attn: bool = True, native_mask: bool = True):
+                 precision: str = "bf16", native_attn: bool = True, native_mask: bool = True, own_loss: bool = True):
         device = flat.device
+        self.own_loss = own_loss                            # False: the caller computes the loss from the returned output and passes its gradient back
+        self.dsr: Optional[torch.Tensor] = None
         self.native_attn = native_attn and batch <= 8      # False: the attention MLPs run as ATen islands (cross-check / larger batches)
         self.native_mask = native_mask                      # False: the OSAdapt mask net + combination run as an ATen island (cross-check)
         self._mask_scratch: Optional[dict] = None
@@ -938,7 +947,7 @@ class TrainPlan:
         st8: dict = {}
         names = [n for n in self.P if n.startswith("upsample.") or n.startswith("tail.")]
 
-        def loss_fwd(st):
+        def satu_fwd(st):
             leaves = [self._export(s).requires_grad_(True) for s in (TR, A)]
             tf32 = torch.backends.cuda.matmul.allow_tf32
             torch.backends.cuda.matmul.allow_tf32 = True        # the expert mixes and their weight gradients (K = B*H*W) on tensor cores, like the convs around them
@@ -946,19 +955,34 @@ class TrainPlan:
                 with torch.enable_grad():
                     sr = net.conv("tail", T.satu(net, "upsample", leaves[0], self.scale, leaves[1]))
                     sr = sr + F.interpolate(self.x_in[:, t // 2], size=(self.H, self.Wd), mode="bilinear", align_corners=False)
-                    loss = T.charbonnier(sr, self.gt)
-                self.sr = sr.detach()
-                self.loss = loss.detach()
-                params = [self.P[n] for n in names]
-                grads = torch.autograd.grad(loss, leaves + params, allow_unused=True)
+                    loss = T.charbonnier(sr, self.gt) if self.own_loss else None
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+            self.sr = sr.detach()
+            self.loss = loss.detach() if loss is not None else None
+            st8["leaves"], st8["sr"], st8["loss"] = leaves, sr, loss
+
+        def satu_bwd(st):
+            params = [self.P[n] for n in names]
+            tf32 = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = True
+            try:
+                if self.own_loss:
+                    grads = torch.autograd.grad(st8["loss"], st8["leaves"] + params, allow_unused=True)
+                else:                                           # the caller's loss: its gradient w.r.t. the output arrives in self.dsr
+                    grads = torch.autograd.grad(st8["sr"], st8["leaves"] + params, self.dsr, allow_unused=True)
             finally:
                 torch.backends.cuda.matmul.allow_tf32 = tf32
             st8["grads"] = grads[:2]
             self._param_grads(names, grads[2:])
-        self._emit(loss_fwd, launches=400, kind="island_satu_loss")
+            st8["sr"] = st8["loss"] = None
+        self._emit(satu_fwd, launches=150, kind="island_satu")
+        self._satu_bwd = satu_bwd
+        self.kinds[id(satu_bwd)] = "bwd:island_satu"
 
         # ---- backward program: builders in reverse order of the forward
         self._emit_to = self.bwd_ops
+        self._emit(self._satu_bwd, launches=250, kind="island_satu")
         self._import_grads([(s, (lambda i=i: st8["grads"][i])) for i, s in enumerate((TR, A))])
         for b in reversed(self._builders):
             b()
@@ -986,18 +1010,13 @@ class TrainPlan:
         self.nbytes = self.arena_t.numel() * 2 + self.tarena.numel() * 2
 
     # ------------------------------------------------------------------ execution
-    def run(self, x: Optional[torch.Tensor] = None, gt: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Forward + loss + backward on the device's current stream; gradients are ACCUMULATED into the flat gradient buffer
-        (the caller zeroes it and has packed the weights: Trainer does both).  Returns the loss (device scalar)."""
+    def run_forward(self) -> None:
+        """Forward of the launch list on the device's current stream (x_in -> sr, and the loss against self.gt when the plan owns it)."""
         with torch.cuda.device(self.device):
-            if x is not None:
-                self.x_in.copy_(x, non_blocking=True)
-            if gt is not None:
-                self.gt.copy_(gt, non_blocking=True)
             self.ctx.set_format(self.fmt)
-            st = torch.cuda.current_stream(self.device).cuda_stream
-            self._keep_step.clear()
             main = torch.cuda.current_stream(self.device)
+            st = main.cuda_stream
+            self._keep_step.clear()
             for op in self.fwd_ops[:-1]:
                 op(st)
             if self._side is None:
@@ -1007,14 +1026,35 @@ class TrainPlan:
                 sst = self._side.cuda_stream
                 for op in self.x3_ops:
                     op(sst)
-            self.fwd_ops[-1](st)                              # ... overlap SATU + tail + loss on the main stream
-            main.wait_stream(self._side)                      # join before the backward
+            self.fwd_ops[-1](st)                              # ... overlap SATU + tail (+ loss) on the main stream
+            if self.nbt_counts:                               # BatchNorms evaluated by native kernels: one counter bump per forward call, as nn.BatchNorm2d does
+                torch._foreach_add_([self.net.B[n] for n in self.nbt_counts], [int(c) for c in self.nbt_counts.values()])
+
+    def run_backward(self, dsr: Optional[torch.Tensor] = None) -> None:
+        """Backward of the launch list; gradients are ACCUMULATED into the flat gradient buffer.  dsr: gradient of the caller's loss
+        w.r.t. the output (plans built with own_loss=False)."""
+        with torch.cuda.device(self.device):
+            self.ctx.set_format(self.fmt)
+            main = torch.cuda.current_stream(self.device)
+            st = main.cuda_stream
+            self.dsr = dsr
+            if self._side is not None:
+                main.wait_stream(self._side)                  # join: the weight-gradient operands are in place
             for op in self.bwd_ops:
                 op(st)
-            if self.nbt_counts:                          # BatchNorms evaluated by native kernels: one counter bump per forward call, as nn.BatchNorm2d does
-                torch._foreach_add_([self.net.B[n] for n in self.nbt_counts], [int(c) for c in self.nbt_counts.values()])
-        return self.loss
+            self.dsr = None
 
+    def run(self, x: Optional[torch.Tensor] = None, gt: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Forward + loss + backward on the device's current stream; gradients are ACCUMULATED into the flat gradient buffer
+        (the caller zeroes it and has packed the weights: NativeTrainer does both).  Returns the loss (device scalar)."""
+        with torch.cuda.device(self.device):
+            if x is not None:
+                self.x_in.copy_(x, non_blocking=True)
+            if gt is not None:
+                self.gt.copy_(gt, non_blocking=True)
+        self.run_forward()
+        self.run_backward()
+        return self.loss
 
     def run_profiled(self) -> Dict[str, Dict[str, float]]:
         """Eager forward + backward with a CUDA-event pair around every op: {phase:kind: {"ms", "ops"}} (islands include their ATen launches)."""
@@ -1137,3 +1177,58 @@ class NativeTrainer:
             self._allreduce()
             self._opt_graph.replay()
             return loss
+
+
+# ====================================================================================================== the module's train-mode forward
+class ModuleTraining:
+    """What `SAVSR.forward` needs to run natively in train mode under SOMEBODY ELSE'S training loop -- the reference's
+    `optimize_parameters` (lbasicsr/models/sr_model.py:101-128: net_g(lq), its own loss, backward(), its own torch.optim.Adam, model_ema),
+    with or without DistributedDataParallel: flat parameter views, the packed weights, one plan per (scale, shape) built with
+    own_loss=False.  The forward returns the output as an autograd node whose backward runs the plan's backward launch list."""
+
+    def __init__(self, net: torch.nn.Module, native_attn: bool = True, native_mask: bool = True):
+        self.net = net
+        self.flat = FlatParams(net, ema=False, assign_grads=False)
+        self.ctx = context(_dev_index(self.flat.device))
+        self.weights = TrainWeights(self.flat, self.ctx)
+        self.native_attn, self.native_mask = native_attn, native_mask
+        self.plans: Dict[tuple, TrainPlan] = {}
+        self.params = list(self.flat.P.values())
+        self.slices = [(self.flat.offsets[n], p.numel(), p.shape) for n, p in self.flat.P.items()]
+
+    def plan_for(self, x: torch.Tensor, scale) -> TrainPlan:
+        b, t, c, h, w = x.shape
+        key = (tuple(normalize_scale(scale)), b, h, w)
+        if key not in self.plans:
+            self.plans[key] = TrainPlan(self.net, self.flat, self.weights, b, h, w, scale, native_attn=self.native_attn, native_mask=self.native_mask,
+                                        own_loss=False)
+        return self.plans[key]
+
+    @staticmethod
+    def supports(x: torch.Tensor) -> bool:
+        return x.is_cuda and x.dim() == 5 and x.shape[1] == 7 and x.shape[3] % 2 == 0 and x.shape[4] % 2 == 0 and x.shape[0] <= 8
+
+    def forward(self, x: torch.Tensor, scale) -> torch.Tensor:
+        return _NativeNet.apply(x, self, self.plan_for(x, scale), *self.params)
+
+
+class _NativeNet(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, state: ModuleTraining, plan: TrainPlan, *params):
+        with torch.cuda.device(plan.device):
+            state.weights.pack(torch.cuda.current_stream(plan.device).cuda_stream)       # the caller's optimizer changed the weights since the last step
+            plan.x_in.copy_(x.detach(), non_blocking=True)
+        plan.run_forward()
+        ctx.state, ctx.plan = state, plan
+        return plan.sr.clone()
+
+    @staticmethod
+    def backward(ctx, dsr: torch.Tensor):
+        state, plan = ctx.state, ctx.plan
+        with torch.cuda.device(plan.device):
+            state.flat.g.zero_()
+            state.weights.zero_scratch()
+            plan.run_backward(dsr.detach().float().contiguous())
+            state.weights.scatter_expanded_grads()
+            g = state.flat.g.clone()                  # autograd may keep what we return as p.grad: hand out a private copy, not views of the scratch
+        return (None, None, None) + tuple(g[o:o + k].view(shape) for o, k, shape in state.slices)

@@ -610,7 +610,7 @@ def check_train_block(block="residual_group", b=2, h=16, w=20, scale=(2.7, 1.5),
     return info
 
 
-def check_train_step(b=2, h=16, w=20, scale=(2, 2), seed=0, steps=3):
+def check_train_step(b=2, h=16, w=20, scale=(2, 2), seed=0, steps=3, native_module=True):
     """Whole-net training step (forward + backward through all 707 parameter tensors + Adam + EMA): loss and gradient norm against the
     fp32 CPU oracle at step 0, every parameter receives a gradient, and the loss goes down over a few steps on a fixed batch."""
     import savsr_b200
@@ -620,6 +620,7 @@ def check_train_step(b=2, h=16, w=20, scale=(2, 2), seed=0, steps=3):
     sd = make_state_dict(seed)
     net = savsr_b200.SAVSR().to(DEV)
     net.load_state_dict(sd, strict=True)
+    net.native_training = native_module          # True: the module's train-mode forward is the native launch list behind one autograd node
     x = make_input(b, h, w, 1234 + seed)
     H, W = O.get_hw(h, w, scale)
     gt = torch.rand(b, 3, H, W, generator=torch.Generator().manual_seed(5))
@@ -640,8 +641,14 @@ def check_train_step(b=2, h=16, w=20, scale=(2, 2), seed=0, steps=3):
     assert not missing, f"{len(missing)} parameters without gradient, e.g. {missing[:3]}"
     gn = float(torch.sqrt(sum((p.grad.float() ** 2).sum() for p in params.values())))
     rn = float(torch.sqrt(sum((v.grad ** 2).sum() for k, v in sd_cpu.items() if v.is_floating_point() and v.grad is not None)))
-    info = dict(loss=float(loss0), ref_loss=float(ref_loss), grad_norm=gn, ref_grad_norm=rn)
-    assert abs(float(loss0) - float(ref_loss)) < 2e-3 * max(1.0, abs(float(ref_loss))), info
+    info = dict(loss=float(loss0), ref_loss=float(ref_loss.detach()), grad_norm=gn, ref_grad_norm=rn, native=bool(net.__dict__.get("_train_state")))
+    assert info["native"] == bool(native_module), info
+    if native_module:                            # per-tensor parity as for the plan itself (the loss and the optimizer are the caller's here)
+        keys = [k for k in params if sd_cpu[k].grad is not None]
+        rep = _grad_report(params, sd_cpu, keys)
+        info["worst"] = sorted(rep.items(), key=lambda kv: -kv[1])[:3]
+        assert all(np.isfinite(v) and v < 0.10 for v in rep.values()), info
+    assert abs(float(loss0) - float(ref_loss.detach())) < 2e-3 * max(1.0, abs(float(ref_loss.detach()))), info
     assert abs(gn - rn) < 0.05 * rn, info
     losses = [float(tr.step(x.to(DEV), gt.to(DEV), scale)) for _ in range(steps)]
     info["losses"] = losses
