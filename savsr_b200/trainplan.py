@@ -984,6 +984,8 @@ class TrainPlan:
         self._emit_to = self.bwd_ops
         self._emit(self._satu_bwd, launches=250, kind="island_satu")
         self._import_grads([(s, (lambda i=i: st8["grads"][i])) for i, s in enumerate((TR, A))])
+        # ops up to the last import read tensors autograd produced this step (eager); everything after works on fixed buffers
+        self.n_bwd_island = 1 + max(i for i, op in enumerate(self.bwd_ops) if self.kinds.get(id(op)) == "bwd:import")
         for b in reversed(self._builders):
             b()
         # every weight gradient that was deferred, in one persistent launch
@@ -1010,39 +1012,62 @@ class TrainPlan:
         self.nbytes = self.arena_t.numel() * 2 + self.tarena.numel() * 2
 
     # ------------------------------------------------------------------ execution
-    def run_forward(self) -> None:
-        """Forward of the launch list on the device's current stream (x_in -> sr, and the loss against self.gt when the plan owns it)."""
+    def run_forward_native(self, join: bool) -> None:
+        """Every forward op except the SATU island, plus (on a side stream) the x-shifted NCHW copies the weight gradient needs."""
         with torch.cuda.device(self.device):
             self.ctx.set_format(self.fmt)
             main = torch.cuda.current_stream(self.device)
             st = main.cuda_stream
-            self._keep_step.clear()
             for op in self.fwd_ops[:-1]:
                 op(st)
             if self._side is None:
                 self._side = torch.cuda.Stream(self.device)
-            self._side.wait_stream(main)                      # fork: the transposed copies of the activations (weight-gradient operands) ...
+            self._side.wait_stream(main)                      # fork: the transposed copies of the activations (weight-gradient operands)
             with torch.cuda.stream(self._side):
                 sst = self._side.cuda_stream
                 for op in self.x3_ops:
                     op(sst)
-            self.fwd_ops[-1](st)                              # ... overlap SATU + tail (+ loss) on the main stream
+            if join:
+                main.wait_stream(self._side)
+
+    def run_forward_island(self) -> None:
+        """SATU's HR side + tail (+ loss): the ATen island, and the BatchNorm call counters."""
+        with torch.cuda.device(self.device):
+            self._keep_step.clear()
+            self.fwd_ops[-1](torch.cuda.current_stream(self.device).cuda_stream)
             if self.nbt_counts:                               # BatchNorms evaluated by native kernels: one counter bump per forward call, as nn.BatchNorm2d does
                 torch._foreach_add_([self.net.B[n] for n in self.nbt_counts], [int(c) for c in self.nbt_counts.values()])
+
+    def run_forward(self) -> None:
+        """Forward of the launch list on the device's current stream (x_in -> sr, and the loss against self.gt when the plan owns it)."""
+        self.run_forward_native(join=False)
+        self.run_forward_island()                             # ... overlaps the side stream's copies
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream(self.device).wait_stream(self._side)      # join
+
+    def run_backward_island(self, dsr: Optional[torch.Tensor] = None) -> None:
+        """Backward of the SATU island (autograd) and the import of its input gradients into arena slots."""
+        with torch.cuda.device(self.device):
+            self.ctx.set_format(self.fmt)
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            self.dsr = dsr
+            for op in self.bwd_ops[:self.n_bwd_island]:
+                op(st)
+            self.dsr = None
+
+    def run_backward_native(self) -> None:
+        """Every other backward op: pure launches on fixed buffers (graph-capturable without any autograd inside)."""
+        with torch.cuda.device(self.device):
+            self.ctx.set_format(self.fmt)
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            for op in self.bwd_ops[self.n_bwd_island:]:
+                op(st)
 
     def run_backward(self, dsr: Optional[torch.Tensor] = None) -> None:
         """Backward of the launch list; gradients are ACCUMULATED into the flat gradient buffer.  dsr: gradient of the caller's loss
         w.r.t. the output (plans built with own_loss=False)."""
-        with torch.cuda.device(self.device):
-            self.ctx.set_format(self.fmt)
-            main = torch.cuda.current_stream(self.device)
-            st = main.cuda_stream
-            self.dsr = dsr
-            if self._side is not None:
-                main.wait_stream(self._side)                  # join: the weight-gradient operands are in place
-            for op in self.bwd_ops:
-                op(st)
-            self.dsr = None
+        self.run_backward_island(dsr)
+        self.run_backward_native()
 
     def run(self, x: Optional[torch.Tensor] = None, gt: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Forward + loss + backward on the device's current stream; gradients are ACCUMULATED into the flat gradient buffer
@@ -1184,14 +1209,17 @@ class ModuleTraining:
     """What `SAVSR.forward` needs to run natively in train mode under SOMEBODY ELSE'S training loop -- the reference's
     `optimize_parameters` (lbasicsr/models/sr_model.py:101-128: net_g(lq), its own loss, backward(), its own torch.optim.Adam, model_ema),
     with or without DistributedDataParallel: flat parameter views, the packed weights, one plan per (scale, shape) built with
-    own_loss=False.  The forward returns the output as an autograd node whose backward runs the plan's backward launch list."""
+    own_loss=False.  The forward returns the output as an autograd node whose backward runs the plan's backward launch list.
+    Both halves are replayed as CUDA graphs (captured on their second use, sharing one memory pool: the backward reads what the
+    forward saved), so the ~1 400 launches of a step cost no host time."""
 
-    def __init__(self, net: torch.nn.Module, native_attn: bool = True, native_mask: bool = True):
+    def __init__(self, net: torch.nn.Module, native_attn: bool = True, native_mask: bool = True, use_graph: bool = True):
         self.net = net
         self.flat = FlatParams(net, ema=False, assign_grads=False)
         self.ctx = context(_dev_index(self.flat.device))
         self.weights = TrainWeights(self.flat, self.ctx)
         self.native_attn, self.native_mask = native_attn, native_mask
+        self.use_graph = use_graph and native_attn and native_mask      # graphs hold native launches only: no ATen island may sit inside the trunk
         self.plans: Dict[tuple, TrainPlan] = {}
         self.params = list(self.flat.P.values())
         self.slices = [(self.flat.offsets[n], p.numel(), p.shape) for n, p in self.flat.P.items()]
@@ -1200,8 +1228,10 @@ class ModuleTraining:
         b, t, c, h, w = x.shape
         key = (tuple(normalize_scale(scale)), b, h, w)
         if key not in self.plans:
-            self.plans[key] = TrainPlan(self.net, self.flat, self.weights, b, h, w, scale, native_attn=self.native_attn, native_mask=self.native_mask,
-                                        own_loss=False)
+            plan = TrainPlan(self.net, self.flat, self.weights, b, h, w, scale, native_attn=self.native_attn, native_mask=self.native_mask, own_loss=False)
+            plan.dsr_buf = torch.zeros(b, 3, plan.H, plan.Wd, device=self.flat.device)
+            plan.uses, plan.g_fwd, plan.g_bwd = 0, None, None
+            self.plans[key] = plan
         return self.plans[key]
 
     @staticmethod
@@ -1211,24 +1241,61 @@ class ModuleTraining:
     def forward(self, x: torch.Tensor, scale) -> torch.Tensor:
         return _NativeNet.apply(x, self, self.plan_for(x, scale), *self.params)
 
+    # ---- CUDA graphs hold the native launches only (no autograd inside a capture); the SATU island runs eagerly on both sides
+    def _fwd_native(self, plan: TrainPlan) -> None:
+        self.weights.pack(torch.cuda.current_stream(plan.device).cuda_stream)      # the caller's optimizer changed the weights since the last step
+        plan.run_forward_native(join=True)
+
+    def _bwd_native(self, plan: TrainPlan) -> None:
+        plan.run_backward_native()
+        self.weights.scatter_expanded_grads()
+
+    def run_forward(self, plan: TrainPlan) -> None:
+        dev = plan.device
+        plan.uses += 1
+        if not self.use_graph or plan.uses == 1 or torch.cuda.is_current_stream_capturing():     # (inside somebody else's capture: just record)
+            self._fwd_native(plan)
+        elif plan.g_fwd is None:
+            # second use: capture BOTH graphs here, on the caller's thread (the backward itself runs on autograd's worker thread)
+            torch.cuda.synchronize(dev)
+            cap = torch.cuda.Stream(dev)
+            gf = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gf, stream=cap):
+                self._fwd_native(plan)
+            gb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gb, stream=cap):
+                self._bwd_native(plan)
+            plan.g_fwd, plan.g_bwd = gf, gb
+            gf.replay()                                  # capture does not execute
+        else:
+            plan.g_fwd.replay()
+        plan.run_forward_island()
+
+    def run_backward(self, plan: TrainPlan) -> None:
+        self.flat.g.zero_()
+        self.weights.zero_scratch()
+        plan.run_backward_island(plan.dsr_buf)
+        if plan.g_bwd is not None and not torch.cuda.is_current_stream_capturing():
+            plan.g_bwd.replay()
+        else:
+            self._bwd_native(plan)
+
 
 class _NativeNet(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x: torch.Tensor, state: ModuleTraining, plan: TrainPlan, *params):
         with torch.cuda.device(plan.device):
-            state.weights.pack(torch.cuda.current_stream(plan.device).cuda_stream)       # the caller's optimizer changed the weights since the last step
             plan.x_in.copy_(x.detach(), non_blocking=True)
-        plan.run_forward()
+            state.run_forward(plan)
+            out = plan.sr.clone()
         ctx.state, ctx.plan = state, plan
-        return plan.sr.clone()
+        return out
 
     @staticmethod
     def backward(ctx, dsr: torch.Tensor):
         state, plan = ctx.state, ctx.plan
         with torch.cuda.device(plan.device):
-            state.flat.g.zero_()
-            state.weights.zero_scratch()
-            plan.run_backward(dsr.detach().float().contiguous())
-            state.weights.scatter_expanded_grads()
+            plan.dsr_buf.copy_(dsr.detach(), non_blocking=True)
+            state.run_backward(plan)
             g = state.flat.g.clone()                  # autograd may keep what we return as p.grad: hand out a private copy, not views of the scratch
         return (None, None, None) + tuple(g[o:o + k].view(shape) for o, k, shape in state.slices)

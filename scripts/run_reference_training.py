@@ -76,8 +76,8 @@ def main() -> None:
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 16
     if not os.path.isdir(os.path.join(REF, "lbasicsr")):
         raise SystemExit("baseline/_ref not installed (DESIGN.md section 2)")
-    ckpt = os.path.join(ROOT, "gpurun_out", "train_check_init.pth")
-    os.makedirs(os.path.dirname(ckpt), exist_ok=True)
+    import tempfile
+    ckpt = os.path.join(tempfile.gettempdir(), "savsr_b200_train_check_init.pth")
     if os.path.exists(ckpt):
         os.remove(ckpt)
     res = {}
