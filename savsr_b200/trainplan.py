@@ -993,9 +993,17 @@ class TrainPlan:
             order = self.deferred
             self._x3([self._wsrc[i] for i in order])
         # ---- allocate, now that slot counts are known
-        self.arena_t = torch.zeros(self.n_slots * B, self.h, self.w, 64, dtype=torch.bfloat16, device=self.device)
+        # The arenas depend on (batch, h, w) and on the op list, not on the scale: every plan of one configuration has the SAME slot
+        # layout (the build is deterministic), plans run one after the other, and every slot is rewritten by each step -- so all
+        # scales share one pair of arenas (5.5 GB at 4 x 64 x 64) instead of owning one each (the training YAML rotates 60 scales).
+        akey = ("arenas", B, self.h, self.w, self.native_attn, self.native_mask, self.n_slots, self.n_tslots)
+        shared = self.W._bufs.get(akey)
+        if shared is None:
+            shared = self.W._bufs[akey] = (
+                torch.zeros(self.n_slots * B, self.h, self.w, 64, dtype=torch.bfloat16, device=self.device),
+                torch.zeros(max(self.n_tslots, 1) * B * 64 * self.h * self.pitch, dtype=torch.bfloat16, device=self.device))
+        self.arena_t, self.tarena = shared
         self.arena = K.Arena(self.ctx, self.arena_t.data_ptr(), self.n_slots, B, self.h, self.w)
-        self.tarena = torch.zeros(max(self.n_tslots, 1) * B * 64 * self.h * self.pitch, dtype=torch.bfloat16, device=self.device)
         # weight-gradient table: inline (OSA) items keep their indices, the deferred ones are gathered behind them
         items = list(self.witems)
         for i, it in enumerate(items):

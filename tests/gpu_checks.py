@@ -722,9 +722,16 @@ def check_trainplan(b=2, h=16, w=20, scale=(2, 2), seed=0, tol_worst=0.10, tol_c
     assert np.isfinite(cos) and cos > tol_cos, info
     assert all(np.isfinite(v) and v < tol_worst for v in rep.values()), info
     if steps:
-        losses = [float(tr.step(x.to(DEV), gt.to(DEV), scale)) for _ in range(steps)]
-        info["losses"] = losses
-        assert all(np.isfinite(l) for l in losses) and losses[-1] < losses[0], info
+        # a second scale interleaved: the plans of all scales share one pair of arenas (and, with graphs, replay into the same addresses)
+        scale_b = (1.5, 4) if tuple(scale) != (1.5, 4) else (2, 2)
+        gt_b = torch.rand(b, 3, *O.get_hw(h, w, scale_b), generator=torch.Generator().manual_seed(6)).to(DEV)
+        losses, losses_b = [], []
+        for _ in range(steps):
+            losses.append(float(tr.step(x.to(DEV), gt.to(DEV), scale)))
+            losses_b.append(float(tr.step(x.to(DEV), gt_b, scale_b)))
+        info["losses"], info["losses_second_scale"] = losses, losses_b
+        assert len(tr.plans) == 2 and len({p.arena_t.data_ptr() for p in tr.plans.values()}) == 1, "plans of different scales must share the arenas"
+        assert all(np.isfinite(l) for l in losses + losses_b) and losses[-1] < losses[0] and losses_b[-1] < losses_b[0], info
     return info
 
 
