@@ -182,8 +182,12 @@ def satu(net: _Net, prefix: str, x: Tensor, scale, st_feat: Tensor) -> Tensor:
     fea0 = gather(x, off)
     wc = net.P[prefix + ".weight_compress"].flatten(2)                                                     # [4, 8, 64]
     we = net.P[prefix + ".weight_expand"].flatten(2)                                                       # [4, 64, 8]
-    t = (torch.einsum("ekc,bchw->bekhw", wc, fea0) * r[None, :, None]).sum(1)                              # two-stage routed mix, 353-370
-    fea = (torch.einsum("eck,bkhw->bechw", we, t) * r[None, :, None]).sum(1) + fea0
+    # two-stage routed mix, 353-370, as two 1x1 convolutions over the 32 = 4 experts x 8 compressed channels (the literal form
+    # materialises a [b, 4, 64, H, W] tensor: 268 MB at 4 x 256 x 256)
+    u = F.conv2d(fea0, wc.reshape(32, c, 1, 1))                                                            # rows e * 8 + k
+    t = (u.view(b, 4, 8, H, W) * r[None, :, None]).sum(1)                                                  # t_k = sum_e r_e (Wc_e fea0)_k
+    v = (r[None, :, None] * t[:, None]).reshape(b, 32, H, W)                                               # v[e * 8 + k] = r_e t_k
+    fea = F.conv2d(v, we.permute(1, 0, 2).reshape(c, 32, 1, 1)) + fea0                                     # sum_e r_e We_e t + fea0
     return net.conv(prefix + ".fusion", torch.cat([gather(sta, st_off), fea], 1))
 
 
