@@ -175,8 +175,9 @@ int savsr_conv_wgrad(savsr_ctx* ctx, const void* x3_nchw16, const void* dy_nchw1
  * The reference's optimisation step (lbasicsr/models/sr_model.py:101-128: forward, Charbonnier, autograd backward through cuDNN
  * dgrad / wgrad, Adam; base_model.py:75-82 EMA) as launches on the activation arena.  Gradients of activations live in slots of
  * the same arena; the weight gradient reads pixel-contiguous copies from a second caller-owned buffer, the "T-arena":
- * 16-bit NCHW, T-slot t = [batch][64][height][pitch] (pitch = width rounded up to a multiple of 8; the padding columns must be
- * zero: allocate it zeroed, these kernels never write non-zero values there).  savsr_b200/trainplan.py drives them.
+ * 16-bit NCHW, T-slot t = [batch][64][height][pitch] (pitch = width rounded up to a multiple of 8; allocate it zeroed: the gradient
+ * copies keep their padding columns zero, which is what makes the padded contraction exact -- the right-shifted activation copy may
+ * carry one pixel into its first padding column).  savsr_b200/trainplan.py drives them.
  * Every `entries` array below is HOST memory (copied into the launch), at most 32 entries per call; `*_dev` arrays are DEVICE memory.
  */
 typedef struct savsr_axpby {

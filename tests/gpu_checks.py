@@ -657,6 +657,179 @@ def check_train_step(b=2, h=16, w=20, scale=(2, 2), seed=0, steps=3, native_modu
     return info
 
 
+# ------------------------------------------------------------------------------------------------ training kernels (train_ops.cu)
+def check_pack_chunks(seed=4):
+    """savsr_pack_conv_chunks (table-driven, one launch): forward orientation == savsr_pack_conv_weight bit for bit; transposed mode ==
+    savsr_pack_conv_weight of the flipped, transposed filter of each 64-channel source (what autograd.py packs for the data gradient)."""
+    import ctypes as C
+    lib = K.load()
+    g = torch.Generator().manual_seed(seed)
+    info = {}
+    for co, ci, ks in ((128, 192, 3), (64, 64, 3), (64, 192, 1), (16, 64, 3)):
+        w = torch.randn(co, ci, ks, ks, generator=g).to(DEV)
+        taps = ks * ks
+        chunks, bufs = [], []
+        if co % 64 == 0:
+            fwd = torch.zeros(co * ci * taps * 2, dtype=torch.uint8, device=DEV)
+            bufs.append(fwd)
+            for ng in range(co // 64):
+                for s in range(ci // 64):
+                    ch = K.PackChunk()
+                    ch.w, ch.dst = w.data_ptr(), fwd.data_ptr() + (ng * (ci // 64) + s) * taps * 8192
+                    ch.co_total, ch.ci_total, ch.o_base, ch.i_base, ch.ksize, ch.transposed = co, ci, ng * 64, s * 64, ks, 0
+                    chunks.append(ch)
+        nh = (co + 63) // 64
+        tr = torch.zeros((ci // 64) * nh * taps * 8192, dtype=torch.uint8, device=DEV)      # per source s: nh K-stacked chunks
+        for s in range(ci // 64):
+            for h in range(nh):
+                ch = K.PackChunk()
+                ch.w, ch.dst = w.data_ptr(), tr.data_ptr() + (s * nh + h) * taps * 8192
+                ch.co_total, ch.ci_total, ch.o_base, ch.i_base, ch.ksize, ch.transposed = co, ci, h * 64, s * 64, ks, 1
+                chunks.append(ch)
+        arr = (K.PackChunk * len(chunks))(*chunks)
+        table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(DEV)
+        K.check(lib.savsr_pack_conv_chunks(ctx().handle, table.data_ptr(), 0, len(chunks), _stream()))
+        torch.cuda.synchronize()
+        if co % 64 == 0:
+            assert torch.equal(fwd, pack_weight(w)), (co, ci, ks, "forward")
+        wpad = torch.zeros(nh * 64, ci, ks, ks, device=DEV)
+        wpad[:co] = w
+        for s in range(ci // 64):
+            # data-gradient filter of source s: [64 in-channels as outputs][nh * 64 out-channels as inputs], taps flipped
+            wt = wpad[:, 64 * s:64 * s + 64].flip(-1, -2).permute(1, 0, 2, 3).contiguous()
+            ref = pack_weight(wt)
+            got = tr[s * nh * taps * 8192:(s + 1) * nh * taps * 8192]
+            assert torch.equal(got, ref), (co, ci, ks, "transposed", s)
+        info[(co, ci, ks)] = len(chunks)
+    return info
+
+
+def check_train_elementwise(B=2, H=6, W=20, seed=5):
+    """savsr_slot_axpby, savsr_grad_prep (activation derivative, channel scale, pooled-mean gradient, bias gradient, NHWC + NCHW outputs)
+    and savsr_slot_to_nchw3 against their definitions; W = 20 exercises the padded pitch (24), W = 72 a second 64-pixel chunk."""
+    lib = K.load()
+    g = torch.Generator().manual_seed(seed)
+    ab = ArenaBox(8, B, H, W)
+    dt = _h16()
+    pitch = (W + 7) // 8 * 8
+    ntslots = 6
+    tar = torch.zeros(ntslots * B * 64 * H * pitch, dtype=dt, device=DEV)
+    dv, out = torch.randn(B, 64, H, W, generator=g), torch.randn(B, 64, H, W, generator=g)
+    ab.put(0, dv); ab.put(1, out)
+    dvr, outr = bf16_round(dv).to(DEV), bf16_round(out).to(DEV)
+    # axpby
+    arr = (K.Axpby * 2)()
+    arr[0].dst_slot, arr[0].x_slot, arr[0].y_slot, arr[0].alpha, arr[0].beta = 2, 0, 1, 0.5, 2.0
+    arr[1].dst_slot, arr[1].x_slot, arr[1].y_slot, arr[1].alpha, arr[1].beta = 3, 1, -1, 1.0, 0.0
+    K.check(lib.savsr_slot_axpby(ctx().handle, ab.a.handle, arr, 2, _stream()))
+    assert torch.equal(ab.get(2), bf16_round(0.5 * dvr + 2.0 * outr)) and torch.equal(ab.get(3), outr)
+    # grad_prep
+    cs, ca = torch.rand(B, 64, generator=g).to(DEV) + 0.5, torch.randn(B, 96, generator=g).to(DEV)
+    dbias = torch.zeros(64, device=DEV)
+    info = {}
+    for act, slope in ((K.ACT_LRELU, 0.2), (K.ACT_RELU, 0.0), (K.ACT_NONE, 0.0)):
+        e = (K.GradPrep * 1)()
+        e[0].dv_slot, e[0].out_slot, e[0].g_slot, e[0].gt_tslot, e[0].act, e[0].slope = 0, 1, 4, 1, act, slope
+        e[0].cscale, e[0].cscale_stride = cs.data_ptr(), 64
+        e[0].cadd, e[0].cadd_stride, e[0].cadd_mul = ca.data_ptr() + 32 * 4, 96, 0.25
+        e[0].dbias = dbias.data_ptr()
+        dbias.zero_()
+        K.check(lib.savsr_grad_prep(ctx().handle, ab.a.handle, tar.data_ptr(), ntslots, pitch, e, 1, _stream()))
+        ref = dvr * cs.view(B, 64, 1, 1) + 0.25 * ca[:, 32:].view(B, 64, 1, 1)
+        if act != K.ACT_NONE:
+            ref = ref * torch.where(outr > 0, torch.ones_like(outr), torch.full_like(outr, slope))
+        ref = bf16_round(ref)
+        got = ab.get(4)
+        # one 16-bit rounding of an fp32 value whose last bit may differ (the kernel contracts dv * cs + ca into an FMA)
+        assert bool(((got - ref).abs() <= 2.0 ** -7 * ref.abs() + 1e-30).all()), (act, float((got - ref).abs().max()))
+        assert float((got != ref).float().mean()) < 1e-3, act
+        gt = tar.view(ntslots, B, 64, H, pitch)[1].float()
+        assert torch.equal(gt[..., :W], got) and float(gt[..., W:].abs().max() if pitch > W else 0.0) == 0.0, act      # both layouts hold the same values
+        info[act] = float((dbias - got.sum(dim=(0, 2, 3))).abs().max() / (got.sum(dim=(0, 2, 3)).abs().max() + 1e-9))
+        assert info[act] < 1e-5, info
+    # three x-shifted NCHW copies
+    n3 = (K.Nchw3 * 1)()
+    n3[0].x_slot, n3[0].t_slot = 1, 3
+    K.check(lib.savsr_slot_to_nchw3(ctx().handle, ab.a.handle, tar.data_ptr(), ntslots, pitch, n3, 1, _stream()))
+    torch.cuda.synchronize()
+    t3 = tar.view(ntslots, B, 64, H, pitch)[3:6].float()
+    ref3 = torch.zeros(3, B, 64, H, pitch, device=DEV)
+    ref3[1, ..., :W] = outr
+    ref3[0, ..., 1:W] = outr[..., :W - 1]
+    if pitch > W:
+        ref3[0, ..., W] = outr[..., W - 1]           # the copy shifted right spills one pixel into the padding: harmless (dY is zero there)
+    ref3[2, ..., :W - 1] = outr[..., 1:]
+    assert torch.equal(t3[1], ref3[1]) and torch.equal(t3[2], ref3[2]) and torch.equal(t3[0][..., :W], ref3[0][..., :W]), "nchw3"
+    return info
+
+
+def check_wgrad_batched(B=2, H=10, W=20, seed=6):
+    """savsr_conv_wgrad_batched: two items of one table (a shared 128 -> 64 filter's second source in OIHW layout, a per-sample 64 -> 64
+    filter in the [tap][i][o] layout) against F.conv2d's weight gradient on the same rounded operands."""
+    import torch.nn.functional as F
+    lib = K.load()
+    g = torch.Generator().manual_seed(seed)
+    dt = _h16()
+    pitch = (W + 7) // 8 * 8
+    ab = ArenaBox(4, B, H, W)
+    ntslots = 8
+    tar = torch.zeros(ntslots * B * 64 * H * pitch, dtype=dt, device=DEV)
+    x, dy = torch.randn(B, 64, H, W, generator=g), torch.randn(B, 64, H, W, generator=g)
+    ab.put(0, x); ab.put(1, dy)
+    xr, dyr = bf16_round(x).to(DEV), bf16_round(dy).to(DEV)
+    n3 = (K.Nchw3 * 1)()
+    n3[0].x_slot, n3[0].t_slot = 0, 0
+    K.check(lib.savsr_slot_to_nchw3(ctx().handle, ab.a.handle, tar.data_ptr(), ntslots, pitch, n3, 1, _stream()))
+    e = (K.GradPrep * 1)()
+    e[0].dv_slot, e[0].out_slot, e[0].g_slot, e[0].gt_tslot, e[0].act = 1, -1, -1, 3, K.ACT_NONE
+    K.check(lib.savsr_grad_prep(ctx().handle, ab.a.handle, tar.data_ptr(), ntslots, pitch, e, 1, _stream()))
+    dw_shared = torch.zeros(64, 128, 3, 3, device=DEV)
+    dw_tio = torch.zeros(B, 9, 64, 64, device=DEV)
+    items = (K.WgradItem * 2)()
+    items[0].x_tslot, items[0].g_tslot, items[0].dw = 0, 3, dw_shared.data_ptr()
+    items[0].ci_total, items[0].ci_off, items[0].o_off, items[0].ksize, items[0].per_sample, items[0].layout = 128, 64, 0, 3, 0, K.WGRAD_OIHW
+    items[1].x_tslot, items[1].g_tslot, items[1].dw = 0, 3, dw_tio.data_ptr()
+    items[1].ci_total, items[1].ci_off, items[1].o_off, items[1].ksize, items[1].per_sample, items[1].layout = 64, 0, 0, 3, 1, K.WGRAD_TIO
+    items[1].sample_stride = 9 * 64 * 64
+    table = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8).to(DEV)
+    K.check(lib.savsr_conv_wgrad_batched(ctx().handle, tar.data_ptr(), ntslots, B, H, W, pitch, table.data_ptr(), 0, 2, _stream()))
+    torch.cuda.synchronize()
+    w0 = torch.zeros(64, 64, 3, 3, device=DEV, requires_grad=True)
+    ref = torch.autograd.grad(F.conv2d(xr, w0, padding=1), w0, dyr)[0]                     # [o, i, ky, kx]
+    scale = float(ref.abs().max())
+    e0 = float((dw_shared[:, 64:] - ref).abs().max()) / scale
+    assert float(dw_shared[:, :64].abs().max()) == 0.0 and e0 < 1e-4, e0
+    per = torch.stack([torch.autograd.grad(F.conv2d(xr[n:n + 1], w0, padding=1), w0, dyr[n:n + 1])[0] for n in range(B)])      # [B, o, i, 3, 3]
+    e1 = float((dw_tio - per.permute(0, 3, 4, 2, 1).reshape(B, 9, 64, 64)).abs().max()) / scale
+    assert e1 < 1e-4, e1
+    return dict(shared_rel=e0, per_sample_tio_rel=e1)
+
+
+def check_adam_ema(n=100003, steps=5, seed=7):
+    """savsr_adam_ema against torch.optim.Adam (lr 2e-4, betas 0.9 / 0.99, eps 1e-8, no weight decay) + the EMA of base_model.py:75-82."""
+    lib = K.load()
+    g = torch.Generator().manual_seed(seed)
+    p0 = torch.randn(n, generator=g).to(DEV)
+    p, m, v, ema = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV), p0.clone()
+    step_t = torch.zeros(1, device=DEV)
+    rp = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([rp], lr=2e-4, betas=(0.9, 0.99), eps=1e-8)
+    rema = p0.clone()
+    for _ in range(steps):
+        grad = torch.randn(n, generator=g).to(DEV) * 1e-3
+        step_t.add_(1.0)
+        K.check(lib.savsr_adam_ema(ctx().handle, p.data_ptr(), (grad * 2).data_ptr(), m.data_ptr(), v.data_ptr(), ema.data_ptr(), n, 2e-4, 0.9, 0.99, 1e-8,
+                                   step_t.data_ptr(), 0.999, 0.5, _stream()))          # gradient pre-scaled by 2, grad_scale 0.5
+        torch.cuda.synchronize()
+        rp.grad = grad.clone()
+        opt.step()
+        rema.mul_(0.999).add_(rp.detach(), alpha=0.001)
+    e_p = float((p - rp.detach()).abs().max())
+    e_ema = float((ema - rema).abs().max())
+    assert e_p < 2e-6 and e_ema < 2e-6, (e_p, e_ema)
+    return dict(param_max_abs=e_p, ema_max_abs=e_ema, moved=float((p - p0).abs().max()))
+
+
 def check_sta_lrelu(B=2, C=5, h=7, w=9, seed=3):
     """The fused sta_conv + LeakyReLU op of the training step (savsr_b200.autograd.sta_lrelu) against its ATen formulation
     (replicate pad -> unfold -> product with the activated kernels -> sum over the 25 taps), forward and both gradients, fp32."""

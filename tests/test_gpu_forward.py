@@ -231,8 +231,9 @@ def test_module_api_errors(G):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kw", [dict(), dict(scale=(1.5, 4), seed=1, b=3, h=12, w=24), dict(native_attn=False, native_mask=False)],
-                         ids=["x2", "x1.5x4_b3", "aten_attention_and_mask_islands"])
+@pytest.mark.parametrize("kw", [dict(), dict(scale=(1.5, 4), seed=1, b=3, h=12, w=24), dict(native_attn=False, native_mask=False),
+                                dict(scale=(2.7, 2.7), seed=2, b=1, h=8, w=72)],
+                         ids=["x2", "x1.5x4_b3", "aten_attention_and_mask_islands", "x2.7_w72"])
 def test_native_training_plan_gradients_match_the_oracle(G, kw):
     """Row f1 stage B: the static forward + backward launch list (savsr_b200.trainplan) against fp32 CPU autograd through the oracle on
     the WHOLE net: loss to 2e-3, every parameter tensor's gradient within 10 % of max(|r|, 1 % of the largest tensor gradient)

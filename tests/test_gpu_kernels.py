@@ -129,3 +129,27 @@ def test_sta_lrelu_matches_the_aten_formulation(G, shape):
     """Training: kernel_conv's LeakyReLU + sta_conv fused (replicate padding, 25 taps), forward and gradients, incl. maps smaller than the 5x5 window."""
     B, C, h, w = shape
     print(G.check_sta_lrelu(B, C, h, w))
+
+
+@pytest.mark.gpu
+def test_training_weight_packing_table(G):
+    """One table-driven launch packs every filter corner, forward orientation and transposed + flipped, bit-identical to the single-filter packer."""
+    print(G.check_pack_chunks())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 6, 20), (1, 4, 72), (3, 5, 64)])
+def test_training_elementwise_kernels(G, shape):
+    """axpby / grad_prep / nchw3 against their definitions, with a padded pitch, a second 64-pixel chunk and the exact fit."""
+    print(G.check_train_elementwise(*shape))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 10, 20), (1, 6, 72)])
+def test_training_batched_weight_gradient(G, shape):
+    print(G.check_wgrad_batched(*shape))
+
+
+@pytest.mark.gpu
+def test_training_adam_ema_kernel(G):
+    print(G.check_adam_ema())
