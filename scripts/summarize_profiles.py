@@ -22,16 +22,23 @@ def launches(tag):
     names = [re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "") for r in rows]
     vals = [float(r["Metric Value"].replace(",", "")) for r in rows]
     starts = [i for i, n in enumerate(names) if "pack_frames" in n]            # one per forward
-    # forwards: plan capture warm-up (1) + 3 warm-up steps x 2 + timed step (2) + e2e ...; take the timed step = forwards 7, 8
-    a, b = starts[7], starts[9]
+    if tag in ("r01", "r02"):
+        # forwards: plan capture warm-up (1) + 3 warm-up steps x 2 + timed step (2) + e2e ...; take the timed step = forwards 7, 8
+        a, b = starts[7], starts[9]
+        what = "one timed step = 2 forwards of 17 windows"
+    else:
+        # one forward per step (the whole 34-frame clip); the e2e leg's plans (26 and 8 windows) are in the list too: take the longest forward
+        segs = [(sum(vals[starts[i]:starts[i + 1]]), starts[i], starts[i + 1]) for i in range(len(starts) - 1)]
+        _, a, b = max(segs)
+        what = "one forward of 34 windows = one step"
     agg = collections.defaultdict(lambda: [0, 0.0])
     for n, v in zip(names[a:b], vals[a:b]):
         agg[n][0] += 1
         agg[n][1] += v
     tot = sum(v for _, v in agg.values())
-    out = [f"# {tag}: ncu launch list of `bench.py --steps 1 --warmup 1` (one timed step = 2 forwards of 17 windows, Vid4 x4)", "",
+    out = [f"# {tag}: ncu launch list of `bench.py --steps 1 --warmup 1` ({what}, Vid4 x4)", "",
            "Command: `ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_%s_bench.csv "
-           "python bench.py --steps 1 --warmup 1 --no-cpu-baseline%s`" % (tag, "" if tag == "r01" else " --no-extras"),
+           "python bench.py --steps 1 --warmup 1 --no-cpu-baseline%s`" % (tag, "" if tag == "r01" else " --no-extras") + ("" if tag in ("r01", "r02") else " (`-c 4000`)"),
            "(per-launch times under ncu are serialised and cold-cache: compare SHARES with `roofline.share_of_step` / `per_kind_ms` of bench.py, not absolutes)", "",
            f"kernel launches in the step: {b - a}, summed kernel time {tot / 1e6:.2f} ms", "",
            "| kernel | launches | total ms | share | avg us |", "|---|---|---|---|---|"]
@@ -132,13 +139,13 @@ R02_KEYS = ["gpu__time_duration.sum", "gpc__cycles_elapsed.avg.per_second", "dra
             "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum"]
 
 
-def r02(tag="r02"):
-    px, B = 144 * 180, 17
+def r02(tag="r02", B=17):
+    px = 144 * 180
     H, W = 576, 720
-    caps = [(f"{tag}_conv_s3g2.ncu-rep", "conv 2 x (192->64) OSA-shaped, B=17", 2.0 * 2 * B * px * 64 * 1728,
+    caps = [(f"{tag}_conv_s3g2.ncu-rep", f"conv 2 x (192->64) OSA-shaped, B={B}", 2.0 * 2 * B * px * 64 * 1728,
              2 * B * (3 + 1) * px * 128 + 2 * B * 64 * 192 * 9 * 2),
-            (f"{tag}_conv_s2g6.ncu-rep", "conv 6 x (128->64) + residual, B=17", 2.0 * 6 * B * px * 64 * 1152, 6 * B * (2 + 1 + 1) * px * 128),
-            (f"{tag}_conv_s1g1.ncu-rep", "conv 1 x (64->64) + pooled sums (RCAB), B=17", 2.0 * 1 * B * px * 64 * 576, B * (1 + 1) * px * 128)]
+            (f"{tag}_conv_s2g6.ncu-rep", f"conv 6 x (128->64) + residual, B={B}", 2.0 * 6 * B * px * 64 * 1152, 6 * B * (2 + 1 + 1) * px * 128),
+            (f"{tag}_conv_s1g1.ncu-rep", f"conv 1 x (64->64) + pooled sums (RCAB), B={B}", 2.0 * 1 * B * px * 64 * 576, B * (1 + 1) * px * 128)]
     cols = []
     for rep, desc, flops, alg in caps:
         if os.path.exists(os.path.join(G, rep)):
@@ -149,10 +156,10 @@ def r02(tag="r02"):
         short = "satu_kconv_sta_kernel" if "kconv" in name else "satu_hr_kernel"
         alg = B * (3 * px * 128) if "kconv" in name else B * (2 * px * 128 + 3 * px * 4 + 3 * H * W * 4) + H * W * 32
         fl = 2.0 * B * px * 64 * 1625 if "kconv" in name else 2.0 * B * H * W * 19904
-        cols.append((f"{tag}_satu_chain.ncu-rep", f"{short}, B=17, Vid4 x4", fl, alg, v, u))
-    out = [f"# {tag}: `ncu --set full` captures (one launch each, Vid4 shape 144x180, 17 windows per launch)", "",
-           "Commands: `ncu --set full --import-source on --clock-control none -k regex:bigk -s 2 -c 1 python scripts/profile_conv.py <nsrc> <convs> 17 halo 3 1 [pool] [res]` and",
-           "`ncu --set full --import-source on --clock-control none -k regex:\"kconv_sta|satu_hr\" -c 2 python scripts/quick_perf.py halo 17`", "",
+        cols.append((f"{tag}_satu_chain.ncu-rep", f"{short}, B={B}, Vid4 x4", fl, alg, v, u))
+    out = [f"# {tag}: `ncu --set full` captures (one launch each, Vid4 shape 144x180, {B} windows per launch)", "",
+           f"Commands: `ncu --set full --import-source on --clock-control none -k regex:bigk -s 2 -c 1 python scripts/profile_conv.py <nsrc> <convs> {B} halo 3 1 [pool] [res]` and",
+           f"`ncu --set full --import-source on --clock-control none -k regex:\"kconv_sta|satu_hr\" -c 2 python scripts/quick_perf.py halo {B}`", "",
            "| metric | " + " | ".join(d for _, d, _, _, _, _ in cols) + " |", "|---|" + "---|" * len(cols)]
     for k in R02_KEYS:
         out.append(f"| `{k}` [{cols[0][5].get(k, '')}] | " + " | ".join(c[4].get(k, "-") for c in cols) + " |")
@@ -183,7 +190,7 @@ def r02(tag="r02"):
     sk = [x for x in cols if "satu" in x[1]]
     if sk:
         tot = sum(traffic[x[1]]["dram_bytes"] for x in sk)
-        json.dump({"dram_bytes_per_launch": tot, "dram_bytes_per_frame": tot / B, "launch": "satu_kconv_sta + satu_hr, 17 windows, Vid4 x4",
+        json.dump({"dram_bytes_per_launch": tot, "dram_bytes_per_frame": tot / B, "launch": f"satu_kconv_sta + satu_hr, {B} windows, Vid4 x4",
                    "compulsory_bytes_per_frame": 4.0 * (2 * 64 * px + 3 * px + 3 * H * W), "source": f"profiles/{tag}_kernels_ncu_summary.md ({sk[0][0]})"},
                   open(os.path.join(P, "satu_traffic.json"), "w"), indent=1)
     print("\n".join(out[-14:]))
@@ -193,8 +200,9 @@ if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(P, exist_ok=True)
     if tag != "r01":
-        launches(tag)
-        r02(tag)
+        if os.path.exists(os.path.join(G, f"launches_{tag}_bench.csv")):
+            launches(tag)
+        r02(tag, int(sys.argv[2]) if len(sys.argv) > 2 else 17)
         sys.exit(0)
     launches(tag)
     px = 144 * 180
