@@ -420,6 +420,37 @@ int savsr_satu_hr(savsr_ctx* ctx, savsr_arena* lr, int x_slot, int sta_slot, int
                   const float* zbias, const float* tail_bias, const float* x_in, int t, int centre, float* out,
                   savsr_stream st);
 
+/* ---- the forward as one call -----------------------------------------------------------------------------------------------------
+ * savsr_plan = an ordered list of recorded launches of the entry points above (argument structures copied at record time), replayed on
+ * a stream by savsr_plan_run; savsr_forward adds the copies between the caller's tensors and the plan's staging buffers
+ * (SAVSR.forward, lbasicsr/archs/savsr_arch.py:692-742: x fp32 [batch][7][3][h][w] -> out fp32 [batch][3][H][W]).  A plan is built for one
+ * (batch, h, w, scale) on buffers the caller prepared (arenas, packed weights, SATU tables: savsr_b200/engine.py does it); it owns no device
+ * memory, never synchronises, and its replay is CUDA-graph capturable.  savsr_plan_add_* take the arguments of the corresponding
+ * entry point minus the stream and return 0 / non-zero like everything else. */
+typedef struct savsr_plan savsr_plan;
+int savsr_plan_create(savsr_ctx* ctx, savsr_plan** out);
+void savsr_plan_destroy(savsr_plan* plan);
+int savsr_plan_size(const savsr_plan* plan);                 /* recorded launches */
+int savsr_plan_set_io(savsr_plan* plan, float* x_in, size_t x_bytes, float* out, size_t out_bytes, int format /* enum savsr_format */);
+int savsr_plan_add_pack_frames(savsr_plan* plan, savsr_arena* arena, const float* x, int t, int h, int w, int dst_slot);
+int savsr_plan_add_conv(savsr_plan* plan, savsr_arena* arena, const savsr_conv_group* groups, int ngroups, int ksize, int n_tile,
+                        int dst_mode, int impl);
+int savsr_plan_add_osa_prologue(savsr_plan* plan, const savsr_osa_params* convs, int nconvs, int batch, int npart, int npix,
+                                float inv_scale_h, float inv_scale_w);
+int savsr_plan_add_ca_scale_residual(savsr_plan* plan, savsr_arena* arena, int t_slot, int x_slot, int dst_slot, const float* pool, int npart,
+                                     const float* w1, const float* b1, const float* w2, const float* b2, float* y_scratch);
+int savsr_plan_add_osadapt_mask(savsr_plan* plan, const float* in16, int batch, int height, int width, const float* wa, const float* ba,
+                                const float* wb, const float* bb, const float* wc, const float* bc, float* half0, float* half1, float* mask);
+int savsr_plan_add_satu_kconv_sta(savsr_plan* plan, savsr_arena* arena, int a_slot, int x_slot, int dst_slot, int h, int w, const void* weights,
+                                  const float* bias, float slope);
+int savsr_plan_add_satu_hr(savsr_plan* plan, savsr_arena* lr, int x_slot, int sta_slot, int h, int w, int H, int W, const float* table,
+                           const float* base_y, const float* base_x, const void* weights, const float* zbias, const float* tail_bias,
+                           const float* x_in, int t, int centre, float* out);
+int savsr_plan_add_arena_export(savsr_plan* plan, savsr_arena* arena, int slot, float* nchw);   /* debug taps */
+int savsr_plan_run(savsr_plan* plan, savsr_stream st);
+/* x -> the plan's input staging buffer (device-to-device, skipped when x IS that buffer), replay, output staging buffer -> out. */
+int savsr_forward(savsr_plan* plan, const float* x, float* out, savsr_stream st);
+
 /* ---- post-processing / metrics on the device (next row 8f3) -------------------------------------------------------
  * tensor2img (lbasicsr/utils/img_util.py:38-94): sr fp32 NCHW [batch][3][H][W] RGB -> uint8 HWC BGR [batch][H][W][3]
  * (clamp, *255, round half to even), and, when gt is given, the per-frame sum of squared Y-channel differences of the two

@@ -163,6 +163,20 @@ SIGNATURES = {
     "savsr_mask_backward_train": (_I, [_VP, _VP, C.POINTER(MaskTrain), _I, _I, _I, _I, _I, _I, _VP]),
     "savsr_sta_lrelu_forward": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _F, _VP]),
     "savsr_sta_lrelu_backward": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _F, _VP]),
+    "savsr_plan_create": (_I, [_VP, C.POINTER(_VP)]),
+    "savsr_plan_destroy": (None, [_VP]),
+    "savsr_plan_size": (_I, [_VP]),
+    "savsr_plan_set_io": (_I, [_VP, _VP, _SZ, _VP, _SZ, _I]),
+    "savsr_plan_add_pack_frames": (_I, [_VP, _VP, _VP, _I, _I, _I, _I]),
+    "savsr_plan_add_conv": (_I, [_VP, _VP, C.POINTER(ConvGroup), _I, _I, _I, _I, _I]),
+    "savsr_plan_add_osa_prologue": (_I, [_VP, C.POINTER(OsaParams), _I, _I, _I, _I, _F, _F]),
+    "savsr_plan_add_ca_scale_residual": (_I, [_VP, _VP, _I, _I, _I, _VP, _I, _VP, _VP, _VP, _VP, _VP]),
+    "savsr_plan_add_osadapt_mask": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "savsr_plan_add_satu_kconv_sta": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP, _VP, _F]),
+    "savsr_plan_add_satu_hr": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _VP]),
+    "savsr_plan_add_arena_export": (_I, [_VP, _VP, _I, _VP]),
+    "savsr_plan_run": (_I, [_VP, _VP]),
+    "savsr_forward": (_I, [_VP, _VP, _VP, _VP]),
     "savsr_pack_frames": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "savsr_osa_prologue": (_I, [_VP, C.POINTER(OsaParams), _I, _I, _I, _I, _F, _F, _VP]),
     "savsr_ca_scale_residual": (_I, [_VP, _VP, _I, _I, _I, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
@@ -252,6 +266,27 @@ class Arena:
         try:
             if getattr(self, "handle", None):
                 self.lib.savsr_arena_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class CPlan:
+    """savsr_plan wrapper: the recorded launch list of one forward, replayed by one C call."""
+
+    def __init__(self, ctx: Context):
+        self.lib = ctx.lib
+        h = C.c_void_p()
+        check(self.lib.savsr_plan_create(ctx.handle, C.byref(h)))
+        self.handle = h
+
+    def __len__(self) -> int:
+        return int(self.lib.savsr_plan_size(self.handle))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.savsr_plan_destroy(self.handle)
                 self.handle = None
         except Exception:
             pass

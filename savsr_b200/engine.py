@@ -170,9 +170,17 @@ class Plan:
         self.nbytes = 0                          # device memory owned by this plan (arenas, scratch, I/O staging)
         self._pool_cache: Dict[str, int] = {}
         self._osa_cache: Dict[str, Tuple[K.OsaParams, int, int]] = {}
+        self.cplan: Optional[K.CPlan] = K.CPlan(self.ctx) if hasattr(K, "CPlan") and hasattr(self.lib, "savsr_plan_create") else None
+        self._recorded = 0
         with torch.cuda.device(device), torch.no_grad():
             self.ctx.set_format(self.fmt)
             self._build()
+            if self.cplan is not None:
+                if self._recorded == len(self.ops):
+                    K.check(self.lib.savsr_plan_set_io(self.cplan.handle, self.x_in.data_ptr(), self.x_in.numel() * 4, self.out.data_ptr(),
+                                                       self.out.numel() * 4, self.fmt))
+                else:
+                    self.cplan = None                       # an op without a C-side record: keep the Python loop
 
     # ------------------------------------------------------------------ memory helpers
     def _buf(self, *shape, dtype=torch.float32) -> torch.Tensor:
@@ -219,10 +227,15 @@ class Plan:
 
     # ------------------------------------------------------------------ op emitters
     def _emit(self, fn: Callable[[int], int], launches: int = 1, kind: str = "other", flops: float = 0.0,
-              detail: str = "") -> None:
+              detail: str = "", rec: Optional[Callable[[object], int]] = None) -> None:
+        """Append one op to the launch list.  `rec` records the same launch into the C-side plan (savsr_plan), which replays the whole
+        list with one call (savsr_plan_run / savsr_forward); the Python closures stay for per-op timing and debugging."""
         self.ops.append(fn)
         self.op_meta.append((kind, flops, launches, detail))
         self.n_launches += launches
+        if rec is not None and self.cplan is not None:
+            K.check(rec(self.cplan.handle))
+            self._recorded += 1
 
     def _group(self, src: Sequence[int], dst: int, weight: int, bias: int = 0, act: int = K.ACT_NONE, slope: float = 0.2,
                res1: int = -1, res2: int = -1, res2_scale: float = 0.0, wstride: int = 0, mask: int = 0, pool: int = 0,
@@ -253,7 +266,8 @@ class Plan:
         osa = any(g.weight_sample_stride != 0 for g in groups)
         self._emit(lambda st: lib.savsr_conv(ctx, ah, arr, n, ksize, n_tile, dst_mode, impl, st),
                    kind=kind or f"conv{ksize}x{ksize}_n{n_tile}", flops=flops,
-                   detail=f"g{n}s{groups[0].nsrc}" + ("osa" if osa else ""))
+                   detail=f"g{n}s{groups[0].nsrc}" + ("osa" if osa else ""),
+                   rec=lambda cp: lib.savsr_plan_add_conv(cp, ah, arr, n, ksize, n_tile, dst_mode, impl))
 
     def _tap(self, name: str, arena: str, slot: int) -> None:
         """Test/debug hook: if `name` was requested in `taps`, snapshot the slot (fp32 NCHW) right here in the
@@ -264,7 +278,7 @@ class Plan:
         buf = self._buf(self.B, 64, a.height, a.width)
         self.tap_bufs[name] = buf
         lib, ah, ptr = self.lib, a.handle, buf.data_ptr()
-        self._emit(lambda st: lib.savsr_arena_export(ah, slot, ptr, st), kind="debug_tap")
+        self._emit(lambda st: lib.savsr_arena_export(ah, slot, ptr, st), kind="debug_tap", rec=lambda cp: lib.savsr_plan_add_arena_export(cp, ah, slot, ptr))
 
     def _osa_params(self, prefix: str, nsrc: int, pools: Sequence[int]) -> Tuple[K.OsaParams, int, int]:
         if prefix in self._osa_cache:
@@ -304,7 +318,8 @@ class Plan:
         inv_w = float(np.float32(1.0) / np.float32(self.scale[1]))
         lib, ctx, n, B = self.lib, self.ctx.handle, len(convs), self.B
         npart, npix = self.lr.tiles * 4, self.hp * self.wp
-        self._emit(lambda st: lib.savsr_osa_prologue(ctx, arr, n, B, npart, npix, inv_h, inv_w, st), launches=4, kind="osa_prologue")
+        self._emit(lambda st: lib.savsr_osa_prologue(ctx, arr, n, B, npart, npix, inv_h, inv_w, st), launches=4, kind="osa_prologue",
+                   rec=lambda cp: lib.savsr_plan_add_osa_prologue(cp, arr, n, B, npart, npix, inv_h, inv_w))
 
     def _pool(self, key: str) -> int:
         """Partial-sum buffer [B][tiles*4][64] written by a conv epilogue (cached per producing conv)."""
@@ -370,7 +385,8 @@ class Plan:
 
         # ---- 1. bi-directional propagation (savsr_arch.py:703-719), both directions per launch
         lrh0, hh0, ww0 = lr.handle, self.h, self.w
-        self._emit(lambda st: lib.savsr_pack_frames(ctx, lrh0, xin, t, hh0, ww0, FR, st), kind="pack_frames")
+        self._emit(lambda st: lib.savsr_pack_frames(ctx, lrh0, xin, t, hh0, ww0, FR, st), kind="pack_frames",
+                   rec=lambda cp: lib.savsr_plan_add_pack_frames(cp, lrh0, xin, t, hh0, ww0, FR))
         hpast = [zero, zero]
         for idx in range(n_it):
             centre = [t - 1 - 1 - idx, idx + 1]                     # f2p walks back, p2f forward
@@ -454,7 +470,9 @@ class Plan:
                 w2, b2 = self._ptr(pr + ".3.attention.3.weight"), self._ptr(pr + ".3.attention.3.bias")
                 self._emit(lambda st, x=x, xa=xa, pl=pl, w1=w1, b1=b1, w2=w2, b2=b2:
                            lib.savsr_ca_scale_residual(ctx, lrh, T2, x, xa, pl, npart, w1, b1, w2, b2, ca_y, st),
-                           launches=2, kind="ca_scale_residual")
+                           launches=2, kind="ca_scale_residual",
+                           rec=lambda cp, x=x, xa=xa, pl=pl, w1=w1, b1=b1, w2=w2, b2=b2:
+                           lib.savsr_plan_add_ca_scale_residual(cp, lrh, T2, x, xa, pl, npart, w1, b1, w2, b2, ca_y))
                 x, xa, xb = xa, xb, xa
             plr = self._pool(f"RG.{gi}.conv")
             self._conv(lr, [self._group([x], R, self._packp(f"RG.{gi}.conv.weight"), self._ptr(f"RG.{gi}.conv.bias"),
@@ -479,7 +497,8 @@ class Plan:
             args = (ctx, in16.data_ptr(), B, self.hp, self.wp, self._dev(m + ".4+bn.w", wa), self._dev(m + ".4+bn.b", ba),
                     self._dev(m + ".7+bn.w", wb), self._dev(m + ".7+bn.b", bb), self._dev(m + ".11+bn.w", wc), self._dev(m + ".11+bn.b", bc),
                     half0.data_ptr(), half1.data_ptr(), maskb.data_ptr())
-            self._emit(lambda st, args=args: lib.savsr_osadapt_mask(*args, st), launches=3, kind="osadapt_mask")
+            self._emit(lambda st, args=args: lib.savsr_osadapt_mask(*args, st), launches=3, kind="osadapt_mask",
+                       rec=lambda cp, args=args: lib.savsr_plan_add_osadapt_mask(cp, *args[1:]))
             osa = self._osa_params(pa + ".adapt", 1, [plr])
             self._osa_prologue([osa[0]])
             self._conv(lr, [self._group([R], Hs, osa[1], wstride=osa[2], mask=maskb.data_ptr(), res1=R, res2=A, res2_scale=gamma)])
@@ -499,7 +518,7 @@ class Plan:
         # kernel_conv + sta_conv in one kernel: the 25 per-pixel kernels stay in TMEM (savsr_arch.py:297-313, 326)
         kflops = 2.0 * B * self.hp * self.wp * 64 * 1600
         self._emit(lambda st: lib.savsr_satu_kconv_sta(ctx, lrh, A, TR, STA, hh, ww, wkp, bkp, 0.1, st), kind="satu_kconv_sta",
-                   flops=kflops)
+                   flops=kflops, rec=lambda cp: lib.savsr_plan_add_satu_kconv_sta(cp, lrh, A, TR, STA, hh, ww, wkp, bkp, 0.1))
         self._tap("satu_sta", "lr", STA)
         sw = K.SatuWeights()
         sw.body0_w, sw.body0_b = self._ptr(u + ".body.0.weight"), self._ptr(u + ".body.0.bias")
@@ -530,7 +549,8 @@ class Plan:
         hwp, outp, cen = hw.data_ptr(), self.out.data_ptr(), t // 2
         hr_flops = 2.0 * B * self.H * self.W * (64 * 32 + 32 * 64 + 128 * 64 + 64 * 3 * 9)      # compress, expand, fusion, tail (reference counts)
         self._emit(lambda st: lib.savsr_satu_hr(ctx, lrh, TR, STA, hh, ww, H, W, tab, by, bx, hwp, zb, tb, xin, t, cen, outp, st),
-                   kind="satu_hr", flops=hr_flops)
+                   kind="satu_hr", flops=hr_flops,
+                   rec=lambda cp: lib.savsr_plan_add_satu_hr(cp, lrh, TR, STA, hh, ww, H, W, tab, by, bx, hwp, zb, tb, xin, t, cen, outp))
         # declared traffic beyond the compulsory SATU bytes (per sample): only the 16-bit sta intermediate (written by kconv_sta, read here)
         self.satu_extra_bytes_per_sample = 2 * 64 * self.hp * self.wp * 2
         self._stream().synchronize()
@@ -547,6 +567,9 @@ class Plan:
         with torch.cuda.device(self.device):
             self.ctx.set_format(self.fmt)           # the format is context state read at launch (baked into captured graphs)
             st = self._stream().cuda_stream
+            if self.cplan is not None:              # the whole list in one C call (savsr_plan_run)
+                K.check(self.lib.savsr_plan_run(self.cplan.handle, st))
+                return
             for op in self.ops:
                 rc = op(st)
                 if rc:
@@ -635,9 +658,22 @@ class Plan:
                 self.run()
             out.copy_(self.out, non_blocking=True)
 
+    def forward_c(self, x: torch.Tensor, out: torch.Tensor) -> None:
+        """x [B,7,3,h,w] fp32 -> out [B,3,H,W] fp32 through ONE C call (savsr_forward: staging copies + the recorded launch list), eagerly on the
+        device's current stream -- what a non-Python host would call."""
+        if self.cplan is None:
+            raise K.SavsrError("this plan has no C-side launch list")
+        if not (x.is_cuda and out.is_cuda and x.is_contiguous() and out.is_contiguous() and x.dtype == out.dtype == torch.float32):
+            raise ValueError("savsr_forward takes contiguous fp32 CUDA tensors")
+        if tuple(x.shape) != tuple(self.x_in.shape) or tuple(out.shape) != tuple(self.out.shape):
+            raise ValueError(f"plan built for {tuple(self.x_in.shape)} -> {tuple(self.out.shape)}, got {tuple(x.shape)} -> {tuple(out.shape)}")
+        with torch.cuda.device(self.device):
+            K.check(self.lib.savsr_forward(self.cplan.handle, x.data_ptr(), out.data_ptr(), self._stream().cuda_stream))
+
     def release(self) -> None:
         """Drop the CUDA graph and every device buffer now (plan-cache eviction), instead of waiting for the collector."""
         self.graph = None
+        self.cplan = None
         self.ops.clear()
         self._keep.clear()
         self._pack_src.clear()

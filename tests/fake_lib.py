@@ -79,5 +79,6 @@ class CpuPlan(engine.Plan):
         self.taps, self.tap_bufs, self.graph = set(kw.get("taps", ())), {}, None
         self._pool_cache, self._osa_cache = {}, {}
         self.store, self.nbytes, self._pack_src = kw.get("store") or engine.WeightStore(), 0, []
+        self.cplan, self._recorded = None, 0            # (the C-side launch list is exercised on the GPU: tests/gpu_checks.check_c_plan)
         with torch.no_grad():
             orig_build()

@@ -908,6 +908,32 @@ def check_trainplan(b=2, h=16, w=20, scale=(2, 2), seed=0, tol_worst=0.10, tol_c
     return info
 
 
+def check_c_plan(b=2, h=13, w=15, scale=(1.5, 4), seed=2):
+    """savsr_forward / savsr_plan_run (the recorded launch list replayed by one C call) against the same launches issued one by one from
+    Python: bit-identical output, and the plan holds one record per op."""
+    import savsr_b200
+    from oracle.state_dict_fixture import make_input, make_state_dict
+    net = savsr_b200.SAVSR().to(DEV).eval()
+    net.load_state_dict(make_state_dict(seed), strict=True)
+    net.set_scale(scale)
+    x = make_input(b, h, w, 1234 + seed).to(DEV)
+    with torch.no_grad():
+        plan = net.plan_for(x)
+        assert plan.cplan is not None and len(plan.cplan) == len(plan.ops), (len(plan.ops), plan.cplan)
+        plan.x_in.copy_(x)
+        st = torch.cuda.current_stream().cuda_stream
+        for op in plan.ops:                         # the Python loop
+            rc = op(st)
+            assert not rc, rc
+        ref = plan.out.clone()
+        plan.out.zero_()
+        out = torch.empty_like(ref)
+        plan.forward_c(x.contiguous(), out)         # one C call
+        torch.cuda.synchronize()
+    assert torch.equal(out, ref), float((out - ref).abs().max())
+    return dict(ops=len(plan.ops), shape=tuple(out.shape))
+
+
 def check_img_metrics(n=3, H=37, W=53, seed=31):
     """tensor2img (bit-exact uint8 BGR) and PSNR-Y on the device vs the oracle's restatement of the reference metric chain."""
     from oracle import savsr_oracle as O

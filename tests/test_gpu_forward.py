@@ -248,3 +248,9 @@ def test_native_training_steps_reduce_the_loss(G, graph):
     """Pack -> forward -> backward -> Adam + EMA for a few steps on a fixed batch, eagerly and as replayed CUDA graphs."""
     info = G.check_trainplan(steps=4, graph=graph)
     print(info["losses"])
+
+
+@pytest.mark.gpu
+def test_forward_as_one_c_call(G):
+    """`savsr_forward(plan, x, out, stream)` -- the recorded launch list of the plan replayed by one C call."""
+    print(G.check_c_plan())
