@@ -238,6 +238,16 @@ class SAVSR(nn.Module):
         with torch.cuda.device(plan.device):
             out = torch.empty_like(plan.out)
             plan.forward_into(x, out, graph=self.use_graph)
+            if self.precision == "fp16" and not plan.__dict__.get("_range_checked"):
+                # fp16 operands meet the <= 1e-3 bound but saturate at 65504: look at every trunk activation of this plan's FIRST forward
+                # (one pass over the arena, once per plan) and refuse to continue silently when the headroom is below 4x
+                plan._range_checked = True
+                peak = plan.activation_absmax()
+                self.fp16_peak_activation = max(getattr(self, "fp16_peak_activation", 0.0), peak)
+                if not peak < 65504.0 / 4:
+                    raise FloatingPointError(
+                        f"precision='fp16': the largest trunk activation of this input is {peak:.4g} (fp16 saturates at 65504); "
+                        "use precision='bf16' (same speed, fp32 range) for these weights")
         return out
 
     # ---- plan management ---------------------------------------------------------------------------

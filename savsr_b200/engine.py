@@ -376,7 +376,7 @@ class Plan:
             pool_free.append(sl.get())
         self.n_lr_slots = sl.n
         self.arena_lr_t = self._buf(self.n_lr_slots * B, self.hp, self.wp, 64, dtype=torch.bfloat16)
-        self.arena_lr_t[zero * B:(zero + 1) * B].zero_()
+        self.arena_lr_t.zero_()                  # the zero slot must be zero; the rest so that activation_absmax never reads stale memory
         self.lr = K.Arena(self.ctx, self.arena_lr_t.data_ptr(), self.n_lr_slots, B, self.hp, self.wp)
         lr = self.lr
         self.x_in = self._buf(B, t, 3, self.h, self.w)
@@ -657,6 +657,14 @@ class Plan:
             else:
                 self.run()
             out.copy_(self.out, non_blocking=True)
+
+    def activation_absmax(self) -> float:
+        """Largest |value| currently held anywhere in the LR arena (every trunk activation of the last forward), read in the plan's
+        16-bit format.  For the fp16 path: its distance from 65504 is the headroom of that input (SAVSR.forward checks it once per plan)."""
+        dt = torch.float16 if self.fmt == K.FMT_FP16 else torch.bfloat16
+        with torch.cuda.device(self.device):
+            peak = float(torch.linalg.vector_norm(self.arena_lr_t.view(dt).reshape(-1), ord=float("inf")))      # one reduction pass, no temporary
+            return peak if peak == peak else float("inf")                                                          # NaN counts as overflow
 
     def forward_c(self, x: torch.Tensor, out: torch.Tensor) -> None:
         """x [B,7,3,h,w] fp32 -> out [B,3,H,W] fp32 through ONE C call (savsr_forward: staging copies + the recorded launch list), eagerly on the

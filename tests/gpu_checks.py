@@ -908,6 +908,32 @@ def check_trainplan(b=2, h=16, w=20, scale=(2, 2), seed=0, tol_worst=0.10, tol_c
     return info
 
 
+def check_fp16_range_guard(seed=0):
+    """precision='fp16': the first forward of a plan measures the largest trunk activation; an input that drives it beyond a quarter of the
+    fp16 range raises instead of returning saturated values (bf16 handles the same input)."""
+    import savsr_b200
+    from oracle.state_dict_fixture import make_input, make_state_dict
+    net = savsr_b200.SAVSR().to(DEV).eval()
+    net.load_state_dict(make_state_dict(seed), strict=True)
+    net.set_scale((2, 2))
+    net.precision = "fp16"
+    x = make_input(1, 16, 20, 1234 + seed).to(DEV)
+    with torch.no_grad():
+        y = net(x)
+        peak = net.fp16_peak_activation
+        assert torch.isfinite(y).all() and 0 < peak < 65504 / 4, ("peak", peak)
+        big = x * (4 * 65504 / peak)                   # the trunk is roughly homogeneous in its input: this overshoots the guard
+        raised = False
+        try:
+            net(big[:, :, :, :14, :18].contiguous())   # a new plan (another size), so the check runs again
+        except FloatingPointError:
+            raised = True
+        assert raised, ("not raised", net.fp16_peak_activation)
+        net.precision = "bf16"
+        net(big[:, :, :, :14, :18].contiguous())       # the guard belongs to the fp16 path only
+    return dict(peak_unit_input=peak)
+
+
 def check_c_plan(b=2, h=13, w=15, scale=(1.5, 4), seed=2):
     """savsr_forward / savsr_plan_run (the recorded launch list replayed by one C call) against the same launches issued one by one from
     Python: bit-identical output, and the plan holds one record per op."""

@@ -254,3 +254,9 @@ def test_native_training_steps_reduce_the_loss(G, graph):
 def test_forward_as_one_c_call(G):
     """`savsr_forward(plan, x, out, stream)` -- the recorded launch list of the plan replayed by one C call."""
     print(G.check_c_plan())
+
+
+@pytest.mark.gpu
+def test_fp16_path_refuses_to_saturate(G):
+    """The criterion-meeting fp16 path has 65504 of range: SAVSR.forward measures the headroom once per plan and raises below 4x."""
+    print(G.check_fp16_range_guard())
