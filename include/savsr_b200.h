@@ -101,7 +101,10 @@ typedef struct savsr_conv_group {
 enum savsr_option {
   SAVSR_OPT_BIGK_ALL = 0,     /* 1 (default): every 3x3 HALO N=64 conv runs on the batched dual-issuer kernel; 0: only K > 18 blocks */
   SAVSR_OPT_BIGK_ISSUERS = 1, /* MMA-issuing warps of that kernel: 2 (default) or 1                                                  */
-  SAVSR_OPT_COUNT = 2
+  SAVSR_OPT_PDL = 2,          /* 1: launch with programmatic stream serialization (the next kernel's CTAs start while this one drains and
+                                 block in griddepcontrol.wait before touching memory); pays for chains of microsecond-sized launches
+                                 (training at 4 x 64 x 64), not for long ones.  Default 0                                                */
+  SAVSR_OPT_COUNT = 3
 };
 
 /* ---- library / context ------------------------------------------------------------------- */

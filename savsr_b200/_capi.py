@@ -22,7 +22,7 @@ IMPL_TAP, IMPL_HALO, IMPL_CHECK = 0, 1, 2
 IMPL_NAMES = {"tap": IMPL_TAP, "halo": IMPL_HALO, "check": IMPL_CHECK}
 FMT_BF16, FMT_FP16 = 0, 1
 FMT_NAMES = {"bf16": FMT_BF16, "fp16": FMT_FP16}
-OPT_BIGK_ALL, OPT_BIGK_ISSUERS = 0, 1   # enum savsr_option
+OPT_BIGK_ALL, OPT_BIGK_ISSUERS, OPT_PDL = 0, 1, 2   # enum savsr_option
 WGRAD_OIHW, WGRAD_TIO = 0, 1     # enum savsr_wgrad_layout
 ROWS_LINEAR, ROWS_QUAD = 0, 1     # enum savsr_row_order: QUAD for everything savsr_conv / savsr_satu_kconv_sta consume with n_tile 64
 

@@ -91,6 +91,7 @@ extern "C" int savsr_ctx_set_option(savsr_ctx* ctx, int option, int value) {
   SAVSR_REQUIRE(option >= 0 && option < SAVSR_OPT_COUNT, "savsr_ctx_set_option: unknown option %d", option);
   if (option == SAVSR_OPT_BIGK_ALL) SAVSR_REQUIRE(value == 0 || value == 1, "savsr_ctx_set_option: BIGK_ALL must be 0 or 1, got %d", value);
   if (option == SAVSR_OPT_BIGK_ISSUERS) SAVSR_REQUIRE(value == 1 || value == 2, "savsr_ctx_set_option: BIGK_ISSUERS must be 1 or 2, got %d", value);
+  if (option == SAVSR_OPT_PDL) SAVSR_REQUIRE(value == 0 || value == 1, "savsr_ctx_set_option: PDL must be 0 or 1, got %d", value);
   ctx->opt[option] = value;
   return 0;
 }

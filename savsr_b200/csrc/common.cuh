@@ -62,6 +62,18 @@ inline int ensure_smem_attr(savsr_ctx* ctx, int bit, F func, size_t bytes) {
   ctx->attr_mask |= 1u << bit;
   return 0;
 }
+// Kernel launch with optional programmatic dependent launch (SAVSR_OPT_PDL): the kernel must call pdl_wait() before its first access to
+// memory a previous kernel may have written, and may call pdl_trigger() after it.
+template <class... KArgs, class... Args>
+inline cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 // Launch on the context's device whatever the caller's current device is; restores it on scope exit.  cudaSetDevice is called
 // even when the device already matches: it also binds the primary context to the calling THREAD, which a fresh thread (e.g.
 // autograd's backward worker) does not have yet -- the driver entry points (cuTensorMapEncodeTiled) fail with
@@ -140,6 +152,10 @@ __device__ __forceinline__ void named_barrier(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// Programmatic dependent launch: block until the preceding kernel of the stream has completed and its writes are visible (a no-op when
+// the kernel was launched normally); then allow the next kernel's CTAs to be scheduled as this grid's CTAs retire.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

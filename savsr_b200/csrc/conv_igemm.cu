@@ -759,6 +759,8 @@ __global__ void __launch_bounds__(kBigkThreads, 1) conv_igemm_bigk_kernel(const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();        // everything above touched only this CTA's own state; from here on the previous kernel's results are read
+  pdl_trigger();
 
   // every role walks the same sequence of batches: up to 4 consecutive tiles of one (conv, sample)
   int item = item_begin;
@@ -1113,8 +1115,7 @@ static int launch_conv(savsr_ctx* ctx, ConvParams& p, int impl, cudaStream_t st)
       if (int rc = ensure_smem_attr(ctx, kAttrBigk, conv_igemm_bigk_kernel, smem)) return rc;
       p.chunk = (total + ctx->sm_count - 1) / ctx->sm_count;
       const int grid = (total + p.chunk - 1) / p.chunk;
-      conv_igemm_bigk_kernel<<<grid, kBigkThreads, smem, st>>>(p);
-      SAVSR_CUDA(cudaGetLastError());
+      SAVSR_CUDA(launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, conv_igemm_bigk_kernel, dim3(grid), dim3(kBigkThreads), smem, st, p));
       return 0;
     }
   }

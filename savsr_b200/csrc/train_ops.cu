@@ -34,6 +34,8 @@ __device__ __forceinline__ uint32_t axpby_word(uint32_t a, uint32_t b, float alp
 }
 
 __global__ void __launch_bounds__(256) slot_axpby_kernel(const __grid_constant__ AxpbyLaunch L) {
+  pdl_wait();
+  pdl_trigger();
   const savsr_axpby& e = L.e[blockIdx.y];
   const uint4* x = reinterpret_cast<const uint4*>(L.arena) + e.x_slot * L.slot_vecs;
   const uint4* y = e.y_slot >= 0 ? reinterpret_cast<const uint4*>(L.arena) + e.y_slot * L.slot_vecs : nullptr;
@@ -81,6 +83,8 @@ __device__ __forceinline__ void store_plane_pair(uint16_t* plane_row0, long plan
 
 __global__ void __launch_bounds__(256) grad_prep_kernel(const __grid_constant__ GradPrepLaunch L) {
   __shared__ uint32_t tile[kTileWords];
+  pdl_wait();
+  pdl_trigger();
   const savsr_grad_prep_entry& e = L.e[blockIdx.z];
   const int y = blockIdx.x, n = blockIdx.y, t = threadIdx.x, fmt = L.fmt;
   const long row_elems = static_cast<long>(L.width) * kC;
@@ -471,8 +475,7 @@ extern "C" int savsr_slot_axpby(savsr_ctx* ctx, savsr_arena* arena, const savsr_
   }
   long blocks = (L.slot_vecs + 255) / 256;
   if (blocks > 4 * ctx->sm_count) blocks = 4 * ctx->sm_count;
-  slot_axpby_kernel<<<dim3(static_cast<unsigned>(blocks), n), 256, 0, static_cast<cudaStream_t>(st)>>>(L);
-  SAVSR_CUDA(cudaGetLastError());
+  SAVSR_CUDA(launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, slot_axpby_kernel, dim3(static_cast<unsigned>(blocks), n), dim3(256), 0, static_cast<cudaStream_t>(st), L));
   return 0;
 }
 
@@ -502,8 +505,7 @@ extern "C" int savsr_grad_prep(savsr_ctx* ctx, savsr_arena* arena, void* tbase, 
     L.e[i] = e;
   }
   if (any_t) if (int rc = check_tarena("savsr_grad_prep", arena, tbase, pitch)) return rc;
-  grad_prep_kernel<<<dim3(arena->height, arena->batch, n), 256, 0, static_cast<cudaStream_t>(st)>>>(L);
-  SAVSR_CUDA(cudaGetLastError());
+  SAVSR_CUDA(launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, grad_prep_kernel, dim3(arena->height, arena->batch, n), dim3(256), 0, static_cast<cudaStream_t>(st), L));
   return 0;
 }
 

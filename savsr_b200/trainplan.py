@@ -34,7 +34,7 @@ import torch.nn.functional as F
 
 from . import _capi as K
 from . import train as T
-from .engine import context, get_hw, normalize_scale
+from .engine import context, get_hw, normalize_scale, pdl
 
 L_ACT = K.ACT_LRELU
 CHUNK3 = 9 * 8192          # bytes of the nine [64][64] 16-bit blocks of one (64 x 64 channel) filter corner
@@ -1022,7 +1022,7 @@ class TrainPlan:
     # ------------------------------------------------------------------ execution
     def run_forward_native(self, join: bool) -> None:
         """Every forward op except the SATU island, plus (on a side stream) the x-shifted NCHW copies the weight gradient needs."""
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), pdl(self.ctx, True):
             self.ctx.set_format(self.fmt)
             main = torch.cuda.current_stream(self.device)
             st = main.cuda_stream
@@ -1055,7 +1055,7 @@ class TrainPlan:
 
     def run_backward_island(self, dsr: Optional[torch.Tensor] = None) -> None:
         """Backward of the SATU island (autograd) and the import of its input gradients into arena slots."""
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), pdl(self.ctx, True):
             self.ctx.set_format(self.fmt)
             st = torch.cuda.current_stream(self.device).cuda_stream
             self.dsr = dsr
@@ -1065,7 +1065,7 @@ class TrainPlan:
 
     def run_backward_native(self) -> None:
         """Every other backward op: pure launches on fixed buffers (graph-capturable without any autograd inside)."""
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), pdl(self.ctx, True):
             self.ctx.set_format(self.fmt)
             st = torch.cuda.current_stream(self.device).cuda_stream
             for op in self.bwd_ops[self.n_bwd_island:]:

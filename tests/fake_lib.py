@@ -36,7 +36,7 @@ class FakeArena:
 @contextlib.contextmanager
 def mocked_engine():
     lib = FakeLib()
-    ctx = SimpleNamespace(lib=lib, handle="ctx", sm_count=148, set_format=lambda f: None)
+    ctx = SimpleNamespace(lib=lib, handle="ctx", sm_count=148, set_format=lambda f: None, set_option=lambda o, v: None)
     saved = (engine.context, K.Arena, K.check, torch.cuda.current_stream, torch.cuda.device, torch.cuda.Stream, torch.cuda.stream)
     engine.context = lambda idx: ctx
     K.Arena = FakeArena
