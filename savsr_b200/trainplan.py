@@ -4,8 +4,8 @@ The reference trains through autograd: forward, Charbonnier, backward through cu
 (lbasicsr/models/sr_model.py:101-128, asvsr_model.py:21-29, losses/basic_loss.py:22-24, base_model.py:75-82).  ``TrainPlan`` is
 the same step as a STATIC LAUNCH LIST, the way ``engine.Plan`` is for inference: activations AND their gradients live in one
 16-bit NHWC arena, every 3x3 / 1x1 convolution of the trunk runs forward, data gradient and weight gradient on the tcgen05
-kernels without any layout conversion in between, and the whole step (forward, loss, backward, optimizer) is replayed as one
-CUDA graph per scale.
+kernels without any layout conversion in between, and the whole step (forward, loss, backward, optimizer) is replayed as CUDA
+graphs, one per scale.
 
   forward   the grouped implicit-GEMM launches of the inference plan (both propagation directions x 3 / 5 streams per launch),
             every activation kept (no slot recycling)
@@ -19,9 +19,14 @@ CUDA graph per scale.
             master copy; Adam + EMA is one kernel over the flat buffers (savsr_adam_ema); data parallelism = one NCCL all-reduce
             of the flat gradient buffer.
 
-Still on the ATen autograd tape, as small "islands" between native launches (their inputs / outputs cross as fp32 tensors):
-the scale-attention MLP of OSA-Conv with its train-mode BatchNorm (tensors of [B, <=640]), the 64->4->64 channel-attention MLP,
-the OSAdapt mask net, and SATU + tail + loss.  No CPU path.
+  attention OSA-Conv's prologue (pooled means -> scale_routing -> ScaleAttention with BatchNorm on batch statistics -> folded per-sample kernels)
+            and its whole backward, the RCAB channel attention, the OSAdapt mask net + combination: native (train_attn.cu, train_mask.cu)
+
+Still on the ATen autograd tape, as ONE "island" between native launches (its inputs / outputs cross as fp32 tensors): SATU at HR resolution
+(coordinate MLP, the two gathers, routed experts, fusion), the tail, the bilinear skip and the loss; SATU's per-pixel dynamic filter is a
+native op inside it (autograd.sta_lrelu).  `native_attn=False` / `native_mask=False` run the attention MLPs / the mask net as islands too
+(cross-checks).  Two ways in: NativeTrainer (the whole step: forward + loss + backward as one CUDA graph per scale, the optimizer as another)
+and ModuleTraining (SAVSR.forward in train mode = one autograd node; the caller's loss / optimizer / DDP).  No CPU path.
 """
 from __future__ import annotations
 
@@ -588,7 +593,6 @@ class TrainPlan:
                 (inline if sp.osa is not None else self.deferred).append(len(self.witems) - 1)
         if inline:
             self._x3([self._wsrc[i] for i in inline])
-            self._inline_ranges.append((inline[0], len(inline)))
             assert inline == list(range(inline[0], inline[0] + len(inline)))
             first, count = inline[0], len(inline)
             self._wgrad_launch(first, count)
@@ -888,7 +892,6 @@ class TrainPlan:
         lib, ctx = self.lib, self.ctx.handle
         new = self._new_slot
         self._wsrc: List[int] = []
-        self._inline_ranges: List[Tuple[int, int]] = []
         self._keep_step: List[torch.Tensor] = []
         tiles = ((self.w + K.TILE_W - 1) // K.TILE_W) * ((self.h + K.TILE_H - 1) // K.TILE_H)
         self.npart = tiles * 4
@@ -1198,13 +1201,10 @@ class NativeTrainer:
                     loss = self._fwd_bwd(plan)
                 ent = self._graphs[key] = (g, loss)
                 if self._opt_graph is None:
-                    snap = [t.clone() for t in (self.flat.p, self.flat.m, self.flat.v, self.flat.step_t)]
-                    esnap = self.flat.ema.clone() if self.flat.ema is not None else None
                     og = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(og, stream=torch.cuda.Stream(dev)):
                         self._optim()
-                    self._opt_graph = og                      # capture does not execute; nothing to roll back, snapshots kept for clarity
-                    del snap, esnap
+                    self._opt_graph = og                      # (capture does not execute: nothing to roll back)
             g, loss = ent
             g.replay()
             self._allreduce()
