@@ -404,6 +404,7 @@ def run_train(args, rank, world, local_rank):
     torch.manual_seed(0)
     net = savsr_b200.SAVSR().to(dev)
     native = args.train_engine == "native"
+    torch.backends.cudnn.benchmark = os.environ.get("SAVSR_BENCH_CUDNN_BENCHMARK", "1") != "0"      # lbasicsr/train.py sets it; the ATen island's convs use it
     if native:
         # stage B: the static launch list of savsr_b200/trainplan.py (arena-resident forward / dgrad / batched wgrad, native attention
         # backward, flat Adam + EMA), one CUDA graph per scale; data parallelism = one NCCL all-reduce of the flat gradient buffer
