@@ -52,6 +52,8 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 // grid (nsrc_max, batch, nconvs), 1024 threads = 16 partial ranges x 64 channels.
 constexpr int kOsaThreads = 1024;
 __global__ void __launch_bounds__(kOsaThreads) osa_pool_kernel(const __grid_constant__ OsaLaunch L) {
+  pdl_wait();
+  pdl_trigger();
   const savsr_osa_params& c = L.c[blockIdx.z];
   const int s = blockIdx.x, n = blockIdx.y;
   if (s * 64 >= c.ci) return;
@@ -79,6 +81,8 @@ __global__ void __launch_bounds__(kOsaThreads) osa_pool_kernel(const __grid_cons
 // shared memory and the row's weights sit in registers, so each weight is fetched once and every sample costs one
 // shared-memory dot product + shuffle reduction.
 __global__ void __launch_bounds__(256) osa_linear_kernel(const __grid_constant__ OsaLaunch L, int layer) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float s_in[];   // [batch][len]
   const savsr_osa_params& c = L.c[blockIdx.y];
   const int rows = layer == 0 ? 2 * c.ci : c.ci;
@@ -232,6 +236,8 @@ struct CaParams {
 };
 // y = sigmoid(W2 relu(W1 mean(t) + b1) + b2) per sample (savsr_arch.py:514-519).  grid (batch), 1024 threads.
 __global__ void __launch_bounds__(1024) ca_vector_kernel(const CaParams p) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[16][64];
   __shared__ float mean[64];
   __shared__ float hid[4];
@@ -266,6 +272,8 @@ __global__ void __launch_bounds__(1024) ca_vector_kernel(const CaParams p) {
 }
 // dst = x + t * y (savsr_arch.py:524, 547-549), streamed as 16-byte chunks.  grid (blocks, batch), 256 threads.
 __global__ void __launch_bounds__(256) ca_scale_residual_kernel(const CaParams p) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float ys[64];
   const int n = blockIdx.y;
   if (threadIdx.x < 64) ys[threadIdx.x] = p.y[n * 64 + threadIdx.x];
@@ -561,15 +569,15 @@ int osa_prologue_front(savsr_ctx* ctx, const savsr_osa_params* convs, int nconvs
   L.nconvs = nconvs; L.batch = batch; L.npart = npart; L.npix = npix;
   L.inv_h = inv_scale_h; L.inv_w = inv_scale_w;
   L.fmt = ctx->fmt;
-  osa_pool_kernel<<<dim3(max_ci / 64, batch, nconvs), kOsaThreads, 0, st>>>(L);
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, osa_pool_kernel, dim3(max_ci / 64, batch, nconvs), dim3(kOsaThreads), 0, st, L);
   const int lin_split = batch >= 12 ? 3 : (batch >= 4 ? 2 : 1);
   const size_t lin_smem = static_cast<size_t>((batch + lin_split - 1) / lin_split) * 2 * max_ci * sizeof(float);
   SAVSR_REQUIRE(lin_smem <= 200 * 1024, "savsr_osa_prologue: batch %d too large for the routing kernel's shared memory", batch);
   if (lin_smem > 48 * 1024) {
     if (int rc = ensure_smem_attr(ctx, kAttrOsaLinear, osa_linear_kernel, 200 * 1024)) return rc;
   }
-  osa_linear_kernel<<<dim3((2 * max_ci + 7) / 8, nconvs, lin_split), 256, lin_smem, st>>>(L, 0);
-  osa_linear_kernel<<<dim3((max_ci + 7) / 8, nconvs, lin_split), 256, lin_smem, st>>>(L, 1);
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, osa_linear_kernel, dim3((2 * max_ci + 7) / 8, nconvs, lin_split), dim3(256), lin_smem, st, L, 0);
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, osa_linear_kernel, dim3((max_ci + 7) / 8, nconvs, lin_split), dim3(256), lin_smem, st, L, 1);
   SAVSR_CUDA(cudaGetLastError());
   return 0;
 }
@@ -626,8 +634,8 @@ extern "C" int savsr_ca_scale_residual(savsr_ctx* ctx, savsr_arena* arena, int t
   const long cap = 8L * ctx->sm_count / (arena->batch > 0 ? arena->batch : 1) + 1;
   if (blocks > cap) blocks = cap;
   if (arena->batch == 0) return 0;
-  ca_vector_kernel<<<arena->batch, 1024, 0, static_cast<cudaStream_t>(st)>>>(p);
-  ca_scale_residual_kernel<<<dim3(static_cast<unsigned>(blocks), arena->batch), 256, 0, static_cast<cudaStream_t>(st)>>>(p);
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, ca_vector_kernel, dim3(arena->batch), dim3(1024), 0, static_cast<cudaStream_t>(st), p);
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, ca_scale_residual_kernel, dim3(static_cast<unsigned>(blocks), arena->batch), dim3(256), 0, static_cast<cudaStream_t>(st), p);
   SAVSR_CUDA(cudaGetLastError());
   return 0;
 }

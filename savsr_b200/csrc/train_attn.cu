@@ -38,6 +38,8 @@ __host__ __device__ inline int st_rstd(int batch) { return 2 * batch * 32 + 32; 
 // ------------------------------------------------------------------------------------------------ forward: attention + fold
 // grid (ceil(co*ci/256), nconvs); every block recomputes the (tiny) attention of ALL samples, block x = 0 saves it.
 __global__ void __launch_bounds__(256) osa_assemble_train_kernel(const __grid_constant__ OsaTrainLaunch L) {
+  pdl_wait();
+  pdl_trigger();
   const savsr_osa_params& c = L.c[blockIdx.y];
   const savsr_osa_train& tr = L.t[blockIdx.y];
   __shared__ float zpre_s[kMaxBatchT][32];
@@ -159,6 +161,8 @@ __global__ void __launch_bounds__(256) osa_assemble_train_kernel(const __grid_co
 // W'[b,o,i,t] = fa[b,o] ca[b,i] sa[b,t] M[b,o,i,t],  M = sum_k ka[b,k] bank[k,o,i,t].   grid (ci / 2, nconvs), 128 threads.
 // Samples are processed four at a time (registers); dwfold is zeroed after it has been read (the next step's atomics start from 0).
 __global__ void __launch_bounds__(128) osa_unfold_bwd_kernel(const __grid_constant__ OsaTrainLaunch L) {
+  pdl_wait();
+  pdl_trigger();
   const savsr_osa_params& c = L.c[blockIdx.y];
   const savsr_osa_grads& g = L.g[blockIdx.y];
   extern __shared__ float sm[];                       // att [B][nout] | part [4 warps][B][18]
@@ -275,6 +279,8 @@ __host__ __device__ inline int dv_dh1(int batch, int nout, int ci) { return batc
 __host__ __device__ inline int dv_total(int batch, int nout, int ci) { return batch * nout + batch * 32 + 3 * batch * ci; }
 
 __global__ void __launch_bounds__(1024) osa_attn_chain_kernel(const __grid_constant__ OsaTrainLaunch L) {
+  pdl_wait();
+  pdl_trigger();
   const savsr_osa_params& c = L.c[blockIdx.x];
   const savsr_osa_train& tr = L.t[blockIdx.x];
   const savsr_osa_grads& g = L.g[blockIdx.x];
@@ -358,6 +364,8 @@ __global__ void __launch_bounds__(1024) osa_attn_chain_kernel(const __grid_const
 //   layer 0: dvin = dh1 R0 ([2ci][ci+2]); columns 2.. are the pooled means -> dpool.
 // grid (ceil(cols/32), nconvs), 512 threads: warp w sums the rows w, w+16, ... for 32 columns (coalesced), shared-memory reduce.
 __global__ void __launch_bounds__(512) osa_attn_matvec_kernel(const __grid_constant__ OsaTrainLaunch L, int layer) {
+  pdl_wait();
+  pdl_trigger();
   const savsr_osa_params& c = L.c[blockIdx.y];
   const savsr_osa_grads& g = L.g[blockIdx.y];
   __shared__ float red[16][kMaxBatchT][32];
@@ -413,6 +421,8 @@ __global__ void __launch_bounds__(512) osa_attn_matvec_kernel(const __grid_const
 // ------------------------------------------------------------------------------------------------ backward 3: weight gradients
 // dW[r][q] += sum_b dout[b][r] in[b][q] for the seven matrices of the prologue, biases likewise; grid (blocks, nconvs).
 __global__ void __launch_bounds__(256) osa_attn_wgrad_kernel(const __grid_constant__ OsaTrainLaunch L) {
+  pdl_wait();
+  pdl_trigger();
   const savsr_osa_params& c = L.c[blockIdx.y];
   const savsr_osa_train& tr = L.t[blockIdx.y];
   const savsr_osa_grads& g = L.g[blockIdx.y];
@@ -472,6 +482,8 @@ __global__ void __launch_bounds__(256) osa_attn_wgrad_kernel(const __grid_consta
 // dy[n][c] = sum_p dout[n,p,c] t[n,p,c] on two arena slots.  grid (blocks, batch), 256 threads; out must be zero on entry.
 __global__ void __launch_bounds__(256) slot_channel_dot_kernel(const uint16_t* __restrict__ a, const uint16_t* __restrict__ b, float* __restrict__ out,
                                                                long npix, int fmt) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[64];
   const int n = blockIdx.y;
   if (threadIdx.x < 64) red[threadIdx.x] = 0.f;
@@ -511,6 +523,8 @@ struct CaBwdParams {
 };
 // one CTA, 1024 threads: the pooled partial sums are reduced by 16 ranges x 64 channels with all loads in flight, the rest is tiny
 __global__ void __launch_bounds__(1024) ca_backward_kernel(const CaBwdParams p) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float part[16][kMaxBatchT][64];
   __shared__ float mean[kMaxBatchT][64], ds[kMaxBatchT][64], hid[kMaxBatchT][4], dhid[kMaxBatchT][4];
   const int tid = threadIdx.x;
@@ -612,7 +626,7 @@ extern "C" int savsr_osa_prologue_train(savsr_ctx* ctx, const savsr_osa_params* 
   if (int rc = osa_prologue_front(ctx, convs, nconvs, batch, npart, npix, inv_scale_h, inv_scale_w, st)) return rc;
   int max_ci = 0;
   for (int i = 0; i < nconvs; ++i) max_ci = convs[i].ci > max_ci ? convs[i].ci : max_ci;
-  osa_assemble_train_kernel<<<dim3((64 * max_ci + 255) / 256, nconvs), 256, 0, st>>>(L);
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, osa_assemble_train_kernel, dim3((64 * max_ci + 255) / 256, nconvs), dim3(256), 0, st, L);
   SAVSR_CUDA(cudaGetLastError());
   return 0;
 }
@@ -632,13 +646,13 @@ extern "C" int savsr_osa_fold_backward(savsr_ctx* ctx, const savsr_osa_params* c
   const int nout = max_ci + 64 + 17;
   const size_t smem1 = (static_cast<size_t>(batch) * nout + 4 * static_cast<size_t>(batch) * 18) * sizeof(float);
   SAVSR_REQUIRE(smem1 <= 48 * 1024, "savsr_osa_fold_backward: batch %d too large", batch);
-  osa_unfold_bwd_kernel<<<dim3(max_ci / 2, nconvs), 128, smem1, st>>>(L);
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, osa_unfold_bwd_kernel, dim3(max_ci / 2, nconvs), dim3(128), smem1, st, L);
   const size_t smem2 = (static_cast<size_t>(batch) * nout + batch * 32 + 3 * static_cast<size_t>(batch) * max_ci + 16) * sizeof(float);
   SAVSR_REQUIRE(smem2 <= 48 * 1024, "savsr_osa_fold_backward: batch %d too large for the chain kernel", batch);
-  osa_attn_chain_kernel<<<nconvs, 1024, smem2, st>>>(L);
-  osa_attn_matvec_kernel<<<dim3((2 * max_ci + 31) / 32, nconvs), 512, 0, st>>>(L, 1);
-  osa_attn_matvec_kernel<<<dim3((max_ci + 2 + 31) / 32, nconvs), 512, 0, st>>>(L, 0);
-  osa_attn_wgrad_kernel<<<dim3(2 * ctx->sm_count / nconvs + 1, nconvs), 256, 0, st>>>(L);
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, osa_attn_chain_kernel, dim3(nconvs), dim3(1024), smem2, st, L);
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, osa_attn_matvec_kernel, dim3((2 * max_ci + 31) / 32, nconvs), dim3(512), 0, st, L, 1);
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, osa_attn_matvec_kernel, dim3((max_ci + 2 + 31) / 32, nconvs), dim3(512), 0, st, L, 0);
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, osa_attn_wgrad_kernel, dim3(2 * ctx->sm_count / nconvs + 1, nconvs), dim3(256), 0, st, L);
   SAVSR_CUDA(cudaGetLastError());
   return 0;
 }
@@ -652,7 +666,7 @@ extern "C" int savsr_slot_channel_dot(savsr_ctx* ctx, savsr_arena* arena, int a_
   long blocks = (npix * 8 + 255) / 256;
   const long cap = 2L * ctx->sm_count / arena->batch + 1;
   if (blocks > cap) blocks = cap;
-  slot_channel_dot_kernel<<<dim3(static_cast<unsigned>(blocks), arena->batch), 256, 0, static_cast<cudaStream_t>(st)>>>(
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, slot_channel_dot_kernel, dim3(static_cast<unsigned>(blocks), arena->batch), dim3(256), 0, static_cast<cudaStream_t>(st), 
       reinterpret_cast<const uint16_t*>(arena->base) + a_slot * img, reinterpret_cast<const uint16_t*>(arena->base) + b_slot * img, out, npix, ctx->fmt);
   SAVSR_CUDA(cudaGetLastError());
   return 0;
@@ -667,7 +681,7 @@ extern "C" int savsr_ca_backward(savsr_ctx* ctx, const float* pool, int npart, i
   CaBwdParams p;
   p.pool = pool; p.npart = npart; p.inv_npix = 1.f / static_cast<float>(npix);
   p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.dy = dy; p.y = y; p.dw1 = dw1; p.db1 = db1; p.dw2 = dw2; p.db2 = db2; p.dmean = dmean; p.batch = batch;
-  ca_backward_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(st)>>>(p);
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, ca_backward_kernel, dim3(1), dim3(1024), 0, static_cast<cudaStream_t>(st), p);
   SAVSR_CUDA(cudaGetLastError());
   return 0;
 }

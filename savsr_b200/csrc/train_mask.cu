@@ -20,6 +20,8 @@ __device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); 
 // ------------------------------------------------------------------------------------------------ BatchNorm statistics
 // x: [rows][C], C = 16 or 1.  sums[0..C) += sum x, sums[C..2C) += sum x^2.  blockDim 256 (a multiple of C): a thread keeps its channel.
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, long n, int C, double* __restrict__ sums) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s1[256], s2[256];
   float a = 0.f, b = 0.f;
   for (long e = blockIdx.x * 256L + threadIdx.x; e < n; e += gridDim.x * 256L) { const float v = x[e]; a += v; b += v * v; }
@@ -34,6 +36,8 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
 }
 // stat[c] = mean, stat[16 + c] = rstd; running statistics updated; sums zeroed.  One block of 32 threads.
 __global__ void bn_finalize_kernel(double* sums, int C, double count, float eps, float momentum, float* rm, float* rv, float* stat) {
+  pdl_wait();
+  pdl_trigger();
   const int c = threadIdx.x;
   if (c >= C) return;
   const double mean = sums[c] / count;
@@ -53,6 +57,8 @@ __global__ void bn_finalize_kernel(double* sums, int C, double count, float eps,
 // t2[b][q][c] = mean over the 2x2 block of ReLU(BN1(m0))
 __global__ void __launch_bounds__(256) mask_norm_pool_kernel(const float* __restrict__ m0, const float* __restrict__ stat, const float* __restrict__ w,
                                                              const float* __restrict__ bb, float* __restrict__ t2, int B, int H, int W) {
+  pdl_wait();
+  pdl_trigger();
   const int h2 = H / 2, w2 = W / 2;
   const long total = static_cast<long>(B) * h2 * w2 * 16;
   for (long e = blockIdx.x * 256L + threadIdx.x; e < total; e += gridDim.x * 256L) {
@@ -68,6 +74,8 @@ __global__ void __launch_bounds__(256) mask_norm_pool_kernel(const float* __rest
 // out = ReLU(BN(x)) elementwise, [rows][16]
 __global__ void __launch_bounds__(256) mask_norm_relu_kernel(const float* __restrict__ x, const float* __restrict__ stat, const float* __restrict__ w,
                                                              const float* __restrict__ bb, float* __restrict__ out, long n) {
+  pdl_wait();
+  pdl_trigger();
   for (long e = blockIdx.x * 256L + threadIdx.x; e < n; e += gridDim.x * 256L) {
     const int c = e & 15;
     const float sc = stat[16 + c] * w[c];
@@ -77,6 +85,8 @@ __global__ void __launch_bounds__(256) mask_norm_relu_kernel(const float* __rest
 // t5 = bilinear x2 (align_corners = False) of ReLU(BN8(m7)); [B][h2*w2][16] -> [B][H*W][16]
 __global__ void __launch_bounds__(256) mask_norm_up_kernel(const float* __restrict__ m7, const float* __restrict__ stat, const float* __restrict__ w,
                                                            const float* __restrict__ bb, float* __restrict__ t5, int B, int H, int W) {
+  pdl_wait();
+  pdl_trigger();
   const int h2 = H / 2, w2 = W / 2;
   const long total = static_cast<long>(B) * H * W * 16;
   for (long e = blockIdx.x * 256L + threadIdx.x; e < total; e += gridDim.x * 256L) {
@@ -97,6 +107,8 @@ __global__ void __launch_bounds__(256) mask_norm_up_kernel(const float* __restri
 template <int CO>
 __global__ void __launch_bounds__(128) mask_conv_kernel(const float* __restrict__ in, const float* __restrict__ wgt, const float* __restrict__ bias,
                                                         float* __restrict__ out, int B, int hh, int ww) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float ws[9 * 16 * CO];          // [tap][c][o]
   for (int k = threadIdx.x; k < 9 * 16 * CO; k += blockDim.x) {
     const int o = k % CO, c = (k / CO) & 15, tap = k / (CO * 16);
@@ -136,6 +148,8 @@ __global__ void __launch_bounds__(256) mask_combine_kernel(const float* __restri
                                                            const float* __restrict__ bb, const float* __restrict__ gamma, const uint16_t* __restrict__ R,
                                                            const uint16_t* __restrict__ A, const uint16_t* __restrict__ S, uint16_t* __restrict__ Hh,
                                                            float* __restrict__ mask, long npix_total, int fmt) {
+  pdl_wait();
+  pdl_trigger();
   const float sc = stat[16] * w[0], sh = bb[0] - stat[0] * sc, gm = gamma[0];
   for (long e = blockIdx.x * 256L + threadIdx.x; e < npix_total * 8; e += gridDim.x * 256L) {
     const long p = e >> 3;
@@ -157,6 +171,8 @@ __global__ void __launch_bounds__(256) mask_combine_bwd_kernel(const uint16_t* _
                                                                const float* __restrict__ mask, const float* __restrict__ gamma, uint16_t* __restrict__ dA,
                                                                uint16_t* __restrict__ gS, float* __restrict__ dmask, float* __restrict__ d_gamma,
                                                                long npix_total, int fmt) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[8];
   const float gm = gamma[0];
   float dg = 0.f;
@@ -221,6 +237,8 @@ __device__ __forceinline__ float bn_bwd_dyp(const BnBwd& p, long e, int c, float
   return dy;
 }
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwd p, double* __restrict__ sums) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s1[256], s2[256];
   float a = 0.f, b = 0.f;
   const int c = threadIdx.x % p.C;
@@ -240,6 +258,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwd p, doubl
 }
 // d weight += s2, d bias += s1; coef = [w * rstd | s1 / count | s2 / count] (16 each); sums zeroed.
 __global__ void bn_bwd_finalize_kernel(double* sums, int C, double count, const float* stat, const float* w, float* dw, float* db, float* coef) {
+  pdl_wait();
+  pdl_trigger();
   const int c = threadIdx.x;
   if (c >= C) return;
   const double s1 = sums[c], s2 = sums[C + c];
@@ -252,6 +272,8 @@ __global__ void bn_bwd_finalize_kernel(double* sums, int C, double count, const 
 }
 // pass 2: dx = coef0 * (dy' - coef1 - xhat * coef2) -> fp32 [rows][C], or (slot != NULL) the first 16 channels of an arena slot
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwd p, const float* __restrict__ coef, float* __restrict__ dx, uint16_t* __restrict__ slot, int fmt) {
+  pdl_wait();
+  pdl_trigger();
   const int c = threadIdx.x % p.C;
   for (long e = blockIdx.x * 256L + threadIdx.x; e < p.n; e += gridDim.x * 256L) {
     float xh;
@@ -267,6 +289,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwd p, const 
 template <int CO>
 __global__ void __launch_bounds__(256) mask_conv_wgrad_kernel(const float* __restrict__ dout, const float* __restrict__ in, float* __restrict__ dW,
                                                               float* __restrict__ dbias, int B, int hh, int ww, int chunk) {
+  pdl_wait();
+  pdl_trigger();
   const long total = static_cast<long>(B) * hh * ww;
   const long q0 = blockIdx.x * static_cast<long>(chunk), q1 = min(q0 + chunk, total);
   if (CO == 16) {
@@ -306,6 +330,8 @@ __global__ void __launch_bounds__(256) mask_conv_wgrad_kernel(const float* __res
 // data gradient of the 16 -> 16 convolution: din[q][c] = sum_tap sum_o W[o][c][tap] dout[q - tap][o].  Thread = pixel.
 __global__ void __launch_bounds__(128) mask_conv16_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ wgt, float* __restrict__ din,
                                                                 int B, int hh, int ww) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float ws[9 * 16 * 16];          // [tap][o][c]
   for (int k = threadIdx.x; k < 9 * 256; k += blockDim.x) {
     const int c = k & 15, o = (k >> 4) & 15, tap = k >> 8;
@@ -344,6 +370,8 @@ __global__ void __launch_bounds__(128) mask_conv16_dgrad_kernel(const float* __r
 // Thread = full-resolution pixel p': dt5[p'][c] = sum_tap W11[c][tap] dm11[p' - tap], scattered to its four source pixels.
 __global__ void __launch_bounds__(128) mask_conv1_dgrad_up_kernel(const float* __restrict__ dm11, const float* __restrict__ w11, float* __restrict__ dt4,
                                                                   int B, int H, int W) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float ws[9 * 16];               // [tap][c]
   for (int k = threadIdx.x; k < 144; k += blockDim.x) ws[k] = w11[(k & 15) * 9 + (k >> 4)];
   __syncthreads();
@@ -407,22 +435,22 @@ extern "C" int savsr_mask_forward_train(savsr_ctx* ctx, savsr_arena* arena, cons
   const int B = arena->batch, H = arena->height, W = arena->width, h2 = H / 2, w2 = W / 2;
   const long P = static_cast<long>(B) * H * W, Q = static_cast<long>(B) * h2 * w2;
   auto stats = [&](const float* x, long rows, int C, int layer) {
-    bn_stats_kernel<<<blocks_for(ctx, rows * C, 256 * 8), 256, 0, st>>>(x, rows * C, C, m->sums);
-    bn_finalize_kernel<<<1, 32, 0, st>>>(m->sums, C, static_cast<double>(rows), m->eps, m->momentum, m->bn_rm[layer], m->bn_rv[layer], m->stat + layer * 32);
+    (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, bn_stats_kernel, dim3(blocks_for(ctx, rows * C, 256 * 8)), dim3(256), 0, st, x, rows * C, C, m->sums);
+    (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, bn_finalize_kernel, dim3(1), dim3(32), 0, st, m->sums, C, static_cast<double>(rows), m->eps, m->momentum, m->bn_rm[layer], m->bn_rv[layer], m->stat + layer * 32);
   };
   stats(m->m0, P, 16, 0);
-  mask_norm_pool_kernel<<<blocks_for(ctx, Q * 16, 256), 256, 0, st>>>(m->m0, m->stat, m->bn_w[0], m->bn_b[0], m->t2, B, H, W);
-  mask_conv_kernel<16><<<blocks_for(ctx, Q, 128), 128, 0, st>>>(m->t2, m->w4, m->b4, m->m4, B, h2, w2);
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, mask_norm_pool_kernel, dim3(blocks_for(ctx, Q * 16, 256)), dim3(256), 0, st, m->m0, m->stat, m->bn_w[0], m->bn_b[0], m->t2, B, H, W);
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, mask_conv_kernel<16>, dim3(blocks_for(ctx, Q, 128)), dim3(128), 0, st, m->t2, m->w4, m->b4, m->m4, B, h2, w2);
   stats(m->m4, Q, 16, 1);
-  mask_norm_relu_kernel<<<blocks_for(ctx, Q * 16, 256), 256, 0, st>>>(m->m4, m->stat + 32, m->bn_w[1], m->bn_b[1], m->t3, Q * 16);
-  mask_conv_kernel<16><<<blocks_for(ctx, Q, 128), 128, 0, st>>>(m->t3, m->w7, m->b7, m->m7, B, h2, w2);
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, mask_norm_relu_kernel, dim3(blocks_for(ctx, Q * 16, 256)), dim3(256), 0, st, m->m4, m->stat + 32, m->bn_w[1], m->bn_b[1], m->t3, Q * 16);
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, mask_conv_kernel<16>, dim3(blocks_for(ctx, Q, 128)), dim3(128), 0, st, m->t3, m->w7, m->b7, m->m7, B, h2, w2);
   stats(m->m7, Q, 16, 2);
-  mask_norm_up_kernel<<<blocks_for(ctx, P * 16, 256), 256, 0, st>>>(m->m7, m->stat + 64, m->bn_w[2], m->bn_b[2], m->t5, B, H, W);
-  mask_conv_kernel<1><<<blocks_for(ctx, P, 128), 128, 0, st>>>(m->t5, m->w11, m->b11, m->m11, B, H, W);
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, mask_norm_up_kernel, dim3(blocks_for(ctx, P * 16, 256)), dim3(256), 0, st, m->m7, m->stat + 64, m->bn_w[2], m->bn_b[2], m->t5, B, H, W);
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, mask_conv_kernel<1>, dim3(blocks_for(ctx, P, 128)), dim3(128), 0, st, m->t5, m->w11, m->b11, m->m11, B, H, W);
   stats(m->m11, P, 1, 3);
   const long img = static_cast<long>(H) * W * kC * B;
   const uint16_t* base = reinterpret_cast<const uint16_t*>(arena->base);
-  mask_combine_kernel<<<blocks_for(ctx, P * 8, 256), 256, 0, st>>>(m->m11, m->stat + 96, m->bn_w[3], m->bn_b[3], m->gamma, base + r_slot * img, base + a_slot * img,
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, mask_combine_kernel, dim3(blocks_for(ctx, P * 8, 256)), dim3(256), 0, st, m->m11, m->stat + 96, m->bn_w[3], m->bn_b[3], m->gamma, base + r_slot * img, base + a_slot * img,
                                                                  base + share_slot * img, reinterpret_cast<uint16_t*>(arena->base) + out_slot * img, m->mask, P, ctx->fmt);
   SAVSR_CUDA(cudaGetLastError());
   return 0;
@@ -442,32 +470,32 @@ extern "C" int savsr_mask_backward_train(savsr_ctx* ctx, savsr_arena* arena, con
   const long P = static_cast<long>(B) * H * W, Q = static_cast<long>(B) * h2 * w2;
   const long img = static_cast<long>(H) * W * kC * B;
   uint16_t* base = reinterpret_cast<uint16_t*>(arena->base);
-  mask_combine_bwd_kernel<<<blocks_for(ctx, P * 8, 256), 256, 0, st>>>(base + dh_slot * img, base + a_slot * img, base + share_slot * img, m->mask, m->gamma,
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, mask_combine_bwd_kernel, dim3(blocks_for(ctx, P * 8, 256)), dim3(256), 0, st, base + dh_slot * img, base + a_slot * img, base + share_slot * img, m->mask, m->gamma,
                                                                      base + da_slot * img, base + gshare_slot * img, m->dmask, m->d_gamma, P, ctx->fmt);
   auto bn_bwd = [&](const float* dy, const float* x, int layer, int C, int act, int pooled, long n, double count, float* dx, uint16_t* slot) {
     BnBwd p;
     p.dy = dy; p.x = x; p.stat = m->stat + layer * 32; p.w = m->bn_w[layer]; p.b = m->bn_b[layer];
     p.C = C; p.act = act; p.pooled = pooled; p.H = H; p.W = W; p.n = n;
-    bn_bwd_reduce_kernel<<<blocks_for(ctx, n, 256 * 8), 256, 0, st>>>(p, m->sums);
-    bn_bwd_finalize_kernel<<<1, 32, 0, st>>>(m->sums, C, count, p.stat, p.w, m->d_bn_w[layer], m->d_bn_b[layer], m->coef + layer * 48);
-    bn_bwd_apply_kernel<<<blocks_for(ctx, n, 256 * 4), 256, 0, st>>>(p, m->coef + layer * 48, dx, slot, ctx->fmt);
+    (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, bn_bwd_reduce_kernel, dim3(blocks_for(ctx, n, 256 * 8)), dim3(256), 0, st, p, m->sums);
+    (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, bn_bwd_finalize_kernel, dim3(1), dim3(32), 0, st, m->sums, C, count, p.stat, p.w, m->d_bn_w[layer], m->d_bn_b[layer], m->coef + layer * 48);
+    (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, bn_bwd_apply_kernel, dim3(blocks_for(ctx, n, 256 * 4)), dim3(256), 0, st, p, m->coef + layer * 48, dx, slot, ctx->fmt);
   };
   // sigmoid + BN12 -> dm11
   bn_bwd(m->dmask, m->m11, 3, 1, 2, 0, P, static_cast<double>(P), m->dm11, nullptr);
   // conv11 (16 -> 1) on the upsampled map
   const int chunk1 = 32;       // short pixel chunks: the per-thread loop is a chain of dependent loads, parallelism comes from the block count
-  mask_conv_wgrad_kernel<1><<<static_cast<int>((P + chunk1 - 1) / chunk1), 256, 0, st>>>(m->dm11, m->t5, m->d_w11, m->d_b11, B, H, W, chunk1);
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, mask_conv_wgrad_kernel<1>, dim3(static_cast<int>((P + chunk1 - 1) / chunk1)), dim3(256), 0, st, m->dm11, m->t5, m->d_w11, m->d_b11, B, H, W, chunk1);
   SAVSR_CUDA(cudaMemsetAsync(m->dt4, 0, static_cast<size_t>(Q) * 16 * sizeof(float), st));
-  mask_conv1_dgrad_up_kernel<<<blocks_for(ctx, P, 128), 128, 0, st>>>(m->dm11, m->w11, m->dt4, B, H, W);
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, mask_conv1_dgrad_up_kernel, dim3(blocks_for(ctx, P, 128)), dim3(128), 0, st, m->dm11, m->w11, m->dt4, B, H, W);
   // ReLU + BN8 -> dm7 ; conv7
   bn_bwd(m->dt4, m->m7, 2, 16, 1, 0, Q * 16, static_cast<double>(Q), m->dm7, nullptr);
   const int chunk16 = 16;
-  mask_conv_wgrad_kernel<16><<<static_cast<int>((Q + chunk16 - 1) / chunk16), 256, 0, st>>>(m->dm7, m->t3, m->d_w7, m->d_b7, B, h2, w2, chunk16);
-  mask_conv16_dgrad_kernel<<<blocks_for(ctx, Q, 128), 128, 0, st>>>(m->dm7, m->w7, m->dt3, B, h2, w2);
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, mask_conv_wgrad_kernel<16>, dim3(static_cast<int>((Q + chunk16 - 1) / chunk16)), dim3(256), 0, st, m->dm7, m->t3, m->d_w7, m->d_b7, B, h2, w2, chunk16);
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, mask_conv16_dgrad_kernel, dim3(blocks_for(ctx, Q, 128)), dim3(128), 0, st, m->dm7, m->w7, m->dt3, B, h2, w2);
   // ReLU + BN5 -> dm4 ; conv4
   bn_bwd(m->dt3, m->m4, 1, 16, 1, 0, Q * 16, static_cast<double>(Q), m->dm4, nullptr);
-  mask_conv_wgrad_kernel<16><<<static_cast<int>((Q + chunk16 - 1) / chunk16), 256, 0, st>>>(m->dm4, m->t2, m->d_w4, m->d_b4, B, h2, w2, chunk16);
-  mask_conv16_dgrad_kernel<<<blocks_for(ctx, Q, 128), 128, 0, st>>>(m->dm4, m->w4, m->dt2, B, h2, w2);
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, mask_conv_wgrad_kernel<16>, dim3(static_cast<int>((Q + chunk16 - 1) / chunk16)), dim3(256), 0, st, m->dm4, m->t2, m->d_w4, m->d_b4, B, h2, w2, chunk16);
+  (void)launch_k(ctx->opt[SAVSR_OPT_PDL] != 0, mask_conv16_dgrad_kernel, dim3(blocks_for(ctx, Q, 128)), dim3(128), 0, st, m->dm4, m->w4, m->dt2, B, h2, w2);
   // AvgPool2 + ReLU + BN1 -> dm0, written as the first 16 channels of an arena slot (the other 48 stay zero): operand of the tensor-core
   // data / weight gradient of the 64 -> 16 convolution
   bn_bwd(m->dt2, m->m0, 0, 16, 1, 1, P * 16, static_cast<double>(P), nullptr, base + dm0_slot * img);
