@@ -453,6 +453,12 @@ def run_train(args, rank, world, local_rank):
                        "scales": [list(s) for s in TRAIN_SCALES], "optimizer": "Adam 2e-4 (0.9, 0.99), Charbonnier, EMA 0.999",
                        "parallelism": f"DistributedDataParallel x{world} (NCCL gradient all-reduce, 75.6 MB fp32)" if world > 1 else "single GPU"},
             "last_loss": round(loss, 5), "cuda_graph_per_scale": bool(graph), "engine": args.train_engine}
+    # algorithmic work of a step: forward FLOPs of SURVEY 8d per sample, x3 for forward + data gradient + weight gradient (SURVEY 8d's own estimate)
+    step_flops = sum(3.0 * flops_per_frame(h, w, *hw_out(h, w, TRAIN_SCALES[i % len(TRAIN_SCALES)])) * per_gpu * world for i in range(args.steps))
+    line["algorithmic_tflops"] = round(step_flops / (ms / 1e3) / 1e12, 1)
+    line["algorithmic_tflop_per_step"] = round(step_flops / args.steps / 1e12, 3)
+    line["note_small_shapes"] = ("4 x 64 x 64 crops are 128 output tiles per convolution: one to six tiles per CTA on 148 SMs, ~1 400 launches of a few "
+                                 "microseconds each -- the step is launch-latency bound, not tensor bound (DESIGN.md section 9)")
     if native:
         plan = next(iter(tr.plans.values()))
         line["config"]["parallelism"] = (f"data parallel x{world}: one NCCL all-reduce of the flat fp32 gradient buffer ({tr.flat.n * 4 / 1e6:.1f} MB) per step"
