@@ -466,6 +466,7 @@ def run_train(args, rank, world, local_rank):
         line["stage"] = ("f1 stage B: static forward + backward launch list on the 16-bit NHWC arena (savsr_b200/trainplan.py): every trunk convolution "
                          "forward / dgrad / batched wgrad on tcgen05 with no layout conversion in between, OSA-Conv attention (train-mode BatchNorm) and "
                          "channel attention forward + backward native, table-driven weight packing, flat Adam + EMA; ATen islands: OSAdapt mask net, SATU + tail + loss")
+        line["gpu_launches"] = args.steps * (plan.launches["fwd"] + plan.launches["bwd"])       # native launches + the island's estimate, timed region
         line["plan"] = {"launches_native_estimate": plan.launches, "arena_slots": plan.n_slots, "t_slots": plan.n_tslots, "plan_gb": round(plan.nbytes / 2 ** 30, 2)}
     else:
         line["stage"] = ("f1 stage A: 3x3 convs (fwd / dgrad / wgrad, 98 % of the FLOPs) on tcgen05 through savsr_b200.autograd.conv3x3, each call "
