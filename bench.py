@@ -593,6 +593,18 @@ def main():
             sharding.infer_clip(net, clip, batch=e2e_batches, out=out_host)      # D2H of batch i overlaps the forward of batch i+1
         torch.cuda.current_stream().synchronize()
 
+    # the same through-the-API measurement for a STREAM of clips: no host synchronisation per clip, two host output buffers in rotation, one
+    # copy stream; every clip's H2D and D2H still happen inside the timed region, the last clip's copy is waited for before the clock stops
+    out_host2 = torch.empty(frames, 3, H, W).pin_memory()
+    pipe_state = {"i": 0, "copy": torch.cuda.Stream(dev)}
+
+    def step_e2e_stream():
+        clip = clip_host.to(dev, non_blocking=True)
+        buf = out_host if pipe_state["i"] % 2 == 0 else out_host2
+        pipe_state["i"] += 1
+        with torch.no_grad():
+            sharding.infer_clip(net, clip, batch=B, out=buf, copy_stream=pipe_state["copy"], join=False)
+
     # reference test loop on the device (rows f2 + f3): uint8 ground-truth frames in pinned host memory -> LR synthesis ->
     # windows -> net -> uint8 BGR images + PSNR-Y + SSIM-Y back in host memory (PNG decode / encode stay outside)
     from savsr_b200 import datapath
@@ -637,6 +649,15 @@ def main():
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    for _ in range(2):
+        step_e2e_stream()
+    torch.cuda.synchronize()
+
+    def stream_steps():
+        for _ in range(args.steps):
+            step_e2e_stream()
+        pipe_state["copy"].synchronize()
+    ms_e2e_stream = timed(stream_steps, 1)
     ms_pipe = None
     if pipeline_ok:
         for _ in range(2):
@@ -731,7 +752,11 @@ def main():
         "e2e": {"value": round(e2e, 2), "unit": "HR Mpix/s", "ms_per_step": round(ms_e2e / args.steps, 3),
                 "h2d_bytes_per_step": clip_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4,
                 "api": "savsr_b200.sharding.infer_clip(savsr_b200.SAVSR, clip, batch=%s)" % (list(e2e_batches),),
-                "batches": list(e2e_batches)},
+                "batches": list(e2e_batches),
+                "note": "synchronous: the host waits for every clip's frames before it submits the next clip",
+                "streamed": {"value": round(mpix_step * args.steps / (ms_e2e_stream / 1e3), 2), "unit": "HR Mpix/s", "ms_per_step": round(ms_e2e_stream / args.steps, 3),
+                             "what": "the same API on a stream of clips (infer_clip(..., batch=%d, copy_stream=s, join=False)): two pinned output buffers in rotation, no "
+                                     "host synchronisation per clip, the clock stops when the last clip's frames are in host memory" % B}},
         "pipeline": None if ms_pipe is None else {
             "value": round(mpix_step * args.steps / (ms_pipe / 1e3), 2), "unit": "HR Mpix/s", "ms_per_step": round(ms_pipe / args.steps, 3),
             "h2d_bytes_per_step": frames * H * W * 3, "d2h_bytes_per_step": frames * H * W * 3 + 16 * frames,

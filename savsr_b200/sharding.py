@@ -65,13 +65,17 @@ def batch_schedule(n: int, batch) -> list:
 
 
 def infer_clip(net: Callable[[torch.Tensor], torch.Tensor], clip: torch.Tensor, frames: Optional[Sequence[int]] = None,
-               batch=1, num_frames: int = 7, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+               batch=1, num_frames: int = 7, out: Optional[torch.Tensor] = None, copy_stream: Optional["torch.cuda.Stream"] = None,
+               join: bool = True) -> torch.Tensor:
     """Run `net` on the windows of `frames` (default: all), `batch` windows per forward (int or a schedule, see batch_schedule).
     Returns [len(frames), 3, H, W].  The last, ragged batch is run at its own size.
     If `out` (e.g. a pinned host tensor) is given, each batch is copied into it on a side stream while the next
-    batch computes, and `out` is returned once all copies are enqueued behind the current stream."""
+    batch computes, and `out` is returned once all copies are enqueued behind the current stream.
+    `copy_stream` / `join=False`: for a stream of clips -- the caller owns ONE copy stream, the compute stream does not wait for the copies
+    (the next clip's forwards overlap this clip's last copy), and the caller synchronises the copy stream before reading `out`."""
     frames = list(range(clip.shape[0])) if frames is None else list(frames)
-    copy_stream = torch.cuda.Stream(clip.device) if (out is not None and clip.is_cuda) else None
+    if copy_stream is None:
+        copy_stream = torch.cuda.Stream(clip.device) if (out is not None and clip.is_cuda) else None
     outs = []
     for i, j in batch_schedule(len(frames), batch):
         chunk = frames[i:j]
@@ -86,7 +90,7 @@ def infer_clip(net: Callable[[torch.Tensor], torch.Tensor], clip: torch.Tensor, 
                 out[i:i + len(chunk)].copy_(y, non_blocking=True)
             y.record_stream(copy_stream)
     if out is not None:
-        if copy_stream is not None:
+        if copy_stream is not None and join:
             torch.cuda.current_stream(clip.device).wait_stream(copy_stream)
         return out
     if not outs:
