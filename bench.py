@@ -445,14 +445,24 @@ def run_train(args, rank, world, local_rank):
 
     for i in range(max(max(args.warmup, 2), len(TRAIN_SCALES) if graph else 0)):      # with graphs: capture every scale before timing
         step(i)
+    sampler = ClockSampler(local_rank); sampler.start()
     ms, loss = timed_steps(step, args.steps)
+    clocks = sampler.stop()
+    # the same step as the reference's loop sees it (sr_model.py:101-128 + the logger reading l_pix): batches from pinned host memory
+    # (already the case above) and the loss value read back by the host EVERY step, which serialises host and device
+    ms_e2e, _ = timed_steps(lambda i: float(step(i)), args.steps)
     line = {"metric": "train_samples_per_s", "value": round(per_gpu * world * args.steps / (ms / 1e3), 2), "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 2), "ms_per_step": round(ms / args.steps, 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16 conv operands, fp32 master weights / accumulation", "data": "synthetic",
             "config": {"workload": "train_cfg5", "per_gpu_batch": per_gpu, "global_batch": per_gpu * world, "lr_crop": [h, w], "frames": 7,
                        "scales": [list(s) for s in TRAIN_SCALES], "optimizer": "Adam 2e-4 (0.9, 0.99), Charbonnier, EMA 0.999",
                        "parallelism": f"DistributedDataParallel x{world} (NCCL gradient all-reduce, 75.6 MB fp32)" if world > 1 else "single GPU"},
-            "last_loss": round(loss, 5), "cuda_graph_per_scale": bool(graph), "engine": args.train_engine}
+            "last_loss": round(loss, 5), "cuda_graph_per_scale": bool(graph), "engine": args.train_engine, "clocks": clocks,
+            "e2e": {"value": round(per_gpu * world * args.steps / (ms_e2e / 1e3), 2), "unit": "samples/s", "ms_per_step": round(ms_e2e / args.steps, 2),
+                    "h2d_bytes_per_step": int(lq_host.numel() * 4 + sum(g.numel() for g in gts.values()) * 4 // len(gts)), "d2h_bytes_per_step": 4,
+                    "api": "NativeTrainer.step(lq, gt, scale) on pinned host batches, float(loss) read by the host every step"
+                           if native else "train.Trainer.step(lq, gt, scale) on pinned host batches, float(loss) read by the host every step",
+                    "note": "`value` feeds the same pinned host batches but reads the loss once at the end (the host runs ahead of the device)"}}
     # algorithmic work of a step: forward FLOPs of SURVEY 8d per sample, x3 for forward + data gradient + weight gradient (SURVEY 8d's own estimate)
     step_flops = sum(3.0 * flops_per_frame(h, w, *hw_out(h, w, TRAIN_SCALES[i % len(TRAIN_SCALES)])) * per_gpu * world for i in range(args.steps))
     line["algorithmic_tflops"] = round(step_flops / (ms / 1e3) / 1e12, 1)
@@ -465,7 +475,8 @@ def run_train(args, rank, world, local_rank):
                                          if world > 1 else "single GPU")
         line["stage"] = ("f1 stage B: static forward + backward launch list on the 16-bit NHWC arena (savsr_b200/trainplan.py): every trunk convolution "
                          "forward / dgrad / batched wgrad on tcgen05 with no layout conversion in between, OSA-Conv attention (train-mode BatchNorm) and "
-                         "channel attention forward + backward native, table-driven weight packing, flat Adam + EMA; ATen islands: OSAdapt mask net, SATU + tail + loss")
+                         "channel attention forward + backward native, OSAdapt mask net (train-mode BatchNorm) native, table-driven weight packing, flat Adam + EMA; "
+                         "ATen island: SATU HR side + tail + loss")
         line["gpu_launches"] = args.steps * (plan.launches["fwd"] + plan.launches["bwd"])       # native launches + the island's estimate, timed region
         line["plan"] = {"launches_native_estimate": plan.launches, "arena_slots": plan.n_slots, "t_slots": plan.n_tslots, "plan_gb": round(plan.nbytes / 2 ** 30, 2)}
     else:
