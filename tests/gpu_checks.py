@@ -852,10 +852,13 @@ def check_sta_lrelu(B=2, C=5, h=7, w=9, seed=3):
     return info
 
 
-def check_trainplan(b=2, h=16, w=20, scale=(2, 2), seed=0, tol_worst=0.10, tol_cos=0.999, steps=0, graph=False, native_attn=True, native_mask=True):
+def check_trainplan(b=2, h=16, w=20, scale=(2, 2), seed=0, tol_worst=0.10, tol_cos=0.999, steps=0, graph=False, native_attn=True, native_mask=True,
+                    oracle_device="cpu"):
     """Row f1 stage B: the NATIVE training step (savsr_b200.trainplan: arena-resident forward / dgrad / batched wgrad, table-driven
     weight packing) against fp32 CPU autograd through the oracle: loss, per-parameter gradient error
-    |g - r| / max(|r|, 1 % of the largest tensor gradient), and the cosine of the whole flat gradient."""
+    |g - r| / max(|r|, 1 % of the largest tensor gradient), and the cosine of the whole flat gradient.
+    oracle_device="cuda": the same oracle evaluated in fp32 on the GPU (TF32 off) -- what makes the BASELINE cfg-5 batch (4 x 7 x 3 x 64 x 64)
+    checkable in seconds; the oracle stays the checker, the product path is unchanged."""
     import savsr_b200
     from oracle import savsr_oracle as O
     from oracle.state_dict_fixture import make_input, make_state_dict
@@ -868,13 +871,27 @@ def check_trainplan(b=2, h=16, w=20, scale=(2, 2), seed=0, tol_worst=0.10, tol_c
     x = make_input(b, h, w, 1234 + seed)
     H, W = O.get_hw(h, w, scale)
     gt = torch.rand(b, 3, H, W, generator=torch.Generator().manual_seed(5))
-    sd_cpu = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    odev = torch.device(oracle_device)
+    sd_cpu = {k: (v.clone().to(odev).requires_grad_(True) if v.is_floating_point() else v.clone().to(odev)) for k, v in sd.items()}
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
     O.BN_TRAIN = True
     try:
-        ref_loss = T.charbonnier(O.forward(sd_cpu, x, scale), gt)
+        ref_loss = T.charbonnier(O.forward(sd_cpu, x.to(odev), scale), gt.to(odev))
         ref_loss.backward()
     finally:
         O.BN_TRAIN = False
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    if odev.type != "cpu":
+        moved = {}                                     # the report below compares on the host
+        for k, v in sd_cpu.items():
+            c = v.detach().cpu()
+            if v.grad is not None:
+                c.requires_grad_(True)
+                c.grad = v.grad.cpu()
+            moved[k] = c
+        sd_cpu = moved
+        ref_loss = ref_loss.detach().cpu()
     tr = TP.NativeTrainer(net, use_graph=graph, native_attn=native_attn, native_mask=native_mask)
     plan = tr.plan_for(x.to(DEV), scale)
     plan.x_in.copy_(x.to(DEV)); plan.gt.copy_(gt.to(DEV))

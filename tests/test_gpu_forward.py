@@ -243,6 +243,16 @@ def test_native_training_plan_gradients_match_the_oracle(G, kw):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("scale", [(4, 4), (1.5, 4)], ids=["x4", "x1.5x4"])
+def test_native_training_plan_at_the_cfg5_batch(G, scale):
+    """BASELINE config 5 at its full size (4 x 7 x 3 x 64 x 64 Vimeo90K crops): loss and every parameter gradient of the native step against
+    the oracle's fp32 autograd evaluated on the GPU (TF32 off).  With 16 384 pixels per sample the batch statistics and the pixel sums are
+    well conditioned: measured worst tensor 1.1 %, median 0.04 %, cosine 0.999994 -- bounds 5 % / 0.9999 (the 16 x 20 CPU-oracle cases keep 10 %)."""
+    info = G.check_trainplan(b=4, h=64, w=64, scale=scale, seed=3, oracle_device="cuda", tol_worst=0.05, tol_cos=0.9999)
+    print({k: info[k] for k in ("loss", "ref_loss", "cos", "median", "worst")})
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("graph", [False, True], ids=["eager", "cuda_graph"])
 def test_native_training_steps_reduce_the_loss(G, graph):
     """Pack -> forward -> backward -> Adam + EMA for a few steps on a fixed batch, eagerly and as replayed CUDA graphs."""
