@@ -234,6 +234,9 @@ class SAVSR(nn.Module):
                 return st.forward(x, self.scale)
             from savsr_b200 import train as _train
             return _train.forward(self, x, self.scale)
+        if x.dim() == 5 and x.shape[0] == 0 and x.is_cuda:        # an empty batch of windows (a rank with no frames of the clip): nothing to launch
+            H, W = engine.get_hw(x.shape[3], x.shape[4], self.scale)
+            return x.new_empty((0, 3, H, W))
         plan = self.plan_for(x)
         with torch.cuda.device(plan.device):
             out = torch.empty_like(plan.out)

@@ -228,6 +228,12 @@ def test_module_api_errors(G):
     net.set_scale(2)
     y = net(torch.rand(1, 7, 3, 8, 10, device="cuda"))
     assert tuple(y.shape) == (1, 3, 16, 20) and y.dtype == torch.float32
+    y0 = net(torch.rand(0, 7, 3, 8, 10, device="cuda"))            # an empty batch (a rank that owns no frame): empty result, no launch
+    assert tuple(y0.shape) == (0, 3, 16, 20) and y0.dtype == torch.float32
+    with pytest.raises(ValueError):
+        net(torch.zeros(1, 5, 3, 8, 10, device="cuda"))            # not a 7-frame window
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 7, 3, 8, 10))                           # CPU tensors are refused: there is no CPU path
 
 
 @pytest.mark.gpu
