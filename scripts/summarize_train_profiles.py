@@ -31,7 +31,7 @@ def launches():
            "Command: `ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r02_train.csv python scripts/profile_trainplan.py 1`",
            "(per-launch times under ncu are serialised and cold-cache: compare SHARES, not absolutes; the timed number is `bench.py --workload train_cfg5`)", "",
            f"kernel launches in the step: {b - a}, summed kernel time {tot / 1e6:.2f} ms; hand-written `savsr::` kernels: {nours} launches, {ours / 1e6:.2f} ms "
-           f"({100 * ours / tot:.0f} % of the kernel time); the rest are the ATen islands (OSAdapt mask net, SATU + tail + loss)", "",
+           f"({100 * ours / tot:.0f} % of the kernel time); the rest is the remaining ATen island (SATU HR side + tail + loss)", "",
            "| kernel | launches | total ms | share | avg us |", "|---|---|---|---|---|"]
     for k, (c, v) in sorted(agg.items(), key=lambda x: -x[1][1])[:40]:
         out.append(f"| `{k[:100]}` | {c} | {v / 1e6:.3f} | {100 * v / tot:.1f}% | {v / c / 1e3:.1f} |")
