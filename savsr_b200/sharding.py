@@ -41,11 +41,26 @@ def shard_frames(n_frames: int, rank: int, world_size: int, contiguous: bool = F
     return list(range(rank, n_frames, world_size))
 
 
+_WINDOW_INDEX_CACHE: "dict[tuple, torch.Tensor]" = {}
+
+
+def _window_index(T: int, frames: Sequence[int], num_frames: int, device: torch.device) -> torch.Tensor:
+    """Flat gather index of the windows of `frames`, resident on `device`.  Cached: building it per call costs a host-to-device copy from
+    pageable memory, which blocks the host until the stream has drained -- between two batches of a clip that is an idle GPU."""
+    key = (T, tuple(int(f) for f in frames), num_frames, device.type, device.index)
+    idx = _WINDOW_INDEX_CACHE.get(key)
+    if idx is None:
+        if len(_WINDOW_INDEX_CACHE) >= 256:
+            _WINDOW_INDEX_CACHE.clear()
+        idx = torch.tensor([frame_window_indices(f, T, num_frames) for f in key[1]], dtype=torch.long).reshape(-1).to(device)
+        _WINDOW_INDEX_CACHE[key] = idx
+    return idx
+
+
 def gather_windows(clip: torch.Tensor, frames: Sequence[int], num_frames: int = 7) -> torch.Tensor:
     """clip [T, 3, h, w] -> windows [len(frames), num_frames, 3, h, w] (temporal halo = duplicated input)."""
-    T = clip.shape[0]
-    idx = torch.tensor([frame_window_indices(f, T, num_frames) for f in frames], dtype=torch.long, device=clip.device)
-    return clip[idx.reshape(-1)].reshape(len(frames), num_frames, *clip.shape[1:])
+    idx = _window_index(clip.shape[0], frames, num_frames, clip.device)
+    return clip.index_select(0, idx).reshape(len(frames), num_frames, *clip.shape[1:])
 
 
 def batch_schedule(n: int, batch) -> list:
