@@ -132,8 +132,13 @@ def evaluate_clip(net: Callable[[torch.Tensor], torch.Tensor], frames_bgr_u8: to
     "ssim_y": float64 [n], "sr": float32 [n,3,H,W]}."""
     lr, gt = synthesize_lr(frames_bgr_u8, scale, want_gt=True)
     idx = list(range(lr.shape[0])) if frames is None else list(frames)
+    # the ground-truth rows of this rank's frames, selected BEFORE the forwards are enqueued: building a device index is a blocking copy,
+    # and behind the forwards it would hold the host until they have finished (an idle GPU before the post-processing launches)
+    if idx == list(range(gt.shape[0])):
+        gt_sel = gt
+    else:
+        gt_sel = gt.index_select(0, torch.tensor(idx, dtype=torch.long).to(gt.device)) if idx else gt[:0]
     sr = sharding.infer_clip(net, lr, idx, batch=batch, num_frames=num_frames)
-    gt_sel = gt[torch.tensor(idx, dtype=torch.long, device=gt.device)] if idx else gt[:0]
     if tuple(sr.shape) != tuple(gt_sel.shape):            # arbitrary-scale BI post-process, sr_model.py:291-294
         sr = resize_aa_bicubic(sr, (gt_sel.shape[-2], gt_sel.shape[-1]))
     images, psnr = postproc.tensor2img_psnr(sr, gt_sel, want_image=want_images)

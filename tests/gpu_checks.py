@@ -1089,6 +1089,13 @@ def check_evaluate_clip(seed=5):
         assert abs(float(res["ssim_y"][i]) - O.ssim_y(sr[i], gt_t[i])) < 1e-9
     dpsnr = abs(O.psnr_y(sr_o, gt_t) - float(res["psnr_y"].mean()))
     assert dpsnr < 0.05, dpsnr                                                  # north-star PSNR gate, bf16 path
+    # a rank's share of the clip (sharding.shard_frames), in any order: the same frames, scored against the same ground-truth rows
+    with torch.no_grad():
+        sub = datapath.evaluate_clip(net, torch.from_numpy(frames).to(DEV), scale, frames=[3, 1], batch=3)
+    assert tuple(sub["sr"].shape) == (2, 3, 48, 64)
+    assert float((sub["sr"].cpu() - sr[[3, 1]]).abs().max()) < 1e-4              # (another batch size regroups the pooled sums: not bit-identical)
+    assert float((sub["psnr_y"].cpu() - res["psnr_y"].cpu()[[3, 1]]).abs().max()) < 1e-2
+    assert float((sub["ssim_y"].cpu() - res["ssim_y"].cpu()[[3, 1]]).abs().max()) < 1e-4
     return dict(sr_max_abs=err, psnr_delta_db=dpsnr, psnr=[round(float(v), 3) for v in res["psnr_y"]])
 
 
