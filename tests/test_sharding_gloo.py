@@ -47,6 +47,26 @@ def test_infer_clip_ragged_batches():
     assert sharding.infer_clip(fake_net, clip, batch=4, out=out) is out and torch.equal(out, full)
 
 
+def test_gather_windows_index_cache():
+    """The gather index is built once per (clip length, frame list, window, device) and kept on the device (building it per call is a
+    blocking host-to-device copy); different clips, frame lists and lengths must not alias."""
+    sharding._WINDOW_INDEX_CACHE.clear()
+    a, b = torch.rand(9, 3, 4, 5), torch.rand(9, 3, 4, 5)
+    for clip in (a, b, a):
+        for frames in ([0, 8, 4], [4], list(range(9))):
+            got = sharding.gather_windows(clip, frames)
+            want = torch.stack([clip[sharding.frame_window_indices(f, 9)] for f in frames])
+            assert torch.equal(got, want)
+    assert len(sharding._WINDOW_INDEX_CACHE) == 3                       # one entry per frame list, shared by both clips
+    c = torch.rand(12, 3, 4, 5)                                         # same frame list, longer clip: another reflection pattern
+    assert torch.equal(sharding.gather_windows(c, [0, 8, 4])[1], c[sharding.frame_window_indices(8, 12)])
+    assert torch.equal(sharding.gather_windows(a, [8], num_frames=5)[0], a[sharding.frame_window_indices(8, 9, 5)])
+    assert len(sharding._WINDOW_INDEX_CACHE) == 5
+    for i in range(300):                                                # bounded
+        sharding.gather_windows(c, [i % 12, (i // 12) % 12, 3])
+    assert len(sharding._WINDOW_INDEX_CACHE) <= 256
+
+
 def _worker(rank, world, port, n_frames, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
