@@ -23,6 +23,14 @@ Parity pin
     outputs + per-stage probes under ``tests/golden/``.  ``tests/test_oracle_golden.py``
     checks this file against those vectors, and the SATU index vectors against
     the known-answer hashes of SURVEY.md appendix A.3.
+    The train-mode restatement (``BN_TRAIN``: BatchNorm on batch statistics, used
+    with autograd as the checker of the native training step, row f1) is pinned
+    the same way: ``scripts/make_golden.py --train-only`` runs the unmodified
+    reference in ``train()`` mode with its own ``CharbonnierLoss`` and commits the
+    loss, every parameter's gradient norm, the small gradient tensors and a random
+    projection of the whole gradient (``tests/golden/train_*.npz``); at generation
+    time the oracle's loss agrees to 3e-8 and its gradients to 3e-6 / 1.7e-3 per
+    tensor.
 
 The oracle deliberately uses a different formulation from the reference where
 that makes the maths explicit (OSA-Conv is evaluated with the four attentions

@@ -119,13 +119,89 @@ def lr_kat(outdir):
     np.savez_compressed(os.path.join(outdir, "lr_kat.npz"), **rec)
 
 
+TRAIN_CASES = [  # name, b, h, w, scale, sd_seed, in_seed  (row f1: the reference's optimisation step, sr_model.py:101-128)
+    ("train_x2_b2_12x14", 2, 12, 14, (2, 2), 0, 1240),
+    ("train_x1p5x4_b3_9x11", 3, 9, 11, (1.5, 4), 1, 1241),    # odd sizes -> pad_spatial + crop; asymmetric scale; b = 3
+]
+
+
+def train_kat(outdir):
+    """Row f1: the UNMODIFIED reference module in train() mode (BatchNorm on batch statistics) + its own CharbonnierLoss
+    (losses/basic_loss.py:84-123, loss_weight 1, mean) + backward, on CPU.  Stored per case: the loss, probes of the output, the L2 norm of
+    every parameter's gradient, the projection of the whole gradient on a seeded random direction, every gradient tensor of at most 4096
+    elements in full, and the BatchNorm buffers after the step.  The oracle's train-mode restatement (oracle.savsr_oracle.BN_TRAIN + autograd)
+    is checked against them here and in tests/test_oracle_golden.py -- it is the checker of the native training path."""
+    build_network, _ = load_reference()
+    from lbasicsr.losses.basic_loss import CharbonnierLoss
+    crit = CharbonnierLoss(loss_weight=1.0, reduction="mean")
+    torch.set_num_threads(os.cpu_count())
+    net = build_network(dict(NETWORK_G))
+    for name, b, h, w, scale, sd_seed, in_seed in TRAIN_CASES:
+        sd = make_state_dict(sd_seed)
+        net.load_state_dict(sd, strict=True)
+        net.train()
+        net.set_scale(scale)
+        x = make_input(b, h, w, in_seed)
+        H, W = O.get_hw(h, w, scale)
+        gt = torch.rand(b, 3, H, W, generator=torch.Generator().manual_seed(in_seed + 7))
+        net.zero_grad(set_to_none=True)
+        out = net(x)
+        loss = crit(out, gt)
+        loss.backward()
+        names = [k for k, p in net.named_parameters()]
+        grads = {k: p.grad for k, p in net.named_parameters()}
+        present = np.array([grads[k] is not None for k in names])
+        norms = np.array([float(grads[k].double().norm()) if grads[k] is not None else 0.0 for k in names], dtype=np.float64)
+        gen = torch.Generator().manual_seed(4242)
+        proj = 0.0
+        for k in names:
+            r = torch.randn(dict(net.named_parameters())[k].shape, generator=gen, dtype=torch.float64)
+            if grads[k] is not None:
+                proj += float((grads[k].double() * r).sum())
+        rec = dict(loss=np.float64(loss.detach().double()), gt=gt.numpy(), names=np.array(names), grad_present=present, grad_norm=norms,
+                   grad_proj=np.float64(proj), scale=np.array(scale, dtype=np.float64), dims=np.array([b, h, w, sd_seed, in_seed], dtype=np.int64))
+        for k, v in probe_summary(out).items():
+            rec["out." + k] = v
+        for k in names:
+            if grads[k] is not None and grads[k].numel() <= 4096:
+                rec["grad." + k] = grads[k].detach().numpy().copy()
+        for k, v in net.state_dict().items():
+            if k.endswith(("running_mean", "running_var", "num_batches_tracked")):
+                rec["buf." + k] = v.detach().numpy().copy()
+        # the oracle's train-mode restatement against it
+        sd_o = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+        O.BN_TRAIN = True
+        try:
+            out_o = O.forward(sd_o, x, scale)
+            loss_o = torch.sqrt((out_o - gt) ** 2 + 1e-12).mean()
+            loss_o.backward()
+        finally:
+            O.BN_TRAIN = False
+        worst, worst_k = 0.0, None
+        big = norms.max()
+        for k in names:
+            if grads[k] is None:
+                assert sd_o[k].grad is None or float(sd_o[k].grad.abs().max()) == 0.0, k
+                continue
+            e = float((sd_o[k].grad - grads[k]).double().norm()) / max(float(grads[k].double().norm()), 1e-3 * big)
+            if e > worst:
+                worst, worst_k = e, k
+        print(f"[{name}] reference train-mode loss {float(loss):.8f}; oracle loss diff {abs(float(loss_o) - float(loss)):.2e}, out max-abs "
+              f"{float((out_o - out).abs().max()):.2e}; worst gradient tensor {worst_k}: {worst:.2e} (of |g| floored at 0.1 % of the largest); "
+              f"{int(present.sum())}/{len(names)} parameters receive a gradient")
+        assert abs(float(loss_o) - float(loss)) < 1e-6 and worst < 2e-3, (worst_k, worst)
+        np.savez_compressed(os.path.join(outdir, name + ".npz"), **rec)
+
+
 def main():
-    if "--metrics-only" in sys.argv or "--lr-only" in sys.argv:
+    if "--metrics-only" in sys.argv or "--lr-only" in sys.argv or "--train-only" in sys.argv:
         load_reference()
         if "--metrics-only" in sys.argv:
             metric_kat(os.path.join(ROOT, "tests", "golden"))
         if "--lr-only" in sys.argv:
             lr_kat(os.path.join(ROOT, "tests", "golden"))
+        if "--train-only" in sys.argv:
+            train_kat(os.path.join(ROOT, "tests", "golden"))
         return
     build_network, ref_arch = load_reference()
     torch.set_num_threads(os.cpu_count())

@@ -9,7 +9,9 @@ import torch
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if "fingerprint" not in p and "metrics" not in p and "lr_kat" not in p)
+CASES = sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
+               if "fingerprint" not in p and "metrics" not in p and "lr_kat" not in p and not os.path.basename(p).startswith("train_"))
+TRAIN_CASES = sorted(glob.glob(os.path.join(GOLDEN, "train_*.npz")))
 
 # Tolerances, straight from the north star:
 #   * bf16 operand path (fp32 accumulate): <= 0.05 dB PSNR delta (test_psnr_delta_gate); max-abs is reported and asserted
@@ -256,6 +258,17 @@ def test_native_training_plan_at_the_cfg5_batch(G, scale):
     well conditioned: measured worst tensor 1.1 %, median 0.04 %, cosine 0.999994 -- bounds 5 % / 0.9999 (the 16 x 20 CPU-oracle cases keep 10 %)."""
     info = G.check_trainplan(b=4, h=64, w=64, scale=scale, seed=3, oracle_device="cuda", tol_worst=0.05, tol_cos=0.9999)
     print({k: info[k] for k in ("loss", "ref_loss", "cos", "median", "worst")})
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", TRAIN_CASES, ids=[os.path.basename(p)[:-4] for p in TRAIN_CASES])
+def test_training_step_matches_reference_golden(G, path):
+    """Row f1 against the reference itself (not through the oracle): tests/golden/train_*.npz hold the loss and the gradients of the
+    unmodified reference in train() mode."""
+    info = G.check_train_golden(path)
+    print(info)
+    if "b2_12x14" in path:
+        assert info["native"], "an even-sized batch must take the native launch list"
 
 
 @pytest.mark.gpu

@@ -12,7 +12,9 @@ from oracle import savsr_oracle as O
 from oracle.state_dict_fixture import make_input, make_state_dict, state_dict_spec
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if "fingerprint" not in p and "metrics" not in p and "lr_kat" not in p)
+CASES = sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
+               if "fingerprint" not in p and "metrics" not in p and "lr_kat" not in p and not os.path.basename(p).startswith("train_"))
+TRAIN_CASES = sorted(glob.glob(os.path.join(GOLDEN, "train_*.npz")))
 
 
 def sha12(a: np.ndarray) -> str:
@@ -50,6 +52,60 @@ def test_oracle_matches_reference_outputs(path):
     assert np.abs(grid0 - g["grid0"]).max() < 1e-6 and np.abs(grid1 - g["grid1"]).max() < 1e-6
     zero = O.satu_grid(h, w, scale, torch.zeros(1, 2, H, W))[0].numpy()
     assert np.array_equal(zero[0, :, 0], O.satu_base_norm(W, w, scale[1]))
+
+
+def _train_case(g):
+    b, h, w, sd_seed, in_seed = (int(v) for v in g["dims"])
+    scale = tuple(float(s) if float(s) != int(s) else int(s) for s in g["scale"])
+    return b, h, w, sd_seed, in_seed, scale
+
+
+@pytest.mark.parametrize("path", TRAIN_CASES, ids=[os.path.basename(p)[:-4] for p in TRAIN_CASES])
+def test_oracle_train_mode_matches_reference_gradients(path):
+    """Row f1: the oracle's train-mode restatement (BatchNorm on batch statistics) + Charbonnier + autograd against the loss and the
+    gradients the UNMODIFIED reference produced in train() mode with its own CharbonnierLoss (scripts/make_golden.py --train-only):
+    loss to 1e-6, every parameter's gradient norm, the projection of the whole gradient on a random direction, and the small gradient
+    tensors element by element.  This pins the checker of the native training path (tests/gpu_checks.py:check_trainplan)."""
+    g = np.load(path)
+    b, h, w, sd_seed, in_seed, scale = _train_case(g)
+    sd = make_state_dict(sd_seed)
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    x = make_input(b, h, w, in_seed)
+    gt = torch.from_numpy(g["gt"])
+    O.BN_TRAIN = True
+    try:
+        out = O.forward(sd, x, scale)
+        loss = torch.sqrt((out - gt) ** 2 + 1e-12).mean()           # CharbonnierLoss(loss_weight=1, reduction='mean'), basic_loss.py:22-24
+        loss.backward()
+    finally:
+        O.BN_TRAIN = False
+    assert abs(float(loss) - float(g["loss"])) < 1e-6
+    t = out.detach().flatten()
+    idx = torch.linspace(0, t.numel() - 1, steps=min(257, t.numel())).long()
+    assert tuple(g["out.shape"]) == tuple(out.shape) and float((t[idx] - torch.from_numpy(g["out.sample"])).abs().max()) < 1e-5
+    names = [str(n) for n in g["names"]]
+    assert names == [k for k, v in sd.items() if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))]
+    norms, present = g["grad_norm"], g["grad_present"]
+    assert present.all() and len(names) == 707                      # every parameter of the net takes part in the step
+    big = float(norms.max())
+    gen = torch.Generator().manual_seed(4242)
+    proj = 0.0
+    for k, n_ref in zip(names, norms):
+        gr = sd[k].grad
+        assert gr is not None, k
+        r = torch.randn(sd[k].shape, generator=gen, dtype=torch.float64)
+        proj += float((gr.double() * r).sum())
+        # (gradients upstream of a train-mode BatchNorm are ill-conditioned -- a conv bias there has a true gradient of zero -- hence the floor)
+        assert abs(float(gr.double().norm()) - float(n_ref)) < 2e-3 * max(float(n_ref), 1e-2 * big), (k, float(gr.norm()), float(n_ref))
+        if "grad." + k in g.files:
+            ref = torch.from_numpy(g["grad." + k])
+            assert float((gr - ref).norm()) < 2e-3 * max(float(ref.norm()), 1e-2 * big), k
+    gnorm = float(np.sqrt((norms ** 2).sum()))
+    assert abs(proj - float(g["grad_proj"])) < 1e-3 * gnorm * 10      # |<g, r>| ~ |g|; fp32 summation-order noise only
+
+
+def test_train_goldens_present():
+    assert len(TRAIN_CASES) == 2
 
 
 def test_default_init_fingerprint_recorded():
