@@ -967,8 +967,25 @@ def check_train_golden(path):
             ref = torch.from_numpy(g["grad." + k])
             worst_full = max(worst_full, (float((gr - ref).norm()) / max(float(ref.norm()), 1e-2 * big), k))
     gnorm = float(np.sqrt((norms ** 2).sum()))
+    # BatchNorm buffers after the step (momentum update of the running statistics with the UNBIASED batch variance, call counters)
+    bufs = dict(net.named_buffers())
+    worst_buf = (0.0, None)
+    nbuf = 0
+    for key in g.files:
+        if not key.startswith("buf."):
+            continue
+        k = key[4:]
+        ref = torch.from_numpy(g[key])
+        got = bufs[k].detach().cpu()
+        nbuf += 1
+        if k.endswith("num_batches_tracked"):
+            assert int(got) == int(ref), (k, int(got), int(ref))
+        else:
+            worst_buf = max(worst_buf, (float((got - ref).abs().max()) / max(float(ref.abs().max()), 1e-3), k))
+    assert nbuf > 0
     info = dict(native=native, loss=float(loss), ref_loss=float(g["loss"]), worst_norm=worst, worst_small_tensor=worst_full,
-                proj_err_over_gnorm=abs(proj - float(g["grad_proj"])) / gnorm)
+                proj_err_over_gnorm=abs(proj - float(g["grad_proj"])) / gnorm, worst_bn_buffer=worst_buf, bn_buffers=nbuf)
+    assert worst_buf[0] < 2e-2, info
     # measured: 0.8 % / 1.6 % (b = 3, stage-A tape) and 9.4 % / 7.3 % (b = 2, native; the worst tensors are OSAdapt's scale_routing, upstream of a
     # train-mode BatchNorm over a batch of TWO 1x1 maps whose output is +-1 whatever its input -- the ill-conditioned case named in _grad_report)
     assert worst[0] < 0.15 and worst_full[0] < 0.15, info
