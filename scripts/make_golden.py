@@ -193,9 +193,23 @@ def train_kat(outdir):
         np.savez_compressed(os.path.join(outdir, name + ".npz"), **rec)
 
 
+def window_kat(outdir):
+    """Row f2: the reference's generate_frame_indices (data_util.py:63-112, padding='reflection' as in every SAVSR test YAML) for every
+    frame of clips of 4..41 frames, 7- and 5-frame windows -- known answers for savsr_b200.sharding.frame_window_indices."""
+    from lbasicsr.data.data_util import generate_frame_indices
+    rec = {}
+    for nf in (7, 5):
+        for T in range(nf // 2 + 1, 42):
+            rec[f"nf{nf}.T{T}"] = np.array([generate_frame_indices(i, T, nf, padding="reflection") for i in range(T)], dtype=np.int64)
+    np.savez_compressed(os.path.join(outdir, "window_kat.npz"), **rec)
+    print(f"window KAT: {len(rec)} (window, clip length) tables from the reference's generate_frame_indices")
+
+
 def main():
-    if "--metrics-only" in sys.argv or "--lr-only" in sys.argv or "--train-only" in sys.argv:
+    if "--metrics-only" in sys.argv or "--lr-only" in sys.argv or "--train-only" in sys.argv or "--window-only" in sys.argv:
         load_reference()
+        if "--window-only" in sys.argv:
+            window_kat(os.path.join(ROOT, "tests", "golden"))
         if "--metrics-only" in sys.argv:
             metric_kat(os.path.join(ROOT, "tests", "golden"))
         if "--lr-only" in sys.argv:

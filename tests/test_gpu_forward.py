@@ -10,7 +10,7 @@ import torch
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-               if "fingerprint" not in p and "metrics" not in p and "lr_kat" not in p and not os.path.basename(p).startswith("train_"))
+               if "fingerprint" not in p and "metrics" not in p and "_kat" not in p and not os.path.basename(p).startswith("train_"))
 TRAIN_CASES = sorted(glob.glob(os.path.join(GOLDEN, "train_*.npz")))
 
 # Tolerances, straight from the north star:

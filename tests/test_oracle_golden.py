@@ -13,7 +13,7 @@ from oracle.state_dict_fixture import make_input, make_state_dict, state_dict_sp
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-               if "fingerprint" not in p and "metrics" not in p and "lr_kat" not in p and not os.path.basename(p).startswith("train_"))
+               if "fingerprint" not in p and "metrics" not in p and "_kat" not in p and not os.path.basename(p).startswith("train_"))
 TRAIN_CASES = sorted(glob.glob(os.path.join(GOLDEN, "train_*.npz")))
 
 

@@ -27,6 +27,19 @@ def test_reflection_window_indices():
         sharding.frame_window_indices(0, 3)                                         # reflection would index frame 3 of 3
 
 
+def test_window_indices_match_reference_kat():
+    """Known answers produced by the reference's own generate_frame_indices (scripts/make_golden.py --window-only): every frame of clips
+    of 4..41 frames (7-frame windows) and 3..41 frames (5-frame windows), reflection padding."""
+    import numpy as np
+    kat = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "window_kat.npz"))
+    assert len(kat.files) == 38 + 39
+    for key in kat.files:
+        nf, T = int(key.split(".")[0][2:]), int(key.split(".")[1][1:])
+        want = kat[key]
+        got = np.array([sharding.frame_window_indices(i, T, nf) for i in range(T)])
+        assert np.array_equal(got, want), key
+
+
 def test_shard_frames_partition():
     for n, world in ((34, 1), (34, 2), (34, 8), (5, 2), (3, 8), (0, 2)):
         for contiguous in (False, True):
