@@ -81,7 +81,9 @@ def workload_config(name, world):
     frames, h, w, scale = WORKLOADS[name]
     H, W = hw_out(h, w, scale)
     return {"workload": name, "frames_per_clip": frames, "clips": world, "lr": [h, w], "hr": [H, W], "scale": list(scale),
-            "weights": "random init (seed 0)", "parallelism": f"frame-sharded x{world}, no data-path collective"}
+            "weights": "random init (seed 0)", "parallelism": f"frame-sharded x{world}, no data-path collective",
+            # timing rule "flush L2 or use inputs larger than L2": the latter (GPU arm; the CPU arm carries the same text so the objects stay equal)
+            "l2": "no explicit flush: the per-step working set (16-bit activation arenas, several GB per clip) exceeds the 126 MB L2"}
 
 
 class ClockSampler(threading.Thread):
@@ -456,6 +458,7 @@ def run_train(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "bf16 conv operands, fp32 master weights / accumulation", "data": "synthetic",
             "config": {"workload": "train_cfg5", "per_gpu_batch": per_gpu, "global_batch": per_gpu * world, "lr_crop": [h, w], "frames": 7,
                        "scales": [list(s) for s in TRAIN_SCALES], "optimizer": "Adam 2e-4 (0.9, 0.99), Charbonnier, EMA 0.999",
+                       "l2": "no explicit flush: a step touches the plan's arenas (5.5 GB) and 300 MB of parameter / optimizer state, far beyond the 126 MB L2",
                        "parallelism": f"DistributedDataParallel x{world} (NCCL gradient all-reduce, 75.6 MB fp32)" if world > 1 else "single GPU"},
             "last_loss": round(loss, 5), "cuda_graph_per_scale": bool(graph), "engine": args.train_engine, "clocks": clocks,
             "e2e": {"value": round(per_gpu * world * args.steps / (ms_e2e / 1e3), 2), "unit": "samples/s", "ms_per_step": round(ms_e2e / args.steps, 2),
